@@ -1,0 +1,161 @@
+/*
+ * simulgen_b200.h - C ABI of the B200-native SimulGen-VAE hot-path engine (libsimulgen_b200.so).
+ *
+ * The reference (leesihun/SimulGen-VAE) is pure Python/PyTorch and defines no FFI of its own
+ * (SURVEY.md 2.1, 8b); the drop-in boundary is its nn.Module API (modules/VAE_network.py:60-121,
+ * encoder.py:116-167, decoder.py:106-223, common.py:15-162, losses.py:8-48).  The Python overlay in
+ * simulgen_vae_b200/overlay/modules keeps that API and calls the entry points below through ctypes;
+ * each one replaces the ATen/cuDNN/cuBLAS kernels the named reference lines launch implicitly.
+ *
+ * Conventions
+ *   - plain pointers and sizes only: no torch types.  All pointers are DEVICE pointers owned by the
+ *     caller (torch-allocated tensors); kernels never allocate or free (workspaces are passed in).
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - return value: 0 = ok, non-zero = error (sg_last_error() gives the text); the Python side raises
+ *     RuntimeError, the reference's only error convention (VAE_network.py:119-121).
+ *   - dtype: SG_BF16 (tcgen05 tensor-core path, bf16 operands + fp32 accumulation) or SG_F32
+ *     (fp32 validation mode, SIMT kernels, no tensor cores).
+ *   - internal activation layout "CR": [C][B][Tp] with Tp = roundup(T + 2, 8); entries t >= T of
+ *     every (c, b) row are zero (they are the conv "same" padding shared by neighbouring samples),
+ *     R = B * Tp.  External layout (reference): [B][C][T] fp32 (SimulGen-VAE.py:281-283).
+ *   - conv weights in GEMM layout "Wg": [k][Cout][Cin_p], Cin_p = roundup(Cin, 8), already divided
+ *     by the spectral norm sigma; ConvTranspose1d weights are stored as the equivalent Conv1d
+ *     (taps flipped, channels swapped; decoder.py:31).
+ */
+#ifndef SIMULGEN_B200_H_
+#define SIMULGEN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { SG_BF16 = 0, SG_F32 = 1 };
+enum { SG_ACT_NONE = 0, SG_ACT_GELU = 1, SG_ACT_TANH = 2 };
+enum { SG_LOSS_MSE = 0, SG_LOSS_MAE = 1, SG_LOSS_SMOOTHL1 = 2, SG_LOSS_HUBER = 3 };
+
+const char* sg_last_error(void);
+int sg_version(void);
+/* 1 if the tcgen05 path can run on the current device (sm_100), else 0. */
+int sg_device_supported(void);
+
+/* ---- layout ------------------------------------------------------------------------------- */
+/* x[B][N][T] fp32 -> out[N][B][Tp] (dtype), zero gap.  Replaces the implicit layout the reference
+ * feeds nn.Conv1d with (encoder.py:34, SimulGen-VAE.py:281-283). */
+int sg_pack_input(const float* x, void* out, int B, int N, int T, int Tp, int dtype, void* stream);
+/* out[B][C][T] fp32 <- in[C][B][Tp] fp32 (used for x_hat-style exports and tests). */
+int sg_unpack_f32(const float* in, float* out, int B, int C, int T, int Tp, void* stream);
+/* dst[i] (+)= alpha * src[i] (fp32), n elements. */
+int sg_axpy_f32(float* dst, const float* src, float alpha, long long n, int accumulate, void* stream);
+/* out(dtype)[i] = in(fp32)[i] */
+int sg_cast_f32(const float* in, void* out, long long n, int dtype, void* stream);
+
+/* ---- spectral norm (common.py:15-37 -> torch/nn/utils/spectral_norm.py:62-114) --------------
+ * W_mat[o][q], q = i*k + j, is addressed inside w_orig as o*so + i*si + j
+ * (Conv1d/Linear: so = Cin*k, si = k; ConvTranspose1d (dim=1): so = k, si = Cout*k).
+ * training != 0: v <- normalize(W^T u), u <- normalize(W v) in place, sigma = u . (W v)
+ * training == 0: sigma = u . (W v) with the stored vectors.  ws: >= (H + Wd + 4) floats. */
+int sg_sn_power_iter(const float* w_orig, float* u, float* v, float* sigma, float* ws,
+                     int H, int Cin, int k, long long so, long long si, int training, void* stream);
+/* Wg[j'][o][i] = w(o,i,j) / sigma   (j' = j, or k-1-j if flip) ; rows padded to Cin_p with zeros. */
+int sg_sn_pack_weight(const float* w_orig, const float* sigma, void* wg, int Cout, int Cin, int Cin_p, int k,
+                      long long so, long long si, int flip, int dtype, void* stream);
+/* Backward of W_n = W / sigma(W) with u, v constant (spectral_norm.py:97-113):
+ *   dW = (G - <G, W_n> * u v^T) / sigma, where G = dWg (fp32, GEMM layout) and <G,W_n> = <G,W>/sigma.
+ * ws: >= 2 doubles.  Writes grad in the w_orig layout (accumulate=0) . */
+int sg_sn_weight_grad(const float* dwg, const float* w_orig, const float* u, const float* v, const float* sigma,
+                      float* grad, double* ws, int Cout, int Cin, int Cin_p, int k, long long so, long long si,
+                      int flip, void* stream);
+
+/* ---- convolutions as implicit GEMM (encoder.py:34,43; common.py:84,110,135-141;
+ *      decoder.py:31,118,135,145,155,164 and their autograd backward, train.py:153) --------------
+ * fprop: out[Cout][R] (fp32) (+)= sum_{j,ci} Wg[j][co][ci] * act[ci][r + j - k/2] + bias[co]
+ * dgrad: dx [Cin][R]  (fp32) (+)= sum_{j,co} Wg[j][co][ci] * dy[co][r - j + k/2]
+ * wgrad: dWg[j][Cout][Cin_p] (fp32) = sum_r dy[co][r] * act[ci][r + j - k/2]
+ * act / dy / Wg are `dtype` (bf16: tcgen05 + TMA kernels; fp32: SIMT validation kernels).
+ * R % 8 == 0 and Cin_p % 8 == 0 are required (TMA global strides are multiples of 16 bytes).  */
+int sg_conv_fprop(const void* wg, const void* act, const float* bias, float* out, int Cin, int Cin_p, int Cout,
+                  int k, int R, int accumulate, int dtype, void* stream);
+int sg_conv_dgrad(const void* wg, const void* dy, float* dx, int Cin, int Cin_p, int Cout, int k, int R,
+                  int accumulate, int dtype, void* stream);
+int sg_conv_wgrad(const void* dy, const void* act, float* dwg, int Cin, int Cin_p, int Cout, int k, int R,
+                  int dtype, void* stream);
+
+/* ---- GroupNorm + activation + residual (encoder.py:35-36, common.py:85-102, decoder.py:32,119-120)
+ * stats[B][G][2] doubles = (sum, sum of squares) over the group's (C/G) x T valid entries. */
+int sg_gn_stats(const float* y, double* stats, int C, int B, int T, int Tp, int G, void* stream);
+/* pre = res + res_scale * act(gamma * (y - mean) * rstd + beta)   (stats == NULL: no norm, y used as is)
+ * out = post_gelu ? gelu(pre) : pre ; written as operand (out_op, dtype, gap zeroed) and/or fp32. */
+int sg_gn_act_fwd(const float* y, const double* stats, const float* gamma, const float* beta,
+                  const void* res, int res_is_f32, float res_scale, int act, int post_gelu,
+                  void* out_op, float* out_f32, int C, int B, int T, int Tp, int G, int dtype, void* stream);
+/* Backward of the above.  dout fp32 [C][B][Tp].  Writes dy (dtype, gap zeroed) = grad wrt y,
+ * dgamma/dbeta (may be NULL when stats == NULL), dbias[C] = sum_{b,t} dy, and dres (fp32,
+ * (+)= per dres_accumulate) when res != NULL.  ws: >= 2*B*G doubles. */
+int sg_gn_act_bwd(const float* y, const double* stats, const float* gamma, const float* beta,
+                  const void* res, int res_is_f32, float res_scale, int act, int post_gelu,
+                  const float* dout, void* dy, float* dgamma, float* dbeta, float* dbias,
+                  float* dres, int dres_accumulate, double* ws,
+                  int C, int B, int T, int Tp, int G, int dtype, void* stream);
+
+/* ---- reconstruction head: Tanh(GroupNorm(y)) + losses (decoder.py:117-121, VAE_network.py:71-77,110-111)
+ * y fp32 [N][B][Tp]; x, x_hat fp32 [B][N][T] (either may be NULL).  loss_sums[2] doubles (zeroed inside):
+ * sum of the selected loss terms and sum of squared errors. */
+int sg_recon_fwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* x,
+                 float* x_hat, double* loss_sums, int N, int B, int T, int Tp, int G, int loss_kind, void* stream);
+/* dx_hat = g_loss[0]*inv_numel*loss'(x_hat-x) + g_mse[0]*inv_numel*2(x_hat-x) + dxhat_ext (each optional),
+ * then backward through tanh and GroupNorm -> dy (dtype) , dgamma, dbeta, dbias.  ws: >= 2*B*G doubles. */
+int sg_recon_bwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* x,
+                 const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext,
+                 void* dy, float* dgamma, float* dbeta, float* dbias, double* ws,
+                 int N, int B, int T, int Tp, int G, int loss_kind, int dtype, void* stream);
+/* out[i] = (float)(in[i] * scale), n small. */
+int sg_scale_f64_to_f32(const double* in, float* out, double scale, int n, void* stream);
+
+/* ---- linear heads (encoder.py:138-142,158-165; decoder.py:133,143) --------------------------
+ * head: out[b][o] = (sum_{c,t} w_orig[o][c*T+t] * h[c][b][t]) / sigma + bias[o];  h fp32 [C][B][Tp]. */
+int sg_head_fwd(const float* h, const float* w_orig, const float* sigma, const float* bias, float* out,
+                int C, int B, int T, int Tp, int O, void* stream);
+/* dwn[o][c*T+t] = sum_b dout[b][o] h[c][b][t] (grad wrt the normalised weight), dbias[o] = sum_b dout[b][o],
+ * dh[c][b][t] (+)= sum_o w_orig[o][c*T+t]/sigma * dout[b][o]. */
+int sg_head_bwd(const float* h, const float* w_orig, const float* sigma, const float* dout, float* dwn,
+                float* dbias, float* dh, int dh_accumulate, int C, int B, int T, int Tp, int O, void* stream);
+/* latent: out[d][b][t] = (sum_e w_orig[d*T+t][e] * z[b][e]) / sigma + bias[d*T+t]   (Linear + Unflatten) */
+int sg_latent_fwd(const float* z, const float* w_orig, const float* sigma, const float* bias, void* out,
+                  int D, int B, int T, int Tp, int dtype, void* stream);
+int sg_latent_bwd(const float* z, const float* w_orig, const float* sigma, const float* dact, float* dwn,
+                  float* dbias, float* dz, int D, int B, int T, int Tp, void* stream);
+
+/* ---- reparameterisation + KL (decoder.py:187-212,218-223; losses.py:8-48; VAE_network.py:103-105,113)
+ * main latent: last[B][2L] = (mu | log_var); z = mu + eps * clamp(exp(.5 clamp(lv)),1e-8,10);
+ * kl_out[0] = mean_b(.5 sum_d(mu^2 + e^lv - lv - 1)). */
+int sg_reparam_main_fwd(const float* last, const float* eps, float* z, float* kl_out, int B, int L, void* stream);
+int sg_reparam_main_bwd(const float* last, const float* eps, const float* dz, const float* dkl, float* dlast,
+                        int B, int L, void* stream);
+/* hierarchical level: cz, cxz fp32 [2C][B][Tp] = (mu | lv), (dmu | dlv); eps fp32 [B][C][T];
+ * z = (mu+dmu) + eps*clamp(std_scale*exp(.5 clamp(lv+dlv)),1e-8,10); zs = h + z (h fp32 [C][B][Tp]);
+ * kl_sum[0] (double, zeroed inside) = sum of the kl_2 integrand (caller scales by .5/B). */
+int sg_kl2_reparam_fwd(const float* cz, const float* cxz, const float* eps, const float* h, float std_scale,
+                       void* zs_op, float* zs_f32, double* kl_sum, int C, int B, int T, int Tp, int dtype,
+                       void* stream);
+/* dzs fp32 [C][B][Tp] (or NULL); dkl = d/d(kl_2 value) (device scalar or NULL), kl_scale = .5/B;
+ * writes dcz, dcxz fp32 [2C][B][Tp] (gap zeroed) = gradients wrt the two condition-conv outputs. */
+int sg_kl2_reparam_bwd(const float* cz, const float* cxz, const float* eps, float std_scale, const float* dzs,
+                       const float* dkl, float kl_scale, float* dcz, float* dcxz, int C, int B, int T, int Tp,
+                       void* stream);
+
+/* ---- counter-based RNG (replaces torch.randn_like, decoder.py:221) ----------------------------
+ * out[b][i] ~ N(0,1), keyed on (seed, stream_id, sample0 + b, i): identical for any batch split. */
+int sg_philox_normal(float* out, int B, long long per_sample, unsigned long long seed,
+                     unsigned long long stream_id, long long sample0, void* stream);
+
+/* ---- optimiser (train.py:92,156-168: AdamW defaults + global grad L2 norm) ----------------------
+ * One launch over a flat fp32 parameter arena.  gnorm_sq (double, (+)=) receives sum g^2. */
+int sg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, float grad_scale, double* gnorm_sq, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMULGEN_B200_H_ */

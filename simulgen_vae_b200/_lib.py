@@ -1,0 +1,84 @@
+"""ctypes binding of libsimulgen_b200.so (the C ABI declared in include/simulgen_b200.h).
+
+There is no CPU fallback: if the shared library is missing or fails to load, every kernel call
+raises RuntimeError.  Build it with `python -c "import __graft_entry__ as g; g.build()"` or
+`python -m simulgen_vae_b200.build`.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsimulgen_b200.so")
+
+_lib = None
+_err = None
+
+c_void_p, c_int, c_float, c_double = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double
+c_ll, c_ull = ctypes.c_longlong, ctypes.c_ulonglong
+
+P, I, F, D, L, U = c_void_p, c_int, c_float, c_double, c_ll, c_ull
+
+# name -> argtypes, in the order of include/simulgen_b200.h
+SIGNATURES = {
+    "sg_pack_input": [P, P, I, I, I, I, I, P],
+    "sg_unpack_f32": [P, P, I, I, I, I, P],
+    "sg_axpy_f32": [P, P, F, L, I, P],
+    "sg_cast_f32": [P, P, L, I, P],
+    "sg_sn_power_iter": [P, P, P, P, P, I, I, I, L, L, I, P],
+    "sg_sn_pack_weight": [P, P, P, I, I, I, I, L, L, I, I, P],
+    "sg_sn_weight_grad": [P, P, P, P, P, P, P, I, I, I, I, L, L, I, P],
+    "sg_conv_fprop": [P, P, P, P, I, I, I, I, I, I, I, P],
+    "sg_conv_dgrad": [P, P, P, I, I, I, I, I, I, I, P],
+    "sg_conv_wgrad": [P, P, P, I, I, I, I, I, I, P],
+    "sg_gn_stats": [P, P, I, I, I, I, I, P],
+    "sg_gn_act_fwd": [P, P, P, P, P, I, F, I, I, P, P, I, I, I, I, I, I, P],
+    "sg_gn_act_bwd": [P, P, P, P, P, I, F, I, I, P, P, P, P, P, P, I, P, I, I, I, I, I, I, P],
+    "sg_recon_fwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, P],
+    "sg_recon_bwd": [P, P, P, P, P, P, P, F, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
+    "sg_scale_f64_to_f32": [P, P, D, I, P],
+    "sg_head_fwd": [P, P, P, P, P, I, I, I, I, I, P],
+    "sg_head_bwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, P],
+    "sg_latent_fwd": [P, P, P, P, P, I, I, I, I, I, P],
+    "sg_latent_bwd": [P, P, P, P, P, P, P, I, I, I, I, P],
+    "sg_reparam_main_fwd": [P, P, P, P, I, I, P],
+    "sg_reparam_main_bwd": [P, P, P, P, P, I, I, P],
+    "sg_kl2_reparam_fwd": [P, P, P, P, F, P, P, P, I, I, I, I, I, P],
+    "sg_kl2_reparam_bwd": [P, P, P, F, P, P, F, P, P, I, I, I, I, P],
+    "sg_philox_normal": [P, I, L, U, U, L, P],
+    "sg_adamw_step": [P, P, P, P, L, F, F, F, F, F, I, F, P, P],
+}
+
+
+def load():
+    """Load the shared library once; raises RuntimeError (never falls back) when unavailable."""
+    global _lib, _err
+    if _lib is not None:
+        return _lib
+    if _err is not None:
+        raise RuntimeError(_err)
+    if not os.path.isfile(LIB_PATH):
+        _err = ("simulgen_b200: %s not found - build the CUDA extension first "
+                "(python -m simulgen_vae_b200.build); there is no CPU fallback" % LIB_PATH)
+        raise RuntimeError(_err)
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        _err = "simulgen_b200: cannot load %s: %s" % (LIB_PATH, e)
+        raise RuntimeError(_err)
+    lib.sg_last_error.restype = ctypes.c_char_p
+    lib.sg_last_error.argtypes = []
+    lib.sg_version.restype = c_int
+    lib.sg_device_supported.restype = c_int
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError("simulgen_b200 %s failed (%d): %s" % (name, rc, lib.sg_last_error().decode()))

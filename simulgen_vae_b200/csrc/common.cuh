@@ -1,0 +1,134 @@
+// Shared device helpers for the simulgen_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/simulgen_b200.h"
+
+namespace sg {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define SG_REQUIRE(cond, ...)                 \
+    do {                                      \
+        if (!(cond)) {                        \
+            sg::set_error(__VA_ARGS__);       \
+            return 1;                         \
+        }                                     \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+constexpr float kGnEps = 1e-5f;
+
+// ---------------------------------------------------------------------------------------------
+// 8-element vector access for fp32 / bf16 rows (rows are 8-element aligned: Tp % 8 == 0)
+// ---------------------------------------------------------------------------------------------
+struct F8 {
+    float v[8];
+};
+
+__device__ __forceinline__ F8 load8(const float* p) {
+    F8 r;
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ F8 load8(const __nv_bfloat16* p) {
+    F8 r;
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        r.v[2 * i] = f.x;
+        r.v[2 * i + 1] = f.y;
+    }
+    return r;
+}
+__device__ __forceinline__ void store8(float* p, const F8& r) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const F8& r) {
+    uint4 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = raw;
+}
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ void from_f(float& d, float x) { d = x; }
+__device__ __forceinline__ void from_f(__nv_bfloat16& d, float x) { d = __float2bfloat16_rn(x); }
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum of a double; result valid in thread 0.  `sh` must hold >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        r = lane < nw ? sh[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// activations (exact erf GELU = nn.GELU() default; nn.Tanh)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+    const float kInvSqrt2Pi = 0.39894228040143267794f;
+    float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    return cdf + x * kInvSqrt2Pi * expf(-0.5f * x * x);
+}
+__device__ __forceinline__ float act_f(int act, float x) {
+    return act == SG_ACT_GELU ? gelu_f(x) : (act == SG_ACT_TANH ? tanhf(x) : x);
+}
+// derivative of act at pre-activation x
+__device__ __forceinline__ float act_grad_f(int act, float x) {
+    if (act == SG_ACT_GELU) return gelu_grad_f(x);
+    if (act == SG_ACT_TANH) {
+        float t = tanhf(x);
+        return 1.0f - t * t;
+    }
+    return 1.0f;
+}
+
+struct GnStat {
+    float mean, rstd;
+};
+__device__ __forceinline__ GnStat gn_stat(const double* stats, int b, int g, int G, double inv_n) {
+    double s = stats[(size_t)(b * G + g) * 2], ss = stats[(size_t)(b * G + g) * 2 + 1];
+    double m = s * inv_n;
+    double var = ss * inv_n - m * m;
+    if (var < 0.0) var = 0.0;
+    GnStat r;
+    r.mean = (float)m;
+    r.rstd = (float)(1.0 / sqrt(var + (double)kGnEps));
+    return r;
+}
+
+}  // namespace sg

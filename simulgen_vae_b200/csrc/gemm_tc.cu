@@ -1,0 +1,507 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernels for the stride-1 "same" Conv1d family (sm_100a).
+//
+// Replaces cuDNN fprop / dgrad / wgrad behind nn.Conv1d / nn.ConvTranspose1d in
+// encoder.py:34,43, common.py:84,110,135-141, decoder.py:31,118,135,145,155,164 and their autograd
+// backward (train.py:153).  Activations are in the CR layout [C][B*Tp] (r contiguous, zero gap
+// between samples = the conv padding), weights in the GEMM layout Wg[k][Cout][Cin_p].
+//
+//   fprop  D[co][r]      = sum_{j,ci} Wg[j][co][ci] * act[ci][r + j - pad]   A: K-major,  B: MN-major
+//   dgrad  D[ci][r]      = sum_{j,co} Wg[j][co][ci] * dy [co][r - j + pad]   A: MN-major, B: MN-major
+//   wgrad  D[j][co][ci]  = sum_r      dy[co][r]     * act[ci][r + j - pad]   A: K-major,  B: K-major
+//
+// One persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+ TMEM
+// alloc), warps 2-5 = epilogue (TMEM -> registers -> global).  Tile 128 x 256 x 64, 4 smem stages
+// (48 KB each, 128B-swizzled TMA boxes of 64 x 64 bf16), two 256-column fp32 accumulators in TMEM
+// so the epilogue of tile i overlaps the main loop of tile i+1.  Conv taps are K-blocks whose TMA
+// coordinates are shifted along r; out-of-bounds box elements are zero-filled by TMA, which is the
+// zero padding of the convolution and the ragged-edge handling in one mechanism.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace sg {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int BOX_BYTES = 64 * 64 * 2;              // one 64 x 64 bf16 TMA box
+constexpr int A_BYTES = BM * BK * 2;                // 16 KB  (2 boxes)
+constexpr int B_BYTES = BN * BK * 2;                // 32 KB  (4 boxes)
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 48 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+enum { MODE_FPROP = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
+
+struct TcParams {
+    float* out;
+    const float* bias;
+    int M, N;            // output tile space (rows, cols); N is a multiple of 8
+    long long ldc;       // row pitch of out
+    long long c_sz;      // wgrad: output stride per tap
+    int m_tiles, n_tiles, z_count, splits;
+    int taps;            // taps looped inside the K loop (fprop/dgrad: k, wgrad: 1)
+    int kblocks;         // K blocks of 64 per tap
+    int pad;
+    int accumulate;      // out += result
+    int atomic;          // split-K: red.add into out
+    int m_fastest;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) {
+            printf("simulgen_b200: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// smem matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=2 [61,64)).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct Work {
+    int m0, n0, z, it_lo, it_hi, split;
+};
+
+__device__ __forceinline__ Work decode_work(const TcParams& p, int w, int total_iters) {
+    Work r;
+    int tiles = p.m_tiles * p.n_tiles;
+    int t = w % tiles;
+    int rest = w / tiles;
+    r.z = rest % p.z_count;
+    r.split = rest / p.z_count;
+    int mt, nt;
+    if (p.m_fastest) { mt = t % p.m_tiles; nt = t / p.m_tiles; } else { nt = t % p.n_tiles; mt = t / p.n_tiles; }
+    r.m0 = mt * BM;
+    r.n0 = nt * BN;
+    int per = (total_iters + p.splits - 1) / p.splits;
+    r.it_lo = r.split * per;
+    r.it_hi = min(total_iters, r.it_lo + per);
+    return r;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;                    // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr bool A_MN = (MODE == MODE_DGRAD);
+    constexpr bool B_MN = (MODE != MODE_WGRAD);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_iters = p.taps * p.kblocks;
+    const int num_work = p.m_tiles * p.n_tiles * p.z_count * p.splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+                Work wk = decode_work(p, w, total_iters);
+                for (int it = wk.it_lo; it < wk.it_hi; ++it) {
+                    int kb = it / p.taps, j = it - kb * p.taps;   // taps innermost: shifted reloads hit L2
+                    int k0 = kb * BK;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    if (MODE == MODE_FPROP) {
+                        tma_load_3d(&tmA, &full_bar[stage], sa, k0, wk.m0, j);
+                        tma_load_3d(&tmA, &full_bar[stage], sa + BOX_BYTES, k0, wk.m0 + 64, j);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            tma_load_2d(&tmB, &full_bar[stage], sb + i * BOX_BYTES, wk.n0 + 64 * i + j - p.pad, k0);
+                    } else if (MODE == MODE_DGRAD) {
+                        tma_load_3d(&tmA, &full_bar[stage], sa, wk.m0, k0, j);
+                        tma_load_3d(&tmA, &full_bar[stage], sa + BOX_BYTES, wk.m0 + 64, k0, j);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            tma_load_2d(&tmB, &full_bar[stage], sb + i * BOX_BYTES, wk.n0 + 64 * i - j + p.pad, k0);
+                    } else {
+                        tma_load_2d(&tmA, &full_bar[stage], sa, k0, wk.m0);
+                        tma_load_2d(&tmA, &full_bar[stage], sa + BOX_BYTES, k0, wk.m0 + 64);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            tma_load_2d(&tmB, &full_bar[stage], sb + i * BOX_BYTES, k0 + wk.z - p.pad, wk.n0 + 64 * i);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, M=128, N=256, majors per mode
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                   ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int tile_iter = 0;
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_iter) {
+                Work wk = decode_work(p, w, total_iters);
+                int as = tile_iter & 1;
+                uint32_t aphase = (tile_iter >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tcgen05_fence_after();
+                uint32_t tmem_d = tmem_base + as * BN;
+                for (int it = wk.it_lo; it < wk.it_hi; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    uint32_t sb = sa + A_BYTES;
+                    // K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); +32 B per UMMA_K=16
+                    // MN-major: 64-element atoms 8192 B apart (LBO = one box), 8-k groups 1024 B apart (SBO);
+                    //           +2048 B per UMMA_K=16
+                    uint64_t da = A_MN ? make_desc(sa, BOX_BYTES, 1024) : make_desc(sa, 16, 1024);
+                    uint64_t db = B_MN ? make_desc(sb, BOX_BYTES, 1024) : make_desc(sb, 16, 1024);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        uint64_t a = da + (uint64_t)((A_MN ? 2048 : 32) * kk >> 4);
+                        uint64_t b = db + (uint64_t)((B_MN ? 2048 : 32) * kk >> 4);
+                        tcgen05_mma_bf16(tmem_d, a, b, idesc, (it > wk.it_lo || kk > 0) ? 1u : 0u);
+                    }
+                    tcgen05_commit(&empty_bar[stage]);      // frees the smem slot when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(&tfull_bar[as]);             // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                              // TMEM lane quarter this warp may access
+        int tile_iter = 0;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_iter) {
+            Work wk = decode_work(p, w, total_iters);
+            int as = tile_iter & 1;
+            uint32_t aphase = (tile_iter >> 1) & 1;
+            mbar_wait(&tfull_bar[as], aphase);
+            tcgen05_fence_after();
+            const int m = wk.m0 + q * 32 + lane;
+            const bool m_ok = m < p.M;
+            float bias = 0.f;
+            if (p.bias != nullptr && m_ok && wk.split == 0) bias = p.bias[m];
+            float* orow = p.out + (long long)wk.z * p.c_sz + (long long)(m_ok ? m : 0) * p.ldc;
+            const bool have_k = wk.it_hi > wk.it_lo;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32);
+                tmem_ld_32x32b_x32(taddr, v);
+                tmem_ld_wait();
+                int n = wk.n0 + c * 32;
+                if (m_ok && have_k) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) {
+                        if (n + e < p.N) {
+                            float4 r = make_float4(__uint_as_float(v[e]) + bias, __uint_as_float(v[e + 1]) + bias,
+                                                   __uint_as_float(v[e + 2]) + bias, __uint_as_float(v[e + 3]) + bias);
+                            float* dst = orow + n + e;
+                            if (p.atomic) {
+                                atomicAdd(dst, r.x); atomicAdd(dst + 1, r.y); atomicAdd(dst + 2, r.z); atomicAdd(dst + 3, r.w);
+                            } else {
+                                if (p.accumulate) {
+                                    float4 o = *reinterpret_cast<const float4*>(dst);
+                                    r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+                                }
+                                *reinterpret_cast<float4*>(dst) = r;
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    return fn;
+}
+
+// 2-D bf16 [rows][cols] (cols contiguous), box 64 x 64, 128B swizzle, zero OOB fill
+static int make_map_2d(CUtensorMap* m, const void* base, long long cols, long long rows, long long pitch_elems) {
+    EncodeTiledFn fn = get_encode_fn();
+    SG_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d) failed: %d (cols=%lld rows=%lld pitch=%lld base=%p)", (int)r,
+               cols, rows, pitch_elems, base);
+    return 0;
+}
+
+// 3-D bf16 Wg[k][Cout][Cin_p], box 64 x 64 x 1
+static int make_map_wg(CUtensorMap* m, const void* base, int Cin_p, int Cout, int k) {
+    EncodeTiledFn fn = get_encode_fn();
+    SG_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)Cout, (cuuint64_t)k};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin_p * 2, (cuuint64_t)Cin_p * Cout * 2};
+    cuuint32_t box[3] = {64, 64, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed: %d (Cin_p=%d Cout=%d k=%d base=%p)", (int)r, Cin_p,
+               Cout, k, base);
+    return 0;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+static int pick_splits(int tiles, int iters) {
+    int sms = num_sms();
+    if (tiles >= sms || iters < 64) return 1;
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= 16; ++s) {
+        if (iters / s < 32) break;
+        double waves = (double)tiles * s / sms;
+        double eff = waves / ceil(waves);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+        if (eff >= 0.93) break;
+    }
+    return best;
+}
+
+template <int MODE>
+static int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        SG_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d) failed: %s", SMEM_BYTES, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    int work = p.m_tiles * p.n_tiles * p.z_count * p.splits;
+    int grid = work < num_sms() ? work : num_sms();
+    conv_gemm_tc_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, b, p);
+    return check_launch("conv_gemm_tc");
+}
+
+int tc_fprop(const void* wg, const void* act, const float* bias, float* out, int Cin, int Cin_p, int Cout, int k, int R,
+             int accumulate, cudaStream_t st) {
+    CUtensorMap ma, mb;
+    if (make_map_wg(&ma, wg, Cin_p, Cout, k)) return 1;
+    if (make_map_2d(&mb, act, R, Cin, R)) return 1;
+    TcParams p{};
+    p.out = out; p.bias = bias; p.M = Cout; p.N = R; p.ldc = R; p.c_sz = 0;
+    p.m_tiles = (int)cdiv(Cout, BM); p.n_tiles = (int)cdiv(R, BN); p.z_count = 1;
+    p.taps = k; p.kblocks = (int)cdiv(Cin, BK); p.pad = k / 2; p.accumulate = accumulate;
+    p.splits = pick_splits(p.m_tiles * p.n_tiles, p.taps * p.kblocks);
+    p.atomic = p.splits > 1;
+    p.m_fastest = p.m_tiles <= p.n_tiles;
+    if (p.atomic && !accumulate) cudaMemsetAsync(out, 0, sizeof(float) * (size_t)Cout * R, st);
+    return launch_tc<MODE_FPROP>(ma, mb, p, st);
+}
+
+int tc_dgrad(const void* wg, const void* dy, float* dx, int Cin, int Cin_p, int Cout, int k, int R, int accumulate,
+             cudaStream_t st) {
+    CUtensorMap ma, mb;
+    if (make_map_wg(&ma, wg, Cin_p, Cout, k)) return 1;
+    if (make_map_2d(&mb, dy, R, Cout, R)) return 1;
+    TcParams p{};
+    p.out = dx; p.bias = nullptr; p.M = Cin; p.N = R; p.ldc = R; p.c_sz = 0;
+    p.m_tiles = (int)cdiv(Cin, BM); p.n_tiles = (int)cdiv(R, BN); p.z_count = 1;
+    p.taps = k; p.kblocks = (int)cdiv(Cout, BK); p.pad = k / 2; p.accumulate = accumulate;
+    p.splits = pick_splits(p.m_tiles * p.n_tiles, p.taps * p.kblocks);
+    p.atomic = p.splits > 1;
+    p.m_fastest = p.m_tiles <= p.n_tiles;
+    if (p.atomic && !accumulate) cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)Cin * R, st);
+    return launch_tc<MODE_DGRAD>(ma, mb, p, st);
+}
+
+int tc_wgrad(const void* dy, const void* act, float* dwg, int Cin, int Cin_p, int Cout, int k, int R, cudaStream_t st) {
+    CUtensorMap ma, mb;
+    if (make_map_2d(&ma, dy, R, Cout, R)) return 1;
+    if (make_map_2d(&mb, act, R, Cin, R)) return 1;
+    TcParams p{};
+    p.out = dwg; p.bias = nullptr; p.M = Cout; p.N = Cin_p; p.ldc = Cin_p; p.c_sz = (long long)Cout * Cin_p;
+    p.m_tiles = (int)cdiv(Cout, BM); p.n_tiles = (int)cdiv(Cin_p, BN); p.z_count = k;
+    p.taps = 1; p.kblocks = (int)cdiv(R, BK); p.pad = k / 2; p.accumulate = 0;
+    p.splits = pick_splits(p.m_tiles * p.n_tiles * k, p.kblocks);
+    p.atomic = p.splits > 1;
+    p.m_fastest = p.m_tiles <= p.n_tiles;
+    if (p.atomic) cudaMemsetAsync(dwg, 0, sizeof(float) * (size_t)k * Cout * Cin_p, st);
+    return launch_tc<MODE_WGRAD>(ma, mb, p, st);
+}
+
+// fp32 validation path (gemm_simt.cu)
+int simt_fprop(const float*, const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
+int simt_dgrad(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
+int simt_wgrad(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+
+int sg_conv_fprop(const void* wg, const void* act, const float* bias, float* out, int Cin, int Cin_p, int Cout, int k,
+                  int R, int accumulate, int dtype, void* stream) {
+    SG_REQUIRE(R % 8 == 0 && Cin_p % 8 == 0 && Cin_p >= Cin && (k & 1), "conv_fprop: bad shape Cin=%d Cin_p=%d k=%d R=%d", Cin, Cin_p, k, R);
+    if (dtype == SG_F32)
+        return simt_fprop((const float*)wg, (const float*)act, bias, out, Cin, Cin_p, Cout, k, R, accumulate, as_stream(stream));
+    return tc_fprop(wg, act, bias, out, Cin, Cin_p, Cout, k, R, accumulate, as_stream(stream));
+}
+
+int sg_conv_dgrad(const void* wg, const void* dy, float* dx, int Cin, int Cin_p, int Cout, int k, int R, int accumulate,
+                  int dtype, void* stream) {
+    SG_REQUIRE(R % 8 == 0 && Cin_p % 8 == 0 && Cin_p >= Cin && (k & 1), "conv_dgrad: bad shape Cin=%d Cin_p=%d k=%d R=%d", Cin, Cin_p, k, R);
+    if (dtype == SG_F32)
+        return simt_dgrad((const float*)wg, (const float*)dy, dx, Cin, Cin_p, Cout, k, R, accumulate, as_stream(stream));
+    return tc_dgrad(wg, dy, dx, Cin, Cin_p, Cout, k, R, accumulate, as_stream(stream));
+}
+
+int sg_conv_wgrad(const void* dy, const void* act, float* dwg, int Cin, int Cin_p, int Cout, int k, int R, int dtype,
+                  void* stream) {
+    SG_REQUIRE(R % 8 == 0 && Cin_p % 8 == 0 && Cin_p >= Cin && (k & 1), "conv_wgrad: bad shape Cin=%d Cin_p=%d k=%d R=%d", Cin, Cin_p, k, R);
+    if (dtype == SG_F32)
+        return simt_wgrad((const float*)dy, (const float*)act, dwg, Cin, Cin_p, Cout, k, R, as_stream(stream));
+    return tc_wgrad(dy, act, dwg, Cin, Cin_p, Cout, k, R, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,577 @@
+// HBM-streaming kernels: layout packing, GroupNorm statistics / apply / backward, activation,
+// residual, and the reconstruction head (tanh + fused loss reductions).
+//
+// Reference arithmetic replaced (all fp32 ATen kernels there):
+//   encoder.py:35-36, common.py:85-102,108-125,133-162 (GroupNorm -> GELU -> x + 0.1 f(x)),
+//   decoder.py:32 (GELU after ConvTranspose1d), decoder.py:117-121 (GroupNorm -> Tanh),
+//   VAE_network.py:71-77,110-111 (MSE / L1 / SmoothL1 / Huber, mean reduction) and their backward.
+//
+// Every kernel is "one warp per (channel, sample) row": a row is Tp contiguous elements of which the
+// first T are valid; each lane owns 8-element (16/32-byte) segments, so global accesses are
+// coalesced 128-bit transactions; reductions use warp shuffles + one atomic per warp.
+#include "common.cuh"
+
+namespace sg {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+
+// ---------------------------------------------------------------------------------------------
+// layout kernels
+// ---------------------------------------------------------------------------------------------
+template <typename OT>
+__global__ void __launch_bounds__(kThreads) pack_input_kernel(const float* __restrict__ x, OT* __restrict__ out,
+                                                              int B, int N, int T, int Tp) {
+    long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);  // row = n * B + b
+    if (row >= (long long)N * B) return;
+    int lane = threadIdx.x & 31;
+    int n = (int)(row / B), b = (int)(row % B);
+    const float* src = x + ((long long)b * N + n) * T;
+    OT* dst = out + row * Tp;
+    for (int seg = lane; seg < Tp / 8; seg += 32) {
+        F8 r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int t = seg * 8 + i;
+            r.v[i] = t < T ? __ldg(src + t) : 0.0f;
+        }
+        store8(dst + seg * 8, r);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) unpack_f32_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                              int B, int C, int T, int Tp) {
+    long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);  // row = c * B + b
+    if (row >= (long long)C * B) return;
+    int lane = threadIdx.x & 31;
+    int c = (int)(row / B), b = (int)(row % B);
+    const float* src = in + row * Tp;
+    float* dst = out + ((long long)b * C + c) * T;
+    for (int t = lane; t < T; t += 32) dst[t] = src[t];
+}
+
+__global__ void axpy_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, float alpha, long long n,
+                                int accumulate) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = accumulate ? dst[i] + alpha * src[i] : alpha * src[i];
+}
+
+template <typename OT>
+__global__ void cast_f32_kernel(const float* __restrict__ in, OT* __restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) from_f(out[i], in[i]);
+}
+
+__global__ void scale_f64_to_f32_kernel(const double* in, float* out, double scale, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)(in[i] * scale);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm statistics: stats[b][g] += (sum, sumsq) over the group's rows
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restrict__ y, double* __restrict__ stats,
+                                                            int C, int B, int T, int Tp, int G, int rows_per_block) {
+    // grid: (chunks per group, G, B)
+    __shared__ double sh[2][32];
+    int g = blockIdx.y, b = blockIdx.z;
+    int Cg = C / G;
+    int c_lo = g * Cg + blockIdx.x * rows_per_block;
+    int c_hi = min(c_lo + rows_per_block, (g + 1) * Cg);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float s = 0.f, ss = 0.f;
+    double ds = 0.0, dss = 0.0;
+    for (int c = c_lo + warp; c < c_hi; c += kWarpsPerBlock) {
+        const float* row = y + ((long long)c * B + b) * Tp;
+        for (int seg = lane; seg < Tp / 8; seg += 32) {
+            F8 r = load8(row + seg * 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (seg * 8 + i < T) {
+                    s += r.v[i];
+                    ss += r.v[i] * r.v[i];
+                }
+            }
+        }
+        ds += (double)s;   // flush the fp32 partials per row to limit round-off growth
+        dss += (double)ss;
+        s = 0.f;
+        ss = 0.f;
+    }
+    double t0 = block_sum(ds, sh[0]);
+    double t1 = block_sum(dss, sh[1]);
+    if (threadIdx.x == 0) {
+        atomicAdd(&stats[(size_t)(b * G + g) * 2], t0);
+        atomicAdd(&stats[(size_t)(b * G + g) * 2 + 1], t1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward apply
+// ---------------------------------------------------------------------------------------------
+template <typename OT, typename RT>
+__global__ void __launch_bounds__(kThreads)
+gn_act_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, const RT* __restrict__ res, float res_scale, int act, int post_gelu,
+                  OT* __restrict__ out_op, float* __restrict__ out_f32, int C, int B, int T, int Tp, int G,
+                  double inv_n) {
+    long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row >= (long long)C * B) return;
+    int lane = threadIdx.x & 31;
+    int c = (int)(row / B), b = (int)(row % B);
+    float a = 1.f, sh = 0.f;
+    if (stats != nullptr) {
+        GnStat st = gn_stat(stats, b, c / (C / G), G, inv_n);
+        a = gamma[c] * st.rstd;
+        sh = beta[c] - st.mean * a;
+    }
+    const float* yrow = y + row * Tp;
+    for (int seg = lane; seg < Tp / 8; seg += 32) {
+        F8 yv = load8(yrow + seg * 8);
+        F8 rv;
+        if (res != nullptr) rv = load8(res + row * Tp + seg * 8);
+        F8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float pre = res_scale * act_f(act, yv.v[i] * a + sh);
+            if (res != nullptr) pre += rv.v[i];
+            if (post_gelu) pre = gelu_f(pre);
+            o.v[i] = (seg * 8 + i < T) ? pre : 0.f;
+        }
+        if (out_op != nullptr) store8(out_op + row * Tp + seg * 8, o);
+        if (out_f32 != nullptr) store8(out_f32 + row * Tp + seg * 8, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward.  The incoming gradient is either a tensor (generic layers) or derived from the
+// reconstruction losses on the fly (recon head), so dx_hat is never materialised.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float loss_term(int kind, float d) {
+    float ad = fabsf(d);
+    if (kind == SG_LOSS_MAE) return ad;
+    if (kind == SG_LOSS_SMOOTHL1 || kind == SG_LOSS_HUBER) return ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+    return d * d;
+}
+__device__ __forceinline__ float loss_grad(int kind, float d) {
+    float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    if (kind == SG_LOSS_MAE) return sgn;
+    if (kind == SG_LOSS_SMOOTHL1 || kind == SG_LOSS_HUBER) return fabsf(d) < 1.0f ? d : sgn;
+    return 2.f * d;
+}
+
+struct BwdArgs {
+    const float* y;
+    const double* stats;
+    const float* gamma;
+    const float* beta;
+    const void* res;
+    float res_scale;
+    int act, post_gelu;
+    const float* dout;        // generic: [C][B][Tp]
+    // loss-derived dout (recon head): x, ext in external layout [B][C][T]
+    const float* x;
+    const float* ext;
+    float ga, gm;             // already multiplied by inv_numel
+    int loss_kind;
+    int C, B, T, Tp, G;
+    double inv_n;
+};
+
+// Computes, for one 8-element segment, dyh = dL/d(gamma*xhat+beta) and xhat; returns dpre for dres.
+template <typename RT, bool LOSS>
+__device__ __forceinline__ void bwd_segment(const BwdArgs& p, long long row, int c, int b, int seg, float a, float sh,
+                                            float mean, float rstd, F8& dyh, F8& xhat, F8& dpre) {
+    F8 yv = load8(p.y + row * p.Tp + seg * 8);
+    F8 rv, dv;
+    const RT* res = reinterpret_cast<const RT*>(p.res);
+    if (res != nullptr) rv = load8(res + row * p.Tp + seg * 8);
+    if (!LOSS) dv = load8(p.dout + row * p.Tp + seg * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int t = seg * 8 + i;
+        bool valid = t < p.T;
+        float yh = yv.v[i] * a + sh;
+        float val = act_f(p.act, yh);
+        float d;
+        if (LOSS) {
+            d = 0.f;
+            if (valid) {
+                long long xi = ((long long)b * p.C + c) * p.T + t;
+                if (p.x != nullptr) {
+                    float diff = val - __ldg(p.x + xi);
+                    d = p.ga * loss_grad(p.loss_kind, diff) + p.gm * 2.f * diff;
+                }
+                if (p.ext != nullptr) d += __ldg(p.ext + xi);
+            }
+        } else {
+            d = dv.v[i];
+        }
+        float dp = d;
+        if (p.post_gelu) {
+            float pre = p.res_scale * val + (res != nullptr ? rv.v[i] : 0.f);
+            dp = d * gelu_grad_f(pre);
+        }
+        float g = p.res_scale * dp * act_grad_f(p.act, yh);
+        dyh.v[i] = valid ? g : 0.f;
+        xhat.v[i] = valid ? (yv.v[i] - mean) * rstd : 0.f;
+        dpre.v[i] = valid ? dp : 0.f;
+    }
+}
+
+template <typename RT, bool LOSS>
+__global__ void __launch_bounds__(kThreads)
+gn_bwd_reduce_kernel(BwdArgs p, float* __restrict__ dgamma, float* __restrict__ dbeta, double* __restrict__ S) {
+    long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row >= (long long)p.C * p.B) return;
+    int lane = threadIdx.x & 31;
+    int c = (int)(row / p.B), b = (int)(row % p.B);
+    int g = c / (p.C / p.G);
+    GnStat st = gn_stat(p.stats, b, g, p.G, p.inv_n);
+    float gm = p.gamma[c];
+    float a = gm * st.rstd, sh = p.beta[c] - st.mean * a;
+    float A = 0.f, Bx = 0.f;
+    for (int seg = lane; seg < p.Tp / 8; seg += 32) {
+        F8 dyh, xhat, dpre;
+        bwd_segment<RT, LOSS>(p, row, c, b, seg, a, sh, st.mean, st.rstd, dyh, xhat, dpre);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            A += dyh.v[i];
+            Bx += dyh.v[i] * xhat.v[i];
+        }
+    }
+    A = warp_sum(A);
+    Bx = warp_sum(Bx);
+    if (lane == 0) {
+        atomicAdd(&dgamma[c], Bx);
+        atomicAdd(&dbeta[c], A);
+        atomicAdd(&S[(size_t)(b * p.G + g) * 2], (double)(gm * A));
+        atomicAdd(&S[(size_t)(b * p.G + g) * 2 + 1], (double)(gm * Bx));
+    }
+}
+
+template <typename OT, typename RT, bool LOSS>
+__global__ void __launch_bounds__(kThreads)
+gn_bwd_apply_kernel(BwdArgs p, const double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias,
+                    float* __restrict__ dres, int dres_accumulate) {
+    long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row >= (long long)p.C * p.B) return;
+    int lane = threadIdx.x & 31;
+    int c = (int)(row / p.B), b = (int)(row % p.B);
+    float a = 1.f, sh = 0.f, mean = 0.f, rstd = 1.f, gm = 1.f, m1 = 0.f, m2 = 0.f;
+    bool has_gn = p.stats != nullptr;
+    if (has_gn) {
+        int g = c / (p.C / p.G);
+        GnStat st = gn_stat(p.stats, b, g, p.G, p.inv_n);
+        gm = p.gamma[c];
+        mean = st.mean;
+        rstd = st.rstd;
+        a = gm * rstd;
+        sh = p.beta[c] - mean * a;
+        m1 = (float)(S[(size_t)(b * p.G + g) * 2] * p.inv_n);
+        m2 = (float)(S[(size_t)(b * p.G + g) * 2 + 1] * p.inv_n);
+    }
+    float db = 0.f;
+    for (int seg = lane; seg < p.Tp / 8; seg += 32) {
+        F8 dyh, xhat, dpre, o;
+        bwd_segment<RT, LOSS>(p, row, c, b, seg, a, sh, mean, rstd, dyh, xhat, dpre);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float v = dyh.v[i];
+            if (has_gn) v = (seg * 8 + i < p.T) ? rstd * (gm * v - m1 - xhat.v[i] * m2) : 0.f;
+            o.v[i] = v;
+            db += v;
+        }
+        store8(dy + row * p.Tp + seg * 8, o);
+        if (dres != nullptr) {
+            float* dr = dres + row * p.Tp + seg * 8;
+            if (dres_accumulate) {
+                F8 old = load8(dr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dpre.v[i] += old.v[i];
+            }
+            store8(dr, dpre);
+        }
+    }
+    db = warp_sum(db);
+    if (lane == 0 && dbias != nullptr) atomicAdd(&dbias[c], db);
+}
+
+// ---------------------------------------------------------------------------------------------
+// recon head forward: x_hat = tanh(GN(y)) in the external layout + loss sums
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+recon_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, const float* __restrict__ x, float* __restrict__ x_hat,
+                 double* __restrict__ loss_sums, int N, int B, int T, int Tp, int G, int loss_kind, double inv_n) {
+    __shared__ double shm[2][32];
+    long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    float l0 = 0.f, l1 = 0.f;
+    if (row < (long long)N * B) {
+        int n = (int)(row / B), b = (int)(row % B);
+        GnStat st = gn_stat(stats, b, n / (N / G), G, inv_n);
+        float a = gamma[n] * st.rstd, sh = beta[n] - st.mean * a;
+        const float* yrow = y + row * Tp;
+        long long xo = ((long long)b * N + n) * T;
+        for (int seg = lane; seg < Tp / 8; seg += 32) {
+            F8 yv = load8(yrow + seg * 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int t = seg * 8 + i;
+                if (t < T) {
+                    float xh = tanhf(yv.v[i] * a + sh);
+                    if (x_hat != nullptr) x_hat[xo + t] = xh;
+                    if (x != nullptr) {
+                        float d = xh - __ldg(x + xo + t);
+                        l0 += loss_term(loss_kind, d);
+                        l1 += d * d;
+                    }
+                }
+            }
+        }
+    }
+    if (x != nullptr) {
+        double t0 = block_sum((double)l0, shm[0]);
+        double t1 = block_sum((double)l1, shm[1]);
+        if (threadIdx.x == 0) {
+            atomicAdd(&loss_sums[0], t0);
+            atomicAdd(&loss_sums[1], t1);
+        }
+    }
+}
+
+static int rows_grid(long long rows) { return (int)cdiv(rows, kWarpsPerBlock); }
+
+template <typename OT>
+static int launch_gn_bwd(BwdArgs p, bool loss, int res_is_f32, OT* dy, float* dgamma, float* dbeta, float* dbias,
+                         float* dres, int dres_accumulate, double* ws, cudaStream_t st) {
+    long long rows = (long long)p.C * p.B;
+    bool has_gn = p.stats != nullptr;
+    if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * p.C, st);
+    if (has_gn) {
+        cudaMemsetAsync(dgamma, 0, sizeof(float) * p.C, st);
+        cudaMemsetAsync(dbeta, 0, sizeof(float) * p.C, st);
+        cudaMemsetAsync(ws, 0, sizeof(double) * 2 * p.B * p.G, st);
+    }
+    int grid = rows_grid(rows);
+#define SG_LAUNCH_BWD(RT, LOSS)                                                                                  \
+    do {                                                                                                         \
+        if (has_gn) gn_bwd_reduce_kernel<RT, LOSS><<<grid, kThreads, 0, st>>>(p, dgamma, dbeta, ws);             \
+        gn_bwd_apply_kernel<OT, RT, LOSS><<<grid, kThreads, 0, st>>>(p, ws, dy, dbias, dres, dres_accumulate);   \
+    } while (0)
+    if (loss) {
+        SG_LAUNCH_BWD(float, true);
+    } else if (p.res == nullptr || res_is_f32) {
+        SG_LAUNCH_BWD(float, false);
+    } else {
+        SG_LAUNCH_BWD(OT, false);
+    }
+#undef SG_LAUNCH_BWD
+    return check_launch("gn_act_bwd");
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+
+int sg_pack_input(const float* x, void* out, int B, int N, int T, int Tp, int dtype, void* stream) {
+    SG_REQUIRE(Tp % 8 == 0 && Tp >= T, "pack_input: bad Tp=%d for T=%d", Tp, T);
+    long long rows = (long long)N * B;
+    if (dtype == SG_BF16)
+        pack_input_kernel<__nv_bfloat16><<<rows_grid(rows), kThreads, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)out, B, N, T, Tp);
+    else
+        pack_input_kernel<float><<<rows_grid(rows), kThreads, 0, as_stream(stream)>>>(x, (float*)out, B, N, T, Tp);
+    return check_launch("pack_input");
+}
+
+int sg_unpack_f32(const float* in, float* out, int B, int C, int T, int Tp, void* stream) {
+    unpack_f32_kernel<<<rows_grid((long long)C * B), kThreads, 0, as_stream(stream)>>>(in, out, B, C, T, Tp);
+    return check_launch("unpack_f32");
+}
+
+int sg_axpy_f32(float* dst, const float* src, float alpha, long long n, int accumulate, void* stream) {
+    if (n <= 0) return 0;
+    int grid = (int)(cdiv(n, 256) < 148 * 16 ? cdiv(n, 256) : 148 * 16);
+    axpy_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(dst, src, alpha, n, accumulate);
+    return check_launch("axpy_f32");
+}
+
+int sg_cast_f32(const float* in, void* out, long long n, int dtype, void* stream) {
+    if (n <= 0) return 0;
+    int grid = (int)(cdiv(n, 256) < 148 * 16 ? cdiv(n, 256) : 148 * 16);
+    if (dtype == SG_BF16)
+        cast_f32_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(in, (__nv_bfloat16*)out, n);
+    else
+        cast_f32_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(in, (float*)out, n);
+    return check_launch("cast_f32");
+}
+
+int sg_scale_f64_to_f32(const double* in, float* out, double scale, int n, void* stream) {
+    scale_f64_to_f32_kernel<<<(n + 63) / 64, 64, 0, as_stream(stream)>>>(in, out, scale, n);
+    return check_launch("scale_f64_to_f32");
+}
+
+int sg_gn_stats(const float* y, double* stats, int C, int B, int T, int Tp, int G, void* stream) {
+    SG_REQUIRE(G > 0 && C % G == 0, "gn_stats: C=%d not divisible by G=%d", C, G);
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * G, st);
+    int Cg = C / G;
+    int rpb = Cg < 64 ? Cg : 64;
+    dim3 grid((unsigned)cdiv(Cg, rpb), G, B);
+    gn_stats_kernel<<<grid, kThreads, 0, st>>>(y, stats, C, B, T, Tp, G, rpb);
+    return check_launch("gn_stats");
+}
+
+int sg_gn_act_fwd(const float* y, const double* stats, const float* gamma, const float* beta, const void* res,
+                  int res_is_f32, float res_scale, int act, int post_gelu, void* out_op, float* out_f32, int C, int B,
+                  int T, int Tp, int G, int dtype, void* stream) {
+    SG_REQUIRE(Tp % 8 == 0, "gn_act_fwd: Tp %% 8 != 0");
+    SG_REQUIRE(stats == nullptr || (G > 0 && C % G == 0), "gn_act_fwd: bad groups");
+    cudaStream_t st = as_stream(stream);
+    long long rows = (long long)C * B;
+    double inv_n = stats ? 1.0 / ((double)(C / G) * T) : 0.0;
+    int grid = rows_grid(rows);
+    if (G <= 0) G = 1;
+#define SG_FWD(OT, RT)                                                                                            \
+    gn_act_fwd_kernel<OT, RT><<<grid, kThreads, 0, st>>>(y, stats, gamma, beta, (const RT*)res, res_scale, act,   \
+                                                         post_gelu, (OT*)out_op, out_f32, C, B, T, Tp, G, inv_n)
+    if (dtype == SG_BF16) {
+        if (res == nullptr || res_is_f32) SG_FWD(__nv_bfloat16, float);
+        else SG_FWD(__nv_bfloat16, __nv_bfloat16);
+    } else {
+        SG_FWD(float, float);
+    }
+#undef SG_FWD
+    return check_launch("gn_act_fwd");
+}
+
+int sg_gn_act_bwd(const float* y, const double* stats, const float* gamma, const float* beta, const void* res,
+                  int res_is_f32, float res_scale, int act, int post_gelu, const float* dout, void* dy, float* dgamma,
+                  float* dbeta, float* dbias, float* dres, int dres_accumulate, double* ws, int C, int B, int T, int Tp,
+                  int G, int dtype, void* stream) {
+    SG_REQUIRE(Tp % 8 == 0, "gn_act_bwd: Tp %% 8 != 0");
+    SG_REQUIRE(stats == nullptr || (G > 0 && C % G == 0 && dgamma && dbeta && ws), "gn_act_bwd: bad GN arguments");
+    if (G <= 0) G = 1;
+    BwdArgs p{};
+    p.y = y; p.stats = stats; p.gamma = gamma; p.beta = beta; p.res = res; p.res_scale = res_scale;
+    p.act = act; p.post_gelu = post_gelu; p.dout = dout; p.x = nullptr; p.ext = nullptr; p.ga = 0; p.gm = 0;
+    p.loss_kind = 0; p.C = C; p.B = B; p.T = T; p.Tp = Tp; p.G = G;
+    p.inv_n = stats ? 1.0 / ((double)(C / G) * T) : 0.0;
+    if (dtype == SG_BF16)
+        return launch_gn_bwd<__nv_bfloat16>(p, false, res_is_f32, (__nv_bfloat16*)dy, dgamma, dbeta, dbias, dres,
+                                            dres_accumulate, ws, as_stream(stream));
+    return launch_gn_bwd<float>(p, false, 1, (float*)dy, dgamma, dbeta, dbias, dres, dres_accumulate, ws,
+                                as_stream(stream));
+}
+
+int sg_recon_fwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* x,
+                 float* x_hat, double* loss_sums, int N, int B, int T, int Tp, int G, int loss_kind, void* stream) {
+    SG_REQUIRE(G > 0 && N % G == 0, "recon_fwd: N=%d not divisible by G=%d", N, G);
+    cudaStream_t st = as_stream(stream);
+    if (x != nullptr) cudaMemsetAsync(loss_sums, 0, sizeof(double) * 2, st);
+    double inv_n = 1.0 / ((double)(N / G) * T);
+    recon_fwd_kernel<<<rows_grid((long long)N * B), kThreads, 0, st>>>(y, stats, gamma, beta, x, x_hat, loss_sums, N,
+                                                                        B, T, Tp, G, loss_kind, inv_n);
+    return check_launch("recon_fwd");
+}
+
+// g_loss / g_mse are device scalars produced by autograd (may be NULL); fold them with inv_numel on device.
+__global__ void recon_scalars_kernel(const float* g_loss, const float* g_mse, float inv_numel, float* out2) {
+    out2[0] = g_loss ? g_loss[0] * inv_numel : 0.f;
+    out2[1] = g_mse ? g_mse[0] * inv_numel : 0.f;
+}
+
+}  // extern "C"
+
+namespace sg {
+// The loss-derived backward needs ga/gm as kernel *values*; they live on the device (autograd
+// scalars), so the two recon backward kernels read them through this small indirection.
+template <typename OT, bool REDUCE>
+__global__ void __launch_bounds__(kThreads)
+recon_bwd_kernel(BwdArgs p, const float* __restrict__ scal, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                 double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias) {
+    p.ga = scal[0];
+    p.gm = scal[1];
+    long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row >= (long long)p.C * p.B) return;
+    int lane = threadIdx.x & 31;
+    int c = (int)(row / p.B), b = (int)(row % p.B);
+    int g = c / (p.C / p.G);
+    GnStat st = gn_stat(p.stats, b, g, p.G, p.inv_n);
+    float gm = p.gamma[c];
+    float a = gm * st.rstd, sh = p.beta[c] - st.mean * a;
+    if (REDUCE) {
+        float A = 0.f, Bx = 0.f;
+        for (int seg = lane; seg < p.Tp / 8; seg += 32) {
+            F8 dyh, xhat, dpre;
+            bwd_segment<float, true>(p, row, c, b, seg, a, sh, st.mean, st.rstd, dyh, xhat, dpre);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                A += dyh.v[i];
+                Bx += dyh.v[i] * xhat.v[i];
+            }
+        }
+        A = warp_sum(A);
+        Bx = warp_sum(Bx);
+        if (lane == 0) {
+            atomicAdd(&dgamma[c], Bx);
+            atomicAdd(&dbeta[c], A);
+            atomicAdd(&S[(size_t)(b * p.G + g) * 2], (double)(gm * A));
+            atomicAdd(&S[(size_t)(b * p.G + g) * 2 + 1], (double)(gm * Bx));
+        }
+    } else {
+        float m1 = (float)(S[(size_t)(b * p.G + g) * 2] * p.inv_n);
+        float m2 = (float)(S[(size_t)(b * p.G + g) * 2 + 1] * p.inv_n);
+        float db = 0.f;
+        for (int seg = lane; seg < p.Tp / 8; seg += 32) {
+            F8 dyh, xhat, dpre, o;
+            bwd_segment<float, true>(p, row, c, b, seg, a, sh, st.mean, st.rstd, dyh, xhat, dpre);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float v = (seg * 8 + i < p.T) ? st.rstd * (gm * dyh.v[i] - m1 - xhat.v[i] * m2) : 0.f;
+                o.v[i] = v;
+                db += v;
+            }
+            store8(dy + row * p.Tp + seg * 8, o);
+        }
+        db = warp_sum(db);
+        if (lane == 0) atomicAdd(&dbias[c], db);
+    }
+}
+}  // namespace sg
+
+extern "C" int sg_recon_bwd(const float* y, const double* stats, const float* gamma, const float* beta,
+                            const float* x, const float* g_loss, const float* g_mse, float inv_numel,
+                            const float* dxhat_ext, void* dy, float* dgamma, float* dbeta, float* dbias, double* ws,
+                            int N, int B, int T, int Tp, int G, int loss_kind, int dtype, void* stream) {
+    SG_REQUIRE(G > 0 && N % G == 0 && Tp % 8 == 0, "recon_bwd: bad shape");
+    SG_REQUIRE(x != nullptr || (g_loss == nullptr && g_mse == nullptr), "recon_bwd: loss gradient without x");
+    cudaStream_t st = as_stream(stream);
+    BwdArgs p{};
+    p.y = y; p.stats = stats; p.gamma = gamma; p.beta = beta; p.res = nullptr; p.res_scale = 1.f;
+    p.act = SG_ACT_TANH; p.post_gelu = 0; p.dout = nullptr; p.x = x; p.ext = dxhat_ext; p.loss_kind = loss_kind;
+    p.C = N; p.B = B; p.T = T; p.Tp = Tp; p.G = G;
+    p.inv_n = 1.0 / ((double)(N / G) * T);
+    // workspace: 2*B*G doubles for S followed by 2 floats for the folded scalars
+    double* S = ws;
+    float* scal = reinterpret_cast<float*>(ws + 2 * (size_t)B * G);
+    cudaMemsetAsync(S, 0, sizeof(double) * 2 * B * G, st);
+    cudaMemsetAsync(dgamma, 0, sizeof(float) * N, st);
+    cudaMemsetAsync(dbeta, 0, sizeof(float) * N, st);
+    cudaMemsetAsync(dbias, 0, sizeof(float) * N, st);
+    recon_scalars_kernel<<<1, 1, 0, st>>>(g_loss, g_mse, inv_numel, scal);
+    int grid = rows_grid((long long)N * B);
+    if (dtype == SG_BF16) {
+        recon_bwd_kernel<__nv_bfloat16, true><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (__nv_bfloat16*)dy, dbias);
+        recon_bwd_kernel<__nv_bfloat16, false><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (__nv_bfloat16*)dy, dbias);
+    } else {
+        recon_bwd_kernel<float, true><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (float*)dy, dbias);
+        recon_bwd_kernel<float, false><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (float*)dy, dbias);
+    }
+    return check_launch("recon_bwd");
+}

@@ -1,0 +1,647 @@
+"""Host side of the B200 engine: forward/backward orchestration of the hierarchical VAE over the
+hand-written CUDA kernels (kernels.py -> libsimulgen_b200.so).
+
+The reference runs ~300 ATen/cuDNN launches per step through autograd
+(/root/reference/modules/VAE_network.py:79-117, encoder.py:146-167, decoder.py:170-216).  Here the
+encoder and the decoder are each ONE torch.autograd.Function; inside, a small tape records the
+backward of every fused block, so no ATen kernel runs on the hot path and gradients are produced in
+a known order (which the data-parallel driver uses to overlap the NCCL all-reduce).
+
+Data layout inside the engine ("CR"): activations are [C, B, Tp] with Tp = roundup(T+2, 8) and the
+tail t >= T of every row zero - it is the convolution's zero padding, shared between neighbouring
+samples - so that every Conv1d is one implicit GEMM  D[Cout, B*Tp] = sum_taps Wg[tap] @ shift(act).
+GEMM operands are bf16 (tcgen05, fp32 accumulation) or fp32 (validation mode); conv outputs, norm
+statistics, the residual stream, latents, KL and losses stay fp32.
+"""
+from __future__ import annotations
+
+import os
+import threading
+
+import torch
+
+from . import kernels as K
+
+_PRECISION = os.environ.get("SIMULGEN_B200_PRECISION", "bf16")
+
+
+def set_precision(p: str):
+    """'bf16' (tcgen05 tensor cores) or 'fp32' (validation mode, SIMT kernels)."""
+    global _PRECISION
+    if p not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _PRECISION = p
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def tp_of(T: int) -> int:
+    return (T + 2 + 7) // 8 * 8
+
+
+# ------------------------------------------------------------------------------------------------
+# eps source: counter-based Philox kernel by default; tests may inject a fixed stream
+# ------------------------------------------------------------------------------------------------
+_ORIG_RANDN_LIKE = torch.randn_like
+_rng = threading.local()
+
+
+def _rng_state():
+    if not hasattr(_rng, "counter"):
+        _rng.counter = 0
+        _rng.seed = None
+        _rng.sample0 = 0
+        _rng.fixed = None
+    return _rng
+
+
+class fixed_eps:
+    """Context manager: feed the given eps tensors (reference layout, draw order) to the engine."""
+
+    def __init__(self, eps_list):
+        self.eps = list(eps_list)
+
+    def __enter__(self):
+        st = _rng_state()
+        self._prev = st.fixed
+        st.fixed = list(self.eps)
+        return self
+
+    def __exit__(self, *exc):
+        _rng_state().fixed = self._prev
+        return False
+
+
+def set_sample_offset(sample0: int):
+    """Global index of the first sample of the local batch (data parallel: rank * local_batch) so
+    that eps depends on the global sample id, not on how the batch is split over ranks."""
+    _rng_state().sample0 = int(sample0)
+
+
+def draw_eps(shape, device):
+    """Standard-normal tensor of the reference's shape ([B, L] or [B, C, T]), replacing
+    torch.randn_like (decoder.py:221).  Order of precedence: fixed_eps() stream, a patched
+    torch.randn_like (the oracle harness patches it), else the Philox kernel."""
+    st = _rng_state()
+    if st.fixed is not None:
+        if not st.fixed:
+            raise RuntimeError("fixed_eps stream exhausted")
+        e = st.fixed.pop(0)
+        if tuple(e.shape) != tuple(shape):
+            raise RuntimeError("fixed eps has shape %s, expected %s" % (tuple(e.shape), tuple(shape)))
+        return e.to(device=device, dtype=torch.float32).contiguous()
+    if torch.randn_like is not _ORIG_RANDN_LIKE:
+        proto = torch.empty(shape, device=device, dtype=torch.float32)
+        return torch.randn_like(proto).to(torch.float32).contiguous()
+    seed = torch.initial_seed()
+    if st.seed != seed:
+        st.seed, st.counter = seed, 0
+    out = torch.empty(shape, device=device, dtype=torch.float32)
+    K.philox_normal(out, seed, st.counter, st.sample0)
+    st.counter += 1
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# tape primitives
+# ------------------------------------------------------------------------------------------------
+class Act:
+    """An activation in CR layout.  data: GEMM operand (bf16 / fp32) or None; f32: fp32 copy or None;
+    grad: fp32 gradient buffer filled during backward."""
+    __slots__ = ("data", "f32", "grad", "C", "needs_grad", "name")
+
+    def __init__(self, C, data=None, f32=None, needs_grad=True, name=""):
+        self.C, self.data, self.f32, self.grad, self.needs_grad, self.name = C, data, f32, None, needs_grad, name
+
+    def as_f32(self):
+        if self.f32 is not None:
+            return self.f32
+        if self.data is not None and self.data.dtype == torch.float32:
+            return self.data
+        raise RuntimeError("activation %s has no fp32 copy" % self.name)
+
+    def residual_source(self):
+        return self.f32 if self.f32 is not None else self.data
+
+
+class Ext:
+    """A tensor that crosses the autograd boundary (input or output of an engine Function)."""
+    __slots__ = ("tensor", "grad")
+
+    def __init__(self, tensor):
+        self.tensor, self.grad = tensor, None
+
+
+class Ctx:
+    def __init__(self, B, T, device, record, capture=None):
+        self.B, self.T, self.Tp = B, T, tp_of(T)
+        self.dev = device
+        self.tape = [] if record else None
+        self.op_dtype = torch.bfloat16 if _PRECISION == "bf16" else torch.float32
+        self.pgrads = {}
+        self.capture = capture
+        self.on_param_grad = None       # callback(param, grad) used by the data-parallel driver
+
+    # -- allocation helpers ------------------------------------------------------------------
+    def f32(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.dev)
+
+    def op(self, *shape):
+        return torch.empty(shape, dtype=self.op_dtype, device=self.dev)
+
+    def f64(self, *shape):
+        return torch.empty(shape, dtype=torch.float64, device=self.dev)
+
+    def grad_buf(self, act: Act):
+        """(buffer, accumulate_flag) for adding a gradient contribution to `act`."""
+        if act.grad is None:
+            act.grad = self.f32(act.C, self.B, self.Tp)
+            return act.grad, 0
+        return act.grad, 1
+
+    def set_pgrad(self, param, grad):
+        if param is None or grad is None:
+            return
+        key = id(param)
+        if key in self.pgrads:
+            K.axpy(self.pgrads[key], grad, 1.0, True)
+        else:
+            self.pgrads[key] = grad
+        if self.on_param_grad is not None:
+            self.on_param_grad(param, self.pgrads[key])
+
+    def cap(self, name, act: Act):
+        if self.capture is None:
+            return
+        src = act.f32 if act.f32 is not None else act.data
+        out = torch.empty(self.B, act.C, self.T, dtype=torch.float32, device=self.dev)
+        K.unpack_f32(src.float() if src.dtype != torch.float32 else src, out, self.T)
+        self.capture[name] = out
+
+    def run_backward(self):
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = None
+
+
+# ------------------------------------------------------------------------------------------------
+# spectral norm / weight preparation
+# ------------------------------------------------------------------------------------------------
+class _Prep:
+    __slots__ = ("w", "u", "v", "sigma", "wg", "Cin", "Cout", "k", "Cin_p", "so", "si", "flip", "sn", "version")
+
+
+def _sn_tensors(ctx, mod):
+    if hasattr(mod, "weight_orig"):
+        return mod.weight_orig, mod.weight_u, mod.weight_v, True
+    return mod.weight, None, None, False
+
+
+def _bump_version(mod):
+    v = getattr(mod, "_sg_sn_version", 0) + 1
+    object.__setattr__(mod, "_sg_sn_version", v)
+    return v
+
+
+def prep_conv(ctx: Ctx, mod, transposed=False) -> _Prep:
+    """Power iteration (training) / sigma (eval) + normalised, permuted, cast weight for the GEMMs.
+    common.py:15-37 -> spectral_norm.py:62-114; ConvTranspose1d uses dim=1 (spectral_norm.py:329-333)."""
+    p = _Prep()
+    w, u, v, sn = _sn_tensors(ctx, mod)
+    if transposed:
+        Cin, Cout, k = w.shape
+        so, si, flip = k, Cout * k, 1
+    else:
+        Cout, Cin, k = w.shape
+        so, si, flip = Cin * k, k, 0
+    p.w, p.u, p.v, p.sn = w, u, v, sn
+    p.Cin, p.Cout, p.k, p.so, p.si, p.flip = Cin, Cout, k, so, si, flip
+    p.Cin_p = (Cin + 7) // 8 * 8
+    if sn:
+        p.sigma = ctx.f32(1)
+        K.sn_power_iter(w, u, v, p.sigma, Cout, Cin, k, so, si, mod.training)
+        p.version = _bump_version(mod) if mod.training else getattr(mod, "_sg_sn_version", 0)
+    else:
+        p.sigma = torch.ones(1, dtype=torch.float32, device=ctx.dev)
+        p.version = 0
+    p.wg = ctx.op(k, Cout, p.Cin_p)
+    K.sn_pack_weight(w, p.sigma, p.wg, Cout, Cin, p.Cin_p, k, so, si, flip)
+    return p
+
+
+def prep_linear(ctx: Ctx, mod) -> _Prep:
+    p = _Prep()
+    w, u, v, sn = _sn_tensors(ctx, mod)
+    O, In = w.shape
+    p.w, p.u, p.v, p.sn = w, u, v, sn
+    p.Cin, p.Cout, p.k, p.so, p.si, p.flip, p.Cin_p = In, O, 1, In, 1, 0, In
+    p.wg = None
+    if sn:
+        p.sigma = ctx.f32(1)
+        K.sn_power_iter(w, u, v, p.sigma, O, In, 1, In, 1, mod.training)
+        p.version = _bump_version(mod) if mod.training else getattr(mod, "_sg_sn_version", 0)
+    else:
+        p.sigma = torch.ones(1, dtype=torch.float32, device=ctx.dev)
+        p.version = 0
+    return p
+
+
+def _weight_grad(ctx: Ctx, mod, p: _Prep, dwg):
+    """dWg (fp32, GEMM layout, gradient wrt W/sigma) -> gradient wrt weight_orig (reference layout)."""
+    if p.sn and getattr(mod, "_sg_sn_version", 0) != p.version:
+        raise RuntimeError("simulgen_b200: spectral-norm state of a layer advanced between forward and backward "
+                           "(two training forwards before one backward are not supported)")
+    grad = torch.empty_like(p.w)
+    if p.sn:
+        u, v = p.u, p.v
+    else:
+        u = torch.zeros(p.Cout, dtype=torch.float32, device=ctx.dev)
+        v = torch.zeros(p.Cin * p.k, dtype=torch.float32, device=ctx.dev)
+    K.sn_weight_grad(dwg, p.w, u, v, p.sigma, grad, p.Cout, p.Cin, p.Cin_p, p.k, p.so, p.si, p.flip)
+    ctx.set_pgrad(p.w, grad)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused blocks
+# ------------------------------------------------------------------------------------------------
+def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.0, post_gelu=False,
+               want_f32=False, out_op_view=None, transposed=False, name="") -> Act:
+    """Conv1d / ConvTranspose1d (+ GroupNorm) (+ activation) (+ residual) (+ trailing GELU).
+    Covers encoder.py:29-46, common.py:78-162, decoder.py:27-33,150-166."""
+    B, T, Tp = ctx.B, ctx.T, ctx.Tp
+    p = prep_conv(ctx, conv, transposed)
+    y = ctx.f32(p.Cout, B, Tp)
+    K.conv_fprop(p.wg, a_in.data, conv.bias, y, p.Cin)
+    plain = gn is None and act == K.ACT_NONE and res is None and not post_gelu
+    G = gn.num_groups if gn is not None else 0
+    stats = None
+    res_t = None
+    if plain:
+        out = Act(p.Cout, data=None, f32=y, name=name)
+    else:
+        if gn is not None:
+            stats = ctx.f64(B, G, 2)
+            K.gn_stats(y, stats, T, G)
+        out_op = out_op_view if out_op_view is not None else ctx.op(p.Cout, B, Tp)
+        out_f32 = ctx.f32(p.Cout, B, Tp) if (want_f32 and ctx.op_dtype != torch.float32) else None
+        res_t = res.residual_source() if res is not None else None
+        K.gn_act_fwd(y, stats, gn.weight if gn is not None else None, gn.bias if gn is not None else None,
+                     res_t, res_scale, act, post_gelu, out_op, out_f32, T, G)
+        out = Act(p.Cout, data=out_op, f32=out_f32, name=name)
+    if name:
+        ctx.cap(name, out)
+
+    if ctx.tape is not None:
+        def bwd():
+            g = out.grad
+            if g is None:
+                return
+            out.grad = None
+            dy = ctx.op(p.Cout, B, Tp)
+            dgamma = ctx.f32(p.Cout) if gn is not None else None
+            dbeta = ctx.f32(p.Cout) if gn is not None else None
+            dbias = ctx.f32(p.Cout) if conv.bias is not None else None
+            dres, acc = (None, 0)
+            if res is not None and res.needs_grad:
+                dres, acc = ctx.grad_buf(res)
+            K.gn_act_bwd(y, stats, gn.weight if gn is not None else None, gn.bias if gn is not None else None,
+                         res_t, res_scale, act, post_gelu, g, dy, dgamma, dbeta, dbias, dres, acc, T, G)
+            if gn is not None:
+                ctx.set_pgrad(gn.weight, dgamma)
+                ctx.set_pgrad(gn.bias, dbeta)
+            ctx.set_pgrad(conv.bias, dbias)
+            if p.w.requires_grad:
+                dwg = ctx.f32(p.k, p.Cout, p.Cin_p)
+                K.conv_wgrad(dy, a_in.data, dwg, p.Cin)
+                _weight_grad(ctx, conv, p, dwg)
+            if a_in.needs_grad:
+                dx, acc_in = ctx.grad_buf(a_in)
+                K.conv_dgrad(p.wg, dy, dx, p.Cin, bool(acc_in))
+        ctx.tape.append(bwd)
+    return out
+
+
+def cgg_seq(ctx: Ctx, seq, a_in: Act, res: Act = None, res_scale=0.1, post_gelu=False, want_f32=False,
+            out_op_view=None, name="") -> Act:
+    """nn.Sequential of (Conv1d, GroupNorm, GELU) triples; the optional residual / trailing GELU /
+    fp32 copy apply to the last triple (common.py:101-102,124-125,161-162)."""
+    n = len(seq) // 3
+    a = a_in
+    for i in range(n):
+        last = i == n - 1
+        a = conv_block(ctx, seq[3 * i], seq[3 * i + 1], a, K.ACT_GELU,
+                       res=res if last else None, res_scale=res_scale if (last and res is not None) else 1.0,
+                       post_gelu=post_gelu if last else False, want_f32=want_f32 if last else False,
+                       out_op_view=out_op_view if last else None, name=name if last else "")
+    return a
+
+
+def head(ctx: Ctx, lin, h: Act, ext_out: bool = True):
+    """Linear over the flattened [C*T] features (encoder.py:158-165).  Returns an Ext (or None when
+    only the spectral-norm state has to advance: the two heads whose outputs the reference never uses)."""
+    p = prep_linear(ctx, lin)
+    if not ext_out:
+        return None
+    B, T = ctx.B, ctx.T
+    O = p.Cout
+    out = ctx.f32(B, O)
+    hf = h.as_f32()
+    K.head_fwd(hf, p.w, p.sigma, lin.bias, out, T)
+    ext = Ext(out)
+    if ctx.tape is not None:
+        def bwd():
+            g = ext.grad
+            if g is None:
+                return
+            dwn = ctx.f32(O, p.Cin)
+            dbias = ctx.f32(O)
+            dh, acc = ctx.grad_buf(h) if h.needs_grad else (None, 0)
+            K.head_bwd(hf, p.w, p.sigma, g, dwn, dbias, dh, acc, T)
+            ctx.set_pgrad(lin.bias, dbias)
+            if p.w.requires_grad:
+                _weight_grad(ctx, lin, p, dwn.view(1, O, p.Cin))
+        ctx.tape.append(bwd)
+    return ext
+
+
+def latent_seq(ctx: Ctx, seq, z: Ext, out_op_view=None, name="") -> Act:
+    """Linear(d, d*T) -> Unflatten -> Conv k5 -> GroupNorm -> GELU (decoder.py:131-148)."""
+    lin, conv, gn = seq[0], seq[2], seq[3]
+    B, T, Tp = ctx.B, ctx.T, ctx.Tp
+    p = prep_linear(ctx, lin)
+    D = p.Cin
+    a = Act(D, data=ctx.op(D, B, Tp), name=name + ".lin")
+    K.latent_fwd(z.tensor, p.w, p.sigma, lin.bias, a.data, T)
+    if ctx.tape is not None:
+        def bwd():
+            g = a.grad
+            if g is None:
+                return
+            a.grad = None
+            dwn = ctx.f32(D * T, D)
+            dbias = ctx.f32(D * T)
+            dz = ctx.f32(B, D)
+            K.latent_bwd(z.tensor, p.w, p.sigma, g, dwn, dbias, dz, T)
+            ctx.set_pgrad(lin.bias, dbias)
+            if p.w.requires_grad:
+                _weight_grad(ctx, lin, p, dwn.view(1, D * T, D))
+            if z.grad is None:
+                z.grad = dz
+            else:
+                K.axpy(z.grad, dz, 1.0, True)
+        ctx.tape.append(bwd)
+    return conv_block(ctx, conv, gn, a, K.ACT_GELU, out_op_view=out_op_view, name=name)
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder / decoder graphs
+# ------------------------------------------------------------------------------------------------
+def encoder_graph(ctx: Ctx, enc, x):
+    """encoder.py:146-167.  Returns (last Ext [B, 2*z_dim], [xs Ext ...] in the reference's reversed
+    order without the deepest level)."""
+    B, N, T = x.shape
+    a = Act(N, data=ctx.op(N, B, ctx.Tp), needs_grad=False, name="x")
+    K.pack_input(x, a.data, T)
+    L = len(enc.encoder_blocks)
+    xs = []
+    h = None
+    for i in range(L):
+        a = cgg_seq(ctx, enc.encoder_blocks[i].module_list[0]._seq, a, want_f32=True)
+        h = cgg_seq(ctx, enc.encoder_residual_blocks[i].seq, a, res=a, res_scale=0.1, want_f32=True,
+                    name="encoder.level%d" % i)
+        # xs_linear[L-1] is evaluated by the reference but its output is dropped (encoder.py:167
+        # xs[:-1]): only its power iteration is observable.  xs_linear[0] is returned (exported to
+        # xs.npy by the callers) but never consumed by the decoder (decoder.py:184,190): no gradient.
+        live = i < L - 1
+        xs.append(head(ctx, enc.xs_linear[i], h, ext_out=live))
+        a = h
+    last = head(ctx, enc.last_x_linear, h)
+    return last, [e for e in xs[:-1][::-1]]
+
+
+def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xhat=True):
+    """decoder.py:170-216 (+ the fused reconstruction losses of VAE_network.py:110-111 when x is given).
+    xs: list of Ext (xs[i] feeds level i); entries beyond the used levels are ignored, None entries skipped.
+    Returns dict(x_hat, recon Ext|None, mse Ext|None, kls [Ext])."""
+    B, T, Tp = ctx.B, ctx.T, ctx.Tp
+    nb = len(dec.decoder_residual_blocks)
+    kls = []
+    zs = latent_seq(ctx, dec.sequence_start[0], z, name="decoder.start")
+    out = None
+    std_scale = 1e-10 if mode == "fix" else 1.0
+    for i in range(nb):
+        lastlvl = i == nb - 1
+        up = conv_block(ctx, dec.decoder_blocks[i].module_list[0]._seq[0], None, zs, K.ACT_GELU, want_f32=True,
+                        transposed=True, name="decoder.up%d" % i)
+        C = up.C
+        cat_buf = None
+        if not lastlvl:
+            cat_buf = ctx.op(2 * C, B, Tp)
+        out = cgg_seq(ctx, dec.decoder_residual_blocks[i].seq, up, res=up, res_scale=0.1, want_f32=True,
+                      out_op_view=cat_buf[C:] if cat_buf is not None else None, name="decoder.level%d" % i)
+        if lastlvl:
+            break
+        # condition_z: ResidualBlock -> GELU -> Conv k3 (decoder.py:150-157)
+        cz_seq = dec.condition_z[i]
+        r = cgg_seq(ctx, cz_seq[0]._seq, out, res=out, res_scale=0.1, post_gelu=True)
+        cz = conv_block(ctx, cz_seq[2], None, r, K.ACT_NONE)
+        # xs path (decoder.py:189-193)
+        xs_act = latent_seq(ctx, dec.xs_sequence[i], xs[i], out_op_view=cat_buf[:C], name="decoder.xs%d" % i)
+        cat = Act(2 * C, data=cat_buf, name="cat%d" % i)
+        if ctx.tape is not None:
+            def cat_bwd(cat=cat, xs_act=xs_act, out=out, C=C):
+                g = cat.grad
+                if g is None:
+                    return
+                cat.grad = None
+                xs_act.grad = g[:C]
+                if out.grad is None:
+                    out.grad = g[C:]
+                else:
+                    K.axpy(out.grad, g[C:], 1.0, True)
+            ctx.tape.append(cat_bwd)
+        cxz_seq = dec.condition_xz[i]
+        r2 = cgg_seq(ctx, cxz_seq[0]._seq, cat, res=cat, res_scale=0.1, post_gelu=True)
+        cxz = conv_block(ctx, cxz_seq[2], None, r2, K.ACT_NONE)
+        # kl_2 + reparameterisation + "decoder_out + z" of the next level (decoder.py:179,193-212)
+        eps = draw_eps((B, C, T), ctx.dev)
+        zs_next = Act(C, data=ctx.op(C, B, Tp), name="decoder.zs%d" % i)
+        kl_sum = ctx.f64(1)
+        out_f32 = out.as_f32()
+        K.kl2_reparam_fwd(cz.f32, cxz.f32, eps, out_f32, std_scale, zs_next.data, None, kl_sum, T)
+        kl_t = ctx.f32(1)
+        K.scale_f64_to_f32(kl_sum, kl_t, 0.5 / B)
+        kl_ext = Ext(kl_t)
+        kls.append(kl_ext)
+        ctx.cap("decoder.zs%d" % i, zs_next)
+        if ctx.tape is not None:
+            def kl_bwd(cz=cz, cxz=cxz, eps=eps, zs_next=zs_next, kl_ext=kl_ext, out=out, C=C):
+                dzs = zs_next.grad
+                dkl = kl_ext.grad
+                if dzs is None and dkl is None:
+                    return
+                zs_next.grad = None
+                cz.grad = ctx.f32(2 * C, B, Tp)
+                cxz.grad = ctx.f32(2 * C, B, Tp)
+                K.kl2_reparam_bwd(cz.f32, cxz.f32, eps, std_scale, dzs, dkl, 0.5 / B, cz.grad, cxz.grad, T)
+                if dzs is not None:
+                    if out.grad is None:
+                        out.grad = dzs
+                    else:
+                        K.axpy(out.grad, dzs, 1.0, True)
+            ctx.tape.append(kl_bwd)
+        zs = zs_next
+
+    # reconstruction head: Conv k1 -> GroupNorm -> Tanh (+ losses)
+    conv, gn = dec.recon[0], dec.recon[1]
+    p = prep_conv(ctx, conv)
+    N, G = p.Cout, gn.num_groups
+    y = ctx.f32(N, B, Tp)
+    K.conv_fprop(p.wg, out.data, conv.bias, y, p.Cin)
+    stats = ctx.f64(B, G, 2)
+    K.gn_stats(y, stats, T, G)
+    x_hat = ctx.f32(B, N, T) if want_xhat else None
+    res = dict(x_hat=x_hat, recon=None, mse=None, kls=kls)
+    loss_kind = K.LOSS_KINDS.get(lossfun, 0)
+    sums = ctx.f64(2)
+    K.recon_fwd(y, stats, gn.weight, gn.bias, x, x_hat, sums, T, G, loss_kind)
+    inv_numel = 1.0 / float(B * N * T)
+    if x is not None:
+        both = ctx.f32(2)
+        K.scale_f64_to_f32(sums, both, inv_numel)
+        res["recon"], res["mse"] = Ext(both[0:1]), Ext(both[1:2])
+    xhat_ext = Ext(x_hat)
+    res["x_hat_ext"] = xhat_ext
+    if ctx.tape is not None:
+        def recon_bwd(out=out):
+            g_loss = res["recon"].grad if res["recon"] is not None else None
+            g_mse = res["mse"].grad if res["mse"] is not None else None
+            g_ext = xhat_ext.grad
+            if g_loss is None and g_mse is None and g_ext is None:
+                return
+            dy = ctx.op(N, B, Tp)
+            dgamma, dbeta, dbias = ctx.f32(N), ctx.f32(N), ctx.f32(N)
+            K.recon_bwd(y, stats, gn.weight, gn.bias, x, g_loss, g_mse, inv_numel, g_ext, dy, dgamma, dbeta, dbias,
+                        T, G, loss_kind)
+            ctx.set_pgrad(gn.weight, dgamma)
+            ctx.set_pgrad(gn.bias, dbeta)
+            ctx.set_pgrad(conv.bias, dbias)
+            if p.w.requires_grad:
+                dwg = ctx.f32(p.k, p.Cout, p.Cin_p)
+                K.conv_wgrad(dy, out.data, dwg, p.Cin)
+                _weight_grad(ctx, conv, p, dwg)
+            dx, acc = ctx.grad_buf(out)
+            K.conv_dgrad(p.wg, dy, dx, p.Cin, bool(acc))
+        ctx.tape.append(recon_bwd)
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd boundary
+# ------------------------------------------------------------------------------------------------
+def _contig_f32(g):
+    if g is None:
+        return None
+    if g.dtype != torch.float32 or not g.is_contiguous():
+        g = g.to(torch.float32).contiguous()
+    return g
+
+
+def _check_input(x, what):
+    if not x.is_cuda:
+        raise RuntimeError("simulgen_b200: %s must be a CUDA tensor - the engine has no CPU fallback" % what)
+
+
+class EncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(fctx, enc, capture, x, *params):
+        _check_input(x, "encoder input")
+        fctx.set_materialize_grads(False)
+        x = x.contiguous().float()
+        record = any(fctx.needs_input_grad)
+        ctx = Ctx(x.shape[0], x.shape[2], x.device, record, capture)
+        last, xs = encoder_graph(ctx, enc, x)
+        fctx.ectx, fctx.exts, fctx.params = ctx, [last] + xs, params
+        return (last.tensor,) + tuple(e.tensor for e in xs)
+
+    @staticmethod
+    def backward(fctx, *grads):
+        ctx = fctx.ectx
+        for e, g in zip(fctx.exts, grads):
+            e.grad = _contig_f32(g)
+        ctx.run_backward()
+        out = tuple(ctx.pgrads.get(id(p)) for p in fctx.params)
+        fctx.ectx = None
+        return (None, None, None) + out
+
+
+class ReparamMainFn(torch.autograd.Function):
+    """VAE_network.py:103-105,113: clamp, exp, reparameterize, kl - one kernel each way."""
+
+    @staticmethod
+    def forward(fctx, last, eps):
+        _check_input(last, "latent head output")
+        fctx.set_materialize_grads(False)
+        last = last.contiguous()
+        B, L2 = last.shape
+        z = torch.empty(B, L2 // 2, dtype=torch.float32, device=last.device)
+        kl = torch.empty(1, dtype=torch.float32, device=last.device)
+        K.reparam_main_fwd(last, eps, z, kl)
+        fctx.save_for_backward(last, eps)
+        return z, kl.view(())
+
+    @staticmethod
+    def backward(fctx, dz, dkl):
+        last, eps = fctx.saved_tensors
+        dlast = torch.empty_like(last)
+        K.reparam_main_bwd(last, eps, _contig_f32(dz), _contig_f32(dkl.reshape(1)) if dkl is not None else None, dlast)
+        return dlast, None
+
+
+class DecoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(fctx, dec, capture, lossfun, mode, n_xs, z, *rest):
+        xs_t = rest[:n_xs]
+        x = rest[n_xs]
+        params = rest[n_xs + 1:]
+        _check_input(z, "decoder latent")
+        fctx.set_materialize_grads(False)
+        z = z.contiguous().float()
+        record = any(fctx.needs_input_grad)
+        ctx = Ctx(z.shape[0], dec.num_time, z.device, record, capture)
+        z_ext = Ext(z)
+        xs_ext = [Ext(t.contiguous().float()) for t in xs_t]
+        if x is not None:
+            x = x.contiguous().float()
+        res = decoder_graph(ctx, dec, z_ext, xs_ext, x, lossfun, mode)
+        fctx.ectx, fctx.res, fctx.params, fctx.z_ext, fctx.xs_ext = ctx, res, params, z_ext, xs_ext
+        fctx.has_x = x is not None
+        outs = [res["x_hat"]]
+        if x is not None:
+            outs += [res["recon"].tensor.view(()), res["mse"].tensor.view(())]
+        outs += [k.tensor.view(()) for k in res["kls"]]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(fctx, *grads):
+        ctx, res = fctx.ectx, fctx.res
+        grads = list(grads)
+        res["x_hat_ext"].grad = _contig_f32(grads.pop(0))
+        if fctx.has_x:
+            g = grads.pop(0)
+            res["recon"].grad = _contig_f32(g.reshape(1)) if g is not None else None
+            g = grads.pop(0)
+            res["mse"].grad = _contig_f32(g.reshape(1)) if g is not None else None
+        for k_ext in res["kls"]:
+            g = grads.pop(0)
+            k_ext.grad = _contig_f32(g.reshape(1)) if g is not None else None
+        ctx.run_backward()
+        pg = tuple(ctx.pgrads.get(id(p)) for p in fctx.params)
+        gz = fctx.z_ext.grad
+        gxs = tuple(e.grad for e in fctx.xs_ext)
+        fctx.ectx = None
+        fctx.res = None
+        return (None, None, None, None, None, gz) + gxs + (None,) + pg
+

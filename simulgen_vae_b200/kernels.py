@@ -1,0 +1,217 @@
+"""Tensor-level wrappers around the C ABI (include/simulgen_b200.h).
+
+Every function takes torch CUDA tensors that the caller allocated, passes raw device pointers,
+sizes and the current CUDA stream to libsimulgen_b200.so, and returns nothing (outputs are written
+in place).  There is no fallback: non-CUDA tensors or a missing extension raise RuntimeError.
+
+The functions are looked up through the module attribute at call time (`K.conv_fprop(...)`), which
+is what lets the CPU unit tests substitute `tests/kernel_emulator.py` to check the host-side wiring
+without a GPU; the product never does that.
+"""
+import torch
+
+from . import _lib
+
+SG_BF16, SG_F32 = 0, 1
+ACT_NONE, ACT_GELU, ACT_TANH = 0, 1, 2
+LOSS_KINDS = {"MSE": 0, "MAE": 1, "smoothL1": 2, "Huber": 3}
+
+LAUNCHES = 0          # number of C-ABI calls (each launches >= 1 of our kernels); bench.py reports it
+
+
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return SG_BF16
+    if t.dtype == torch.float32:
+        return SG_F32
+    raise RuntimeError("simulgen_b200: unsupported operand dtype %s" % t.dtype)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("simulgen_b200: CUDA tensor required (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("simulgen_b200: contiguous tensor required, got strides %s for shape %s"
+                           % (t.stride(), tuple(t.shape)))
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    _lib.call(name, *args)
+
+
+def _f32(t, name):
+    if t is not None and t.dtype != torch.float32:
+        raise RuntimeError("simulgen_b200: %s must be float32" % name)
+    return t
+
+
+# ---- layout -------------------------------------------------------------------------------------
+def pack_input(x, out, T):
+    B, N, _ = x.shape
+    Tp = out.shape[2]
+    _call("sg_pack_input", _p(_f32(x, "x")), _p(out), B, N, T, Tp, _dt(out), _stream())
+
+
+def unpack_f32(inp, out, T):
+    C, B, Tp = inp.shape
+    _call("sg_unpack_f32", _p(_f32(inp, "inp")), _p(_f32(out, "out")), B, C, T, Tp, _stream())
+
+
+def axpy(dst, src, alpha, accumulate):
+    assert dst.numel() == src.numel()
+    _call("sg_axpy_f32", _p(_f32(dst, "dst")), _p(_f32(src, "src")), float(alpha), dst.numel(), int(accumulate), _stream())
+
+
+def scale_f64_to_f32(inp, out, scale):
+    assert inp.dtype == torch.float64 and out.dtype == torch.float32
+    _call("sg_scale_f64_to_f32", _p(inp), _p(out), float(scale), inp.numel(), _stream())
+
+
+# ---- spectral norm ------------------------------------------------------------------------------
+def sn_power_iter(w_orig, u, v, sigma, H, Cin, k, so, si, training):
+    ws = torch.empty(H + Cin * k + 8, dtype=torch.float32, device=w_orig.device)
+    _call("sg_sn_power_iter", _p(_f32(w_orig, "w")), _p(u), _p(v), _p(sigma), _p(ws), H, Cin, k, so, si,
+          int(training), _stream())
+
+
+def sn_pack_weight(w_orig, sigma, wg, Cout, Cin, Cin_p, k, so, si, flip):
+    _call("sg_sn_pack_weight", _p(_f32(w_orig, "w")), _p(sigma), _p(wg), Cout, Cin, Cin_p, k, so, si, int(flip),
+          _dt(wg), _stream())
+
+
+def sn_weight_grad(dwg, w_orig, u, v, sigma, grad, Cout, Cin, Cin_p, k, so, si, flip):
+    ws = torch.empty(2, dtype=torch.float64, device=w_orig.device)
+    _call("sg_sn_weight_grad", _p(_f32(dwg, "dwg")), _p(w_orig), _p(u), _p(v), _p(sigma), _p(_f32(grad, "grad")), _p(ws),
+          Cout, Cin, Cin_p, k, so, si, int(flip), _stream())
+
+
+# ---- convolutions -------------------------------------------------------------------------------
+def conv_fprop(wg, act, bias, out, Cin, accumulate=False):
+    k, Cout, Cin_p = wg.shape
+    R = act.numel() // act.shape[0]
+    assert act.shape[0] == Cin and out.shape[0] == Cout and out.numel() == Cout * R and wg.dtype == act.dtype
+    _call("sg_conv_fprop", _p(wg), _p(act), _p(bias), _p(_f32(out, "out")), Cin, Cin_p, Cout, k, R, int(accumulate),
+          _dt(act), _stream())
+
+
+def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
+    k, Cout, Cin_p = wg.shape
+    R = dy.numel() // dy.shape[0]
+    assert dy.shape[0] == Cout and dx.shape[0] == Cin and dx.numel() == Cin * R and wg.dtype == dy.dtype
+    _call("sg_conv_dgrad", _p(wg), _p(dy), _p(_f32(dx, "dx")), Cin, Cin_p, Cout, k, R, int(accumulate), _dt(dy), _stream())
+
+
+def conv_wgrad(dy, act, dwg, Cin):
+    k, Cout, Cin_p = dwg.shape
+    R = dy.numel() // dy.shape[0]
+    assert dy.shape[0] == Cout and act.shape[0] == Cin and act.numel() == Cin * R and dy.dtype == act.dtype
+    _call("sg_conv_wgrad", _p(dy), _p(act), _p(_f32(dwg, "dwg")), Cin, Cin_p, Cout, k, R, _dt(act), _stream())
+
+
+# ---- GroupNorm + activation ---------------------------------------------------------------------
+def gn_stats(y, stats, T, G):
+    C, B, Tp = y.shape
+    _call("sg_gn_stats", _p(_f32(y, "y")), _p(stats), C, B, T, Tp, G, _stream())
+
+
+def gn_act_fwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, out_op, out_f32, T, G):
+    C, B, Tp = y.shape
+    dt = _dt(out_op) if out_op is not None else SG_F32
+    res_is_f32 = int(res is not None and res.dtype == torch.float32)
+    _call("sg_gn_act_fwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(res), res_is_f32, float(res_scale),
+          int(act), int(post_gelu), _p(out_op), _p(out_f32), C, B, T, Tp, int(G), dt, _stream())
+
+
+def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, dgamma, dbeta, dbias, dres,
+               dres_accumulate, T, G):
+    C, B, Tp = y.shape
+    res_is_f32 = int(res is not None and res.dtype == torch.float32)
+    ws = torch.empty(2 * B * max(int(G), 1) + 2, dtype=torch.float64, device=y.device)
+    _call("sg_gn_act_bwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(res), res_is_f32, float(res_scale),
+          int(act), int(post_gelu), _p(_f32(dout, "dout")), _p(dy), _p(dgamma), _p(dbeta), _p(dbias), _p(dres),
+          int(dres_accumulate), _p(ws), C, B, T, Tp, int(G), _dt(dy), _stream())
+
+
+def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind):
+    N, B, Tp = y.shape
+    _call("sg_recon_fwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(x), _p(x_hat), _p(loss_sums), N, B, T, Tp,
+          G, int(loss_kind), _stream())
+
+
+def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy, dgamma, dbeta, dbias, T, G, loss_kind):
+    N, B, Tp = y.shape
+    ws = torch.empty(2 * B * G + 2, dtype=torch.float64, device=y.device)
+    _call("sg_recon_bwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(x), _p(g_loss), _p(g_mse), float(inv_numel),
+          _p(dxhat_ext), _p(dy), _p(dgamma), _p(dbeta), _p(dbias), _p(ws), N, B, T, Tp, G, int(loss_kind), _dt(dy),
+          _stream())
+
+
+# ---- linear heads -------------------------------------------------------------------------------
+def head_fwd(h, w_orig, sigma, bias, out, T):
+    C, B, Tp = h.shape
+    O = w_orig.shape[0]
+    _call("sg_head_fwd", _p(_f32(h, "h")), _p(w_orig), _p(sigma), _p(bias), _p(out), C, B, T, Tp, O, _stream())
+
+
+def head_bwd(h, w_orig, sigma, dout, dwn, dbias, dh, dh_accumulate, T):
+    C, B, Tp = h.shape
+    O = w_orig.shape[0]
+    _call("sg_head_bwd", _p(_f32(h, "h")), _p(w_orig), _p(sigma), _p(_f32(dout, "dout")), _p(dwn), _p(dbias), _p(dh),
+          int(dh_accumulate), C, B, T, Tp, O, _stream())
+
+
+def latent_fwd(z, w_orig, sigma, bias, out, T):
+    D, B, Tp = out.shape
+    _call("sg_latent_fwd", _p(_f32(z, "z")), _p(w_orig), _p(sigma), _p(bias), _p(out), D, B, T, Tp, _dt(out), _stream())
+
+
+def latent_bwd(z, w_orig, sigma, dact, dwn, dbias, dz, T):
+    D, B, Tp = dact.shape
+    _call("sg_latent_bwd", _p(_f32(z, "z")), _p(w_orig), _p(sigma), _p(_f32(dact, "dact")), _p(dwn), _p(dbias), _p(dz),
+          D, B, T, Tp, _stream())
+
+
+# ---- reparameterisation + KL --------------------------------------------------------------------
+def reparam_main_fwd(last, eps, z, kl_out):
+    B, L2 = last.shape
+    _call("sg_reparam_main_fwd", _p(_f32(last, "last")), _p(_f32(eps, "eps")), _p(z), _p(kl_out), B, L2 // 2, _stream())
+
+
+def reparam_main_bwd(last, eps, dz, dkl, dlast):
+    B, L2 = last.shape
+    _call("sg_reparam_main_bwd", _p(last), _p(eps), _p(dz), _p(dkl), _p(dlast), B, L2 // 2, _stream())
+
+
+def kl2_reparam_fwd(cz, cxz, eps, h, std_scale, zs_op, zs_f32, kl_sum, T):
+    C2, B, Tp = cz.shape
+    dt = _dt(zs_op) if zs_op is not None else SG_F32
+    _call("sg_kl2_reparam_fwd", _p(_f32(cz, "cz")), _p(_f32(cxz, "cxz")), _p(_f32(eps, "eps")), _p(_f32(h, "h")),
+          float(std_scale), _p(zs_op), _p(zs_f32), _p(kl_sum), C2 // 2, B, T, Tp, dt, _stream())
+
+
+def kl2_reparam_bwd(cz, cxz, eps, std_scale, dzs, dkl, kl_scale, dcz, dcxz, T):
+    C2, B, Tp = cz.shape
+    _call("sg_kl2_reparam_bwd", _p(cz), _p(cxz), _p(eps), float(std_scale), _p(dzs), _p(dkl), float(kl_scale),
+          _p(_f32(dcz, "dcz")), _p(_f32(dcxz, "dcxz")), C2 // 2, B, T, Tp, _stream())
+
+
+# ---- RNG / optimiser ----------------------------------------------------------------------------
+def philox_normal(out, seed, stream_id, sample0):
+    B = out.shape[0]
+    per = out.numel() // B
+    _call("sg_philox_normal", _p(_f32(out, "out")), B, per, int(seed) & (2 ** 64 - 1), int(stream_id), int(sample0),
+          _stream())
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq):
+    _call("sg_adamw_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+          float(weight_decay), int(step), float(grad_scale), _p(gnorm_sq), _stream())
