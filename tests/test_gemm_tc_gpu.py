@@ -1,0 +1,85 @@
+"""-m gpu: the tcgen05/TMEM/TMA implicit-GEMM convolution kernels (bf16 operands, fp32 accumulate)
+against the plain PyTorch conv of the same bf16 inputs, through the C ABI."""
+import pytest
+import torch
+
+import kernel_emulator as emu
+from conftest import rel_l2
+from simulgen_vae_b200 import kernels as K
+from simulgen_vae_b200.engine import tp_of
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF = torch.bfloat16
+
+SHAPES = [
+    # Cin, Cout, k, B, T
+    (24, 72, 1, 3, 21),          # everything ragged, single tile
+    (24, 72, 3, 3, 21),
+    (64, 128, 5, 2, 30),
+    (256, 384, 3, 4, 200),       # multi-tile M and N, T = 200 -> Tp = 208
+    (1280, 1280, 5, 2, 200),     # the decoder residual shape (scaled), deep K loop
+    (8200, 136, 1, 2, 100),      # large K with split-K, ragged M
+    (200, 4104, 1, 2, 100),      # recon-like: large M
+]
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def make(Cin, Cout, k, B, T):
+    Tp = tp_of(T)
+    Cin_p = (Cin + 7) // 8 * 8
+    wg = rnd(k, Cout, Cin_p, seed=1, scale=1.0 / (Cin * k) ** 0.5)
+    wg[:, :, Cin:] = 0
+    act = rnd(Cin, B, Tp, seed=2)
+    act[:, :, T:] = 0
+    dy = rnd(Cout, B, Tp, seed=3)
+    dy[:, :, T:] = 0
+    return wg.to(BF), act.to(BF), dy.to(BF), rnd(Cout, seed=4), Tp, Cin_p
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_tc_fprop(shape):
+    Cin, Cout, k, B, T = shape
+    wg, act, dy, bias, Tp, Cin_p = make(*shape)
+    o1 = torch.full((Cout, B, Tp), 5.0, device=DEV)
+    o2 = torch.empty_like(o1)
+    K.conv_fprop(wg, act, bias, o1, Cin)
+    emu.conv_fprop(wg, act, bias, o2, Cin)
+    torch.cuda.synchronize()
+    assert rel_l2(o1, o2) < 1e-4, rel_l2(o1, o2)
+    K.conv_fprop(wg, act, None, o1, Cin, accumulate=True)
+    emu.conv_fprop(wg, act, None, o2, Cin, accumulate=True)
+    assert rel_l2(o1, o2) < 1e-4, rel_l2(o1, o2)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_tc_dgrad(shape):
+    Cin, Cout, k, B, T = shape
+    wg, act, dy, bias, Tp, Cin_p = make(*shape)
+    d1 = torch.full((Cin, B, Tp), 5.0, device=DEV)
+    d2 = torch.empty_like(d1)
+    K.conv_dgrad(wg, dy, d1, Cin)
+    emu.conv_dgrad(wg, dy, d2, Cin)
+    torch.cuda.synchronize()
+    assert rel_l2(d1, d2) < 1e-4, rel_l2(d1, d2)
+    K.conv_dgrad(wg, dy, d1, Cin, accumulate=True)
+    emu.conv_dgrad(wg, dy, d2, Cin, accumulate=True)
+    assert rel_l2(d1, d2) < 1e-4, rel_l2(d1, d2)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_tc_wgrad(shape):
+    Cin, Cout, k, B, T = shape
+    wg, act, dy, bias, Tp, Cin_p = make(*shape)
+    w1 = torch.full((k, Cout, Cin_p), 5.0, device=DEV)
+    w2 = torch.empty_like(w1)
+    K.conv_wgrad(dy, act, w1, Cin)
+    emu.conv_wgrad(dy, act, w2, Cin)
+    torch.cuda.synchronize()
+    assert rel_l2(w1[:, :, :Cin], w2[:, :, :Cin]) < 1e-4, rel_l2(w1[:, :, :Cin], w2[:, :, :Cin])
+    if Cin_p > Cin:
+        assert float(w1[:, :, Cin:].abs().max()) == 0.0

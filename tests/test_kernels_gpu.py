@@ -1,0 +1,354 @@
+"""-m gpu: every streaming / small CUDA kernel against its plain PyTorch model (tests/kernel_emulator.py),
+called through the C ABI (simulgen_vae_b200.kernels -> libsimulgen_b200.so)."""
+import pytest
+import torch
+
+import kernel_emulator as emu
+from conftest import rel_l2
+from simulgen_vae_b200 import kernels as K
+from simulgen_vae_b200.engine import tp_of
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def cr(C, B, T, seed=0, dtype=torch.float32, scale=1.0):
+    """random CR-layout tensor with a zero gap"""
+    Tp = tp_of(T)
+    t = rnd(C, B, Tp, seed=seed, scale=scale)
+    t[:, :, T:] = 0
+    return t.to(dtype)
+
+
+def close(a, b, tol, what=""):
+    e = rel_l2(a, b)
+    assert e < tol, "%s rel-L2 %.3e >= %.1e" % (what, e, tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_pack_unpack(dtype):
+    B, N, T = 3, 37, 20
+    x = rnd(B, N, T)
+    out = torch.full((N, B, tp_of(T)), 7.0, device=DEV, dtype=dtype)
+    ref = torch.empty_like(out)
+    K.pack_input(x, out, T)
+    emu.pack_input(x, ref, T)
+    assert torch.equal(out, ref)
+    if dtype == torch.float32:
+        back = torch.empty(B, N, T, device=DEV)
+        K.unpack_f32(out, back, T)
+        assert torch.equal(back, x)
+
+
+@pytest.mark.parametrize("kind", ["conv", "convT", "linear"])
+@pytest.mark.parametrize("training", [True, False])
+def test_sn_power_iter_pack_grad(kind, training):
+    Cout, Cin, k = 40, 24, 3
+    if kind == "conv":
+        w = rnd(Cout, Cin, k)
+        so, si, flip = Cin * k, k, 0
+    elif kind == "convT":
+        w = rnd(Cin, Cout, k)
+        so, si, flip = k, Cout * k, 1
+    else:
+        k = 1
+        w = rnd(Cout, Cin)
+        so, si, flip = Cin, 1, 0
+    u = torch.nn.functional.normalize(rnd(Cout, seed=1), dim=0)
+    v = torch.nn.functional.normalize(rnd(Cin * k, seed=2), dim=0)
+    u2, v2 = u.clone(), v.clone()
+    s1, s2 = torch.empty(1, device=DEV), torch.empty(1, device=DEV)
+    K.sn_power_iter(w, u, v, s1, Cout, Cin, k, so, si, training)
+    emu.sn_power_iter(w, u2, v2, s2, Cout, Cin, k, so, si, training)
+    close(u, u2, 1e-5, "u")
+    close(v, v2, 1e-5, "v")
+    close(s1, s2, 1e-5, "sigma")
+    if kind == "linear":
+        Cin_p = Cin
+    else:
+        Cin_p = (Cin + 7) // 8 * 8
+        for dt in (torch.float32, torch.bfloat16):
+            wg = torch.full((k, Cout, Cin_p), 3.0, device=DEV, dtype=dt)
+            wg2 = torch.empty_like(wg)
+            K.sn_pack_weight(w, s1, wg, Cout, Cin, Cin_p, k, so, si, flip)
+            emu.sn_pack_weight(w, s1, wg2, Cout, Cin, Cin_p, k, so, si, flip)
+            close(wg.float(), wg2.float(), 1e-6 if dt == torch.float32 else 4e-3, "wg")
+    dwg = rnd(k, Cout, Cin_p, seed=5)
+    g1, g2 = torch.empty_like(w), torch.empty_like(w)
+    K.sn_weight_grad(dwg, w, u, v, s1, g1, Cout, Cin, Cin_p, k, so, si, flip)
+    emu.sn_weight_grad(dwg, w, u, v, s1, g2, Cout, Cin, Cin_p, k, so, si, flip)
+    close(g1, g2, 1e-5, "sn grad")
+
+
+@pytest.mark.parametrize("k", [1, 3, 5])
+def test_conv_simt_fp32(k):
+    Cin, Cout, B, T = 20, 72, 3, 21
+    Cin_p = (Cin + 7) // 8 * 8
+    Tp = tp_of(T)
+    wg = rnd(k, Cout, Cin_p, seed=1, scale=0.2)
+    wg[:, :, Cin:] = 0
+    act = cr(Cin, B, T, seed=2)
+    bias = rnd(Cout, seed=3)
+    o1 = torch.empty(Cout, B, Tp, device=DEV)
+    o2 = torch.empty_like(o1)
+    K.conv_fprop(wg, act, bias, o1, Cin)
+    emu.conv_fprop(wg, act, bias, o2, Cin)
+    close(o1, o2, 1e-5, "fprop")
+    K.conv_fprop(wg, act, None, o1, Cin, accumulate=True)
+    emu.conv_fprop(wg, act, None, o2, Cin, accumulate=True)
+    close(o1, o2, 1e-5, "fprop acc")
+    dy = cr(Cout, B, T, seed=4)
+    d1 = torch.empty(Cin, B, Tp, device=DEV)
+    d2 = torch.empty_like(d1)
+    K.conv_dgrad(wg, dy, d1, Cin)
+    emu.conv_dgrad(wg, dy, d2, Cin)
+    close(d1, d2, 1e-5, "dgrad")
+    w1 = torch.empty(k, Cout, Cin_p, device=DEV)
+    w2 = torch.empty_like(w1)
+    K.conv_wgrad(dy, act, w1, Cin)
+    emu.conv_wgrad(dy, act, w2, Cin)
+    close(w1[:, :, :Cin], w2[:, :, :Cin], 1e-5, "wgrad")
+
+
+def test_gn_stats():
+    C, B, T, G = 48, 3, 21, 8
+    y = cr(C, B, T, seed=1) + 0.5
+    s1 = torch.empty(B, G, 2, device=DEV, dtype=torch.float64)
+    s2 = torch.empty_like(s1)
+    K.gn_stats(y, s1, T, G)
+    emu.gn_stats(y, s2, T, G)
+    close(s1, s2, 1e-6, "stats")
+
+
+CASES = [
+    # use_gn, act, res ('none'|'f32'|'op'), res_scale, post_gelu
+    (True, K.ACT_GELU, "none", 1.0, False),
+    (True, K.ACT_GELU, "f32", 0.1, False),
+    (True, K.ACT_GELU, "op", 0.1, True),
+    (False, K.ACT_GELU, "none", 1.0, False),
+    (False, K.ACT_NONE, "none", 1.0, False),
+    (True, K.ACT_TANH, "none", 1.0, False),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gn_act_fwd_bwd(case, dtype):
+    use_gn, act, res_kind, res_scale, post = case
+    C, B, T, G = 48, 3, 21, 8
+    Tp = tp_of(T)
+    y = cr(C, B, T, seed=1) * 1.5 + 0.3
+    gamma, beta = rnd(C, seed=2) * 0.5 + 1.0, rnd(C, seed=3) * 0.2
+    stats = None
+    if use_gn:
+        stats = torch.empty(B, G, 2, device=DEV, dtype=torch.float64)
+        K.gn_stats(y, stats, T, G)
+    res = None
+    if res_kind == "f32":
+        res = cr(C, B, T, seed=4)
+    elif res_kind == "op":
+        res = cr(C, B, T, seed=4).to(dtype)
+    o1 = torch.full((C, B, Tp), 9.0, device=DEV, dtype=dtype)
+    f1 = torch.full((C, B, Tp), 9.0, device=DEV)
+    o2, f2 = torch.empty_like(o1), torch.empty_like(f1)
+    GG = G if use_gn else 0
+    K.gn_act_fwd(y, stats, gamma if use_gn else None, beta if use_gn else None, res, res_scale, act, post, o1, f1, T, GG)
+    emu.gn_act_fwd(y, stats, gamma, beta, res, res_scale, act, post, o2, f2, T, G)
+    close(f1, f2, 2e-6, "fwd f32")
+    close(o1.float(), o2.float(), 2e-6 if dtype == torch.float32 else 4e-3, "fwd op")
+    assert float(o1[:, :, T:].float().abs().max()) == 0.0
+    # backward
+    dout = cr(C, B, T, seed=5)
+    dy1 = torch.full((C, B, Tp), 9.0, device=DEV, dtype=dtype)
+    dy2 = torch.empty_like(dy1)
+    dg1, db1, dbi1 = (torch.empty(C, device=DEV) for _ in range(3))
+    dg2, db2, dbi2 = (torch.empty(C, device=DEV) for _ in range(3))
+    dr1 = cr(C, B, T, seed=6) if res is not None else None
+    dr2 = dr1.clone() if dr1 is not None else None
+    K.gn_act_bwd(y, stats, gamma if use_gn else None, beta if use_gn else None, res, res_scale, act, post, dout, dy1,
+                 dg1 if use_gn else None, db1 if use_gn else None, dbi1, dr1, 1, T, GG)
+    emu.gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post, dout, dy2, dg2, db2, dbi2, dr2, 1, T, G)
+    tol = 2e-5 if dtype == torch.float32 else 5e-3
+    close(dy1.float(), dy2.float(), tol, "dy")
+    close(dbi1, dbi2, tol * 2, "dbias")
+    if use_gn:
+        close(dg1, dg2, 2e-5, "dgamma")
+        close(db1, db2, 2e-5, "dbeta")
+    if res is not None:
+        close(dr1[:, :, :T], dr2[:, :, :T], 2e-5, "dres")
+    assert float(dy1[:, :, T:].float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("loss", ["MSE", "MAE", "smoothL1", "Huber"])
+@pytest.mark.parametrize("with_ext", [False, True])
+def test_recon_fwd_bwd(loss, with_ext):
+    N, B, T, G = 40, 3, 21, 8
+    Tp = tp_of(T)
+    kind = K.LOSS_KINDS[loss]
+    y = cr(N, B, T, seed=1) * 2.0
+    gamma, beta = rnd(N, seed=2) * 0.5 + 1.0, rnd(N, seed=3) * 0.2
+    x = rnd(B, N, T, seed=4) * 1.5
+    stats = torch.empty(B, G, 2, device=DEV, dtype=torch.float64)
+    K.gn_stats(y, stats, T, G)
+    xh1, xh2 = torch.empty(B, N, T, device=DEV), torch.empty(B, N, T, device=DEV)
+    s1, s2 = (torch.empty(2, device=DEV, dtype=torch.float64) for _ in range(2))
+    K.recon_fwd(y, stats, gamma, beta, x, xh1, s1, T, G, kind)
+    emu.recon_fwd(y, stats, gamma, beta, x, xh2, s2, T, G, kind)
+    close(xh1, xh2, 2e-6, "x_hat")
+    close(s1, s2, 1e-5, "loss sums")
+    g_loss = torch.tensor([1.0e6], device=DEV)
+    g_mse = torch.tensor([0.5], device=DEV)
+    ext = rnd(B, N, T, seed=7) * 0.01 if with_ext else None
+    inv = 1.0 / (B * N * T)
+    outs = []
+    for fn in (K.recon_bwd, emu.recon_bwd):
+        dy = torch.full((N, B, Tp), 9.0, device=DEV)
+        dg, db, dbi = (torch.empty(N, device=DEV) for _ in range(3))
+        fn(y, stats, gamma, beta, x, g_loss, g_mse, inv, ext, dy, dg, db, dbi, T, G, kind)
+        outs.append((dy, dg, db, dbi))
+    for a, b, nm in zip(outs[0], outs[1], ("dy", "dgamma", "dbeta", "dbias")):
+        close(a, b, 5e-5, nm)
+    # ext-only path (decoder used without the fused loss)
+    if with_ext:
+        outs = []
+        for fn in (K.recon_bwd, emu.recon_bwd):
+            dy = torch.full((N, B, Tp), 9.0, device=DEV, dtype=torch.bfloat16)
+            dg, db, dbi = (torch.empty(N, device=DEV) for _ in range(3))
+            fn(y, stats, gamma, beta, None, None, None, inv, ext, dy, dg, db, dbi, T, G, kind)
+            outs.append((dy.float(), dg, db, dbi))
+        for a, b, nm in zip(outs[0], outs[1], ("dy", "dgamma", "dbeta", "dbias")):
+            close(a, b, 5e-3, nm)
+
+
+@pytest.mark.parametrize("O", [8, 64])
+def test_head_fwd_bwd(O):
+    C, B, T = 24, 3, 21
+    Tp = tp_of(T)
+    h = cr(C, B, T, seed=1)
+    w = rnd(O, C * T, seed=2, scale=0.1)
+    sigma = torch.tensor([1.7], device=DEV)
+    bias = rnd(O, seed=3)
+    o1, o2 = torch.empty(B, O, device=DEV), torch.empty(B, O, device=DEV)
+    K.head_fwd(h, w, sigma, bias, o1, T)
+    emu.head_fwd(h, w, sigma, bias, o2, T)
+    close(o1, o2, 1e-5, "head")
+    dout = rnd(B, O, seed=4)
+    res = []
+    for fn in (K.head_bwd, emu.head_bwd):
+        dwn, dbias = torch.empty(O, C * T, device=DEV), torch.empty(O, device=DEV)
+        dh = cr(C, B, T, seed=5)
+        fn(h, w, sigma, dout, dwn, dbias, dh, 1, T)
+        res.append((dwn, dbias, dh[:, :, :T]))
+    for a, b, nm in zip(res[0], res[1], ("dwn", "dbias", "dh")):
+        close(a, b, 1e-5, nm)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_latent_fwd_bwd(dtype):
+    D, B, T = 8, 3, 21
+    Tp = tp_of(T)
+    z = rnd(B, D, seed=1)
+    w = rnd(D * T, D, seed=2, scale=0.3)
+    sigma = torch.tensor([0.8], device=DEV)
+    bias = rnd(D * T, seed=3)
+    o1 = torch.full((D, B, Tp), 9.0, device=DEV, dtype=dtype)
+    o2 = torch.empty_like(o1)
+    K.latent_fwd(z, w, sigma, bias, o1, T)
+    emu.latent_fwd(z, w, sigma, bias, o2, T)
+    close(o1.float(), o2.float(), 1e-5 if dtype == torch.float32 else 4e-3, "latent")
+    dact = cr(D, B, T, seed=4)
+    res = []
+    for fn in (K.latent_bwd, emu.latent_bwd):
+        dwn, dbias, dz = torch.empty(D * T, D, device=DEV), torch.empty(D * T, device=DEV), torch.empty(B, D, device=DEV)
+        fn(z, w, sigma, dact, dwn, dbias, dz, T)
+        res.append((dwn, dbias, dz))
+    for a, b, nm in zip(res[0], res[1], ("dwn", "dbias", "dz")):
+        close(a, b, 1e-5, nm)
+
+
+def test_reparam_main():
+    B, L = 5, 32
+    last = rnd(B, 2 * L, seed=1) * 2
+    last[0, L] = 40.0      # exercises the clamp
+    last[1, L + 1] = -40.0
+    last[2, L + 2] = 8.0   # std clamp (exp(4) > 10)
+    eps = rnd(B, L, seed=2)
+    z1, z2 = torch.empty(B, L, device=DEV), torch.empty(B, L, device=DEV)
+    k1, k2 = torch.empty(1, device=DEV), torch.empty(1, device=DEV)
+    K.reparam_main_fwd(last, eps, z1, k1)
+    emu.reparam_main_fwd(last, eps, z2, k2)
+    close(z1, z2, 1e-6, "z")
+    close(k1, k2, 1e-6, "kl")
+    dz, dkl = rnd(B, L, seed=3), torch.tensor([1e-4], device=DEV)
+    d1, d2 = torch.empty_like(last), torch.empty_like(last)
+    K.reparam_main_bwd(last, eps, dz, dkl, d1)
+    emu.reparam_main_bwd(last, eps, dz, dkl, d2)
+    close(d1, d2, 1e-5, "dlast")
+
+
+@pytest.mark.parametrize("std_scale", [1.0, 1e-10])
+def test_kl2_reparam(std_scale):
+    C, B, T = 16, 3, 21
+    Tp = tp_of(T)
+    cz, cxz = cr(2 * C, B, T, seed=1) * 1.5, cr(2 * C, B, T, seed=2) * 1.5
+    cz[C, 0, 0] = 35.0
+    cxz[C + 1, 1, 1] = -35.0
+    cz[C + 2, 0, 2] = 20.0
+    eps = rnd(B, C, T, seed=3)
+    h = cr(C, B, T, seed=4)
+    zs1 = torch.full((C, B, Tp), 9.0, device=DEV, dtype=torch.bfloat16)
+    zs2 = torch.empty_like(zs1)
+    f1, f2 = torch.empty(C, B, Tp, device=DEV), torch.empty(C, B, Tp, device=DEV)
+    k1, k2 = (torch.empty(1, device=DEV, dtype=torch.float64) for _ in range(2))
+    K.kl2_reparam_fwd(cz, cxz, eps, h, std_scale, zs1, f1, k1, T)
+    emu.kl2_reparam_fwd(cz, cxz, eps, h, std_scale, zs2, f2, k2, T)
+    close(f1, f2, 1e-6, "zs")
+    close(zs1.float(), zs2.float(), 4e-3, "zs op")
+    close(k1, k2, 1e-5, "kl sum")
+    dzs = cr(C, B, T, seed=5)
+    dkl = torch.tensor([1e-4], device=DEV)
+    res = []
+    for fn in (K.kl2_reparam_bwd, emu.kl2_reparam_bwd):
+        a, b = torch.full((2 * C, B, Tp), 9.0, device=DEV), torch.full((2 * C, B, Tp), 9.0, device=DEV)
+        fn(cz, cxz, eps, std_scale, dzs, dkl, 0.5 / B, a, b, T)
+        res.append((a, b))
+    close(res[0][0], res[1][0], 1e-5, "dcz")
+    close(res[0][1], res[1][1], 1e-5, "dcxz")
+
+
+def test_philox_normal_statistics_and_batch_split_invariance():
+    B, per = 8, 4099
+    a = torch.empty(B, per, device=DEV)
+    K.philox_normal(a, 1234, 0, 0)
+    assert abs(float(a.mean())) < 0.02 and abs(float(a.std()) - 1.0) < 0.02
+    assert abs(float((a[0] * a[1]).mean())) < 0.05
+    b = torch.empty(B // 2, per, device=DEV)
+    K.philox_normal(b, 1234, 0, 4)          # second half of the batch drawn on "another rank"
+    assert torch.equal(a[4:], b)
+    c = torch.empty(B, per, device=DEV)
+    K.philox_normal(c, 1234, 1, 0)          # another draw
+    assert not torch.equal(a, c)
+    # tails look Gaussian
+    frac = float((a.abs() > 1.96).float().mean())
+    assert 0.04 < frac < 0.06
+
+
+def test_adamw_matches_torch():
+    n = 10007
+    p0, g = rnd(n, seed=1), rnd(n, seed=2)
+    p = p0.clone()
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3)
+    gn = torch.zeros(1, device=DEV, dtype=torch.float64)
+    for step in range(1, 4):
+        ref.grad = g.clone()
+        opt.step()
+        K.adamw_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, 1.0, gn)
+    close(p, ref.detach(), 1e-6, "adamw")
+    assert abs(float(gn) - 3 * float((g.double() ** 2).sum())) / float(gn) < 1e-9

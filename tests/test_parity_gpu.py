@@ -1,0 +1,178 @@
+"""-m gpu: the engine (overlay modules -> C ABI -> CUDA kernels) against the reference's outputs
+(golden fixtures generated from the unmodified reference) and against the oracle at larger sizes.
+
+Tolerances (BASELINE.json north_star): fp32 validation mode 1e-5 relative L2 per tensor (a little
+slack is left for fp32 summation order, stated per assert); bf16 mode 1e-2 per layer on realistic
+channel counts; ELBO curve over 100 steps within 1 %."""
+import os
+
+import pytest
+import torch
+
+import simulgen_vae_b200 as sg
+from conftest import GOLDEN_CASES, GOLDEN_DIR, load_golden, rel_l2
+from oracle import vae_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def build_engine_vae(cfg, state_dict=None, seed=0):
+    VAE = sg.load_vae_class()
+    from modules.common import add_sn, initialize_weights_He
+    torch.manual_seed(seed)
+    m = VAE(cfg["latent_dim"], cfg["hierarchical_dim"], list(cfg["enc"]), list(cfg["enc"])[::-1], cfg["num_node"],
+            cfg["num_time"], lossfun=cfg.get("lossfun", "MSE"), batch_size=cfg.get("batch", 1), small=cfg.get("small", True))
+    m.apply(initialize_weights_He)
+    m.apply(add_sn)
+    if state_dict is not None:
+        m.load_state_dict(state_dict)
+    return m.to(DEV)
+
+
+@pytest.fixture(autouse=True)
+def _restore_precision():
+    yield
+    sg.set_precision("bf16")
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_fp32_mode_matches_reference_golden(name):
+    g = load_golden(name)
+    cfg = g["cfg"]
+    sg.set_precision("fp32")
+    m = build_engine_vae(cfg, g["state_dict"])
+    m.train(True)
+    with sg.fixed_eps(g["eps"]):
+        x_hat, rl, kls, mse = m(g["x"].to(DEV))
+    (rl * g["alpha"] + sum(kls) * g["beta"]).backward()
+    assert rel_l2(x_hat, g["ref"]["x_hat"]) < 1e-5
+    assert rel_l2(rl, g["ref"]["recon"]) < 1e-5
+    assert rel_l2(mse, g["ref"]["mse"]) < 1e-5
+    for a, b in zip(kls, g["ref"]["kls"]):
+        assert rel_l2(a, b) < 1e-5
+    for n, p in m.named_parameters():
+        gref = g["grads"][n]
+        if gref is None:
+            assert p.grad is None, n
+        else:
+            assert rel_l2(p.grad, gref) < 5e-5, (n, rel_l2(p.grad, gref))     # 1e-5 target + summation-order slack
+    sd = m.state_dict()
+    for k, v in g["uv_after"].items():
+        assert rel_l2(sd[k], v) < 1e-5, k
+    # eval mode: no power iteration, same outputs as the reference's eval forward
+    m.eval()
+    with torch.no_grad(), sg.fixed_eps(g["eps"]):
+        xe, rle, _, _ = m(g["x"].to(DEV))
+    assert rel_l2(xe, g["ref_eval"]["x_hat"]) < 1e-5
+    assert rel_l2(rle, g["ref_eval"]["recon"]) < 1e-5
+    for k, v in g["uv_after"].items():
+        assert torch.equal(m.state_dict()[k].cpu(), sd[k].cpu()), k
+
+
+@pytest.mark.parametrize("name", ["toy3_small_mse", "toy4_small_huber"])
+def test_bf16_mode_close_to_reference_golden(name):
+    """Toy channel counts (8..80) give little averaging, so the bf16 bound here is loose; the
+    realistic-size bound is test_bf16_per_layer_parity_medium."""
+    g = load_golden(name)
+    cfg = g["cfg"]
+    sg.set_precision("bf16")
+    m = build_engine_vae(cfg, g["state_dict"])
+    m.train(True)
+    with sg.fixed_eps(g["eps"]):
+        x_hat, rl, kls, mse = m(g["x"].to(DEV))
+    (rl * g["alpha"] + sum(kls) * g["beta"]).backward()
+    assert rel_l2(x_hat, g["ref"]["x_hat"]) < 2e-2
+    assert rel_l2(rl, g["ref"]["recon"]) < 2e-2
+    for a, b in zip(kls, g["ref"]["kls"]):
+        assert rel_l2(a, b) < 2e-2
+    for n, p in m.named_parameters():
+        gref = g["grads"][n]
+        if gref is not None:
+            assert rel_l2(p.grad, gref) < 8e-2, (n, rel_l2(p.grad, gref))
+
+
+MEDIUM = dict(latent_dim=32, hierarchical_dim=8, enc=[256, 128, 64, 32], num_node=1024, num_time=200, small=True,
+              batch=4, lossfun="MSE")
+
+
+def _oracle_on_gpu(cfg, sd, x, eps):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    p = O.params_from_state_dict({k: v.to(DEV) for k, v in sd.items()})
+    acts = {}
+    xh, rl, kls, mse = O.vae_forward(p, x, eps, cfg["latent_dim"], cfg["lossfun"], training=True, acts=acts)
+    O.total_loss(rl, kls, 1e6, 1e-4).backward()
+    return p, acts, xh, rl, kls, mse
+
+
+@pytest.mark.parametrize("precision,tol_act,tol_grad", [("fp32", 1e-5, 1e-4), ("bf16", 1e-2, 3e-2)])
+def test_per_layer_parity_medium(precision, tol_act, tol_grad):
+    cfg = MEDIUM
+    sg.set_precision(precision)
+    m = build_engine_vae(cfg, seed=5)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    B = cfg["batch"]
+    x = O.synthetic_field(B, cfg["num_node"], cfg["num_time"], seed=3).to(DEV)
+    g = torch.Generator().manual_seed(1)
+    eps = [torch.randn(s, generator=g).to(DEV) for s in O.eps_shapes(cfg, B)]
+    p, acts, oxh, orl, okls, omse = _oracle_on_gpu(cfg, sd, x, eps)
+    cap = {}
+    m.train(True)
+    with sg.fixed_eps(eps):
+        x_hat, rl, kls, mse = m(x, _capture=cap)
+    (rl * 1e6 + sum(kls) * 1e-4).backward()
+    report = []
+    for name, t in cap.items():
+        if name in acts:
+            report.append((name, rel_l2(t, acts[name])))
+    report.append(("x_hat", rel_l2(x_hat, oxh)))
+    report.append(("recon", rel_l2(rl, orl)))
+    for i, (a, b) in enumerate(zip(kls, okls)):
+        report.append(("kl%d" % i, rel_l2(a, b)))
+    greport = []
+    for n, prm in m.named_parameters():
+        og = p[n].grad
+        if og is None:
+            assert prm.grad is None, n
+        else:
+            greport.append((n, rel_l2(prm.grad, og)))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_medium_%s.txt" % precision, "w") as f:
+        for n, e in report + greport:
+            f.write("%-70s %.3e\n" % (n, e))
+    worst_a = max(e for _, e in report)
+    worst_g = max(e for _, e in greport)
+    print(precision, "worst activation", worst_a, "worst grad", worst_g)
+    assert worst_a < tol_act, [r for r in report if r[1] >= tol_act]
+    assert worst_g < tol_grad, [r for r in greport if r[1] >= tol_grad]
+
+
+def test_elbo_curve_100_steps_within_1_percent():
+    """train.py:139-168 step semantics for 100 steps on the toy fixture; bf16 engine vs the
+    reference's recorded curve (same data, same eps stream, torch AdamW on both sides)."""
+    g = torch.load(os.path.join(GOLDEN_DIR, "elbo_curve_toy3.pt"), weights_only=False)
+    cfg = g["cfg"]
+    for precision, tol in (("fp32", 1e-3), ("bf16", 1e-2)):
+        sg.set_precision(precision)
+        m = build_engine_vae(cfg, g["state_dict"])
+        opt = torch.optim.AdamW(m.parameters(), lr=g["lr"])
+        data = g["data"].to(DEV)
+        B = cfg["batch"]
+        m.train(True)
+        curve = []
+        for step in range(100):
+            xb = data[(step % 2) * B:(step % 2) * B + B]
+            opt.zero_grad(set_to_none=True)
+            with sg.fixed_eps(g["eps"][step]):
+                _, rl, kls, _ = m(xb)
+            beta = O.warmup_beta(step // 10, g["epochs"])
+            loss = rl * g["alpha"] + sum(kls) * beta
+            loss.backward()
+            opt.step()
+            curve.append(float(loss))
+        ref = torch.tensor(g["loss"])
+        cur = torch.tensor(curve)
+        dev = ((cur - ref).abs() / ref.abs()).max()
+        print(precision, "max ELBO deviation over 100 steps: %.3e" % float(dev))
+        assert float(dev) < tol, (precision, float(dev))
