@@ -18,6 +18,10 @@
  *   - internal activation layout "CR": [C][B][Tp] with Tp = roundup(T + 2, 8); entries t >= T of
  *     every (c, b) row are zero (they are the conv "same" padding shared by neighbouring samples),
  *     R = B * Tp.  External layout (reference): [B][C][T] fp32 (SimulGen-VAE.py:281-283).
+ *   - GEMM operands (activations / output gradients that feed a k-tap conv) are stored as `planes`
+ *     (1, 3 or 5 >= k) pre-shifted copies: op[pl][c][b][t] = value[c][b][t + pl - planes/2], zero outside
+ *     [0, T); `plane_stride` is the element distance between planes.  TMA moves 16-byte granules, so
+ *     a tap cannot be a 1-element shift of a box along the contiguous axis; it selects a plane.
  *   - conv weights in GEMM layout "Wg": [k][Cout][Cin_p], Cin_p = roundup(Cin, 8), already divided
  *     by the spectral norm sigma; ConvTranspose1d weights are stored as the equivalent Conv1d
  *     (taps flipped, channels swapped; decoder.py:31).
@@ -75,12 +79,13 @@ int sg_sn_weight_grad(const float* dwg, const float* w_orig, const float* u, con
  * wgrad: dWg[j][Cout][Cin_p] (fp32) = sum_r dy[co][r] * act[ci][r + j - k/2]
  * act / dy / Wg are `dtype` (bf16: tcgen05 + TMA kernels; fp32: SIMT validation kernels).
  * R % 8 == 0 and Cin_p % 8 == 0 are required (TMA global strides are multiples of 16 bytes).  */
-int sg_conv_fprop(const void* wg, const void* act, const float* bias, float* out, int Cin, int Cin_p, int Cout,
-                  int k, int R, int accumulate, int dtype, void* stream);
-int sg_conv_dgrad(const void* wg, const void* dy, float* dx, int Cin, int Cin_p, int Cout, int k, int R,
-                  int accumulate, int dtype, void* stream);
-int sg_conv_wgrad(const void* dy, const void* act, float* dwg, int Cin, int Cin_p, int Cout, int k, int R,
-                  int dtype, void* stream);
+int sg_conv_fprop(const void* wg, const void* act, int act_planes, long long act_plane_stride, const float* bias,
+                  float* out, int Cin, int Cin_p, int Cout, int k, int R, int accumulate, int dtype, void* stream);
+int sg_conv_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_plane_stride, float* dx, int Cin,
+                  int Cin_p, int Cout, int k, int R, int accumulate, int dtype, void* stream);
+int sg_conv_wgrad(const void* dy, int dy_planes, long long dy_plane_stride, const void* act, int act_planes,
+                  long long act_plane_stride, float* dwg, int Cin, int Cin_p, int Cout, int k, int R, int dtype,
+                  void* stream);
 
 /* ---- GroupNorm + activation + residual (encoder.py:35-36, common.py:85-102, decoder.py:32,119-120)
  * stats[B][G][2] doubles = (sum, sum of squares) over the group's (C/G) x T valid entries. */
@@ -89,14 +94,15 @@ int sg_gn_stats(const float* y, double* stats, int C, int B, int T, int Tp, int 
  * out = post_gelu ? gelu(pre) : pre ; written as operand (out_op, dtype, gap zeroed) and/or fp32. */
 int sg_gn_act_fwd(const float* y, const double* stats, const float* gamma, const float* beta,
                   const void* res, int res_is_f32, float res_scale, int act, int post_gelu,
-                  void* out_op, float* out_f32, int C, int B, int T, int Tp, int G, int dtype, void* stream);
+                  void* out_op, int planes, long long plane_stride, float* out_f32,
+                  int C, int B, int T, int Tp, int G, int dtype, void* stream);
 /* Backward of the above.  dout fp32 [C][B][Tp].  Writes dy (dtype, gap zeroed) = grad wrt y,
  * dgamma/dbeta (may be NULL when stats == NULL), dbias[C] = sum_{b,t} dy, and dres (fp32,
  * (+)= per dres_accumulate) when res != NULL.  ws: >= 2*B*G doubles. */
 int sg_gn_act_bwd(const float* y, const double* stats, const float* gamma, const float* beta,
                   const void* res, int res_is_f32, float res_scale, int act, int post_gelu,
-                  const float* dout, void* dy, float* dgamma, float* dbeta, float* dbias,
-                  float* dres, int dres_accumulate, double* ws,
+                  const float* dout, void* dy, int planes, long long plane_stride,
+                  float* dgamma, float* dbeta, float* dbias, float* dres, int dres_accumulate, double* ws,
                   int C, int B, int T, int Tp, int G, int dtype, void* stream);
 
 /* ---- reconstruction head: Tanh(GroupNorm(y)) + losses (decoder.py:117-121, VAE_network.py:71-77,110-111)
@@ -105,7 +111,8 @@ int sg_gn_act_bwd(const float* y, const double* stats, const float* gamma, const
 int sg_recon_fwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* x,
                  float* x_hat, double* loss_sums, int N, int B, int T, int Tp, int G, int loss_kind, void* stream);
 /* dx_hat = g_loss[0]*inv_numel*loss'(x_hat-x) + g_mse[0]*inv_numel*2(x_hat-x) + dxhat_ext (each optional),
- * then backward through tanh and GroupNorm -> dy (dtype) , dgamma, dbeta, dbias.  ws: >= 2*B*G doubles. */
+ * then backward through tanh and GroupNorm -> dy (dtype, 1 plane), dgamma, dbeta, dbias.
+ * ws: >= 2*B*G + 2 doubles. */
 int sg_recon_bwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* x,
                  const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext,
                  void* dy, float* dgamma, float* dbeta, float* dbias, double* ws,
@@ -123,7 +130,7 @@ int sg_head_bwd(const float* h, const float* w_orig, const float* sigma, const f
                 float* dbias, float* dh, int dh_accumulate, int C, int B, int T, int Tp, int O, void* stream);
 /* latent: out[d][b][t] = (sum_e w_orig[d*T+t][e] * z[b][e]) / sigma + bias[d*T+t]   (Linear + Unflatten) */
 int sg_latent_fwd(const float* z, const float* w_orig, const float* sigma, const float* bias, void* out,
-                  int D, int B, int T, int Tp, int dtype, void* stream);
+                  int planes, long long plane_stride, int D, int B, int T, int Tp, int dtype, void* stream);
 int sg_latent_bwd(const float* z, const float* w_orig, const float* sigma, const float* dact, float* dwn,
                   float* dbias, float* dz, int D, int B, int T, int Tp, void* stream);
 
@@ -137,8 +144,8 @@ int sg_reparam_main_bwd(const float* last, const float* eps, const float* dz, co
  * z = (mu+dmu) + eps*clamp(std_scale*exp(.5 clamp(lv+dlv)),1e-8,10); zs = h + z (h fp32 [C][B][Tp]);
  * kl_sum[0] (double, zeroed inside) = sum of the kl_2 integrand (caller scales by .5/B). */
 int sg_kl2_reparam_fwd(const float* cz, const float* cxz, const float* eps, const float* h, float std_scale,
-                       void* zs_op, float* zs_f32, double* kl_sum, int C, int B, int T, int Tp, int dtype,
-                       void* stream);
+                       void* zs_op, int planes, long long plane_stride, float* zs_f32, double* kl_sum,
+                       int C, int B, int T, int Tp, int dtype, void* stream);
 /* dzs fp32 [C][B][Tp] (or NULL); dkl = d/d(kl_2 value) (device scalar or NULL), kl_scale = .5/B;
  * writes dcz, dcxz fp32 [2C][B][Tp] (gap zeroed) = gradients wrt the two condition-conv outputs. */
 int sg_kl2_reparam_bwd(const float* cz, const float* cxz, const float* eps, float std_scale, const float* dzs,

@@ -70,6 +70,40 @@ __device__ __forceinline__ void from_f(float& d, float x) { d = x; }
 __device__ __forceinline__ void from_f(__nv_bfloat16& d, float x) { d = __float2bfloat16_rn(x); }
 
 // ---------------------------------------------------------------------------------------------
+// shifted operand planes.  TMA moves 16-byte granules, so a conv tap cannot be a 1-element shift of
+// the box along the contiguous r axis.  Operands that feed a k-tap conv are therefore stored as k
+// "planes": plane[pl][c][b][t] = value[c][b][t + pl - planes/2] (zero outside [0, T)), and tap j of
+// the conv simply selects a plane (an aligned TMA coordinate).  Rows are independent: the shift
+// never crosses a sample because the gap t >= T is zero.
+//
+// srow: per-warp smem buffer of Tp + 8 floats; the row lives at srow[4 + t] (zero for t >= T) with
+// 4 zero floats of halo on both sides.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void srow_clear_halo(float* srow, int Tp, int lane) {
+    if (lane < 4) srow[lane] = 0.f;
+    else if (lane < 8) srow[Tp + lane] = 0.f;
+}
+
+template <typename OT>
+__device__ __forceinline__ void store_row_planes(OT* base, long long row_off, int planes, long long pstride,
+                                                 const float* srow, int T, int Tp, int lane) {
+    const int half = planes / 2;
+    for (int pl = 0; pl < planes; ++pl) {
+        const int s = pl - half;
+        OT* dst = base + (long long)pl * pstride + row_off;
+        for (int seg = lane; seg < Tp / 8; seg += 32) {
+            F8 o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int t = seg * 8 + i;
+                o.v[i] = (t < T) ? srow[4 + t + s] : 0.f;
+            }
+            store8(dst + seg * 8, o);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------
 template <typename T>

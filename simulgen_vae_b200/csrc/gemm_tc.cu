@@ -12,9 +12,11 @@
 // One persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+ TMEM
 // alloc), warps 2-5 = epilogue (TMEM -> registers -> global).  Tile 128 x 256 x 64, 4 smem stages
 // (48 KB each, 128B-swizzled TMA boxes of 64 x 64 bf16), two 256-column fp32 accumulators in TMEM
-// so the epilogue of tile i overlaps the main loop of tile i+1.  Conv taps are K-blocks whose TMA
-// coordinates are shifted along r; out-of-bounds box elements are zero-filled by TMA, which is the
-// zero padding of the convolution and the ragged-edge handling in one mechanism.
+// so the epilogue of tile i overlaps the main loop of tile i+1.  Out-of-bounds box elements are
+// zero-filled by TMA (ragged edges need no special code).  TMA moves 16-byte granules, so a conv tap
+// cannot be a 1-element shift of a box along the contiguous r axis: operands of k-tap convs are stored
+// as k pre-shifted planes (common.cuh, store_row_planes) and tap j selects a plane through the third
+// TMA coordinate - the conv's zero padding is already baked into the planes.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -45,6 +47,8 @@ struct TcParams {
     int accumulate;      // out += result
     int atomic;          // split-K: red.add into out
     int m_fastest;
+    int b_plane0, b_plane_step;   // B operand plane for tap j (or output tap z): b_plane0 + j * b_plane_step
+    int a_plane;                  // wgrad: plane of dy that holds the unshifted gradient
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -217,19 +221,22 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         tma_load_3d(&tmA, &full_bar[stage], sa + BOX_BYTES, k0, wk.m0 + 64, j);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            tma_load_2d(&tmB, &full_bar[stage], sb + i * BOX_BYTES, wk.n0 + 64 * i + j - p.pad, k0);
+                            tma_load_3d(&tmB, &full_bar[stage], sb + i * BOX_BYTES, wk.n0 + 64 * i, k0,
+                                        p.b_plane0 + j * p.b_plane_step);
                     } else if (MODE == MODE_DGRAD) {
                         tma_load_3d(&tmA, &full_bar[stage], sa, wk.m0, k0, j);
                         tma_load_3d(&tmA, &full_bar[stage], sa + BOX_BYTES, wk.m0 + 64, k0, j);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            tma_load_2d(&tmB, &full_bar[stage], sb + i * BOX_BYTES, wk.n0 + 64 * i - j + p.pad, k0);
+                            tma_load_3d(&tmB, &full_bar[stage], sb + i * BOX_BYTES, wk.n0 + 64 * i, k0,
+                                        p.b_plane0 + j * p.b_plane_step);
                     } else {
-                        tma_load_2d(&tmA, &full_bar[stage], sa, k0, wk.m0);
-                        tma_load_2d(&tmA, &full_bar[stage], sa + BOX_BYTES, k0, wk.m0 + 64);
+                        tma_load_3d(&tmA, &full_bar[stage], sa, k0, wk.m0, p.a_plane);
+                        tma_load_3d(&tmA, &full_bar[stage], sa + BOX_BYTES, k0, wk.m0 + 64, p.a_plane);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            tma_load_2d(&tmB, &full_bar[stage], sb + i * BOX_BYTES, k0 + wk.z - p.pad, wk.n0 + 64 * i);
+                            tma_load_3d(&tmB, &full_bar[stage], sb + i * BOX_BYTES, k0, wk.n0 + 64 * i,
+                                        p.b_plane0 + wk.z * p.b_plane_step);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -350,19 +357,21 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D bf16 [rows][cols] (cols contiguous), box 64 x 64, 128B swizzle, zero OOB fill
-static int make_map_2d(CUtensorMap* m, const void* base, long long cols, long long rows, long long pitch_elems) {
+// 3-D bf16 operand [planes][rows][cols] (cols contiguous), box 64 x 64 x 1, 128B swizzle, zero OOB fill
+static int make_map_op(CUtensorMap* m, const void* base, long long cols, long long rows, int planes,
+                       long long plane_stride_elems) {
     EncodeTiledFn fn = get_encode_fn();
     SG_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
-    cuuint32_t box[2] = {64, 64};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    SG_REQUIRE(planes == 1 || plane_stride_elems % 8 == 0, "operand plane stride must be a multiple of 8 elements");
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)(planes > 1 ? plane_stride_elems : cols * rows) * 2};
+    cuuint32_t box[3] = {64, 64, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d) failed: %d (cols=%lld rows=%lld pitch=%lld base=%p)", (int)r,
-               cols, rows, pitch_elems, base);
+    SG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(op) failed: %d (cols=%lld rows=%lld planes=%d pstride=%lld base=%p)",
+               (int)r, cols, rows, planes, plane_stride_elems, base);
     return 0;
 }
 
@@ -422,15 +431,16 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, cud
     return check_launch("conv_gemm_tc");
 }
 
-int tc_fprop(const void* wg, const void* act, const float* bias, float* out, int Cin, int Cin_p, int Cout, int k, int R,
-             int accumulate, cudaStream_t st) {
+int tc_fprop(const void* wg, const void* act, int act_planes, long long act_pstride, const float* bias, float* out,
+             int Cin, int Cin_p, int Cout, int k, int R, int accumulate, cudaStream_t st) {
     CUtensorMap ma, mb;
     if (make_map_wg(&ma, wg, Cin_p, Cout, k)) return 1;
-    if (make_map_2d(&mb, act, R, Cin, R)) return 1;
+    if (make_map_op(&mb, act, R, Cin, act_planes, act_pstride)) return 1;
     TcParams p{};
     p.out = out; p.bias = bias; p.M = Cout; p.N = R; p.ldc = R; p.c_sz = 0;
     p.m_tiles = (int)cdiv(Cout, BM); p.n_tiles = (int)cdiv(R, BN); p.z_count = 1;
     p.taps = k; p.kblocks = (int)cdiv(Cin, BK); p.pad = k / 2; p.accumulate = accumulate;
+    p.b_plane0 = act_planes / 2 - k / 2; p.b_plane_step = 1; p.a_plane = 0;
     p.splits = pick_splits(p.m_tiles * p.n_tiles, p.taps * p.kblocks);
     p.atomic = p.splits > 1;
     p.m_fastest = p.m_tiles <= p.n_tiles;
@@ -438,15 +448,16 @@ int tc_fprop(const void* wg, const void* act, const float* bias, float* out, int
     return launch_tc<MODE_FPROP>(ma, mb, p, st);
 }
 
-int tc_dgrad(const void* wg, const void* dy, float* dx, int Cin, int Cin_p, int Cout, int k, int R, int accumulate,
-             cudaStream_t st) {
+int tc_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_pstride, float* dx, int Cin, int Cin_p,
+             int Cout, int k, int R, int accumulate, cudaStream_t st) {
     CUtensorMap ma, mb;
     if (make_map_wg(&ma, wg, Cin_p, Cout, k)) return 1;
-    if (make_map_2d(&mb, dy, R, Cout, R)) return 1;
+    if (make_map_op(&mb, dy, R, Cout, dy_planes, dy_pstride)) return 1;
     TcParams p{};
     p.out = dx; p.bias = nullptr; p.M = Cin; p.N = R; p.ldc = R; p.c_sz = 0;
     p.m_tiles = (int)cdiv(Cin, BM); p.n_tiles = (int)cdiv(R, BN); p.z_count = 1;
     p.taps = k; p.kblocks = (int)cdiv(Cout, BK); p.pad = k / 2; p.accumulate = accumulate;
+    p.b_plane0 = dy_planes / 2 + k / 2; p.b_plane_step = -1; p.a_plane = 0;
     p.splits = pick_splits(p.m_tiles * p.n_tiles, p.taps * p.kblocks);
     p.atomic = p.splits > 1;
     p.m_fastest = p.m_tiles <= p.n_tiles;
@@ -454,14 +465,16 @@ int tc_dgrad(const void* wg, const void* dy, float* dx, int Cin, int Cin_p, int 
     return launch_tc<MODE_DGRAD>(ma, mb, p, st);
 }
 
-int tc_wgrad(const void* dy, const void* act, float* dwg, int Cin, int Cin_p, int Cout, int k, int R, cudaStream_t st) {
+int tc_wgrad(const void* dy, int dy_planes, long long dy_pstride, const void* act, int act_planes,
+             long long act_pstride, float* dwg, int Cin, int Cin_p, int Cout, int k, int R, cudaStream_t st) {
     CUtensorMap ma, mb;
-    if (make_map_2d(&ma, dy, R, Cout, R)) return 1;
-    if (make_map_2d(&mb, act, R, Cin, R)) return 1;
+    if (make_map_op(&ma, dy, R, Cout, dy_planes, dy_pstride)) return 1;
+    if (make_map_op(&mb, act, R, Cin, act_planes, act_pstride)) return 1;
     TcParams p{};
     p.out = dwg; p.bias = nullptr; p.M = Cout; p.N = Cin_p; p.ldc = Cin_p; p.c_sz = (long long)Cout * Cin_p;
     p.m_tiles = (int)cdiv(Cout, BM); p.n_tiles = (int)cdiv(Cin_p, BN); p.z_count = k;
     p.taps = 1; p.kblocks = (int)cdiv(R, BK); p.pad = k / 2; p.accumulate = 0;
+    p.b_plane0 = act_planes / 2 - k / 2; p.b_plane_step = 1; p.a_plane = dy_planes / 2;
     p.splits = pick_splits(p.m_tiles * p.n_tiles * k, p.kblocks);
     p.atomic = p.splits > 1;
     p.m_fastest = p.m_tiles <= p.n_tiles;
@@ -480,28 +493,39 @@ using namespace sg;
 
 extern "C" {
 
-int sg_conv_fprop(const void* wg, const void* act, const float* bias, float* out, int Cin, int Cin_p, int Cout, int k,
-                  int R, int accumulate, int dtype, void* stream) {
-    SG_REQUIRE(R % 8 == 0 && Cin_p % 8 == 0 && Cin_p >= Cin && (k & 1), "conv_fprop: bad shape Cin=%d Cin_p=%d k=%d R=%d", Cin, Cin_p, k, R);
+#define SG_CONV_CHECK(name, planes)                                                                                   \
+    SG_REQUIRE(R % 8 == 0 && Cin_p % 8 == 0 && Cin_p >= Cin && (k & 1) && (planes) >= k && ((planes) & 1),            \
+               name ": bad shape Cin=%d Cin_p=%d k=%d R=%d planes=%d", Cin, Cin_p, k, R, (planes))
+
+int sg_conv_fprop(const void* wg, const void* act, int act_planes, long long act_pstride, const float* bias,
+                  float* out, int Cin, int Cin_p, int Cout, int k, int R, int accumulate, int dtype, void* stream) {
+    SG_CONV_CHECK("conv_fprop", act_planes);
     if (dtype == SG_F32)
-        return simt_fprop((const float*)wg, (const float*)act, bias, out, Cin, Cin_p, Cout, k, R, accumulate, as_stream(stream));
-    return tc_fprop(wg, act, bias, out, Cin, Cin_p, Cout, k, R, accumulate, as_stream(stream));
+        return simt_fprop((const float*)wg, (const float*)act + (long long)(act_planes / 2) * act_pstride, bias, out, Cin,
+                          Cin_p, Cout, k, R, accumulate, as_stream(stream));
+    return tc_fprop(wg, act, act_planes, act_pstride, bias, out, Cin, Cin_p, Cout, k, R, accumulate, as_stream(stream));
 }
 
-int sg_conv_dgrad(const void* wg, const void* dy, float* dx, int Cin, int Cin_p, int Cout, int k, int R, int accumulate,
-                  int dtype, void* stream) {
-    SG_REQUIRE(R % 8 == 0 && Cin_p % 8 == 0 && Cin_p >= Cin && (k & 1), "conv_dgrad: bad shape Cin=%d Cin_p=%d k=%d R=%d", Cin, Cin_p, k, R);
+int sg_conv_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_pstride, float* dx, int Cin, int Cin_p,
+                  int Cout, int k, int R, int accumulate, int dtype, void* stream) {
+    SG_CONV_CHECK("conv_dgrad", dy_planes);
     if (dtype == SG_F32)
-        return simt_dgrad((const float*)wg, (const float*)dy, dx, Cin, Cin_p, Cout, k, R, accumulate, as_stream(stream));
-    return tc_dgrad(wg, dy, dx, Cin, Cin_p, Cout, k, R, accumulate, as_stream(stream));
+        return simt_dgrad((const float*)wg, (const float*)dy + (long long)(dy_planes / 2) * dy_pstride, dx, Cin, Cin_p,
+                          Cout, k, R, accumulate, as_stream(stream));
+    return tc_dgrad(wg, dy, dy_planes, dy_pstride, dx, Cin, Cin_p, Cout, k, R, accumulate, as_stream(stream));
 }
 
-int sg_conv_wgrad(const void* dy, const void* act, float* dwg, int Cin, int Cin_p, int Cout, int k, int R, int dtype,
+int sg_conv_wgrad(const void* dy, int dy_planes, long long dy_pstride, const void* act, int act_planes,
+                  long long act_pstride, float* dwg, int Cin, int Cin_p, int Cout, int k, int R, int dtype,
                   void* stream) {
-    SG_REQUIRE(R % 8 == 0 && Cin_p % 8 == 0 && Cin_p >= Cin && (k & 1), "conv_wgrad: bad shape Cin=%d Cin_p=%d k=%d R=%d", Cin, Cin_p, k, R);
+    SG_CONV_CHECK("conv_wgrad", act_planes);
+    SG_REQUIRE(dy_planes & 1, "conv_wgrad: dy_planes must be odd");
     if (dtype == SG_F32)
-        return simt_wgrad((const float*)dy, (const float*)act, dwg, Cin, Cin_p, Cout, k, R, as_stream(stream));
-    return tc_wgrad(dy, act, dwg, Cin, Cin_p, Cout, k, R, as_stream(stream));
+        return simt_wgrad((const float*)dy + (long long)(dy_planes / 2) * dy_pstride,
+                          (const float*)act + (long long)(act_planes / 2) * act_pstride, dwg, Cin, Cin_p, Cout, k, R,
+                          as_stream(stream));
+    return tc_wgrad(dy, dy_planes, dy_pstride, act, act_planes, act_pstride, dwg, Cin, Cin_p, Cout, k, R,
+                    as_stream(stream));
 }
 
 }  // extern "C"

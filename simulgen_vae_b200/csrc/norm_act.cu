@@ -115,11 +115,15 @@ template <typename OT, typename RT>
 __global__ void __launch_bounds__(kThreads)
 gn_act_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
                   const float* __restrict__ beta, const RT* __restrict__ res, float res_scale, int act, int post_gelu,
-                  OT* __restrict__ out_op, float* __restrict__ out_f32, int C, int B, int T, int Tp, int G,
-                  double inv_n) {
+                  OT* __restrict__ out_op, int planes, long long pstride, float* __restrict__ out_f32, int C, int B,
+                  int T, int Tp, int G, double inv_n) {
+    extern __shared__ float sg_rows[];
     long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (row >= (long long)C * B) return;
     int lane = threadIdx.x & 31;
+    float* srow = sg_rows + (threadIdx.x >> 5) * (Tp + 8);
+    const bool multi = planes > 1 && out_op != nullptr;
+    if (multi) srow_clear_halo(srow, Tp, lane);
     int c = (int)(row / B), b = (int)(row % B);
     float a = 1.f, sh = 0.f;
     if (stats != nullptr) {
@@ -140,8 +144,17 @@ gn_act_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats,
             if (post_gelu) pre = gelu_f(pre);
             o.v[i] = (seg * 8 + i < T) ? pre : 0.f;
         }
-        if (out_op != nullptr) store8(out_op + row * Tp + seg * 8, o);
+        if (multi) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) srow[4 + seg * 8 + i] = o.v[i];
+        } else if (out_op != nullptr) {
+            store8(out_op + row * Tp + seg * 8, o);
+        }
         if (out_f32 != nullptr) store8(out_f32 + row * Tp + seg * 8, o);
+    }
+    if (multi) {
+        __syncwarp();
+        store_row_planes(out_op, row * Tp, planes, pstride, srow, T, Tp, lane);
     }
 }
 
@@ -254,11 +267,15 @@ gn_bwd_reduce_kernel(BwdArgs p, float* __restrict__ dgamma, float* __restrict__ 
 
 template <typename OT, typename RT, bool LOSS>
 __global__ void __launch_bounds__(kThreads)
-gn_bwd_apply_kernel(BwdArgs p, const double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias,
-                    float* __restrict__ dres, int dres_accumulate) {
+gn_bwd_apply_kernel(BwdArgs p, const double* __restrict__ S, OT* __restrict__ dy, int planes, long long pstride,
+                    float* __restrict__ dbias, float* __restrict__ dres, int dres_accumulate) {
+    extern __shared__ float sg_rows[];
     long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (row >= (long long)p.C * p.B) return;
     int lane = threadIdx.x & 31;
+    float* srow = sg_rows + (threadIdx.x >> 5) * (p.Tp + 8);
+    const bool multi = planes > 1;
+    if (multi) srow_clear_halo(srow, p.Tp, lane);
     int c = (int)(row / p.B), b = (int)(row % p.B);
     float a = 1.f, sh = 0.f, mean = 0.f, rstd = 1.f, gm = 1.f, m1 = 0.f, m2 = 0.f;
     bool has_gn = p.stats != nullptr;
@@ -284,7 +301,12 @@ gn_bwd_apply_kernel(BwdArgs p, const double* __restrict__ S, OT* __restrict__ dy
             o.v[i] = v;
             db += v;
         }
-        store8(dy + row * p.Tp + seg * 8, o);
+        if (multi) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) srow[4 + seg * 8 + i] = o.v[i];
+        } else {
+            store8(dy + row * p.Tp + seg * 8, o);
+        }
         if (dres != nullptr) {
             float* dr = dres + row * p.Tp + seg * 8;
             if (dres_accumulate) {
@@ -297,6 +319,10 @@ gn_bwd_apply_kernel(BwdArgs p, const double* __restrict__ S, OT* __restrict__ dy
     }
     db = warp_sum(db);
     if (lane == 0 && dbias != nullptr) atomicAdd(&dbias[c], db);
+    if (multi) {
+        __syncwarp();
+        store_row_planes(dy, row * p.Tp, planes, pstride, srow, p.T, p.Tp, lane);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -346,8 +372,9 @@ recon_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats, 
 static int rows_grid(long long rows) { return (int)cdiv(rows, kWarpsPerBlock); }
 
 template <typename OT>
-static int launch_gn_bwd(BwdArgs p, bool loss, int res_is_f32, OT* dy, float* dgamma, float* dbeta, float* dbias,
-                         float* dres, int dres_accumulate, double* ws, cudaStream_t st) {
+static int launch_gn_bwd(BwdArgs p, bool loss, int res_is_f32, OT* dy, int planes, long long pstride, float* dgamma,
+                         float* dbeta, float* dbias, float* dres, int dres_accumulate, double* ws, cudaStream_t st) {
+    size_t sm = planes > 1 ? sizeof(float) * kWarpsPerBlock * (p.Tp + 8) : 0;
     long long rows = (long long)p.C * p.B;
     bool has_gn = p.stats != nullptr;
     if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * p.C, st);
@@ -360,7 +387,8 @@ static int launch_gn_bwd(BwdArgs p, bool loss, int res_is_f32, OT* dy, float* dg
 #define SG_LAUNCH_BWD(RT, LOSS)                                                                                  \
     do {                                                                                                         \
         if (has_gn) gn_bwd_reduce_kernel<RT, LOSS><<<grid, kThreads, 0, st>>>(p, dgamma, dbeta, ws);             \
-        gn_bwd_apply_kernel<OT, RT, LOSS><<<grid, kThreads, 0, st>>>(p, ws, dy, dbias, dres, dres_accumulate);   \
+        gn_bwd_apply_kernel<OT, RT, LOSS><<<grid, kThreads, sm, st>>>(p, ws, dy, planes, pstride, dbias, dres,   \
+                                                                      dres_accumulate);                          \
     } while (0)
     if (loss) {
         SG_LAUNCH_BWD(float, true);
@@ -428,9 +456,11 @@ int sg_gn_stats(const float* y, double* stats, int C, int B, int T, int Tp, int 
 }
 
 int sg_gn_act_fwd(const float* y, const double* stats, const float* gamma, const float* beta, const void* res,
-                  int res_is_f32, float res_scale, int act, int post_gelu, void* out_op, float* out_f32, int C, int B,
-                  int T, int Tp, int G, int dtype, void* stream) {
+                  int res_is_f32, float res_scale, int act, int post_gelu, void* out_op, int planes,
+                  long long plane_stride, float* out_f32, int C, int B, int T, int Tp, int G, int dtype, void* stream) {
     SG_REQUIRE(Tp % 8 == 0, "gn_act_fwd: Tp %% 8 != 0");
+    SG_REQUIRE(planes == 1 || planes == 3 || planes == 5, "gn_act_fwd: planes must be 1, 3 or 5");
+    size_t sm = (planes > 1 && out_op) ? sizeof(float) * kWarpsPerBlock * (Tp + 8) : 0;
     SG_REQUIRE(stats == nullptr || (G > 0 && C % G == 0), "gn_act_fwd: bad groups");
     cudaStream_t st = as_stream(stream);
     long long rows = (long long)C * B;
@@ -438,8 +468,9 @@ int sg_gn_act_fwd(const float* y, const double* stats, const float* gamma, const
     int grid = rows_grid(rows);
     if (G <= 0) G = 1;
 #define SG_FWD(OT, RT)                                                                                            \
-    gn_act_fwd_kernel<OT, RT><<<grid, kThreads, 0, st>>>(y, stats, gamma, beta, (const RT*)res, res_scale, act,   \
-                                                         post_gelu, (OT*)out_op, out_f32, C, B, T, Tp, G, inv_n)
+    gn_act_fwd_kernel<OT, RT><<<grid, kThreads, sm, st>>>(y, stats, gamma, beta, (const RT*)res, res_scale, act,  \
+                                                          post_gelu, (OT*)out_op, planes, plane_stride, out_f32,  \
+                                                          C, B, T, Tp, G, inv_n)
     if (dtype == SG_BF16) {
         if (res == nullptr || res_is_f32) SG_FWD(__nv_bfloat16, float);
         else SG_FWD(__nv_bfloat16, __nv_bfloat16);
@@ -451,10 +482,11 @@ int sg_gn_act_fwd(const float* y, const double* stats, const float* gamma, const
 }
 
 int sg_gn_act_bwd(const float* y, const double* stats, const float* gamma, const float* beta, const void* res,
-                  int res_is_f32, float res_scale, int act, int post_gelu, const float* dout, void* dy, float* dgamma,
-                  float* dbeta, float* dbias, float* dres, int dres_accumulate, double* ws, int C, int B, int T, int Tp,
-                  int G, int dtype, void* stream) {
+                  int res_is_f32, float res_scale, int act, int post_gelu, const float* dout, void* dy, int planes,
+                  long long plane_stride, float* dgamma, float* dbeta, float* dbias, float* dres, int dres_accumulate,
+                  double* ws, int C, int B, int T, int Tp, int G, int dtype, void* stream) {
     SG_REQUIRE(Tp % 8 == 0, "gn_act_bwd: Tp %% 8 != 0");
+    SG_REQUIRE(planes == 1 || planes == 3 || planes == 5, "gn_act_bwd: planes must be 1, 3 or 5");
     SG_REQUIRE(stats == nullptr || (G > 0 && C % G == 0 && dgamma && dbeta && ws), "gn_act_bwd: bad GN arguments");
     if (G <= 0) G = 1;
     BwdArgs p{};
@@ -463,10 +495,10 @@ int sg_gn_act_bwd(const float* y, const double* stats, const float* gamma, const
     p.loss_kind = 0; p.C = C; p.B = B; p.T = T; p.Tp = Tp; p.G = G;
     p.inv_n = stats ? 1.0 / ((double)(C / G) * T) : 0.0;
     if (dtype == SG_BF16)
-        return launch_gn_bwd<__nv_bfloat16>(p, false, res_is_f32, (__nv_bfloat16*)dy, dgamma, dbeta, dbias, dres,
-                                            dres_accumulate, ws, as_stream(stream));
-    return launch_gn_bwd<float>(p, false, 1, (float*)dy, dgamma, dbeta, dbias, dres, dres_accumulate, ws,
-                                as_stream(stream));
+        return launch_gn_bwd<__nv_bfloat16>(p, false, res_is_f32, (__nv_bfloat16*)dy, planes, plane_stride, dgamma, dbeta,
+                                            dbias, dres, dres_accumulate, ws, as_stream(stream));
+    return launch_gn_bwd<float>(p, false, 1, (float*)dy, planes, plane_stride, dgamma, dbeta, dbias, dres,
+                                dres_accumulate, ws, as_stream(stream));
 }
 
 int sg_recon_fwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* x,

@@ -229,24 +229,33 @@ __global__ void colsum_kernel(const float* __restrict__ dout, float* __restrict_
 // =============================================================================================
 // latent expansion (Linear(D, D*T) + Unflatten): out[d][b][t] = (w[d*T+t][:] . z[b][:]) / sigma + bias[d*T+t]
 // =============================================================================================
+// warp per (d, b) row; `planes` shifted copies of the row are written (the consumer is a k5 conv)
 template <typename OT>
-__global__ void latent_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ sigma,
-                                  const float* __restrict__ bias, OT* __restrict__ out, int D, int B, int T, int Tp) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)D * B * Tp;
-    if (idx >= total) return;
-    int t = (int)(idx % Tp);
-    int b = (int)((idx / Tp) % B);
-    int d = (int)(idx / ((long long)Tp * B));
-    float val = 0.f;
-    if (t < T) {
-        const float* wrow = w + ((long long)d * T + t) * D;
-        const float* zrow = z + (long long)b * D;
-        float acc = 0.f;
-        for (int e = 0; e < D; ++e) acc += __ldg(wrow + e) * __ldg(zrow + e);
-        val = acc / sigma[0] + bias[d * T + t];
+__global__ void __launch_bounds__(256)
+latent_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ sigma,
+                  const float* __restrict__ bias, OT* __restrict__ out, int planes, long long pstride, int D, int B,
+                  int T, int Tp) {
+    extern __shared__ float sg_rows[];
+    long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);   // row = d * B + b
+    if (row >= (long long)D * B) return;
+    int lane = threadIdx.x & 31;
+    float* srow = sg_rows + (threadIdx.x >> 5) * (Tp + 8);
+    int d = (int)(row / B), b = (int)(row % B);
+    srow_clear_halo(srow, Tp, lane);
+    const float* zrow = z + (long long)b * D;
+    float inv = 1.f / sigma[0];
+    for (int t = lane; t < Tp; t += 32) {
+        float val = 0.f;
+        if (t < T) {
+            const float* wrow = w + ((long long)d * T + t) * D;
+            float acc = 0.f;
+            for (int e = 0; e < D; ++e) acc += __ldg(wrow + e) * __ldg(zrow + e);
+            val = acc * inv + bias[d * T + t];
+        }
+        srow[4 + t] = val;
     }
-    from_f(out[idx], val);
+    __syncwarp();
+    store_row_planes(out, row * Tp, planes, pstride, srow, T, Tp, lane);
 }
 
 // dwn[(d*T+t)][e] = sum_b dact[d][b][t] z[b][e] ; dbias[d*T+t] = sum_b dact[d][b][t]
@@ -332,13 +341,17 @@ constexpr int kThreads = 256;
 template <typename OT>
 __global__ void __launch_bounds__(kThreads)
 kl2_reparam_fwd_kernel(const float* __restrict__ cz, const float* __restrict__ cxz, const float* __restrict__ eps,
-                       const float* __restrict__ h, float std_scale, OT* __restrict__ zs_op, float* __restrict__ zs_f32,
-                       double* __restrict__ kl_sum, int C, int B, int T, int Tp) {
+                       const float* __restrict__ h, float std_scale, OT* __restrict__ zs_op, int planes, long long pstride,
+                       float* __restrict__ zs_f32, double* __restrict__ kl_sum, int C, int B, int T, int Tp) {
     __shared__ double sh[32];
+    extern __shared__ float sg_rows[];
     long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
+    float* srow = sg_rows + (threadIdx.x >> 5) * (Tp + 8);
+    const bool multi = planes > 1 && zs_op != nullptr;
     float ks = 0.f;
     if (row < (long long)C * B) {
+        if (multi) srow_clear_halo(srow, Tp, lane);
         int c = (int)(row / B), b = (int)(row % B);
         long long off_mu = row * Tp, off_lv = ((long long)(C + c) * B + b) * Tp;
         const float* erow = eps + ((long long)b * C + c) * T;
@@ -362,8 +375,17 @@ kl2_reparam_fwd_kernel(const float* __restrict__ cz, const float* __restrict__ c
                 }
                 o.v[i] = val;
             }
-            if (zs_op != nullptr) store8(zs_op + off_mu + seg * 8, o);
+            if (multi) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) srow[4 + seg * 8 + i] = o.v[i];
+            } else if (zs_op != nullptr) {
+                store8(zs_op + off_mu + seg * 8, o);
+            }
             if (zs_f32 != nullptr) store8(zs_f32 + off_mu + seg * 8, o);
+        }
+        if (multi) {
+            __syncwarp();
+            store_row_planes(zs_op, off_mu, planes, pstride, srow, T, Tp, lane);
         }
     }
     double t = block_sum((double)ks, sh);
@@ -569,14 +591,15 @@ int sg_head_bwd(const float* h, const float* w_orig, const float* sigma, const f
     return check_launch("head_bwd");
 }
 
-int sg_latent_fwd(const float* z, const float* w_orig, const float* sigma, const float* bias, void* out, int D, int B,
-                  int T, int Tp, int dtype, void* stream) {
-    long long total = (long long)D * B * Tp;
-    int grid = (int)cdiv(total, 256);
+int sg_latent_fwd(const float* z, const float* w_orig, const float* sigma, const float* bias, void* out, int planes,
+                  long long plane_stride, int D, int B, int T, int Tp, int dtype, void* stream) {
+    SG_REQUIRE(planes == 1 || planes == 3 || planes == 5, "latent_fwd: planes must be 1, 3 or 5");
+    int grid = (int)cdiv((long long)D * B, 8);
+    size_t sm = sizeof(float) * 8 * (Tp + 8);
     if (dtype == SG_BF16)
-        latent_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(z, w_orig, sigma, bias, (__nv_bfloat16*)out, D, B, T, Tp);
+        latent_fwd_kernel<__nv_bfloat16><<<grid, 256, sm, as_stream(stream)>>>(z, w_orig, sigma, bias, (__nv_bfloat16*)out, planes, plane_stride, D, B, T, Tp);
     else
-        latent_fwd_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(z, w_orig, sigma, bias, (float*)out, D, B, T, Tp);
+        latent_fwd_kernel<float><<<grid, 256, sm, as_stream(stream)>>>(z, w_orig, sigma, bias, (float*)out, planes, plane_stride, D, B, T, Tp);
     return check_launch("latent_fwd");
 }
 
@@ -604,15 +627,17 @@ int sg_reparam_main_bwd(const float* last, const float* eps, const float* dz, co
 }
 
 int sg_kl2_reparam_fwd(const float* cz, const float* cxz, const float* eps, const float* h, float std_scale,
-                       void* zs_op, float* zs_f32, double* kl_sum, int C, int B, int T, int Tp, int dtype,
-                       void* stream) {
+                       void* zs_op, int planes, long long plane_stride, float* zs_f32, double* kl_sum, int C, int B,
+                       int T, int Tp, int dtype, void* stream) {
+    SG_REQUIRE(planes == 1 || planes == 3 || planes == 5, "kl2_reparam_fwd: planes must be 1, 3 or 5");
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(kl_sum, 0, sizeof(double), st);
     int grid = (int)cdiv((long long)C * B, kWarpsPerBlock);
+    size_t sm = (planes > 1 && zs_op) ? sizeof(float) * kWarpsPerBlock * (Tp + 8) : 0;
     if (dtype == SG_BF16)
-        kl2_reparam_fwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(cz, cxz, eps, h, std_scale, (__nv_bfloat16*)zs_op, zs_f32, kl_sum, C, B, T, Tp);
+        kl2_reparam_fwd_kernel<__nv_bfloat16><<<grid, kThreads, sm, st>>>(cz, cxz, eps, h, std_scale, (__nv_bfloat16*)zs_op, planes, plane_stride, zs_f32, kl_sum, C, B, T, Tp);
     else
-        kl2_reparam_fwd_kernel<float><<<grid, kThreads, 0, st>>>(cz, cxz, eps, h, std_scale, (float*)zs_op, zs_f32, kl_sum, C, B, T, Tp);
+        kl2_reparam_fwd_kernel<float><<<grid, kThreads, sm, st>>>(cz, cxz, eps, h, std_scale, (float*)zs_op, planes, plane_stride, zs_f32, kl_sum, C, B, T, Tp);
     return check_launch("kl2_reparam_fwd");
 }
 

@@ -108,22 +108,26 @@ def draw_eps(shape, device):
 # tape primitives
 # ------------------------------------------------------------------------------------------------
 class Act:
-    """An activation in CR layout.  data: GEMM operand (bf16 / fp32) or None; f32: fp32 copy or None;
-    grad: fp32 gradient buffer filled during backward."""
+    """An activation in CR layout.  data: GEMM operand [planes, C, B, Tp] (bf16 / fp32; plane pl holds
+    the rows shifted by pl - planes//2, see csrc/common.cuh) or None; f32: fp32 copy [C, B, Tp] or None;
+    grad: fp32 gradient buffer [C, B, Tp] filled during backward."""
     __slots__ = ("data", "f32", "grad", "C", "needs_grad", "name")
 
     def __init__(self, C, data=None, f32=None, needs_grad=True, name=""):
         self.C, self.data, self.f32, self.grad, self.needs_grad, self.name = C, data, f32, None, needs_grad, name
 
+    def center(self):
+        return self.data[self.data.shape[0] // 2]
+
     def as_f32(self):
         if self.f32 is not None:
             return self.f32
         if self.data is not None and self.data.dtype == torch.float32:
-            return self.data
+            return self.center()
         raise RuntimeError("activation %s has no fp32 copy" % self.name)
 
     def residual_source(self):
-        return self.f32 if self.f32 is not None else self.data
+        return self.f32 if self.f32 is not None else self.center()
 
 
 class Ext:
@@ -175,7 +179,7 @@ class Ctx:
     def cap(self, name, act: Act):
         if self.capture is None:
             return
-        src = act.f32 if act.f32 is not None else act.data
+        src = act.f32 if act.f32 is not None else act.center()
         out = torch.empty(self.B, act.C, self.T, dtype=torch.float32, device=self.dev)
         K.unpack_f32(src.float() if src.dtype != torch.float32 else src, out, self.T)
         self.capture[name] = out
@@ -266,8 +270,12 @@ def _weight_grad(ctx: Ctx, mod, p: _Prep, dwg):
 # ------------------------------------------------------------------------------------------------
 # fused blocks
 # ------------------------------------------------------------------------------------------------
+def _k(conv) -> int:
+    return int(conv.kernel_size[0])
+
+
 def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.0, post_gelu=False,
-               want_f32=False, out_op_view=None, transposed=False, name="") -> Act:
+               want_f32=False, out_op_view=None, out_planes=1, transposed=False, name="") -> Act:
     """Conv1d / ConvTranspose1d (+ GroupNorm) (+ activation) (+ residual) (+ trailing GELU).
     Covers encoder.py:29-46, common.py:78-162, decoder.py:27-33,150-166."""
     B, T, Tp = ctx.B, ctx.T, ctx.Tp
@@ -284,7 +292,7 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
         if gn is not None:
             stats = ctx.f64(B, G, 2)
             K.gn_stats(y, stats, T, G)
-        out_op = out_op_view if out_op_view is not None else ctx.op(p.Cout, B, Tp)
+        out_op = out_op_view if out_op_view is not None else ctx.op(out_planes, p.Cout, B, Tp)
         out_f32 = ctx.f32(p.Cout, B, Tp) if (want_f32 and ctx.op_dtype != torch.float32) else None
         res_t = res.residual_source() if res is not None else None
         K.gn_act_fwd(y, stats, gn.weight if gn is not None else None, gn.bias if gn is not None else None,
@@ -299,7 +307,7 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
             if g is None:
                 return
             out.grad = None
-            dy = ctx.op(p.Cout, B, Tp)
+            dy = ctx.op(p.k, p.Cout, B, Tp)          # k planes: dgrad reads dy shifted by the taps
             dgamma = ctx.f32(p.Cout) if gn is not None else None
             dbeta = ctx.f32(p.Cout) if gn is not None else None
             dbias = ctx.f32(p.Cout) if conv.bias is not None else None
@@ -324,7 +332,7 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
 
 
 def cgg_seq(ctx: Ctx, seq, a_in: Act, res: Act = None, res_scale=0.1, post_gelu=False, want_f32=False,
-            out_op_view=None, name="") -> Act:
+            out_op_view=None, out_planes=1, name="") -> Act:
     """nn.Sequential of (Conv1d, GroupNorm, GELU) triples; the optional residual / trailing GELU /
     fp32 copy apply to the last triple (common.py:101-102,124-125,161-162)."""
     n = len(seq) // 3
@@ -334,7 +342,8 @@ def cgg_seq(ctx: Ctx, seq, a_in: Act, res: Act = None, res_scale=0.1, post_gelu=
         a = conv_block(ctx, seq[3 * i], seq[3 * i + 1], a, K.ACT_GELU,
                        res=res if last else None, res_scale=res_scale if (last and res is not None) else 1.0,
                        post_gelu=post_gelu if last else False, want_f32=want_f32 if last else False,
-                       out_op_view=out_op_view if last else None, name=name if last else "")
+                       out_op_view=out_op_view if last else None,
+                       out_planes=out_planes if last else _k(seq[3 * (i + 1)]), name=name if last else "")
     return a
 
 
@@ -366,13 +375,13 @@ def head(ctx: Ctx, lin, h: Act, ext_out: bool = True):
     return ext
 
 
-def latent_seq(ctx: Ctx, seq, z: Ext, out_op_view=None, name="") -> Act:
+def latent_seq(ctx: Ctx, seq, z: Ext, out_op_view=None, out_planes=1, name="") -> Act:
     """Linear(d, d*T) -> Unflatten -> Conv k5 -> GroupNorm -> GELU (decoder.py:131-148)."""
     lin, conv, gn = seq[0], seq[2], seq[3]
     B, T, Tp = ctx.B, ctx.T, ctx.Tp
     p = prep_linear(ctx, lin)
     D = p.Cin
-    a = Act(D, data=ctx.op(D, B, Tp), name=name + ".lin")
+    a = Act(D, data=ctx.op(_k(conv), D, B, Tp), name=name + ".lin")
     K.latent_fwd(z.tensor, p.w, p.sigma, lin.bias, a.data, T)
     if ctx.tape is not None:
         def bwd():
@@ -392,7 +401,7 @@ def latent_seq(ctx: Ctx, seq, z: Ext, out_op_view=None, name="") -> Act:
             else:
                 K.axpy(z.grad, dz, 1.0, True)
         ctx.tape.append(bwd)
-    return conv_block(ctx, conv, gn, a, K.ACT_GELU, out_op_view=out_op_view, name=name)
+    return conv_block(ctx, conv, gn, a, K.ACT_GELU, out_op_view=out_op_view, out_planes=out_planes, name=name)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -402,14 +411,16 @@ def encoder_graph(ctx: Ctx, enc, x):
     """encoder.py:146-167.  Returns (last Ext [B, 2*z_dim], [xs Ext ...] in the reference's reversed
     order without the deepest level)."""
     B, N, T = x.shape
-    a = Act(N, data=ctx.op(N, B, ctx.Tp), needs_grad=False, name="x")
+    a = Act(N, data=ctx.op(1, N, B, ctx.Tp), needs_grad=False, name="x")
     K.pack_input(x, a.data, T)
     L = len(enc.encoder_blocks)
     xs = []
     h = None
     for i in range(L):
-        a = cgg_seq(ctx, enc.encoder_blocks[i].module_list[0]._seq, a, want_f32=True)
-        h = cgg_seq(ctx, enc.encoder_residual_blocks[i].seq, a, res=a, res_scale=0.1, want_f32=True,
+        res_seq = enc.encoder_residual_blocks[i].seq
+        a = cgg_seq(ctx, enc.encoder_blocks[i].module_list[0]._seq, a, want_f32=True, out_planes=_k(res_seq[0]))
+        nxt = _k(enc.encoder_blocks[i + 1].module_list[0]._seq[0]) if i + 1 < L else 1
+        h = cgg_seq(ctx, res_seq, a, res=a, res_scale=0.1, want_f32=True, out_planes=nxt,
                     name="encoder.level%d" % i)
         # xs_linear[L-1] is evaluated by the reference but its output is dropped (encoder.py:167
         # xs[:-1]): only its power iteration is observable.  xs_linear[0] is returned (exported to
@@ -428,27 +439,33 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     B, T, Tp = ctx.B, ctx.T, ctx.Tp
     nb = len(dec.decoder_residual_blocks)
     kls = []
-    zs = latent_seq(ctx, dec.sequence_start[0], z, name="decoder.start")
+    zs = latent_seq(ctx, dec.sequence_start[0], z, out_planes=_k(dec.decoder_blocks[0].module_list[0]._seq[0]),
+                    name="decoder.start")
     out = None
     std_scale = 1e-10 if mode == "fix" else 1.0
     for i in range(nb):
         lastlvl = i == nb - 1
+        res_seq = dec.decoder_residual_blocks[i].seq
         up = conv_block(ctx, dec.decoder_blocks[i].module_list[0]._seq[0], None, zs, K.ACT_GELU, want_f32=True,
-                        transposed=True, name="decoder.up%d" % i)
+                        out_planes=_k(res_seq[0]), transposed=True, name="decoder.up%d" % i)
         C = up.C
         cat_buf = None
         if not lastlvl:
-            cat_buf = ctx.op(2 * C, B, Tp)
-        out = cgg_seq(ctx, dec.decoder_residual_blocks[i].seq, up, res=up, res_scale=0.1, want_f32=True,
-                      out_op_view=cat_buf[C:] if cat_buf is not None else None, name="decoder.level%d" % i)
+            # [xs_sample ; decoder_out] of decoder.py:192 is a channel concat = adjacent rows in CR layout:
+            # both producers write straight into the halves of one buffer (3 planes: its consumers are k3 convs)
+            cat_planes = max(_k(dec.condition_z[i][0]._seq[0]), _k(dec.condition_xz[i][0]._seq[0]))
+            cat_buf = ctx.op(cat_planes, 2 * C, B, Tp)
+        out = cgg_seq(ctx, res_seq, up, res=up, res_scale=0.1, want_f32=True,
+                      out_op_view=cat_buf[:, C:] if cat_buf is not None else None,
+                      out_planes=_k(dec.recon[0]), name="decoder.level%d" % i)
         if lastlvl:
             break
         # condition_z: ResidualBlock -> GELU -> Conv k3 (decoder.py:150-157)
         cz_seq = dec.condition_z[i]
-        r = cgg_seq(ctx, cz_seq[0]._seq, out, res=out, res_scale=0.1, post_gelu=True)
+        r = cgg_seq(ctx, cz_seq[0]._seq, out, res=out, res_scale=0.1, post_gelu=True, out_planes=_k(cz_seq[2]))
         cz = conv_block(ctx, cz_seq[2], None, r, K.ACT_NONE)
         # xs path (decoder.py:189-193)
-        xs_act = latent_seq(ctx, dec.xs_sequence[i], xs[i], out_op_view=cat_buf[:C], name="decoder.xs%d" % i)
+        xs_act = latent_seq(ctx, dec.xs_sequence[i], xs[i], out_op_view=cat_buf[:, :C], name="decoder.xs%d" % i)
         cat = Act(2 * C, data=cat_buf, name="cat%d" % i)
         if ctx.tape is not None:
             def cat_bwd(cat=cat, xs_act=xs_act, out=out, C=C):
@@ -463,11 +480,12 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
                     K.axpy(out.grad, g[C:], 1.0, True)
             ctx.tape.append(cat_bwd)
         cxz_seq = dec.condition_xz[i]
-        r2 = cgg_seq(ctx, cxz_seq[0]._seq, cat, res=cat, res_scale=0.1, post_gelu=True)
+        r2 = cgg_seq(ctx, cxz_seq[0]._seq, cat, res=cat, res_scale=0.1, post_gelu=True, out_planes=_k(cxz_seq[2]))
         cxz = conv_block(ctx, cxz_seq[2], None, r2, K.ACT_NONE)
         # kl_2 + reparameterisation + "decoder_out + z" of the next level (decoder.py:179,193-212)
         eps = draw_eps((B, C, T), ctx.dev)
-        zs_next = Act(C, data=ctx.op(C, B, Tp), name="decoder.zs%d" % i)
+        zs_next = Act(C, data=ctx.op(_k(dec.decoder_blocks[i + 1].module_list[0]._seq[0]), C, B, Tp),
+                      name="decoder.zs%d" % i)
         kl_sum = ctx.f64(1)
         out_f32 = out.as_f32()
         K.kl2_reparam_fwd(cz.f32, cxz.f32, eps, out_f32, std_scale, zs_next.data, None, kl_sum, T)
@@ -521,7 +539,7 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
             g_ext = xhat_ext.grad
             if g_loss is None and g_mse is None and g_ext is None:
                 return
-            dy = ctx.op(N, B, Tp)
+            dy = ctx.op(1, N, B, Tp)
             dgamma, dbeta, dbias = ctx.f32(N), ctx.f32(N), ctx.f32(N)
             K.recon_bwd(y, stats, gn.weight, gn.bias, x, g_loss, g_mse, inv_numel, g_ext, dy, dgamma, dbeta, dbias,
                         T, G, loss_kind)

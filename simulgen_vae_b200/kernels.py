@@ -38,6 +38,19 @@ def _p(t):
     return t.data_ptr()
 
 
+def _planes(t):
+    """(pointer, planes, plane_stride) of an operand tensor [P, C, B, Tp] whose planes are contiguous
+    [C, B, Tp] blocks (the tensor itself may be a channel slice of a wider buffer)."""
+    if t is None:
+        return None, 1, 0
+    if not t.is_cuda:
+        raise RuntimeError("simulgen_b200: CUDA tensor required (there is no CPU fallback)")
+    if t.dim() != 4 or not t[0].is_contiguous():
+        raise RuntimeError("simulgen_b200: operand must be [planes, C, B, Tp] with contiguous planes, got %s / %s"
+                           % (tuple(t.shape), t.stride()))
+    return t.data_ptr(), t.shape[0], (t.stride(0) if t.shape[0] > 1 else t[0].numel())
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -56,8 +69,10 @@ def _f32(t, name):
 
 # ---- layout -------------------------------------------------------------------------------------
 def pack_input(x, out, T):
+    """out: operand [1, N, B, Tp]."""
     B, N, _ = x.shape
-    Tp = out.shape[2]
+    Tp = out.shape[3]
+    assert out.shape[0] == 1
     _call("sg_pack_input", _p(_f32(x, "x")), _p(out), B, N, T, Tp, _dt(out), _stream())
 
 
@@ -96,25 +111,33 @@ def sn_weight_grad(dwg, w_orig, u, v, sigma, grad, Cout, Cin, Cin_p, k, so, si, 
 
 # ---- convolutions -------------------------------------------------------------------------------
 def conv_fprop(wg, act, bias, out, Cin, accumulate=False):
+    """act: operand [P, Cin, B, Tp] (P >= k planes); out fp32 [Cout, B, Tp]."""
     k, Cout, Cin_p = wg.shape
-    R = act.numel() // act.shape[0]
-    assert act.shape[0] == Cin and out.shape[0] == Cout and out.numel() == Cout * R and wg.dtype == act.dtype
-    _call("sg_conv_fprop", _p(wg), _p(act), _p(bias), _p(_f32(out, "out")), Cin, Cin_p, Cout, k, R, int(accumulate),
+    ap, an, astr = _planes(act)
+    R = act.shape[2] * act.shape[3]
+    assert act.shape[1] == Cin and out.shape[0] == Cout and out.numel() == Cout * R and wg.dtype == act.dtype
+    _call("sg_conv_fprop", _p(wg), ap, an, astr, _p(bias), _p(_f32(out, "out")), Cin, Cin_p, Cout, k, R, int(accumulate),
           _dt(act), _stream())
 
 
 def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
+    """dy: operand [P, Cout, B, Tp]; dx fp32 [Cin, B, Tp]."""
     k, Cout, Cin_p = wg.shape
-    R = dy.numel() // dy.shape[0]
-    assert dy.shape[0] == Cout and dx.shape[0] == Cin and dx.numel() == Cin * R and wg.dtype == dy.dtype
-    _call("sg_conv_dgrad", _p(wg), _p(dy), _p(_f32(dx, "dx")), Cin, Cin_p, Cout, k, R, int(accumulate), _dt(dy), _stream())
+    dp, dn, dstr = _planes(dy)
+    R = dy.shape[2] * dy.shape[3]
+    assert dy.shape[1] == Cout and dx.shape[0] == Cin and dx.numel() == Cin * R and wg.dtype == dy.dtype
+    _call("sg_conv_dgrad", _p(wg), dp, dn, dstr, _p(_f32(dx, "dx")), Cin, Cin_p, Cout, k, R, int(accumulate), _dt(dy),
+          _stream())
 
 
 def conv_wgrad(dy, act, dwg, Cin):
+    """dy: operand [Pd, Cout, B, Tp]; act: operand [Pa, Cin, B, Tp]; dwg fp32 [k, Cout, Cin_p]."""
     k, Cout, Cin_p = dwg.shape
-    R = dy.numel() // dy.shape[0]
-    assert dy.shape[0] == Cout and act.shape[0] == Cin and act.numel() == Cin * R and dy.dtype == act.dtype
-    _call("sg_conv_wgrad", _p(dy), _p(act), _p(_f32(dwg, "dwg")), Cin, Cin_p, Cout, k, R, _dt(act), _stream())
+    dp, dn, dstr = _planes(dy)
+    ap, an, astr = _planes(act)
+    R = dy.shape[2] * dy.shape[3]
+    assert dy.shape[1] == Cout and act.shape[1] == Cin and dy.dtype == act.dtype
+    _call("sg_conv_wgrad", dp, dn, dstr, ap, an, astr, _p(_f32(dwg, "dwg")), Cin, Cin_p, Cout, k, R, _dt(act), _stream())
 
 
 # ---- GroupNorm + activation ---------------------------------------------------------------------
@@ -124,11 +147,13 @@ def gn_stats(y, stats, T, G):
 
 
 def gn_act_fwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, out_op, out_f32, T, G):
+    """out_op: operand [P, C, B, Tp] (all planes written) or None; res: [C, B, Tp] fp32 or operand dtype."""
     C, B, Tp = y.shape
     dt = _dt(out_op) if out_op is not None else SG_F32
+    op, on, ostr = _planes(out_op)
     res_is_f32 = int(res is not None and res.dtype == torch.float32)
     _call("sg_gn_act_fwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(res), res_is_f32, float(res_scale),
-          int(act), int(post_gelu), _p(out_op), _p(out_f32), C, B, T, Tp, int(G), dt, _stream())
+          int(act), int(post_gelu), op, on, ostr, _p(out_f32), C, B, T, Tp, int(G), dt, _stream())
 
 
 def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, dgamma, dbeta, dbias, dres,
@@ -136,8 +161,9 @@ def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, 
     C, B, Tp = y.shape
     res_is_f32 = int(res is not None and res.dtype == torch.float32)
     ws = torch.empty(2 * B * max(int(G), 1) + 2, dtype=torch.float64, device=y.device)
+    dp, dn, dstr = _planes(dy)
     _call("sg_gn_act_bwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(res), res_is_f32, float(res_scale),
-          int(act), int(post_gelu), _p(_f32(dout, "dout")), _p(dy), _p(dgamma), _p(dbeta), _p(dbias), _p(dres),
+          int(act), int(post_gelu), _p(_f32(dout, "dout")), dp, dn, dstr, _p(dgamma), _p(dbeta), _p(dbias), _p(dres),
           int(dres_accumulate), _p(ws), C, B, T, Tp, int(G), _dt(dy), _stream())
 
 
@@ -150,8 +176,10 @@ def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind):
 def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy, dgamma, dbeta, dbias, T, G, loss_kind):
     N, B, Tp = y.shape
     ws = torch.empty(2 * B * G + 2, dtype=torch.float64, device=y.device)
+    dp, dn, _ = _planes(dy)
+    assert dn == 1
     _call("sg_recon_bwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(x), _p(g_loss), _p(g_mse), float(inv_numel),
-          _p(dxhat_ext), _p(dy), _p(dgamma), _p(dbeta), _p(dbias), _p(ws), N, B, T, Tp, G, int(loss_kind), _dt(dy),
+          _p(dxhat_ext), dp, _p(dgamma), _p(dbeta), _p(dbias), _p(ws), N, B, T, Tp, G, int(loss_kind), _dt(dy),
           _stream())
 
 
@@ -170,8 +198,11 @@ def head_bwd(h, w_orig, sigma, dout, dwn, dbias, dh, dh_accumulate, T):
 
 
 def latent_fwd(z, w_orig, sigma, bias, out, T):
-    D, B, Tp = out.shape
-    _call("sg_latent_fwd", _p(_f32(z, "z")), _p(w_orig), _p(sigma), _p(bias), _p(out), D, B, T, Tp, _dt(out), _stream())
+    """out: operand [P, D, B, Tp]."""
+    _, D, B, Tp = out.shape
+    op, on, ostr = _planes(out)
+    _call("sg_latent_fwd", _p(_f32(z, "z")), _p(w_orig), _p(sigma), _p(bias), op, on, ostr, D, B, T, Tp, _dt(out),
+          _stream())
 
 
 def latent_bwd(z, w_orig, sigma, dact, dwn, dbias, dz, T):
@@ -194,8 +225,9 @@ def reparam_main_bwd(last, eps, dz, dkl, dlast):
 def kl2_reparam_fwd(cz, cxz, eps, h, std_scale, zs_op, zs_f32, kl_sum, T):
     C2, B, Tp = cz.shape
     dt = _dt(zs_op) if zs_op is not None else SG_F32
+    zp, zn, zstr = _planes(zs_op)
     _call("sg_kl2_reparam_fwd", _p(_f32(cz, "cz")), _p(_f32(cxz, "cxz")), _p(_f32(eps, "eps")), _p(_f32(h, "h")),
-          float(std_scale), _p(zs_op), _p(zs_f32), _p(kl_sum), C2 // 2, B, T, Tp, dt, _stream())
+          float(std_scale), zp, zn, zstr, _p(zs_f32), _p(kl_sum), C2 // 2, B, T, Tp, dt, _stream())
 
 
 def kl2_reparam_bwd(cz, cxz, eps, std_scale, dzs, dkl, kl_scale, dcz, dcxz, T):

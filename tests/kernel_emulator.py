@@ -24,10 +24,25 @@ def _act(kind, x):
     return x
 
 
+# ---- operand planes -----------------------------------------------------------------------------
+def write_planes(dst, val, T):
+    """dst [P, C, B, Tp] <- val [C, B, T]: dst[pl][c][b][t] = val[c][b][t + pl - P//2], zero outside [0, T)."""
+    P = dst.shape[0]
+    dst.zero_()
+    for pl in range(P):
+        s = pl - P // 2
+        lo, hi = max(0, -s), min(T, T - s)
+        if hi > lo:
+            dst[pl, :, :, lo:hi] = val[:, :, lo + s:hi + s].to(dst.dtype)
+
+
+def center(t):
+    return t[t.shape[0] // 2]
+
+
 # ---- layout -------------------------------------------------------------------------------------
 def pack_input(x, out, T):
-    out.zero_()
-    out[:, :, :T] = x.permute(1, 0, 2).to(out.dtype)
+    write_planes(out, x.permute(1, 0, 2), T)
 
 
 def unpack_f32(inp, out, T):
@@ -88,9 +103,11 @@ def sn_weight_grad(dwg, w, u, v, sigma, grad, Cout, Cin, Cin_p, k, so, si, flip)
 
 
 # ---- convolutions -------------------------------------------------------------------------------
+# The models use ONLY the centre plane and do the tap shifts themselves (F.conv1d), so they also check
+# that the pre-shifted planes the CUDA path reads are consistent with a real convolution.
 def conv_fprop(wg, act, bias, out, Cin, accumulate=False):
     k, Cout, Cin_p = wg.shape
-    a = act.reshape(Cin, -1).float()[None]
+    a = center(act).reshape(Cin, -1).float()[None]
     w = wg[:, :, :Cin].float().permute(1, 2, 0).contiguous()
     y = F.conv1d(a, w, bias.detach() if bias is not None else None, padding=k // 2)[0]
     y = y.reshape(out.shape)
@@ -102,7 +119,7 @@ def conv_fprop(wg, act, bias, out, Cin, accumulate=False):
 
 def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
     k, Cout, Cin_p = wg.shape
-    g = dy.reshape(Cout, -1).float()[None]
+    g = center(dy).reshape(Cout, -1).float()[None]
     w = wg[:, :, :Cin].float().flip(0).permute(2, 1, 0).contiguous()      # [ci][co][j'] = wg[k-1-j'][co][ci]
     y = F.conv1d(g, w, None, padding=k // 2)[0].reshape(dx.shape)
     if accumulate:
@@ -113,8 +130,8 @@ def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
 
 def conv_wgrad(dy, act, dwg, Cin):
     k, Cout, Cin_p = dwg.shape
-    g = dy.reshape(Cout, -1).float()
-    a = act.reshape(Cin, -1).float()
+    g = center(dy).reshape(Cout, -1).float()
+    a = center(act).reshape(Cin, -1).float()
     R = a.shape[1]
     pad = k // 2
     ap = F.pad(a, (pad, pad))
@@ -152,10 +169,11 @@ def _gn_forward(y, gamma, beta, res, res_scale, act, post_gelu, T, G, use_gn):
 def gn_act_fwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, out_op, out_f32, T, G):
     with torch.no_grad():
         o = _gn_forward(y, gamma, beta, res, res_scale, act, post_gelu, T, G, stats is not None)
-    for dst in (out_op, out_f32):
-        if dst is not None:
-            dst.zero_()
-            dst[:, :, :T] = o.to(dst.dtype)
+    if out_op is not None:
+        write_planes(out_op, o, T)
+    if out_f32 is not None:
+        out_f32.zero_()
+        out_f32[:, :, :T] = o
 
 
 def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, dgamma, dbeta, dbias, dres,
@@ -173,7 +191,7 @@ def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, 
     gy = gmap[id(yl)]
     gy = gy.clone()
     gy[:, :, T:] = 0
-    dy.copy_(gy.to(dy.dtype))
+    write_planes(dy, gy[:, :, :T], T)
     if dbias is not None:
         dbias.copy_(gy.sum(dim=(1, 2)))
     if use_gn:
@@ -231,7 +249,7 @@ def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy,
         gy, gg, gb = torch.autograd.grad(obj, [yl, gl, bl])
     gy = gy.clone()
     gy[:, :, T:] = 0
-    dy.copy_(gy.to(dy.dtype))
+    write_planes(dy, gy[:, :, :T], T)
     dgamma.copy_(gg)
     dbeta.copy_(gb)
     dbias.copy_(gy.sum(dim=(1, 2)))
@@ -273,11 +291,10 @@ def _latent(z, w, sigma, bias, D, T):
 
 
 def latent_fwd(z, w_orig, sigma, bias, out, T):
-    D, B, Tp = out.shape
+    _, D, B, Tp = out.shape
     with torch.no_grad():
         o = _latent(z, w_orig, sigma, bias, D, T)
-    out.zero_()
-    out[:, :, :T] = o.to(out.dtype)
+    write_planes(out, o, T)
 
 
 def latent_bwd(z, w_orig, sigma, dact, dwn, dbias, dz, T):
@@ -341,10 +358,11 @@ def _kl2_reparam(cz, cxz, eps, h, std_scale, T):
 def kl2_reparam_fwd(cz, cxz, eps, h, std_scale, zs_op, zs_f32, kl_sum, T):
     with torch.no_grad():
         zs, s = _kl2_reparam(cz, cxz, eps, h, std_scale, T)
-    for dst in (zs_op, zs_f32):
-        if dst is not None:
-            dst.zero_()
-            dst[:, :, :T] = zs.to(dst.dtype)
+    if zs_op is not None:
+        write_planes(zs_op, zs, T)
+    if zs_f32 is not None:
+        zs_f32.zero_()
+        zs_f32[:, :, :T] = zs
     kl_sum.copy_(s.double().reshape(1))
 
 

@@ -34,11 +34,14 @@ def make(Cin, Cout, k, B, T):
     Cin_p = (Cin + 7) // 8 * 8
     wg = rnd(k, Cout, Cin_p, seed=1, scale=1.0 / (Cin * k) ** 0.5)
     wg[:, :, Cin:] = 0
-    act = rnd(Cin, B, Tp, seed=2)
-    act[:, :, T:] = 0
-    dy = rnd(Cout, B, Tp, seed=3)
-    dy[:, :, T:] = 0
-    return wg.to(BF), act.to(BF), dy.to(BF), rnd(Cout, seed=4), Tp, Cin_p
+    # operands as the engine stores them: k pre-shifted planes (one more pair than needed for k=1, to
+    # exercise the plane offset arithmetic)
+    Pa = 3 if k == 1 else k
+    act = torch.empty(Pa, Cin, B, Tp, device=DEV, dtype=BF)
+    emu.write_planes(act, rnd(Cin, B, T, seed=2), T)
+    dy = torch.empty(k, Cout, B, Tp, device=DEV, dtype=BF)
+    emu.write_planes(dy, rnd(Cout, B, T, seed=3), T)
+    return wg.to(BF), act, dy, rnd(Cout, seed=4), Tp, Cin_p
 
 
 @pytest.mark.parametrize("shape", SHAPES)

@@ -25,6 +25,14 @@ def cr(C, B, T, seed=0, dtype=torch.float32, scale=1.0):
     return t.to(dtype)
 
 
+def planes_of(val, P, T, dtype=torch.float32):
+    """operand tensor [P, C, B, Tp] holding `val` [C, B, Tp] in pre-shifted planes"""
+    C, B, Tp = val.shape
+    out = torch.empty(P, C, B, Tp, device=DEV, dtype=dtype)
+    emu.write_planes(out, val[:, :, :T], T)
+    return out
+
+
 def close(a, b, tol, what=""):
     e = rel_l2(a, b)
     assert e < tol, "%s rel-L2 %.3e >= %.1e" % (what, e, tol)
@@ -34,14 +42,14 @@ def close(a, b, tol, what=""):
 def test_pack_unpack(dtype):
     B, N, T = 3, 37, 20
     x = rnd(B, N, T)
-    out = torch.full((N, B, tp_of(T)), 7.0, device=DEV, dtype=dtype)
+    out = torch.full((1, N, B, tp_of(T)), 7.0, device=DEV, dtype=dtype)
     ref = torch.empty_like(out)
     K.pack_input(x, out, T)
     emu.pack_input(x, ref, T)
     assert torch.equal(out, ref)
     if dtype == torch.float32:
         back = torch.empty(B, N, T, device=DEV)
-        K.unpack_f32(out, back, T)
+        K.unpack_f32(out[0], back, T)
         assert torch.equal(back, x)
 
 
@@ -92,7 +100,7 @@ def test_conv_simt_fp32(k):
     Tp = tp_of(T)
     wg = rnd(k, Cout, Cin_p, seed=1, scale=0.2)
     wg[:, :, Cin:] = 0
-    act = cr(Cin, B, T, seed=2)
+    act = planes_of(cr(Cin, B, T, seed=2), k + 2 if k < 5 else 5, T)
     bias = rnd(Cout, seed=3)
     o1 = torch.empty(Cout, B, Tp, device=DEV)
     o2 = torch.empty_like(o1)
@@ -102,7 +110,7 @@ def test_conv_simt_fp32(k):
     K.conv_fprop(wg, act, None, o1, Cin, accumulate=True)
     emu.conv_fprop(wg, act, None, o2, Cin, accumulate=True)
     close(o1, o2, 1e-5, "fprop acc")
-    dy = cr(Cout, B, T, seed=4)
+    dy = planes_of(cr(Cout, B, T, seed=4), k, T)
     d1 = torch.empty(Cin, B, Tp, device=DEV)
     d2 = torch.empty_like(d1)
     K.conv_dgrad(wg, dy, d1, Cin)
@@ -138,7 +146,8 @@ CASES = [
 
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-def test_gn_act_fwd_bwd(case, dtype):
+@pytest.mark.parametrize("P", [1, 3, 5])
+def test_gn_act_fwd_bwd(case, dtype, P):
     use_gn, act, res_kind, res_scale, post = case
     C, B, T, G = 48, 3, 21, 8
     Tp = tp_of(T)
@@ -153,7 +162,7 @@ def test_gn_act_fwd_bwd(case, dtype):
         res = cr(C, B, T, seed=4)
     elif res_kind == "op":
         res = cr(C, B, T, seed=4).to(dtype)
-    o1 = torch.full((C, B, Tp), 9.0, device=DEV, dtype=dtype)
+    o1 = torch.full((P, C, B, Tp), 9.0, device=DEV, dtype=dtype)
     f1 = torch.full((C, B, Tp), 9.0, device=DEV)
     o2, f2 = torch.empty_like(o1), torch.empty_like(f1)
     GG = G if use_gn else 0
@@ -161,10 +170,10 @@ def test_gn_act_fwd_bwd(case, dtype):
     emu.gn_act_fwd(y, stats, gamma, beta, res, res_scale, act, post, o2, f2, T, G)
     close(f1, f2, 2e-6, "fwd f32")
     close(o1.float(), o2.float(), 2e-6 if dtype == torch.float32 else 4e-3, "fwd op")
-    assert float(o1[:, :, T:].float().abs().max()) == 0.0
+    assert float(o1[:, :, :, T:].float().abs().max()) == 0.0
     # backward
     dout = cr(C, B, T, seed=5)
-    dy1 = torch.full((C, B, Tp), 9.0, device=DEV, dtype=dtype)
+    dy1 = torch.full((P, C, B, Tp), 9.0, device=DEV, dtype=dtype)
     dy2 = torch.empty_like(dy1)
     dg1, db1, dbi1 = (torch.empty(C, device=DEV) for _ in range(3))
     dg2, db2, dbi2 = (torch.empty(C, device=DEV) for _ in range(3))
@@ -181,7 +190,7 @@ def test_gn_act_fwd_bwd(case, dtype):
         close(db1, db2, 2e-5, "dbeta")
     if res is not None:
         close(dr1[:, :, :T], dr2[:, :, :T], 2e-5, "dres")
-    assert float(dy1[:, :, T:].float().abs().max()) == 0.0
+    assert float(dy1[:, :, :, T:].float().abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("loss", ["MSE", "MAE", "smoothL1", "Huber"])
@@ -207,7 +216,7 @@ def test_recon_fwd_bwd(loss, with_ext):
     inv = 1.0 / (B * N * T)
     outs = []
     for fn in (K.recon_bwd, emu.recon_bwd):
-        dy = torch.full((N, B, Tp), 9.0, device=DEV)
+        dy = torch.full((1, N, B, Tp), 9.0, device=DEV)
         dg, db, dbi = (torch.empty(N, device=DEV) for _ in range(3))
         fn(y, stats, gamma, beta, x, g_loss, g_mse, inv, ext, dy, dg, db, dbi, T, G, kind)
         outs.append((dy, dg, db, dbi))
@@ -217,7 +226,7 @@ def test_recon_fwd_bwd(loss, with_ext):
     if with_ext:
         outs = []
         for fn in (K.recon_bwd, emu.recon_bwd):
-            dy = torch.full((N, B, Tp), 9.0, device=DEV, dtype=torch.bfloat16)
+            dy = torch.full((1, N, B, Tp), 9.0, device=DEV, dtype=torch.bfloat16)
             dg, db, dbi = (torch.empty(N, device=DEV) for _ in range(3))
             fn(y, stats, gamma, beta, None, None, None, inv, ext, dy, dg, db, dbi, T, G, kind)
             outs.append((dy.float(), dg, db, dbi))
@@ -256,7 +265,7 @@ def test_latent_fwd_bwd(dtype):
     w = rnd(D * T, D, seed=2, scale=0.3)
     sigma = torch.tensor([0.8], device=DEV)
     bias = rnd(D * T, seed=3)
-    o1 = torch.full((D, B, Tp), 9.0, device=DEV, dtype=dtype)
+    o1 = torch.full((5, D, B, Tp), 9.0, device=DEV, dtype=dtype)
     o2 = torch.empty_like(o1)
     K.latent_fwd(z, w, sigma, bias, o1, T)
     emu.latent_fwd(z, w, sigma, bias, o2, T)
@@ -301,7 +310,7 @@ def test_kl2_reparam(std_scale):
     cz[C + 2, 0, 2] = 20.0
     eps = rnd(B, C, T, seed=3)
     h = cr(C, B, T, seed=4)
-    zs1 = torch.full((C, B, Tp), 9.0, device=DEV, dtype=torch.bfloat16)
+    zs1 = torch.full((3, C, B, Tp), 9.0, device=DEV, dtype=torch.bfloat16)
     zs2 = torch.empty_like(zs1)
     f1, f2 = torch.empty(C, B, Tp, device=DEV), torch.empty(C, B, Tp, device=DEV)
     k1, k2 = (torch.empty(1, device=DEV, dtype=torch.float64) for _ in range(2))
