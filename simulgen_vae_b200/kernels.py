@@ -17,6 +17,19 @@ ACT_NONE, ACT_GELU, ACT_TANH = 0, 1, 2
 LOSS_KINDS = {"MSE": 0, "MAE": 1, "smoothL1": 2, "Huber": 3}
 
 LAUNCHES = 0          # number of C-ABI calls (each launches >= 1 of our kernels); bench.py reports it
+PROFILE = None        # bench.py sets this to a list: (name, algorithmic_flops, start_event, end_event) per GEMM
+
+
+def _timed(name, flops, fn):
+    if PROFILE is None:
+        fn()
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    PROFILE.append((name, flops, e0, e1))
 
 
 def _dt(t):
@@ -116,8 +129,9 @@ def conv_fprop(wg, act, bias, out, Cin, accumulate=False):
     ap, an, astr = _planes(act)
     R = act.shape[2] * act.shape[3]
     assert act.shape[1] == Cin and out.shape[0] == Cout and out.numel() == Cout * R and wg.dtype == act.dtype
-    _call("sg_conv_fprop", _p(wg), ap, an, astr, _p(bias), _p(_f32(out, "out")), Cin, Cin_p, Cout, k, R, int(accumulate),
-          _dt(act), _stream())
+    _timed("fprop", 2.0 * Cin * Cout * k * R, lambda: _call(
+        "sg_conv_fprop", _p(wg), ap, an, astr, _p(bias), _p(_f32(out, "out")), Cin, Cin_p, Cout, k, R, int(accumulate),
+        _dt(act), _stream()))
 
 
 def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
@@ -126,8 +140,9 @@ def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
     dp, dn, dstr = _planes(dy)
     R = dy.shape[2] * dy.shape[3]
     assert dy.shape[1] == Cout and dx.shape[0] == Cin and dx.numel() == Cin * R and wg.dtype == dy.dtype
-    _call("sg_conv_dgrad", _p(wg), dp, dn, dstr, _p(_f32(dx, "dx")), Cin, Cin_p, Cout, k, R, int(accumulate), _dt(dy),
-          _stream())
+    _timed("dgrad", 2.0 * Cin * Cout * k * R, lambda: _call(
+        "sg_conv_dgrad", _p(wg), dp, dn, dstr, _p(_f32(dx, "dx")), Cin, Cin_p, Cout, k, R, int(accumulate), _dt(dy),
+        _stream()))
 
 
 def conv_wgrad(dy, act, dwg, Cin):
@@ -137,7 +152,8 @@ def conv_wgrad(dy, act, dwg, Cin):
     ap, an, astr = _planes(act)
     R = dy.shape[2] * dy.shape[3]
     assert dy.shape[1] == Cout and act.shape[1] == Cin and dy.dtype == act.dtype
-    _call("sg_conv_wgrad", dp, dn, dstr, ap, an, astr, _p(_f32(dwg, "dwg")), Cin, Cin_p, Cout, k, R, _dt(act), _stream())
+    _timed("wgrad", 2.0 * Cin * Cout * k * R, lambda: _call(
+        "sg_conv_wgrad", dp, dn, dstr, ap, an, astr, _p(_f32(dwg, "dwg")), Cin, Cin_p, Cout, k, R, _dt(act), _stream()))
 
 
 # ---- GroupNorm + activation ---------------------------------------------------------------------

@@ -53,10 +53,11 @@ def test_tc_fprop(shape):
     K.conv_fprop(wg, act, bias, o1, Cin)
     emu.conv_fprop(wg, act, bias, o2, Cin)
     torch.cuda.synchronize()
-    assert rel_l2(o1, o2) < 1e-4, rel_l2(o1, o2)
+    # gap columns t >= T are don't-care (the model convolves across the zero gap, the planes do not)
+    assert rel_l2(o1[:, :, :T], o2[:, :, :T]) < 1e-4, rel_l2(o1[:, :, :T], o2[:, :, :T])
     K.conv_fprop(wg, act, None, o1, Cin, accumulate=True)
     emu.conv_fprop(wg, act, None, o2, Cin, accumulate=True)
-    assert rel_l2(o1, o2) < 1e-4, rel_l2(o1, o2)
+    assert rel_l2(o1[:, :, :T], o2[:, :, :T]) < 1e-4, rel_l2(o1[:, :, :T], o2[:, :, :T])
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -68,10 +69,10 @@ def test_tc_dgrad(shape):
     K.conv_dgrad(wg, dy, d1, Cin)
     emu.conv_dgrad(wg, dy, d2, Cin)
     torch.cuda.synchronize()
-    assert rel_l2(d1, d2) < 1e-4, rel_l2(d1, d2)
+    assert rel_l2(d1[:, :, :T], d2[:, :, :T]) < 1e-4, rel_l2(d1[:, :, :T], d2[:, :, :T])
     K.conv_dgrad(wg, dy, d1, Cin, accumulate=True)
     emu.conv_dgrad(wg, dy, d2, Cin, accumulate=True)
-    assert rel_l2(d1, d2) < 1e-4, rel_l2(d1, d2)
+    assert rel_l2(d1[:, :, :T], d2[:, :, :T]) < 1e-4, rel_l2(d1[:, :, :T], d2[:, :, :T])
 
 
 @pytest.mark.parametrize("shape", SHAPES)
