@@ -41,13 +41,13 @@ __global__ void vec_sumsq_kernel(const float* __restrict__ x, int n, float* __re
     if (threadIdx.x == 0) out[0] = (float)t;
 }
 
-// uraw[o] += sum_{q in chunk} W[o][q] * vin[q] * scale      grid: (ceil(Wd/chunk), H), block 256
+// uraw[o] += sum_{q in chunk} W[o][q] * vin[q] * scale      grid: (H, ceil(Wd/chunk)), block 256
 // scale = 1 / max(sqrt(vsq[0]), eps) when vsq != NULL (training), else 1.
 __global__ void sn_w_v_kernel(const float* __restrict__ w, const float* __restrict__ vin, const float* __restrict__ vsq,
                               float* __restrict__ uraw, int H, int Wd, int k, long long so, long long si, int chunk) {
     __shared__ double sh[32];
-    int o = blockIdx.y;
-    int q_lo = blockIdx.x * chunk, q_hi = min(Wd, q_lo + chunk);
+    int o = blockIdx.x;
+    int q_lo = blockIdx.y * chunk, q_hi = min(Wd, q_lo + chunk);
     float acc = 0.f;
     for (int q = q_lo + threadIdx.x; q < q_hi; q += blockDim.x) acc += __ldg(w + wm_addr(o, q, k, so, si)) * __ldg(vin + q);
     double t = block_sum((double)acc, sh);
@@ -529,7 +529,7 @@ int sg_sn_power_iter(const float* w_orig, float* u, float* v, float* sigma, floa
     float* vsq = ws + Wd + H;
     cudaMemsetAsync(uraw, 0, sizeof(float) * H, st);
     int chunk = 4096;
-    dim3 g3((unsigned)cdiv(Wd, chunk), H);
+    dim3 g3(H, (unsigned)cdiv(Wd, chunk));
     if (training) {
         cudaMemsetAsync(vraw, 0, sizeof(float) * Wd, st);
         int rows = 64;

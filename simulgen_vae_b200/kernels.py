@@ -68,10 +68,21 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+PROFILE_ALL = None    # scripts/profile_step.py: list of (c_abi_name, start_event, end_event) for every call
+
+
 def _call(name, *args):
     global LAUNCHES
     LAUNCHES += 1
+    if PROFILE_ALL is None:
+        _lib.call(name, *args)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
     _lib.call(name, *args)
+    e1.record()
+    PROFILE_ALL.append((name, e0, e1))
 
 
 def _f32(t, name):
