@@ -108,14 +108,18 @@ int sg_gn_act_bwd(const float* y, const double* stats, const float* gamma, const
 /* ---- reconstruction head: Tanh(GroupNorm(y)) + losses (decoder.py:117-121, VAE_network.py:71-77,110-111)
  * y fp32 [N][B][Tp]; x, x_hat fp32 [B][N][T] (either may be NULL).  loss_sums[2] doubles (zeroed inside):
  * sum of the selected loss terms and sum of squared errors. */
+/* rowsums (optional, fp32 [N*B][4], 16-byte aligned; needs x): per-(n,b)-row partial sums of the GroupNorm
+ * backward reductions, taken while y and x are in registers anyway; sg_recon_bwd then needs one pass. */
 int sg_recon_fwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* x,
-                 float* x_hat, double* loss_sums, int N, int B, int T, int Tp, int G, int loss_kind, void* stream);
+                 float* x_hat, double* loss_sums, float* rowsums, int N, int B, int T, int Tp, int G, int loss_kind,
+                 void* stream);
 /* dx_hat = g_loss[0]*inv_numel*loss'(x_hat-x) + g_mse[0]*inv_numel*2(x_hat-x) + dxhat_ext (each optional),
  * then backward through tanh and GroupNorm -> dy (dtype, 1 plane), dgamma, dbeta, dbias.
+ * rowsums: the buffer sg_recon_fwd filled (or NULL: two passes; also used when dxhat_ext != NULL).
  * ws: >= 2*B*G + 2 doubles. */
 int sg_recon_bwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* x,
                  const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext,
-                 void* dy, float* dgamma, float* dbeta, float* dbias, double* ws,
+                 const float* rowsums, void* dy, float* dgamma, float* dbeta, float* dbias, double* ws,
                  int N, int B, int T, int Tp, int G, int loss_kind, int dtype, void* stream);
 /* out[i] = (float)(in[i] * scale), n small. */
 int sg_scale_f64_to_f32(const double* in, float* out, double scale, int n, void* stream);
@@ -161,6 +165,31 @@ int sg_philox_normal(float* out, int B, long long per_sample, unsigned long long
  * One launch over a flat fp32 parameter arena.  gnorm_sq (double, (+)=) receives sum g^2. */
 int sg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, double* gnorm_sq, void* stream);
+
+/* ---- multi-tensor optimiser step (train.py:92,156-168 for the whole model in two launches) -----------
+ * One item per parameter tensor.  Plain tensors (u == NULL): g is the gradient in p's layout.
+ * Spectral-normalised weights (u != NULL): g is the wgrad GEMM output dWg [k][Cout][Cin_p] (gradient wrt
+ * W/sigma); the gradient wrt weight_orig, (G - (<G,W>/sigma) u v^T)/sigma (spectral_norm.py:97-113 backward),
+ * is formed on the fly - `dot` (one double per item, inside `dots`) receives <G,W> in the first launch.
+ * p is walked in its native layout: Conv1d/Linear [Cout][Cin][k] (flip == 0), ConvTranspose1d
+ * [Cin][Cout][k] (flip == 1, taps reversed in G).  AdamW: torch.optim.AdamW semantics (amsgrad off);
+ * gnorm_sq (+)= sum of squared (scaled) gradients.  items_dev / items_host: the same array on the device
+ * (read by the kernels) and on the host (read to size the grid). */
+typedef struct {
+    float* p;            /* parameter (updated in place) */
+    const float* g;      /* gradient, see above */
+    float* m;            /* exp_avg */
+    float* v;            /* exp_avg_sq */
+    const float* u;      /* weight_u [Cout] or NULL */
+    const float* vv;     /* weight_v [Cin*k] */
+    const float* sigma;  /* [1] */
+    double* dot;         /* [1], scratch inside `dots` */
+    long long n;         /* elements of p */
+    int Cout, Cin, Cin_p, k, flip, reserved;
+} sg_opt_item;
+int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots, int n_dots,
+                float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                double* gnorm_sq, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,8 +33,8 @@ SIGNATURES = {
     "sg_gn_stats": [P, P, I, I, I, I, I, P],
     "sg_gn_act_fwd": [P, P, P, P, P, I, F, I, I, P, I, L, P, I, I, I, I, I, I, P],
     "sg_gn_act_bwd": [P, P, P, P, P, I, F, I, I, P, P, I, L, P, P, P, P, I, P, I, I, I, I, I, I, P],
-    "sg_recon_fwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, P],
-    "sg_recon_bwd": [P, P, P, P, P, P, P, F, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
+    "sg_recon_fwd": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, P],
+    "sg_recon_bwd": [P, P, P, P, P, P, P, F, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "sg_scale_f64_to_f32": [P, P, D, I, P],
     "sg_head_fwd": [P, P, P, P, P, I, I, I, I, I, P],
     "sg_head_bwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, P],
@@ -46,7 +46,15 @@ SIGNATURES = {
     "sg_kl2_reparam_bwd": [P, P, P, F, P, P, F, P, P, I, I, I, I, P],
     "sg_philox_normal": [P, I, L, U, U, L, P],
     "sg_adamw_step": [P, P, P, P, L, F, F, F, F, F, I, F, P, P],
+    "sg_opt_step": [P, P, I, P, I, F, F, F, F, F, I, F, P, P],
 }
+
+
+class OptItem(ctypes.Structure):
+    """sg_opt_item of include/simulgen_b200.h"""
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("u", c_void_p), ("vv", c_void_p),
+                ("sigma", c_void_p), ("dot", c_void_p), ("n", c_ll), ("Cout", c_int), ("Cin", c_int), ("Cin_p", c_int),
+                ("k", c_int), ("flip", c_int), ("reserved", c_int)]
 
 
 def load():

@@ -326,46 +326,185 @@ gn_bwd_apply_kernel(BwdArgs p, const double* __restrict__ S, OT* __restrict__ dy
 }
 
 // ---------------------------------------------------------------------------------------------
-// recon head forward: x_hat = tanh(GN(y)) in the external layout + loss sums
+// recon head forward: x_hat = tanh(GN(y)) in the external layout + loss sums (+ the per-row partial
+// sums of the GroupNorm backward, so that the backward needs ONE pass over y / x instead of two)
 // ---------------------------------------------------------------------------------------------
+// tanh(x) = 1 - 2 / (exp(2x) + 1): MUFU.EX2 + MUFU.RCP, abs error < 4e-7 (tanhf costs ~3x the issue slots;
+// these kernels run over B*N*T elements and were ALU-bound with it).
+__device__ __forceinline__ float tanh_fast(float x) {
+    float e = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, e + 1.f);
+}
+
+// 8 consecutive elements of an external-layout row ([B][N][T], row start 16-byte aligned when VEC)
+template <bool VEC>
+__device__ __forceinline__ F8 load8_ext(const float* row, int t0, int T) {
+    F8 r;
+    if (VEC && t0 + 8 <= T) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(row + t0));
+        float4 b = __ldg(reinterpret_cast<const float4*>(row + t0 + 4));
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+        r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = (t0 + i < T) ? __ldg(row + t0 + i) : 0.f;
+    }
+    return r;
+}
+template <bool VEC>
+__device__ __forceinline__ void store8_ext(float* row, int t0, int T, const F8& r) {
+    if (VEC && t0 + 8 <= T) {
+        *reinterpret_cast<float4*>(row + t0) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+        *reinterpret_cast<float4*>(row + t0 + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (t0 + i < T) row[t0 + i] = r.v[i];
+    }
+}
+
+// persistent: grid = min(rows / 8, a few waves); every warp strides over (n, b) rows.
+// rowsums[row] = (sum gL, sum gL*xn, sum gM, sum gM*xn) with gL = loss'(d)(1 - xh^2), gM = 2 d (1 - xh^2),
+// xn = (y - mean) rstd: the backward scales them by the upstream loss gradients (they are linear in them).
+template <bool VEC>
 __global__ void __launch_bounds__(kThreads)
 recon_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ x, float* __restrict__ x_hat,
-                 double* __restrict__ loss_sums, int N, int B, int T, int Tp, int G, int loss_kind, double inv_n) {
+                 double* __restrict__ loss_sums, float4* __restrict__ rowsums, int N, int B, int T, int Tp, int G,
+                 int loss_kind, double inv_n) {
     __shared__ double shm[2][32];
-    long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    float l0 = 0.f, l1 = 0.f;
-    if (row < (long long)N * B) {
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)N * B;
+    const long long wstride = (long long)gridDim.x * kWarpsPerBlock;
+    double d0 = 0.0, d1 = 0.0;
+    for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
         int n = (int)(row / B), b = (int)(row % B);
         GnStat st = gn_stat(stats, b, n / (N / G), G, inv_n);
         float a = gamma[n] * st.rstd, sh = beta[n] - st.mean * a;
         const float* yrow = y + row * Tp;
         long long xo = ((long long)b * N + n) * T;
-        for (int seg = lane; seg < Tp / 8; seg += 32) {
+        float l0 = 0.f, l1 = 0.f, aL = 0.f, bL = 0.f, aM = 0.f, bM = 0.f;
+        for (int seg = lane; seg * 8 < T; seg += 32) {
             F8 yv = load8(yrow + seg * 8);
+            F8 xv, xh;
+            if (x != nullptr) xv = load8_ext<VEC>(x + xo, seg * 8, T);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                int t = seg * 8 + i;
-                if (t < T) {
-                    float xh = tanhf(yv.v[i] * a + sh);
-                    if (x_hat != nullptr) x_hat[xo + t] = xh;
-                    if (x != nullptr) {
-                        float d = xh - __ldg(x + xo + t);
-                        l0 += loss_term(loss_kind, d);
-                        l1 += d * d;
+                bool valid = seg * 8 + i < T;
+                float h = tanh_fast(yv.v[i] * a + sh);
+                xh.v[i] = h;
+                if (x != nullptr && valid) {
+                    float d = h - xv.v[i];
+                    l0 += loss_term(loss_kind, d);
+                    l1 += d * d;
+                    if (rowsums != nullptr) {
+                        float om = 1.f - h * h;
+                        float xn = (yv.v[i] - st.mean) * st.rstd;
+                        float gl = loss_grad(loss_kind, d) * om, gm = 2.f * d * om;
+                        aL += gl; bL += gl * xn; aM += gm; bM += gm * xn;
                     }
                 }
             }
+            if (x_hat != nullptr) store8_ext<VEC>(x_hat + xo, seg * 8, T, xh);
         }
+        if (rowsums != nullptr) {
+            aL = warp_sum(aL); bL = warp_sum(bL); aM = warp_sum(aM); bM = warp_sum(bM);
+            if (lane == 0) rowsums[row] = make_float4(aL, bL, aM, bM);
+        }
+        d0 += (double)l0;   // flush the fp32 partials per row
+        d1 += (double)l1;
     }
     if (x != nullptr) {
-        double t0 = block_sum((double)l0, shm[0]);
-        double t1 = block_sum((double)l1, shm[1]);
+        double t0 = block_sum(d0, shm[0]);
+        double t1 = block_sum(d1, shm[1]);
         if (threadIdx.x == 0) {
             atomicAdd(&loss_sums[0], t0);
             atomicAdd(&loss_sums[1], t1);
         }
+    }
+}
+
+// backward, step 1 of the one-pass path: fold the forward's row sums with the upstream scalars.
+// grid (ceil(Cg / 64), G), block 256: warp w handles channels c0 + w, c0 + w + 8, ... (< 64 per block)
+// dgamma[c] = sum_b Bx, dbeta[c] = sum_b A, S[b][g] += gamma_c * (A, Bx)  with (A, Bx) = ga*(.L) + gm*(.M)
+__global__ void __launch_bounds__(kThreads)
+recon_bwd_combine_kernel(const float4* __restrict__ rowsums, const float* __restrict__ scal,
+                         const float* __restrict__ gamma, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         double* __restrict__ S, int N, int B, int G) {
+    extern __shared__ float sacc[];   // [B][2]
+    const int Cg = N / G, g = blockIdx.y;
+    const int c_lo = g * Cg + blockIdx.x * 64, c_hi = min(c_lo + 64, (g + 1) * Cg);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 2 * B; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    const float ga = scal[0], gm = scal[1];
+    for (int c = c_lo + warp; c < c_hi; c += kWarpsPerBlock) {
+        float gam = gamma[c], sa = 0.f, sb = 0.f;
+        for (int b = lane; b < B; b += 32) {
+            float4 r = rowsums[(long long)c * B + b];
+            float A = ga * r.x + gm * r.z, Bx = ga * r.y + gm * r.w;
+            sa += A;
+            sb += Bx;
+            atomicAdd(&sacc[2 * b], gam * A);
+            atomicAdd(&sacc[2 * b + 1], gam * Bx);
+        }
+        sa = warp_sum(sa);
+        sb = warp_sum(sb);
+        if (lane == 0) {
+            dbeta[c] = sa;
+            dgamma[c] = sb;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * B; i += blockDim.x)
+        atomicAdd(&S[(size_t)((i >> 1) * G + g) * 2 + (i & 1)], (double)sacc[i]);
+}
+
+// backward, step 2: dy = rstd * (gamma * g - m1 - xn * m2), g = (ga loss'(d) + gm 2d)(1 - xh^2)
+template <typename OT, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+recon_bwd_apply_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const float* __restrict__ x, const float* __restrict__ scal,
+                       const double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias, int N, int B, int T,
+                       int Tp, int G, int loss_kind, double inv_n) {
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)N * B;
+    const long long wstride = (long long)gridDim.x * kWarpsPerBlock;
+    const float ga = scal[0], gm = scal[1];
+    for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
+        int n = (int)(row / B), b = (int)(row % B);
+        int g = n / (N / G);
+        GnStat st = gn_stat(stats, b, g, G, inv_n);
+        float gam = gamma[n];
+        float a = gam * st.rstd, sh = beta[n] - st.mean * a;
+        float m1 = (float)(S[(size_t)(b * G + g) * 2] * inv_n);
+        float m2 = (float)(S[(size_t)(b * G + g) * 2 + 1] * inv_n);
+        const float* yrow = y + row * Tp;
+        long long xo = ((long long)b * N + n) * T;
+        float db = 0.f;
+        for (int seg = lane; seg < Tp / 8; seg += 32) {
+            F8 o;
+            if (seg * 8 < T) {
+                F8 yv = load8(yrow + seg * 8);
+                F8 xv = load8_ext<VEC>(x + xo, seg * 8, T);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float h = tanh_fast(yv.v[i] * a + sh);
+                    float d = h - xv.v[i];
+                    float gg = (ga * loss_grad(loss_kind, d) + gm * 2.f * d) * (1.f - h * h);
+                    float xn = (yv.v[i] - st.mean) * st.rstd;
+                    float v = (seg * 8 + i < T) ? st.rstd * (gam * gg - m1 - xn * m2) : 0.f;
+                    o.v[i] = v;
+                    db += v;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+            }
+            store8(dy + row * Tp + seg * 8, o);
+        }
+        db = warp_sum(db);
+        if (lane == 0) atomicAdd(&dbias[n], db);
     }
 }
 
@@ -501,14 +640,29 @@ int sg_gn_act_bwd(const float* y, const double* stats, const float* gamma, const
                                 dres_accumulate, ws, as_stream(stream));
 }
 
+static int persistent_grid(long long rows) {
+    long long blocks = cdiv(rows, kWarpsPerBlock);
+    long long cap = 148LL * 16;
+    return (int)(blocks < cap ? blocks : cap);
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 int sg_recon_fwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* x,
-                 float* x_hat, double* loss_sums, int N, int B, int T, int Tp, int G, int loss_kind, void* stream) {
+                 float* x_hat, double* loss_sums, float* rowsums, int N, int B, int T, int Tp, int G, int loss_kind,
+                 void* stream) {
     SG_REQUIRE(G > 0 && N % G == 0, "recon_fwd: N=%d not divisible by G=%d", N, G);
+    SG_REQUIRE(rowsums == nullptr || (x != nullptr && aligned16(rowsums)), "recon_fwd: rowsums needs x and 16-byte alignment");
     cudaStream_t st = as_stream(stream);
     if (x != nullptr) cudaMemsetAsync(loss_sums, 0, sizeof(double) * 2, st);
     double inv_n = 1.0 / ((double)(N / G) * T);
-    recon_fwd_kernel<<<rows_grid((long long)N * B), kThreads, 0, st>>>(y, stats, gamma, beta, x, x_hat, loss_sums, N,
-                                                                        B, T, Tp, G, loss_kind, inv_n);
+    bool vec = (T % 4 == 0) && aligned16(x) && aligned16(x_hat);
+    int grid = persistent_grid((long long)N * B);
+    if (vec)
+        recon_fwd_kernel<true><<<grid, kThreads, 0, st>>>(y, stats, gamma, beta, x, x_hat, loss_sums, (float4*)rowsums, N,
+                                                          B, T, Tp, G, loss_kind, inv_n);
+    else
+        recon_fwd_kernel<false><<<grid, kThreads, 0, st>>>(y, stats, gamma, beta, x, x_hat, loss_sums, (float4*)rowsums,
+                                                           N, B, T, Tp, G, loss_kind, inv_n);
     return check_launch("recon_fwd");
 }
 
@@ -579,24 +733,42 @@ recon_bwd_kernel(BwdArgs p, const float* __restrict__ scal, float* __restrict__ 
 
 extern "C" int sg_recon_bwd(const float* y, const double* stats, const float* gamma, const float* beta,
                             const float* x, const float* g_loss, const float* g_mse, float inv_numel,
-                            const float* dxhat_ext, void* dy, float* dgamma, float* dbeta, float* dbias, double* ws,
-                            int N, int B, int T, int Tp, int G, int loss_kind, int dtype, void* stream) {
+                            const float* dxhat_ext, const float* rowsums, void* dy, float* dgamma, float* dbeta,
+                            float* dbias, double* ws, int N, int B, int T, int Tp, int G, int loss_kind, int dtype,
+                            void* stream) {
     SG_REQUIRE(G > 0 && N % G == 0 && Tp % 8 == 0, "recon_bwd: bad shape");
     SG_REQUIRE(x != nullptr || (g_loss == nullptr && g_mse == nullptr), "recon_bwd: loss gradient without x");
     cudaStream_t st = as_stream(stream);
-    BwdArgs p{};
-    p.y = y; p.stats = stats; p.gamma = gamma; p.beta = beta; p.res = nullptr; p.res_scale = 1.f;
-    p.act = SG_ACT_TANH; p.post_gelu = 0; p.dout = nullptr; p.x = x; p.ext = dxhat_ext; p.loss_kind = loss_kind;
-    p.C = N; p.B = B; p.T = T; p.Tp = Tp; p.G = G;
-    p.inv_n = 1.0 / ((double)(N / G) * T);
+    double inv_n = 1.0 / ((double)(N / G) * T);
     // workspace: 2*B*G doubles for S followed by 2 floats for the folded scalars
     double* S = ws;
     float* scal = reinterpret_cast<float*>(ws + 2 * (size_t)B * G);
     cudaMemsetAsync(S, 0, sizeof(double) * 2 * B * G, st);
-    cudaMemsetAsync(dgamma, 0, sizeof(float) * N, st);
-    cudaMemsetAsync(dbeta, 0, sizeof(float) * N, st);
     cudaMemsetAsync(dbias, 0, sizeof(float) * N, st);
     recon_scalars_kernel<<<1, 1, 0, st>>>(g_loss, g_mse, inv_numel, scal);
+    if (rowsums != nullptr && dxhat_ext == nullptr && x != nullptr) {
+        // one pass over y / x: the reductions of the GroupNorm backward were taken by the forward
+        SG_REQUIRE((size_t)B * 2 * sizeof(float) <= 48 * 1024, "recon_bwd: batch too large for the combine kernel");
+        dim3 gc((unsigned)cdiv(N / G, 64), G);
+        recon_bwd_combine_kernel<<<gc, kThreads, sizeof(float) * 2 * B, st>>>((const float4*)rowsums, scal, gamma, dgamma,
+                                                                               dbeta, S, N, B, G);
+        int grid = persistent_grid((long long)N * B);
+        bool vec = (T % 4 == 0) && aligned16(x);
+#define SG_APPLY(OT, VEC)                                                                                       \
+    recon_bwd_apply_kernel<OT, VEC><<<grid, kThreads, 0, st>>>(y, stats, gamma, beta, x, scal, S, (OT*)dy, dbias, N, B, \
+                                                                T, Tp, G, loss_kind, inv_n)
+        if (dtype == SG_BF16) { if (vec) SG_APPLY(__nv_bfloat16, true); else SG_APPLY(__nv_bfloat16, false); }
+        else                  { if (vec) SG_APPLY(float, true); else SG_APPLY(float, false); }
+#undef SG_APPLY
+        return check_launch("recon_bwd");
+    }
+    BwdArgs p{};
+    p.y = y; p.stats = stats; p.gamma = gamma; p.beta = beta; p.res = nullptr; p.res_scale = 1.f;
+    p.act = SG_ACT_TANH; p.post_gelu = 0; p.dout = nullptr; p.x = x; p.ext = dxhat_ext; p.loss_kind = loss_kind;
+    p.C = N; p.B = B; p.T = T; p.Tp = Tp; p.G = G;
+    p.inv_n = inv_n;
+    cudaMemsetAsync(dgamma, 0, sizeof(float) * N, st);
+    cudaMemsetAsync(dbeta, 0, sizeof(float) * N, st);
     int grid = rows_grid((long long)N * B);
     if (dtype == SG_BF16) {
         recon_bwd_kernel<__nv_bfloat16, true><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (__nv_bfloat16*)dy, dbias);

@@ -1,0 +1,215 @@
+// Multi-tensor optimiser step: spectral-norm weight gradient + AdamW + global gradient norm in two
+// launches for the whole model (train.py:92,156-168; torch/nn/utils/spectral_norm.py:97-113 backward).
+//
+// The per-layer path (sg_sn_weight_grad + sg_adamw_step) costs two passes over every weight gradient,
+// a materialised gradient in the reference layout and ~250 launches per step.  Here the wgrad GEMM
+// output G (fp32, GEMM layout [k][Cout][Cin_p]) is consumed directly:
+//     dot_l  = <G_l, W_l>                                          (launch 1, all layers)
+//     grad   = (G - (dot/sigma) u v^T) / sigma  ->  AdamW update   (launch 2, all tensors)
+// Launch 2 walks every tensor in its NATIVE layout (p, m, v coalesced); G is gathered from its k tap
+// planes.  HBM traffic per element: launch 1 reads G, W (8 B); launch 2 reads G, W, m, v and writes
+// W, m, v (28 B) - the AdamW minimum.
+#include "common.cuh"
+
+namespace sg {
+
+constexpr int kOptChunk = 8192;      // elements per CTA
+constexpr int kOptThreads = 256;
+constexpr int kMaxItems = 512;
+
+struct OptPrefix {
+    int n_items;
+    int start[kMaxItems + 1];        // first chunk of item i; start[n_items] = total chunks
+};
+
+__device__ __forceinline__ int find_item(const OptPrefix& pf, int chunk) {
+    int lo = 0, hi = pf.n_items;     // invariant: start[lo] <= chunk < start[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (pf.start[mid] <= chunk) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ bool aligned16(const void* a, const void* b) {
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
+// native flat index e of weight_orig -> (o, q = i*k + j, index into the GEMM-layout gradient)
+__device__ __forceinline__ void decode(const sg_opt_item& it, int e, int& o, int& q, long long& gidx) {
+    int i, j;
+    if (it.k == 1 && !it.flip) {
+        o = e / it.Cin;
+        i = e - o * it.Cin;
+        j = 0;
+    } else if (!it.flip) {           // Conv1d [Cout][Cin][k]
+        int wd = it.Cin * it.k;
+        o = e / wd;
+        int r = e - o * wd;
+        i = r / it.k;
+        j = r - i * it.k;
+    } else {                         // ConvTranspose1d [Cin][Cout][k]
+        int wd = it.Cout * it.k;
+        i = e / wd;
+        int r = e - i * wd;
+        o = r / it.k;
+        j = r - o * it.k;
+    }
+    q = i * it.k + j;
+    int jj = it.flip ? it.k - 1 - j : j;
+    gidx = ((long long)jj * it.Cout + o) * it.Cin_p + i;
+}
+
+__global__ void __launch_bounds__(kOptThreads)
+opt_dot_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ OptPrefix pf) {
+    __shared__ double sh[32];
+    const int idx = find_item(pf, blockIdx.x);
+    const sg_opt_item it = items[idx];
+    if (it.u == nullptr) return;
+    const long long e0 = (long long)(blockIdx.x - pf.start[idx]) * kOptChunk;
+    const long long e1 = min(it.n, e0 + kOptChunk);
+    float acc = 0.f;
+    const bool direct = it.k == 1 && !it.flip && it.Cin_p == it.Cin;
+    if (direct && (it.n & 3) == 0 && aligned16(it.g, it.p)) {
+        for (long long e = e0 + threadIdx.x * 4; e < e1; e += kOptThreads * 4) {
+            float4 g = *reinterpret_cast<const float4*>(it.g + e);
+            float4 w = *reinterpret_cast<const float4*>(it.p + e);
+            acc += g.x * w.x + g.y * w.y + g.z * w.z + g.w * w.w;
+        }
+    } else {
+        for (long long e = e0 + threadIdx.x; e < e1; e += kOptThreads) {
+            int o, q;
+            long long gi;
+            decode(it, (int)e, o, q, gi);
+            acc += it.g[gi] * it.p[e];
+        }
+    }
+    double t = block_sum((double)acc, sh);
+    if (threadIdx.x == 0) atomicAdd(it.dot, t);
+}
+
+struct AdamArgs {
+    float lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale;
+};
+
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamArgs& a) {
+    p = p * (1.f - a.lr * a.wd);
+    m = a.b1 * m + (1.f - a.b1) * g;
+    v = a.b2 * v + (1.f - a.b2) * g * g;
+    float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+    p = p - (a.lr / a.bc1) * (m / denom);
+}
+
+__global__ void __launch_bounds__(kOptThreads)
+opt_step_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ OptPrefix pf, AdamArgs a,
+                double* __restrict__ gnorm_sq) {
+    __shared__ double sh[32];
+    const int idx = find_item(pf, blockIdx.x);
+    const sg_opt_item it = items[idx];
+    const long long e0 = (long long)(blockIdx.x - pf.start[idx]) * kOptChunk;
+    const long long e1 = min(it.n, e0 + kOptChunk);
+    const bool sn = it.u != nullptr;
+    float inv_sigma = 1.f, coef = 0.f;
+    if (sn) {
+        float s = it.sigma[0];
+        inv_sigma = 1.f / s;
+        coef = (float)(it.dot[0] / (double)s);
+    }
+    float ss = 0.f;
+    const bool direct = !sn || (it.k == 1 && !it.flip && it.Cin_p == it.Cin);
+    if (direct && (it.n & 3) == 0 && (!sn || ((it.Cin & 3) == 0 && aligned16(it.vv, it.vv))) && aligned16(it.g, it.p) &&
+        aligned16(it.m, it.v)) {
+        for (long long e = e0 + threadIdx.x * 4; e < e1; e += kOptThreads * 4) {
+            float4 g4 = *reinterpret_cast<const float4*>(it.g + e);
+            float4 p4 = *reinterpret_cast<const float4*>(it.p + e);
+            float4 m4 = *reinterpret_cast<const float4*>(it.m + e);
+            float4 v4 = *reinterpret_cast<const float4*>(it.v + e);
+            float g[4] = {g4.x, g4.y, g4.z, g4.w};
+            float p[4] = {p4.x, p4.y, p4.z, p4.w};
+            float m[4] = {m4.x, m4.y, m4.z, m4.w};
+            float v[4] = {v4.x, v4.y, v4.z, v4.w};
+            if (sn) {
+                int o = (int)(e / it.Cin);
+                int q = (int)(e - (long long)o * it.Cin);
+                float cu = coef * __ldg(it.u + o);
+                float4 vv = __ldg(reinterpret_cast<const float4*>(it.vv + q));
+                g[0] = (g[0] - cu * vv.x) * inv_sigma;
+                g[1] = (g[1] - cu * vv.y) * inv_sigma;
+                g[2] = (g[2] - cu * vv.z) * inv_sigma;
+                g[3] = (g[3] - cu * vv.w) * inv_sigma;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float gi = g[i] * a.grad_scale;
+                ss += gi * gi;
+                adam_update(p[i], m[i], v[i], gi, a);
+            }
+            *reinterpret_cast<float4*>(it.p + e) = make_float4(p[0], p[1], p[2], p[3]);
+            *reinterpret_cast<float4*>(it.m + e) = make_float4(m[0], m[1], m[2], m[3]);
+            *reinterpret_cast<float4*>(it.v + e) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    } else {
+        for (long long e = e0 + threadIdx.x; e < e1; e += kOptThreads) {
+            float g;
+            if (sn) {
+                int o, q;
+                long long gi;
+                decode(it, (int)e, o, q, gi);
+                g = (it.g[gi] - coef * __ldg(it.u + o) * __ldg(it.vv + q)) * inv_sigma;
+            } else {
+                g = it.g[e];
+            }
+            g *= a.grad_scale;
+            ss += g * g;
+            float p = it.p[e], m = it.m[e], v = it.v[e];
+            adam_update(p, m, v, g, a);
+            it.p[e] = p;
+            it.m[e] = m;
+            it.v[e] = v;
+        }
+    }
+    if (gnorm_sq != nullptr) {
+        double t = block_sum((double)ss, sh);
+        if (threadIdx.x == 0) atomicAdd(gnorm_sq, t);
+    }
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots,
+                           int n_dots, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                           float grad_scale, double* gnorm_sq, void* stream) {
+    SG_REQUIRE(n_items > 0 && n_items <= kMaxItems, "opt_step: n_items=%d out of range (max %d)", n_items, kMaxItems);
+    cudaStream_t st = as_stream(stream);
+    OptPrefix pf;
+    pf.n_items = n_items;
+    long long total = 0;
+    bool any_sn = false;
+    for (int i = 0; i < n_items; ++i) {
+        const sg_opt_item& it = items_host[i];
+        SG_REQUIRE(it.n > 0 && it.n < (1LL << 31), "opt_step: item %d has n=%lld", i, it.n);
+        if (it.u != nullptr) {
+            any_sn = true;
+            SG_REQUIRE(it.dot != nullptr && it.sigma != nullptr && it.vv != nullptr && it.k >= 1 &&
+                           (long long)it.Cout * it.Cin * it.k == it.n && it.Cin_p >= it.Cin,
+                       "opt_step: item %d has inconsistent spectral-norm fields", i);
+        }
+        pf.start[i] = (int)total;
+        total += cdiv(it.n, kOptChunk);
+    }
+    SG_REQUIRE(total < (1LL << 31), "opt_step: too many chunks");
+    pf.start[n_items] = (int)total;
+    if (any_sn) {
+        SG_REQUIRE(dots != nullptr && n_dots > 0, "opt_step: dots buffer missing");
+        cudaMemsetAsync(dots, 0, sizeof(double) * n_dots, st);
+        opt_dot_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf);
+    }
+    AdamArgs a;
+    a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.wd = weight_decay; a.grad_scale = grad_scale;
+    a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    a.bc2_sqrt = sqrtf((float)(1.0 - pow((double)beta2, (double)step)));
+    opt_step_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, a, gnorm_sq);
+    return check_launch("opt_step");
+}

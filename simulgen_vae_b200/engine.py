@@ -105,6 +105,108 @@ def draw_eps(shape, device):
 
 
 # ------------------------------------------------------------------------------------------------
+# gradient sink: persistent destinations for parameter gradients (Trainer's fused optimiser path)
+# ------------------------------------------------------------------------------------------------
+class GradSink:
+    """Owns one flat fp32 arena for the wgrad GEMM outputs (GEMM layout, consumed as is by the fused
+    spectral-norm-gradient + AdamW kernel) and one for the small vectors (biases, GroupNorm affine).
+    Buffers are bump-allocated in the order backward first produces them, so the arena is laid out in
+    backward-completion order: contiguous slices are all-reduced while the rest of backward runs.
+    With a sink installed the autograd Functions return no parameter gradients (p.grad stays None)."""
+
+    ALIGN = 64
+
+    def __init__(self, weight_elems, vec_elems, n_layers, device):
+        self.dev = device
+        self.weights = torch.zeros(max(weight_elems, 1), dtype=torch.float32, device=device)
+        self.vecs = torch.zeros(max(vec_elems, 1), dtype=torch.float32, device=device)
+        self.sigmas = torch.ones(max(n_layers, 1), dtype=torch.float32, device=device)
+        self.w_used = self.v_used = self.s_used = 0
+        self.w_slots, self.v_slots, self.s_slots = {}, {}, {}
+        self.items = {}                 # id(param) -> optimiser item description (first backward)
+        self.order = []                 # params in commit order
+        self.committed = 0              # arena elements whose producers have been enqueued this step
+        self.on_commit = None           # callback(committed_elems) for the data-parallel driver
+        self.frozen = False
+
+    @staticmethod
+    def _round(n):
+        return (n + GradSink.ALIGN - 1) // GradSink.ALIGN * GradSink.ALIGN
+
+    def begin_step(self):
+        self.committed = 0
+
+    def sigma_buffer(self, param):
+        key = id(param)
+        if key not in self.s_slots:
+            if self.s_used >= self.sigmas.numel():
+                raise RuntimeError("simulgen_b200: GradSink sigma arena exhausted")
+            self.s_slots[key] = self.s_used
+            self.s_used += 1
+        i = self.s_slots[key]
+        return self.sigmas[i:i + 1]
+
+    def weight_buffer(self, param, shape):
+        key = id(param)
+        n = 1
+        for d in shape:
+            n *= d
+        if key not in self.w_slots:
+            if self.frozen:
+                raise RuntimeError("simulgen_b200: a parameter produced a gradient for the first time after the "
+                                   "optimiser plan was built")
+            if self.w_used + n > self.weights.numel():
+                raise RuntimeError("simulgen_b200: GradSink weight arena exhausted")
+            self.w_slots[key] = (self.w_used, n)
+            self.w_used += self._round(n)
+        off, n0 = self.w_slots[key]
+        if n0 != n:
+            raise RuntimeError("simulgen_b200: weight-gradient shape changed between steps")
+        return self.weights[off:off + n].view(shape)
+
+    def vec_buffer(self, param, n):
+        key = id(param)
+        if key not in self.v_slots:
+            if self.frozen:
+                raise RuntimeError("simulgen_b200: a parameter produced a gradient for the first time after the "
+                                   "optimiser plan was built")
+            if self.v_used + n > self.vecs.numel():
+                raise RuntimeError("simulgen_b200: GradSink vector arena exhausted")
+            self.v_slots[key] = (self.v_used, n)
+            self.items[key] = dict(param=param, g=self.vecs[self.v_used:self.v_used + n])
+            self.order.append(key)
+            self.v_used += self._round(n)
+        off, n0 = self.v_slots[key]
+        if n0 != n:
+            raise RuntimeError("simulgen_b200: gradient size changed between steps")
+        return self.vecs[off:off + n0]
+
+    def commit_weight(self, prep, dwg):
+        """Called once the wgrad GEMM writing `dwg` (a weight_buffer) has been enqueued."""
+        key = id(prep.w)
+        if key not in self.items:
+            self.items[key] = dict(param=prep.w, g=dwg, u=prep.u, vv=prep.v, sigma=prep.sigma, Cout=prep.Cout,
+                                   Cin=prep.Cin, Cin_p=prep.Cin_p, k=prep.k, flip=prep.flip)
+            self.order.append(key)
+        off, n = self.w_slots[key]
+        self.committed = max(self.committed, off + self._round(n))
+        if self.on_commit is not None:
+            self.on_commit(self.committed)
+
+
+_sink = threading.local()
+
+
+def set_grad_sink(sink):
+    """Install (or remove, with None) the gradient sink used by the next forward/backward of this thread."""
+    _sink.value = sink
+
+
+def get_grad_sink():
+    return getattr(_sink, "value", None)
+
+
+# ------------------------------------------------------------------------------------------------
 # tape primitives
 # ------------------------------------------------------------------------------------------------
 class Act:
@@ -146,7 +248,7 @@ class Ctx:
         self.op_dtype = torch.bfloat16 if _PRECISION == "bf16" else torch.float32
         self.pgrads = {}
         self.capture = capture
-        self.on_param_grad = None       # callback(param, grad) used by the data-parallel driver
+        self.sink = get_grad_sink() if record else None
 
     # -- allocation helpers ------------------------------------------------------------------
     def f32(self, *shape):
@@ -166,15 +268,33 @@ class Ctx:
         return act.grad, 1
 
     def set_pgrad(self, param, grad):
-        if param is None or grad is None:
-            return
+        if param is None or grad is None or self.sink is not None:
+            return                      # with a sink the gradient already sits in its persistent buffer
         key = id(param)
         if key in self.pgrads:
             K.axpy(self.pgrads[key], grad, 1.0, True)
         else:
             self.pgrads[key] = grad
-        if self.on_param_grad is not None:
-            self.on_param_grad(param, self.pgrads[key])
+
+    def vec_grad(self, param, n):
+        """fp32 [n] buffer for the gradient of a bias / GroupNorm affine vector (None if there is no such
+        parameter).  Persistent when a sink is installed."""
+        if param is None:
+            return None
+        if self.sink is not None and param.requires_grad:
+            return self.sink.vec_buffer(param, n)
+        return self.f32(n)
+
+    def weight_grad_buf(self, prep, *shape):
+        """fp32 buffer for the wgrad GEMM output of a layer (GEMM layout)."""
+        if self.sink is not None and prep.sn:
+            return self.sink.weight_buffer(prep.w, shape)
+        return self.f32(*shape)
+
+    def sigma_buf(self, param):
+        if self.sink is not None:
+            return self.sink.sigma_buffer(param)
+        return self.f32(1)
 
     def cap(self, name, act: Act):
         if self.capture is None:
@@ -224,7 +344,7 @@ def prep_conv(ctx: Ctx, mod, transposed=False) -> _Prep:
     p.Cin, p.Cout, p.k, p.so, p.si, p.flip = Cin, Cout, k, so, si, flip
     p.Cin_p = (Cin + 7) // 8 * 8
     if sn:
-        p.sigma = ctx.f32(1)
+        p.sigma = ctx.sigma_buf(w)
         K.sn_power_iter(w, u, v, p.sigma, Cout, Cin, k, so, si, mod.training)
         p.version = _bump_version(mod) if mod.training else getattr(mod, "_sg_sn_version", 0)
     else:
@@ -243,7 +363,7 @@ def prep_linear(ctx: Ctx, mod) -> _Prep:
     p.Cin, p.Cout, p.k, p.so, p.si, p.flip, p.Cin_p = In, O, 1, In, 1, 0, In
     p.wg = None
     if sn:
-        p.sigma = ctx.f32(1)
+        p.sigma = ctx.sigma_buf(w)
         K.sn_power_iter(w, u, v, p.sigma, O, In, 1, In, 1, mod.training)
         p.version = _bump_version(mod) if mod.training else getattr(mod, "_sg_sn_version", 0)
     else:
@@ -257,7 +377,13 @@ def _weight_grad(ctx: Ctx, mod, p: _Prep, dwg):
     if p.sn and getattr(mod, "_sg_sn_version", 0) != p.version:
         raise RuntimeError("simulgen_b200: spectral-norm state of a layer advanced between forward and backward "
                            "(two training forwards before one backward are not supported)")
-    grad = torch.empty_like(p.w)
+    if ctx.sink is not None and p.sn:
+        ctx.sink.commit_weight(p, dwg)  # consumed in the GEMM layout by the fused optimiser kernel
+        return
+    if ctx.sink is not None:
+        grad = ctx.sink.vec_buffer(p.w, p.w.numel()).view(p.w.shape)
+    else:
+        grad = torch.empty_like(p.w)
     if p.sn:
         u, v = p.u, p.v
     else:
@@ -308,9 +434,9 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
                 return
             out.grad = None
             dy = ctx.op(p.k, p.Cout, B, Tp)          # k planes: dgrad reads dy shifted by the taps
-            dgamma = ctx.f32(p.Cout) if gn is not None else None
-            dbeta = ctx.f32(p.Cout) if gn is not None else None
-            dbias = ctx.f32(p.Cout) if conv.bias is not None else None
+            dgamma = ctx.vec_grad(gn.weight, p.Cout) if gn is not None else None
+            dbeta = ctx.vec_grad(gn.bias, p.Cout) if gn is not None else None
+            dbias = ctx.vec_grad(conv.bias, p.Cout)
             dres, acc = (None, 0)
             if res is not None and res.needs_grad:
                 dres, acc = ctx.grad_buf(res)
@@ -321,7 +447,7 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
                 ctx.set_pgrad(gn.bias, dbeta)
             ctx.set_pgrad(conv.bias, dbias)
             if p.w.requires_grad:
-                dwg = ctx.f32(p.k, p.Cout, p.Cin_p)
+                dwg = ctx.weight_grad_buf(p, p.k, p.Cout, p.Cin_p)
                 K.conv_wgrad(dy, a_in.data, dwg, p.Cin)
                 _weight_grad(ctx, conv, p, dwg)
             if a_in.needs_grad:
@@ -364,8 +490,8 @@ def head(ctx: Ctx, lin, h: Act, ext_out: bool = True):
             g = ext.grad
             if g is None:
                 return
-            dwn = ctx.f32(O, p.Cin)
-            dbias = ctx.f32(O)
+            dwn = ctx.weight_grad_buf(p, 1, O, p.Cin).view(O, p.Cin)
+            dbias = ctx.vec_grad(lin.bias, O)
             dh, acc = ctx.grad_buf(h) if h.needs_grad else (None, 0)
             K.head_bwd(hf, p.w, p.sigma, g, dwn, dbias, dh, acc, T)
             ctx.set_pgrad(lin.bias, dbias)
@@ -389,8 +515,8 @@ def latent_seq(ctx: Ctx, seq, z: Ext, out_op_view=None, out_planes=1, name="") -
             if g is None:
                 return
             a.grad = None
-            dwn = ctx.f32(D * T, D)
-            dbias = ctx.f32(D * T)
+            dwn = ctx.weight_grad_buf(p, 1, D * T, D).view(D * T, D)
+            dbias = ctx.vec_grad(lin.bias, D * T)
             dz = ctx.f32(B, D)
             K.latent_bwd(z.tensor, p.w, p.sigma, g, dwn, dbias, dz, T)
             ctx.set_pgrad(lin.bias, dbias)
@@ -524,7 +650,9 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     res = dict(x_hat=x_hat, recon=None, mse=None, kls=kls)
     loss_kind = K.LOSS_KINDS.get(lossfun, 0)
     sums = ctx.f64(2)
-    K.recon_fwd(y, stats, gn.weight, gn.bias, x, x_hat, sums, T, G, loss_kind)
+    # training: the forward also takes the row sums of the GroupNorm backward (one backward pass instead of two)
+    rowsums = ctx.f32(N * B, 4) if (ctx.tape is not None and x is not None) else None
+    K.recon_fwd(y, stats, gn.weight, gn.bias, x, x_hat, sums, T, G, loss_kind, rowsums)
     inv_numel = 1.0 / float(B * N * T)
     if x is not None:
         both = ctx.f32(2)
@@ -540,14 +668,14 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
             if g_loss is None and g_mse is None and g_ext is None:
                 return
             dy = ctx.op(1, N, B, Tp)
-            dgamma, dbeta, dbias = ctx.f32(N), ctx.f32(N), ctx.f32(N)
+            dgamma, dbeta, dbias = ctx.vec_grad(gn.weight, N), ctx.vec_grad(gn.bias, N), ctx.vec_grad(conv.bias, N)
             K.recon_bwd(y, stats, gn.weight, gn.bias, x, g_loss, g_mse, inv_numel, g_ext, dy, dgamma, dbeta, dbias,
-                        T, G, loss_kind)
+                        T, G, loss_kind, rowsums)
             ctx.set_pgrad(gn.weight, dgamma)
             ctx.set_pgrad(gn.bias, dbeta)
             ctx.set_pgrad(conv.bias, dbias)
             if p.w.requires_grad:
-                dwg = ctx.f32(p.k, p.Cout, p.Cin_p)
+                dwg = ctx.weight_grad_buf(p, p.k, p.Cout, p.Cin_p)
                 K.conv_wgrad(dy, out.data, dwg, p.Cin)
                 _weight_grad(ctx, conv, p, dwg)
             dx, acc = ctx.grad_buf(out)

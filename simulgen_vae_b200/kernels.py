@@ -194,19 +194,22 @@ def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, 
           int(dres_accumulate), _p(ws), C, B, T, Tp, int(G), _dt(dy), _stream())
 
 
-def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind):
+def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind, rowsums=None):
+    """rowsums: optional fp32 [N*B, 4] - partial sums of the GroupNorm backward taken by the forward."""
     N, B, Tp = y.shape
-    _call("sg_recon_fwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(x), _p(x_hat), _p(loss_sums), N, B, T, Tp,
-          G, int(loss_kind), _stream())
+    _call("sg_recon_fwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(x), _p(x_hat), _p(loss_sums),
+          _p(_f32(rowsums, "rowsums")), N, B, T, Tp, G, int(loss_kind), _stream())
 
 
-def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy, dgamma, dbeta, dbias, T, G, loss_kind):
+def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy, dgamma, dbeta, dbias, T, G, loss_kind,
+              rowsums=None):
     N, B, Tp = y.shape
     ws = torch.empty(2 * B * G + 2, dtype=torch.float64, device=y.device)
     dp, dn, _ = _planes(dy)
     assert dn == 1
     _call("sg_recon_bwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(x), _p(g_loss), _p(g_mse), float(inv_numel),
-          _p(dxhat_ext), dp, _p(dgamma), _p(dbeta), _p(dbias), _p(ws), N, B, T, Tp, G, int(loss_kind), _dt(dy),
+          _p(dxhat_ext), _p(_f32(rowsums, "rowsums")), dp, _p(dgamma), _p(dbeta), _p(dbias), _p(ws), N, B, T, Tp, G,
+          int(loss_kind), _dt(dy),
           _stream())
 
 
@@ -274,3 +277,40 @@ def philox_normal(out, seed, stream_id, sample0):
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq):
     _call("sg_adamw_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
           float(weight_decay), int(step), float(grad_scale), _p(gnorm_sq), _stream())
+
+
+class OptPlan:
+    """Static description of one multi-tensor optimiser step (sg_opt_step): a list of items
+    dict(p, g, m, v[, u, vv, sigma, Cout, Cin, Cin_p, k, flip]) whose tensors keep their addresses
+    across steps (persistent gradient arena, optimiser state, spectral-norm buffers)."""
+
+    def __init__(self, items, device):
+        import ctypes
+        self.items = items
+        n_sn = sum(1 for it in items if it.get("u") is not None)
+        self.dots = torch.zeros(max(n_sn, 1), dtype=torch.float64, device=device)
+        arr = (_lib.OptItem * len(items))()
+        d = 0
+        for a, it in zip(arr, items):
+            a.p, a.g, a.m, a.v = _p(it["p"]), _p(it["g"]), _p(it["m"]), _p(it["v"])
+            a.n = it["p"].numel()
+            if it.get("u") is not None:
+                a.u, a.vv, a.sigma = _p(it["u"]), _p(it["vv"]), _p(it["sigma"])
+                a.dot = self.dots.data_ptr() + 8 * d
+                it["dot_index"] = d
+                d += 1
+                a.Cout, a.Cin, a.Cin_p, a.k, a.flip = it["Cout"], it["Cin"], it["Cin_p"], it["k"], int(it["flip"])
+                assert it["g"].numel() == it["k"] * it["Cout"] * it["Cin_p"]
+            else:
+                assert it["g"].numel() == a.n
+        self._host = arr                                  # keeps the host copy alive (read at every launch)
+        raw = bytes(arr)
+        self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        self.n = len(items)
+
+
+def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq):
+    import ctypes
+    _call("sg_opt_step", plan.table.data_ptr(), ctypes.addressof(plan._host), plan.n, plan.dots.data_ptr(),
+          plan.dots.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+          float(grad_scale), _p(gnorm_sq), _stream())

@@ -1,13 +1,21 @@
 """Training-step driver for the engine: the reference's step semantics (train.py:139-168) without
 its host synchronisations, plus data-parallel gradient all-reduce over NCCL.
 
-  step(x):  zero grads -> VAE.forward -> alpha*recon + beta*sum(kl) -> backward
-            -> (DP) bucketed all-reduce of the gradients, overlapped with the rest of backward
-            -> fused AdamW + global grad-norm (sg_adamw_step), AdamW defaults of torch (train.py:92).
+  step(x):  VAE.forward -> alpha*recon + beta*sum(kl) -> backward
+            -> (DP) bucketed all-reduce of the gradient arena, overlapped with the rest of backward
+            -> ONE fused multi-tensor launch pair: spectral-norm gradient + AdamW + global grad-norm
+               (sg_opt_step; AdamW defaults of torch, train.py:92).
 
-The reference computes the gradient norm with one `.item()` per parameter (126 blocking D2H copies
-per step, train.py:156-161) and four more for logging (train.py:171-174); here all scalars stay on
-the device and are fetched only when the caller asks (`Trainer.scalars()`).
+Gradients never take the reference layout on this path: the wgrad GEMMs write into a persistent flat
+arena (engine.GradSink, laid out in backward-completion order), NCCL reduces contiguous slices of that
+arena in place, and the optimiser kernel reads it directly.  The reference computes the gradient norm
+with one `.item()` per parameter (126 blocking D2H copies per step, train.py:156-161) and four more
+for logging (train.py:171-174); here all scalars stay on the device and are fetched only when the
+caller asks (`Trainer.scalars()`).
+
+`fused=False` keeps the per-parameter path (p.grad materialised, one AdamW launch per tensor); it is the
+cross-check for the fused path in the tests and what the untouched reference train.py effectively runs
+with torch.optim.AdamW.
 """
 from __future__ import annotations
 
@@ -27,9 +35,21 @@ def warmup_beta(epoch: int, epochs: int, init_beta: float = 1e-4, beta_target: f
     return beta_target
 
 
+def _gemm_layout_elems(mod):
+    """Elements of the wgrad output for a Conv1d / ConvTranspose1d / Linear (GEMM layout, Cin padded to 8)."""
+    w = mod.weight_orig if hasattr(mod, "weight_orig") else mod.weight
+    if w.dim() == 2:
+        return w.numel()
+    if isinstance(mod, torch.nn.ConvTranspose1d):
+        cin, cout, k = w.shape
+    else:
+        cout, cin, k = w.shape
+    return k * cout * ((cin + 7) // 8 * 8)
+
+
 class Trainer:
     def __init__(self, model, lr=1e-3, alpha=1.0e6, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                 process_group=None, bucket_mb=64):
+                 process_group=None, bucket_mb=64, fused=True):
         self.model = model
         self.lr, self.alpha, self.betas, self.eps, self.wd = lr, alpha, betas, eps, weight_decay
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -37,28 +57,74 @@ class Trainer:
         self.v = {}
         self.step_count = 0
         dev = self.params[0].device
+        self.dev = dev
         self.gnorm_sq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
-        self.bucket_bytes = bucket_mb * (1 << 20)
-        self.comm_stream = torch.cuda.Stream(device=dev) if (self.world > 1 and dev.type == "cuda") else None
+        self.bucket_elems = bucket_mb * (1 << 20) // 4
+        self.fused = fused
         self._last = None
+        self.sink = None
+        self.plan = None
+        self._works = []
+        self._launched = 0
+        if fused:
+            w_elems = v_elems = n_layers = 0
+            wparams = set()
+            for mod in model.modules():
+                if isinstance(mod, (torch.nn.Conv1d, torch.nn.ConvTranspose1d, torch.nn.Linear)):
+                    w = mod.weight_orig if hasattr(mod, "weight_orig") else mod.weight
+                    wparams.add(id(w))
+                    n_layers += 1
+                    if hasattr(mod, "weight_orig"):
+                        w_elems += engine.GradSink._round(_gemm_layout_elems(mod))
+                    else:
+                        v_elems += engine.GradSink._round(w.numel())
+            for p in self.params:
+                if id(p) not in wparams:
+                    v_elems += engine.GradSink._round(p.numel())
+            self.sink = engine.GradSink(w_elems, v_elems, n_layers, dev)
+            if self.world > 1:
+                self.sink.on_commit = self._on_commit
 
     # -- data parallel --------------------------------------------------------------------------
-    def _allreduce_grads(self):
-        """Bucketed sum all-reduce of the local gradients (mean is folded into AdamW's grad_scale).
-        Gradients are taken in reverse parameter order = the order backward produced them."""
+    def _on_commit(self, committed):
+        """Gradient arena filled up to `committed` elements: all-reduce complete buckets right away.  The
+        collective is enqueued behind the wgrad GEMMs already issued on the compute stream and runs on
+        NCCL's own stream while backward continues."""
+        if committed - self._launched >= self.bucket_elems:
+            self._reduce(self.sink.weights[self._launched:committed])
+            self._launched = committed
+
+    def _reduce(self, flat):
+        dist = torch.distributed
+        self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def _finish_reduce(self):
         if self.world == 1:
             return
-        dist = torch.distributed
+        sink = self.sink
+        if sink.committed > self._launched:
+            self._reduce(sink.weights[self._launched:sink.committed])
+        self._launched = 0
+        if sink.v_used:
+            self._reduce(sink.vecs[:sink.v_used])
+        for w in self._works:
+            w.wait()
+        self._works = []
+
+    def _allreduce_grads(self):
+        """Unfused path: bucketed sum all-reduce of p.grad (mean is folded into AdamW's grad_scale)."""
+        if self.world == 1:
+            return
         grads = [p.grad for p in reversed(self.params) if p.grad is not None]
         bucket, size, handles = [], 0, []
         for g in grads:
             bucket.append(g)
-            size += g.numel() * 4
-            if size >= self.bucket_bytes:
+            size += g.numel()
+            if size >= self.bucket_elems:
                 handles.append(self._launch_bucket(bucket))
                 bucket, size = [], 0
         if bucket:
@@ -80,33 +146,65 @@ class Trainer:
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
         return flat, ([] if len(bucket) == 1 else bucket), work
 
+    # -- optimiser ---------------------------------------------------------------------------------
+    def _state(self, p):
+        if p not in self.m:
+            self.m[p] = torch.zeros_like(p)
+            self.v[p] = torch.zeros_like(p)
+        return self.m[p], self.v[p]
+
+    def _build_plan(self):
+        items = []
+        for key in self.sink.order:
+            it = dict(self.sink.items[key])
+            p = it.pop("param")
+            m, v = self._state(p)
+            it.update(p=p.data, m=m, v=v)
+            items.append(it)
+        self.sink.frozen = True
+        self.plan = K.OptPlan(items, self.dev)
+
     # -- one optimisation step -------------------------------------------------------------------
     def step(self, x, beta=1e-4, sample_offset=0):
         model = self.model
-        for p in self.params:
-            p.grad = None
         engine.set_sample_offset(sample_offset)
-        x_hat, recon, kls, mse = model(x)
-        kl_sum = kls[0]
-        for k in kls[1:]:
-            kl_sum = kl_sum + k
-        loss = recon * self.alpha + kl_sum * beta
-        loss.backward()
-        self._allreduce_grads()
-        self.step_count += 1
-        self.gnorm_sq.zero_()
         b1, b2 = self.betas
         scale = 1.0 / self.world
-        for p in self.params:
-            g = p.grad
-            if g is None:
-                continue
-            st = self.m.get(p)
-            if st is None:
-                self.m[p] = torch.zeros_like(p)
-                self.v[p] = torch.zeros_like(p)
-            K.adamw_step(p.data, g, self.m[p], self.v[p], self.lr, b1, b2, self.eps, self.wd, self.step_count, scale,
-                         self.gnorm_sq)
+        self.gnorm_sq.zero_()
+        if self.fused:
+            self.sink.begin_step()
+            engine.set_grad_sink(self.sink)
+            try:
+                x_hat, recon, kls, mse = model(x)
+                kl_sum = kls[0]
+                for k in kls[1:]:
+                    kl_sum = kl_sum + k
+                loss = recon * self.alpha + kl_sum * beta
+                loss.backward()
+            finally:
+                engine.set_grad_sink(None)
+            self._finish_reduce()
+            if self.plan is None:
+                self._build_plan()
+            self.step_count += 1
+            K.opt_step(self.plan, self.lr, b1, b2, self.eps, self.wd, self.step_count, scale, self.gnorm_sq)
+        else:
+            for p in self.params:
+                p.grad = None
+            x_hat, recon, kls, mse = model(x)
+            kl_sum = kls[0]
+            for k in kls[1:]:
+                kl_sum = kl_sum + k
+            loss = recon * self.alpha + kl_sum * beta
+            loss.backward()
+            self._allreduce_grads()
+            self.step_count += 1
+            for p in self.params:
+                g = p.grad
+                if g is None:
+                    continue
+                m, v = self._state(p)
+                K.adamw_step(p.data, g, m, v, self.lr, b1, b2, self.eps, self.wd, self.step_count, scale, self.gnorm_sq)
         self._last = (loss.detach(), recon.detach(), kl_sum.detach(), mse.detach())
         return self._last
 

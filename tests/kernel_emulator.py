@@ -220,7 +220,7 @@ def _recon_xhat(y, gamma, beta, T, G):
     return o.permute(1, 0, 2)                                                     # [B,N,T]
 
 
-def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind):
+def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind, rowsums=None):
     with torch.no_grad():
         xh = _recon_xhat(y, gamma, beta, T, G)
         if x_hat is not None:
@@ -231,7 +231,8 @@ def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind):
             loss_sums[1] = (d * d).sum()
 
 
-def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy, dgamma, dbeta, dbias, T, G, loss_kind):
+def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy, dgamma, dbeta, dbias, T, G, loss_kind,
+              rowsums=None):
     with torch.enable_grad():
         yl = y.detach().clone().requires_grad_(True)
         gl = gamma.detach().clone().requires_grad_(True)
@@ -402,7 +403,28 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale
     p.addcdiv_(m, denom, value=-lr / bc1)
 
 
-NAMES = ["pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
+class OptPlan:
+    """Emulated counterpart of kernels.OptPlan: keeps the item list (tensors) instead of a device table."""
+
+    def __init__(self, items, device):
+        self.items = items
+        self.n = len(items)
+
+
+def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq):
+    for it in plan.items:
+        p = it["p"]
+        if it.get("u") is not None:
+            k, Cout, Cin, Cin_p = it["k"], it["Cout"], it["Cin"], it["Cin_p"]
+            grad = torch.empty_like(p)
+            sn_weight_grad(it["g"].reshape(k, Cout, Cin_p), p, it["u"], it["vv"], it["sigma"], grad, Cout, Cin, Cin_p, k,
+                           0, 0, it["flip"])
+        else:
+            grad = it["g"].reshape(p.shape)
+        adamw_step(p, grad, it["m"], it["v"], lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq)
+
+
+NAMES = ["OptPlan", "opt_step", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
          "conv_fprop", "conv_dgrad", "conv_wgrad", "gn_stats", "gn_act_fwd", "gn_act_bwd", "recon_fwd", "recon_bwd",
          "head_fwd", "head_bwd", "latent_fwd", "latent_bwd", "reparam_main_fwd", "reparam_main_bwd", "kl2_reparam_fwd",
          "kl2_reparam_bwd", "philox_normal", "adamw_step"]

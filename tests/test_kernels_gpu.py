@@ -194,9 +194,10 @@ def test_gn_act_fwd_bwd(case, dtype, P):
 
 
 @pytest.mark.parametrize("loss", ["MSE", "MAE", "smoothL1", "Huber"])
-@pytest.mark.parametrize("with_ext", [False, True])
-def test_recon_fwd_bwd(loss, with_ext):
-    N, B, T, G = 40, 3, 21, 8
+@pytest.mark.parametrize("with_ext,one_pass", [(False, False), (True, False), (False, True)])
+@pytest.mark.parametrize("T", [21, 24])          # 24: the float4 path of the external layout (T % 4 == 0)
+def test_recon_fwd_bwd(loss, with_ext, one_pass, T):
+    N, B, G = 40, 3, 8
     Tp = tp_of(T)
     kind = K.LOSS_KINDS[loss]
     y = cr(N, B, T, seed=1) * 2.0
@@ -206,9 +207,10 @@ def test_recon_fwd_bwd(loss, with_ext):
     K.gn_stats(y, stats, T, G)
     xh1, xh2 = torch.empty(B, N, T, device=DEV), torch.empty(B, N, T, device=DEV)
     s1, s2 = (torch.empty(2, device=DEV, dtype=torch.float64) for _ in range(2))
-    K.recon_fwd(y, stats, gamma, beta, x, xh1, s1, T, G, kind)
+    rowsums = torch.full((N * B, 4), 9.0, device=DEV) if one_pass else None
+    K.recon_fwd(y, stats, gamma, beta, x, xh1, s1, T, G, kind, rowsums)
     emu.recon_fwd(y, stats, gamma, beta, x, xh2, s2, T, G, kind)
-    close(xh1, xh2, 2e-6, "x_hat")
+    close(xh1, xh2, 3e-6, "x_hat")
     close(s1, s2, 1e-5, "loss sums")
     g_loss = torch.tensor([1.0e6], device=DEV)
     g_mse = torch.tensor([0.5], device=DEV)
@@ -218,7 +220,7 @@ def test_recon_fwd_bwd(loss, with_ext):
     for fn in (K.recon_bwd, emu.recon_bwd):
         dy = torch.full((1, N, B, Tp), 9.0, device=DEV)
         dg, db, dbi = (torch.empty(N, device=DEV) for _ in range(3))
-        fn(y, stats, gamma, beta, x, g_loss, g_mse, inv, ext, dy, dg, db, dbi, T, G, kind)
+        fn(y, stats, gamma, beta, x, g_loss, g_mse, inv, ext, dy, dg, db, dbi, T, G, kind, rowsums)
         outs.append((dy, dg, db, dbi))
     for a, b, nm in zip(outs[0], outs[1], ("dy", "dgamma", "dbeta", "dbias")):
         close(a, b, 5e-5, nm)
@@ -361,3 +363,41 @@ def test_adamw_matches_torch():
         K.adamw_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, 1.0, gn)
     close(p, ref.detach(), 1e-6, "adamw")
     assert abs(float(gn) - 3 * float((g.double() ** 2).sum())) / float(gn) < 1e-9
+
+
+def test_opt_step_multi_tensor_matches_model():
+    """sg_opt_step (spectral-norm gradient + AdamW + grad norm for all tensors in two launches) against the
+    per-tensor torch model, over every layout the fused kernel distinguishes."""
+    specs = [("conv", 40, 24, 3), ("convT", 40, 24, 3), ("linear", 16, 64, 1), ("conv", 24, 20, 1), ("conv", 300, 40, 5),
+             ("vec", 10007, 0, 0), ("vec", 4096, 0, 0), ("linear", 8, 12000, 1)]
+
+    def make():
+        items = []
+        for si, (kind, a, b, k) in enumerate(specs):
+            if kind == "vec":
+                p = rnd(a, seed=si)
+                items.append(dict(p=p, g=rnd(a, seed=100 + si), m=rnd(a, seed=200 + si) * 0.1,
+                                  v=rnd(a, seed=300 + si).abs() * 0.01))
+                continue
+            Cout, Cin = a, b
+            Cin_p = Cin if kind == "linear" else (Cin + 7) // 8 * 8
+            shape = (Cout, Cin) if kind == "linear" else ((Cin, Cout, k) if kind == "convT" else (Cout, Cin, k))
+            p = rnd(*shape, seed=si)
+            g = rnd(k, Cout, Cin_p, seed=100 + si)
+            items.append(dict(p=p, g=g, m=torch.zeros_like(p), v=torch.zeros_like(p),
+                              u=torch.nn.functional.normalize(rnd(Cout, seed=400 + si), dim=0),
+                              vv=torch.nn.functional.normalize(rnd(Cin * k, seed=500 + si), dim=0),
+                              sigma=torch.tensor([1.3 + 0.1 * si], device=DEV), Cout=Cout, Cin=Cin, Cin_p=Cin_p, k=k,
+                              flip=int(kind == "convT")))
+        return items
+    a_items, b_items = make(), make()
+    pa, pb = K.OptPlan(a_items, DEV), emu.OptPlan(b_items, DEV)
+    ga, gb = (torch.zeros(1, device=DEV, dtype=torch.float64) for _ in range(2))
+    for step in (1, 2, 3):
+        K.opt_step(pa, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, 0.5, ga)
+        emu.opt_step(pb, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, 0.5, gb)
+    for ia, ib, sp in zip(a_items, b_items, specs):
+        close(ia["p"], ib["p"], 2e-6, "p %s" % (sp,))
+        close(ia["m"], ib["m"], 2e-5, "m %s" % (sp,))
+        close(ia["v"], ib["v"], 2e-5, "v %s" % (sp,))
+    assert abs(float(ga) - float(gb)) / float(gb) < 1e-5

@@ -1,0 +1,121 @@
+"""CPU tests of the Trainer's host logic (gradient sink / persistent arena, optimiser plan, data-parallel
+all-reduce over gloo) with the CUDA kernels replaced by their torch models (tests/kernel_emulator.py)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import kernel_emulator as emu
+import simulgen_vae_b200 as sg
+from conftest import load_golden, rel_l2
+from test_wiring_cpu import build_engine_vae
+
+
+def _reference_steps(g, n_steps, xs):
+    """torch autograd through the emulated engine + torch.optim.AdamW = the reference's step semantics."""
+    m = build_engine_vae(g["cfg"], g["state_dict"])
+    m.train(True)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+    losses = []
+    for i in range(n_steps):
+        opt.zero_grad(set_to_none=True)
+        with sg.fixed_eps(g["eps"]):
+            _, rl, kls, _ = m(xs[i])
+        loss = rl * g["alpha"] + sum(kls) * g["beta"]
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    return m, losses
+
+
+@pytest.mark.parametrize("name", ["toy3_small_mse", "toy4_large_mae"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_trainer_matches_torch_adamw(name, fused):
+    from simulgen_vae_b200.trainer import Trainer
+    g = load_golden(name)
+    sg.set_precision("fp32")
+    try:
+        with emu.install():
+            xs = [g["x"], g["x"] * 0.9, g["x"] * 1.1]
+            ref, ref_losses = _reference_steps(g, 3, xs)
+            m = build_engine_vae(g["cfg"], g["state_dict"])
+            m.train(True)
+            tr = Trainer(m, lr=1e-3, alpha=g["alpha"], fused=fused)
+            losses = []
+            for i in range(3):
+                with sg.fixed_eps(g["eps"]):
+                    out = tr.step(xs[i], beta=g["beta"])
+                losses.append(float(out[0]))
+            if fused:
+                assert all(p.grad is None for p in m.parameters())       # gradients live in the arena only
+                assert tr.plan is not None and tr.sink.frozen
+                n_live = sum(1 for v in g["grads"].values() if v is not None)
+                assert tr.plan.n == n_live
+    finally:
+        sg.set_precision("bf16")
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) / abs(b) < 1e-5
+    rsd, sd = ref.state_dict(), m.state_dict()
+    for k in rsd:
+        assert rel_l2(sd[k], rsd[k]) < 2e-5, k
+    assert tr.scalars()[4] > 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _dp_worker(rank, world, port, name, fused, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from simulgen_vae_b200.trainer import Trainer
+    g = load_golden(name)
+    B = g["x"].shape[0]
+    half = B // world
+    sg.set_precision("fp32")
+    with emu.install():
+        m = build_engine_vae(g["cfg"], g["state_dict"])
+        m.train(True)
+        tr = Trainer(m, lr=1e-3, alpha=g["alpha"], fused=fused, bucket_mb=0)      # bucket_mb=0: one bucket per layer
+        for i in range(2):
+            eps = [e[rank * half:(rank + 1) * half] for e in g["eps"]]
+            with sg.fixed_eps(eps):
+                tr.step(g["x"][rank * half:(rank + 1) * half], beta=g["beta"], sample_offset=rank * half)
+    if rank == 0:
+        torch.save({k: v.clone() for k, v in m.state_dict().items()}, out)
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_data_parallel_world2_equals_single_process(tmp_path, fused):
+    """Two gloo ranks, each with half of the batch, must reproduce the single-process full-batch weights:
+    every op is per-sample and the losses are batch means."""
+    from simulgen_vae_b200.trainer import Trainer
+    name = "toy3_small_mse"
+    g = load_golden(name)
+    if g["x"].shape[0] % 2:
+        pytest.skip("odd batch")
+    out = str(tmp_path / "rank0.pt")
+    mp.spawn(_dp_worker, args=(2, _free_port(), name, fused, out), nprocs=2, join=True)
+    dp = torch.load(out)
+    sg.set_precision("fp32")
+    try:
+        with emu.install():
+            m = build_engine_vae(g["cfg"], g["state_dict"])
+            m.train(True)
+            tr = Trainer(m, lr=1e-3, alpha=g["alpha"], fused=True)
+            for i in range(2):
+                with sg.fixed_eps(g["eps"]):
+                    tr.step(g["x"], beta=g["beta"])
+    finally:
+        sg.set_precision("bf16")
+    sd = m.state_dict()
+    for k in sd:
+        assert rel_l2(dp[k], sd[k]) < 5e-5, (k, rel_l2(dp[k], sd[k]))
