@@ -166,6 +166,25 @@ int sg_philox_normal(float* out, int B, long long per_sample, unsigned long long
 int sg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, double* gnorm_sq, void* stream);
 
+/* ---- batched spectral-norm preparation: every layer of a sub-network in five launches ---------------
+ * Same arithmetic as sg_sn_power_iter + sg_sn_pack_weight per layer (spectral_norm.py:62-114): the power
+ * iteration depends only on the weights and the stored u / v, so all layers are prepared up front.
+ * ws: per-layer scratch of (Cin*k + H) floats inside one arena [ws_base, ws_base + ws_elems) that is
+ * zeroed here.  has_sn == 0: sigma = 1 (layer not spectral-normalised).  has_wg == 0: no operand copy
+ * (Linear layers: the head / latent kernels read w_orig and sigma directly). */
+typedef struct {
+    const float* w;      /* weight_orig */
+    float* u;            /* weight_u [H] (updated when training) */
+    float* v;            /* weight_v [Cin*k] (updated when training) */
+    float* sigma;        /* [1] out */
+    void* wg;            /* [k][H][Cin_p] out (dtype) or NULL */
+    float* ws;           /* scratch */
+    long long so, si;    /* W_mat[o][i*k+j] = w[o*so + i*si + j] */
+    int H, Cin, k, Cin_p, flip, has_sn, has_wg, reserved;
+} sg_sn_layer;
+int sg_sn_prepare(const sg_sn_layer* layers_dev, const sg_sn_layer* layers_host, int n_layers, float* ws_base,
+                  long long ws_elems, int training, int dtype, void* stream);
+
 /* ---- multi-tensor optimiser step (train.py:92,156-168 for the whole model in two launches) -----------
  * One item per parameter tensor.  Plain tensors (u == NULL): g is the gradient in p's layout.
  * Spectral-normalised weights (u != NULL): g is the wgrad GEMM output dWg [k][Cout][Cin_p] (gradient wrt

@@ -47,7 +47,15 @@ SIGNATURES = {
     "sg_philox_normal": [P, I, L, U, U, L, P],
     "sg_adamw_step": [P, P, P, P, L, F, F, F, F, F, I, F, P, P],
     "sg_opt_step": [P, P, I, P, I, F, F, F, F, F, I, F, P, P],
+    "sg_sn_prepare": [P, P, I, P, L, I, I, P],
 }
+
+
+class SnLayer(ctypes.Structure):
+    """sg_sn_layer of include/simulgen_b200.h"""
+    _fields_ = [("w", c_void_p), ("u", c_void_p), ("v", c_void_p), ("sigma", c_void_p), ("wg", c_void_p),
+                ("ws", c_void_p), ("so", c_ll), ("si", c_ll), ("H", c_int), ("Cin", c_int), ("k", c_int),
+                ("Cin_p", c_int), ("flip", c_int), ("has_sn", c_int), ("has_wg", c_int), ("reserved", c_int)]
 
 
 class OptItem(ctypes.Structure):

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import os
 import threading
+import weakref
 
 import torch
 
@@ -116,13 +117,12 @@ class GradSink:
 
     ALIGN = 64
 
-    def __init__(self, weight_elems, vec_elems, n_layers, device):
+    def __init__(self, weight_elems, vec_elems, device):
         self.dev = device
         self.weights = torch.zeros(max(weight_elems, 1), dtype=torch.float32, device=device)
         self.vecs = torch.zeros(max(vec_elems, 1), dtype=torch.float32, device=device)
-        self.sigmas = torch.ones(max(n_layers, 1), dtype=torch.float32, device=device)
-        self.w_used = self.v_used = self.s_used = 0
-        self.w_slots, self.v_slots, self.s_slots = {}, {}, {}
+        self.w_used = self.v_used = 0
+        self.w_slots, self.v_slots = {}, {}
         self.items = {}                 # id(param) -> optimiser item description (first backward)
         self.order = []                 # params in commit order
         self.committed = 0              # arena elements whose producers have been enqueued this step
@@ -135,16 +135,6 @@ class GradSink:
 
     def begin_step(self):
         self.committed = 0
-
-    def sigma_buffer(self, param):
-        key = id(param)
-        if key not in self.s_slots:
-            if self.s_used >= self.sigmas.numel():
-                raise RuntimeError("simulgen_b200: GradSink sigma arena exhausted")
-            self.s_slots[key] = self.s_used
-            self.s_used += 1
-        i = self.s_slots[key]
-        return self.sigmas[i:i + 1]
 
     def weight_buffer(self, param, shape):
         key = id(param)
@@ -249,6 +239,9 @@ class Ctx:
         self.pgrads = {}
         self.capture = capture
         self.sink = get_grad_sink() if record else None
+        self.prepared = {}              # id(module) -> _Prep from the batched preparation
+        self.prep_record = []           # (module, kind) in execution order when preparing layer by layer
+        self.prep_root = None
 
     # -- allocation helpers ------------------------------------------------------------------
     def f32(self, *shape):
@@ -291,10 +284,6 @@ class Ctx:
             return self.sink.weight_buffer(prep.w, shape)
         return self.f32(*shape)
 
-    def sigma_buf(self, param):
-        if self.sink is not None:
-            return self.sink.sigma_buffer(param)
-        return self.f32(1)
 
     def cap(self, name, act: Act):
         if self.capture is None:
@@ -314,7 +303,110 @@ class Ctx:
 # spectral norm / weight preparation
 # ------------------------------------------------------------------------------------------------
 class _Prep:
-    __slots__ = ("w", "u", "v", "sigma", "wg", "Cin", "Cout", "k", "Cin_p", "so", "si", "flip", "sn", "version")
+    __slots__ = ("w", "u", "v", "sigma", "wg", "Cin", "Cout", "k", "Cin_p", "so", "si", "flip", "sn", "version", "mod")
+
+
+_SIGMAS = {}                                # id(weight parameter) -> (weakref, persistent [1] fp32 sigma tensor)
+_PREP_CACHE = weakref.WeakKeyDictionary()   # encoder / decoder module -> _PrepCache
+
+
+def sigma_of(param):
+    """Persistent device scalar for the spectral norm of `param`: written by every forward, read by the
+    backward and by the fused optimiser step (whose launch table stores its address)."""
+    key = id(param)
+    ent = _SIGMAS.get(key)
+    if ent is None or ent[0]() is not param or ent[1].device != param.device:
+        t = torch.ones(1, dtype=torch.float32, device=param.device)
+        _SIGMAS[key] = (weakref.ref(param, lambda _, key=key: _SIGMAS.pop(key, None)), t)
+        return t
+    return ent[1]
+
+
+class _PrepCache:
+    """Everything the batched spectral-norm preparation of one sub-network needs, built from the layer
+    sequence recorded during the first forward: persistent operand copies of the weights, the launch table
+    (kernels.SnPlan) and the _Prep objects handed to the graph."""
+
+    def __init__(self, record, op_dtype, device):
+        self.op_dtype, self.device = op_dtype, device
+        self.preps = {}
+        self.mods = []
+        layers = []
+        for mod, kind in record:
+            p = _prep_shapes(mod, kind)
+            p.sigma = sigma_of(p.w)
+            p.wg = torch.empty(p.k, p.Cout, p.Cin_p, dtype=op_dtype, device=device) if kind != "linear" else None
+            p.version = 0
+            self.preps[id(mod)] = p
+            self.mods.append(mod)
+            layers.append(dict(w=p.w.data, u=p.u, v=p.v, sigma=p.sigma, wg=p.wg, H=p.Cout, Cin=p.Cin, k=p.k,
+                               Cin_p=p.Cin_p, so=p.so, si=p.si, flip=p.flip))
+        self.key = self._key()
+        self.plan = K.SnPlan(layers, device, op_dtype)
+
+    def _key(self):
+        k = []
+        for mod in self.mods:
+            p = self.preps[id(mod)]
+            w, u, v, sn = _sn_tensors(None, mod)
+            k.append((w.data_ptr(), u.data_ptr() if sn else 0, v.data_ptr() if sn else 0, sn))
+        return tuple(k)
+
+    def valid(self, ctx, training):
+        if self.op_dtype != ctx.op_dtype or self.device != ctx.dev:
+            return False
+        if any(m.training != training for m in self.mods):
+            return False
+        return self._key() == self.key
+
+
+def prepare_all(ctx, root):
+    """Batched power iteration + weight packing for every layer `root` executed in its first forward.
+    Returns False when there is no (valid) cache yet: the graph then prepares layer by layer and records."""
+    ctx.prep_root = root
+    cache = _PREP_CACHE.get(root)
+    training = root.training
+    if cache is None or not cache.valid(ctx, training):
+        if cache is not None:
+            del _PREP_CACHE[root]
+        return False
+    K.sn_prepare(cache.plan, training)
+    for mod in cache.mods:
+        p = cache.preps[id(mod)]
+        if p.sn:
+            p.version = _bump_version(mod) if training else getattr(mod, "_sg_sn_version", 0)
+    ctx.prepared = cache.preps
+    return True
+
+
+def finish_prepare(ctx):
+    """After the first forward of a sub-network: turn the recorded layer sequence into a cache."""
+    root = ctx.prep_root
+    if root is None or ctx.prepared or not ctx.prep_record:
+        return
+    if len(set(id(m) for m, _ in ctx.prep_record)) != len(ctx.prep_record):
+        return                              # a layer used twice in one forward: keep the per-layer path
+    _PREP_CACHE[root] = _PrepCache(ctx.prep_record, ctx.op_dtype, ctx.dev)
+
+
+def _prep_shapes(mod, kind):
+    p = _Prep()
+    w, u, v, sn = _sn_tensors(None, mod)
+    if kind == "linear":
+        O, In = w.shape
+        p.Cin, p.Cout, p.k, p.so, p.si, p.flip, p.Cin_p = In, O, 1, In, 1, 0, In
+    else:
+        if kind == "convT":
+            Cin, Cout, k = w.shape
+            so, si, flip = k, Cout * k, 1
+        else:
+            Cout, Cin, k = w.shape
+            so, si, flip = Cin * k, k, 0
+        p.Cin, p.Cout, p.k, p.so, p.si, p.flip = Cin, Cout, k, so, si, flip
+        p.Cin_p = (Cin + 7) // 8 * 8
+    p.w, p.u, p.v, p.sn, p.mod = w, u, v, sn, mod
+    p.wg = None
+    return p
 
 
 def _sn_tensors(ctx, mod):
@@ -331,40 +423,35 @@ def _bump_version(mod):
 
 def prep_conv(ctx: Ctx, mod, transposed=False) -> _Prep:
     """Power iteration (training) / sigma (eval) + normalised, permuted, cast weight for the GEMMs.
-    common.py:15-37 -> spectral_norm.py:62-114; ConvTranspose1d uses dim=1 (spectral_norm.py:329-333)."""
-    p = _Prep()
-    w, u, v, sn = _sn_tensors(ctx, mod)
-    if transposed:
-        Cin, Cout, k = w.shape
-        so, si, flip = k, Cout * k, 1
-    else:
-        Cout, Cin, k = w.shape
-        so, si, flip = Cin * k, k, 0
-    p.w, p.u, p.v, p.sn = w, u, v, sn
-    p.Cin, p.Cout, p.k, p.so, p.si, p.flip = Cin, Cout, k, so, si, flip
-    p.Cin_p = (Cin + 7) // 8 * 8
-    if sn:
-        p.sigma = ctx.sigma_buf(w)
-        K.sn_power_iter(w, u, v, p.sigma, Cout, Cin, k, so, si, mod.training)
+    common.py:15-37 -> spectral_norm.py:62-114; ConvTranspose1d uses dim=1 (spectral_norm.py:329-333).
+    Served from the batched preparation (prepare_all) when the sub-network has a cache."""
+    p = ctx.prepared.get(id(mod))
+    if p is not None:
+        return p
+    kind = "convT" if transposed else "conv"
+    ctx.prep_record.append((mod, kind))
+    p = _prep_shapes(mod, kind)
+    if p.sn:
+        p.sigma = sigma_of(p.w)
+        K.sn_power_iter(p.w, p.u, p.v, p.sigma, p.Cout, p.Cin, p.k, p.so, p.si, mod.training)
         p.version = _bump_version(mod) if mod.training else getattr(mod, "_sg_sn_version", 0)
     else:
         p.sigma = torch.ones(1, dtype=torch.float32, device=ctx.dev)
         p.version = 0
-    p.wg = ctx.op(k, Cout, p.Cin_p)
-    K.sn_pack_weight(w, p.sigma, p.wg, Cout, Cin, p.Cin_p, k, so, si, flip)
+    p.wg = ctx.op(p.k, p.Cout, p.Cin_p)
+    K.sn_pack_weight(p.w, p.sigma, p.wg, p.Cout, p.Cin, p.Cin_p, p.k, p.so, p.si, p.flip)
     return p
 
 
 def prep_linear(ctx: Ctx, mod) -> _Prep:
-    p = _Prep()
-    w, u, v, sn = _sn_tensors(ctx, mod)
-    O, In = w.shape
-    p.w, p.u, p.v, p.sn = w, u, v, sn
-    p.Cin, p.Cout, p.k, p.so, p.si, p.flip, p.Cin_p = In, O, 1, In, 1, 0, In
-    p.wg = None
-    if sn:
-        p.sigma = ctx.sigma_buf(w)
-        K.sn_power_iter(w, u, v, p.sigma, O, In, 1, In, 1, mod.training)
+    p = ctx.prepared.get(id(mod))
+    if p is not None:
+        return p
+    ctx.prep_record.append((mod, "linear"))
+    p = _prep_shapes(mod, "linear")
+    if p.sn:
+        p.sigma = sigma_of(p.w)
+        K.sn_power_iter(p.w, p.u, p.v, p.sigma, p.Cout, p.Cin, 1, p.Cin, 1, mod.training)
         p.version = _bump_version(mod) if mod.training else getattr(mod, "_sg_sn_version", 0)
     else:
         p.sigma = torch.ones(1, dtype=torch.float32, device=ctx.dev)
@@ -537,6 +624,7 @@ def encoder_graph(ctx: Ctx, enc, x):
     """encoder.py:146-167.  Returns (last Ext [B, 2*z_dim], [xs Ext ...] in the reference's reversed
     order without the deepest level)."""
     B, N, T = x.shape
+    prepare_all(ctx, enc)
     a = Act(N, data=ctx.op(1, N, B, ctx.Tp), needs_grad=False, name="x")
     K.pack_input(x, a.data, T)
     L = len(enc.encoder_blocks)
@@ -555,6 +643,7 @@ def encoder_graph(ctx: Ctx, enc, x):
         xs.append(head(ctx, enc.xs_linear[i], h, ext_out=live))
         a = h
     last = head(ctx, enc.last_x_linear, h)
+    finish_prepare(ctx)
     return last, [e for e in xs[:-1][::-1]]
 
 
@@ -565,6 +654,7 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     B, T, Tp = ctx.B, ctx.T, ctx.Tp
     nb = len(dec.decoder_residual_blocks)
     kls = []
+    prepare_all(ctx, dec)
     zs = latent_seq(ctx, dec.sequence_start[0], z, out_planes=_k(dec.decoder_blocks[0].module_list[0]._seq[0]),
                     name="decoder.start")
     out = None
@@ -641,6 +731,7 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     # reconstruction head: Conv k1 -> GroupNorm -> Tanh (+ losses)
     conv, gn = dec.recon[0], dec.recon[1]
     p = prep_conv(ctx, conv)
+    finish_prepare(ctx)
     N, G = p.Cout, gn.num_groups
     y = ctx.f32(N, B, Tp)
     K.conv_fprop(p.wg, out.data, conv.bias, y, p.Cin)

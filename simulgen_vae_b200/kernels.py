@@ -314,3 +314,37 @@ def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_
     _call("sg_opt_step", plan.table.data_ptr(), ctypes.addressof(plan._host), plan.n, plan.dots.data_ptr(),
           plan.dots.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
           float(grad_scale), _p(gnorm_sq), _stream())
+
+
+class SnPlan:
+    """Static description of one batched spectral-norm preparation (sg_sn_prepare): a list of layers
+    dict(w, u, v, sigma, wg, H, Cin, k, Cin_p, so, si, flip) over persistent tensors."""
+
+    def __init__(self, layers, device, dtype):
+        import ctypes
+        self.layers = layers
+        self.dtype = SG_BF16 if dtype == torch.bfloat16 else SG_F32
+        total = sum(L["Cin"] * L["k"] + L["H"] + 8 for L in layers if L.get("u") is not None)
+        self.ws = torch.zeros(max(total, 1), dtype=torch.float32, device=device)
+        arr = (_lib.SnLayer * len(layers))()
+        off = 0
+        for a, L in zip(arr, layers):
+            a.w, a.sigma = _p(L["w"]), _p(L["sigma"])
+            a.H, a.Cin, a.k, a.Cin_p, a.flip = L["H"], L["Cin"], L["k"], L["Cin_p"], int(L["flip"])
+            a.so, a.si = L["so"], L["si"]
+            if L.get("u") is not None:
+                a.u, a.v, a.has_sn = _p(L["u"]), _p(L["v"]), 1
+                a.ws = self.ws.data_ptr() + 4 * off
+                off += (L["Cin"] * L["k"] + L["H"] + 7) // 4 * 4
+            if L.get("wg") is not None:
+                assert L["wg"].is_contiguous() and tuple(L["wg"].shape) == (L["k"], L["H"], L["Cin_p"])
+                a.wg, a.has_wg = _p(L["wg"]), 1
+        self._host = arr
+        self.table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+        self.n = len(layers)
+
+
+def sn_prepare(plan, training):
+    import ctypes
+    _call("sg_sn_prepare", plan.table.data_ptr(), ctypes.addressof(plan._host), plan.n, plan.ws.data_ptr(),
+          plan.ws.numel(), int(training), plan.dtype, _stream())

@@ -85,7 +85,7 @@ class Trainer:
             for p in self.params:
                 if id(p) not in wparams:
                     v_elems += engine.GradSink._round(p.numel())
-            self.sink = engine.GradSink(w_elems, v_elems, n_layers, dev)
+            self.sink = engine.GradSink(w_elems, v_elems, dev)
             if self.world > 1:
                 self.sink.on_commit = self._on_commit
 

@@ -424,7 +424,23 @@ def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_
         adamw_step(p, grad, it["m"], it["v"], lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq)
 
 
-NAMES = ["OptPlan", "opt_step", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
+class SnPlan:
+    def __init__(self, layers, device, dtype):
+        self.layers = layers
+        self.n = len(layers)
+
+
+def sn_prepare(plan, training):
+    for L in plan.layers:
+        if L.get("u") is not None:
+            sn_power_iter(L["w"], L["u"], L["v"], L["sigma"], L["H"], L["Cin"], L["k"], L["so"], L["si"], training)
+        else:
+            L["sigma"].fill_(1.0)
+        if L.get("wg") is not None:
+            sn_pack_weight(L["w"], L["sigma"], L["wg"], L["H"], L["Cin"], L["Cin_p"], L["k"], L["so"], L["si"], L["flip"])
+
+
+NAMES = ["OptPlan", "opt_step", "SnPlan", "sn_prepare", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
          "conv_fprop", "conv_dgrad", "conv_wgrad", "gn_stats", "gn_act_fwd", "gn_act_bwd", "recon_fwd", "recon_bwd",
          "head_fwd", "head_bwd", "latent_fwd", "latent_bwd", "reparam_main_fwd", "reparam_main_bwd", "kl2_reparam_fwd",
          "kl2_reparam_bwd", "philox_normal", "adamw_step"]

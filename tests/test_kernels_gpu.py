@@ -401,3 +401,40 @@ def test_opt_step_multi_tensor_matches_model():
         close(ia["m"], ib["m"], 2e-5, "m %s" % (sp,))
         close(ia["v"], ib["v"], 2e-5, "v %s" % (sp,))
     assert abs(float(ga) - float(gb)) / float(gb) < 1e-5
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_sn_prepare_batched_matches_per_layer_model(training, dtype):
+    """sg_sn_prepare (all layers in five launches) against the per-layer torch model."""
+    specs = [("conv", 40, 24, 3, True), ("convT", 40, 24, 3, True), ("linear", 16, 4100, 1, True), ("conv", 72, 64, 1, True),
+             ("conv", 24, 20, 5, False), ("conv", 300, 9000, 1, True), ("linear", 2000, 8, 1, True)]
+
+    def make():
+        layers = []
+        for si_, (kind, Cout, Cin, k, sn) in enumerate(specs):
+            if kind == "linear":
+                w, so, si, flip, Cin_p = rnd(Cout, Cin, seed=si_), Cin, 1, 0, Cin
+            elif kind == "convT":
+                w, so, si, flip, Cin_p = rnd(Cin, Cout, k, seed=si_), k, Cout * k, 1, (Cin + 7) // 8 * 8
+            else:
+                w, so, si, flip, Cin_p = rnd(Cout, Cin, k, seed=si_), Cin * k, k, 0, (Cin + 7) // 8 * 8
+            L = dict(w=w, sigma=torch.zeros(1, device=DEV), H=Cout, Cin=Cin, k=k, Cin_p=Cin_p, so=so, si=si, flip=flip,
+                     wg=None if kind == "linear" else torch.full((k, Cout, Cin_p), 3.0, device=DEV, dtype=dtype))
+            if sn:
+                L["u"] = torch.nn.functional.normalize(rnd(Cout, seed=50 + si_), dim=0)
+                L["v"] = torch.nn.functional.normalize(rnd(Cin * k, seed=80 + si_), dim=0)
+            layers.append(L)
+        return layers
+    la, lb = make(), make()
+    pa, pb = K.SnPlan(la, DEV, dtype), emu.SnPlan(lb, DEV, dtype)
+    for _ in range(2):
+        K.sn_prepare(pa, training)
+        emu.sn_prepare(pb, training)
+    for A, Bm, sp in zip(la, lb, specs):
+        close(A["sigma"], Bm["sigma"], 1e-5, "sigma %s" % (sp,))
+        if sp[4]:
+            close(A["u"], Bm["u"], 1e-5, "u %s" % (sp,))
+            close(A["v"], Bm["v"], 1e-5, "v %s" % (sp,))
+        if A["wg"] is not None:
+            close(A["wg"].float(), Bm["wg"].float(), 1e-6 if dtype == torch.float32 else 4e-3, "wg %s" % (sp,))
