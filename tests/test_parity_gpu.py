@@ -196,7 +196,11 @@ def test_trainer_fused_step_equals_per_tensor_path(precision):
                 tr.step(g["x"].to(DEV) * (1.0 - 0.05 * i), beta=g["beta"])
         res.append(({k: v.detach().clone() for k, v in m.state_dict().items()}, tr.scalars()))
     (sa, ca), (sb, cb) = res
+    # fp32: same arithmetic up to summation order.  bf16: the order of the split-K / row atomics decides a few
+    # 1-ulp bf16 roundings of dy, and AdamW's m/sqrt(v) turns that into O(lr) noise on noise-dominated
+    # gradients (conv biases in front of a GroupNorm), so only a loose bound is meaningful there.
+    tol = 1e-4 if precision == "fp32" else 2e-2
     for k in sa:
-        assert rel_l2(sa[k], sb[k]) < 1e-4, (k, rel_l2(sa[k], sb[k]))
+        assert rel_l2(sa[k], sb[k]) < tol, (k, rel_l2(sa[k], sb[k]))
     for a, b in zip(ca, cb):
-        assert abs(a - b) <= 1e-4 * abs(b) + 1e-12
+        assert abs(a - b) <= tol * abs(b) + 1e-12
