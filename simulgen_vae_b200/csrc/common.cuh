@@ -131,24 +131,51 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 
 // ---------------------------------------------------------------------------------------------
 // activations (exact erf GELU = nn.GELU() default; nn.Tanh)
+//
+// erf through Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32 round-off level): one MUFU.EX2, one
+// MUFU.RCP and 6 FMAs, and the exponential exp(-x^2/2) is the very one the Gaussian pdf of GELU' needs, so
+// value and derivative cost ~20 issue slots together.  erff() + expf() cost ~100 and made the GroupNorm /
+// activation kernels ALU-bound instead of HBM-bound.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
+    float z = fabsf(x) * 0.70710678118654752440f;
+    float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float e = __expf(-z * z);                                    // exp(-x^2 / 2)
+    float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+    float half_erfc = 0.5f * poly * e;                           // 0.5 * (1 - erf(|x| / sqrt 2))
+    float cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+    g = x * cdf;
+    dg = cdf + x * 0.39894228040143267794f * e;
+}
+__device__ __forceinline__ float gelu_f(float x) {
+    float g, dg;
+    gelu_both(x, g, dg);
+    return g;
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
-    const float kInvSqrt2Pi = 0.39894228040143267794f;
-    float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-    return cdf + x * kInvSqrt2Pi * expf(-0.5f * x * x);
+    float g, dg;
+    gelu_both(x, g, dg);
+    return dg;
+}
+// tanh(x) = 1 - 2 / (exp(2x) + 1): MUFU.EX2 + MUFU.RCP, abs error < 4e-7
+__device__ __forceinline__ float tanh_fast(float x) {
+    float e = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, e + 1.f);
 }
 __device__ __forceinline__ float act_f(int act, float x) {
-    return act == SG_ACT_GELU ? gelu_f(x) : (act == SG_ACT_TANH ? tanhf(x) : x);
+    return act == SG_ACT_GELU ? gelu_f(x) : (act == SG_ACT_TANH ? tanh_fast(x) : x);
 }
-// derivative of act at pre-activation x
-__device__ __forceinline__ float act_grad_f(int act, float x) {
-    if (act == SG_ACT_GELU) return gelu_grad_f(x);
-    if (act == SG_ACT_TANH) {
-        float t = tanhf(x);
-        return 1.0f - t * t;
+// value and derivative of act at pre-activation x
+__device__ __forceinline__ void act_both(int act, float x, float& val, float& dval) {
+    if (act == SG_ACT_GELU) {
+        gelu_both(x, val, dval);
+    } else if (act == SG_ACT_TANH) {
+        val = tanh_fast(x);
+        dval = 1.0f - val * val;
+    } else {
+        val = x;
+        dval = 1.0f;
     }
-    return 1.0f;
 }
 
 struct GnStat {

@@ -17,9 +17,9 @@
 // cannot be a 1-element shift of a box along the contiguous r axis: operands of k-tap convs are stored
 // as k pre-shifted planes (common.cuh, store_row_planes) and tap j selects a plane through the third
 // TMA coordinate - the conv's zero padding is already baked into the planes.
-#include <cuda.h>
+#include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace sg {
 
@@ -31,112 +31,6 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 48 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-
-enum { MODE_FPROP = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
-
-struct TcParams {
-    float* out;
-    const float* bias;
-    int M, N;            // output tile space (rows, cols); N is a multiple of 8
-    long long ldc;       // row pitch of out
-    long long c_sz;      // wgrad: output stride per tap
-    int m_tiles, n_tiles, z_count, splits;
-    int taps;            // taps looped inside the K loop (fprop/dgrad: k, wgrad: 1)
-    int kblocks;         // K blocks of 64 per tap
-    int pad;
-    int accumulate;      // out += result
-    int atomic;          // split-K: red.add into out
-    int m_fastest;
-    int b_plane0, b_plane_step;   // B operand plane for tap j (or output tap z): b_plane0 + j * b_plane_step
-    int a_plane;                  // wgrad: plane of dy that holds the unshifted gradient
-};
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) {
-            printf("simulgen_b200: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                                 uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// smem matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout_type=2 [61,64)).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 
 struct Work {
     int m0, n0, z, it_lo, it_hi, split;
@@ -402,8 +296,7 @@ static int num_sms() {
     return n;
 }
 
-static int pick_splits(int tiles, int iters) {
-    int sms = num_sms();
+static int pick_splits(int tiles, int iters, int sms) {
     if (tiles >= sms || iters < 64) return 1;
     int best = 1;
     double best_eff = 0.0;
@@ -431,20 +324,52 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, cud
     return check_launch("conv_gemm_tc");
 }
 
+}  // namespace sg
+#include "gemm_tc2.cuh"
+namespace sg {
+
+template <int MODE>
+static int launch_tc2(const CUtensorMap& a, const CUtensorMap& b, TcParams p, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(pair::conv_gemm_tc2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             pair::SMEM_BYTES);
+        SG_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(pair smem=%d) failed: %s", pair::SMEM_BYTES, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    int work = p.m_tiles * p.n_tiles * p.z_count * p.splits;
+    int pairs = num_sms() / 2;
+    int grid = 2 * (work < pairs ? work : pairs);
+    pair::conv_gemm_tc2_kernel<MODE><<<grid, pair::NUM_THREADS, pair::SMEM_BYTES, st>>>(a, b, p);
+    return check_launch("conv_gemm_tc2");
+}
+
+// CTA-pair kernel for every GEMM with more than one 128-row tile; SG_TC_PAIR=0 forces the single-CTA kernel.
+static bool use_pair(int M) {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("SG_TC_PAIR");
+        mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return mode == 1 && M > 128;
+}
+
 int tc_fprop(const void* wg, const void* act, int act_planes, long long act_pstride, const float* bias, float* out,
              int Cin, int Cin_p, int Cout, int k, int R, int accumulate, cudaStream_t st) {
     CUtensorMap ma, mb;
     if (make_map_wg(&ma, wg, Cin_p, Cout, k)) return 1;
     if (make_map_op(&mb, act, R, Cin, act_planes, act_pstride)) return 1;
     TcParams p{};
+    const bool pair = use_pair(Cout);
     p.out = out; p.bias = bias; p.M = Cout; p.N = R; p.ldc = R; p.c_sz = 0;
-    p.m_tiles = (int)cdiv(Cout, BM); p.n_tiles = (int)cdiv(R, BN); p.z_count = 1;
+    p.m_tiles = (int)cdiv(Cout, pair ? pair::PM : BM); p.n_tiles = (int)cdiv(R, BN); p.z_count = 1; p.group_m = 8;
     p.taps = k; p.kblocks = (int)cdiv(Cin, BK); p.pad = k / 2; p.accumulate = accumulate;
     p.b_plane0 = act_planes / 2 - k / 2; p.b_plane_step = 1; p.a_plane = 0;
-    p.splits = pick_splits(p.m_tiles * p.n_tiles, p.taps * p.kblocks);
+    p.splits = pick_splits(p.m_tiles * p.n_tiles, p.taps * p.kblocks, pair ? num_sms() / 2 : num_sms());
     p.atomic = p.splits > 1;
     p.m_fastest = p.m_tiles <= p.n_tiles;
     if (p.atomic && !accumulate) cudaMemsetAsync(out, 0, sizeof(float) * (size_t)Cout * R, st);
+    if (pair) return launch_tc2<MODE_FPROP>(ma, mb, p, st);
     return launch_tc<MODE_FPROP>(ma, mb, p, st);
 }
 
@@ -454,14 +379,16 @@ int tc_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_pstride
     if (make_map_wg(&ma, wg, Cin_p, Cout, k)) return 1;
     if (make_map_op(&mb, dy, R, Cout, dy_planes, dy_pstride)) return 1;
     TcParams p{};
+    const bool pair = use_pair(Cin);
     p.out = dx; p.bias = nullptr; p.M = Cin; p.N = R; p.ldc = R; p.c_sz = 0;
-    p.m_tiles = (int)cdiv(Cin, BM); p.n_tiles = (int)cdiv(R, BN); p.z_count = 1;
+    p.m_tiles = (int)cdiv(Cin, pair ? pair::PM : BM); p.n_tiles = (int)cdiv(R, BN); p.z_count = 1; p.group_m = 8;
     p.taps = k; p.kblocks = (int)cdiv(Cout, BK); p.pad = k / 2; p.accumulate = accumulate;
     p.b_plane0 = dy_planes / 2 + k / 2; p.b_plane_step = -1; p.a_plane = 0;
-    p.splits = pick_splits(p.m_tiles * p.n_tiles, p.taps * p.kblocks);
+    p.splits = pick_splits(p.m_tiles * p.n_tiles, p.taps * p.kblocks, pair ? num_sms() / 2 : num_sms());
     p.atomic = p.splits > 1;
     p.m_fastest = p.m_tiles <= p.n_tiles;
     if (p.atomic && !accumulate) cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)Cin * R, st);
+    if (pair) return launch_tc2<MODE_DGRAD>(ma, mb, p, st);
     return launch_tc<MODE_DGRAD>(ma, mb, p, st);
 }
 
@@ -471,14 +398,16 @@ int tc_wgrad(const void* dy, int dy_planes, long long dy_pstride, const void* ac
     if (make_map_op(&ma, dy, R, Cout, dy_planes, dy_pstride)) return 1;
     if (make_map_op(&mb, act, R, Cin, act_planes, act_pstride)) return 1;
     TcParams p{};
+    const bool pair = use_pair(Cout);
     p.out = dwg; p.bias = nullptr; p.M = Cout; p.N = Cin_p; p.ldc = Cin_p; p.c_sz = (long long)Cout * Cin_p;
-    p.m_tiles = (int)cdiv(Cout, BM); p.n_tiles = (int)cdiv(Cin_p, BN); p.z_count = k;
+    p.m_tiles = (int)cdiv(Cout, pair ? pair::PM : BM); p.n_tiles = (int)cdiv(Cin_p, BN); p.z_count = k; p.group_m = 8;
     p.taps = 1; p.kblocks = (int)cdiv(R, BK); p.pad = k / 2; p.accumulate = 0;
     p.b_plane0 = act_planes / 2 - k / 2; p.b_plane_step = 1; p.a_plane = dy_planes / 2;
-    p.splits = pick_splits(p.m_tiles * p.n_tiles * k, p.kblocks);
+    p.splits = pick_splits(p.m_tiles * p.n_tiles * k, p.kblocks, pair ? num_sms() / 2 : num_sms());
     p.atomic = p.splits > 1;
     p.m_fastest = p.m_tiles <= p.n_tiles;
     if (p.atomic) cudaMemsetAsync(dwg, 0, sizeof(float) * (size_t)k * Cout * Cin_p, st);
+    if (pair) return launch_tc2<MODE_WGRAD>(ma, mb, p, st);
     return launch_tc<MODE_WGRAD>(ma, mb, p, st);
 }
 

@@ -1,0 +1,306 @@
+// CTA-pair (cta_group::2) variant of the tcgen05 implicit-GEMM kernel.  Included by gemm_tc.cu.
+//
+// Two CTAs of a cluster (same TPC) work on one 256 x 256 output tile: CTA r owns rows [128 r, 128 r + 128)
+// of A and of the accumulator, and loads only HALF of the B tile (columns [128 r, 128 r + 128)); the
+// tcgen05.mma.cta_group::2 issued by the leader reads A and B from both CTAs' shared memory.  Per CTA and
+// 64-deep k-block that is 32 KB of TMA traffic instead of 48 KB for the same FLOPs: the single-CTA kernel
+// was bound by L2 -> SM bandwidth / power (profiles/r1_ncu_full_gemm_*: L2 throughput 55-68 %, tensor pipe
+// 45-75 % active, SM clock capped at 1.2-1.5 GHz), so bytes per FLOP is the lever.
+//
+// Protocol (per smem stage s, per accumulator buffer a):
+//   full[s]   (leader CTA, count 1): leader's producer arrives with expect_tx(64 KB); the TMA loads of BOTH
+//             CTAs complete_tx on it (the peer's loads name the leader's barrier: address bit 24 cleared)
+//   empty[s]  (each CTA, count 1):   tcgen05.commit ... multicast::cluster from the leader's MMA thread
+//   tfull[a]  (each CTA, count 1):   same multicast commit after the last k-block of a tile
+//   tempty[a] (leader CTA, count 8): the 4 epilogue warps of both CTAs arrive (the peer's remotely)
+//
+// Epilogue: TMEM -> registers (tcgen05.ld 32x32b.x32: lane = row) -> per-warp padded smem slab -> global
+// stores in which 8 consecutive lanes write one 128-byte row segment (the single-CTA kernel stores 16 bytes
+// per lane into 32 different rows per instruction).
+#pragma once
+
+namespace sg {
+namespace pair {
+
+constexpr int BMH = 128;            // rows per CTA
+constexpr int PM = 256;             // rows per pair tile
+constexpr int BN = 256, BNH = 128, BK = 64, STAGES = 6;
+constexpr int BOX_BYTES = 64 * 64 * 2;
+constexpr int A_BYTES = BMH * BK * 2;                 // 16 KB
+constexpr int B_BYTES = BNH * BK * 2;                 // 16 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // 32 KB
+constexpr int EPI_PITCH = 33;                         // floats per staged row (bank-conflict-free)
+constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;     // 4 epilogue warps
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, uint32_t bar_addr, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                     uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at the same smem offset in the leader CTA (rank 0 of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
+
+struct PairWork {
+    int m0, n0, z, it_lo, it_hi, split;
+};
+
+// tile order: groups of `group_m` m-tiles; inside a group n is the slow index, so one wave of CTA pairs covers a
+// roughly square patch of the output and every operand row/column it needs is fetched from DRAM once per wave.
+__device__ __forceinline__ PairWork decode_pair_work(const TcParams& p, int w, int total_iters) {
+    PairWork r;
+    int tiles = p.m_tiles * p.n_tiles;
+    int t = w % tiles;
+    int rest = w / tiles;
+    r.z = rest % p.z_count;
+    r.split = rest / p.z_count;
+    int per_group = p.group_m * p.n_tiles;
+    int g = t / per_group;
+    int in_g = t - g * per_group;
+    int gm = min(p.group_m, p.m_tiles - g * p.group_m);     // m-tiles in this (possibly last, smaller) group
+    int nt = in_g / gm, mt = g * p.group_m + (in_g - nt * gm);
+    r.m0 = mt * PM;
+    r.n0 = nt * BN;
+    int per = (total_iters + p.splits - 1) / p.splits;
+    r.it_lo = r.split * per;
+    r.it_hi = min(total_iters, r.it_lo + per);
+    return r;
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+    uint64_t* full_bar = bars;                    // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    constexpr bool A_MN = (MODE == MODE_DGRAD);
+    constexpr bool B_MN = (MODE != MODE_WGRAD);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_iters = p.taps * p.kblocks;
+    const int num_work = p.m_tiles * p.n_tiles * p.z_count * p.splits;
+    const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = pair_id; w < num_work; w += num_pairs) {
+                PairWork wk = decode_pair_work(p, w, total_iters);
+                const int m_cta = wk.m0 + (int)rank * BMH;
+                const int n_cta = wk.n0 + (int)rank * BNH;
+                for (int it = wk.it_lo; it < wk.it_hi; ++it) {
+                    int kb = it / p.taps, j = it - kb * p.taps;   // taps innermost: shifted reloads hit L2
+                    int k0 = kb * BK;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                    const uint32_t bar = smem_u32(&full_bar[stage]) & kPeerMask;     // the leader's barrier
+                    if (MODE == MODE_FPROP) {
+                        tma_load_3d_2sm(&tmA, bar, sa, k0, m_cta, j);
+                        tma_load_3d_2sm(&tmA, bar, sa + BOX_BYTES, k0, m_cta + 64, j);
+                        const int pl = p.b_plane0 + j * p.b_plane_step;
+                        tma_load_3d_2sm(&tmB, bar, sb, n_cta, k0, pl);
+                        tma_load_3d_2sm(&tmB, bar, sb + BOX_BYTES, n_cta + 64, k0, pl);
+                    } else if (MODE == MODE_DGRAD) {
+                        tma_load_3d_2sm(&tmA, bar, sa, m_cta, k0, j);
+                        tma_load_3d_2sm(&tmA, bar, sa + BOX_BYTES, m_cta + 64, k0, j);
+                        const int pl = p.b_plane0 + j * p.b_plane_step;
+                        tma_load_3d_2sm(&tmB, bar, sb, n_cta, k0, pl);
+                        tma_load_3d_2sm(&tmB, bar, sb + BOX_BYTES, n_cta + 64, k0, pl);
+                    } else {
+                        tma_load_3d_2sm(&tmA, bar, sa, k0, m_cta, p.a_plane);
+                        tma_load_3d_2sm(&tmA, bar, sa + BOX_BYTES, k0, m_cta + 64, p.a_plane);
+                        const int pl = p.b_plane0 + wk.z * p.b_plane_step;
+                        tma_load_3d_2sm(&tmB, bar, sb, k0, n_cta, pl);
+                        tma_load_3d_2sm(&tmB, bar, sb + BOX_BYTES, k0, n_cta + 64, pl);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();                   // reconverge: the cluster barrier below is .aligned
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, M=256 (pair), N=256, majors per mode
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                   ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(PM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int tile_iter = 0;
+            for (int w = pair_id; w < num_work; w += num_pairs, ++tile_iter) {
+                PairWork wk = decode_pair_work(p, w, total_iters);
+                int as = tile_iter & 1;
+                uint32_t aphase = (tile_iter >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tcgen05_fence_after();
+                uint32_t tmem_d = tmem_base + as * BN;
+                for (int it = wk.it_lo; it < wk.it_hi; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    uint32_t sb = sa + A_BYTES;
+                    uint64_t da = A_MN ? make_desc(sa, BOX_BYTES, 1024) : make_desc(sa, 16, 1024);
+                    uint64_t db = B_MN ? make_desc(sb, BOX_BYTES, 1024) : make_desc(sb, 16, 1024);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        uint64_t a = da + (uint64_t)((A_MN ? 2048 : 32) * kk >> 4);
+                        uint64_t b = db + (uint64_t)((B_MN ? 2048 : 32) * kk >> 4);
+                        tcgen05_mma_bf16_2sm(tmem_d, a, b, idesc, (it > wk.it_lo || kk > 0) ? 1u : 0u);
+                    }
+                    tcgen05_commit_2sm(&empty_bar[stage]);      // frees the slot in both CTAs
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit_2sm(&tfull_bar[as]);             // accumulator ready in both CTAs
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warps 2..5, both CTAs) =====================
+        const int q = warp & 3;                              // TMEM lane quarter this warp may access
+        float* slab = epi + q * 32 * EPI_PITCH;
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        int tile_iter = 0;
+        for (int w = pair_id; w < num_work; w += num_pairs, ++tile_iter) {
+            PairWork wk = decode_pair_work(p, w, total_iters);
+            int as = tile_iter & 1;
+            uint32_t aphase = (tile_iter >> 1) & 1;
+            mbar_wait(&tfull_bar[as], aphase);
+            tcgen05_fence_after();
+            const int m_base = wk.m0 + (int)rank * BMH + q * 32;
+            float bias = 0.f;
+            if (p.bias != nullptr && m_base + lane < p.M && wk.split == 0) bias = p.bias[m_base + lane];
+            const bool have_k = wk.it_hi > wk.it_lo;
+            float* obase = p.out + (long long)wk.z * p.c_sz;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32);
+                tmem_ld_32x32b_x32(taddr, v);
+                tmem_ld_wait();
+                const int n = wk.n0 + c * 32 + sub_c;
+                if (have_k && wk.n0 + c * 32 < p.N) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) slab[lane * EPI_PITCH + e] = __uint_as_float(v[e]) + bias;
+                    __syncwarp();
+                    if (n < p.N) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rl = i * 4 + sub_r;
+                            const int m = m_base + rl;
+                            if (m < p.M) {
+                                const float* sp = slab + rl * EPI_PITCH + sub_c;
+                                float4 r = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                                if (p.out_bf16) {
+                                    __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
+                                    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(obase) + (long long)m * p.ldc + n) = pk;
+                                } else {
+                                    float* dst = obase + (long long)m * p.ldc + n;
+                                    if (p.atomic) {
+                                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(r.x), "f"(r.y),
+                                                     "f"(r.z), "f"(r.w)
+                                                     : "memory");
+                                    } else {
+                                        if (p.accumulate) {
+                                            float4 o = *reinterpret_cast<const float4*>(dst);
+                                            r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+                                        }
+                                        *reinterpret_cast<float4*>(dst) = r;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_leader(&tempty_bar[as]);
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();                 // nobody leaves (or frees TMEM) while the peer may still touch this CTA
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+    }
+}
+
+}  // namespace pair
+}  // namespace sg

@@ -207,7 +207,8 @@ __device__ __forceinline__ void bwd_segment(const BwdArgs& p, long long row, int
         int t = seg * 8 + i;
         bool valid = t < p.T;
         float yh = yv.v[i] * a + sh;
-        float val = act_f(p.act, yh);
+        float val, dval;
+        act_both(p.act, yh, val, dval);
         float d;
         if (LOSS) {
             d = 0.f;
@@ -227,7 +228,7 @@ __device__ __forceinline__ void bwd_segment(const BwdArgs& p, long long row, int
             float pre = p.res_scale * val + (res != nullptr ? rv.v[i] : 0.f);
             dp = d * gelu_grad_f(pre);
         }
-        float g = p.res_scale * dp * act_grad_f(p.act, yh);
+        float g = p.res_scale * dp * dval;
         dyh.v[i] = valid ? g : 0.f;
         xhat.v[i] = valid ? (yv.v[i] - mean) * rstd : 0.f;
         dpre.v[i] = valid ? dp : 0.f;
@@ -329,13 +330,6 @@ gn_bwd_apply_kernel(BwdArgs p, const double* __restrict__ S, OT* __restrict__ dy
 // recon head forward: x_hat = tanh(GN(y)) in the external layout + loss sums (+ the per-row partial
 // sums of the GroupNorm backward, so that the backward needs ONE pass over y / x instead of two)
 // ---------------------------------------------------------------------------------------------
-// tanh(x) = 1 - 2 / (exp(2x) + 1): MUFU.EX2 + MUFU.RCP, abs error < 4e-7 (tanhf costs ~3x the issue slots;
-// these kernels run over B*N*T elements and were ALU-bound with it).
-__device__ __forceinline__ float tanh_fast(float x) {
-    float e = __expf(2.f * x);
-    return 1.f - __fdividef(2.f, e + 1.f);
-}
-
 // 8 consecutive elements of an external-layout row ([B][N][T], row start 16-byte aligned when VEC)
 template <bool VEC>
 __device__ __forceinline__ F8 load8_ext(const float* row, int t0, int T) {
@@ -366,7 +360,7 @@ __device__ __forceinline__ void store8_ext(float* row, int t0, int T, const F8& 
 // persistent: grid = min(rows / 8, a few waves); every warp strides over (n, b) rows.
 // rowsums[row] = (sum gL, sum gL*xn, sum gM, sum gM*xn) with gL = loss'(d)(1 - xh^2), gM = 2 d (1 - xh^2),
 // xn = (y - mean) rstd: the backward scales them by the upstream loss gradients (they are linear in them).
-template <bool VEC>
+template <bool VEC, bool MSE>
 __global__ void __launch_bounds__(kThreads)
 recon_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ x, float* __restrict__ x_hat,
@@ -395,23 +389,28 @@ recon_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats, 
                 xh.v[i] = h;
                 if (x != nullptr && valid) {
                     float d = h - xv.v[i];
-                    l0 += loss_term(loss_kind, d);
                     l1 += d * d;
+                    if (!MSE) l0 += loss_term(loss_kind, d);
                     if (rowsums != nullptr) {
                         float om = 1.f - h * h;
                         float xn = (yv.v[i] - st.mean) * st.rstd;
-                        float gl = loss_grad(loss_kind, d) * om, gm = 2.f * d * om;
-                        aL += gl; bL += gl * xn; aM += gm; bM += gm * xn;
+                        float gm = 2.f * d * om;
+                        aM += gm; bM += gm * xn;
+                        if (!MSE) {
+                            float gl = loss_grad(loss_kind, d) * om;
+                            aL += gl; bL += gl * xn;
+                        }
                     }
                 }
             }
             if (x_hat != nullptr) store8_ext<VEC>(x_hat + xo, seg * 8, T, xh);
         }
         if (rowsums != nullptr) {
-            aL = warp_sum(aL); bL = warp_sum(bL); aM = warp_sum(aM); bM = warp_sum(bM);
+            aM = warp_sum(aM); bM = warp_sum(bM);
+            if (MSE) { aL = aM; bL = bM; } else { aL = warp_sum(aL); bL = warp_sum(bL); }
             if (lane == 0) rowsums[row] = make_float4(aL, bL, aM, bM);
         }
-        d0 += (double)l0;   // flush the fp32 partials per row
+        d0 += (double)(MSE ? l1 : l0);   // flush the fp32 partials per row
         d1 += (double)l1;
     }
     if (x != nullptr) {
@@ -461,7 +460,7 @@ recon_bwd_combine_kernel(const float4* __restrict__ rowsums, const float* __rest
 }
 
 // backward, step 2: dy = rstd * (gamma * g - m1 - xn * m2), g = (ga loss'(d) + gm 2d)(1 - xh^2)
-template <typename OT, bool VEC>
+template <typename OT, bool VEC, bool MSE>
 __global__ void __launch_bounds__(kThreads)
 recon_bwd_apply_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
                        const float* __restrict__ beta, const float* __restrict__ x, const float* __restrict__ scal,
@@ -471,6 +470,7 @@ recon_bwd_apply_kernel(const float* __restrict__ y, const double* __restrict__ s
     const long long rows = (long long)N * B;
     const long long wstride = (long long)gridDim.x * kWarpsPerBlock;
     const float ga = scal[0], gm = scal[1];
+    const float g2 = 2.f * (ga + gm);      // MSE: ga * 2d + gm * 2d
     for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
         int n = (int)(row / B), b = (int)(row % B);
         int g = n / (N / G);
@@ -491,7 +491,7 @@ recon_bwd_apply_kernel(const float* __restrict__ y, const double* __restrict__ s
                 for (int i = 0; i < 8; ++i) {
                     float h = tanh_fast(yv.v[i] * a + sh);
                     float d = h - xv.v[i];
-                    float gg = (ga * loss_grad(loss_kind, d) + gm * 2.f * d) * (1.f - h * h);
+                    float gg = (MSE ? g2 * d : ga * loss_grad(loss_kind, d) + gm * 2.f * d) * (1.f - h * h);
                     float xn = (yv.v[i] - st.mean) * st.rstd;
                     float v = (seg * 8 + i < T) ? st.rstd * (gam * gg - m1 - xn * m2) : 0.f;
                     o.v[i] = v;
@@ -657,12 +657,13 @@ int sg_recon_fwd(const float* y, const double* stats, const float* gamma, const 
     double inv_n = 1.0 / ((double)(N / G) * T);
     bool vec = (T % 4 == 0) && aligned16(x) && aligned16(x_hat);
     int grid = persistent_grid((long long)N * B);
-    if (vec)
-        recon_fwd_kernel<true><<<grid, kThreads, 0, st>>>(y, stats, gamma, beta, x, x_hat, loss_sums, (float4*)rowsums, N,
-                                                          B, T, Tp, G, loss_kind, inv_n);
-    else
-        recon_fwd_kernel<false><<<grid, kThreads, 0, st>>>(y, stats, gamma, beta, x, x_hat, loss_sums, (float4*)rowsums,
-                                                           N, B, T, Tp, G, loss_kind, inv_n);
+    const bool mse = loss_kind == SG_LOSS_MSE;
+#define SG_RFWD(VEC, MSE)                                                                                              \
+    recon_fwd_kernel<VEC, MSE><<<grid, kThreads, 0, st>>>(y, stats, gamma, beta, x, x_hat, loss_sums, (float4*)rowsums, N, \
+                                                          B, T, Tp, G, loss_kind, inv_n)
+    if (vec) { if (mse) SG_RFWD(true, true); else SG_RFWD(true, false); }
+    else     { if (mse) SG_RFWD(false, true); else SG_RFWD(false, false); }
+#undef SG_RFWD
     return check_launch("recon_fwd");
 }
 
@@ -754,11 +755,14 @@ extern "C" int sg_recon_bwd(const float* y, const double* stats, const float* ga
                                                                                dbeta, S, N, B, G);
         int grid = persistent_grid((long long)N * B);
         bool vec = (T % 4 == 0) && aligned16(x);
-#define SG_APPLY(OT, VEC)                                                                                       \
-    recon_bwd_apply_kernel<OT, VEC><<<grid, kThreads, 0, st>>>(y, stats, gamma, beta, x, scal, S, (OT*)dy, dbias, N, B, \
-                                                                T, Tp, G, loss_kind, inv_n)
-        if (dtype == SG_BF16) { if (vec) SG_APPLY(__nv_bfloat16, true); else SG_APPLY(__nv_bfloat16, false); }
-        else                  { if (vec) SG_APPLY(float, true); else SG_APPLY(float, false); }
+        const bool mse = loss_kind == SG_LOSS_MSE;
+#define SG_APPLY(OT, VEC, MSE)                                                                                       \
+    recon_bwd_apply_kernel<OT, VEC, MSE><<<grid, kThreads, 0, st>>>(y, stats, gamma, beta, x, scal, S, (OT*)dy, dbias, N, \
+                                                                     B, T, Tp, G, loss_kind, inv_n)
+#define SG_APPLY2(OT, VEC) do { if (mse) SG_APPLY(OT, VEC, true); else SG_APPLY(OT, VEC, false); } while (0)
+        if (dtype == SG_BF16) { if (vec) SG_APPLY2(__nv_bfloat16, true); else SG_APPLY2(__nv_bfloat16, false); }
+        else                  { if (vec) SG_APPLY2(float, true); else SG_APPLY2(float, false); }
+#undef SG_APPLY2
 #undef SG_APPLY
         return check_launch("recon_bwd");
     }

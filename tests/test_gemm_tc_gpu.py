@@ -21,6 +21,8 @@ SHAPES = [
     (1280, 1280, 5, 2, 200),     # the decoder residual shape (scaled), deep K loop
     (8200, 136, 1, 2, 100),      # large K with split-K, ragged M
     (200, 4104, 1, 2, 100),      # recon-like: large M
+    (300, 2600, 3, 6, 200),      # CTA-pair kernel: 11 pair m-tiles (raster groups of 8 + 3) x 5 n-tiles, ragged everywhere
+    (136, 300, 1, 1, 40),        # pair tile with a mostly empty peer half, single n-tile
 ]
 
 
