@@ -210,7 +210,7 @@ def main():
 def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=int(os.environ.get("SIMULGEN_BENCH_BATCH", "32")), help="per-GPU batch")
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
