@@ -88,18 +88,19 @@ int sg_conv_wgrad(const void* dy, int dy_planes, long long dy_plane_stride, cons
                   void* stream);
 
 /* ---- GroupNorm + activation + residual (encoder.py:35-36, common.py:85-102, decoder.py:32,119-120)
- * stats[B][G][2] doubles = (sum, sum of squares) over the group's (C/G) x T valid entries. */
-int sg_gn_stats(const float* y, double* stats, int C, int B, int T, int Tp, int G, void* stream);
+ * stats[B][G][2] fp32 = (mean, 1/sqrt(biased variance + 1e-5)) over the group's (C/G) x T valid entries
+ * (nn.GroupNorm semantics; accumulated and finalised in fp64).  ws: >= 2*B*G doubles. */
+int sg_gn_stats(const float* y, double* ws, float* stats, int C, int B, int T, int Tp, int G, void* stream);
 /* pre = res + res_scale * act(gamma * (y - mean) * rstd + beta)   (stats == NULL: no norm, y used as is)
  * out = post_gelu ? gelu(pre) : pre ; written as operand (out_op, dtype, gap zeroed) and/or fp32. */
-int sg_gn_act_fwd(const float* y, const double* stats, const float* gamma, const float* beta,
+int sg_gn_act_fwd(const float* y, const float* stats, const float* gamma, const float* beta,
                   const void* res, int res_is_f32, float res_scale, int act, int post_gelu,
                   void* out_op, int planes, long long plane_stride, float* out_f32,
                   int C, int B, int T, int Tp, int G, int dtype, void* stream);
 /* Backward of the above.  dout fp32 [C][B][Tp].  Writes dy (dtype, gap zeroed) = grad wrt y,
  * dgamma/dbeta (may be NULL when stats == NULL), dbias[C] = sum_{b,t} dy, and dres (fp32,
  * (+)= per dres_accumulate) when res != NULL.  ws: >= 2*B*G doubles. */
-int sg_gn_act_bwd(const float* y, const double* stats, const float* gamma, const float* beta,
+int sg_gn_act_bwd(const float* y, const float* stats, const float* gamma, const float* beta,
                   const void* res, int res_is_f32, float res_scale, int act, int post_gelu,
                   const float* dout, void* dy, int planes, long long plane_stride,
                   float* dgamma, float* dbeta, float* dbias, float* dres, int dres_accumulate, double* ws,
@@ -110,14 +111,14 @@ int sg_gn_act_bwd(const float* y, const double* stats, const float* gamma, const
  * sum of the selected loss terms and sum of squared errors. */
 /* rowsums (optional, fp32 [N*B][4], 16-byte aligned; needs x): per-(n,b)-row partial sums of the GroupNorm
  * backward reductions, taken while y and x are in registers anyway; sg_recon_bwd then needs one pass. */
-int sg_recon_fwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* x,
+int sg_recon_fwd(const float* y, const float* stats, const float* gamma, const float* beta, const float* x,
                  float* x_hat, double* loss_sums, float* rowsums, int N, int B, int T, int Tp, int G, int loss_kind,
                  void* stream);
 /* dx_hat = g_loss[0]*inv_numel*loss'(x_hat-x) + g_mse[0]*inv_numel*2(x_hat-x) + dxhat_ext (each optional),
  * then backward through tanh and GroupNorm -> dy (dtype, 1 plane), dgamma, dbeta, dbias.
  * rowsums: the buffer sg_recon_fwd filled (or NULL: two passes; also used when dxhat_ext != NULL).
  * ws: >= 2*B*G + 2 doubles. */
-int sg_recon_bwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* x,
+int sg_recon_bwd(const float* y, const float* stats, const float* gamma, const float* beta, const float* x,
                  const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext,
                  const float* rowsums, void* dy, float* dgamma, float* dbeta, float* dbias, double* ws,
                  int N, int B, int T, int Tp, int G, int loss_kind, int dtype, void* stream);

@@ -1,0 +1,126 @@
+"""Stand-alone timing of the HBM-streaming kernels at the headline shapes (per-GPU batch B): CUDA-event time and
+achieved algorithmic GB/s against the measured HBM copy bandwidth.  Small memory footprint so that it can also
+run under `ncu --set full`."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from simulgen_vae_b200 import kernels as K  # noqa: E402
+from simulgen_vae_b200.engine import tp_of  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+ONLY = sys.argv[3] if len(sys.argv) > 3 else ""
+T, N, G = 200, 95008, 8
+Tp = tp_of(T)
+dev = torch.device("cuda")
+BF = torch.bfloat16
+try:
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    PEAK = 6650.0
+
+
+def timed(fn):
+    fn()
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ts = []
+    for _ in range(REPS):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+def report(name, ms, nbytes):
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    print("%-34s B=%d %8.3f ms  %7.2f GB  %7.0f GB/s  %.3f of measured HBM peak (%.0f)" % (name, B, ms, nbytes / 1e9, gbs, gbs / PEAK, PEAK),
+          flush=True)
+
+
+def want(name):
+    return not ONLY or ONLY in name
+
+
+if want("recon") or want("pack"):
+    x = torch.rand(B, N, T, device=dev) * 1.4 - 0.7
+if want("pack"):
+    op = torch.empty(1, N, B, Tp, device=dev, dtype=BF)
+    report("pack_input", timed(lambda: K.pack_input(x, op, T)), x.numel() * 4 + op.numel() * 2)
+    del op
+if want("recon"):
+    y = torch.randn(N, B, Tp, device=dev)
+    y[..., T:] = 0
+    gamma, beta = torch.ones(N, device=dev), torch.zeros(N, device=dev)
+    stats = torch.empty(B, G, 2, device=dev)
+    report("gn_stats (recon y)", timed(lambda: K.gn_stats(y, stats, T, G)), y.numel() * 4)
+    x_hat = torch.empty(B, N, T, device=dev)
+    sums = torch.empty(2, device=dev, dtype=torch.float64)
+    rows = torch.empty(N * B, 4, device=dev)
+    report("recon_fwd (x_hat + rowsums)", timed(lambda: K.recon_fwd(y, stats, gamma, beta, x, x_hat, sums, T, G, 0, rows)),
+           y.numel() * 4 + x.numel() * 8 + rows.numel() * 4)
+    report("recon_fwd (no x_hat)", timed(lambda: K.recon_fwd(y, stats, gamma, beta, x, None, sums, T, G, 0, rows)),
+           y.numel() * 4 + x.numel() * 4 + rows.numel() * 4)
+    del x_hat
+    dy = torch.empty(1, N, B, Tp, device=dev, dtype=BF)
+    dg, db, dbi = (torch.empty(N, device=dev) for _ in range(3))
+    gl, gm = torch.tensor([1e6], device=dev), torch.tensor([0.0], device=dev)
+    inv = 1.0 / (B * N * T)
+    report("recon_bwd (one pass)", timed(lambda: K.recon_bwd(y, stats, gamma, beta, x, gl, gm, inv, None, dy, dg, db, dbi, T, G, 0, rows)),
+           y.numel() * 4 + x.numel() * 4 + dy.numel() * 2 + rows.numel() * 4)
+    del y, dy, rows, x
+if want("gn_act"):
+    for C, P, res in ((5120, 5, False), (5120, 1, False), (1024, 1, True)):
+        y = torch.randn(C, B, Tp, device=dev)
+        y[..., T:] = 0
+        gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        stats = torch.empty(B, G, 2, device=dev)
+        report("gn_stats C=%d" % C, timed(lambda: K.gn_stats(y, stats, T, G)), y.numel() * 4)
+        out = torch.empty(P, C, B, Tp, device=dev, dtype=BF)
+        of = torch.empty(C, B, Tp, device=dev) if res else None
+        r = torch.randn(C, B, Tp, device=dev) if res else None
+        nb = y.numel() * 4 + out.numel() * 2 + (y.numel() * 8 if res else 0)
+        report("gn_act_fwd C=%d planes=%d res=%d" % (C, P, res),
+               timed(lambda: K.gn_act_fwd(y, stats, gamma, beta, r, 0.1 if res else 1.0, K.ACT_GELU, False, out, of, T, G)), nb)
+        dout = torch.randn(C, B, Tp, device=dev)
+        dyo = torch.empty(P, C, B, Tp, device=dev, dtype=BF)
+        dg, db, dbi = (torch.empty(C, device=dev) for _ in range(3))
+        dres = torch.zeros(C, B, Tp, device=dev) if res else None
+        nb = y.numel() * 16 + dyo.numel() * 2 + (y.numel() * 12 if res else 0)
+        report("gn_act_bwd C=%d planes=%d res=%d" % (C, P, res),
+               timed(lambda: K.gn_act_bwd(y, stats, gamma, beta, r, 0.1 if res else 1.0, K.ACT_GELU, False, dout, dyo, dg, db, dbi,
+                                          dres, 1, T, G)), nb)
+        del y, out, dout, dyo, of, r, dres
+if want("opt"):
+    items = []
+    for Cout, Cin, k in ((1024, 95008, 1), (5120, 5120, 5)):
+        Cin_p = (Cin + 7) // 8 * 8
+        p = torch.randn(Cout, Cin, k, device=dev) * 0.01
+        items.append(dict(p=p, g=torch.randn(k, Cout, Cin_p, device=dev), m=torch.zeros_like(p), v=torch.zeros_like(p),
+                          u=torch.randn(Cout, device=dev), vv=torch.randn(Cin * k, device=dev), sigma=torch.ones(1, device=dev),
+                          Cout=Cout, Cin=Cin, Cin_p=Cin_p, k=k, flip=0))
+    gn = torch.zeros(1, device=dev, dtype=torch.float64)
+    for i, it in enumerate(items):
+        plan = K.OptPlan([it], dev)
+        n = it["p"].numel()
+        report("opt_step k=%d (%dM elems)" % (it["k"], n // 1000000),
+               timed(lambda: K.opt_step(plan, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0, gn)), n * 36)
+if want("sn_prepare"):
+    layers = []
+    for Cout, Cin, k in ((1024, 95008, 1), (5120, 5120, 5), (95008, 1024, 1)):
+        Cin_p = (Cin + 7) // 8 * 8
+        w = torch.randn(Cout, Cin, k, device=dev) * 0.01
+        layers.append(dict(w=w, u=torch.randn(Cout, device=dev), v=torch.randn(Cin * k, device=dev), sigma=torch.ones(1, device=dev),
+                           wg=torch.empty(k, Cout, Cin_p, device=dev, dtype=BF), H=Cout, Cin=Cin, k=k, Cin_p=Cin_p, so=Cin * k, si=k,
+                           flip=0))
+    plan = K.SnPlan(layers, dev, BF)
+    n = sum(L["w"].numel() for L in layers)
+    report("sn_prepare (3 big layers, %dM)" % (n // 1000000), timed(lambda: K.sn_prepare(plan, True)), n * 14)

@@ -30,7 +30,7 @@ SIGNATURES = {
     "sg_conv_fprop": [P, P, I, L, P, P, I, I, I, I, I, I, I, P],
     "sg_conv_dgrad": [P, P, I, L, P, I, I, I, I, I, I, I, P],
     "sg_conv_wgrad": [P, I, L, P, I, L, P, I, I, I, I, I, I, P],
-    "sg_gn_stats": [P, P, I, I, I, I, I, P],
+    "sg_gn_stats": [P, P, P, I, I, I, I, I, P],
     "sg_gn_act_fwd": [P, P, P, P, P, I, F, I, I, P, I, L, P, I, I, I, I, I, I, P],
     "sg_gn_act_bwd": [P, P, P, P, P, I, F, I, I, P, P, I, L, P, P, P, P, I, P, I, I, I, I, I, I, P],
     "sg_recon_fwd": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, P],

@@ -103,6 +103,136 @@ __device__ __forceinline__ void store_row_planes(OT* base, long long row_off, in
     }
 }
 
+// Register / shuffle variant of store_row_planes for rows of at most 256 elements (one 8-element segment per
+// lane): the two neighbours a shifted plane needs on each side come from the adjacent lanes by warp shuffle, so
+// the k shifted copies cost 4 shuffles instead of a shared-memory round trip per element and plane (the smem
+// version made the 5-plane writers MIO-bound).  Must be called by all 32 lanes; `o` holds this lane's segment
+// (zeros for t >= T and for lanes beyond the row), lanes with seg >= nseg_p do not store.
+template <typename OT, int PLANES>
+__device__ __forceinline__ void store_planes_shfl(OT* base, long long row_off, long long pstride, const F8& o, int T, int nseg_p,
+                                                  int lane) {
+    float ext[12];
+    ext[0] = __shfl_up_sync(0xffffffffu, o.v[6], 1);
+    ext[1] = __shfl_up_sync(0xffffffffu, o.v[7], 1);
+    ext[10] = __shfl_down_sync(0xffffffffu, o.v[0], 1);
+    ext[11] = __shfl_down_sync(0xffffffffu, o.v[1], 1);
+    if (lane == 0) { ext[0] = 0.f; ext[1] = 0.f; }
+    if (lane == 31) { ext[10] = 0.f; ext[11] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ext[2 + i] = o.v[i];
+    if (lane >= nseg_p) return;
+    const int t0 = lane * 8;
+#pragma unroll
+    for (int pl = 0; pl < PLANES; ++pl) {
+        const int s = pl - PLANES / 2;
+        F8 r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = (t0 + i < T) ? ext[2 + i + s] : 0.f;
+        store8(base + (long long)pl * pstride + row_off + t0, r);
+    }
+}
+template <typename OT>
+__device__ __forceinline__ void store_planes_shfl_n(OT* base, long long row_off, int planes, long long pstride, const F8& o, int T,
+                                                    int nseg_p, int lane) {
+    if (planes == 5) store_planes_shfl<OT, 5>(base, row_off, pstride, o, T, nseg_p, lane);
+    else if (planes == 3) store_planes_shfl<OT, 3>(base, row_off, pstride, o, T, nseg_p, lane);
+    else store_planes_shfl<OT, 1>(base, row_off, pstride, o, T, nseg_p, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + bulk-copy (TMA 1-D) helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) {
+            printf("simulgen_b200: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+// contiguous global -> shared copy by the TMA unit; `bytes` and both addresses are multiples of 16
+__device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src_gmem)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Per-warp asynchronous row prefetcher for the HBM-streaming kernels.  The bytes a streaming kernel keeps in
+// flight normally live in destination registers of pending loads, and with ~50 registers per thread that is
+// 30-60 KB per SM: not enough to cover the ~1 us HBM latency at 6.5 TB/s (round 1: 30-70 % of the HBM roofline,
+// while the 32-register pack kernel reached 88 %).  Here each warp owns DEPTH shared-memory slots; lane 0 asks the
+// TMA unit to copy the next DEPTH rows (each row = up to NS contiguous streams) and the warp consumes them in
+// order, re-arming a slot as soon as its data has been read into registers.
+template <int NS, int DEPTH>
+struct RowPipe {
+    uint8_t* slots;          // this warp's DEPTH * slot_bytes staging area (16-byte aligned)
+    uint64_t* bars;          // this warp's DEPTH mbarriers
+    uint32_t slot_bytes;
+    uint32_t off[NS];        // byte offset of each stream inside a slot
+
+    __device__ __forceinline__ void init(uint8_t* smem, int warps, int warp, int lane, const uint32_t (&stream_bytes)[NS]) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            off[s] = o;
+            o += (stream_bytes[s] + 127u) & ~127u;
+        }
+        slot_bytes = o;
+        slots = smem + (size_t)warp * DEPTH * slot_bytes;
+        bars = reinterpret_cast<uint64_t*>(smem + (size_t)warps * DEPTH * slot_bytes) + warp * DEPTH;
+        if (lane == 0) {
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) mbar_init(&bars[d], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    static __host__ __device__ size_t smem_bytes(int warps, const uint32_t* stream_bytes) {
+        size_t o = 0;
+        for (int s = 0; s < NS; ++s) o += (stream_bytes[s] + 127u) & ~127u;
+        return (size_t)warps * DEPTH * o + (size_t)warps * DEPTH * 8;
+    }
+    // lane 0 only: start the copies of one row into `slot` (src[s] == nullptr skips a stream)
+    __device__ __forceinline__ void issue(int slot, const void* const (&src)[NS], const uint32_t (&bytes)[NS]) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) total += src[s] != nullptr ? bytes[s] : 0u;
+        mbar_arrive_expect_tx(&bars[slot], total);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if (src[s] != nullptr) bulk_load_1d(slots + (size_t)slot * slot_bytes + off[s], src[s], bytes[s], &bars[slot]);
+    }
+    __device__ __forceinline__ void wait(int slot, uint32_t parity) { mbar_wait(&bars[slot], parity); }
+    template <typename T>
+    __device__ __forceinline__ const T* row(int slot, int s) const {
+        return reinterpret_cast<const T*>(slots + (size_t)slot * slot_bytes + off[s]);
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------
@@ -137,15 +267,31 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 // value and derivative cost ~20 issue slots together.  erff() + expf() cost ~100 and made the GroupNorm /
 // activation kernels ALU-bound instead of HBM-bound.
 // ---------------------------------------------------------------------------------------------
+// single-instruction MUFU approximations (the CUDA intrinsics __expf / __fdividef add denormal and range
+// handling - FSETP / FSEL / extra FMULs per call - that these bounded arguments never need)
+__device__ __forceinline__ float fast_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
-    float z = fabsf(x) * 0.70710678118654752440f;
-    float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-    float e = __expf(-z * z);                                    // exp(-x^2 / 2)
-    float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
-    float half_erfc = 0.5f * poly * e;                           // 0.5 * (1 - erf(|x| / sqrt 2))
-    float cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
+    const float e = fast_ex2(x * x * -0.72134752044448170368f);      // exp(-x^2 / 2)
+    // 0.5 * (a1 t + ... + a5 t^5)
+    float poly = fmaf(t, 0.5307027145f, -0.7265760135f);
+    poly = fmaf(t, poly, 0.7107068705f);
+    poly = fmaf(t, poly, -0.142248368f);
+    poly = fmaf(t, poly, 0.127414796f);
+    const float half_erfc = poly * t * e;                           // 0.5 * (1 - erf(|x| / sqrt 2))
+    const float cdf = 0.5f + copysignf(0.5f - half_erfc, x);
     g = x * cdf;
-    dg = cdf + x * 0.39894228040143267794f * e;
+    dg = fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 __device__ __forceinline__ float gelu_f(float x) {
     float g, dg;
@@ -159,8 +305,8 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 }
 // tanh(x) = 1 - 2 / (exp(2x) + 1): MUFU.EX2 + MUFU.RCP, abs error < 4e-7
 __device__ __forceinline__ float tanh_fast(float x) {
-    float e = __expf(2.f * x);
-    return 1.f - __fdividef(2.f, e + 1.f);
+    const float e = fast_ex2(x * 2.88539008177792681472f);           // exp(2x); +inf for large x -> rcp = 0 -> 1
+    return fmaf(-2.f, fast_rcp(e + 1.f), 1.f);
 }
 __device__ __forceinline__ float act_f(int act, float x) {
     return act == SG_ACT_GELU ? gelu_f(x) : (act == SG_ACT_TANH ? tanh_fast(x) : x);

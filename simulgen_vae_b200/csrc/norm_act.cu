@@ -6,9 +6,16 @@
 //   decoder.py:32 (GELU after ConvTranspose1d), decoder.py:117-121 (GroupNorm -> Tanh),
 //   VAE_network.py:71-77,110-111 (MSE / L1 / SmoothL1 / Huber, mean reduction) and their backward.
 //
-// Every kernel is "one warp per (channel, sample) row": a row is Tp contiguous elements of which the
-// first T are valid; each lane owns 8-element (16/32-byte) segments, so global accesses are
-// coalesced 128-bit transactions; reductions use warp shuffles + one atomic per warp.
+// Structure shared by every kernel: a row is the Tp contiguous elements of one (channel, sample) pair, of
+// which the first T are valid.  Grids are persistent (a few CTAs per SM); each warp strides over rows, each
+// lane owns 8-element (16/32-byte) segments, so global accesses are coalesced 128-bit transactions;
+// reductions use warp shuffles + one atomic (or plain store) per row.  GroupNorm statistics reach these
+// kernels as fp32 (mean, rstd) pairs per (sample, group) - the fp64 finalisation runs once per layer in
+// gn_finalize_kernel, not once per row - and the activation is a template parameter, so the inner loops are
+// ~15-30 issue slots per element: below the HBM time per element (round 1: they were ALU-bound at 30-60 %
+// of the HBM roofline, gpurun_out/stream_bench32.txt).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sg {
@@ -16,26 +23,54 @@ namespace sg {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 
+static int rows_grid(long long rows) { return (int)cdiv(rows, kWarpsPerBlock); }
+static int persistent_grid(long long rows) {
+    long long blocks = cdiv(rows, kWarpsPerBlock);
+    long long cap = 148LL * 8;
+    return (int)(blocks < cap ? blocks : cap);
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // ---------------------------------------------------------------------------------------------
 // layout kernels
 // ---------------------------------------------------------------------------------------------
-template <typename OT>
+// 8 consecutive elements of an external-layout row ([B][N][T], row start 16-byte aligned when VEC)
+template <bool VEC>
+__device__ __forceinline__ F8 load8_ext(const float* row, int t0, int T) {
+    F8 r;
+    if (VEC && t0 + 8 <= T) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(row + t0));
+        float4 b = __ldg(reinterpret_cast<const float4*>(row + t0 + 4));
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+        r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = (t0 + i < T) ? __ldg(row + t0 + i) : 0.f;
+    }
+    return r;
+}
+template <bool VEC>
+__device__ __forceinline__ void store8_ext(float* row, int t0, int T, const F8& r) {
+    if (VEC && t0 + 8 <= T) {
+        *reinterpret_cast<float4*>(row + t0) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+        *reinterpret_cast<float4*>(row + t0 + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (t0 + i < T) row[t0 + i] = r.v[i];
+    }
+}
+
+template <typename OT, bool VEC>
 __global__ void __launch_bounds__(kThreads) pack_input_kernel(const float* __restrict__ x, OT* __restrict__ out,
                                                               int B, int N, int T, int Tp) {
-    long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);  // row = n * B + b
-    if (row >= (long long)N * B) return;
-    int lane = threadIdx.x & 31;
-    int n = (int)(row / B), b = (int)(row % B);
-    const float* src = x + ((long long)b * N + n) * T;
-    OT* dst = out + row * Tp;
-    for (int seg = lane; seg < Tp / 8; seg += 32) {
-        F8 r;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int t = seg * 8 + i;
-            r.v[i] = t < T ? __ldg(src + t) : 0.0f;
-        }
-        store8(dst + seg * 8, r);
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)N * B, wstride = (long long)gridDim.x * kWarpsPerBlock;
+    for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
+        int n = (int)(row / B), b = (int)(row % B);                                 // row = n * B + b
+        const float* src = x + ((long long)b * N + n) * T;
+        OT* dst = out + row * Tp;
+        for (int seg = lane; seg < Tp / 8; seg += 32) store8(dst + seg * 8, load8_ext<VEC>(src, seg * 8, T));
     }
 }
 
@@ -70,9 +105,9 @@ __global__ void scale_f64_to_f32_kernel(const double* in, float* out, double sca
 }
 
 // ---------------------------------------------------------------------------------------------
-// GroupNorm statistics: stats[b][g] += (sum, sumsq) over the group's rows
+// GroupNorm statistics: sums[b][g] += (sum, sumsq) over the group's rows; then (mean, rstd) in fp32
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restrict__ y, double* __restrict__ stats,
+__global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restrict__ y, double* __restrict__ sums,
                                                             int C, int B, int T, int Tp, int G, int rows_per_block) {
     // grid: (chunks per group, G, B)
     __shared__ double sh[2][32];
@@ -103,64 +138,121 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restr
     double t0 = block_sum(ds, sh[0]);
     double t1 = block_sum(dss, sh[1]);
     if (threadIdx.x == 0) {
-        atomicAdd(&stats[(size_t)(b * G + g) * 2], t0);
-        atomicAdd(&stats[(size_t)(b * G + g) * 2 + 1], t1);
+        atomicAdd(&sums[(size_t)(b * G + g) * 2], t0);
+        atomicAdd(&sums[(size_t)(b * G + g) * 2 + 1], t1);
+    }
+}
+
+// mr[b][g] = (mean, 1 / sqrt(biased var + eps)) - nn.GroupNorm semantics, finalised in fp64
+__global__ void gn_finalize_kernel(const double* __restrict__ sums, float* __restrict__ mr, int n, double inv_n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double m = sums[2 * i] * inv_n;
+    double var = sums[2 * i + 1] * inv_n - m * m;
+    if (var < 0.0) var = 0.0;
+    mr[2 * i] = (float)m;
+    mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)kGnEps));
+}
+
+// ---------------------------------------------------------------------------------------------
+// activation dispatch (compile time)
+// ---------------------------------------------------------------------------------------------
+template <int ACT>
+__device__ __forceinline__ float act_t(float x) {
+    if (ACT == SG_ACT_GELU) return gelu_f(x);
+    if (ACT == SG_ACT_TANH) return tanh_fast(x);
+    return x;
+}
+template <int ACT>
+__device__ __forceinline__ void act_both_t(float x, float& val, float& dval) {
+    if (ACT == SG_ACT_GELU) {
+        gelu_both(x, val, dval);
+    } else if (ACT == SG_ACT_TANH) {
+        val = tanh_fast(x);
+        dval = 1.0f - val * val;
+    } else {
+        val = x;
+        dval = 1.0f;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward apply
+// forward apply: pre = res + res_scale * act(a*y + sh); out = POST ? gelu(pre) : pre
 // ---------------------------------------------------------------------------------------------
-template <typename OT, typename RT>
+template <typename OT, typename RT, int ACT, bool POST>
 __global__ void __launch_bounds__(kThreads)
-gn_act_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, const RT* __restrict__ res, float res_scale, int act, int post_gelu,
-                  OT* __restrict__ out_op, int planes, long long pstride, float* __restrict__ out_f32, int C, int B,
-                  int T, int Tp, int G, double inv_n) {
+gn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, const RT* __restrict__ res, float res_scale, OT* __restrict__ out_op,
+                  int planes, long long pstride, float* __restrict__ out_f32, int C, int B, int T, int Tp, int G) {
     extern __shared__ float sg_rows[];
-    long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (row >= (long long)C * B) return;
-    int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     float* srow = sg_rows + (threadIdx.x >> 5) * (Tp + 8);
     const bool multi = planes > 1 && out_op != nullptr;
-    if (multi) srow_clear_halo(srow, Tp, lane);
-    int c = (int)(row / B), b = (int)(row % B);
-    float a = 1.f, sh = 0.f;
-    if (stats != nullptr) {
-        GnStat st = gn_stat(stats, b, c / (C / G), G, inv_n);
-        a = gamma[c] * st.rstd;
-        sh = beta[c] - st.mean * a;
-    }
-    const float* yrow = y + row * Tp;
-    for (int seg = lane; seg < Tp / 8; seg += 32) {
-        F8 yv = load8(yrow + seg * 8);
-        F8 rv;
-        if (res != nullptr) rv = load8(res + row * Tp + seg * 8);
-        F8 o;
+    const int nseg_p = Tp >> 3;
+    const bool shfl = multi && nseg_p <= 32;
+    if (multi && !shfl) srow_clear_halo(srow, Tp, lane);
+    const int Cg = mr != nullptr ? C / G : 1;
+    const long long rows = (long long)C * B, wstride = (long long)gridDim.x * kWarpsPerBlock;
+    for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
+        int c = (int)(row / B), b = (int)(row % B);
+        float a = 1.f, sh = 0.f;
+        if (mr != nullptr) {
+            float2 st = *reinterpret_cast<const float2*>(mr + 2 * (b * G + c / Cg));
+            a = gamma[c] * st.y;
+            sh = beta[c] - st.x * a;
+        }
+        const float* yrow = y + row * Tp;
+        auto compute = [&](int seg, F8& o) {
+            if (seg * 8 < T) {
+                F8 yv = load8(yrow + seg * 8);
+                F8 rv;
+                if (res != nullptr) rv = load8(res + row * Tp + seg * 8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float pre = res_scale * act_f(act, yv.v[i] * a + sh);
-            if (res != nullptr) pre += rv.v[i];
-            if (post_gelu) pre = gelu_f(pre);
-            o.v[i] = (seg * 8 + i < T) ? pre : 0.f;
+                for (int i = 0; i < 8; ++i) {
+                    float pre = res_scale * act_t<ACT>(fmaf(yv.v[i], a, sh));
+                    if (res != nullptr) pre += rv.v[i];
+                    if (POST) pre = gelu_f(pre);
+                    o.v[i] = pre;
+                }
+                if (seg * 8 + 8 > T) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (seg * 8 + i >= T) o.v[i] = 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+            }
+        };
+        if (shfl) {
+            // rows of <= 256 elements: one segment per lane, shifted planes built from registers + shuffles
+            F8 o;
+            compute(lane, o);
+            if (out_f32 != nullptr && lane < nseg_p) store8(out_f32 + row * Tp + lane * 8, o);
+            store_planes_shfl_n(out_op, row * Tp, planes, pstride, o, T, nseg_p, lane);
+            continue;
+        }
+        for (int seg = lane; seg < nseg_p; seg += 32) {
+            F8 o;
+            compute(seg, o);
+            if (multi) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) srow[4 + seg * 8 + i] = o.v[i];
+            } else if (out_op != nullptr) {
+                store8(out_op + row * Tp + seg * 8, o);
+            }
+            if (out_f32 != nullptr) store8(out_f32 + row * Tp + seg * 8, o);
         }
         if (multi) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) srow[4 + seg * 8 + i] = o.v[i];
-        } else if (out_op != nullptr) {
-            store8(out_op + row * Tp + seg * 8, o);
+            __syncwarp();
+            store_row_planes(out_op, row * Tp, planes, pstride, srow, T, Tp, lane);
+            __syncwarp();
         }
-        if (out_f32 != nullptr) store8(out_f32 + row * Tp + seg * 8, o);
-    }
-    if (multi) {
-        __syncwarp();
-        store_row_planes(out_op, row * Tp, planes, pstride, srow, T, Tp, lane);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward.  The incoming gradient is either a tensor (generic layers) or derived from the
-// reconstruction losses on the fly (recon head), so dx_hat is never materialised.
+// backward.  The incoming gradient is a tensor (generic layers); the recon head has its own kernels below.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float loss_term(int kind, float d) {
     float ad = fabsf(d);
@@ -177,204 +269,195 @@ __device__ __forceinline__ float loss_grad(int kind, float d) {
 
 struct BwdArgs {
     const float* y;
-    const double* stats;
+    const float* mr;          // (mean, rstd) per (b, g) or NULL
     const float* gamma;
     const float* beta;
     const void* res;
     float res_scale;
-    int act, post_gelu;
-    const float* dout;        // generic: [C][B][Tp]
-    // loss-derived dout (recon head): x, ext in external layout [B][C][T]
-    const float* x;
-    const float* ext;
-    float ga, gm;             // already multiplied by inv_numel
-    int loss_kind;
+    const float* dout;        // [C][B][Tp]
     int C, B, T, Tp, G;
     double inv_n;
 };
 
-// Computes, for one 8-element segment, dyh = dL/d(gamma*xhat+beta) and xhat; returns dpre for dres.
-template <typename RT, bool LOSS>
-__device__ __forceinline__ void bwd_segment(const BwdArgs& p, long long row, int c, int b, int seg, float a, float sh,
-                                            float mean, float rstd, F8& dyh, F8& xhat, F8& dpre) {
+// One fully/partially valid 8-element segment: dyh = dL/d(gamma*xhat+beta), xhat, dpre (gradient wrt the residual input)
+template <typename RT, int ACT, bool POST>
+__device__ __forceinline__ void bwd_segment(const BwdArgs& p, long long row, int seg, float a, float sh, float mean, float rstd,
+                                            F8& dyh, F8& xhat, F8& dpre) {
     F8 yv = load8(p.y + row * p.Tp + seg * 8);
-    F8 rv, dv;
+    F8 dv = load8(p.dout + row * p.Tp + seg * 8);
+    F8 rv;
     const RT* res = reinterpret_cast<const RT*>(p.res);
-    if (res != nullptr) rv = load8(res + row * p.Tp + seg * 8);
-    if (!LOSS) dv = load8(p.dout + row * p.Tp + seg * 8);
+    if (POST && res != nullptr) rv = load8(res + row * p.Tp + seg * 8);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        int t = seg * 8 + i;
-        bool valid = t < p.T;
         float yh = yv.v[i] * a + sh;
         float val, dval;
-        act_both(p.act, yh, val, dval);
-        float d;
-        if (LOSS) {
-            d = 0.f;
-            if (valid) {
-                long long xi = ((long long)b * p.C + c) * p.T + t;
-                if (p.x != nullptr) {
-                    float diff = val - __ldg(p.x + xi);
-                    d = p.ga * loss_grad(p.loss_kind, diff) + p.gm * 2.f * diff;
-                }
-                if (p.ext != nullptr) d += __ldg(p.ext + xi);
-            }
-        } else {
-            d = dv.v[i];
-        }
-        float dp = d;
-        if (p.post_gelu) {
+        act_both_t<ACT>(yh, val, dval);
+        float dp = dv.v[i];
+        if (POST) {
             float pre = p.res_scale * val + (res != nullptr ? rv.v[i] : 0.f);
-            dp = d * gelu_grad_f(pre);
+            dp *= gelu_grad_f(pre);
         }
-        float g = p.res_scale * dp * dval;
-        dyh.v[i] = valid ? g : 0.f;
-        xhat.v[i] = valid ? (yv.v[i] - mean) * rstd : 0.f;
-        dpre.v[i] = valid ? dp : 0.f;
+        dyh.v[i] = p.res_scale * dp * dval;
+        xhat.v[i] = (yv.v[i] - mean) * rstd;
+        dpre.v[i] = dp;
+    }
+    if (seg * 8 + 8 > p.T) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (seg * 8 + i >= p.T) { dyh.v[i] = 0.f; xhat.v[i] = 0.f; dpre.v[i] = 0.f; }
     }
 }
 
-template <typename RT, bool LOSS>
+// pass 1 (GroupNorm layers only): dgamma[c] += sum dyh*xhat, dbeta[c] += sum dyh, S[b][g] += gamma_c * (those)
+template <typename RT, int ACT, bool POST>
 __global__ void __launch_bounds__(kThreads)
 gn_bwd_reduce_kernel(BwdArgs p, float* __restrict__ dgamma, float* __restrict__ dbeta, double* __restrict__ S) {
-    long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (row >= (long long)p.C * p.B) return;
-    int lane = threadIdx.x & 31;
-    int c = (int)(row / p.B), b = (int)(row % p.B);
-    int g = c / (p.C / p.G);
-    GnStat st = gn_stat(p.stats, b, g, p.G, p.inv_n);
-    float gm = p.gamma[c];
-    float a = gm * st.rstd, sh = p.beta[c] - st.mean * a;
-    float A = 0.f, Bx = 0.f;
-    for (int seg = lane; seg < p.Tp / 8; seg += 32) {
-        F8 dyh, xhat, dpre;
-        bwd_segment<RT, LOSS>(p, row, c, b, seg, a, sh, st.mean, st.rstd, dyh, xhat, dpre);
+    const int lane = threadIdx.x & 31;
+    const int Cg = p.C / p.G;
+    const long long rows = (long long)p.C * p.B, wstride = (long long)gridDim.x * kWarpsPerBlock;
+    for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
+        int c = (int)(row / p.B), b = (int)(row % p.B);
+        int g = c / Cg;
+        float2 st = *reinterpret_cast<const float2*>(p.mr + 2 * (b * p.G + g));
+        float gm = p.gamma[c];
+        float a = gm * st.y, sh = p.beta[c] - st.x * a;
+        float A = 0.f, Bx = 0.f;
+        for (int seg = lane; seg * 8 < p.T; seg += 32) {
+            F8 dyh, xhat, dpre;
+            bwd_segment<RT, ACT, POST>(p, row, seg, a, sh, st.x, st.y, dyh, xhat, dpre);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            A += dyh.v[i];
-            Bx += dyh.v[i] * xhat.v[i];
+            for (int i = 0; i < 8; ++i) {
+                A += dyh.v[i];
+                Bx += dyh.v[i] * xhat.v[i];
+            }
         }
-    }
-    A = warp_sum(A);
-    Bx = warp_sum(Bx);
-    if (lane == 0) {
-        atomicAdd(&dgamma[c], Bx);
-        atomicAdd(&dbeta[c], A);
-        atomicAdd(&S[(size_t)(b * p.G + g) * 2], (double)(gm * A));
-        atomicAdd(&S[(size_t)(b * p.G + g) * 2 + 1], (double)(gm * Bx));
+        A = warp_sum(A);
+        Bx = warp_sum(Bx);
+        if (lane == 0) {
+            atomicAdd(&dgamma[c], Bx);
+            atomicAdd(&dbeta[c], A);
+            atomicAdd(&S[(size_t)(b * p.G + g) * 2], (double)(gm * A));
+            atomicAdd(&S[(size_t)(b * p.G + g) * 2 + 1], (double)(gm * Bx));
+        }
     }
 }
 
-template <typename OT, typename RT, bool LOSS>
+// pass 2: dy = rstd * (gamma * dyh - mean_g(gamma dyh) - xhat * mean_g(gamma dyh xhat)) (or dyh without GroupNorm)
+template <typename OT, typename RT, int ACT, bool POST>
 __global__ void __launch_bounds__(kThreads)
 gn_bwd_apply_kernel(BwdArgs p, const double* __restrict__ S, OT* __restrict__ dy, int planes, long long pstride,
                     float* __restrict__ dbias, float* __restrict__ dres, int dres_accumulate) {
     extern __shared__ float sg_rows[];
-    long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (row >= (long long)p.C * p.B) return;
-    int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     float* srow = sg_rows + (threadIdx.x >> 5) * (p.Tp + 8);
     const bool multi = planes > 1;
-    if (multi) srow_clear_halo(srow, p.Tp, lane);
-    int c = (int)(row / p.B), b = (int)(row % p.B);
-    float a = 1.f, sh = 0.f, mean = 0.f, rstd = 1.f, gm = 1.f, m1 = 0.f, m2 = 0.f;
-    bool has_gn = p.stats != nullptr;
-    if (has_gn) {
-        int g = c / (p.C / p.G);
-        GnStat st = gn_stat(p.stats, b, g, p.G, p.inv_n);
-        gm = p.gamma[c];
-        mean = st.mean;
-        rstd = st.rstd;
-        a = gm * rstd;
-        sh = p.beta[c] - mean * a;
-        m1 = (float)(S[(size_t)(b * p.G + g) * 2] * p.inv_n);
-        m2 = (float)(S[(size_t)(b * p.G + g) * 2 + 1] * p.inv_n);
-    }
-    float db = 0.f;
-    for (int seg = lane; seg < p.Tp / 8; seg += 32) {
-        F8 dyh, xhat, dpre, o;
-        bwd_segment<RT, LOSS>(p, row, c, b, seg, a, sh, mean, rstd, dyh, xhat, dpre);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float v = dyh.v[i];
-            if (has_gn) v = (seg * 8 + i < p.T) ? rstd * (gm * v - m1 - xhat.v[i] * m2) : 0.f;
-            o.v[i] = v;
-            db += v;
+    const int nseg_p = p.Tp >> 3;
+    const bool shfl = multi && nseg_p <= 32;
+    if (multi && !shfl) srow_clear_halo(srow, p.Tp, lane);
+    const bool has_gn = p.mr != nullptr;
+    const int Cg = has_gn ? p.C / p.G : 1;
+    const long long rows = (long long)p.C * p.B, wstride = (long long)gridDim.x * kWarpsPerBlock;
+    for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
+        int c = (int)(row / p.B), b = (int)(row % p.B);
+        float a = 1.f, sh = 0.f, mean = 0.f, rstd = 1.f, gm = 1.f, m1 = 0.f, m2 = 0.f;
+        if (has_gn) {
+            int g = c / Cg;
+            float2 st = *reinterpret_cast<const float2*>(p.mr + 2 * (b * p.G + g));
+            gm = p.gamma[c];
+            mean = st.x;
+            rstd = st.y;
+            a = gm * rstd;
+            sh = p.beta[c] - mean * a;
+            m1 = (float)(S[(size_t)(b * p.G + g) * 2] * p.inv_n);
+            m2 = (float)(S[(size_t)(b * p.G + g) * 2 + 1] * p.inv_n);
         }
-        if (multi) {
+        float db = 0.f;
+        auto compute = [&](int seg, F8& o, F8& dpre) {
+            if (seg * 8 < p.T) {
+                F8 dyh, xhat;
+                bwd_segment<RT, ACT, POST>(p, row, seg, a, sh, mean, rstd, dyh, xhat, dpre);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) srow[4 + seg * 8 + i] = o.v[i];
-        } else {
-            store8(dy + row * p.Tp + seg * 8, o);
-        }
-        if (dres != nullptr) {
-            float* dr = dres + row * p.Tp + seg * 8;
-            if (dres_accumulate) {
-                F8 old = load8(dr);
+                for (int i = 0; i < 8; ++i) {
+                    float v = dyh.v[i];
+                    if (has_gn) v = rstd * (gm * v - m1 - xhat.v[i] * m2);
+                    o.v[i] = v;
+                }
+                if (has_gn && seg * 8 + 8 > p.T) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dpre.v[i] += old.v[i];
+                    for (int i = 0; i < 8; ++i)
+                        if (seg * 8 + i >= p.T) o.v[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) db += o.v[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { o.v[i] = 0.f; dpre.v[i] = 0.f; }
             }
-            store8(dr, dpre);
+        };
+        auto store_dres = [&](int seg, F8& dpre) {
+            if (dres != nullptr) {
+                float* dr = dres + row * p.Tp + seg * 8;
+                if (dres_accumulate) {
+                    F8 old = load8(dr);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dpre.v[i] += old.v[i];
+                }
+                store8(dr, dpre);
+            }
+        };
+        if (shfl) {
+            F8 o, dpre;
+            compute(lane, o, dpre);
+            if (lane < nseg_p) store_dres(lane, dpre);
+            store_planes_shfl_n(dy, row * p.Tp, planes, pstride, o, p.T, nseg_p, lane);
+        } else {
+            for (int seg = lane; seg < nseg_p; seg += 32) {
+                F8 o, dpre;
+                compute(seg, o, dpre);
+                if (multi) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) srow[4 + seg * 8 + i] = o.v[i];
+                } else {
+                    store8(dy + row * p.Tp + seg * 8, o);
+                }
+                store_dres(seg, dpre);
+            }
         }
-    }
-    db = warp_sum(db);
-    if (lane == 0 && dbias != nullptr) atomicAdd(&dbias[c], db);
-    if (multi) {
-        __syncwarp();
-        store_row_planes(dy, row * p.Tp, planes, pstride, srow, p.T, p.Tp, lane);
+        db = warp_sum(db);
+        if (lane == 0 && dbias != nullptr) atomicAdd(&dbias[c], db);
+        if (multi && !shfl) {
+            __syncwarp();
+            store_row_planes(dy, row * p.Tp, planes, pstride, srow, p.T, p.Tp, lane);
+            __syncwarp();
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // recon head forward: x_hat = tanh(GN(y)) in the external layout + loss sums (+ the per-row partial
 // sums of the GroupNorm backward, so that the backward needs ONE pass over y / x instead of two)
-// ---------------------------------------------------------------------------------------------
-// 8 consecutive elements of an external-layout row ([B][N][T], row start 16-byte aligned when VEC)
-template <bool VEC>
-__device__ __forceinline__ F8 load8_ext(const float* row, int t0, int T) {
-    F8 r;
-    if (VEC && t0 + 8 <= T) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(row + t0));
-        float4 b = __ldg(reinterpret_cast<const float4*>(row + t0 + 4));
-        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
-        r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r.v[i] = (t0 + i < T) ? __ldg(row + t0 + i) : 0.f;
-    }
-    return r;
-}
-template <bool VEC>
-__device__ __forceinline__ void store8_ext(float* row, int t0, int T, const F8& r) {
-    if (VEC && t0 + 8 <= T) {
-        *reinterpret_cast<float4*>(row + t0) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-        *reinterpret_cast<float4*>(row + t0 + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (t0 + i < T) row[t0 + i] = r.v[i];
-    }
-}
-
-// persistent: grid = min(rows / 8, a few waves); every warp strides over (n, b) rows.
 // rowsums[row] = (sum gL, sum gL*xn, sum gM, sum gM*xn) with gL = loss'(d)(1 - xh^2), gM = 2 d (1 - xh^2),
 // xn = (y - mean) rstd: the backward scales them by the upstream loss gradients (they are linear in them).
+// ---------------------------------------------------------------------------------------------
 template <bool VEC, bool MSE>
 __global__ void __launch_bounds__(kThreads)
-recon_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
+recon_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ x, float* __restrict__ x_hat,
                  double* __restrict__ loss_sums, float4* __restrict__ rowsums, int N, int B, int T, int Tp, int G,
-                 int loss_kind, double inv_n) {
+                 int loss_kind) {
     __shared__ double shm[2][32];
     const int lane = threadIdx.x & 31;
+    const int Cg = N / G;
     const long long rows = (long long)N * B;
     const long long wstride = (long long)gridDim.x * kWarpsPerBlock;
     double d0 = 0.0, d1 = 0.0;
     for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
         int n = (int)(row / B), b = (int)(row % B);
-        GnStat st = gn_stat(stats, b, n / (N / G), G, inv_n);
-        float a = gamma[n] * st.rstd, sh = beta[n] - st.mean * a;
+        float2 st = *reinterpret_cast<const float2*>(mr + 2 * (b * G + n / Cg));
+        const float mean = st.x, rstd = st.y;
+        float a = gamma[n] * rstd, sh = beta[n] - mean * a;
+        const float nm = -mean * rstd;                        // xn = y * rstd + nm
         const float* yrow = y + row * Tp;
         long long xo = ((long long)b * N + n) * T;
         float l0 = 0.f, l1 = 0.f, aL = 0.f, bL = 0.f, aM = 0.f, bM = 0.f;
@@ -382,23 +465,26 @@ recon_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats, 
             F8 yv = load8(yrow + seg * 8);
             F8 xv, xh;
             if (x != nullptr) xv = load8_ext<VEC>(x + xo, seg * 8, T);
+            const bool full = seg * 8 + 8 <= T;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                bool valid = seg * 8 + i < T;
                 float h = tanh_fast(yv.v[i] * a + sh);
                 xh.v[i] = h;
-                if (x != nullptr && valid) {
+                if (x != nullptr) {
                     float d = h - xv.v[i];
-                    l1 += d * d;
+                    if (!full && seg * 8 + i >= T) d = 0.f;     // tail of a ragged row contributes nothing
+                    l1 = fmaf(d, d, l1);
                     if (!MSE) l0 += loss_term(loss_kind, d);
                     if (rowsums != nullptr) {
-                        float om = 1.f - h * h;
-                        float xn = (yv.v[i] - st.mean) * st.rstd;
-                        float gm = 2.f * d * om;
-                        aM += gm; bM += gm * xn;
+                        float om = fmaf(-h, h, 1.f);
+                        float xn = fmaf(yv.v[i], rstd, nm);
+                        float gm = d * om;                    // x2 folded in after the loop
+                        aM += gm;
+                        bM = fmaf(gm, xn, bM);
                         if (!MSE) {
                             float gl = loss_grad(loss_kind, d) * om;
-                            aL += gl; bL += gl * xn;
+                            aL += gl;
+                            bL = fmaf(gl, xn, bL);
                         }
                     }
                 }
@@ -406,7 +492,8 @@ recon_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats, 
             if (x_hat != nullptr) store8_ext<VEC>(x_hat + xo, seg * 8, T, xh);
         }
         if (rowsums != nullptr) {
-            aM = warp_sum(aM); bM = warp_sum(bM);
+            aM = 2.f * warp_sum(aM);
+            bM = 2.f * warp_sum(bM);
             if (MSE) { aL = aM; bL = bM; } else { aL = warp_sum(aL); bL = warp_sum(bL); }
             if (lane == 0) rowsums[row] = make_float4(aL, bL, aM, bM);
         }
@@ -420,6 +507,130 @@ recon_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats, 
             atomicAdd(&loss_sums[0], t0);
             atomicAdd(&loss_sums[1], t1);
         }
+    }
+}
+
+// Fast paths of the training step: x present, T % 8 == 0 (every 8-element segment is entirely valid or entirely
+// padding) and 16-byte aligned external rows.  No per-element predicates and 32-bit row arithmetic: the generic
+// kernel above spends ~190 of its ~370 instructions per row on index math and predication and is issue-bound
+// (ncu: issue slots 65 % busy at 58 % DRAM throughput).
+template <bool MSE, bool ROWSUMS, bool XHAT>
+__global__ void __launch_bounds__(kThreads)
+recon_fwd_fast_kernel(const float* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, const float* __restrict__ x, float* __restrict__ x_hat,
+                      double* __restrict__ loss_sums, float4* __restrict__ rowsums, int N, int B, int T, int Tp, int G,
+                      int loss_kind) {
+    __shared__ double shm[2][32];
+    const int lane = threadIdx.x & 31;
+    const int Cg = N / G;
+    const int rows = N * B, wstride = gridDim.x * kWarpsPerBlock;
+    const int nseg = T >> 3;
+    double d0 = 0.0, d1 = 0.0;
+    for (int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
+        const int n = row / B, b = row - n * B;
+        const float2 st = __ldg(reinterpret_cast<const float2*>(mr) + (b * G + n / Cg));
+        const float rstd = st.y;
+        const float a = __ldg(gamma + n) * rstd, sh = __ldg(beta + n) - st.x * a;
+        const float nm = -st.x * rstd;
+        const float* yrow = y + (size_t)row * Tp;
+        const size_t xo = ((size_t)b * N + n) * T;
+        float l0 = 0.f, l1 = 0.f, aL = 0.f, bL = 0.f, aM = 0.f, bM = 0.f;
+        for (int seg = lane; seg < nseg; seg += 32) {
+            const F8 yv = load8(yrow + seg * 8);
+            const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + xo + seg * 8));
+            const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + xo + seg * 8 + 4));
+            const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            float h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                h[i] = tanh_fast(fmaf(yv.v[i], a, sh));
+                const float d = h[i] - xv[i];
+                l1 = fmaf(d, d, l1);
+                if (!MSE) l0 += loss_term(loss_kind, d);
+                if (ROWSUMS) {
+                    const float om = fmaf(-h[i], h[i], 1.f);
+                    const float xn = fmaf(yv.v[i], rstd, nm);
+                    const float gm = d * om;
+                    aM += gm;
+                    bM = fmaf(gm, xn, bM);
+                    if (!MSE) {
+                        const float gl = loss_grad(loss_kind, d) * om;
+                        aL += gl;
+                        bL = fmaf(gl, xn, bL);
+                    }
+                }
+            }
+            if (XHAT) {
+                *reinterpret_cast<float4*>(x_hat + xo + seg * 8) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(x_hat + xo + seg * 8 + 4) = make_float4(h[4], h[5], h[6], h[7]);
+            }
+        }
+        if (ROWSUMS) {
+            aM = 2.f * warp_sum(aM);
+            bM = 2.f * warp_sum(bM);
+            if (MSE) { aL = aM; bL = bM; } else { aL = warp_sum(aL); bL = warp_sum(bL); }
+            if (lane == 0) rowsums[row] = make_float4(aL, bL, aM, bM);
+        }
+        d0 += (double)(MSE ? l1 : l0);
+        d1 += (double)l1;
+    }
+    double t0 = block_sum(d0, shm[0]);
+    double t1 = block_sum(d1, shm[1]);
+    if (threadIdx.x == 0) {
+        atomicAdd(&loss_sums[0], t0);
+        atomicAdd(&loss_sums[1], t1);
+    }
+}
+
+template <typename OT, bool MSE>
+__global__ void __launch_bounds__(kThreads)
+recon_bwd_apply_fast_kernel(const float* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, const float* __restrict__ x, const float* __restrict__ scal,
+                            const double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias, int N, int B,
+                            int T, int Tp, int G, int loss_kind, float inv_n) {
+    const int lane = threadIdx.x & 31;
+    const int Cg = N / G;
+    const int rows = N * B, wstride = gridDim.x * kWarpsPerBlock;
+    const int nseg = T >> 3, nseg_p = Tp >> 3;
+    const float ga = scal[0], gm = scal[1];
+    const float g2 = 2.f * (ga + gm);
+    for (int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
+        const int n = row / B, b = row - n * B;
+        const int g = n / Cg;
+        const float2 st = __ldg(reinterpret_cast<const float2*>(mr) + (b * G + g));
+        const float mean = st.x, rstd = st.y;
+        const float gam = __ldg(gamma + n);
+        const float a = gam * rstd, sh = __ldg(beta + n) - mean * a;
+        const float m1 = (float)S[(size_t)(b * G + g) * 2] * inv_n;
+        const float m2 = (float)S[(size_t)(b * G + g) * 2 + 1] * inv_n;
+        const float c1 = rstd * gam, c2 = -rstd * rstd * m2, c3 = rstd * (mean * rstd * m2 - m1);
+        const float* yrow = y + (size_t)row * Tp;
+        OT* drow = dy + (size_t)row * Tp;
+        const size_t xo = ((size_t)b * N + n) * T;
+        float db = 0.f;
+        for (int seg = lane; seg < nseg_p; seg += 32) {
+            F8 o;
+            if (seg < nseg) {
+                const F8 yv = load8(yrow + seg * 8);
+                const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + xo + seg * 8));
+                const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + xo + seg * 8 + 4));
+                const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float h = tanh_fast(fmaf(yv.v[i], a, sh));
+                    const float d = h - xv[i];
+                    const float gg = (MSE ? g2 * d : ga * loss_grad(loss_kind, d) + gm * 2.f * d) * fmaf(-h, h, 1.f);
+                    o.v[i] = fmaf(c1, gg, fmaf(c2, yv.v[i], c3));
+                    db += o.v[i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+            }
+            store8(drow + seg * 8, o);
+        }
+        db = warp_sum(db);
+        if (lane == 0) atomicAdd(&dbias[n], db);
     }
 }
 
@@ -462,23 +673,27 @@ recon_bwd_combine_kernel(const float4* __restrict__ rowsums, const float* __rest
 // backward, step 2: dy = rstd * (gamma * g - m1 - xn * m2), g = (ga loss'(d) + gm 2d)(1 - xh^2)
 template <typename OT, bool VEC, bool MSE>
 __global__ void __launch_bounds__(kThreads)
-recon_bwd_apply_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
+recon_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                        const float* __restrict__ beta, const float* __restrict__ x, const float* __restrict__ scal,
                        const double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias, int N, int B, int T,
                        int Tp, int G, int loss_kind, double inv_n) {
     const int lane = threadIdx.x & 31;
+    const int Cg = N / G;
     const long long rows = (long long)N * B;
     const long long wstride = (long long)gridDim.x * kWarpsPerBlock;
     const float ga = scal[0], gm = scal[1];
     const float g2 = 2.f * (ga + gm);      // MSE: ga * 2d + gm * 2d
     for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
         int n = (int)(row / B), b = (int)(row % B);
-        int g = n / (N / G);
-        GnStat st = gn_stat(stats, b, g, G, inv_n);
+        int g = n / Cg;
+        float2 st = *reinterpret_cast<const float2*>(mr + 2 * (b * G + g));
+        const float mean = st.x, rstd = st.y;
         float gam = gamma[n];
-        float a = gam * st.rstd, sh = beta[n] - st.mean * a;
-        float m1 = (float)(S[(size_t)(b * G + g) * 2] * inv_n);
-        float m2 = (float)(S[(size_t)(b * G + g) * 2 + 1] * inv_n);
+        float a = gam * rstd, sh = beta[n] - mean * a;
+        // dy = rstd*gam*gg - rstd*m1 - xn*rstd*m2 with xn = y*rstd - mean*rstd  ->  c1*gg + c2*y + c3
+        const float m1 = (float)(S[(size_t)(b * G + g) * 2] * inv_n);
+        const float m2 = (float)(S[(size_t)(b * G + g) * 2 + 1] * inv_n);
+        const float c1 = rstd * gam, c2 = -rstd * rstd * m2, c3 = rstd * (mean * rstd * m2 - m1);
         const float* yrow = y + row * Tp;
         long long xo = ((long long)b * N + n) * T;
         float db = 0.f;
@@ -491,12 +706,16 @@ recon_bwd_apply_kernel(const float* __restrict__ y, const double* __restrict__ s
                 for (int i = 0; i < 8; ++i) {
                     float h = tanh_fast(yv.v[i] * a + sh);
                     float d = h - xv.v[i];
-                    float gg = (MSE ? g2 * d : ga * loss_grad(loss_kind, d) + gm * 2.f * d) * (1.f - h * h);
-                    float xn = (yv.v[i] - st.mean) * st.rstd;
-                    float v = (seg * 8 + i < T) ? st.rstd * (gam * gg - m1 - xn * m2) : 0.f;
-                    o.v[i] = v;
-                    db += v;
+                    float gg = (MSE ? g2 * d : ga * loss_grad(loss_kind, d) + gm * 2.f * d) * fmaf(-h, h, 1.f);
+                    o.v[i] = fmaf(c1, gg, fmaf(c2, yv.v[i], c3));
                 }
+                if (seg * 8 + 8 > T) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (seg * 8 + i >= T) o.v[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) db += o.v[i];
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
@@ -508,35 +727,141 @@ recon_bwd_apply_kernel(const float* __restrict__ y, const double* __restrict__ s
     }
 }
 
-static int rows_grid(long long rows) { return (int)cdiv(rows, kWarpsPerBlock); }
+// two-pass recon backward (used when a gradient wrt x_hat itself arrives, or without the forward's row sums)
+struct ReconBwdArgs {
+    const float* y;
+    const float* mr;
+    const float* gamma;
+    const float* beta;
+    const float* x;
+    const float* ext;
+    int loss_kind, N, B, T, Tp, G;
+    double inv_n;
+};
 
-template <typename OT>
-static int launch_gn_bwd(BwdArgs p, bool loss, int res_is_f32, OT* dy, int planes, long long pstride, float* dgamma,
-                         float* dbeta, float* dbias, float* dres, int dres_accumulate, double* ws, cudaStream_t st) {
+template <typename OT, bool REDUCE>
+__global__ void __launch_bounds__(kThreads)
+recon_bwd_kernel(ReconBwdArgs p, const float* __restrict__ scal, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                 double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias) {
+    const float ga = scal[0], gmse = scal[1];
+    const int lane = threadIdx.x & 31;
+    const int Cg = p.N / p.G;
+    const long long rows = (long long)p.N * p.B, wstride = (long long)gridDim.x * kWarpsPerBlock;
+    for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
+        int c = (int)(row / p.B), b = (int)(row % p.B);
+        int g = c / Cg;
+        float2 st = *reinterpret_cast<const float2*>(p.mr + 2 * (b * p.G + g));
+        const float mean = st.x, rstd = st.y;
+        float gm = p.gamma[c];
+        float a = gm * rstd, sh = p.beta[c] - mean * a;
+        float m1 = 0.f, m2 = 0.f;
+        if (!REDUCE) {
+            m1 = (float)(S[(size_t)(b * p.G + g) * 2] * p.inv_n);
+            m2 = (float)(S[(size_t)(b * p.G + g) * 2 + 1] * p.inv_n);
+        }
+        float A = 0.f, Bx = 0.f, db = 0.f;
+        for (int seg = lane; seg < p.Tp / 8; seg += 32) {
+            F8 o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+            if (seg * 8 < p.T) {
+                F8 yv = load8(p.y + row * p.Tp + seg * 8);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    int t = seg * 8 + i;
+                    if (t < p.T) {
+                        float h = tanh_fast(yv.v[i] * a + sh);
+                        long long xi = ((long long)b * p.N + c) * p.T + t;
+                        float d = 0.f;
+                        if (p.x != nullptr) {
+                            float diff = h - __ldg(p.x + xi);
+                            d = ga * loss_grad(p.loss_kind, diff) + gmse * 2.f * diff;
+                        }
+                        if (p.ext != nullptr) d += __ldg(p.ext + xi);
+                        float gg = d * (1.f - h * h);
+                        float xn = (yv.v[i] - mean) * rstd;
+                        if (REDUCE) {
+                            A += gg;
+                            Bx += gg * xn;
+                        } else {
+                            float v = rstd * (gm * gg - m1 - xn * m2);
+                            o.v[i] = v;
+                            db += v;
+                        }
+                    }
+                }
+            }
+            if (!REDUCE) store8(dy + row * p.Tp + seg * 8, o);
+        }
+        if (REDUCE) {
+            A = warp_sum(A);
+            Bx = warp_sum(Bx);
+            if (lane == 0) {
+                atomicAdd(&dgamma[c], Bx);
+                atomicAdd(&dbeta[c], A);
+                atomicAdd(&S[(size_t)(b * p.G + g) * 2], (double)(gm * A));
+                atomicAdd(&S[(size_t)(b * p.G + g) * 2 + 1], (double)(gm * Bx));
+            }
+        } else {
+            db = warp_sum(db);
+            if (lane == 0) atomicAdd(&dbias[c], db);
+        }
+    }
+}
+
+// g_loss / g_mse are device scalars produced by autograd (may be NULL); fold them with inv_numel on device.
+__global__ void recon_scalars_kernel(const float* g_loss, const float* g_mse, float inv_numel, float* out2) {
+    out2[0] = g_loss ? g_loss[0] * inv_numel : 0.f;
+    out2[1] = g_mse ? g_mse[0] * inv_numel : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side dispatch over the template parameters
+// ---------------------------------------------------------------------------------------------
+template <typename OT, typename RT, int ACT, bool POST>
+static void launch_fwd_t(const float* y, const float* mr, const float* gamma, const float* beta, const void* res,
+                         float res_scale, void* out_op, int planes, long long pstride, float* out_f32, int C, int B, int T,
+                         int Tp, int G, cudaStream_t st) {
+    size_t sm = (planes > 1 && out_op) ? sizeof(float) * kWarpsPerBlock * (Tp + 8) : 0;
+    gn_act_fwd_kernel<OT, RT, ACT, POST><<<persistent_grid((long long)C * B), kThreads, sm, st>>>(
+        y, mr, gamma, beta, (const RT*)res, res_scale, (OT*)out_op, planes, pstride, out_f32, C, B, T, Tp, G);
+}
+
+template <typename OT, typename RT>
+static int launch_fwd(int act, int post, const float* y, const float* mr, const float* gamma, const float* beta,
+                      const void* res, float res_scale, void* out_op, int planes, long long pstride, float* out_f32, int C,
+                      int B, int T, int Tp, int G, cudaStream_t st) {
+#define SG_F(ACT, POST) launch_fwd_t<OT, RT, ACT, POST>(y, mr, gamma, beta, res, res_scale, out_op, planes, pstride, out_f32, C, B, T, Tp, G, st)
+    if (act == SG_ACT_GELU) { if (post) SG_F(SG_ACT_GELU, true); else SG_F(SG_ACT_GELU, false); }
+    else if (act == SG_ACT_TANH) { if (post) SG_F(SG_ACT_TANH, true); else SG_F(SG_ACT_TANH, false); }
+    else { if (post) SG_F(SG_ACT_NONE, true); else SG_F(SG_ACT_NONE, false); }
+#undef SG_F
+    return check_launch("gn_act_fwd");
+}
+
+template <typename OT, typename RT, int ACT, bool POST>
+static void launch_bwd_t(const BwdArgs& p, OT* dy, int planes, long long pstride, float* dgamma, float* dbeta, float* dbias,
+                         float* dres, int dres_accumulate, double* ws, cudaStream_t st) {
     size_t sm = planes > 1 ? sizeof(float) * kWarpsPerBlock * (p.Tp + 8) : 0;
-    long long rows = (long long)p.C * p.B;
-    bool has_gn = p.stats != nullptr;
+    int grid = persistent_grid((long long)p.C * p.B);
+    if (p.mr != nullptr) gn_bwd_reduce_kernel<RT, ACT, POST><<<grid, kThreads, 0, st>>>(p, dgamma, dbeta, ws);
+    gn_bwd_apply_kernel<OT, RT, ACT, POST><<<grid, kThreads, sm, st>>>(p, ws, dy, planes, pstride, dbias, dres, dres_accumulate);
+}
+
+template <typename OT, typename RT>
+static int launch_bwd(int act, int post, const BwdArgs& p, OT* dy, int planes, long long pstride, float* dgamma, float* dbeta,
+                      float* dbias, float* dres, int dres_accumulate, double* ws, cudaStream_t st) {
     if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * p.C, st);
-    if (has_gn) {
+    if (p.mr != nullptr) {
         cudaMemsetAsync(dgamma, 0, sizeof(float) * p.C, st);
         cudaMemsetAsync(dbeta, 0, sizeof(float) * p.C, st);
         cudaMemsetAsync(ws, 0, sizeof(double) * 2 * p.B * p.G, st);
     }
-    int grid = rows_grid(rows);
-#define SG_LAUNCH_BWD(RT, LOSS)                                                                                  \
-    do {                                                                                                         \
-        if (has_gn) gn_bwd_reduce_kernel<RT, LOSS><<<grid, kThreads, 0, st>>>(p, dgamma, dbeta, ws);             \
-        gn_bwd_apply_kernel<OT, RT, LOSS><<<grid, kThreads, sm, st>>>(p, ws, dy, planes, pstride, dbias, dres,   \
-                                                                      dres_accumulate);                          \
-    } while (0)
-    if (loss) {
-        SG_LAUNCH_BWD(float, true);
-    } else if (p.res == nullptr || res_is_f32) {
-        SG_LAUNCH_BWD(float, false);
-    } else {
-        SG_LAUNCH_BWD(OT, false);
-    }
-#undef SG_LAUNCH_BWD
+#define SG_B(ACT, POST) launch_bwd_t<OT, RT, ACT, POST>(p, dy, planes, pstride, dgamma, dbeta, dbias, dres, dres_accumulate, ws, st)
+    if (act == SG_ACT_GELU) { if (post) SG_B(SG_ACT_GELU, true); else SG_B(SG_ACT_GELU, false); }
+    else if (act == SG_ACT_TANH) { if (post) SG_B(SG_ACT_TANH, true); else SG_B(SG_ACT_TANH, false); }
+    else { if (post) SG_B(SG_ACT_NONE, true); else SG_B(SG_ACT_NONE, false); }
+#undef SG_B
     return check_launch("gn_act_bwd");
 }
 
@@ -549,10 +874,13 @@ extern "C" {
 int sg_pack_input(const float* x, void* out, int B, int N, int T, int Tp, int dtype, void* stream) {
     SG_REQUIRE(Tp % 8 == 0 && Tp >= T, "pack_input: bad Tp=%d for T=%d", Tp, T);
     long long rows = (long long)N * B;
-    if (dtype == SG_BF16)
-        pack_input_kernel<__nv_bfloat16><<<rows_grid(rows), kThreads, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)out, B, N, T, Tp);
-    else
-        pack_input_kernel<float><<<rows_grid(rows), kThreads, 0, as_stream(stream)>>>(x, (float*)out, B, N, T, Tp);
+    int grid = persistent_grid(rows) * 2;
+    bool vec = (T % 4 == 0) && aligned16(x);
+    cudaStream_t st = as_stream(stream);
+#define SG_PACK(OT, VEC) pack_input_kernel<OT, VEC><<<grid, kThreads, 0, st>>>(x, (OT*)out, B, N, T, Tp)
+    if (dtype == SG_BF16) { if (vec) SG_PACK(__nv_bfloat16, true); else SG_PACK(__nv_bfloat16, false); }
+    else                  { if (vec) SG_PACK(float, true); else SG_PACK(float, false); }
+#undef SG_PACK
     return check_launch("pack_input");
 }
 
@@ -583,160 +911,96 @@ int sg_scale_f64_to_f32(const double* in, float* out, double scale, int n, void*
     return check_launch("scale_f64_to_f32");
 }
 
-int sg_gn_stats(const float* y, double* stats, int C, int B, int T, int Tp, int G, void* stream) {
+int sg_gn_stats(const float* y, double* ws, float* mr, int C, int B, int T, int Tp, int G, void* stream) {
     SG_REQUIRE(G > 0 && C % G == 0, "gn_stats: C=%d not divisible by G=%d", C, G);
     cudaStream_t st = as_stream(stream);
-    cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * G, st);
+    cudaMemsetAsync(ws, 0, sizeof(double) * 2 * B * G, st);
     int Cg = C / G;
     int rpb = Cg < 64 ? Cg : 64;
     dim3 grid((unsigned)cdiv(Cg, rpb), G, B);
-    gn_stats_kernel<<<grid, kThreads, 0, st>>>(y, stats, C, B, T, Tp, G, rpb);
+    gn_stats_kernel<<<grid, kThreads, 0, st>>>(y, ws, C, B, T, Tp, G, rpb);
+    gn_finalize_kernel<<<(B * G + 127) / 128, 128, 0, st>>>(ws, mr, B * G, 1.0 / ((double)Cg * T));
     return check_launch("gn_stats");
 }
 
-int sg_gn_act_fwd(const float* y, const double* stats, const float* gamma, const float* beta, const void* res,
+int sg_gn_act_fwd(const float* y, const float* mr, const float* gamma, const float* beta, const void* res,
                   int res_is_f32, float res_scale, int act, int post_gelu, void* out_op, int planes,
                   long long plane_stride, float* out_f32, int C, int B, int T, int Tp, int G, int dtype, void* stream) {
     SG_REQUIRE(Tp % 8 == 0, "gn_act_fwd: Tp %% 8 != 0");
     SG_REQUIRE(planes == 1 || planes == 3 || planes == 5, "gn_act_fwd: planes must be 1, 3 or 5");
-    size_t sm = (planes > 1 && out_op) ? sizeof(float) * kWarpsPerBlock * (Tp + 8) : 0;
-    SG_REQUIRE(stats == nullptr || (G > 0 && C % G == 0), "gn_act_fwd: bad groups");
+    SG_REQUIRE(mr == nullptr || (G > 0 && C % G == 0), "gn_act_fwd: bad groups");
     cudaStream_t st = as_stream(stream);
-    long long rows = (long long)C * B;
-    double inv_n = stats ? 1.0 / ((double)(C / G) * T) : 0.0;
-    int grid = rows_grid(rows);
     if (G <= 0) G = 1;
-#define SG_FWD(OT, RT)                                                                                            \
-    gn_act_fwd_kernel<OT, RT><<<grid, kThreads, sm, st>>>(y, stats, gamma, beta, (const RT*)res, res_scale, act,  \
-                                                          post_gelu, (OT*)out_op, planes, plane_stride, out_f32,  \
-                                                          C, B, T, Tp, G, inv_n)
     if (dtype == SG_BF16) {
-        if (res == nullptr || res_is_f32) SG_FWD(__nv_bfloat16, float);
-        else SG_FWD(__nv_bfloat16, __nv_bfloat16);
-    } else {
-        SG_FWD(float, float);
+        if (res == nullptr || res_is_f32)
+            return launch_fwd<__nv_bfloat16, float>(act, post_gelu, y, mr, gamma, beta, res, res_scale, out_op, planes,
+                                                    plane_stride, out_f32, C, B, T, Tp, G, st);
+        return launch_fwd<__nv_bfloat16, __nv_bfloat16>(act, post_gelu, y, mr, gamma, beta, res, res_scale, out_op, planes,
+                                                        plane_stride, out_f32, C, B, T, Tp, G, st);
     }
-#undef SG_FWD
-    return check_launch("gn_act_fwd");
+    return launch_fwd<float, float>(act, post_gelu, y, mr, gamma, beta, res, res_scale, out_op, planes, plane_stride, out_f32,
+                                    C, B, T, Tp, G, st);
 }
 
-int sg_gn_act_bwd(const float* y, const double* stats, const float* gamma, const float* beta, const void* res,
+int sg_gn_act_bwd(const float* y, const float* mr, const float* gamma, const float* beta, const void* res,
                   int res_is_f32, float res_scale, int act, int post_gelu, const float* dout, void* dy, int planes,
                   long long plane_stride, float* dgamma, float* dbeta, float* dbias, float* dres, int dres_accumulate,
                   double* ws, int C, int B, int T, int Tp, int G, int dtype, void* stream) {
     SG_REQUIRE(Tp % 8 == 0, "gn_act_bwd: Tp %% 8 != 0");
     SG_REQUIRE(planes == 1 || planes == 3 || planes == 5, "gn_act_bwd: planes must be 1, 3 or 5");
-    SG_REQUIRE(stats == nullptr || (G > 0 && C % G == 0 && dgamma && dbeta && ws), "gn_act_bwd: bad GN arguments");
+    SG_REQUIRE(mr == nullptr || (G > 0 && C % G == 0 && dgamma && dbeta && ws), "gn_act_bwd: bad GN arguments");
     if (G <= 0) G = 1;
     BwdArgs p{};
-    p.y = y; p.stats = stats; p.gamma = gamma; p.beta = beta; p.res = res; p.res_scale = res_scale;
-    p.act = act; p.post_gelu = post_gelu; p.dout = dout; p.x = nullptr; p.ext = nullptr; p.ga = 0; p.gm = 0;
-    p.loss_kind = 0; p.C = C; p.B = B; p.T = T; p.Tp = Tp; p.G = G;
-    p.inv_n = stats ? 1.0 / ((double)(C / G) * T) : 0.0;
-    if (dtype == SG_BF16)
-        return launch_gn_bwd<__nv_bfloat16>(p, false, res_is_f32, (__nv_bfloat16*)dy, planes, plane_stride, dgamma, dbeta,
-                                            dbias, dres, dres_accumulate, ws, as_stream(stream));
-    return launch_gn_bwd<float>(p, false, 1, (float*)dy, planes, plane_stride, dgamma, dbeta, dbias, dres,
-                                dres_accumulate, ws, as_stream(stream));
+    p.y = y; p.mr = mr; p.gamma = gamma; p.beta = beta; p.res = res; p.res_scale = res_scale; p.dout = dout;
+    p.C = C; p.B = B; p.T = T; p.Tp = Tp; p.G = G;
+    p.inv_n = mr ? 1.0 / ((double)(C / G) * T) : 0.0;
+    cudaStream_t st = as_stream(stream);
+    if (dtype == SG_BF16) {
+        if (res == nullptr || res_is_f32)
+            return launch_bwd<__nv_bfloat16, float>(act, post_gelu, p, (__nv_bfloat16*)dy, planes, plane_stride, dgamma, dbeta,
+                                                    dbias, dres, dres_accumulate, ws, st);
+        return launch_bwd<__nv_bfloat16, __nv_bfloat16>(act, post_gelu, p, (__nv_bfloat16*)dy, planes, plane_stride, dgamma,
+                                                        dbeta, dbias, dres, dres_accumulate, ws, st);
+    }
+    return launch_bwd<float, float>(act, post_gelu, p, (float*)dy, planes, plane_stride, dgamma, dbeta, dbias, dres,
+                                    dres_accumulate, ws, st);
 }
 
-static int persistent_grid(long long rows) {
-    long long blocks = cdiv(rows, kWarpsPerBlock);
-    long long cap = 148LL * 16;
-    return (int)(blocks < cap ? blocks : cap);
-}
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
-int sg_recon_fwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* x,
+int sg_recon_fwd(const float* y, const float* mr, const float* gamma, const float* beta, const float* x,
                  float* x_hat, double* loss_sums, float* rowsums, int N, int B, int T, int Tp, int G, int loss_kind,
                  void* stream) {
     SG_REQUIRE(G > 0 && N % G == 0, "recon_fwd: N=%d not divisible by G=%d", N, G);
     SG_REQUIRE(rowsums == nullptr || (x != nullptr && aligned16(rowsums)), "recon_fwd: rowsums needs x and 16-byte alignment");
     cudaStream_t st = as_stream(stream);
     if (x != nullptr) cudaMemsetAsync(loss_sums, 0, sizeof(double) * 2, st);
-    double inv_n = 1.0 / ((double)(N / G) * T);
     bool vec = (T % 4 == 0) && aligned16(x) && aligned16(x_hat);
-    int grid = persistent_grid((long long)N * B);
+    int grid = persistent_grid((long long)N * B) * 2;
     const bool mse = loss_kind == SG_LOSS_MSE;
 #define SG_RFWD(VEC, MSE)                                                                                              \
-    recon_fwd_kernel<VEC, MSE><<<grid, kThreads, 0, st>>>(y, stats, gamma, beta, x, x_hat, loss_sums, (float4*)rowsums, N, \
-                                                          B, T, Tp, G, loss_kind, inv_n)
+    recon_fwd_kernel<VEC, MSE><<<grid, kThreads, 0, st>>>(y, mr, gamma, beta, x, x_hat, loss_sums, (float4*)rowsums, N, B, \
+                                                          T, Tp, G, loss_kind)
+    if (vec && x != nullptr && (T & 7) == 0 && (long long)N * B < (1LL << 31)) {
+#define SG_FAST(MSE, RS, XH) \
+    recon_fwd_fast_kernel<MSE, RS, XH><<<grid, kThreads, 0, st>>>(y, mr, gamma, beta, x, x_hat, loss_sums, (float4*)rowsums, N, \
+                                                                  B, T, Tp, G, loss_kind)
+#define SG_FAST2(MSE) do { \
+        if (rowsums) { if (x_hat) SG_FAST(MSE, true, true); else SG_FAST(MSE, true, false); } \
+        else         { if (x_hat) SG_FAST(MSE, false, true); else SG_FAST(MSE, false, false); } } while (0)
+        if (mse) SG_FAST2(true); else SG_FAST2(false);
+#undef SG_FAST2
+#undef SG_FAST
+        return check_launch("recon_fwd");
+    }
     if (vec) { if (mse) SG_RFWD(true, true); else SG_RFWD(true, false); }
     else     { if (mse) SG_RFWD(false, true); else SG_RFWD(false, false); }
 #undef SG_RFWD
     return check_launch("recon_fwd");
 }
 
-// g_loss / g_mse are device scalars produced by autograd (may be NULL); fold them with inv_numel on device.
-__global__ void recon_scalars_kernel(const float* g_loss, const float* g_mse, float inv_numel, float* out2) {
-    out2[0] = g_loss ? g_loss[0] * inv_numel : 0.f;
-    out2[1] = g_mse ? g_mse[0] * inv_numel : 0.f;
-}
-
-}  // extern "C"
-
-namespace sg {
-// The loss-derived backward needs ga/gm as kernel *values*; they live on the device (autograd
-// scalars), so the two recon backward kernels read them through this small indirection.
-template <typename OT, bool REDUCE>
-__global__ void __launch_bounds__(kThreads)
-recon_bwd_kernel(BwdArgs p, const float* __restrict__ scal, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                 double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias) {
-    p.ga = scal[0];
-    p.gm = scal[1];
-    long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (row >= (long long)p.C * p.B) return;
-    int lane = threadIdx.x & 31;
-    int c = (int)(row / p.B), b = (int)(row % p.B);
-    int g = c / (p.C / p.G);
-    GnStat st = gn_stat(p.stats, b, g, p.G, p.inv_n);
-    float gm = p.gamma[c];
-    float a = gm * st.rstd, sh = p.beta[c] - st.mean * a;
-    if (REDUCE) {
-        float A = 0.f, Bx = 0.f;
-        for (int seg = lane; seg < p.Tp / 8; seg += 32) {
-            F8 dyh, xhat, dpre;
-            bwd_segment<float, true>(p, row, c, b, seg, a, sh, st.mean, st.rstd, dyh, xhat, dpre);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                A += dyh.v[i];
-                Bx += dyh.v[i] * xhat.v[i];
-            }
-        }
-        A = warp_sum(A);
-        Bx = warp_sum(Bx);
-        if (lane == 0) {
-            atomicAdd(&dgamma[c], Bx);
-            atomicAdd(&dbeta[c], A);
-            atomicAdd(&S[(size_t)(b * p.G + g) * 2], (double)(gm * A));
-            atomicAdd(&S[(size_t)(b * p.G + g) * 2 + 1], (double)(gm * Bx));
-        }
-    } else {
-        float m1 = (float)(S[(size_t)(b * p.G + g) * 2] * p.inv_n);
-        float m2 = (float)(S[(size_t)(b * p.G + g) * 2 + 1] * p.inv_n);
-        float db = 0.f;
-        for (int seg = lane; seg < p.Tp / 8; seg += 32) {
-            F8 dyh, xhat, dpre, o;
-            bwd_segment<float, true>(p, row, c, b, seg, a, sh, st.mean, st.rstd, dyh, xhat, dpre);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float v = (seg * 8 + i < p.T) ? st.rstd * (gm * dyh.v[i] - m1 - xhat.v[i] * m2) : 0.f;
-                o.v[i] = v;
-                db += v;
-            }
-            store8(dy + row * p.Tp + seg * 8, o);
-        }
-        db = warp_sum(db);
-        if (lane == 0) atomicAdd(&dbias[c], db);
-    }
-}
-}  // namespace sg
-
-extern "C" int sg_recon_bwd(const float* y, const double* stats, const float* gamma, const float* beta,
-                            const float* x, const float* g_loss, const float* g_mse, float inv_numel,
-                            const float* dxhat_ext, const float* rowsums, void* dy, float* dgamma, float* dbeta,
-                            float* dbias, double* ws, int N, int B, int T, int Tp, int G, int loss_kind, int dtype,
-                            void* stream) {
+int sg_recon_bwd(const float* y, const float* mr, const float* gamma, const float* beta, const float* x,
+                 const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext, const float* rowsums,
+                 void* dy, float* dgamma, float* dbeta, float* dbias, double* ws, int N, int B, int T, int Tp, int G,
+                 int loss_kind, int dtype, void* stream) {
     SG_REQUIRE(G > 0 && N % G == 0 && Tp % 8 == 0, "recon_bwd: bad shape");
     SG_REQUIRE(x != nullptr || (g_loss == nullptr && g_mse == nullptr), "recon_bwd: loss gradient without x");
     cudaStream_t st = as_stream(stream);
@@ -747,18 +1011,27 @@ extern "C" int sg_recon_bwd(const float* y, const double* stats, const float* ga
     cudaMemsetAsync(S, 0, sizeof(double) * 2 * B * G, st);
     cudaMemsetAsync(dbias, 0, sizeof(float) * N, st);
     recon_scalars_kernel<<<1, 1, 0, st>>>(g_loss, g_mse, inv_numel, scal);
+    int grid = persistent_grid((long long)N * B) * 2;
     if (rowsums != nullptr && dxhat_ext == nullptr && x != nullptr) {
         // one pass over y / x: the reductions of the GroupNorm backward were taken by the forward
         SG_REQUIRE((size_t)B * 2 * sizeof(float) <= 48 * 1024, "recon_bwd: batch too large for the combine kernel");
         dim3 gc((unsigned)cdiv(N / G, 64), G);
         recon_bwd_combine_kernel<<<gc, kThreads, sizeof(float) * 2 * B, st>>>((const float4*)rowsums, scal, gamma, dgamma,
                                                                                dbeta, S, N, B, G);
-        int grid = persistent_grid((long long)N * B);
         bool vec = (T % 4 == 0) && aligned16(x);
         const bool mse = loss_kind == SG_LOSS_MSE;
-#define SG_APPLY(OT, VEC, MSE)                                                                                       \
-    recon_bwd_apply_kernel<OT, VEC, MSE><<<grid, kThreads, 0, st>>>(y, stats, gamma, beta, x, scal, S, (OT*)dy, dbias, N, \
-                                                                     B, T, Tp, G, loss_kind, inv_n)
+        if (vec && (T & 7) == 0 && (long long)N * B < (1LL << 31)) {
+#define SG_AF(OT, MSE) \
+    recon_bwd_apply_fast_kernel<OT, MSE><<<grid, kThreads, 0, st>>>(y, mr, gamma, beta, x, scal, S, (OT*)dy, dbias, N, B, T, Tp, \
+                                                                    G, loss_kind, (float)inv_n)
+            if (dtype == SG_BF16) { if (mse) SG_AF(__nv_bfloat16, true); else SG_AF(__nv_bfloat16, false); }
+            else                  { if (mse) SG_AF(float, true); else SG_AF(float, false); }
+#undef SG_AF
+            return check_launch("recon_bwd");
+        }
+#define SG_APPLY(OT, VEC, MSE)                                                                                           \
+    recon_bwd_apply_kernel<OT, VEC, MSE><<<grid, kThreads, 0, st>>>(y, mr, gamma, beta, x, scal, S, (OT*)dy, dbias, N, B, T, \
+                                                                     Tp, G, loss_kind, inv_n)
 #define SG_APPLY2(OT, VEC) do { if (mse) SG_APPLY(OT, VEC, true); else SG_APPLY(OT, VEC, false); } while (0)
         if (dtype == SG_BF16) { if (vec) SG_APPLY2(__nv_bfloat16, true); else SG_APPLY2(__nv_bfloat16, false); }
         else                  { if (vec) SG_APPLY2(float, true); else SG_APPLY2(float, false); }
@@ -766,14 +1039,11 @@ extern "C" int sg_recon_bwd(const float* y, const double* stats, const float* ga
 #undef SG_APPLY
         return check_launch("recon_bwd");
     }
-    BwdArgs p{};
-    p.y = y; p.stats = stats; p.gamma = gamma; p.beta = beta; p.res = nullptr; p.res_scale = 1.f;
-    p.act = SG_ACT_TANH; p.post_gelu = 0; p.dout = nullptr; p.x = x; p.ext = dxhat_ext; p.loss_kind = loss_kind;
-    p.C = N; p.B = B; p.T = T; p.Tp = Tp; p.G = G;
-    p.inv_n = inv_n;
+    ReconBwdArgs p{};
+    p.y = y; p.mr = mr; p.gamma = gamma; p.beta = beta; p.x = x; p.ext = dxhat_ext; p.loss_kind = loss_kind;
+    p.N = N; p.B = B; p.T = T; p.Tp = Tp; p.G = G; p.inv_n = inv_n;
     cudaMemsetAsync(dgamma, 0, sizeof(float) * N, st);
     cudaMemsetAsync(dbeta, 0, sizeof(float) * N, st);
-    int grid = rows_grid((long long)N * B);
     if (dtype == SG_BF16) {
         recon_bwd_kernel<__nv_bfloat16, true><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (__nv_bfloat16*)dy, dbias);
         recon_bwd_kernel<__nv_bfloat16, false><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (__nv_bfloat16*)dy, dbias);
@@ -783,3 +1053,5 @@ extern "C" int sg_recon_bwd(const float* y, const double* stats, const float* ga
     }
     return check_launch("recon_bwd");
 }
+
+}  // extern "C"

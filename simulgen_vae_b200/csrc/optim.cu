@@ -76,6 +76,21 @@ opt_dot_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ Op
             float4 w = *reinterpret_cast<const float4*>(it.p + e);
             acc += g.x * w.x + g.y * w.y + g.z * w.z + g.w * w.w;
         }
+    } else if (!it.flip && (it.n & 3) == 0 && aligned16(it.p, it.p)) {
+        // k-tap Conv1d: p is walked 4 native elements per thread (16-byte loads), G is gathered from its tap planes
+        for (long long e = e0 + threadIdx.x * 4; e < e1; e += kOptThreads * 4) {
+            float4 w4 = *reinterpret_cast<const float4*>(it.p + e);
+            float w[4] = {w4.x, w4.y, w4.z, w4.w};
+            int o, q;
+            long long gi;
+            decode(it, (int)e, o, q, gi);
+            int i = q / it.k, j = q - i * it.k;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                acc += __ldg(it.g + ((long long)j * it.Cout + o) * it.Cin_p + i) * w[t];
+                if (++j == it.k) { j = 0; if (++i == it.Cin) { i = 0; ++o; } }
+            }
+        }
     } else {
         for (long long e = e0 + threadIdx.x; e < e1; e += kOptThreads) {
             int o, q;
@@ -143,6 +158,35 @@ opt_step_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ O
                 float gi = g[i] * a.grad_scale;
                 ss += gi * gi;
                 adam_update(p[i], m[i], v[i], gi, a);
+            }
+            *reinterpret_cast<float4*>(it.p + e) = make_float4(p[0], p[1], p[2], p[3]);
+            *reinterpret_cast<float4*>(it.m + e) = make_float4(m[0], m[1], m[2], m[3]);
+            *reinterpret_cast<float4*>(it.v + e) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    } else if (sn && !it.flip && (it.n & 3) == 0 && aligned16(it.p, it.m) && aligned16(it.v, it.v)) {
+        for (long long e = e0 + threadIdx.x * 4; e < e1; e += kOptThreads * 4) {
+            float4 p4 = *reinterpret_cast<const float4*>(it.p + e);
+            float4 m4 = *reinterpret_cast<const float4*>(it.m + e);
+            float4 v4 = *reinterpret_cast<const float4*>(it.v + e);
+            float p[4] = {p4.x, p4.y, p4.z, p4.w};
+            float m[4] = {m4.x, m4.y, m4.z, m4.w};
+            float v[4] = {v4.x, v4.y, v4.z, v4.w};
+            float g[4];
+            int o, q;
+            long long gi;
+            decode(it, (int)e, o, q, gi);
+            int i = q / it.k, j = q - i * it.k;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float graw = __ldg(it.g + ((long long)j * it.Cout + o) * it.Cin_p + i);
+                g[t] = (graw - coef * __ldg(it.u + o) * __ldg(it.vv + i * it.k + j)) * inv_sigma;
+                if (++j == it.k) { j = 0; if (++i == it.Cin) { i = 0; ++o; } }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float gi2 = g[t] * a.grad_scale;
+                ss += gi2 * gi2;
+                adam_update(p[t], m[t], v[t], gi2, a);
             }
             *reinterpret_cast<float4*>(it.p + e) = make_float4(p[0], p[1], p[2], p[3]);
             *reinterpret_cast<float4*>(it.m + e) = make_float4(m[0], m[1], m[2], m[3]);

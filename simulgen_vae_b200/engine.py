@@ -503,7 +503,7 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
         out = Act(p.Cout, data=None, f32=y, name=name)
     else:
         if gn is not None:
-            stats = ctx.f64(B, G, 2)
+            stats = ctx.f32(B, G, 2)
             K.gn_stats(y, stats, T, G)
         out_op = out_op_view if out_op_view is not None else ctx.op(out_planes, p.Cout, B, Tp)
         out_f32 = ctx.f32(p.Cout, B, Tp) if (want_f32 and ctx.op_dtype != torch.float32) else None
@@ -735,7 +735,7 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     N, G = p.Cout, gn.num_groups
     y = ctx.f32(N, B, Tp)
     K.conv_fprop(p.wg, out.data, conv.bias, y, p.Cin)
-    stats = ctx.f64(B, G, 2)
+    stats = ctx.f32(B, G, 2)
     K.gn_stats(y, stats, T, G)
     x_hat = ctx.f32(B, N, T) if want_xhat else None
     res = dict(x_hat=x_hat, recon=None, mse=None, kls=kls)

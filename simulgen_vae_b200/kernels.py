@@ -169,8 +169,10 @@ def conv_wgrad(dy, act, dwg, Cin):
 
 # ---- GroupNorm + activation ---------------------------------------------------------------------
 def gn_stats(y, stats, T, G):
+    """stats: fp32 [B, G, 2] <- (mean, rstd) of every (sample, group)."""
     C, B, Tp = y.shape
-    _call("sg_gn_stats", _p(_f32(y, "y")), _p(stats), C, B, T, Tp, G, _stream())
+    ws = torch.empty(2 * B * G, dtype=torch.float64, device=y.device)
+    _call("sg_gn_stats", _p(_f32(y, "y")), _p(ws), _p(_f32(stats, "stats")), C, B, T, Tp, G, _stream())
 
 
 def gn_act_fwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, out_op, out_f32, T, G):
@@ -179,7 +181,7 @@ def gn_act_fwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, out_op, ou
     dt = _dt(out_op) if out_op is not None else SG_F32
     op, on, ostr = _planes(out_op)
     res_is_f32 = int(res is not None and res.dtype == torch.float32)
-    _call("sg_gn_act_fwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(res), res_is_f32, float(res_scale),
+    _call("sg_gn_act_fwd", _p(_f32(y, "y")), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(res), res_is_f32, float(res_scale),
           int(act), int(post_gelu), op, on, ostr, _p(out_f32), C, B, T, Tp, int(G), dt, _stream())
 
 
@@ -189,7 +191,7 @@ def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, 
     res_is_f32 = int(res is not None and res.dtype == torch.float32)
     ws = torch.empty(2 * B * max(int(G), 1) + 2, dtype=torch.float64, device=y.device)
     dp, dn, dstr = _planes(dy)
-    _call("sg_gn_act_bwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(res), res_is_f32, float(res_scale),
+    _call("sg_gn_act_bwd", _p(_f32(y, "y")), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(res), res_is_f32, float(res_scale),
           int(act), int(post_gelu), _p(_f32(dout, "dout")), dp, dn, dstr, _p(dgamma), _p(dbeta), _p(dbias), _p(dres),
           int(dres_accumulate), _p(ws), C, B, T, Tp, int(G), _dt(dy), _stream())
 
@@ -197,7 +199,7 @@ def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, 
 def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind, rowsums=None):
     """rowsums: optional fp32 [N*B, 4] - partial sums of the GroupNorm backward taken by the forward."""
     N, B, Tp = y.shape
-    _call("sg_recon_fwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(x), _p(x_hat), _p(loss_sums),
+    _call("sg_recon_fwd", _p(_f32(y, "y")), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), _p(x_hat), _p(loss_sums),
           _p(_f32(rowsums, "rowsums")), N, B, T, Tp, G, int(loss_kind), _stream())
 
 
@@ -207,7 +209,7 @@ def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy,
     ws = torch.empty(2 * B * G + 2, dtype=torch.float64, device=y.device)
     dp, dn, _ = _planes(dy)
     assert dn == 1
-    _call("sg_recon_bwd", _p(_f32(y, "y")), _p(stats), _p(gamma), _p(beta), _p(x), _p(g_loss), _p(g_mse), float(inv_numel),
+    _call("sg_recon_bwd", _p(_f32(y, "y")), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), _p(g_loss), _p(g_mse), float(inv_numel),
           _p(dxhat_ext), _p(_f32(rowsums, "rowsums")), dp, _p(dgamma), _p(dbeta), _p(dbias), _p(ws), N, B, T, Tp, G,
           int(loss_kind), _dt(dy),
           _stream())

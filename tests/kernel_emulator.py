@@ -144,8 +144,10 @@ def conv_wgrad(dy, act, dwg, Cin):
 def gn_stats(y, stats, T, G):
     C, B, Tp = y.shape
     v = y[:, :, :T].double().reshape(G, C // G, B, T)
-    stats[:, :, 0] = v.sum(dim=(1, 3)).t()
-    stats[:, :, 1] = (v * v).sum(dim=(1, 3)).t()
+    mean = v.mean(dim=(1, 3))
+    var = (v * v).mean(dim=(1, 3)) - mean * mean
+    stats[:, :, 0] = mean.t().float()
+    stats[:, :, 1] = (1.0 / torch.sqrt(var.clamp_min(0) + 1e-5)).t().float()
 
 
 def _gn_forward(y, gamma, beta, res, res_scale, act, post_gelu, T, G, use_gn):

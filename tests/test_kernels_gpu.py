@@ -126,11 +126,11 @@ def test_conv_simt_fp32(k):
 def test_gn_stats():
     C, B, T, G = 48, 3, 21, 8
     y = cr(C, B, T, seed=1) + 0.5
-    s1 = torch.empty(B, G, 2, device=DEV, dtype=torch.float64)
+    s1 = torch.empty(B, G, 2, device=DEV)
     s2 = torch.empty_like(s1)
     K.gn_stats(y, s1, T, G)
     emu.gn_stats(y, s2, T, G)
-    close(s1, s2, 1e-6, "stats")
+    close(s1, s2, 1e-6, "stats (mean, rstd)")
 
 
 CASES = [
@@ -146,16 +146,18 @@ CASES = [
 
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("P", [1, 3, 5])
-def test_gn_act_fwd_bwd(case, dtype, P):
+@pytest.mark.parametrize("P,T", [(1, 21), (3, 21), (5, 21), (3, 300), (5, 200)])
+def test_gn_act_fwd_bwd(case, dtype, P, T):
+    """T=21 / 200: rows of <= 256 elements (one segment per lane, shifted planes by warp shuffle);
+    T=300: longer rows (several segments per lane, planes staged through shared memory)."""
     use_gn, act, res_kind, res_scale, post = case
-    C, B, T, G = 48, 3, 21, 8
+    C, B, G = 48, 3, 8
     Tp = tp_of(T)
     y = cr(C, B, T, seed=1) * 1.5 + 0.3
     gamma, beta = rnd(C, seed=2) * 0.5 + 1.0, rnd(C, seed=3) * 0.2
     stats = None
     if use_gn:
-        stats = torch.empty(B, G, 2, device=DEV, dtype=torch.float64)
+        stats = torch.empty(B, G, 2, device=DEV)
         K.gn_stats(y, stats, T, G)
     res = None
     if res_kind == "f32":
@@ -203,7 +205,7 @@ def test_recon_fwd_bwd(loss, with_ext, one_pass, T):
     y = cr(N, B, T, seed=1) * 2.0
     gamma, beta = rnd(N, seed=2) * 0.5 + 1.0, rnd(N, seed=3) * 0.2
     x = rnd(B, N, T, seed=4) * 1.5
-    stats = torch.empty(B, G, 2, device=DEV, dtype=torch.float64)
+    stats = torch.empty(B, G, 2, device=DEV)
     K.gn_stats(y, stats, T, G)
     xh1, xh2 = torch.empty(B, N, T, device=DEV), torch.empty(B, N, T, device=DEV)
     s1, s2 = (torch.empty(2, device=DEV, dtype=torch.float64) for _ in range(2))
