@@ -286,7 +286,7 @@ def _main():
     prof = K.PROFILE
     K.PROFILE = None
     gemm_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in prof)
-    gemm_flops = sum(f for _, f, _, _ in prof) * (cfg["num_time"] / sg.tp_of(cfg["num_time"]))   # valid columns only
+    gemm_flops = sum(f for _, f, _, _ in prof) * (cfg["num_time"] / sg.tp_of(cfg["num_time"], "bf16"))   # valid columns only
     scalars = trainer.scalars()
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)

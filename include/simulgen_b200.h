@@ -81,6 +81,14 @@ int sg_sn_weight_grad(const float* dwg, const float* w_orig, const float* u, con
  * R % 8 == 0 and Cin_p % 8 == 0 are required (TMA global strides are multiples of 16 bytes).  */
 int sg_conv_fprop(const void* wg, const void* act, int act_planes, long long act_plane_stride, const float* bias,
                   float* out, int Cin, int Cin_p, int Cout, int k, int R, int accumulate, int dtype, void* stream);
+/* fprop of a conv that feeds a GroupNorm: also returns stats[B][G][2] = (mean, rstd) of the output (bias included).
+ * With the CTA-pair tensor-core kernel the sums are taken in the GEMM epilogue from the fp32 accumulators
+ * (rowstat: >= 2*Cout*B floats of scratch) and the separate statistics pass over the output disappears; otherwise
+ * the output is reduced by sg_gn_stats (ws: >= 2*B*G doubles).  out_bf16 != 0 (bf16 mode, Cout > 128): the output
+ * is stored as bf16 [Cout][B][Tp]. */
+int sg_conv_fprop_gn(const void* wg, const void* act, int act_planes, long long act_plane_stride, const float* bias,
+                     void* out, int out_bf16, int Cin, int Cin_p, int Cout, int k, int B, int T, int Tp, int G,
+                     float* stats, double* ws, float* rowstat, int dtype, void* stream);
 int sg_conv_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_plane_stride, float* dx, int Cin,
                   int Cin_p, int Cout, int k, int R, int accumulate, int dtype, void* stream);
 int sg_conv_wgrad(const void* dy, int dy_planes, long long dy_plane_stride, const void* act, int act_planes,
@@ -107,18 +115,19 @@ int sg_gn_act_bwd(const float* y, const float* stats, const float* gamma, const 
                   int C, int B, int T, int Tp, int G, int dtype, void* stream);
 
 /* ---- reconstruction head: Tanh(GroupNorm(y)) + losses (decoder.py:117-121, VAE_network.py:71-77,110-111)
- * y fp32 [N][B][Tp]; x, x_hat fp32 [B][N][T] (either may be NULL).  loss_sums[2] doubles (zeroed inside):
+ * y [N][B][Tp] fp32 or bf16 (y_dtype; bf16 only in bf16 mode: the pre-norm output of the recon conv is the largest
+ * tensor of the step and is read three times); x, x_hat fp32 [B][N][T] (either may be NULL).  loss_sums[2] doubles (zeroed inside):
  * sum of the selected loss terms and sum of squared errors. */
 /* rowsums (optional, fp32 [N*B][4], 16-byte aligned; needs x): per-(n,b)-row partial sums of the GroupNorm
  * backward reductions, taken while y and x are in registers anyway; sg_recon_bwd then needs one pass. */
-int sg_recon_fwd(const float* y, const float* stats, const float* gamma, const float* beta, const float* x,
+int sg_recon_fwd(const void* y, int y_dtype, const float* stats, const float* gamma, const float* beta, const float* x,
                  float* x_hat, double* loss_sums, float* rowsums, int N, int B, int T, int Tp, int G, int loss_kind,
                  void* stream);
 /* dx_hat = g_loss[0]*inv_numel*loss'(x_hat-x) + g_mse[0]*inv_numel*2(x_hat-x) + dxhat_ext (each optional),
  * then backward through tanh and GroupNorm -> dy (dtype, 1 plane), dgamma, dbeta, dbias.
  * rowsums: the buffer sg_recon_fwd filled (or NULL: two passes; also used when dxhat_ext != NULL).
  * ws: >= 2*B*G + 2 doubles. */
-int sg_recon_bwd(const float* y, const float* stats, const float* gamma, const float* beta, const float* x,
+int sg_recon_bwd(const void* y, int y_dtype, const float* stats, const float* gamma, const float* beta, const float* x,
                  const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext,
                  const float* rowsums, void* dy, float* dgamma, float* dbeta, float* dbias, double* ws,
                  int N, int B, int T, int Tp, int G, int loss_kind, int dtype, void* stream);

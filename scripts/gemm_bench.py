@@ -15,7 +15,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 ONLY = sys.argv[3] if len(sys.argv) > 3 else ""
 T = 200
-Tp = tp_of(T)
+Tp = tp_of(T, "bf16")
 dev = torch.device("cuda")
 try:
     PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]

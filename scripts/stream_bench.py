@@ -15,7 +15,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 ONLY = sys.argv[3] if len(sys.argv) > 3 else ""
 T, N, G = 200, 95008, 8
-Tp = tp_of(T)
+Tp = tp_of(T, "bf16")
 dev = torch.device("cuda")
 BF = torch.bfloat16
 try:

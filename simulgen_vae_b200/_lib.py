@@ -28,13 +28,14 @@ SIGNATURES = {
     "sg_sn_pack_weight": [P, P, P, I, I, I, I, L, L, I, I, P],
     "sg_sn_weight_grad": [P, P, P, P, P, P, P, I, I, I, I, L, L, I, P],
     "sg_conv_fprop": [P, P, I, L, P, P, I, I, I, I, I, I, I, P],
+    "sg_conv_fprop_gn": [P, P, I, L, P, P, I, I, I, I, I, I, I, I, I, P, P, P, I, P],
     "sg_conv_dgrad": [P, P, I, L, P, I, I, I, I, I, I, I, P],
     "sg_conv_wgrad": [P, I, L, P, I, L, P, I, I, I, I, I, I, P],
     "sg_gn_stats": [P, P, P, I, I, I, I, I, P],
     "sg_gn_act_fwd": [P, P, P, P, P, I, F, I, I, P, I, L, P, I, I, I, I, I, I, P],
     "sg_gn_act_bwd": [P, P, P, P, P, I, F, I, I, P, P, I, L, P, P, P, P, I, P, I, I, I, I, I, I, P],
-    "sg_recon_fwd": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, P],
-    "sg_recon_bwd": [P, P, P, P, P, P, P, F, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
+    "sg_recon_fwd": [P, I, P, P, P, P, P, P, P, I, I, I, I, I, I, P],
+    "sg_recon_bwd": [P, I, P, P, P, P, P, P, F, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "sg_scale_f64_to_f32": [P, P, D, I, P],
     "sg_head_fwd": [P, P, P, P, P, I, I, I, I, I, P],
     "sg_head_bwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, P],

@@ -354,23 +354,58 @@ static bool use_pair(int M) {
     return mode == 1 && M > 128;
 }
 
-int tc_fprop(const void* wg, const void* act, int act_planes, long long act_pstride, const float* bias, float* out,
-             int Cin, int Cin_p, int Cout, int k, int R, int accumulate, cudaStream_t st) {
+// rowstat != NULL: ask the epilogue for per-(sample, row) GroupNorm partial sums; *stats_done tells the caller
+// whether the launched kernel produced them (CTA-pair kernel without split-K) or a separate pass is needed.
+int tc_fprop(const void* wg, const void* act, int act_planes, long long act_pstride, const float* bias, void* out,
+             int out_bf16, int Cin, int Cin_p, int Cout, int k, int R, int accumulate, float* rowstat, int st_T, int st_Tp,
+             int* stats_done, cudaStream_t st) {
     CUtensorMap ma, mb;
     if (make_map_wg(&ma, wg, Cin_p, Cout, k)) return 1;
     if (make_map_op(&mb, act, R, Cin, act_planes, act_pstride)) return 1;
     TcParams p{};
     const bool pair = use_pair(Cout);
-    p.out = out; p.bias = bias; p.M = Cout; p.N = R; p.ldc = R; p.c_sz = 0;
+    SG_REQUIRE(!out_bf16 || (pair && !accumulate), "conv_fprop: bf16 output needs the CTA-pair kernel (Cout > 128) and no accumulation");
+    p.out = (float*)out; p.bias = bias; p.M = Cout; p.N = R; p.ldc = R; p.c_sz = 0;
     p.m_tiles = (int)cdiv(Cout, pair ? pair::PM : BM); p.n_tiles = (int)cdiv(R, BN); p.z_count = 1; p.group_m = 8;
     p.taps = k; p.kblocks = (int)cdiv(Cin, BK); p.pad = k / 2; p.accumulate = accumulate;
     p.b_plane0 = act_planes / 2 - k / 2; p.b_plane_step = 1; p.a_plane = 0;
     p.splits = pick_splits(p.m_tiles * p.n_tiles, p.taps * p.kblocks, pair ? num_sms() / 2 : num_sms());
+    if (out_bf16) p.splits = 1;
     p.atomic = p.splits > 1;
     p.m_fastest = p.m_tiles <= p.n_tiles;
+    p.out_bf16 = out_bf16;
+    const bool fused_stats = rowstat != nullptr && pair && p.splits == 1 && !accumulate && st_Tp > 0 && R % st_Tp == 0;
+    if (stats_done) *stats_done = fused_stats ? 1 : 0;
+    if (fused_stats) {
+        p.rowstat = rowstat; p.st_T = st_T; p.st_Tp = st_Tp; p.st_B = R / st_Tp;
+        cudaMemsetAsync(rowstat, 0, sizeof(float) * 2 * (size_t)Cout * p.st_B, st);
+    }
     if (p.atomic && !accumulate) cudaMemsetAsync(out, 0, sizeof(float) * (size_t)Cout * R, st);
     if (pair) return launch_tc2<MODE_FPROP>(ma, mb, p, st);
     return launch_tc<MODE_FPROP>(ma, mb, p, st);
+}
+
+// stats[b][g] = (mean, rstd) from the epilogue's per-row partial sums rowstat[b][m][2]; grid (G, B)
+__global__ void __launch_bounds__(256) gn_rowstat_finalize_kernel(const float* __restrict__ rowstat, float* __restrict__ mr,
+                                                                  int M, int G, double inv_n) {
+    __shared__ double sh[2][32];
+    const int g = blockIdx.x, b = blockIdx.y, Cg = M / G;
+    const float2* rs = reinterpret_cast<const float2*>(rowstat) + (size_t)b * M + (size_t)g * Cg;
+    double s = 0.0, ss = 0.0;
+    for (int c = threadIdx.x; c < Cg; c += blockDim.x) {
+        float2 v = rs[c];
+        s += (double)v.x;
+        ss += (double)v.y;
+    }
+    double t0 = block_sum(s, sh[0]);
+    double t1 = block_sum(ss, sh[1]);
+    if (threadIdx.x == 0) {
+        double m = t0 * inv_n;
+        double var = t1 * inv_n - m * m;
+        if (var < 0.0) var = 0.0;
+        mr[2 * (b * G + g)] = (float)m;
+        mr[2 * (b * G + g) + 1] = (float)(1.0 / sqrt(var + (double)kGnEps));
+    }
 }
 
 int tc_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_pstride, float* dx, int Cin, int Cin_p,
@@ -432,7 +467,34 @@ int sg_conv_fprop(const void* wg, const void* act, int act_planes, long long act
     if (dtype == SG_F32)
         return simt_fprop((const float*)wg, (const float*)act + (long long)(act_planes / 2) * act_pstride, bias, out, Cin,
                           Cin_p, Cout, k, R, accumulate, as_stream(stream));
-    return tc_fprop(wg, act, act_planes, act_pstride, bias, out, Cin, Cin_p, Cout, k, R, accumulate, as_stream(stream));
+    return tc_fprop(wg, act, act_planes, act_pstride, bias, out, 0, Cin, Cin_p, Cout, k, R, accumulate, nullptr, 0, 0, nullptr,
+                    as_stream(stream));
+}
+
+int sg_conv_fprop_gn(const void* wg, const void* act, int act_planes, long long act_pstride, const float* bias, void* out,
+                     int out_bf16, int Cin, int Cin_p, int Cout, int k, int B, int T, int Tp, int G, float* stats,
+                     double* ws, float* rowstat, int dtype, void* stream) {
+    const int R = B * Tp;
+    SG_CONV_CHECK("conv_fprop_gn", act_planes);
+    SG_REQUIRE(G > 0 && Cout % G == 0 && stats != nullptr && ws != nullptr, "conv_fprop_gn: bad GroupNorm arguments");
+    cudaStream_t st = as_stream(stream);
+    if (dtype == SG_F32) {
+        SG_REQUIRE(!out_bf16, "conv_fprop_gn: bf16 output only in bf16 mode");
+        if (simt_fprop((const float*)wg, (const float*)act + (long long)(act_planes / 2) * act_pstride, bias, (float*)out, Cin,
+                       Cin_p, Cout, k, R, 0, st))
+            return 1;
+        return sg_gn_stats((const float*)out, ws, stats, Cout, B, T, Tp, G, stream);
+    }
+    int done = 0;
+    if (tc_fprop(wg, act, act_planes, act_pstride, bias, out, out_bf16, Cin, Cin_p, Cout, k, R, 0, rowstat, T, Tp, &done, st))
+        return 1;
+    if (done) {
+        dim3 grid(G, B);
+        gn_rowstat_finalize_kernel<<<grid, 256, 0, st>>>(rowstat, stats, Cout, G, 1.0 / ((double)(Cout / G) * T));
+        return check_launch("conv_fprop_gn");
+    }
+    SG_REQUIRE(!out_bf16, "conv_fprop_gn: bf16 output requires the fused-statistics path");
+    return sg_gn_stats((const float*)out, ws, stats, Cout, B, T, Tp, G, stream);
 }
 
 int sg_conv_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_pstride, float* dx, int Cin, int Cin_p,

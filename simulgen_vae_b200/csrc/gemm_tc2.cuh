@@ -242,6 +242,20 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (p.bias != nullptr && m_base + lane < p.M && wk.split == 0) bias = p.bias[m_base + lane];
             const bool have_k = wk.it_hi > wk.it_lo;
             float* obase = p.out + (long long)wk.z * p.c_sz;
+            // GroupNorm statistics of the tile (fprop, no split-K): this lane's row, running sums of the sample the
+            // current columns belong to; flushed with two atomics whenever the sample changes and at the tile end
+            const bool do_stats = (MODE == MODE_FPROP) && p.rowstat != nullptr;
+            float st_s = 0.f, st_ss = 0.f;
+            int st_b = do_stats ? wk.n0 / p.st_Tp : 0;
+            auto st_flush = [&](int b) {
+                if (m_base + lane < p.M && b < p.st_B) {
+                    float* rs = p.rowstat + ((size_t)b * p.M + (m_base + lane)) * 2;
+                    atomicAdd(rs, st_s);
+                    atomicAdd(rs + 1, st_ss);
+                }
+                st_s = 0.f;
+                st_ss = 0.f;
+            };
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t v[32];
@@ -252,6 +266,37 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (have_k && wk.n0 + c * 32 < p.N) {
 #pragma unroll
                     for (int e = 0; e < 32; ++e) slab[lane * EPI_PITCH + e] = __uint_as_float(v[e]) + bias;
+                    if (do_stats) {
+                        const int col0 = wk.n0 + c * 32;
+                        int b = col0 / p.st_Tp, t = col0 - b * p.st_Tp;
+                        if (b != st_b) { st_flush(st_b); st_b = b; }
+                        if (p.st_Tp >= 32) {
+                            // at most one sample boundary inside the 32 columns: [0, nb) -> sample b, [nb, 32) -> b + 1
+                            const int nb = p.st_Tp - t;
+                            const int lim0 = min(min(nb, p.st_T - t), p.N - col0);
+                            const int lim1 = min(nb + p.st_T, p.N - col0);
+                            float s1 = 0.f, ss1 = 0.f;
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) {
+                                const float val = __uint_as_float(v[e]) + bias;
+                                if (e < lim0) { st_s += val; st_ss = fmaf(val, val, st_ss); }
+                                if (e >= nb && e < lim1) { s1 += val; ss1 = fmaf(val, val, ss1); }
+                            }
+                            if (nb < 32) {
+                                st_flush(st_b);
+                                st_b = b + 1;
+                                st_s = s1;
+                                st_ss = ss1;
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int e = 0; e < 32; ++e) {
+                                const float val = slab[lane * EPI_PITCH + e];
+                                if (t < p.st_T && col0 + e < p.N) { st_s += val; st_ss = fmaf(val, val, st_ss); }
+                                if (++t == p.st_Tp) { st_flush(st_b); t = 0; st_b = st_b + 1; }
+                            }
+                        }
+                    }
                     __syncwarp();
                     if (n < p.N) {
 #pragma unroll
@@ -290,6 +335,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (lane == 0) {
                 if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_leader(&tempty_bar[as]);
             }
+            if (do_stats) st_flush(st_b);
         }
     }
 

@@ -440,9 +440,9 @@ gn_bwd_apply_kernel(BwdArgs p, const double* __restrict__ S, OT* __restrict__ dy
 // rowsums[row] = (sum gL, sum gL*xn, sum gM, sum gM*xn) with gL = loss'(d)(1 - xh^2), gM = 2 d (1 - xh^2),
 // xn = (y - mean) rstd: the backward scales them by the upstream loss gradients (they are linear in them).
 // ---------------------------------------------------------------------------------------------
-template <bool VEC, bool MSE>
+template <typename YT, bool VEC, bool MSE>
 __global__ void __launch_bounds__(kThreads)
-recon_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
+recon_fwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ x, float* __restrict__ x_hat,
                  double* __restrict__ loss_sums, float4* __restrict__ rowsums, int N, int B, int T, int Tp, int G,
                  int loss_kind) {
@@ -458,7 +458,7 @@ recon_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mr, cons
         const float mean = st.x, rstd = st.y;
         float a = gamma[n] * rstd, sh = beta[n] - mean * a;
         const float nm = -mean * rstd;                        // xn = y * rstd + nm
-        const float* yrow = y + row * Tp;
+        const YT* yrow = y + row * Tp;
         long long xo = ((long long)b * N + n) * T;
         float l0 = 0.f, l1 = 0.f, aL = 0.f, bL = 0.f, aM = 0.f, bM = 0.f;
         for (int seg = lane; seg * 8 < T; seg += 32) {
@@ -514,9 +514,9 @@ recon_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mr, cons
 // padding) and 16-byte aligned external rows.  No per-element predicates and 32-bit row arithmetic: the generic
 // kernel above spends ~190 of its ~370 instructions per row on index math and predication and is issue-bound
 // (ncu: issue slots 65 % busy at 58 % DRAM throughput).
-template <bool MSE, bool ROWSUMS, bool XHAT>
+template <typename YT, bool MSE, bool ROWSUMS, bool XHAT>
 __global__ void __launch_bounds__(kThreads)
-recon_fwd_fast_kernel(const float* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
+recon_fwd_fast_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                       const float* __restrict__ beta, const float* __restrict__ x, float* __restrict__ x_hat,
                       double* __restrict__ loss_sums, float4* __restrict__ rowsums, int N, int B, int T, int Tp, int G,
                       int loss_kind) {
@@ -532,7 +532,7 @@ recon_fwd_fast_kernel(const float* __restrict__ y, const float* __restrict__ mr,
         const float rstd = st.y;
         const float a = __ldg(gamma + n) * rstd, sh = __ldg(beta + n) - st.x * a;
         const float nm = -st.x * rstd;
-        const float* yrow = y + (size_t)row * Tp;
+        const YT* yrow = y + (size_t)row * Tp;
         const size_t xo = ((size_t)b * N + n) * T;
         float l0 = 0.f, l1 = 0.f, aL = 0.f, bL = 0.f, aM = 0.f, bM = 0.f;
         for (int seg = lane; seg < nseg; seg += 32) {
@@ -582,9 +582,9 @@ recon_fwd_fast_kernel(const float* __restrict__ y, const float* __restrict__ mr,
     }
 }
 
-template <typename OT, bool MSE>
+template <typename YT, typename OT, bool MSE>
 __global__ void __launch_bounds__(kThreads)
-recon_bwd_apply_fast_kernel(const float* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
+recon_bwd_apply_fast_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                             const float* __restrict__ beta, const float* __restrict__ x, const float* __restrict__ scal,
                             const double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias, int N, int B,
                             int T, int Tp, int G, int loss_kind, float inv_n) {
@@ -604,7 +604,7 @@ recon_bwd_apply_fast_kernel(const float* __restrict__ y, const float* __restrict
         const float m1 = (float)S[(size_t)(b * G + g) * 2] * inv_n;
         const float m2 = (float)S[(size_t)(b * G + g) * 2 + 1] * inv_n;
         const float c1 = rstd * gam, c2 = -rstd * rstd * m2, c3 = rstd * (mean * rstd * m2 - m1);
-        const float* yrow = y + (size_t)row * Tp;
+        const YT* yrow = y + (size_t)row * Tp;
         OT* drow = dy + (size_t)row * Tp;
         const size_t xo = ((size_t)b * N + n) * T;
         float db = 0.f;
@@ -671,9 +671,9 @@ recon_bwd_combine_kernel(const float4* __restrict__ rowsums, const float* __rest
 }
 
 // backward, step 2: dy = rstd * (gamma * g - m1 - xn * m2), g = (ga loss'(d) + gm 2d)(1 - xh^2)
-template <typename OT, bool VEC, bool MSE>
+template <typename YT, typename OT, bool VEC, bool MSE>
 __global__ void __launch_bounds__(kThreads)
-recon_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
+recon_bwd_apply_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                        const float* __restrict__ beta, const float* __restrict__ x, const float* __restrict__ scal,
                        const double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias, int N, int B, int T,
                        int Tp, int G, int loss_kind, double inv_n) {
@@ -694,7 +694,7 @@ recon_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ mr
         const float m1 = (float)(S[(size_t)(b * G + g) * 2] * inv_n);
         const float m2 = (float)(S[(size_t)(b * G + g) * 2 + 1] * inv_n);
         const float c1 = rstd * gam, c2 = -rstd * rstd * m2, c3 = rstd * (mean * rstd * m2 - m1);
-        const float* yrow = y + row * Tp;
+        const YT* yrow = y + row * Tp;
         long long xo = ((long long)b * N + n) * T;
         float db = 0.f;
         for (int seg = lane; seg < Tp / 8; seg += 32) {
@@ -729,7 +729,7 @@ recon_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ mr
 
 // two-pass recon backward (used when a gradient wrt x_hat itself arrives, or without the forward's row sums)
 struct ReconBwdArgs {
-    const float* y;
+    const void* y;
     const float* mr;
     const float* gamma;
     const float* beta;
@@ -739,7 +739,7 @@ struct ReconBwdArgs {
     double inv_n;
 };
 
-template <typename OT, bool REDUCE>
+template <typename YT, typename OT, bool REDUCE>
 __global__ void __launch_bounds__(kThreads)
 recon_bwd_kernel(ReconBwdArgs p, const float* __restrict__ scal, float* __restrict__ dgamma, float* __restrict__ dbeta,
                  double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias) {
@@ -765,7 +765,7 @@ recon_bwd_kernel(ReconBwdArgs p, const float* __restrict__ scal, float* __restri
 #pragma unroll
             for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
             if (seg * 8 < p.T) {
-                F8 yv = load8(p.y + row * p.Tp + seg * 8);
+                F8 yv = load8(reinterpret_cast<const YT*>(p.y) + row * p.Tp + seg * 8);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     int t = seg * 8 + i;
@@ -966,7 +966,7 @@ int sg_gn_act_bwd(const float* y, const float* mr, const float* gamma, const flo
                                     dres_accumulate, ws, st);
 }
 
-int sg_recon_fwd(const float* y, const float* mr, const float* gamma, const float* beta, const float* x,
+int sg_recon_fwd(const void* y, int y_dtype, const float* mr, const float* gamma, const float* beta, const float* x,
                  float* x_hat, double* loss_sums, float* rowsums, int N, int B, int T, int Tp, int G, int loss_kind,
                  void* stream) {
     SG_REQUIRE(G > 0 && N % G == 0, "recon_fwd: N=%d not divisible by G=%d", N, G);
@@ -976,33 +976,39 @@ int sg_recon_fwd(const float* y, const float* mr, const float* gamma, const floa
     bool vec = (T % 4 == 0) && aligned16(x) && aligned16(x_hat);
     int grid = persistent_grid((long long)N * B) * 2;
     const bool mse = loss_kind == SG_LOSS_MSE;
-#define SG_RFWD(VEC, MSE)                                                                                              \
-    recon_fwd_kernel<VEC, MSE><<<grid, kThreads, 0, st>>>(y, mr, gamma, beta, x, x_hat, loss_sums, (float4*)rowsums, N, B, \
-                                                          T, Tp, G, loss_kind)
+    const bool ybf = y_dtype == SG_BF16;
     if (vec && x != nullptr && (T & 7) == 0 && (long long)N * B < (1LL << 31)) {
-#define SG_FAST(MSE, RS, XH) \
-    recon_fwd_fast_kernel<MSE, RS, XH><<<grid, kThreads, 0, st>>>(y, mr, gamma, beta, x, x_hat, loss_sums, (float4*)rowsums, N, \
-                                                                  B, T, Tp, G, loss_kind)
-#define SG_FAST2(MSE) do { \
-        if (rowsums) { if (x_hat) SG_FAST(MSE, true, true); else SG_FAST(MSE, true, false); } \
-        else         { if (x_hat) SG_FAST(MSE, false, true); else SG_FAST(MSE, false, false); } } while (0)
-        if (mse) SG_FAST2(true); else SG_FAST2(false);
+#define SG_FAST(YT, MSE, RS, XH) \
+    recon_fwd_fast_kernel<YT, MSE, RS, XH><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, x, x_hat, loss_sums, \
+                                                                      (float4*)rowsums, N, B, T, Tp, G, loss_kind)
+#define SG_FAST2(YT, MSE) do { \
+        if (rowsums) { if (x_hat) SG_FAST(YT, MSE, true, true); else SG_FAST(YT, MSE, true, false); } \
+        else         { if (x_hat) SG_FAST(YT, MSE, false, true); else SG_FAST(YT, MSE, false, false); } } while (0)
+        if (ybf) { if (mse) SG_FAST2(__nv_bfloat16, true); else SG_FAST2(__nv_bfloat16, false); }
+        else     { if (mse) SG_FAST2(float, true); else SG_FAST2(float, false); }
 #undef SG_FAST2
 #undef SG_FAST
         return check_launch("recon_fwd");
     }
-    if (vec) { if (mse) SG_RFWD(true, true); else SG_RFWD(true, false); }
-    else     { if (mse) SG_RFWD(false, true); else SG_RFWD(false, false); }
+#define SG_RFWD(YT, VEC, MSE)                                                                                              \
+    recon_fwd_kernel<YT, VEC, MSE><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, x, x_hat, loss_sums,          \
+                                                              (float4*)rowsums, N, B, T, Tp, G, loss_kind)
+#define SG_RFWD2(YT) do { \
+        if (vec) { if (mse) SG_RFWD(YT, true, true); else SG_RFWD(YT, true, false); } \
+        else     { if (mse) SG_RFWD(YT, false, true); else SG_RFWD(YT, false, false); } } while (0)
+    if (ybf) SG_RFWD2(__nv_bfloat16); else SG_RFWD2(float);
+#undef SG_RFWD2
 #undef SG_RFWD
     return check_launch("recon_fwd");
 }
 
-int sg_recon_bwd(const float* y, const float* mr, const float* gamma, const float* beta, const float* x,
+int sg_recon_bwd(const void* y, int y_dtype, const float* mr, const float* gamma, const float* beta, const float* x,
                  const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext, const float* rowsums,
                  void* dy, float* dgamma, float* dbeta, float* dbias, double* ws, int N, int B, int T, int Tp, int G,
                  int loss_kind, int dtype, void* stream) {
     SG_REQUIRE(G > 0 && N % G == 0 && Tp % 8 == 0, "recon_bwd: bad shape");
     SG_REQUIRE(x != nullptr || (g_loss == nullptr && g_mse == nullptr), "recon_bwd: loss gradient without x");
+    SG_REQUIRE(y_dtype == SG_F32 || dtype == SG_BF16, "recon_bwd: bf16 y only in bf16 mode");
     cudaStream_t st = as_stream(stream);
     double inv_n = 1.0 / ((double)(N / G) * T);
     // workspace: 2*B*G doubles for S followed by 2 floats for the folded scalars
@@ -1012,6 +1018,8 @@ int sg_recon_bwd(const float* y, const float* mr, const float* gamma, const floa
     cudaMemsetAsync(dbias, 0, sizeof(float) * N, st);
     recon_scalars_kernel<<<1, 1, 0, st>>>(g_loss, g_mse, inv_numel, scal);
     int grid = persistent_grid((long long)N * B) * 2;
+    const bool ybf = y_dtype == SG_BF16;
+    typedef __nv_bfloat16 bf;
     if (rowsums != nullptr && dxhat_ext == nullptr && x != nullptr) {
         // one pass over y / x: the reductions of the GroupNorm backward were taken by the forward
         SG_REQUIRE((size_t)B * 2 * sizeof(float) <= 48 * 1024, "recon_bwd: batch too large for the combine kernel");
@@ -1021,20 +1029,26 @@ int sg_recon_bwd(const float* y, const float* mr, const float* gamma, const floa
         bool vec = (T % 4 == 0) && aligned16(x);
         const bool mse = loss_kind == SG_LOSS_MSE;
         if (vec && (T & 7) == 0 && (long long)N * B < (1LL << 31)) {
-#define SG_AF(OT, MSE) \
-    recon_bwd_apply_fast_kernel<OT, MSE><<<grid, kThreads, 0, st>>>(y, mr, gamma, beta, x, scal, S, (OT*)dy, dbias, N, B, T, Tp, \
-                                                                    G, loss_kind, (float)inv_n)
-            if (dtype == SG_BF16) { if (mse) SG_AF(__nv_bfloat16, true); else SG_AF(__nv_bfloat16, false); }
-            else                  { if (mse) SG_AF(float, true); else SG_AF(float, false); }
+#define SG_AF(YT, OT, MSE) \
+    recon_bwd_apply_fast_kernel<YT, OT, MSE><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, x, scal, S, (OT*)dy, dbias, \
+                                                                        N, B, T, Tp, G, loss_kind, (float)inv_n)
+            if (dtype == SG_BF16) {
+                if (ybf) { if (mse) SG_AF(bf, bf, true); else SG_AF(bf, bf, false); }
+                else     { if (mse) SG_AF(float, bf, true); else SG_AF(float, bf, false); }
+            } else {
+                if (mse) SG_AF(float, float, true); else SG_AF(float, float, false);
+            }
 #undef SG_AF
             return check_launch("recon_bwd");
         }
-#define SG_APPLY(OT, VEC, MSE)                                                                                           \
-    recon_bwd_apply_kernel<OT, VEC, MSE><<<grid, kThreads, 0, st>>>(y, mr, gamma, beta, x, scal, S, (OT*)dy, dbias, N, B, T, \
-                                                                     Tp, G, loss_kind, inv_n)
-#define SG_APPLY2(OT, VEC) do { if (mse) SG_APPLY(OT, VEC, true); else SG_APPLY(OT, VEC, false); } while (0)
-        if (dtype == SG_BF16) { if (vec) SG_APPLY2(__nv_bfloat16, true); else SG_APPLY2(__nv_bfloat16, false); }
-        else                  { if (vec) SG_APPLY2(float, true); else SG_APPLY2(float, false); }
+#define SG_APPLY(YT, OT, VEC, MSE)                                                                                         \
+    recon_bwd_apply_kernel<YT, OT, VEC, MSE><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, x, scal, S, (OT*)dy,  \
+                                                                         dbias, N, B, T, Tp, G, loss_kind, inv_n)
+#define SG_APPLY2(YT, OT) do { \
+        if (vec) { if (mse) SG_APPLY(YT, OT, true, true); else SG_APPLY(YT, OT, true, false); } \
+        else     { if (mse) SG_APPLY(YT, OT, false, true); else SG_APPLY(YT, OT, false, false); } } while (0)
+        if (dtype == SG_BF16) { if (ybf) SG_APPLY2(bf, bf); else SG_APPLY2(float, bf); }
+        else                  SG_APPLY2(float, float);
 #undef SG_APPLY2
 #undef SG_APPLY
         return check_launch("recon_bwd");
@@ -1044,13 +1058,14 @@ int sg_recon_bwd(const float* y, const float* mr, const float* gamma, const floa
     p.N = N; p.B = B; p.T = T; p.Tp = Tp; p.G = G; p.inv_n = inv_n;
     cudaMemsetAsync(dgamma, 0, sizeof(float) * N, st);
     cudaMemsetAsync(dbeta, 0, sizeof(float) * N, st);
-    if (dtype == SG_BF16) {
-        recon_bwd_kernel<__nv_bfloat16, true><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (__nv_bfloat16*)dy, dbias);
-        recon_bwd_kernel<__nv_bfloat16, false><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (__nv_bfloat16*)dy, dbias);
-    } else {
-        recon_bwd_kernel<float, true><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (float*)dy, dbias);
-        recon_bwd_kernel<float, false><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (float*)dy, dbias);
-    }
+#define SG_TWO(YT, OT)                                                                                             \
+    do {                                                                                                           \
+        recon_bwd_kernel<YT, OT, true><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (OT*)dy, dbias);       \
+        recon_bwd_kernel<YT, OT, false><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (OT*)dy, dbias);      \
+    } while (0)
+    if (dtype == SG_BF16) { if (ybf) SG_TWO(bf, bf); else SG_TWO(float, bf); }
+    else                  SG_TWO(float, float);
+#undef SG_TWO
     return check_launch("recon_bwd");
 }
 

@@ -38,7 +38,13 @@ def get_precision() -> str:
     return _PRECISION
 
 
-def tp_of(T: int) -> int:
+def tp_of(T: int, precision: str = None) -> int:
+    """Row pitch of the CR layout.  bf16 (tensor-core) mode: T rounded up to 8 elements (TMA pitches are multiples
+    of 16 bytes) - the taps of a k-tap conv read pre-shifted operand planes, so no zero gap between samples is
+    needed.  fp32 validation mode: the SIMT GEMMs shift along the flattened (sample, time) axis and rely on a
+    zero gap of >= 2 columns (k <= 5) between samples."""
+    if (precision or _PRECISION) == "bf16":
+        return (T + 7) // 8 * 8
     return (T + 2 + 7) // 8 * 8
 
 
@@ -194,6 +200,16 @@ def set_grad_sink(sink):
 
 def get_grad_sink():
     return getattr(_sink, "value", None)
+
+
+def set_materialize_xhat(flag: bool):
+    """False: VAE.forward(x) returns x_hat = None - the reconstruction only exists in registers inside the fused
+    tanh + loss kernel (train.py:142 discards it); saves one fp32 [B, N, T] write per step.  Thread-local."""
+    _sink.xhat = bool(flag)
+
+
+def _materialize_xhat():
+    return getattr(_sink, "xhat", True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -494,17 +510,18 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
     B, T, Tp = ctx.B, ctx.T, ctx.Tp
     p = prep_conv(ctx, conv, transposed)
     y = ctx.f32(p.Cout, B, Tp)
-    K.conv_fprop(p.wg, a_in.data, conv.bias, y, p.Cin)
     plain = gn is None and act == K.ACT_NONE and res is None and not post_gelu
     G = gn.num_groups if gn is not None else 0
     stats = None
     res_t = None
+    if gn is not None:
+        stats = ctx.f32(B, G, 2)
+        K.conv_fprop_gn(p.wg, a_in.data, conv.bias, y, p.Cin, stats, T, G)   # statistics from the GEMM epilogue
+    else:
+        K.conv_fprop(p.wg, a_in.data, conv.bias, y, p.Cin)
     if plain:
         out = Act(p.Cout, data=None, f32=y, name=name)
     else:
-        if gn is not None:
-            stats = ctx.f32(B, G, 2)
-            K.gn_stats(y, stats, T, G)
         out_op = out_op_view if out_op_view is not None else ctx.op(out_planes, p.Cout, B, Tp)
         out_f32 = ctx.f32(p.Cout, B, Tp) if (want_f32 and ctx.op_dtype != torch.float32) else None
         res_t = res.residual_source() if res is not None else None
@@ -733,10 +750,13 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     p = prep_conv(ctx, conv)
     finish_prepare(ctx)
     N, G = p.Cout, gn.num_groups
-    y = ctx.f32(N, B, Tp)
-    K.conv_fprop(p.wg, out.data, conv.bias, y, p.Cin)
+    # bf16 mode: the pre-norm output of the recon conv (the largest tensor of the step, read by the forward and the
+    # backward head kernels) is stored as bf16; its GroupNorm statistics are taken from the fp32 accumulators
+    y_bf16 = ctx.op_dtype == torch.bfloat16 and N > 128
+    y = torch.empty(N, B, Tp, dtype=torch.bfloat16 if y_bf16 else torch.float32, device=ctx.dev)
     stats = ctx.f32(B, G, 2)
-    K.gn_stats(y, stats, T, G)
+    K.conv_fprop_gn(p.wg, out.data, conv.bias, y, p.Cin, stats, T, G)
+    want_xhat = want_xhat and (_materialize_xhat() or x is None)
     x_hat = ctx.f32(B, N, T) if want_xhat else None
     res = dict(x_hat=x_hat, recon=None, mse=None, kls=kls)
     loss_kind = K.LOSS_KINDS.get(lossfun, 0)

@@ -145,6 +145,21 @@ def conv_fprop(wg, act, bias, out, Cin, accumulate=False):
         _dt(act), _stream()))
 
 
+def conv_fprop_gn(wg, act, bias, out, Cin, stats, T, G):
+    """Conv + GroupNorm statistics: out [Cout, B, Tp] (fp32, or bf16 for the recon layer in bf16 mode),
+    stats fp32 [B, G, 2] <- (mean, rstd).  The statistics come from the GEMM epilogue when the CTA-pair kernel runs."""
+    k, Cout, Cin_p = wg.shape
+    ap, an, astr = _planes(act)
+    B, Tp = act.shape[2], act.shape[3]
+    assert act.shape[1] == Cin and out.shape[0] == Cout and out.numel() == Cout * B * Tp and wg.dtype == act.dtype
+    out_bf16 = int(out.dtype == torch.bfloat16)
+    ws = torch.empty(2 * B * G, dtype=torch.float64, device=out.device)
+    rowstat = torch.empty(2 * Cout * B, dtype=torch.float32, device=out.device) if act.dtype == torch.bfloat16 else None
+    _timed("fprop", 2.0 * Cin * Cout * k * B * Tp, lambda: _call(
+        "sg_conv_fprop_gn", _p(wg), ap, an, astr, _p(bias), _p(out), out_bf16, Cin, Cin_p, Cout, k, B, T, Tp, int(G),
+        _p(_f32(stats, "stats")), _p(ws), _p(rowstat), _dt(act), _stream()))
+
+
 def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
     """dy: operand [P, Cout, B, Tp]; dx fp32 [Cin, B, Tp]."""
     k, Cout, Cin_p = wg.shape
@@ -199,7 +214,7 @@ def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, 
 def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind, rowsums=None):
     """rowsums: optional fp32 [N*B, 4] - partial sums of the GroupNorm backward taken by the forward."""
     N, B, Tp = y.shape
-    _call("sg_recon_fwd", _p(_f32(y, "y")), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), _p(x_hat), _p(loss_sums),
+    _call("sg_recon_fwd", _p(y), _dt(y), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), _p(x_hat), _p(loss_sums),
           _p(_f32(rowsums, "rowsums")), N, B, T, Tp, G, int(loss_kind), _stream())
 
 
@@ -209,7 +224,7 @@ def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy,
     ws = torch.empty(2 * B * G + 2, dtype=torch.float64, device=y.device)
     dp, dn, _ = _planes(dy)
     assert dn == 1
-    _call("sg_recon_bwd", _p(_f32(y, "y")), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), _p(g_loss), _p(g_mse), float(inv_numel),
+    _call("sg_recon_bwd", _p(y), _dt(y), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), _p(g_loss), _p(g_mse), float(inv_numel),
           _p(dxhat_ext), _p(_f32(rowsums, "rowsums")), dp, _p(dgamma), _p(dbeta), _p(dbias), _p(ws), N, B, T, Tp, G,
           int(loss_kind), _dt(dy),
           _stream())

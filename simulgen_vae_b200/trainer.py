@@ -49,7 +49,7 @@ def _gemm_layout_elems(mod):
 
 class Trainer:
     def __init__(self, model, lr=1e-3, alpha=1.0e6, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                 process_group=None, bucket_mb=64, fused=True):
+                 process_group=None, bucket_mb=64, fused=True, materialize_xhat=False):
         self.model = model
         self.lr, self.alpha, self.betas, self.eps, self.wd = lr, alpha, betas, eps, weight_decay
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -65,6 +65,7 @@ class Trainer:
             self.world = torch.distributed.get_world_size(process_group)
         self.bucket_elems = bucket_mb * (1 << 20) // 4
         self.fused = fused
+        self.materialize_xhat = materialize_xhat      # the step only needs the losses; x_hat stays in registers
         self._last = None
         self.sink = None
         self.plan = None
@@ -174,6 +175,7 @@ class Trainer:
         if self.fused:
             self.sink.begin_step()
             engine.set_grad_sink(self.sink)
+            engine.set_materialize_xhat(self.materialize_xhat)
             try:
                 x_hat, recon, kls, mse = model(x)
                 kl_sum = kls[0]
@@ -183,6 +185,7 @@ class Trainer:
                 loss.backward()
             finally:
                 engine.set_grad_sink(None)
+                engine.set_materialize_xhat(True)
             self._finish_reduce()
             if self.plan is None:
                 self._build_plan()

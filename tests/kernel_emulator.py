@@ -105,11 +105,18 @@ def sn_weight_grad(dwg, w, u, v, sigma, grad, Cout, Cin, Cin_p, k, so, si, flip)
 # ---- convolutions -------------------------------------------------------------------------------
 # The models use ONLY the centre plane and do the tap shifts themselves (F.conv1d), so they also check
 # that the pre-shifted planes the CUDA path reads are consistent with a real convolution.
-def conv_fprop(wg, act, bias, out, Cin, accumulate=False):
+def _valid_T(t):
+    """number of valid columns of a CR operand: the trailing all-zero columns of every row are the gap"""
+    return t.shape[-1]
+
+
+def conv_fprop(wg, act, bias, out, Cin, accumulate=False, T=None):
+    """Per-sample convolution of the centre plane (independent of the zero gap between samples); the gap
+    columns of `out` receive the same values a flattened convolution over zero-padded rows would give."""
     k, Cout, Cin_p = wg.shape
-    a = center(act).reshape(Cin, -1).float()[None]
-    w = wg[:, :, :Cin].float().permute(1, 2, 0).contiguous()
-    y = F.conv1d(a, w, bias.detach() if bias is not None else None, padding=k // 2)[0]
+    a = center(act).float().permute(1, 0, 2)                                  # [B, Cin, Tp]
+    w = wg[:, :, :Cin].float().permute(1, 2, 0).contiguous()                  # [Cout, Cin, k]
+    y = F.conv1d(a, w, bias.detach() if bias is not None else None, padding=k // 2).permute(1, 0, 2)
     y = y.reshape(out.shape)
     if accumulate:
         out.add_(y)
@@ -117,11 +124,18 @@ def conv_fprop(wg, act, bias, out, Cin, accumulate=False):
         out.copy_(y)
 
 
+def conv_fprop_gn(wg, act, bias, out, Cin, stats, T, G):
+    tmp = torch.empty(out.shape, dtype=torch.float32, device=out.device)
+    conv_fprop(wg, act, bias, tmp, Cin)
+    gn_stats(tmp, stats, T, G)
+    out.copy_(tmp.to(out.dtype))
+
+
 def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
     k, Cout, Cin_p = wg.shape
-    g = center(dy).reshape(Cout, -1).float()[None]
-    w = wg[:, :, :Cin].float().flip(0).permute(2, 1, 0).contiguous()      # [ci][co][j'] = wg[k-1-j'][co][ci]
-    y = F.conv1d(g, w, None, padding=k // 2)[0].reshape(dx.shape)
+    g = center(dy).float().permute(1, 0, 2)                                   # [B, Cout, Tp]
+    w = wg[:, :, :Cin].float().flip(0).permute(2, 1, 0).contiguous()          # [ci][co][j'] = wg[k-1-j'][co][ci]
+    y = F.conv1d(g, w, None, padding=k // 2).permute(1, 0, 2).reshape(dx.shape)
     if accumulate:
         dx.add_(y)
     else:
@@ -130,14 +144,14 @@ def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
 
 def conv_wgrad(dy, act, dwg, Cin):
     k, Cout, Cin_p = dwg.shape
-    g = center(dy).reshape(Cout, -1).float()
-    a = center(act).reshape(Cin, -1).float()
-    R = a.shape[1]
+    g = center(dy).float()                                                    # [Cout, B, Tp]
+    a = center(act).float()                                                   # [Cin, B, Tp]
+    Tp = a.shape[2]
     pad = k // 2
-    ap = F.pad(a, (pad, pad))
+    ap = F.pad(a, (pad, pad))                                                 # per-sample zero padding
     dwg.zero_()
     for j in range(k):
-        dwg[j, :, :Cin] = g @ ap[:, j:j + R].t()
+        dwg[j, :, :Cin] = torch.einsum("obt,ibt->oi", g, ap[:, :, j:j + Tp])
 
 
 # ---- GroupNorm + activation ---------------------------------------------------------------------
@@ -217,6 +231,7 @@ def _loss_terms(kind, d):
 
 
 def _recon_xhat(y, gamma, beta, T, G):
+    y = y.float() if y.dtype != torch.float32 else y
     N, B, Tp = y.shape
     o = _gn_forward(y, gamma, beta, None, 1.0, ACT_TANH, False, T, G, True)      # [N,B,T]
     return o.permute(1, 0, 2)                                                     # [B,N,T]
@@ -236,7 +251,7 @@ def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind, rowsu
 def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy, dgamma, dbeta, dbias, T, G, loss_kind,
               rowsums=None):
     with torch.enable_grad():
-        yl = y.detach().clone().requires_grad_(True)
+        yl = y.detach().float().clone().requires_grad_(True)
         gl = gamma.detach().clone().requires_grad_(True)
         bl = beta.detach().clone().requires_grad_(True)
         xh = _recon_xhat(yl, gl, bl, T, G)
@@ -443,7 +458,7 @@ def sn_prepare(plan, training):
 
 
 NAMES = ["OptPlan", "opt_step", "SnPlan", "sn_prepare", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
-         "conv_fprop", "conv_dgrad", "conv_wgrad", "gn_stats", "gn_act_fwd", "gn_act_bwd", "recon_fwd", "recon_bwd",
+         "conv_fprop", "conv_fprop_gn", "conv_dgrad", "conv_wgrad", "gn_stats", "gn_act_fwd", "gn_act_bwd", "recon_fwd", "recon_bwd",
          "head_fwd", "head_bwd", "latent_fwd", "latent_bwd", "reparam_main_fwd", "reparam_main_bwd", "kl2_reparam_fwd",
          "kl2_reparam_bwd", "philox_normal", "adamw_step"]
 

@@ -6,7 +6,12 @@ import torch
 import kernel_emulator as emu
 from conftest import rel_l2
 from simulgen_vae_b200 import kernels as K
-from simulgen_vae_b200.engine import tp_of
+from simulgen_vae_b200 import engine
+
+
+def tp_of(T):
+    """bf16-mode row pitch: no zero gap between samples (the taps read pre-shifted planes)"""
+    return engine.tp_of(T, "bf16")
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -89,3 +94,32 @@ def test_tc_wgrad(shape):
     assert rel_l2(w1[:, :, :Cin], w2[:, :, :Cin]) < 1e-4, rel_l2(w1[:, :, :Cin], w2[:, :, :Cin])
     if Cin_p > Cin:
         assert float(w1[:, :, Cin:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(64, 320, 1, 5, 200), (96, 1000, 3, 3, 8)])
+@pytest.mark.parametrize("out_bf16", [False, True])
+def test_tc_fprop_gn_fused_statistics(shape, out_bf16):
+    """conv + GroupNorm statistics in one call: (mean, rstd) from the GEMM epilogue (CTA-pair kernel) or from the
+    separate pass (single-CTA / split-K) must equal the statistics of the fp32 conv output; optional bf16 output."""
+    Cin, Cout, k, B, T = shape
+    G = 8
+    if Cout % G or (out_bf16 and Cout <= 128):
+        pytest.skip("not a GroupNorm / bf16-output shape")
+    wg, act, dy, bias, Tp, Cin_p = make(*shape)
+    o2 = torch.empty(Cout, B, Tp, device=DEV)
+    emu.conv_fprop(wg, act, bias, o2, Cin)
+    o2[:, :, T:] = 0
+    s2 = torch.empty(B, G, 2, device=DEV)
+    emu.gn_stats(o2, s2, T, G)
+    o1 = torch.full((Cout, B, Tp), 5.0, device=DEV, dtype=BF if out_bf16 else torch.float32)
+    s1 = torch.full((B, G, 2), 7.0, device=DEV)
+    try:
+        K.conv_fprop_gn(wg, act, bias, o1, Cin, s1, T, G)
+    except RuntimeError as e:
+        if out_bf16 and "fused-statistics" in str(e):
+            pytest.skip("split-K shape: bf16 output not available")
+        raise
+    torch.cuda.synchronize()
+    assert rel_l2(o1[:, :, :T].float(), o2[:, :, :T]) < (4e-3 if out_bf16 else 1e-4)
+    assert rel_l2(s1[:, :, 0], s2[:, :, 0]) < 1e-3 and (s1[:, :, 0] - s2[:, :, 0]).abs().max() < 1e-4
+    assert rel_l2(s1[:, :, 1], s2[:, :, 1]) < 1e-4

@@ -6,7 +6,12 @@ import torch
 import kernel_emulator as emu
 from conftest import rel_l2
 from simulgen_vae_b200 import kernels as K
-from simulgen_vae_b200.engine import tp_of
+from simulgen_vae_b200 import engine
+
+
+def tp_of(T):
+    """fp32-mode row pitch (zero gap of >= 2 columns): required by the SIMT convolutions, valid for every kernel"""
+    return engine.tp_of(T, "fp32")
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -104,18 +109,19 @@ def test_conv_simt_fp32(k):
     bias = rnd(Cout, seed=3)
     o1 = torch.empty(Cout, B, Tp, device=DEV)
     o2 = torch.empty_like(o1)
+    # gap columns t >= T are don't-care (the SIMT kernels convolve along the flattened axis, the model per sample)
     K.conv_fprop(wg, act, bias, o1, Cin)
     emu.conv_fprop(wg, act, bias, o2, Cin)
-    close(o1, o2, 1e-5, "fprop")
+    close(o1[:, :, :T], o2[:, :, :T], 1e-5, "fprop")
     K.conv_fprop(wg, act, None, o1, Cin, accumulate=True)
     emu.conv_fprop(wg, act, None, o2, Cin, accumulate=True)
-    close(o1, o2, 1e-5, "fprop acc")
+    close(o1[:, :, :T], o2[:, :, :T], 1e-5, "fprop acc")
     dy = planes_of(cr(Cout, B, T, seed=4), k, T)
     d1 = torch.empty(Cin, B, Tp, device=DEV)
     d2 = torch.empty_like(d1)
     K.conv_dgrad(wg, dy, d1, Cin)
     emu.conv_dgrad(wg, dy, d2, Cin)
-    close(d1, d2, 1e-5, "dgrad")
+    close(d1[:, :, :T], d2[:, :, :T], 1e-5, "dgrad")
     w1 = torch.empty(k, Cout, Cin_p, device=DEV)
     w2 = torch.empty_like(w1)
     K.conv_wgrad(dy, act, w1, Cin)
@@ -197,8 +203,8 @@ def test_gn_act_fwd_bwd(case, dtype, P, T):
 
 @pytest.mark.parametrize("loss", ["MSE", "MAE", "smoothL1", "Huber"])
 @pytest.mark.parametrize("with_ext,one_pass", [(False, False), (True, False), (False, True)])
-@pytest.mark.parametrize("T", [21, 24])          # 24: the float4 path of the external layout (T % 4 == 0)
-def test_recon_fwd_bwd(loss, with_ext, one_pass, T):
+@pytest.mark.parametrize("T,y_bf16", [(21, False), (24, False), (24, True), (21, True)])   # 24: fast path (T % 8 == 0)
+def test_recon_fwd_bwd(loss, with_ext, one_pass, T, y_bf16):
     N, B, G = 40, 3, 8
     Tp = tp_of(T)
     kind = K.LOSS_KINDS[loss]
@@ -207,6 +213,9 @@ def test_recon_fwd_bwd(loss, with_ext, one_pass, T):
     x = rnd(B, N, T, seed=4) * 1.5
     stats = torch.empty(B, G, 2, device=DEV)
     K.gn_stats(y, stats, T, G)
+    if y_bf16:                       # bf16-stored pre-norm output; the model recomputes the statistics from what it is given
+        y = y.to(torch.bfloat16)
+        K.gn_stats(y.float(), stats, T, G)
     xh1, xh2 = torch.empty(B, N, T, device=DEV), torch.empty(B, N, T, device=DEV)
     s1, s2 = (torch.empty(2, device=DEV, dtype=torch.float64) for _ in range(2))
     rowsums = torch.full((N * B, 4), 9.0, device=DEV) if one_pass else None
@@ -220,12 +229,12 @@ def test_recon_fwd_bwd(loss, with_ext, one_pass, T):
     inv = 1.0 / (B * N * T)
     outs = []
     for fn in (K.recon_bwd, emu.recon_bwd):
-        dy = torch.full((1, N, B, Tp), 9.0, device=DEV)
+        dy = torch.full((1, N, B, Tp), 9.0, device=DEV, dtype=torch.bfloat16 if y_bf16 else torch.float32)
         dg, db, dbi = (torch.empty(N, device=DEV) for _ in range(3))
         fn(y, stats, gamma, beta, x, g_loss, g_mse, inv, ext, dy, dg, db, dbi, T, G, kind, rowsums)
-        outs.append((dy, dg, db, dbi))
+        outs.append((dy.float(), dg, db, dbi))
     for a, b, nm in zip(outs[0], outs[1], ("dy", "dgamma", "dbeta", "dbias")):
-        close(a, b, 5e-5, nm)
+        close(a, b, 5e-3 if (y_bf16 and nm in ("dy", "dbias")) else 5e-5, nm)
     # ext-only path (decoder used without the fused loss)
     if with_ext:
         outs = []
