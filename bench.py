@@ -212,7 +212,7 @@ def _main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("SIMULGEN_BENCH_BATCH", "32")), help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("SIMULGEN_BENCH_BATCH", "64")), help="per-GPU batch")
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--nodes", type=int, default=HEADLINE["num_node"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -345,18 +345,28 @@ def _main():
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md sustained ~1.4 PF)"
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None          # DRAM bytes per GEMM launch from the committed ncu capture of this very command line
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_traffic_b64.json")))
+        if tr.get("per_gpu_batch") == B and cfg["num_node"] == HEADLINE["num_node"]:
+            traffic = tr["gemm_dram_bytes_per_launch"]
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": workload, "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2_policy": "inputs larger than L2 (%.0f MB per batch, 4 batches cycled)" % (pool[0].numel() * 4 / 1e6),
-                   "gflop_per_sample_fwd_bwd": gflop, "loss": scalars[0], "grad_norm": scalars[4]},
+                   "gflop_per_sample_fwd_bwd": gflop, "loss": scalars[0], "grad_norm": scalars[4],
+                   "notes": "x_hat is not written to HBM by the training step (train.py:142 discards it); the recon layer's "
+                            "pre-norm output is stored as bf16; gpu_launches counts C-ABI calls (each >= 1 kernel)"},
         "clocks": clocks,
         "gpu_launches": launches,
         "step_tensor_frac": value / world * gflop * 1e9 / (peak * 1e12),
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_tc_kernel (tcgen05 implicit-GEMM fprop/dgrad/wgrad)",
-                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                     "algorithmic_flop_per_launch": gemm_flops / max(len(prof), 1),
                      "peak_source": peak_src, "launches_timed": len(prof),
                      "share_of_step": gemm_ms / ms if ms > 0 else None},
     }

@@ -255,6 +255,7 @@ class Ctx:
         self.pgrads = {}
         self.capture = capture
         self.sink = get_grad_sink() if record else None
+        self._side_used = False
         self.prepared = {}              # id(module) -> _Prep from the batched preparation
         self.prep_record = []           # (module, kind) in execution order when preparing layer by layer
         self.prep_root = None
@@ -313,6 +314,60 @@ class Ctx:
         for fn in reversed(self.tape):
             fn()
         self.tape = None
+        self.join_side()
+
+    # -- weight-gradient stream -----------------------------------------------------------------------
+    # The wgrad GEMM of a layer only feeds the optimiser, while the activation-gradient chain
+    # (GroupNorm/activation backward -> dgrad -> next layer) is what the rest of backward waits for.  wgrad and the
+    # spectral-norm gradient therefore run on a second stream: the two tensor-core GEMMs still take turns on the
+    # SMs (each persistent CTA needs > 200 KB of shared memory), but the HBM-bound streaming kernels of the chain
+    # co-reside with whichever GEMM is running instead of waiting behind it.
+    def side(self, *tensors):
+        """Context manager: run the enclosed launches on the weight-gradient stream, after everything issued so far
+        on the current stream; `tensors` are marked as in use by that stream (caching-allocator safety)."""
+        return _SideStream(self, tensors)
+
+    def join_side(self):
+        if self._side_used:
+            torch.cuda.current_stream(self.dev).wait_stream(_side_stream_of(self.dev))
+            self._side_used = False
+
+
+_SIDE_STREAMS = {}
+_OVERLAP_WGRAD = os.environ.get("SIMULGEN_B200_OVERLAP_WGRAD", "0") != "0"   # measured: +1-2 % at best (the step is power-bound), off by default
+
+
+def _side_stream_of(dev):
+    key = (dev.type, dev.index)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=dev)
+        _SIDE_STREAMS[key] = st
+    return st
+
+
+class _SideStream:
+    def __init__(self, ctx, tensors):
+        self.ctx, self.tensors = ctx, tensors
+        self.active = _OVERLAP_WGRAD and ctx.dev.type == "cuda"
+        self.cm = None
+
+    def __enter__(self):
+        if self.active:
+            side = _side_stream_of(self.ctx.dev)
+            side.wait_stream(torch.cuda.current_stream(self.ctx.dev))
+            for t in self.tensors:
+                if t is not None:
+                    t.record_stream(side)
+            self.cm = torch.cuda.stream(side)
+            self.cm.__enter__()
+            self.ctx._side_used = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.cm is not None:
+            self.cm.__exit__(*exc)
+        return False
 
 
 # ------------------------------------------------------------------------------------------------
@@ -550,13 +605,18 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
                 ctx.set_pgrad(gn.weight, dgamma)
                 ctx.set_pgrad(gn.bias, dbeta)
             ctx.set_pgrad(conv.bias, dbias)
-            if p.w.requires_grad:
-                dwg = ctx.weight_grad_buf(p, p.k, p.Cout, p.Cin_p)
-                K.conv_wgrad(dy, a_in.data, dwg, p.Cin)
-                _weight_grad(ctx, conv, p, dwg)
+            # dgrad first (the chain waits for it), after the previous layer's wgrad has left the SMs: the two
+            # tensor-core GEMMs never compete; this layer's wgrad then runs on the side stream underneath the NEXT
+            # layer's (HBM-bound) GroupNorm / activation backward
             if a_in.needs_grad:
+                ctx.join_side()
                 dx, acc_in = ctx.grad_buf(a_in)
                 K.conv_dgrad(p.wg, dy, dx, p.Cin, bool(acc_in))
+            if p.w.requires_grad:
+                with ctx.side(dy, a_in.data):
+                    dwg = ctx.weight_grad_buf(p, p.k, p.Cout, p.Cin_p)
+                    K.conv_wgrad(dy, a_in.data, dwg, p.Cin)
+                    _weight_grad(ctx, conv, p, dwg)
         ctx.tape.append(bwd)
     return out
 
@@ -785,12 +845,13 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
             ctx.set_pgrad(gn.weight, dgamma)
             ctx.set_pgrad(gn.bias, dbeta)
             ctx.set_pgrad(conv.bias, dbias)
-            if p.w.requires_grad:
-                dwg = ctx.weight_grad_buf(p, p.k, p.Cout, p.Cin_p)
-                K.conv_wgrad(dy, out.data, dwg, p.Cin)
-                _weight_grad(ctx, conv, p, dwg)
             dx, acc = ctx.grad_buf(out)
             K.conv_dgrad(p.wg, dy, dx, p.Cin, bool(acc))
+            if p.w.requires_grad:
+                with ctx.side(dy, out.data):
+                    dwg = ctx.weight_grad_buf(p, p.k, p.Cout, p.Cin_p)
+                    K.conv_wgrad(dy, out.data, dwg, p.Cin)
+                    _weight_grad(ctx, conv, p, dwg)
         ctx.tape.append(recon_bwd)
     return res
 
