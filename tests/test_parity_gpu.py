@@ -211,3 +211,35 @@ def test_trainer_fused_step_equals_per_tensor_path(precision):
         assert rel_l2(sa[k], sb[k]) < tol, (k, rel_l2(sa[k], sb[k]))
     for a, b in zip(ca, cb):
         assert abs(a - b) <= tol * abs(b) + 1e-12
+
+
+@pytest.mark.parametrize("name", ["toy3_small_mse", "toy4_large_mae"])
+def test_export_path_encoder_then_decoder_fix_mode(name):
+    """The inference / latent-export callers (utils.py:492-499, reconstruction_evaluator.py:174,
+    latent_conditioner_e2e.py:371): `mu, log_var, xs = VAE.encoder(x)` then `VAE.decoder(mu, xs, mode='fix')` under
+    eval() and no_grad; also with a 3-entry xs list of which only the first entries are read."""
+    g = load_golden(name)
+    cfg = g["cfg"]
+    sg.set_precision("fp32")
+    sd = dict(g["state_dict"])
+    sd.update(g["uv_after"])
+    m = build_engine_vae(cfg, sd)
+    m.eval()
+    x = g["x"].to(DEV)
+    with torch.no_grad():
+        mu, log_var, xs = m.encoder(x)
+        x_hat, kls = m.decoder(mu, xs, mode="fix")
+        x_hat3, _ = m.decoder(mu, list(xs) + [xs[-1]] * 2, mode="fix")
+    osd = {k: v.to(DEV) for k, v in sd.items()}
+    with torch.no_grad():
+        omu, olv, oxs = O.encoder_forward(osd, x, cfg["latent_dim"], training=False)
+        eps = [torch.zeros(s, device=DEV) for s in O.eps_shapes(cfg, x.shape[0])[1:]]
+        oxh, okls = O.decoder_forward(osd, omu, oxs, eps, cfg["num_time"], training=False, mode="fix")
+    assert rel_l2(mu, omu) < 1e-5 and rel_l2(log_var, olv) < 1e-5
+    assert len(xs) == len(oxs)
+    for a, b in zip(xs, oxs):
+        assert rel_l2(a, b) < 1e-5
+    assert rel_l2(x_hat, oxh) < 1e-5
+    assert torch.equal(x_hat, x_hat3)
+    for a, b in zip(kls, okls):
+        assert rel_l2(a, b) < 1e-5
