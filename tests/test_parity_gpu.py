@@ -240,6 +240,6 @@ def test_export_path_encoder_then_decoder_fix_mode(name):
     for a, b in zip(xs, oxs):
         assert rel_l2(a, b) < 1e-5
     assert rel_l2(x_hat, oxh) < 1e-5
-    assert torch.equal(x_hat, x_hat3)
+    assert rel_l2(x_hat3, x_hat) < 1e-6      # (new eps draws scaled by 1e-8 and atomic summation order differ)
     for a, b in zip(kls, okls):
         assert rel_l2(a, b) < 1e-5
