@@ -62,20 +62,22 @@ if want("recon"):
     gamma, beta = torch.ones(N, device=dev), torch.zeros(N, device=dev)
     stats = torch.empty(B, G, 2, device=dev)
     report("gn_stats (recon y)", timed(lambda: K.gn_stats(y, stats, T, G)), y.numel() * 4)
+    y = y.to(BF)                                   # bf16 mode stores the recon layer's pre-norm output as bf16
+    ybytes = 2
     x_hat = torch.empty(B, N, T, device=dev)
     sums = torch.empty(2, device=dev, dtype=torch.float64)
     rows = torch.empty(N * B, 4, device=dev)
     report("recon_fwd (x_hat + rowsums)", timed(lambda: K.recon_fwd(y, stats, gamma, beta, x, x_hat, sums, T, G, 0, rows)),
-           y.numel() * 4 + x.numel() * 8 + rows.numel() * 4)
+           y.numel() * ybytes + x.numel() * 8 + rows.numel() * 4)
     report("recon_fwd (no x_hat)", timed(lambda: K.recon_fwd(y, stats, gamma, beta, x, None, sums, T, G, 0, rows)),
-           y.numel() * 4 + x.numel() * 4 + rows.numel() * 4)
+           y.numel() * ybytes + x.numel() * 4 + rows.numel() * 4)
     del x_hat
     dy = torch.empty(1, N, B, Tp, device=dev, dtype=BF)
     dg, db, dbi = (torch.empty(N, device=dev) for _ in range(3))
     gl, gm = torch.tensor([1e6], device=dev), torch.tensor([0.0], device=dev)
     inv = 1.0 / (B * N * T)
     report("recon_bwd (one pass)", timed(lambda: K.recon_bwd(y, stats, gamma, beta, x, gl, gm, inv, None, dy, dg, db, dbi, T, G, 0, rows)),
-           y.numel() * 4 + x.numel() * 4 + dy.numel() * 2 + rows.numel() * 4)
+           y.numel() * ybytes + x.numel() * 4 + dy.numel() * 2 + rows.numel() * 4)
     del y, dy, rows, x
 if want("gn_act"):
     for C, P, res in ((5120, 5, False), (5120, 1, False), (1024, 1, True)):

@@ -514,65 +514,99 @@ recon_fwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const f
 // padding) and 16-byte aligned external rows.  No per-element predicates and 32-bit row arithmetic: the generic
 // kernel above spends ~190 of its ~370 instructions per row on index math and predication and is issue-bound
 // (ncu: issue slots 65 % busy at 58 % DRAM throughput).
+// kRowsInFlight rows per warp iteration: all their loads are issued before the first dependent instruction, which
+// doubles the bytes each warp keeps in flight (one 200-element row is only 1.2 KB of loads per warp, too little
+// to cover the HBM latency at the occupancy these kernels reach).  A lane-per-row mapping (each lane walking its own
+// row, no shuffles, all 32 lanes busy) was measured 2-5x SLOWER: 32 different cache lines per load instruction
+// times ~48 resident warps overflow L1 before a line is consumed.
+constexpr int kRowsInFlight = 2;
+
 template <typename YT, bool MSE, bool ROWSUMS, bool XHAT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 recon_fwd_fast_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                       const float* __restrict__ beta, const float* __restrict__ x, float* __restrict__ x_hat,
                       double* __restrict__ loss_sums, float4* __restrict__ rowsums, int N, int B, int T, int Tp, int G,
                       int loss_kind) {
+    constexpr int R = kRowsInFlight;
     __shared__ double shm[2][32];
     const int lane = threadIdx.x & 31;
     const int Cg = N / G;
     const int rows = N * B, wstride = gridDim.x * kWarpsPerBlock;
     const int nseg = T >> 3;
     double d0 = 0.0, d1 = 0.0;
-    for (int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
-        const int n = row / B, b = row - n * B;
-        const float2 st = __ldg(reinterpret_cast<const float2*>(mr) + (b * G + n / Cg));
-        const float rstd = st.y;
-        const float a = __ldg(gamma + n) * rstd, sh = __ldg(beta + n) - st.x * a;
-        const float nm = -st.x * rstd;
-        const YT* yrow = y + (size_t)row * Tp;
-        const size_t xo = ((size_t)b * N + n) * T;
-        float l0 = 0.f, l1 = 0.f, aL = 0.f, bL = 0.f, aM = 0.f, bM = 0.f;
-        for (int seg = lane; seg < nseg; seg += 32) {
-            const F8 yv = load8(yrow + seg * 8);
-            const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + xo + seg * 8));
-            const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + xo + seg * 8 + 4));
-            const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-            float h[8];
+    for (int row0 = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row0 < rows; row0 += R * wstride) {
+        float a[R], sh[R], rstd[R], nm[R];
+        const YT* yrow[R];
+        size_t xo[R];
+        bool ok[R];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                h[i] = tanh_fast(fmaf(yv.v[i], a, sh));
-                const float d = h[i] - xv[i];
-                l1 = fmaf(d, d, l1);
-                if (!MSE) l0 += loss_term(loss_kind, d);
-                if (ROWSUMS) {
-                    const float om = fmaf(-h[i], h[i], 1.f);
-                    const float xn = fmaf(yv.v[i], rstd, nm);
-                    const float gm = d * om;
-                    aM += gm;
-                    bM = fmaf(gm, xn, bM);
-                    if (!MSE) {
-                        const float gl = loss_grad(loss_kind, d) * om;
-                        aL += gl;
-                        bL = fmaf(gl, xn, bL);
+        for (int r = 0; r < R; ++r) {
+            const int row = row0 + r * wstride;
+            ok[r] = row < rows;
+            const int rr = ok[r] ? row : row0;
+            const int n = rr / B, b = rr - n * B;
+            const float2 st = __ldg(reinterpret_cast<const float2*>(mr) + (b * G + n / Cg));
+            rstd[r] = st.y;
+            a[r] = __ldg(gamma + n) * st.y;
+            sh[r] = __ldg(beta + n) - st.x * a[r];
+            nm[r] = -st.x * st.y;
+            yrow[r] = y + (size_t)rr * Tp;
+            xo[r] = ((size_t)b * N + n) * T;
+        }
+        float l0[R], l1[R], aL[R], bL[R], aM[R], bM[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { l0[r] = l1[r] = aL[r] = bL[r] = aM[r] = bM[r] = 0.f; }
+        for (int seg = lane; seg < nseg; seg += 32) {
+            F8 yv[R];
+            float4 x0[R], x1[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {                    // every load of every row first
+                yv[r] = load8(yrow[r] + seg * 8);
+                x0[r] = __ldg(reinterpret_cast<const float4*>(x + xo[r] + seg * 8));
+                x1[r] = __ldg(reinterpret_cast<const float4*>(x + xo[r] + seg * 8 + 4));
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float xv[8] = {x0[r].x, x0[r].y, x0[r].z, x0[r].w, x1[r].x, x1[r].y, x1[r].z, x1[r].w};
+                float h[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    h[i] = tanh_fast(fmaf(yv[r].v[i], a[r], sh[r]));
+                    const float d = h[i] - xv[i];
+                    l1[r] = fmaf(d, d, l1[r]);
+                    if (!MSE) l0[r] += loss_term(loss_kind, d);
+                    if (ROWSUMS) {
+                        const float om = fmaf(-h[i], h[i], 1.f);
+                        const float xn = fmaf(yv[r].v[i], rstd[r], nm[r]);
+                        const float gm = d * om;
+                        aM[r] += gm;
+                        bM[r] = fmaf(gm, xn, bM[r]);
+                        if (!MSE) {
+                            const float gl = loss_grad(loss_kind, d) * om;
+                            aL[r] += gl;
+                            bL[r] = fmaf(gl, xn, bL[r]);
+                        }
                     }
                 }
-            }
-            if (XHAT) {
-                *reinterpret_cast<float4*>(x_hat + xo + seg * 8) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(x_hat + xo + seg * 8 + 4) = make_float4(h[4], h[5], h[6], h[7]);
+                if (XHAT && ok[r]) {
+                    *reinterpret_cast<float4*>(x_hat + xo[r] + seg * 8) = make_float4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4*>(x_hat + xo[r] + seg * 8 + 4) = make_float4(h[4], h[5], h[6], h[7]);
+                }
             }
         }
-        if (ROWSUMS) {
-            aM = 2.f * warp_sum(aM);
-            bM = 2.f * warp_sum(bM);
-            if (MSE) { aL = aM; bL = bM; } else { aL = warp_sum(aL); bL = warp_sum(bL); }
-            if (lane == 0) rowsums[row] = make_float4(aL, bL, aM, bM);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (ROWSUMS) {
+                float am = 2.f * warp_sum(aM[r]), bm = 2.f * warp_sum(bM[r]);
+                float al = am, bl = bm;
+                if (!MSE) { al = warp_sum(aL[r]); bl = warp_sum(bL[r]); }
+                if (lane == 0 && ok[r]) rowsums[row0 + r * wstride] = make_float4(al, bl, am, bm);
+            }
+            if (ok[r]) {
+                d0 += (double)(MSE ? l1[r] : l0[r]);
+                d1 += (double)l1[r];
+            }
         }
-        d0 += (double)(MSE ? l1 : l0);
-        d1 += (double)l1;
     }
     double t0 = block_sum(d0, shm[0]);
     double t1 = block_sum(d1, shm[1]);
@@ -583,54 +617,86 @@ recon_fwd_fast_kernel(const YT* __restrict__ y, const float* __restrict__ mr, co
 }
 
 template <typename YT, typename OT, bool MSE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 recon_bwd_apply_fast_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                             const float* __restrict__ beta, const float* __restrict__ x, const float* __restrict__ scal,
                             const double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias, int N, int B,
                             int T, int Tp, int G, int loss_kind, float inv_n) {
+    constexpr int R = kRowsInFlight;
     const int lane = threadIdx.x & 31;
     const int Cg = N / G;
     const int rows = N * B, wstride = gridDim.x * kWarpsPerBlock;
     const int nseg = T >> 3, nseg_p = Tp >> 3;
     const float ga = scal[0], gm = scal[1];
     const float g2 = 2.f * (ga + gm);
-    for (int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
-        const int n = row / B, b = row - n * B;
-        const int g = n / Cg;
-        const float2 st = __ldg(reinterpret_cast<const float2*>(mr) + (b * G + g));
-        const float mean = st.x, rstd = st.y;
-        const float gam = __ldg(gamma + n);
-        const float a = gam * rstd, sh = __ldg(beta + n) - mean * a;
-        const float m1 = (float)S[(size_t)(b * G + g) * 2] * inv_n;
-        const float m2 = (float)S[(size_t)(b * G + g) * 2 + 1] * inv_n;
-        const float c1 = rstd * gam, c2 = -rstd * rstd * m2, c3 = rstd * (mean * rstd * m2 - m1);
-        const YT* yrow = y + (size_t)row * Tp;
-        OT* drow = dy + (size_t)row * Tp;
-        const size_t xo = ((size_t)b * N + n) * T;
-        float db = 0.f;
-        for (int seg = lane; seg < nseg_p; seg += 32) {
-            F8 o;
-            if (seg < nseg) {
-                const F8 yv = load8(yrow + seg * 8);
-                const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + xo + seg * 8));
-                const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + xo + seg * 8 + 4));
-                const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    for (int row0 = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row0 < rows; row0 += R * wstride) {
+        float a[R], sh[R], c1[R], c2[R], c3[R], db[R];
+        const YT* yrow[R];
+        OT* drow[R];
+        size_t xo[R];
+        int nn[R];
+        bool ok[R];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float h = tanh_fast(fmaf(yv.v[i], a, sh));
-                    const float d = h - xv[i];
-                    const float gg = (MSE ? g2 * d : ga * loss_grad(loss_kind, d) + gm * 2.f * d) * fmaf(-h, h, 1.f);
-                    o.v[i] = fmaf(c1, gg, fmaf(c2, yv.v[i], c3));
-                    db += o.v[i];
+        for (int r = 0; r < R; ++r) {
+            const int row = row0 + r * wstride;
+            ok[r] = row < rows;
+            const int rr = ok[r] ? row : row0;
+            const int n = rr / B, b = rr - n * B;
+            const int g = n / Cg;
+            const float2 st = __ldg(reinterpret_cast<const float2*>(mr) + (b * G + g));
+            const float mean = st.x, rstd = st.y;
+            const float gam = __ldg(gamma + n);
+            a[r] = gam * rstd;
+            sh[r] = __ldg(beta + n) - mean * a[r];
+            const float m1 = (float)S[(size_t)(b * G + g) * 2] * inv_n;
+            const float m2 = (float)S[(size_t)(b * G + g) * 2 + 1] * inv_n;
+            c1[r] = rstd * gam;
+            c2[r] = -rstd * rstd * m2;
+            c3[r] = rstd * (mean * rstd * m2 - m1);
+            yrow[r] = y + (size_t)rr * Tp;
+            drow[r] = dy + (size_t)rr * Tp;
+            xo[r] = ((size_t)b * N + n) * T;
+            nn[r] = n;
+            db[r] = 0.f;
+        }
+        for (int seg = lane; seg < nseg_p; seg += 32) {
+            if (seg < nseg) {
+                F8 yv[R];
+                float4 x0[R], x1[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    yv[r] = load8(yrow[r] + seg * 8);
+                    x0[r] = __ldg(reinterpret_cast<const float4*>(x + xo[r] + seg * 8));
+                    x1[r] = __ldg(reinterpret_cast<const float4*>(x + xo[r] + seg * 8 + 4));
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float xv[8] = {x0[r].x, x0[r].y, x0[r].z, x0[r].w, x1[r].x, x1[r].y, x1[r].z, x1[r].w};
+                    F8 o;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float h = tanh_fast(fmaf(yv[r].v[i], a[r], sh[r]));
+                        const float d = h - xv[i];
+                        const float gg = (MSE ? g2 * d : ga * loss_grad(loss_kind, d) + gm * 2.f * d) * fmaf(-h, h, 1.f);
+                        o.v[i] = fmaf(c1[r], gg, fmaf(c2[r], yv[r].v[i], c3[r]));
+                        db[r] += o.v[i];
+                    }
+                    if (ok[r]) store8(drow[r] + seg * 8, o);
                 }
             } else {
+                F8 o;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (ok[r]) store8(drow[r] + seg * 8, o);
             }
-            store8(drow + seg * 8, o);
         }
-        db = warp_sum(db);
-        if (lane == 0) atomicAdd(&dbias[n], db);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float t = warp_sum(db[r]);
+            if (lane == 0 && ok[r]) atomicAdd(&dbias[nn[r]], t);
+        }
     }
 }
 
