@@ -279,27 +279,35 @@ struct BwdArgs {
     double inv_n;
 };
 
-// One fully/partially valid 8-element segment: dyh = dL/d(gamma*xhat+beta), xhat, dpre (gradient wrt the residual input)
-template <typename RT, int ACT, bool POST>
-__device__ __forceinline__ void bwd_segment(const BwdArgs& p, long long row, int seg, float a, float sh, float mean, float rstd,
-                                            F8& dyh, F8& xhat, F8& dpre) {
-    F8 yv = load8(p.y + row * p.Tp + seg * 8);
-    F8 dv = load8(p.dout + row * p.Tp + seg * 8);
-    F8 rv;
+// One fully/partially valid 8-element segment, split into a load phase and a compute phase so that the loads of
+// several rows can be issued before the first dependent instruction.
+struct SegIn {
+    F8 yv, dv, rv;
+};
+template <typename RT, bool POST>
+__device__ __forceinline__ void bwd_load(const BwdArgs& p, long long row, int seg, SegIn& in) {
+    in.yv = load8(p.y + row * p.Tp + seg * 8);
+    in.dv = load8(p.dout + row * p.Tp + seg * 8);
     const RT* res = reinterpret_cast<const RT*>(p.res);
-    if (POST && res != nullptr) rv = load8(res + row * p.Tp + seg * 8);
+    if (POST && res != nullptr) in.rv = load8(res + row * p.Tp + seg * 8);
+}
+// dyh = dL/d(gamma*xhat+beta), xhat, dpre (gradient wrt the residual input)
+template <int ACT, bool POST>
+__device__ __forceinline__ void bwd_compute(const BwdArgs& p, const SegIn& in, int seg, float a, float sh, float mean, float rstd,
+                                            F8& dyh, F8& xhat, F8& dpre) {
+    const bool has_res = p.res != nullptr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        float yh = yv.v[i] * a + sh;
+        float yh = fmaf(in.yv.v[i], a, sh);
         float val, dval;
         act_both_t<ACT>(yh, val, dval);
-        float dp = dv.v[i];
+        float dp = in.dv.v[i];
         if (POST) {
-            float pre = p.res_scale * val + (res != nullptr ? rv.v[i] : 0.f);
+            float pre = p.res_scale * val + (has_res ? in.rv.v[i] : 0.f);
             dp *= gelu_grad_f(pre);
         }
         dyh.v[i] = p.res_scale * dp * dval;
-        xhat.v[i] = (yv.v[i] - mean) * rstd;
+        xhat.v[i] = (in.yv.v[i] - mean) * rstd;
         dpre.v[i] = dp;
     }
     if (seg * 8 + 8 > p.T) {
@@ -309,36 +317,73 @@ __device__ __forceinline__ void bwd_segment(const BwdArgs& p, long long row, int
     }
 }
 
+// Work decomposition of the backward kernels: a warp takes one (channel, chunk of <= kChunkB samples) task and walks
+// the chunk's rows - contiguous in memory - kRowsInFlight at a time.  Channel constants are loaded once per task,
+// there is no per-row index division, and the per-channel sums (dgamma, dbeta, dbias) cost one atomic per task.
+constexpr int kChunkB = 16;
+constexpr int kRowsInFlight = 2;
+
 // pass 1 (GroupNorm layers only): dgamma[c] += sum dyh*xhat, dbeta[c] += sum dyh, S[b][g] += gamma_c * (those)
 template <typename RT, int ACT, bool POST>
 __global__ void __launch_bounds__(kThreads)
 gn_bwd_reduce_kernel(BwdArgs p, float* __restrict__ dgamma, float* __restrict__ dbeta, double* __restrict__ S) {
+    constexpr int R = kRowsInFlight;
     const int lane = threadIdx.x & 31;
     const int Cg = p.C / p.G;
-    const long long rows = (long long)p.C * p.B, wstride = (long long)gridDim.x * kWarpsPerBlock;
-    for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
-        int c = (int)(row / p.B), b = (int)(row % p.B);
-        int g = c / Cg;
-        float2 st = *reinterpret_cast<const float2*>(p.mr + 2 * (b * p.G + g));
-        float gm = p.gamma[c];
-        float a = gm * st.y, sh = p.beta[c] - st.x * a;
-        float A = 0.f, Bx = 0.f;
-        for (int seg = lane; seg * 8 < p.T; seg += 32) {
-            F8 dyh, xhat, dpre;
-            bwd_segment<RT, ACT, POST>(p, row, seg, a, sh, st.x, st.y, dyh, xhat, dpre);
+    const int nchunk = (p.B + kChunkB - 1) / kChunkB;
+    const int tasks = p.C * nchunk, wstride = gridDim.x * kWarpsPerBlock;
+    const float2* mr2 = reinterpret_cast<const float2*>(p.mr);
+    for (int task = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < tasks; task += wstride) {
+        const int c = task / nchunk, ch = task - c * nchunk;
+        const int b_lo = ch * kChunkB, b_hi = min(p.B, b_lo + kChunkB);
+        const int g = c / Cg;
+        const float gm = __ldg(p.gamma + c), bt = __ldg(p.beta + c);
+        float sumA = 0.f, sumB = 0.f;
+        for (int b0 = b_lo; b0 < b_hi; b0 += R) {
+            float a[R], sh[R], mean[R], rstd[R], A[R], Bx[R];
+            bool ok[R];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                A += dyh.v[i];
-                Bx += dyh.v[i] * xhat.v[i];
+            for (int r = 0; r < R; ++r) {
+                ok[r] = b0 + r < b_hi;
+                const float2 st = __ldg(mr2 + (ok[r] ? b0 + r : b0) * p.G + g);
+                mean[r] = st.x;
+                rstd[r] = st.y;
+                a[r] = gm * st.y;
+                sh[r] = bt - st.x * a[r];
+                A[r] = 0.f;
+                Bx[r] = 0.f;
+            }
+            for (int seg = lane; seg * 8 < p.T; seg += 32) {
+                SegIn in[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) bwd_load<RT, POST>(p, (long long)c * p.B + (ok[r] ? b0 + r : b0), seg, in[r]);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    F8 dyh, xhat, dpre;
+                    bwd_compute<ACT, POST>(p, in[r], seg, a[r], sh[r], mean[r], rstd[r], dyh, xhat, dpre);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        A[r] += dyh.v[i];
+                        Bx[r] = fmaf(dyh.v[i], xhat.v[i], Bx[r]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float sa = warp_sum(A[r]), sb = warp_sum(Bx[r]);
+                if (ok[r]) {
+                    sumA += sa;
+                    sumB += sb;
+                    if (lane == 0) {
+                        atomicAdd(&S[(size_t)((b0 + r) * p.G + g) * 2], (double)(gm * sa));
+                        atomicAdd(&S[(size_t)((b0 + r) * p.G + g) * 2 + 1], (double)(gm * sb));
+                    }
+                }
             }
         }
-        A = warp_sum(A);
-        Bx = warp_sum(Bx);
         if (lane == 0) {
-            atomicAdd(&dgamma[c], Bx);
-            atomicAdd(&dbeta[c], A);
-            atomicAdd(&S[(size_t)(b * p.G + g) * 2], (double)(gm * A));
-            atomicAdd(&S[(size_t)(b * p.G + g) * 2 + 1], (double)(gm * Bx));
+            atomicAdd(&dgamma[c], sumB);
+            atomicAdd(&dbeta[c], sumA);
         }
     }
 }
@@ -348,6 +393,7 @@ template <typename OT, typename RT, int ACT, bool POST>
 __global__ void __launch_bounds__(kThreads)
 gn_bwd_apply_kernel(BwdArgs p, const double* __restrict__ S, OT* __restrict__ dy, int planes, long long pstride,
                     float* __restrict__ dbias, float* __restrict__ dres, int dres_accumulate) {
+    constexpr int R = kRowsInFlight;
     extern __shared__ float sg_rows[];
     const int lane = threadIdx.x & 31;
     float* srow = sg_rows + (threadIdx.x >> 5) * (p.Tp + 8);
@@ -357,30 +403,44 @@ gn_bwd_apply_kernel(BwdArgs p, const double* __restrict__ S, OT* __restrict__ dy
     if (multi && !shfl) srow_clear_halo(srow, p.Tp, lane);
     const bool has_gn = p.mr != nullptr;
     const int Cg = has_gn ? p.C / p.G : 1;
-    const long long rows = (long long)p.C * p.B, wstride = (long long)gridDim.x * kWarpsPerBlock;
-    for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
-        int c = (int)(row / p.B), b = (int)(row % p.B);
-        float a = 1.f, sh = 0.f, mean = 0.f, rstd = 1.f, gm = 1.f, m1 = 0.f, m2 = 0.f;
-        if (has_gn) {
-            int g = c / Cg;
-            float2 st = *reinterpret_cast<const float2*>(p.mr + 2 * (b * p.G + g));
-            gm = p.gamma[c];
-            mean = st.x;
-            rstd = st.y;
-            a = gm * rstd;
-            sh = p.beta[c] - mean * a;
-            m1 = (float)(S[(size_t)(b * p.G + g) * 2] * p.inv_n);
-            m2 = (float)(S[(size_t)(b * p.G + g) * 2 + 1] * p.inv_n);
-        }
+    const int nchunk = (p.B + kChunkB - 1) / kChunkB;
+    const int tasks = p.C * nchunk, wstride = gridDim.x * kWarpsPerBlock;
+    const float2* mr2 = reinterpret_cast<const float2*>(p.mr);
+    const float inv_n = (float)p.inv_n;
+    for (int task = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < tasks; task += wstride) {
+        const int c = task / nchunk, ch = task - c * nchunk;
+        const int b_lo = ch * kChunkB, b_hi = min(p.B, b_lo + kChunkB);
+        const int g = has_gn ? c / Cg : 0;
+        const float gm = has_gn ? __ldg(p.gamma + c) : 1.f, bt = has_gn ? __ldg(p.beta + c) : 0.f;
         float db = 0.f;
-        auto compute = [&](int seg, F8& o, F8& dpre) {
-            if (seg * 8 < p.T) {
+        for (int b0 = b_lo; b0 < b_hi; b0 += R) {
+            float a[R], sh[R], mean[R], rstd[R], m1[R], m2[R];
+            bool ok[R];
+            long long row[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                ok[r] = b0 + r < b_hi;
+                const int bb = ok[r] ? b0 + r : b0;
+                row[r] = (long long)c * p.B + bb;
+                a[r] = 1.f; sh[r] = 0.f; mean[r] = 0.f; rstd[r] = 1.f; m1[r] = 0.f; m2[r] = 0.f;
+                if (has_gn) {
+                    const float2 st = __ldg(mr2 + bb * p.G + g);
+                    mean[r] = st.x;
+                    rstd[r] = st.y;
+                    a[r] = gm * st.y;
+                    sh[r] = bt - st.x * a[r];
+                    m1[r] = (float)S[(size_t)(bb * p.G + g) * 2] * inv_n;
+                    m2[r] = (float)S[(size_t)(bb * p.G + g) * 2 + 1] * inv_n;
+                }
+            }
+            // one segment of one row: gradient wrt the conv output (o) and wrt the residual input (dpre)
+            auto finish = [&](int r, int seg, const SegIn& in, F8& o, F8& dpre) {
                 F8 dyh, xhat;
-                bwd_segment<RT, ACT, POST>(p, row, seg, a, sh, mean, rstd, dyh, xhat, dpre);
+                bwd_compute<ACT, POST>(p, in, seg, a[r], sh[r], mean[r], rstd[r], dyh, xhat, dpre);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     float v = dyh.v[i];
-                    if (has_gn) v = rstd * (gm * v - m1 - xhat.v[i] * m2);
+                    if (has_gn) v = rstd[r] * (gm * v - m1[r] - xhat.v[i] * m2[r]);
                     o.v[i] = v;
                 }
                 if (has_gn && seg * 8 + 8 > p.T) {
@@ -388,49 +448,75 @@ gn_bwd_apply_kernel(BwdArgs p, const double* __restrict__ S, OT* __restrict__ dy
                     for (int i = 0; i < 8; ++i)
                         if (seg * 8 + i >= p.T) o.v[i] = 0.f;
                 }
+                if (ok[r]) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) db += o.v[i];
+                    for (int i = 0; i < 8; ++i) db += o.v[i];
+                }
+            };
+            auto store_dres = [&](int r, int seg, F8& dpre) {
+                if (dres != nullptr && ok[r]) {
+                    float* dr = dres + row[r] * p.Tp + seg * 8;
+                    if (dres_accumulate) {
+                        F8 old = load8(dr);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dpre.v[i] += old.v[i];
+                    }
+                    store8(dr, dpre);
+                }
+            };
+            if (shfl || !multi) {
+                // rows of <= 256 elements with shifted planes (one segment per lane), or single-plane rows of any length
+                for (int seg = lane; seg < (shfl ? 32 : nseg_p); seg += 32) {
+                    SegIn in[R];
+                    const bool live = seg * 8 < p.T;
+                    if (live) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) bwd_load<RT, POST>(p, row[r], seg, in[r]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        F8 o, dpre;
+                        if (live) {
+                            finish(r, seg, in[r], o, dpre);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { o.v[i] = 0.f; dpre.v[i] = 0.f; }
+                        }
+                        if (seg < nseg_p) store_dres(r, seg, dpre);
+                        if (shfl) {
+                            if (ok[r]) store_planes_shfl_n(dy, row[r] * p.Tp, planes, pstride, o, p.T, nseg_p, lane);
+                        } else if (ok[r]) {
+                            store8(dy + row[r] * p.Tp + seg * 8, o);
+                        }
+                    }
+                }
             } else {
+                // long rows with shifted planes: staged through shared memory, one row at a time
+#pragma unroll 1
+                for (int r = 0; r < R; ++r) {
+                    if (!ok[r]) continue;
+                    for (int seg = lane; seg < nseg_p; seg += 32) {
+                        F8 o, dpre;
+                        if (seg * 8 < p.T) {
+                            SegIn in;
+                            bwd_load<RT, POST>(p, row[r], seg, in);
+                            finish(r, seg, in, o, dpre);
+                        } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { o.v[i] = 0.f; dpre.v[i] = 0.f; }
-            }
-        };
-        auto store_dres = [&](int seg, F8& dpre) {
-            if (dres != nullptr) {
-                float* dr = dres + row * p.Tp + seg * 8;
-                if (dres_accumulate) {
-                    F8 old = load8(dr);
+                            for (int i = 0; i < 8; ++i) { o.v[i] = 0.f; dpre.v[i] = 0.f; }
+                        }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dpre.v[i] += old.v[i];
+                        for (int i = 0; i < 8; ++i) srow[4 + seg * 8 + i] = o.v[i];
+                        store_dres(r, seg, dpre);
+                    }
+                    __syncwarp();
+                    store_row_planes(dy, row[r] * p.Tp, planes, pstride, srow, p.T, p.Tp, lane);
+                    __syncwarp();
                 }
-                store8(dr, dpre);
-            }
-        };
-        if (shfl) {
-            F8 o, dpre;
-            compute(lane, o, dpre);
-            if (lane < nseg_p) store_dres(lane, dpre);
-            store_planes_shfl_n(dy, row * p.Tp, planes, pstride, o, p.T, nseg_p, lane);
-        } else {
-            for (int seg = lane; seg < nseg_p; seg += 32) {
-                F8 o, dpre;
-                compute(seg, o, dpre);
-                if (multi) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) srow[4 + seg * 8 + i] = o.v[i];
-                } else {
-                    store8(dy + row * p.Tp + seg * 8, o);
-                }
-                store_dres(seg, dpre);
             }
         }
         db = warp_sum(db);
         if (lane == 0 && dbias != nullptr) atomicAdd(&dbias[c], db);
-        if (multi && !shfl) {
-            __syncwarp();
-            store_row_planes(dy, row * p.Tp, planes, pstride, srow, p.T, p.Tp, lane);
-            __syncwarp();
-        }
     }
 }
 
@@ -514,12 +600,15 @@ recon_fwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const f
 // padding) and 16-byte aligned external rows.  No per-element predicates and 32-bit row arithmetic: the generic
 // kernel above spends ~190 of its ~370 instructions per row on index math and predication and is issue-bound
 // (ncu: issue slots 65 % busy at 58 % DRAM throughput).
-// kRowsInFlight rows per warp iteration: all their loads are issued before the first dependent instruction, which
-// doubles the bytes each warp keeps in flight (one 200-element row is only 1.2 KB of loads per warp, too little
-// to cover the HBM latency at the occupancy these kernels reach).  A lane-per-row mapping (each lane walking its own
-// row, no shuffles, all 32 lanes busy) was measured 2-5x SLOWER: 32 different cache lines per load instruction
-// times ~48 resident warps overflow L1 before a line is consumed.
-constexpr int kRowsInFlight = 2;
+// Fast-path mapping: one warp per CHANNEL, looping over the B samples of that channel two rows at a time.
+//  * the rows (n, b = 0..B-1) are contiguous in y / dy, gamma/beta/group index are loaded once per channel and
+//    the per-row index divisions disappear (ncu source counters before: 263 warp instructions per row, 143 of them
+//    index math, predication and reductions; issue slots 72 % busy at 47 % of the DRAM bandwidth);
+//  * kRowsInFlight rows are loaded before the first dependent instruction (one 200-element row is only 1.2 KB of
+//    loads per warp: too little to cover the HBM latency at the occupancy these kernels reach);
+//  * dbias[n] is a register sum over the channel's rows: no atomics, no memset.
+// A lane-per-row mapping (each lane walking its own row) was measured 2-5x slower: 32 different cache lines per
+// load instruction times ~48 resident warps overflow L1 before a line is consumed.
 
 template <typename YT, bool MSE, bool ROWSUMS, bool XHAT>
 __global__ void __launch_bounds__(kThreads, 4)
@@ -531,82 +620,89 @@ recon_fwd_fast_kernel(const YT* __restrict__ y, const float* __restrict__ mr, co
     __shared__ double shm[2][32];
     const int lane = threadIdx.x & 31;
     const int Cg = N / G;
-    const int rows = N * B, wstride = gridDim.x * kWarpsPerBlock;
+    const int wstride = gridDim.x * kWarpsPerBlock;
     const int nseg = T >> 3;
+    const size_t xstride = (size_t)N * T;                    // x / x_hat: distance between samples of one channel
+    const float2* mr2 = reinterpret_cast<const float2*>(mr);
     double d0 = 0.0, d1 = 0.0;
-    for (int row0 = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row0 < rows; row0 += R * wstride) {
-        float a[R], sh[R], rstd[R], nm[R];
-        const YT* yrow[R];
-        size_t xo[R];
-        bool ok[R];
+    for (int n = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); n < N; n += wstride) {
+        const float gam = __ldg(gamma + n), bet = __ldg(beta + n);
+        const int g = n / Cg;
+        const YT* ych = y + (size_t)n * B * Tp;
+        const float* xch = x + (size_t)n * T;
+        float* hch = XHAT ? x_hat + (size_t)n * T : nullptr;
+        float s0 = 0.f, s1 = 0.f;                            // fp32 partials of this channel, flushed to fp64 per channel
+        for (int b0 = 0; b0 < B; b0 += R) {
+            float a[R], sh[R], rstd[R], nm[R];
+            bool ok[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int row = row0 + r * wstride;
-            ok[r] = row < rows;
-            const int rr = ok[r] ? row : row0;
-            const int n = rr / B, b = rr - n * B;
-            const float2 st = __ldg(reinterpret_cast<const float2*>(mr) + (b * G + n / Cg));
-            rstd[r] = st.y;
-            a[r] = __ldg(gamma + n) * st.y;
-            sh[r] = __ldg(beta + n) - st.x * a[r];
-            nm[r] = -st.x * st.y;
-            yrow[r] = y + (size_t)rr * Tp;
-            xo[r] = ((size_t)b * N + n) * T;
-        }
-        float l0[R], l1[R], aL[R], bL[R], aM[R], bM[R];
+            for (int r = 0; r < R; ++r) {
+                ok[r] = b0 + r < B;
+                const float2 st = __ldg(mr2 + (ok[r] ? b0 + r : b0) * G + g);
+                rstd[r] = st.y;
+                a[r] = gam * st.y;
+                sh[r] = bet - st.x * a[r];
+                nm[r] = -st.x * st.y;
+            }
+            float l0[R], l1[R], aL[R], bL[R], aM[R], bM[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) { l0[r] = l1[r] = aL[r] = bL[r] = aM[r] = bM[r] = 0.f; }
-        for (int seg = lane; seg < nseg; seg += 32) {
-            F8 yv[R];
-            float4 x0[R], x1[R];
+            for (int r = 0; r < R; ++r) { l0[r] = l1[r] = aL[r] = bL[r] = aM[r] = bM[r] = 0.f; }
+            for (int seg = lane; seg < nseg; seg += 32) {
+                F8 yv[R];
+                float4 x0[R], x1[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {                    // every load of every row first
-                yv[r] = load8(yrow[r] + seg * 8);
-                x0[r] = __ldg(reinterpret_cast<const float4*>(x + xo[r] + seg * 8));
-                x1[r] = __ldg(reinterpret_cast<const float4*>(x + xo[r] + seg * 8 + 4));
+                for (int r = 0; r < R; ++r) {                // every load of every row first
+                    const int bb = ok[r] ? b0 + r : b0;
+                    yv[r] = load8(ych + (size_t)bb * Tp + seg * 8);
+                    x0[r] = __ldg(reinterpret_cast<const float4*>(xch + bb * xstride + seg * 8));
+                    x1[r] = __ldg(reinterpret_cast<const float4*>(xch + bb * xstride + seg * 8 + 4));
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float xv[8] = {x0[r].x, x0[r].y, x0[r].z, x0[r].w, x1[r].x, x1[r].y, x1[r].z, x1[r].w};
+                    float h[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        h[i] = tanh_fast(fmaf(yv[r].v[i], a[r], sh[r]));
+                        const float d = h[i] - xv[i];
+                        l1[r] = fmaf(d, d, l1[r]);
+                        if (!MSE) l0[r] += loss_term(loss_kind, d);
+                        if (ROWSUMS) {
+                            const float om = fmaf(-h[i], h[i], 1.f);
+                            const float xn = fmaf(yv[r].v[i], rstd[r], nm[r]);
+                            const float gm = d * om;
+                            aM[r] += gm;
+                            bM[r] = fmaf(gm, xn, bM[r]);
+                            if (!MSE) {
+                                const float gl = loss_grad(loss_kind, d) * om;
+                                aL[r] += gl;
+                                bL[r] = fmaf(gl, xn, bL[r]);
+                            }
+                        }
+                    }
+                    if (XHAT && ok[r]) {
+                        float* hp = hch + (b0 + r) * xstride + seg * 8;
+                        *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4*>(hp + 4) = make_float4(h[4], h[5], h[6], h[7]);
+                    }
+                }
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const float xv[8] = {x0[r].x, x0[r].y, x0[r].z, x0[r].w, x1[r].x, x1[r].y, x1[r].z, x1[r].w};
-                float h[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    h[i] = tanh_fast(fmaf(yv[r].v[i], a[r], sh[r]));
-                    const float d = h[i] - xv[i];
-                    l1[r] = fmaf(d, d, l1[r]);
-                    if (!MSE) l0[r] += loss_term(loss_kind, d);
-                    if (ROWSUMS) {
-                        const float om = fmaf(-h[i], h[i], 1.f);
-                        const float xn = fmaf(yv[r].v[i], rstd[r], nm[r]);
-                        const float gm = d * om;
-                        aM[r] += gm;
-                        bM[r] = fmaf(gm, xn, bM[r]);
-                        if (!MSE) {
-                            const float gl = loss_grad(loss_kind, d) * om;
-                            aL[r] += gl;
-                            bL[r] = fmaf(gl, xn, bL[r]);
-                        }
-                    }
+                if (ROWSUMS) {
+                    float am = 2.f * warp_sum(aM[r]), bm = 2.f * warp_sum(bM[r]);
+                    float al = am, bl = bm;
+                    if (!MSE) { al = warp_sum(aL[r]); bl = warp_sum(bL[r]); }
+                    if (lane == 0 && ok[r]) rowsums[(size_t)n * B + b0 + r] = make_float4(al, bl, am, bm);
                 }
-                if (XHAT && ok[r]) {
-                    *reinterpret_cast<float4*>(x_hat + xo[r] + seg * 8) = make_float4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<float4*>(x_hat + xo[r] + seg * 8 + 4) = make_float4(h[4], h[5], h[6], h[7]);
+                if (ok[r]) {
+                    s0 += MSE ? l1[r] : l0[r];
+                    s1 += l1[r];
                 }
             }
         }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (ROWSUMS) {
-                float am = 2.f * warp_sum(aM[r]), bm = 2.f * warp_sum(bM[r]);
-                float al = am, bl = bm;
-                if (!MSE) { al = warp_sum(aL[r]); bl = warp_sum(bL[r]); }
-                if (lane == 0 && ok[r]) rowsums[row0 + r * wstride] = make_float4(al, bl, am, bm);
-            }
-            if (ok[r]) {
-                d0 += (double)(MSE ? l1[r] : l0[r]);
-                d1 += (double)l1[r];
-            }
-        }
+        d0 += (double)s0;
+        d1 += (double)s1;
     }
     double t0 = block_sum(d0, shm[0]);
     double t1 = block_sum(d1, shm[1]);
@@ -625,78 +721,77 @@ recon_bwd_apply_fast_kernel(const YT* __restrict__ y, const float* __restrict__ 
     constexpr int R = kRowsInFlight;
     const int lane = threadIdx.x & 31;
     const int Cg = N / G;
-    const int rows = N * B, wstride = gridDim.x * kWarpsPerBlock;
+    const int wstride = gridDim.x * kWarpsPerBlock;
     const int nseg = T >> 3, nseg_p = Tp >> 3;
+    const size_t xstride = (size_t)N * T;
+    const float2* mr2 = reinterpret_cast<const float2*>(mr);
     const float ga = scal[0], gm = scal[1];
     const float g2 = 2.f * (ga + gm);
-    for (int row0 = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row0 < rows; row0 += R * wstride) {
-        float a[R], sh[R], c1[R], c2[R], c3[R], db[R];
-        const YT* yrow[R];
-        OT* drow[R];
-        size_t xo[R];
-        int nn[R];
-        bool ok[R];
+    for (int n = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); n < N; n += wstride) {
+        const float gam = __ldg(gamma + n), bet = __ldg(beta + n);
+        const int g = n / Cg;
+        const YT* ych = y + (size_t)n * B * Tp;
+        OT* dch = dy + (size_t)n * B * Tp;
+        const float* xch = x + (size_t)n * T;
+        float db = 0.f;
+        for (int b0 = 0; b0 < B; b0 += R) {
+            float a[R], sh[R], c1[R], c2[R], c3[R];
+            bool ok[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int row = row0 + r * wstride;
-            ok[r] = row < rows;
-            const int rr = ok[r] ? row : row0;
-            const int n = rr / B, b = rr - n * B;
-            const int g = n / Cg;
-            const float2 st = __ldg(reinterpret_cast<const float2*>(mr) + (b * G + g));
-            const float mean = st.x, rstd = st.y;
-            const float gam = __ldg(gamma + n);
-            a[r] = gam * rstd;
-            sh[r] = __ldg(beta + n) - mean * a[r];
-            const float m1 = (float)S[(size_t)(b * G + g) * 2] * inv_n;
-            const float m2 = (float)S[(size_t)(b * G + g) * 2 + 1] * inv_n;
-            c1[r] = rstd * gam;
-            c2[r] = -rstd * rstd * m2;
-            c3[r] = rstd * (mean * rstd * m2 - m1);
-            yrow[r] = y + (size_t)rr * Tp;
-            drow[r] = dy + (size_t)rr * Tp;
-            xo[r] = ((size_t)b * N + n) * T;
-            nn[r] = n;
-            db[r] = 0.f;
-        }
-        for (int seg = lane; seg < nseg_p; seg += 32) {
-            if (seg < nseg) {
-                F8 yv[R];
-                float4 x0[R], x1[R];
+            for (int r = 0; r < R; ++r) {
+                ok[r] = b0 + r < B;
+                const int bb = ok[r] ? b0 + r : b0;
+                const float2 st = __ldg(mr2 + bb * G + g);
+                const float mean = st.x, rstd = st.y;
+                a[r] = gam * rstd;
+                sh[r] = bet - mean * a[r];
+                const float m1 = (float)S[(size_t)(bb * G + g) * 2] * inv_n;
+                const float m2 = (float)S[(size_t)(bb * G + g) * 2 + 1] * inv_n;
+                c1[r] = rstd * gam;
+                c2[r] = -rstd * rstd * m2;
+                c3[r] = rstd * (mean * rstd * m2 - m1);
+            }
+            for (int seg = lane; seg < nseg_p; seg += 32) {
+                if (seg < nseg) {
+                    F8 yv[R];
+                    float4 x0[R], x1[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    yv[r] = load8(yrow[r] + seg * 8);
-                    x0[r] = __ldg(reinterpret_cast<const float4*>(x + xo[r] + seg * 8));
-                    x1[r] = __ldg(reinterpret_cast<const float4*>(x + xo[r] + seg * 8 + 4));
-                }
+                    for (int r = 0; r < R; ++r) {
+                        const int bb = ok[r] ? b0 + r : b0;
+                        yv[r] = load8(ych + (size_t)bb * Tp + seg * 8);
+                        x0[r] = __ldg(reinterpret_cast<const float4*>(xch + bb * xstride + seg * 8));
+                        x1[r] = __ldg(reinterpret_cast<const float4*>(xch + bb * xstride + seg * 8 + 4));
+                    }
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float xv[8] = {x0[r].x, x0[r].y, x0[r].z, x0[r].w, x1[r].x, x1[r].y, x1[r].z, x1[r].w};
+                    for (int r = 0; r < R; ++r) {
+                        const float xv[8] = {x0[r].x, x0[r].y, x0[r].z, x0[r].w, x1[r].x, x1[r].y, x1[r].z, x1[r].w};
+                        F8 o;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float h = tanh_fast(fmaf(yv[r].v[i], a[r], sh[r]));
+                            const float d = h - xv[i];
+                            const float gg = (MSE ? g2 * d : ga * loss_grad(loss_kind, d) + gm * 2.f * d) * fmaf(-h, h, 1.f);
+                            o.v[i] = fmaf(c1[r], gg, fmaf(c2[r], yv[r].v[i], c3[r]));
+                            acc += o.v[i];
+                        }
+                        if (ok[r]) {
+                            store8(dch + (size_t)(b0 + r) * Tp + seg * 8, o);
+                            db += acc;
+                        }
+                    }
+                } else {
                     F8 o;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float h = tanh_fast(fmaf(yv[r].v[i], a[r], sh[r]));
-                        const float d = h - xv[i];
-                        const float gg = (MSE ? g2 * d : ga * loss_grad(loss_kind, d) + gm * 2.f * d) * fmaf(-h, h, 1.f);
-                        o.v[i] = fmaf(c1[r], gg, fmaf(c2[r], yv[r].v[i], c3[r]));
-                        db[r] += o.v[i];
-                    }
-                    if (ok[r]) store8(drow[r] + seg * 8, o);
+                    for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (ok[r]) store8(dch + (size_t)(b0 + r) * Tp + seg * 8, o);
                 }
-            } else {
-                F8 o;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (ok[r]) store8(drow[r] + seg * 8, o);
             }
         }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float t = warp_sum(db[r]);
-            if (lane == 0 && ok[r]) atomicAdd(&dbias[nn[r]], t);
-        }
+        db = warp_sum(db);
+        if (lane == 0) dbias[n] = db;
     }
 }
 
@@ -909,7 +1004,7 @@ template <typename OT, typename RT, int ACT, bool POST>
 static void launch_bwd_t(const BwdArgs& p, OT* dy, int planes, long long pstride, float* dgamma, float* dbeta, float* dbias,
                          float* dres, int dres_accumulate, double* ws, cudaStream_t st) {
     size_t sm = planes > 1 ? sizeof(float) * kWarpsPerBlock * (p.Tp + 8) : 0;
-    int grid = persistent_grid((long long)p.C * p.B);
+    int grid = persistent_grid((long long)p.C * cdiv(p.B, kChunkB));
     if (p.mr != nullptr) gn_bwd_reduce_kernel<RT, ACT, POST><<<grid, kThreads, 0, st>>>(p, dgamma, dbeta, ws);
     gn_bwd_apply_kernel<OT, RT, ACT, POST><<<grid, kThreads, sm, st>>>(p, ws, dy, planes, pstride, dbias, dres, dres_accumulate);
 }
@@ -1044,6 +1139,7 @@ int sg_recon_fwd(const void* y, int y_dtype, const float* mr, const float* gamma
     const bool mse = loss_kind == SG_LOSS_MSE;
     const bool ybf = y_dtype == SG_BF16;
     if (vec && x != nullptr && (T & 7) == 0 && (long long)N * B < (1LL << 31)) {
+        grid = persistent_grid(N);                           // one warp per channel
 #define SG_FAST(YT, MSE, RS, XH) \
     recon_fwd_fast_kernel<YT, MSE, RS, XH><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, x, x_hat, loss_sums, \
                                                                       (float4*)rowsums, N, B, T, Tp, G, loss_kind)
@@ -1095,6 +1191,7 @@ int sg_recon_bwd(const void* y, int y_dtype, const float* mr, const float* gamma
         bool vec = (T % 4 == 0) && aligned16(x);
         const bool mse = loss_kind == SG_LOSS_MSE;
         if (vec && (T & 7) == 0 && (long long)N * B < (1LL << 31)) {
+            grid = persistent_grid(N);                       // one warp per channel; dbias written, not accumulated
 #define SG_AF(YT, OT, MSE) \
     recon_bwd_apply_fast_kernel<YT, OT, MSE><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, x, scal, S, (OT*)dy, dbias, \
                                                                         N, B, T, Tp, G, loss_kind, (float)inv_n)
