@@ -107,7 +107,8 @@ int sg_gn_act_fwd(const float* y, const float* stats, const float* gamma, const 
                   int C, int B, int T, int Tp, int G, int dtype, void* stream);
 /* Backward of the above.  dout fp32 [C][B][Tp].  Writes dy (dtype, gap zeroed) = grad wrt y,
  * dgamma/dbeta (may be NULL when stats == NULL), dbias[C] = sum_{b,t} dy, and dres (fp32,
- * (+)= per dres_accumulate) when res != NULL.  ws: >= 2*B*G doubles. */
+ * (+)= per dres_accumulate bit 0) when res != NULL.  ws: >= 2*B*G doubles.  dres_accumulate bit 1: dgamma, dbeta,
+ * dbias and ws were zeroed by the caller (they are accumulated into with atomics). */
 int sg_gn_act_bwd(const float* y, const float* stats, const float* gamma, const float* beta,
                   const void* res, int res_is_f32, float res_scale, int act, int post_gelu,
                   const float* dout, void* dy, int planes, long long plane_stride,

@@ -1012,11 +1012,17 @@ static void launch_bwd_t(const BwdArgs& p, OT* dy, int planes, long long pstride
 template <typename OT, typename RT>
 static int launch_bwd(int act, int post, const BwdArgs& p, OT* dy, int planes, long long pstride, float* dgamma, float* dbeta,
                       float* dbias, float* dres, int dres_accumulate, double* ws, cudaStream_t st) {
-    if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * p.C, st);
-    if (p.mr != nullptr) {
-        cudaMemsetAsync(dgamma, 0, sizeof(float) * p.C, st);
-        cudaMemsetAsync(dbeta, 0, sizeof(float) * p.C, st);
-        cudaMemsetAsync(ws, 0, sizeof(double) * 2 * p.B * p.G, st);
+    // dres_accumulate bit 1: the caller hands in dbias / dgamma / dbeta / ws already zeroed (one memset per step for
+    // the whole gradient arena instead of four tiny ones per layer)
+    const bool prezeroed = (dres_accumulate & 2) != 0;
+    dres_accumulate &= 1;
+    if (!prezeroed) {
+        if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * p.C, st);
+        if (p.mr != nullptr) {
+            cudaMemsetAsync(dgamma, 0, sizeof(float) * p.C, st);
+            cudaMemsetAsync(dbeta, 0, sizeof(float) * p.C, st);
+            cudaMemsetAsync(ws, 0, sizeof(double) * 2 * p.B * p.G, st);
+        }
     }
 #define SG_B(ACT, POST) launch_bwd_t<OT, RT, ACT, POST>(p, dy, planes, pstride, dgamma, dbeta, dbias, dres, dres_accumulate, ws, st)
     if (act == SG_ACT_GELU) { if (post) SG_B(SG_ACT_GELU, true); else SG_B(SG_ACT_GELU, false); }

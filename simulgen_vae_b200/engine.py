@@ -127,6 +127,8 @@ class GradSink:
         self.dev = device
         self.weights = torch.zeros(max(weight_elems, 1), dtype=torch.float32, device=device)
         self.vecs = torch.zeros(max(vec_elems, 1), dtype=torch.float32, device=device)
+        self.scratch = torch.zeros(1 << 18, dtype=torch.float64, device=device)
+        self.scratch_used = 0
         self.w_used = self.v_used = 0
         self.w_slots, self.v_slots = {}, {}
         self.items = {}                 # id(param) -> optimiser item description (first backward)
@@ -141,6 +143,20 @@ class GradSink:
 
     def begin_step(self):
         self.committed = 0
+        # the per-channel gradient vectors (bias, GroupNorm gain/shift) are accumulated with atomics: one memset of
+        # the whole arena per step instead of three per layer; same for the fp64 scratch of the GroupNorm backward
+        self.vecs.zero_()
+        self.scratch.zero_()
+        self.scratch_used = 0
+
+    def zeroed_scratch(self, n):
+        """n zeroed float64 elements (valid until the next begin_step), or None when the arena is exhausted"""
+        n = (n + 1) // 2 * 2
+        if self.scratch_used + n > self.scratch.numel():
+            return None
+        out = self.scratch[self.scratch_used:self.scratch_used + n]
+        self.scratch_used += n
+        return out
 
     def weight_buffer(self, param, shape):
         key = id(param)
@@ -599,8 +615,12 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
             dres, acc = (None, 0)
             if res is not None and res.needs_grad:
                 dres, acc = ctx.grad_buf(res)
+            ws = None
+            if ctx.sink is not None and (dbias is None or conv.bias.requires_grad) and \
+                    (gn is None or (gn.weight.requires_grad and gn.bias.requires_grad)):
+                ws = ctx.sink.zeroed_scratch(2 * B * max(G, 1) + 2)     # arena buffers: zeroed once per step
             K.gn_act_bwd(y, stats, gn.weight if gn is not None else None, gn.bias if gn is not None else None,
-                         res_t, res_scale, act, post_gelu, g, dy, dgamma, dbeta, dbias, dres, acc, T, G)
+                         res_t, res_scale, act, post_gelu, g, dy, dgamma, dbeta, dbias, dres, acc, T, G, ws)
             if gn is not None:
                 ctx.set_pgrad(gn.weight, dgamma)
                 ctx.set_pgrad(gn.bias, dbeta)

@@ -201,14 +201,20 @@ def gn_act_fwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, out_op, ou
 
 
 def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, dgamma, dbeta, dbias, dres,
-               dres_accumulate, T, G):
+               dres_accumulate, T, G, ws=None):
+    """ws: optional ZEROED float64 workspace of >= 2*B*G elements; passing it also declares dgamma / dbeta / dbias as
+    already zeroed by the caller (the engine zeroes its whole gradient arena once per step)."""
     C, B, Tp = y.shape
     res_is_f32 = int(res is not None and res.dtype == torch.float32)
-    ws = torch.empty(2 * B * max(int(G), 1) + 2, dtype=torch.float64, device=y.device)
+    flags = int(bool(dres_accumulate))
+    if ws is None:
+        ws = torch.empty(2 * B * max(int(G), 1) + 2, dtype=torch.float64, device=y.device)
+    else:
+        flags |= 2
     dp, dn, dstr = _planes(dy)
     _call("sg_gn_act_bwd", _p(_f32(y, "y")), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(res), res_is_f32, float(res_scale),
           int(act), int(post_gelu), _p(_f32(dout, "dout")), dp, dn, dstr, _p(dgamma), _p(dbeta), _p(dbias), _p(dres),
-          int(dres_accumulate), _p(ws), C, B, T, Tp, int(G), _dt(dy), _stream())
+          flags, _p(ws), C, B, T, Tp, int(G), _dt(dy), _stream())
 
 
 def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind, rowsums=None):

@@ -193,7 +193,7 @@ def gn_act_fwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, out_op, ou
 
 
 def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, dgamma, dbeta, dbias, dres,
-               dres_accumulate, T, G):
+               dres_accumulate, T, G, ws=None):
     use_gn = stats is not None
     with torch.enable_grad():
         yl = y.detach().clone().requires_grad_(True)
