@@ -177,6 +177,16 @@ int sg_philox_normal(float* out, int B, long long per_sample, unsigned long long
 int sg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, double* gnorm_sq, void* stream);
 
+/* ---- batch assembly + augmentation (modules/augmentation.py:43-124, utils.py:56-66) ----------
+ * data fp32 [P][N][T] resident on the GPU.  ids int32 [2][B] = (dataset index, mixup partner or -1);
+ * table fp32 [4][B] = (noise_level or 0, scale, lambda, 1 - lambda).  out fp32 [B][N][T] =
+ *     lambda * scale * (data[idx] + noise_level * eps) + (1 - lambda) * data[partner]
+ * (reference order: noise, scaling, mixup; every product and sum rounded separately like the ATen sequence).  eps: injected_noise [B][N][T] if given, else Philox normals keyed on
+ * (seed, draw, dataset index, element).  operand (optional): bf16 [N][B][Tp] copy for the first encoder conv. */
+int sg_assemble_batch(const float* data, int P, const int* ids, const float* table, const float* injected_noise,
+                      float* out, void* operand, int B, int N, int T, int Tp, unsigned long long seed,
+                      unsigned long long draw, void* stream);
+
 /* ---- batched spectral-norm preparation: every layer of a sub-network in five launches ---------------
  * Same arithmetic as sg_sn_power_iter + sg_sn_pack_weight per layer (spectral_norm.py:62-114): the power
  * iteration depends only on the weights and the stored u / v, so all layers are prepared up front.

@@ -50,6 +50,25 @@ def want(name):
     return not ONLY or ONLY in name
 
 
+if want("assemble"):
+    Pn = 6
+    data = torch.rand(Pn, N, T, device=dev) * 1.4 - 0.7
+    g = torch.Generator().manual_seed(0)
+    idx = torch.randint(0, Pn, (B,), generator=g)
+    oth = torch.where(torch.rand(B, generator=g) < 0.5, torch.randint(0, Pn, (B,), generator=g), torch.full((B,), -1))
+    ids = torch.stack([idx, oth]).to(torch.int32).to(dev)
+    nl = torch.where(torch.rand(B, generator=g) < 0.5, torch.full((B,), 0.05), torch.zeros(B))
+    lam = torch.rand(B, generator=g) * 0.8 + 0.1
+    table = torch.stack([nl, torch.rand(B, generator=g) * 0.2 + 0.9, lam, 1 - lam]).float().to(dev)
+    outb = torch.empty(B, N, T, device=dev)
+    opb = torch.empty(1, N, B, Tp, device=dev, dtype=BF)
+    nmix = int((oth >= 0).sum())
+    per = N * T * 4
+    report("assemble_batch (aug, fp32 out)", timed(lambda: K.assemble_batch(data, ids, table, None, outb, 1, 0)),
+           (2 * B + nmix) * per)
+    report("assemble_batch (+ bf16 operand)", timed(lambda: K.assemble_batch(data, ids, table, None, outb, 1, 0, opb)),
+           (2 * B + nmix) * per + opb.numel() * 2)
+    del data, outb, opb
 if want("recon") or want("pack"):
     x = torch.rand(B, N, T, device=dev) * 1.4 - 0.7
 if want("pack"):

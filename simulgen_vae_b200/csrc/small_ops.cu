@@ -447,15 +447,6 @@ kl2_reparam_bwd_kernel(const float* __restrict__ cz, const float* __restrict__ c
 // =============================================================================================
 // Philox4x32-10 + Box-Muller
 // =============================================================================================
-__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
-                                             uint32_t k1) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-}
-
 __global__ void philox_normal_kernel(float* __restrict__ out, int B, long long per_sample, uint64_t seed,
                                      uint64_t stream_id, long long sample0) {
     long long quads = (per_sample + 3) / 4;
@@ -464,25 +455,8 @@ __global__ void philox_normal_kernel(float* __restrict__ out, int B, long long p
     int b = (int)(idx / quads);
     long long qd = idx - (long long)b * quads;
     uint64_t sample = (uint64_t)(sample0 + b);
-    uint32_t c0 = (uint32_t)qd, c1 = (uint32_t)((uint64_t)qd >> 32) ^ (uint32_t)(stream_id << 8);
-    uint32_t c2 = (uint32_t)sample, c3 = (uint32_t)(sample >> 32) ^ (uint32_t)(stream_id >> 24);
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        philox_round(c0, c1, c2, c3, k0, k1);
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    const float k2_32 = 2.3283064365386963e-10f;  // 2^-32
-    float u0 = ((float)c0 + 0.5f) * k2_32, u1 = ((float)c1 + 0.5f) * k2_32;
-    float u2 = ((float)c2 + 0.5f) * k2_32, u3 = ((float)c3 + 0.5f) * k2_32;
-    u0 = fminf(fmaxf(u0, 1e-10f), 1.0f);
-    u2 = fminf(fmaxf(u2, 1e-10f), 1.0f);
-    float r0 = sqrtf(-2.f * logf(u0)), r1 = sqrtf(-2.f * logf(u2));
-    float s0, co0, s1, co1;
-    sincospif(2.f * u1, &s0, &co0);
-    sincospif(2.f * u3, &s1, &co1);
-    float n[4] = {r0 * co0, r0 * s0, r1 * co1, r1 * s1};
+    float n[4];
+    philox_normal4(seed, stream_id, sample, (uint64_t)qd, n);
     float* dst = out + (long long)b * per_sample + qd * 4;
 #pragma unroll
     for (int i = 0; i < 4; ++i)

@@ -228,6 +228,18 @@ def _materialize_xhat():
     return getattr(_sink, "xhat", True)
 
 
+def set_packed_input(op):
+    """Hand the next encoder forward of this thread the already packed bf16 operand [1, N, B, Tp] of its input
+    (written by sg_assemble_batch together with the batch): sg_pack_input is skipped once."""
+    _sink.packed = op
+
+
+def _take_packed_input():
+    op = getattr(_sink, "packed", None)
+    _sink.packed = None
+    return op
+
+
 # ------------------------------------------------------------------------------------------------
 # tape primitives
 # ------------------------------------------------------------------------------------------------
@@ -722,8 +734,12 @@ def encoder_graph(ctx: Ctx, enc, x):
     order without the deepest level)."""
     B, N, T = x.shape
     prepare_all(ctx, enc)
-    a = Act(N, data=ctx.op(1, N, B, ctx.Tp), needs_grad=False, name="x")
-    K.pack_input(x, a.data, T)
+    packed = _take_packed_input()
+    if packed is not None and tuple(packed.shape) == (1, N, B, ctx.Tp) and packed.dtype == ctx.op_dtype:
+        a = Act(N, data=packed, needs_grad=False, name="x")
+    else:
+        a = Act(N, data=ctx.op(1, N, B, ctx.Tp), needs_grad=False, name="x")
+        K.pack_input(x, a.data, T)
     L = len(enc.encoder_blocks)
     xs = []
     h = None

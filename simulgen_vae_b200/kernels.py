@@ -371,3 +371,17 @@ def sn_prepare(plan, training):
     import ctypes
     _call("sg_sn_prepare", plan.table.data_ptr(), ctypes.addressof(plan._host), plan.n, plan.ws.data_ptr(),
           plan.ws.numel(), int(training), plan.dtype, _stream())
+
+
+# ---- batch assembly + augmentation --------------------------------------------------------------
+def assemble_batch(data, ids, table, injected_noise, out, seed, draw, operand=None):
+    """data fp32 [P, N, T]; ids int32 [2, B]; table fp32 [4, B]; out fp32 [B, N, T]; operand: optional bf16
+    [1, N, B, Tp] (the packed input of the first encoder conv)."""
+    P, N, T = data.shape
+    B = out.shape[0]
+    assert ids.dtype == torch.int32 and tuple(ids.shape) == (2, B) and tuple(table.shape) == (4, B)
+    Tp = operand.shape[3] if operand is not None else 0
+    if operand is not None:
+        assert operand.dtype == torch.bfloat16 and tuple(operand.shape[:3]) == (1, N, B)
+    _call("sg_assemble_batch", _p(_f32(data, "data")), P, _p(ids), _p(_f32(table, "table")), _p(_f32(injected_noise, "noise")),
+          _p(_f32(out, "out")), _p(operand), B, N, T, Tp, int(seed) & (2 ** 64 - 1), int(draw), _stream())

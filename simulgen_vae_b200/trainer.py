@@ -166,9 +166,12 @@ class Trainer:
         self.plan = K.OptPlan(items, self.dev)
 
     # -- one optimisation step -------------------------------------------------------------------
-    def step(self, x, beta=1e-4, sample_offset=0):
+    def step(self, x, beta=1e-4, sample_offset=0, packed=None):
+        """packed: optional bf16 operand of x written by the batch-assembly kernel (augment.B200AugmentedLoader with
+        emit_operand=True): the encoder then skips its own input packing pass."""
         model = self.model
         engine.set_sample_offset(sample_offset)
+        engine.set_packed_input(packed)
         b1, b2 = self.betas
         scale = 1.0 / self.world
         self.gnorm_sq.zero_()

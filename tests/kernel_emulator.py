@@ -420,6 +420,26 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale
     p.addcdiv_(m, denom, value=-lr / bc1)
 
 
+def assemble_batch(data, ids, table, injected_noise, out, seed, draw, operand=None):
+    B = out.shape[0]
+    idx, other = ids[0].long(), ids[1].long()
+    nl, sc, lam, om = table[0], table[1], table[2], table[3]
+    s = data[idx]
+    if injected_noise is not None:
+        eps = injected_noise
+    else:
+        g = torch.Generator().manual_seed(int(seed) * 7919 + int(draw))
+        eps = torch.randn(s.shape, generator=g).to(s.device)
+    s = torch.where((nl != 0)[:, None, None], s + eps * nl[:, None, None], s)
+    s = s * sc[:, None, None]
+    mix = other >= 0
+    partner = data[other.clamp_min(0)]
+    s = torch.where(mix[:, None, None], lam[:, None, None] * s + om[:, None, None] * partner, s)
+    out.copy_(s)
+    if operand is not None:
+        write_planes(operand, s.permute(1, 0, 2), data.shape[2])
+
+
 class OptPlan:
     """Emulated counterpart of kernels.OptPlan: keeps the item list (tensors) instead of a device table."""
 
@@ -457,7 +477,7 @@ def sn_prepare(plan, training):
             sn_pack_weight(L["w"], L["sigma"], L["wg"], L["H"], L["Cin"], L["Cin_p"], L["k"], L["so"], L["si"], L["flip"])
 
 
-NAMES = ["OptPlan", "opt_step", "SnPlan", "sn_prepare", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
+NAMES = ["OptPlan", "opt_step", "SnPlan", "sn_prepare", "assemble_batch", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
          "conv_fprop", "conv_fprop_gn", "conv_dgrad", "conv_wgrad", "gn_stats", "gn_act_fwd", "gn_act_bwd", "recon_fwd", "recon_bwd",
          "head_fwd", "head_bwd", "latent_fwd", "latent_bwd", "reparam_main_fwd", "reparam_main_bwd", "kl2_reparam_fwd",
          "kl2_reparam_bwd", "philox_normal", "adamw_step"]

@@ -1,0 +1,122 @@
+"""Batch assembly + augmentation against golden batches recorded from the UNMODIFIED reference
+DataLoader (oracle/make_golden_augment.py): same python / numpy / torch seeds, same injected Gaussian noise.
+CPU: host logic (sampling order, per-sample decisions) with the kernel replaced by its torch model.
+GPU (-m gpu): the real sg_assemble_batch kernel - bit-exact, it is plain fp32 arithmetic in the reference's order."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import kernel_emulator as emu
+from conftest import GOLDEN_DIR
+
+
+def _run(device):
+    from simulgen_vae_b200 import augment
+    g = torch.load(os.path.join(GOLDEN_DIR, "augment_toy.pt"), weights_only=False)
+    random.seed(g["seeds"]["python"])
+    np.random.seed(g["seeds"]["numpy"])
+    torch.manual_seed(g["seeds"]["torch"])
+    train, val = augment.create_augmented_dataloaders(g["data"].numpy(), g["batch"], load_all=True, device=device)
+    assert len(train) == len(g["train_epochs"][0]) and len(val) == len(g["val_epoch"])
+    worst = 0.0
+    exact = True
+    for epoch in g["train_epochs"]:
+        it = iter(epoch)
+
+        def inject(levels, shape, it=it, holder={}):
+            b = holder["batch"]
+            noise = torch.zeros((len(levels),) + tuple(shape))
+            pos = [i for i, l in enumerate(levels) if l > 0]
+            assert len(pos) == len(b["noise"]), "noise decisions differ from the reference"
+            for i, e in zip(pos, b["noise"]):
+                noise[i] = e
+            return noise
+        holder = inject.__defaults__[1]
+        train.injected_noise = inject
+        loader_it = iter(train)
+        for b in epoch:
+            holder["batch"] = b
+            x = next(loader_it).cpu()
+            assert x.shape == b["x"].shape
+            worst = max(worst, float((x - b["x"]).abs().max()))
+            exact = exact and torch.equal(x, b["x"])
+        with pytest.raises(StopIteration):
+            next(loader_it)
+    for x, ref in zip(val, g["val_epoch"]):
+        assert torch.equal(x.cpu(), ref)
+    return worst, exact
+
+
+def test_loader_decisions_and_batches_match_reference_cpu():
+    with emu.install():
+        worst, exact = _run("cpu")
+    assert worst < 1e-6, worst
+
+
+@pytest.mark.gpu
+def test_assemble_batch_kernel_matches_reference_bit_exact():
+    worst, exact = _run("cuda")
+    assert exact, worst
+
+
+@pytest.mark.gpu
+def test_assemble_batch_philox_noise_and_operand():
+    """Without injected noise: the Philox stream is keyed on the dataset index (not the batch slot), has the requested
+    standard deviation, and the optional bf16 operand equals the packed fp32 batch."""
+    from simulgen_vae_b200 import kernels as K
+    from simulgen_vae_b200.engine import tp_of
+    P, N, T, B = 5, 40, 200, 4
+    dev = "cuda"
+    data = torch.zeros(P, N, T, device=dev)
+    ids = torch.tensor([[0, 1, 2, 1], [-1, -1, -1, -1]], dtype=torch.int32, device=dev)
+    table = torch.tensor([[0.05, 0.05, 0.0, 0.05], [1, 1, 1, 1], [1, 1, 1, 1], [0, 0, 0, 0]], dtype=torch.float32, device=dev)
+    out = torch.empty(B, N, T, device=dev)
+    Tp = tp_of(T, "bf16")
+    op = torch.full((1, N, B, Tp), 3.0, device=dev, dtype=torch.bfloat16)
+    K.assemble_batch(data, ids, table, None, out, 11, 0, op)
+    assert abs(float(out[0].std()) - 0.05) < 0.003 and abs(float(out[0].mean())) < 0.002
+    assert float(out[2].abs().max()) == 0.0
+    assert torch.equal(out[1], out[3])                    # same dataset index -> same noise, whatever the slot
+    assert not torch.equal(out[0], out[1])
+    ref = torch.empty_like(op)
+    K.pack_input(out, ref, T)
+    assert torch.equal(op, ref)
+    out2 = torch.empty_like(out)
+    K.assemble_batch(data, ids, table, None, out2, 11, 1)      # next draw: fresh noise
+    assert not torch.equal(out2[0], out[0])
+
+
+@pytest.mark.gpu
+def test_trainer_step_with_packed_operand_equals_plain_step():
+    """The loader can emit the bf16 operand of the first conv together with the batch; feeding it to Trainer.step must
+    give the same step as letting the encoder pack x itself."""
+    import simulgen_vae_b200 as sg
+    from simulgen_vae_b200 import augment
+    from simulgen_vae_b200.trainer import Trainer
+    from test_parity_gpu import build_engine_vae
+    from conftest import load_golden, rel_l2
+    g = load_golden("toy3_small_mse")
+    cfg = g["cfg"]
+    sg.set_precision("bf16")
+    data = torch.cat([g["x"], g["x"] * 0.8, g["x"] * 1.1]).numpy()
+    res = []
+    for packed in (False, True):
+        random.seed(1); np.random.seed(2); torch.manual_seed(3)
+        train, _ = augment.create_augmented_dataloaders(data, cfg["batch"], load_all=True)
+        train.emit_operand = packed
+        m = build_engine_vae(cfg, g["state_dict"])
+        m.train(True)
+        tr = Trainer(m, lr=1e-3, alpha=g["alpha"])
+        for x in train:
+            if x.shape[0] != cfg["batch"]:
+                continue
+            with sg.fixed_eps(g["eps"]):
+                tr.step(x, beta=g["beta"], packed=train.last_operand)
+        res.append({k: v.detach().clone() for k, v in m.state_dict().items()})
+    for k in res[0]:
+        assert rel_l2(res[0][k], res[1][k]) < 2e-2, k          # bf16 mode: see test_trainer_fused_step_equals_per_tensor_path
+    w = "decoder.recon.0.weight_orig"
+    assert rel_l2(res[0][w], res[1][w]) < 1e-4
