@@ -175,7 +175,7 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream_id
 }
 
 // ---------------------------------------------------------------------------------------------
-// mbarrier + bulk-copy (TMA 1-D) helpers
+// mbarrier helpers (used by the tcgen05 GEMM pipelines)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -209,65 +209,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
-// contiguous global -> shared copy by the TMA unit; `bytes` and both addresses are multiples of 16
-__device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src_gmem)), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// Per-warp asynchronous row prefetcher for the HBM-streaming kernels.  The bytes a streaming kernel keeps in
-// flight normally live in destination registers of pending loads, and with ~50 registers per thread that is
-// 30-60 KB per SM: not enough to cover the ~1 us HBM latency at 6.5 TB/s (round 1: 30-70 % of the HBM roofline,
-// while the 32-register pack kernel reached 88 %).  Here each warp owns DEPTH shared-memory slots; lane 0 asks the
-// TMA unit to copy the next DEPTH rows (each row = up to NS contiguous streams) and the warp consumes them in
-// order, re-arming a slot as soon as its data has been read into registers.
-template <int NS, int DEPTH>
-struct RowPipe {
-    uint8_t* slots;          // this warp's DEPTH * slot_bytes staging area (16-byte aligned)
-    uint64_t* bars;          // this warp's DEPTH mbarriers
-    uint32_t slot_bytes;
-    uint32_t off[NS];        // byte offset of each stream inside a slot
-
-    __device__ __forceinline__ void init(uint8_t* smem, int warps, int warp, int lane, const uint32_t (&stream_bytes)[NS]) {
-        uint32_t o = 0;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            off[s] = o;
-            o += (stream_bytes[s] + 127u) & ~127u;
-        }
-        slot_bytes = o;
-        slots = smem + (size_t)warp * DEPTH * slot_bytes;
-        bars = reinterpret_cast<uint64_t*>(smem + (size_t)warps * DEPTH * slot_bytes) + warp * DEPTH;
-        if (lane == 0) {
-#pragma unroll
-            for (int d = 0; d < DEPTH; ++d) mbar_init(&bars[d], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-    }
-    static __host__ __device__ size_t smem_bytes(int warps, const uint32_t* stream_bytes) {
-        size_t o = 0;
-        for (int s = 0; s < NS; ++s) o += (stream_bytes[s] + 127u) & ~127u;
-        return (size_t)warps * DEPTH * o + (size_t)warps * DEPTH * 8;
-    }
-    // lane 0 only: start the copies of one row into `slot` (src[s] == nullptr skips a stream)
-    __device__ __forceinline__ void issue(int slot, const void* const (&src)[NS], const uint32_t (&bytes)[NS]) {
-        uint32_t total = 0;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) total += src[s] != nullptr ? bytes[s] : 0u;
-        mbar_arrive_expect_tx(&bars[slot], total);
-#pragma unroll
-        for (int s = 0; s < NS; ++s)
-            if (src[s] != nullptr) bulk_load_1d(slots + (size_t)slot * slot_bytes + off[s], src[s], bytes[s], &bars[slot]);
-    }
-    __device__ __forceinline__ void wait(int slot, uint32_t parity) { mbar_wait(&bars[slot], parity); }
-    template <typename T>
-    __device__ __forceinline__ const T* row(int slot, int s) const {
-        return reinterpret_cast<const T*>(slots + (size_t)slot * slot_bytes + off[s]);
-    }
-};
-
 // ---------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------
