@@ -1,0 +1,66 @@
+"""CPU test of the drop-in claim: the UNMODIFIED /root/reference/modules/train.py::train() runs on the
+engine's overlay modules (namespace-package shadowing, `install_overlay()`), with the CUDA kernels replaced by their
+torch models.  Checks that the reference's own driver - model.apply(initialize_weights_He / add_sn), AdamW over
+model.parameters(), the per-parameter grad-norm loop, validation under no_grad, torch.save(state_dict) and
+torch.save(model) - works against the engine and that the checkpoint layout equals the reference's.
+Skipped where the reference checkout is absent (GPU box)."""
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+
+import kernel_emulator as emu
+import simulgen_vae_b200 as sg
+from oracle import ref_import
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present")
+
+
+def _purge_modules():
+    for k in [k for k in sys.modules if k == "modules" or k.startswith("modules.")]:
+        del sys.modules[k]
+
+
+def test_reference_train_runs_on_the_overlay(tmp_path, monkeypatch):
+    ref_import._install_stubs()
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("checkpoints")
+    os.makedirs("model_save")
+    _purge_modules()
+    overlay = sg.install_overlay()
+    sys.path.insert(1, ref_import.REFERENCE_ROOT)
+    try:
+        train_mod = importlib.import_module("modules.train")
+        vae_mod = importlib.import_module("modules.VAE_network")
+        assert vae_mod.__file__.startswith(overlay), "train.py must bind to the overlay's VAE"
+        assert train_mod.__file__.startswith(ref_import.REFERENCE_ROOT), "train.py itself must be the reference's"
+        assert train_mod.VAE is vae_mod.VAE
+        cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[32, 16, 8], num_node=64, num_time=20)
+        g = torch.Generator().manual_seed(0)
+        data = torch.rand(16, cfg["num_node"], cfg["num_time"], generator=g) * 1.4 - 0.7
+        train_dl = torch.utils.data.DataLoader(data[:12], batch_size=4, shuffle=False)
+        val_dl = torch.utils.data.DataLoader(data[12:], batch_size=4, shuffle=False)
+        sg.set_precision("fp32")
+        monkeypatch.setattr(train_mod, "device", torch.device("cpu"), raising=False)
+        with emu.install():
+            out = train_mod.train(4, 4, train_dl, val_dl, 1e-3, cfg["enc"], cfg["enc"][::-1], cfg["num_node"],
+                                  cfg["latent_dim"], cfg["hierarchical_dim"], cfg["num_time"], 1000000, "MSE", True, True)
+        assert len(out) == 4 and all(len(c) == 4 for c in out)
+        loss_curve = [float(v) for v in out[0]]
+        assert all(v == v and v < 1e12 for v in loss_curve)            # finite
+        sd = torch.load("checkpoints/SimulGen-VAE.pth", weights_only=False)
+        # the checkpoint layout of the reference at this toy preset (weight_orig / weight_u / weight_v ...)
+        ref = ref_import.build_reference_vae(dict(cfg, batch=4, small=True, lossfun="MSE"))
+        assert list(sd.keys()) == list(ref.state_dict().keys())
+        for k, v in ref.state_dict().items():
+            assert tuple(sd[k].shape) == tuple(v.shape), k
+        ref.load_state_dict(sd)                                          # engine checkpoint loads into the reference
+        whole = torch.load("model_save/SimulGen-VAE", weights_only=False)
+        assert type(whole).__module__ == "modules.VAE_network" and type(whole).__name__ == "VAE"
+    finally:
+        sg.set_precision("bf16")
+        if ref_import.REFERENCE_ROOT in sys.path:
+            sys.path.remove(ref_import.REFERENCE_ROOT)
+        _purge_modules()
