@@ -177,6 +177,24 @@ CONFIG_CASES = {
 }
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_headline_shape_parity(precision):
+    """configs[1] at FULL size: preset 1 --size=small, N = 95008 nodes (371 full 256-row tile pairs + a 32-row tail),
+    T = 200, 438 M parameters, batch 2 - engine vs the fp32 oracle (cuDNN/cuBLAS fp32, TF32 off) on the same weights,
+    inputs and eps."""
+    cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[1024, 512, 256, 128], num_node=95008, num_time=200, small=True,
+               batch=2, lossfun="MSE")
+    report, greport, worst_a, worst_g, med = _per_layer_report(cfg, precision, tag="headline_95008")
+    torch.cuda.empty_cache()
+    if precision == "fp32":
+        assert worst_a < 2e-5, [r for r in report if r[1] >= 2e-5]
+        assert worst_g < 2e-4, [r for r in greport if r[1] >= 2e-4]
+    else:
+        assert worst_a < 1e-2, [r for r in report if r[1] >= 1e-2]
+        assert med < 1.5e-2, med
+        assert worst_g < 5e-2, [r for r in greport if r[1] >= 5e-2]
+
+
 @pytest.mark.parametrize("case", sorted(CONFIG_CASES))
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_baseline_config_shapes_parity(case, precision):
