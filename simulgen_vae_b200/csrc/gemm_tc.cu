@@ -140,7 +140,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ===================== MMA issuer =====================
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, M=128, N=256, majors per mode
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+            const uint32_t idesc = (1u << 4) | ((uint32_t)p.a_fmt << 7) | ((uint32_t)p.b_fmt << 10) | ((A_MN ? 1u : 0u) << 15) |
                                    ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
@@ -310,6 +310,13 @@ static int pick_splits(int tiles, int iters, int sms) {
     return best;
 }
 
+static void default_formats(TcParams& p) {
+    p.a_fmt = 1;
+    p.b_fmt = 1;
+    const char* e = getenv("SG_TC_FMT");     // experiment: "<a><b>", 0 = fp16, 1 = bf16
+    if (e != nullptr && e[0] && e[1]) { p.a_fmt = e[0] - '0'; p.b_fmt = e[1] - '0'; }
+}
+
 template <int MODE>
 static int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, cudaStream_t st) {
     static bool attr_set = false;
@@ -363,6 +370,7 @@ int tc_fprop(const void* wg, const void* act, int act_planes, long long act_pstr
     if (make_map_wg(&ma, wg, Cin_p, Cout, k)) return 1;
     if (make_map_op(&mb, act, R, Cin, act_planes, act_pstride)) return 1;
     TcParams p{};
+    default_formats(p);
     const bool pair = use_pair(Cout);
     SG_REQUIRE(!out_bf16 || (pair && !accumulate), "conv_fprop: bf16 output needs the CTA-pair kernel (Cout > 128) and no accumulation");
     p.out = (float*)out; p.bias = bias; p.M = Cout; p.N = R; p.ldc = R; p.c_sz = 0;
@@ -414,6 +422,7 @@ int tc_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_pstride
     if (make_map_wg(&ma, wg, Cin_p, Cout, k)) return 1;
     if (make_map_op(&mb, dy, R, Cout, dy_planes, dy_pstride)) return 1;
     TcParams p{};
+    default_formats(p);
     const bool pair = use_pair(Cin);
     p.out = dx; p.bias = nullptr; p.M = Cin; p.N = R; p.ldc = R; p.c_sz = 0;
     p.m_tiles = (int)cdiv(Cin, pair ? pair::PM : BM); p.n_tiles = (int)cdiv(R, BN); p.z_count = 1; p.group_m = 8;
@@ -433,6 +442,7 @@ int tc_wgrad(const void* dy, int dy_planes, long long dy_pstride, const void* ac
     if (make_map_op(&ma, dy, R, Cout, dy_planes, dy_pstride)) return 1;
     if (make_map_op(&mb, act, R, Cin, act_planes, act_pstride)) return 1;
     TcParams p{};
+    default_formats(p);
     const bool pair = use_pair(Cout);
     p.out = dwg; p.bias = nullptr; p.M = Cout; p.N = Cin_p; p.ldc = Cin_p; p.c_sz = (long long)Cout * Cin_p;
     p.m_tiles = (int)cdiv(Cout, pair ? pair::PM : BM); p.n_tiles = (int)cdiv(Cin_p, BN); p.z_count = k; p.group_m = 8;

@@ -193,7 +193,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, M=256 (pair), N=256, majors per mode
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+            const uint32_t idesc = (1u << 4) | ((uint32_t)p.a_fmt << 7) | ((uint32_t)p.b_fmt << 10) | ((A_MN ? 1u : 0u) << 15) |
                                    ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(PM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;

@@ -25,6 +25,7 @@ struct TcParams {
     int group_m;         // pair kernel: m-tiles per raster group
     int b_plane0, b_plane_step;   // B operand plane for tap j (or output tap z): b_plane0 + j * b_plane_step
     int a_plane;                  // wgrad: plane of dy that holds the unshifted gradient
+    int a_fmt, b_fmt;             // operand formats of the kind::f16 MMA: 0 = fp16, 1 = bf16
     // pair kernel, fprop: per-(row, sample) partial GroupNorm statistics taken in the epilogue
     float* rowstat;               // [st_B][M][2] (sum, sum of squares), zeroed by the host; NULL = off
     int st_T, st_Tp, st_B;        // valid columns per sample, row pitch, samples (N == st_B * st_Tp)
