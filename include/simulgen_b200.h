@@ -13,8 +13,9 @@
  *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
  *   - return value: 0 = ok, non-zero = error (sg_last_error() gives the text); the Python side raises
  *     RuntimeError, the reference's only error convention (VAE_network.py:119-121).
- *   - dtype: SG_BF16 (tcgen05 tensor-core path, bf16 operands + fp32 accumulation) or SG_F32
- *     (fp32 validation mode, SIMT kernels, no tensor cores).
+ *   - dtype: SG_BF16 (tcgen05 tensor-core path, bf16 operands + fp32 accumulation), SG_F16 (the same kernels with
+ *     IEEE fp16 operands: 3 more mantissa bits at the same tensor-core rate; gradients need loss scaling) or SG_F32
+ *     (fp32 validation mode, SIMT kernels, no tensor cores).  One 16-bit format per process at a time.
  *   - internal activation layout "CR": [C][B][Tp] with Tp = roundup(T + 2, 8); entries t >= T of
  *     every (c, b) row are zero (they are the conv "same" padding shared by neighbouring samples),
  *     R = B * Tp.  External layout (reference): [B][C][T] fp32 (SimulGen-VAE.py:281-283).
@@ -35,7 +36,7 @@
 extern "C" {
 #endif
 
-enum { SG_BF16 = 0, SG_F32 = 1 };
+enum { SG_BF16 = 0, SG_F32 = 1, SG_F16 = 2 };
 enum { SG_ACT_NONE = 0, SG_ACT_GELU = 1, SG_ACT_TANH = 2 };
 enum { SG_LOSS_MSE = 0, SG_LOSS_MAE = 1, SG_LOSS_SMOOTHL1 = 2, SG_LOSS_HUBER = 3 };
 

@@ -8,10 +8,11 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsimulgen_b200.so")
+LIB_PATH = os.environ.get("SIMULGEN_B200_LIB") or os.path.join(_HERE, "libsimulgen_b200.so")
+LIB_PATH_FP16 = os.path.join(_HERE, "libsimulgen_b200_fp16.so")      # same sources, -DSG_OP16_HALF
 
-_lib = None
-_err = None
+_libs = {}
+_errs = {}
 
 c_void_p, c_int, c_float, c_double = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double
 c_ll, c_ull = ctypes.c_longlong, ctypes.c_ulonglong
@@ -67,22 +68,23 @@ class OptItem(ctypes.Structure):
                 ("k", c_int), ("flip", c_int), ("reserved", c_int)]
 
 
-def load():
-    """Load the shared library once; raises RuntimeError (never falls back) when unavailable."""
-    global _lib, _err
-    if _lib is not None:
-        return _lib
-    if _err is not None:
-        raise RuntimeError(_err)
-    if not os.path.isfile(LIB_PATH):
-        _err = ("simulgen_b200: %s not found - build the CUDA extension first "
-                "(python -m simulgen_vae_b200.build); there is no CPU fallback" % LIB_PATH)
-        raise RuntimeError(_err)
+def load(half=False):
+    """Load a library variant once (bf16 operands by default, fp16 operands with half=True); raises RuntimeError (never
+    falls back) when unavailable."""
+    if half in _libs:
+        return _libs[half]
+    if half in _errs:
+        raise RuntimeError(_errs[half])
+    path = LIB_PATH_FP16 if half else LIB_PATH
+    if not os.path.isfile(path):
+        _errs[half] = ("simulgen_b200: %s not found - build the CUDA extension first "
+                       "(python -m simulgen_vae_b200.build); there is no CPU fallback" % path)
+        raise RuntimeError(_errs[half])
     try:
-        lib = ctypes.CDLL(LIB_PATH)
+        lib = ctypes.CDLL(path)
     except OSError as e:  # pragma: no cover
-        _err = "simulgen_b200: cannot load %s: %s" % (LIB_PATH, e)
-        raise RuntimeError(_err)
+        _errs[half] = "simulgen_b200: cannot load %s: %s" % (path, e)
+        raise RuntimeError(_errs[half])
     lib.sg_last_error.restype = ctypes.c_char_p
     lib.sg_last_error.argtypes = []
     lib.sg_version.restype = c_int
@@ -91,12 +93,12 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = c_int
-    _lib = lib
+    _libs[half] = lib
     return lib
 
 
-def call(name, *args):
-    lib = load()
+def call(name, *args, half=False):
+    lib = load(half)
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError("simulgen_b200 %s failed (%d): %s" % (name, rc, lib.sg_last_error().decode()))

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
@@ -22,9 +23,11 @@ int check_launch(const char* what);
     } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline bool is_op16(int dtype) { return dtype == SG_BF16 || dtype == SG_F16; }
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
 constexpr float kGnEps = 1e-5f;
+
 
 // ---------------------------------------------------------------------------------------------
 // 8-element vector access for fp32 / bf16 rows (rows are 8-element aligned: Tp % 8 == 0)
@@ -41,13 +44,40 @@ __device__ __forceinline__ F8 load8(const float* p) {
     r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
     return r;
 }
+// 16-bit operands.  Every 16-bit tensor of the engine is typed __nv_bfloat16 in the kernels; whether the bits are
+// bf16 or IEEE fp16 ("fp16" precision mode: 3 more mantissa bits, tcgen05 kind::f16 runs both at the same rate) is a
+// compile-time constant of the LIBRARY: the sources are built twice (libsimulgen_b200.so and, with -DSG_OP16_HALF,
+// libsimulgen_b200_fp16.so) and the Python side calls the one that matches the operand dtype.  (A run-time switch in
+// constant memory was measured at -1.6 % step throughput: these kernels are issue-bound.)
+#ifdef SG_OP16_HALF
+constexpr bool c_op16_half = true;
+#else
+constexpr bool c_op16_half = false;
+#endif
+// every entry point that takes a dtype checks that this library variant handles it
+#define SG_CHECK_OP16(dtype)                                                                                         \
+    SG_REQUIRE((dtype) != (sg::c_op16_half ? SG_BF16 : SG_F16), "this build of libsimulgen_b200 handles %s operands", \
+               sg::c_op16_half ? "fp16 (and fp32)" : "bf16 (and fp32)")
+
+__device__ __forceinline__ float2 op16x2_to_f2(uint32_t bits) {
+    if (c_op16_half) return __half22float2(*reinterpret_cast<const __half2*>(&bits));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bits));
+}
+__device__ __forceinline__ uint32_t f2_to_op16x2(float a, float b) {
+    if (c_op16_half) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ F8 load8(const __nv_bfloat16* p) {
     F8 r;
     uint4 raw = *reinterpret_cast<const uint4*>(p);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float2 f = __bfloat1622float2(h[i]);
+        float2 f = op16x2_to_f2(w[i]);
         r.v[2 * i] = f.x;
         r.v[2 * i + 1] = f.y;
     }
@@ -59,15 +89,25 @@ __device__ __forceinline__ void store8(float* p, const F8& r) {
 }
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const F8& r) {
     uint4 raw;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+    uint32_t* w = reinterpret_cast<uint32_t*>(&raw);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) w[i] = f2_to_op16x2(r.v[2 * i], r.v[2 * i + 1]);
     *reinterpret_cast<uint4*>(p) = raw;
 }
 __device__ __forceinline__ float to_f(float x) { return x; }
-__device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ float to_f(__nv_bfloat16 x) {
+    if (c_op16_half) return __half2float(*reinterpret_cast<const __half*>(&x));
+    return __bfloat162float(x);
+}
 __device__ __forceinline__ void from_f(float& d, float x) { d = x; }
-__device__ __forceinline__ void from_f(__nv_bfloat16& d, float x) { d = __float2bfloat16_rn(x); }
+__device__ __forceinline__ void from_f(__nv_bfloat16& d, float x) {
+    if (c_op16_half) {
+        __half h = __float2half_rn(x);
+        d = *reinterpret_cast<__nv_bfloat16*>(&h);
+    } else {
+        d = __float2bfloat16_rn(x);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // shifted operand planes.  TMA moves 16-byte granules, so a conv tap cannot be a 1-element shift of

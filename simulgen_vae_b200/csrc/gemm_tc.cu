@@ -311,9 +311,8 @@ static int pick_splits(int tiles, int iters, int sms) {
 }
 
 static void default_formats(TcParams& p) {
-    p.a_fmt = 1;
-    p.b_fmt = 1;
-    const char* e = getenv("SG_TC_FMT");     // experiment: "<a><b>", 0 = fp16, 1 = bf16
+    p.a_fmt = p.b_fmt = c_op16_half ? 0 : 1;    // kind::f16 operand formats: 0 = fp16, 1 = bf16
+    const char* e = getenv("SG_TC_FMT");     // experiment (scripts/fmt_experiment.py): "<a><b>", 0 = fp16, 1 = bf16
     if (e != nullptr && e[0] && e[1]) { p.a_fmt = e[0] - '0'; p.b_fmt = e[1] - '0'; }
 }
 
@@ -473,6 +472,7 @@ extern "C" {
 
 int sg_conv_fprop(const void* wg, const void* act, int act_planes, long long act_pstride, const float* bias,
                   float* out, int Cin, int Cin_p, int Cout, int k, int R, int accumulate, int dtype, void* stream) {
+    SG_CHECK_OP16(dtype);
     SG_CONV_CHECK("conv_fprop", act_planes);
     if (dtype == SG_F32)
         return simt_fprop((const float*)wg, (const float*)act + (long long)(act_planes / 2) * act_pstride, bias, out, Cin,
@@ -484,6 +484,7 @@ int sg_conv_fprop(const void* wg, const void* act, int act_planes, long long act
 int sg_conv_fprop_gn(const void* wg, const void* act, int act_planes, long long act_pstride, const float* bias, void* out,
                      int out_bf16, int Cin, int Cin_p, int Cout, int k, int B, int T, int Tp, int G, float* stats,
                      double* ws, float* rowstat, int dtype, void* stream) {
+    SG_CHECK_OP16(dtype);
     const int R = B * Tp;
     SG_CONV_CHECK("conv_fprop_gn", act_planes);
     SG_REQUIRE(G > 0 && Cout % G == 0 && stats != nullptr && ws != nullptr, "conv_fprop_gn: bad GroupNorm arguments");
@@ -509,6 +510,7 @@ int sg_conv_fprop_gn(const void* wg, const void* act, int act_planes, long long 
 
 int sg_conv_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_pstride, float* dx, int Cin, int Cin_p,
                   int Cout, int k, int R, int accumulate, int dtype, void* stream) {
+    SG_CHECK_OP16(dtype);
     SG_CONV_CHECK("conv_dgrad", dy_planes);
     if (dtype == SG_F32)
         return simt_dgrad((const float*)wg, (const float*)dy + (long long)(dy_planes / 2) * dy_pstride, dx, Cin, Cin_p,
@@ -519,6 +521,7 @@ int sg_conv_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_ps
 int sg_conv_wgrad(const void* dy, int dy_planes, long long dy_pstride, const void* act, int act_planes,
                   long long act_pstride, float* dwg, int Cin, int Cin_p, int Cout, int k, int R, int dtype,
                   void* stream) {
+    SG_CHECK_OP16(dtype);
     SG_CONV_CHECK("conv_wgrad", act_planes);
     SG_REQUIRE(dy_planes & 1, "conv_wgrad: dy_planes must be odd");
     if (dtype == SG_F32)

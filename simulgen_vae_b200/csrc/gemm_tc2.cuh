@@ -307,8 +307,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                 const float* sp = slab + rl * EPI_PITCH + sub_c;
                                 float4 r = make_float4(sp[0], sp[1], sp[2], sp[3]);
                                 if (p.out_bf16) {
-                                    __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
-                                    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                                    uint2 pk = make_uint2(f2_to_op16x2(r.x, r.y), f2_to_op16x2(r.z, r.w));
                                     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(obase) + (long long)m * p.ldc + n) = pk;
                                 } else {
                                     float* dst = obase + (long long)m * p.ldc + n;

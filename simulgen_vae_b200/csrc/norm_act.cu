@@ -1039,13 +1039,14 @@ using namespace sg;
 extern "C" {
 
 int sg_pack_input(const float* x, void* out, int B, int N, int T, int Tp, int dtype, void* stream) {
+    SG_CHECK_OP16(dtype);
     SG_REQUIRE(Tp % 8 == 0 && Tp >= T, "pack_input: bad Tp=%d for T=%d", Tp, T);
     long long rows = (long long)N * B;
     int grid = persistent_grid(rows) * 2;
     bool vec = (T % 4 == 0) && aligned16(x);
     cudaStream_t st = as_stream(stream);
 #define SG_PACK(OT, VEC) pack_input_kernel<OT, VEC><<<grid, kThreads, 0, st>>>(x, (OT*)out, B, N, T, Tp)
-    if (dtype == SG_BF16) { if (vec) SG_PACK(__nv_bfloat16, true); else SG_PACK(__nv_bfloat16, false); }
+    if (is_op16(dtype)) { if (vec) SG_PACK(__nv_bfloat16, true); else SG_PACK(__nv_bfloat16, false); }
     else                  { if (vec) SG_PACK(float, true); else SG_PACK(float, false); }
 #undef SG_PACK
     return check_launch("pack_input");
@@ -1064,9 +1065,10 @@ int sg_axpy_f32(float* dst, const float* src, float alpha, long long n, int accu
 }
 
 int sg_cast_f32(const float* in, void* out, long long n, int dtype, void* stream) {
+    SG_CHECK_OP16(dtype);
     if (n <= 0) return 0;
     int grid = (int)(cdiv(n, 256) < 148 * 16 ? cdiv(n, 256) : 148 * 16);
-    if (dtype == SG_BF16)
+    if (is_op16(dtype))
         cast_f32_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(in, (__nv_bfloat16*)out, n);
     else
         cast_f32_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(in, (float*)out, n);
@@ -1093,12 +1095,13 @@ int sg_gn_stats(const float* y, double* ws, float* mr, int C, int B, int T, int 
 int sg_gn_act_fwd(const float* y, const float* mr, const float* gamma, const float* beta, const void* res,
                   int res_is_f32, float res_scale, int act, int post_gelu, void* out_op, int planes,
                   long long plane_stride, float* out_f32, int C, int B, int T, int Tp, int G, int dtype, void* stream) {
+    SG_CHECK_OP16(dtype);
     SG_REQUIRE(Tp % 8 == 0, "gn_act_fwd: Tp %% 8 != 0");
     SG_REQUIRE(planes == 1 || planes == 3 || planes == 5, "gn_act_fwd: planes must be 1, 3 or 5");
     SG_REQUIRE(mr == nullptr || (G > 0 && C % G == 0), "gn_act_fwd: bad groups");
     cudaStream_t st = as_stream(stream);
     if (G <= 0) G = 1;
-    if (dtype == SG_BF16) {
+    if (is_op16(dtype)) {
         if (res == nullptr || res_is_f32)
             return launch_fwd<__nv_bfloat16, float>(act, post_gelu, y, mr, gamma, beta, res, res_scale, out_op, planes,
                                                     plane_stride, out_f32, C, B, T, Tp, G, st);
@@ -1113,6 +1116,7 @@ int sg_gn_act_bwd(const float* y, const float* mr, const float* gamma, const flo
                   int res_is_f32, float res_scale, int act, int post_gelu, const float* dout, void* dy, int planes,
                   long long plane_stride, float* dgamma, float* dbeta, float* dbias, float* dres, int dres_accumulate,
                   double* ws, int C, int B, int T, int Tp, int G, int dtype, void* stream) {
+    SG_CHECK_OP16(dtype);
     SG_REQUIRE(Tp % 8 == 0, "gn_act_bwd: Tp %% 8 != 0");
     SG_REQUIRE(planes == 1 || planes == 3 || planes == 5, "gn_act_bwd: planes must be 1, 3 or 5");
     SG_REQUIRE(mr == nullptr || (G > 0 && C % G == 0 && dgamma && dbeta && ws), "gn_act_bwd: bad GN arguments");
@@ -1122,7 +1126,7 @@ int sg_gn_act_bwd(const float* y, const float* mr, const float* gamma, const flo
     p.C = C; p.B = B; p.T = T; p.Tp = Tp; p.G = G;
     p.inv_n = mr ? 1.0 / ((double)(C / G) * T) : 0.0;
     cudaStream_t st = as_stream(stream);
-    if (dtype == SG_BF16) {
+    if (is_op16(dtype)) {
         if (res == nullptr || res_is_f32)
             return launch_bwd<__nv_bfloat16, float>(act, post_gelu, p, (__nv_bfloat16*)dy, planes, plane_stride, dgamma, dbeta,
                                                     dbias, dres, dres_accumulate, ws, st);
@@ -1136,6 +1140,7 @@ int sg_gn_act_bwd(const float* y, const float* mr, const float* gamma, const flo
 int sg_recon_fwd(const void* y, int y_dtype, const float* mr, const float* gamma, const float* beta, const float* x,
                  float* x_hat, double* loss_sums, float* rowsums, int N, int B, int T, int Tp, int G, int loss_kind,
                  void* stream) {
+    SG_CHECK_OP16(y_dtype);
     SG_REQUIRE(G > 0 && N % G == 0, "recon_fwd: N=%d not divisible by G=%d", N, G);
     SG_REQUIRE(rowsums == nullptr || (x != nullptr && aligned16(rowsums)), "recon_fwd: rowsums needs x and 16-byte alignment");
     cudaStream_t st = as_stream(stream);
@@ -1143,7 +1148,7 @@ int sg_recon_fwd(const void* y, int y_dtype, const float* mr, const float* gamma
     bool vec = (T % 4 == 0) && aligned16(x) && aligned16(x_hat);
     int grid = persistent_grid((long long)N * B) * 2;
     const bool mse = loss_kind == SG_LOSS_MSE;
-    const bool ybf = y_dtype == SG_BF16;
+    const bool ybf = is_op16(y_dtype);
     if (vec && x != nullptr && (T & 7) == 0 && (long long)N * B < (1LL << 31)) {
         grid = persistent_grid(N);                           // one warp per channel
 #define SG_FAST(YT, MSE, RS, XH) \
@@ -1174,9 +1179,10 @@ int sg_recon_bwd(const void* y, int y_dtype, const float* mr, const float* gamma
                  const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext, const float* rowsums,
                  void* dy, float* dgamma, float* dbeta, float* dbias, double* ws, int N, int B, int T, int Tp, int G,
                  int loss_kind, int dtype, void* stream) {
+    SG_CHECK_OP16(dtype);
     SG_REQUIRE(G > 0 && N % G == 0 && Tp % 8 == 0, "recon_bwd: bad shape");
     SG_REQUIRE(x != nullptr || (g_loss == nullptr && g_mse == nullptr), "recon_bwd: loss gradient without x");
-    SG_REQUIRE(y_dtype == SG_F32 || dtype == SG_BF16, "recon_bwd: bf16 y only in bf16 mode");
+    SG_REQUIRE(y_dtype == SG_F32 || y_dtype == dtype, "recon_bwd: a 16-bit y needs the same 16-bit mode");
     cudaStream_t st = as_stream(stream);
     double inv_n = 1.0 / ((double)(N / G) * T);
     // workspace: 2*B*G doubles for S followed by 2 floats for the folded scalars
@@ -1186,7 +1192,7 @@ int sg_recon_bwd(const void* y, int y_dtype, const float* mr, const float* gamma
     cudaMemsetAsync(dbias, 0, sizeof(float) * N, st);
     recon_scalars_kernel<<<1, 1, 0, st>>>(g_loss, g_mse, inv_numel, scal);
     int grid = persistent_grid((long long)N * B) * 2;
-    const bool ybf = y_dtype == SG_BF16;
+    const bool ybf = is_op16(y_dtype);
     typedef __nv_bfloat16 bf;
     if (rowsums != nullptr && dxhat_ext == nullptr && x != nullptr) {
         // one pass over y / x: the reductions of the GroupNorm backward were taken by the forward
@@ -1201,7 +1207,7 @@ int sg_recon_bwd(const void* y, int y_dtype, const float* mr, const float* gamma
 #define SG_AF(YT, OT, MSE) \
     recon_bwd_apply_fast_kernel<YT, OT, MSE><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, x, scal, S, (OT*)dy, dbias, \
                                                                         N, B, T, Tp, G, loss_kind, (float)inv_n)
-            if (dtype == SG_BF16) {
+            if (is_op16(dtype)) {
                 if (ybf) { if (mse) SG_AF(bf, bf, true); else SG_AF(bf, bf, false); }
                 else     { if (mse) SG_AF(float, bf, true); else SG_AF(float, bf, false); }
             } else {
@@ -1216,7 +1222,7 @@ int sg_recon_bwd(const void* y, int y_dtype, const float* mr, const float* gamma
 #define SG_APPLY2(YT, OT) do { \
         if (vec) { if (mse) SG_APPLY(YT, OT, true, true); else SG_APPLY(YT, OT, true, false); } \
         else     { if (mse) SG_APPLY(YT, OT, false, true); else SG_APPLY(YT, OT, false, false); } } while (0)
-        if (dtype == SG_BF16) { if (ybf) SG_APPLY2(bf, bf); else SG_APPLY2(float, bf); }
+        if (is_op16(dtype)) { if (ybf) SG_APPLY2(bf, bf); else SG_APPLY2(float, bf); }
         else                  SG_APPLY2(float, float);
 #undef SG_APPLY2
 #undef SG_APPLY
@@ -1232,7 +1238,7 @@ int sg_recon_bwd(const void* y, int y_dtype, const float* mr, const float* gamma
         recon_bwd_kernel<YT, OT, true><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (OT*)dy, dbias);       \
         recon_bwd_kernel<YT, OT, false><<<grid, kThreads, 0, st>>>(p, scal, dgamma, dbeta, S, (OT*)dy, dbias);      \
     } while (0)
-    if (dtype == SG_BF16) { if (ybf) SG_TWO(bf, bf); else SG_TWO(float, bf); }
+    if (is_op16(dtype)) { if (ybf) SG_TWO(bf, bf); else SG_TWO(float, bf); }
     else                  SG_TWO(float, float);
 #undef SG_TWO
     return check_launch("recon_bwd");

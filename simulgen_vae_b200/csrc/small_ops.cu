@@ -520,9 +520,10 @@ int sg_sn_power_iter(const float* w_orig, float* u, float* v, float* sigma, floa
 
 int sg_sn_pack_weight(const float* w_orig, const float* sigma, void* wg, int Cout, int Cin, int Cin_p, int k,
                       long long so, long long si, int flip, int dtype, void* stream) {
+    SG_CHECK_OP16(dtype);
     long long total = (long long)k * Cout * Cin_p;
     int grid = (int)cdiv(total, 256);
-    if (dtype == SG_BF16)
+    if (is_op16(dtype))
         sn_pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(w_orig, sigma, (__nv_bfloat16*)wg, Cout, Cin, Cin_p, k, so, si, flip);
     else
         sn_pack_weight_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(w_orig, sigma, (float*)wg, Cout, Cin, Cin_p, k, so, si, flip);
@@ -567,10 +568,11 @@ int sg_head_bwd(const float* h, const float* w_orig, const float* sigma, const f
 
 int sg_latent_fwd(const float* z, const float* w_orig, const float* sigma, const float* bias, void* out, int planes,
                   long long plane_stride, int D, int B, int T, int Tp, int dtype, void* stream) {
+    SG_CHECK_OP16(dtype);
     SG_REQUIRE(planes == 1 || planes == 3 || planes == 5, "latent_fwd: planes must be 1, 3 or 5");
     int grid = (int)cdiv((long long)D * B, 8);
     size_t sm = sizeof(float) * 8 * (Tp + 8);
-    if (dtype == SG_BF16)
+    if (is_op16(dtype))
         latent_fwd_kernel<__nv_bfloat16><<<grid, 256, sm, as_stream(stream)>>>(z, w_orig, sigma, bias, (__nv_bfloat16*)out, planes, plane_stride, D, B, T, Tp);
     else
         latent_fwd_kernel<float><<<grid, 256, sm, as_stream(stream)>>>(z, w_orig, sigma, bias, (float*)out, planes, plane_stride, D, B, T, Tp);
@@ -603,12 +605,13 @@ int sg_reparam_main_bwd(const float* last, const float* eps, const float* dz, co
 int sg_kl2_reparam_fwd(const float* cz, const float* cxz, const float* eps, const float* h, float std_scale,
                        void* zs_op, int planes, long long plane_stride, float* zs_f32, double* kl_sum, int C, int B,
                        int T, int Tp, int dtype, void* stream) {
+    SG_CHECK_OP16(dtype);
     SG_REQUIRE(planes == 1 || planes == 3 || planes == 5, "kl2_reparam_fwd: planes must be 1, 3 or 5");
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(kl_sum, 0, sizeof(double), st);
     int grid = (int)cdiv((long long)C * B, kWarpsPerBlock);
     size_t sm = (planes > 1 && zs_op) ? sizeof(float) * kWarpsPerBlock * (Tp + 8) : 0;
-    if (dtype == SG_BF16)
+    if (is_op16(dtype))
         kl2_reparam_fwd_kernel<__nv_bfloat16><<<grid, kThreads, sm, st>>>(cz, cxz, eps, h, std_scale, (__nv_bfloat16*)zs_op, planes, plane_stride, zs_f32, kl_sum, C, B, T, Tp);
     else
         kl2_reparam_fwd_kernel<float><<<grid, kThreads, sm, st>>>(cz, cxz, eps, h, std_scale, (float*)zs_op, planes, plane_stride, zs_f32, kl_sum, C, B, T, Tp);

@@ -191,6 +191,7 @@ using namespace sg;
 
 extern "C" int sg_sn_prepare(const sg_sn_layer* layers_dev, const sg_sn_layer* layers_host, int n_layers, float* ws_base,
                              long long ws_elems, int training, int dtype, void* stream) {
+    SG_CHECK_OP16(dtype);
     SG_REQUIRE(n_layers > 0 && n_layers <= kMaxLayers, "sn_prepare: n_layers=%d out of range (max %d)", n_layers, kMaxLayers);
     cudaStream_t st = as_stream(stream);
     SnPrefix p1, p2, p4;
@@ -224,7 +225,7 @@ extern "C" int sg_sn_prepare(const sg_sn_layer* layers_dev, const sg_sn_layer* l
     }
     sn_p3_kernel<<<n_layers, 1024, 0, st>>>(layers_dev, training);
     if (t4 > 0) {
-        if (dtype == SG_BF16) sn_p4_kernel<__nv_bfloat16><<<(unsigned)t4, kSnThreads, 0, st>>>(layers_dev, p4);
+        if (is_op16(dtype)) sn_p4_kernel<__nv_bfloat16><<<(unsigned)t4, kSnThreads, 0, st>>>(layers_dev, p4);
         else sn_p4_kernel<float><<<(unsigned)t4, kSnThreads, 0, st>>>(layers_dev, p4);
     }
     return check_launch("sn_prepare");

@@ -27,10 +27,11 @@ _PRECISION = os.environ.get("SIMULGEN_B200_PRECISION", "bf16")
 
 
 def set_precision(p: str):
-    """'bf16' (tcgen05 tensor cores) or 'fp32' (validation mode, SIMT kernels)."""
+    """'bf16' (tcgen05 tensor cores, default), 'fp16' (the same kernels with IEEE fp16 operands: ~8x smaller rounding
+    error at the same speed; the backward needs loss scaling - Trainer applies it) or 'fp32' (validation mode, SIMT)."""
     global _PRECISION
-    if p not in ("bf16", "fp32"):
-        raise ValueError("precision must be 'bf16' or 'fp32'")
+    if p not in ("bf16", "fp16", "fp32"):
+        raise ValueError("precision must be 'bf16', 'fp16' or 'fp32'")
     _PRECISION = p
 
 
@@ -43,7 +44,7 @@ def tp_of(T: int, precision: str = None) -> int:
     of 16 bytes) - the taps of a k-tap conv read pre-shifted operand planes, so no zero gap between samples is
     needed.  fp32 validation mode: the SIMT GEMMs shift along the flattened (sample, time) axis and rely on a
     zero gap of >= 2 columns (k <= 5) between samples."""
-    if (precision or _PRECISION) == "bf16":
+    if (precision or _PRECISION) in ("bf16", "fp16"):
         return (T + 7) // 8 * 8
     return (T + 2 + 7) // 8 * 8
 
@@ -279,7 +280,7 @@ class Ctx:
         self.B, self.T, self.Tp = B, T, tp_of(T)
         self.dev = device
         self.tape = [] if record else None
-        self.op_dtype = torch.bfloat16 if _PRECISION == "bf16" else torch.float32
+        self.op_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(_PRECISION, torch.float32)
         self.pgrads = {}
         self.capture = capture
         self.sink = get_grad_sink() if record else None
@@ -848,8 +849,8 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     N, G = p.Cout, gn.num_groups
     # bf16 mode: the pre-norm output of the recon conv (the largest tensor of the step, read by the forward and the
     # backward head kernels) is stored as bf16; its GroupNorm statistics are taken from the fp32 accumulators
-    y_bf16 = ctx.op_dtype == torch.bfloat16 and N > 128
-    y = torch.empty(N, B, Tp, dtype=torch.bfloat16 if y_bf16 else torch.float32, device=ctx.dev)
+    y_16 = ctx.op_dtype != torch.float32 and N > 128
+    y = torch.empty(N, B, Tp, dtype=ctx.op_dtype if y_16 else torch.float32, device=ctx.dev)
     stats = ctx.f32(B, G, 2)
     K.conv_fprop_gn(p.wg, out.data, conv.bias, y, p.Cin, stats, T, G)
     want_xhat = want_xhat and (_materialize_xhat() or x is None)

@@ -12,7 +12,8 @@ import torch
 
 from . import _lib
 
-SG_BF16, SG_F32 = 0, 1
+SG_BF16, SG_F32, SG_F16 = 0, 1, 2
+OP16 = (torch.bfloat16, torch.float16)
 ACT_NONE, ACT_GELU, ACT_TANH = 0, 1, 2
 LOSS_KINDS = {"MSE": 0, "MAE": 1, "smoothL1": 2, "Huber": 3}
 
@@ -32,11 +33,19 @@ def _timed(name, flops, fn):
     PROFILE.append((name, flops, e0, e1))
 
 
+_HALF = False         # library variant of the next call: set by _dt() whenever a 16-bit operand is seen
+
+
 def _dt(t):
+    global _HALF
     if t.dtype == torch.bfloat16:
+        _HALF = False
         return SG_BF16
     if t.dtype == torch.float32:
         return SG_F32
+    if t.dtype == torch.float16:
+        _HALF = True
+        return SG_F16
     raise RuntimeError("simulgen_b200: unsupported operand dtype %s" % t.dtype)
 
 
@@ -75,12 +84,12 @@ def _call(name, *args):
     global LAUNCHES
     LAUNCHES += 1
     if PROFILE_ALL is None:
-        _lib.call(name, *args)
+        _lib.call(name, *args, half=_HALF)
         return
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    _lib.call(name, *args)
+    _lib.call(name, *args, half=_HALF)
     e1.record()
     PROFILE_ALL.append((name, e0, e1))
 
@@ -152,9 +161,9 @@ def conv_fprop_gn(wg, act, bias, out, Cin, stats, T, G):
     ap, an, astr = _planes(act)
     B, Tp = act.shape[2], act.shape[3]
     assert act.shape[1] == Cin and out.shape[0] == Cout and out.numel() == Cout * B * Tp and wg.dtype == act.dtype
-    out_bf16 = int(out.dtype == torch.bfloat16)
+    out_bf16 = int(out.dtype in OP16)
     ws = torch.empty(2 * B * G, dtype=torch.float64, device=out.device)
-    rowstat = torch.empty(2 * Cout * B, dtype=torch.float32, device=out.device) if act.dtype == torch.bfloat16 else None
+    rowstat = torch.empty(2 * Cout * B, dtype=torch.float32, device=out.device) if act.dtype in OP16 else None
     _timed("fprop", 2.0 * Cin * Cout * k * B * Tp, lambda: _call(
         "sg_conv_fprop_gn", _p(wg), ap, an, astr, _p(bias), _p(out), out_bf16, Cin, Cin_p, Cout, k, B, T, Tp, int(G),
         _p(_f32(stats, "stats")), _p(ws), _p(rowstat), _dt(act), _stream()))
@@ -346,7 +355,7 @@ class SnPlan:
     def __init__(self, layers, device, dtype):
         import ctypes
         self.layers = layers
-        self.dtype = SG_BF16 if dtype == torch.bfloat16 else SG_F32
+        self.dtype = {torch.bfloat16: SG_BF16, torch.float16: SG_F16}.get(dtype, SG_F32)
         total = sum(L["Cin"] * L["k"] + L["H"] + 8 for L in layers if L.get("u") is not None)
         self.ws = torch.zeros(max(total, 1), dtype=torch.float32, device=device)
         arr = (_lib.SnLayer * len(layers))()

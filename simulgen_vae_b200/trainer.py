@@ -49,7 +49,7 @@ def _gemm_layout_elems(mod):
 
 class Trainer:
     def __init__(self, model, lr=1e-3, alpha=1.0e6, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                 process_group=None, bucket_mb=64, fused=True, materialize_xhat=False):
+                 process_group=None, bucket_mb=64, fused=True, materialize_xhat=False, loss_scale=None):
         self.model = model
         self.lr, self.alpha, self.betas, self.eps, self.wd = lr, alpha, betas, eps, weight_decay
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -65,6 +65,10 @@ class Trainer:
             self.world = torch.distributed.get_world_size(process_group)
         self.bucket_elems = bucket_mb * (1 << 20) // 4
         self.fused = fused
+        # fp16 mode: gradients are stored as fp16 GEMM operands, so the loss is scaled by a power of two before backward
+        # and the optimiser divides it out again (everything in between is linear).  None = automatic: numel/alpha
+        # rounded to a power of two puts the reconstruction-loss gradient at O(1); bf16 / fp32 need none.
+        self.loss_scale = loss_scale
         self.materialize_xhat = materialize_xhat      # the step only needs the losses; x_hat stays in registers
         self._last = None
         self.sink = None
@@ -173,7 +177,13 @@ class Trainer:
         engine.set_sample_offset(sample_offset)
         engine.set_packed_input(packed)
         b1, b2 = self.betas
-        scale = 1.0 / self.world
+        S = self.loss_scale
+        if S is None:
+            S = 1.0
+            if engine.get_precision() == "fp16":
+                import math
+                S = 2.0 ** max(-24, min(24, round(math.log2(x.numel() / max(self.alpha, 1e-30)))))
+        scale = 1.0 / (self.world * S)
         self.gnorm_sq.zero_()
         if self.fused:
             self.sink.begin_step()
@@ -185,7 +195,7 @@ class Trainer:
                 for k in kls[1:]:
                     kl_sum = kl_sum + k
                 loss = recon * self.alpha + kl_sum * beta
-                loss.backward()
+                (loss * S if S != 1.0 else loss).backward()
             finally:
                 engine.set_grad_sink(None)
                 engine.set_materialize_xhat(True)
@@ -202,7 +212,7 @@ class Trainer:
             for k in kls[1:]:
                 kl_sum = kl_sum + k
             loss = recon * self.alpha + kl_sum * beta
-            loss.backward()
+            (loss * S if S != 1.0 else loss).backward()
             self._allreduce_grads()
             self.step_count += 1
             for p in self.params:

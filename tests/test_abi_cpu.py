@@ -16,12 +16,13 @@ def header_symbols():
 
 def test_library_exports_every_declared_symbol():
     from simulgen_vae_b200 import build, _lib
-    path = build.build()
-    lib = ctypes.CDLL(path)
+    build.build()
     names = header_symbols()
     assert len(names) >= 30
-    missing = [n for n in names if not hasattr(lib, n)]
-    assert not missing, missing
+    for path in (build.OUT, build.OUT_FP16):          # bf16-operand and fp16-operand builds of the same sources
+        lib = ctypes.CDLL(path)
+        missing = [n for n in names if not hasattr(lib, n)]
+        assert not missing, (path, missing)
     bound = set(_lib.SIGNATURES) | {"sg_last_error", "sg_version", "sg_device_supported"}
     assert set(names) <= bound, sorted(set(names) - bound)
     assert bound <= set(names), sorted(bound - set(names))

@@ -123,3 +123,28 @@ def test_tc_fprop_gn_fused_statistics(shape, out_bf16):
     assert rel_l2(o1[:, :, :T].float(), o2[:, :, :T]) < (4e-3 if out_bf16 else 1e-4)
     assert rel_l2(s1[:, :, 0], s2[:, :, 0]) < 1e-3 and (s1[:, :, 0] - s2[:, :, 0]).abs().max() < 1e-4
     assert rel_l2(s1[:, :, 1], s2[:, :, 1]) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(256, 384, 3, 4, 200), (1280, 1280, 5, 2, 200), (24, 72, 3, 3, 21)])
+def test_tc_fp16_operands(shape):
+    """'fp16' precision mode: the same tcgen05 kernels with IEEE fp16 operand formats (kind::f16, fp32 accumulation)."""
+    Cin, Cout, k, B, T = shape
+    wg, act, dy, bias, Tp, Cin_p = make(*shape)
+    wg, act, dy = wg.float().half(), act.float().half(), dy.float().half()
+    o1, o2 = torch.full((Cout, B, Tp), 5.0, device=DEV), torch.empty(Cout, B, Tp, device=DEV)
+    K.conv_fprop(wg, act, bias, o1, Cin)
+    emu.conv_fprop(wg, act, bias, o2, Cin)
+    assert rel_l2(o1[:, :, :T], o2[:, :, :T]) < 1e-4
+    d1, d2 = torch.empty(Cin, B, Tp, device=DEV), torch.empty(Cin, B, Tp, device=DEV)
+    K.conv_dgrad(wg, dy, d1, Cin)
+    emu.conv_dgrad(wg, dy, d2, Cin)
+    assert rel_l2(d1[:, :, :T], d2[:, :, :T]) < 1e-4
+    w1, w2 = torch.empty(k, Cout, Cin_p, device=DEV), torch.empty(k, Cout, Cin_p, device=DEV)
+    K.conv_wgrad(dy, act, w1, Cin)
+    emu.conv_wgrad(dy, act, w2, Cin)
+    assert rel_l2(w1[:, :, :Cin], w2[:, :, :Cin]) < 1e-4
+    # back to bf16 in the same process: the format is selected per call
+    wgb, actb, _, _, _, _ = make(*shape)
+    K.conv_fprop(wgb, actb, bias, o1, Cin)
+    emu.conv_fprop(wgb, actb, bias, o2, Cin)
+    assert rel_l2(o1[:, :, :T], o2[:, :, :T]) < 1e-4

@@ -177,7 +177,7 @@ CONFIG_CASES = {
 }
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_headline_shape_parity(precision):
     """configs[1] at FULL size: preset 1 --size=small, N = 95008 nodes (371 full 256-row tile pairs + a 32-row tail),
     T = 200, 438 M parameters, batch 2 - engine vs the fp32 oracle (cuDNN/cuBLAS fp32, TF32 off) on the same weights,
@@ -189,10 +189,22 @@ def test_headline_shape_parity(precision):
     if precision == "fp32":
         assert worst_a < 2e-5, [r for r in report if r[1] >= 2e-5]
         assert worst_g < 2e-4, [r for r in greport if r[1] >= 2e-4]
+    elif precision == "fp16":
+        # the north-star bound (1e-2 per layer, outputs AND gradients) holds in the fp16-operand mode
+        assert worst_a < 1e-2, [r for r in report if r[1] >= 1e-2]
+        assert worst_g < 1e-2, [r for r in greport if r[1] >= 1e-2]
     else:
         assert worst_a < 1e-2, [r for r in report if r[1] >= 1e-2]
         assert med < 1.5e-2, med
         assert worst_g < 5e-2, [r for r in greport if r[1] >= 5e-2]
+
+
+def test_fp16_mode_meets_north_star_bound_medium():
+    """Same tensor-core kernels, fp16 operand formats: every per-layer activation and every parameter gradient within
+    1e-2 relative L2 of the fp32 oracle (north_star's bound) on the medium model."""
+    report, greport, worst_a, worst_g, med = _per_layer_report(MEDIUM, "fp16")
+    assert worst_a < 1e-2, [r for r in report if r[1] >= 1e-2]
+    assert worst_g < 1e-2, [r for r in greport if r[1] >= 1e-2]
 
 
 @pytest.mark.parametrize("case", sorted(CONFIG_CASES))
@@ -240,7 +252,7 @@ def test_elbo_curve_100_steps_within_1_percent():
         assert float(dev) < tol, (precision, float(dev))
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_trainer_fused_step_equals_per_tensor_path(precision):
     """Trainer(fused=True): gradients stay in the GEMM-layout arena and sg_opt_step applies the spectral-norm
     backward + AdamW; it must reproduce the per-parameter path (p.grad + sg_adamw_step) step for step."""
@@ -261,7 +273,7 @@ def test_trainer_fused_step_equals_per_tensor_path(precision):
     # fp32: same arithmetic up to summation order.  bf16: the order of the split-K / row atomics decides a few
     # 1-ulp bf16 roundings of dy, and AdamW's m/sqrt(v) turns that into O(lr) noise on noise-dominated
     # gradients (conv biases in front of a GroupNorm), so only a loose bound is meaningful there.
-    tol = 1e-4 if precision == "fp32" else 2e-2
+    tol = 1e-4 if precision == "fp32" else 2e-2        # fp16: also exercises the Trainer's automatic loss scale
     for k in sa:
         assert rel_l2(sa[k], sb[k]) < tol, (k, rel_l2(sa[k], sb[k]))
     for a, b in zip(ca, cb):
