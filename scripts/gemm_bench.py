@@ -62,9 +62,16 @@ for name, Cin, Cout, k in SHAPES:
     dx = torch.empty(Cin, B, Tp, device=dev)
     dwg = torch.empty(k, Cout, Cin_p, device=dev)
     flops = 2.0 * Cin * Cout * k * B * T
-    for mode, fn in (("fprop", lambda: K.conv_fprop(wg, act, bias, out, Cin)),
+    G = 8
+    stats = torch.empty(B, G, 2, device=dev)
+    out16 = torch.empty(Cout, B, Tp, device=dev, dtype=torch.bfloat16) if Cout > 128 else None
+    variants = [("fprop", lambda: K.conv_fprop(wg, act, bias, out, Cin)),
+                ("fp+gn", lambda: K.conv_fprop_gn(wg, act, bias, out, Cin, stats, T, G))]
+    if out16 is not None and "recon" in name:
+        variants.append(("gn16", lambda: K.conv_fprop_gn(wg, act, bias, out16, Cin, stats, T, G)))
+    for mode, fn in variants + [
                      ("dgrad", lambda: K.conv_dgrad(wg, dy, dx, Cin)),
-                     ("wgrad", lambda: K.conv_wgrad(dy, act, dwg, Cin))):
+                     ("wgrad", lambda: K.conv_wgrad(dy, act, dwg, Cin))]:
         ms = timed(fn)
         tf = flops / (ms * 1e-3) / 1e12
         print("%-28s %-5s B=%d  %8.3f ms  %7.1f TFLOP/s  %.3f of measured sustained peak (%.0f)" %

@@ -101,6 +101,149 @@ __device__ __forceinline__ PairWork decode_pair_work(const TcParams& p, int w, i
     return r;
 }
 
+// One tile of the epilogue for one warp: TMEM lane quarter q (32 rows, lane = row) x BN columns, in chunks of 32 columns.
+// The tcgen05.ld of chunk c + 1 is in flight while chunk c is processed.  fp32 output: the chunk is staged through a
+// padded smem slab and leaves as 128-byte row segments (plain, accumulate or red.add).  16-bit output (OUT16): values are
+// packed before staging and two chunks (64 columns = 128 bytes per row) leave together as 16-byte stores.
+template <int MODE, bool OUT16>
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, const PairWork& wk, uint32_t tmem_acc, float* slab,
+                                              int m_base, int lane) {
+    const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+    float bias = 0.f;
+    if (p.bias != nullptr && m_base + lane < p.M && wk.split == 0) bias = p.bias[m_base + lane];
+    const bool have_k = wk.it_hi > wk.it_lo;
+    float* obase = p.out + (long long)wk.z * p.c_sz;
+    uint32_t* slab_u = reinterpret_cast<uint32_t*>(slab);
+    // GroupNorm statistics of the tile (fprop, no split-K): this lane's row, running sums of the sample the current
+    // columns belong to; flushed with two atomics whenever the sample changes and at the tile end
+    const bool do_stats = (MODE == MODE_FPROP) && p.rowstat != nullptr;
+    float st_s = 0.f, st_ss = 0.f;
+    int st_b = do_stats ? wk.n0 / p.st_Tp : 0;
+    auto st_flush = [&](int b) {
+        if (m_base + lane < p.M && b < p.st_B) {
+            float* rs = p.rowstat + ((size_t)b * p.M + (m_base + lane)) * 2;
+            atomicAdd(rs, st_s);
+            atomicAdd(rs + 1, st_ss);
+        }
+        st_s = 0.f;
+        st_ss = 0.f;
+    };
+    auto chunk = [&](uint32_t* v, int c) {
+        const int col0 = wk.n0 + c * 32;
+        if (have_k && col0 < p.N) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + bias);
+            if (do_stats) {
+                int b = col0 / p.st_Tp, t = col0 - b * p.st_Tp;
+                if (b != st_b) { st_flush(st_b); st_b = b; }
+                if (t + 32 <= p.st_T && col0 + 32 <= p.N) {
+                    // the usual case: all 32 columns are valid time steps of one sample
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float val = __uint_as_float(v[e]);
+                        st_s += val;
+                        st_ss = fmaf(val, val, st_ss);
+                    }
+                } else if (p.st_Tp >= 32) {
+                    // at most one sample boundary inside the 32 columns: [0, nb) -> sample b, [nb, 32) -> b + 1
+                    const int nb = p.st_Tp - t;
+                    const int lim0 = min(min(nb, p.st_T - t), p.N - col0);
+                    const int lim1 = min(nb + p.st_T, p.N - col0);
+                    float s1 = 0.f, ss1 = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float val = __uint_as_float(v[e]);
+                        if (e < lim0) { st_s += val; st_ss = fmaf(val, val, st_ss); }
+                        if (e >= nb && e < lim1) { s1 += val; ss1 = fmaf(val, val, ss1); }
+                    }
+                    if (nb < 32) {
+                        st_flush(st_b);
+                        st_b = b + 1;
+                        st_s = s1;
+                        st_ss = ss1;
+                    }
+                } else {
+                    // short rows (static fields, Tp = 8): several samples per chunk
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float val = __uint_as_float(v[e]);
+                        if (t < p.st_T && col0 + e < p.N) { st_s += val; st_ss = fmaf(val, val, st_ss); }
+                        if (++t == p.st_Tp) { st_flush(st_b); t = 0; st_b = st_b + 1; }
+                    }
+                }
+            }
+            if (OUT16) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    slab_u[lane * EPI_PITCH + (c & 1) * 16 + e] =
+                        f2_to_op16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) slab_u[lane * EPI_PITCH + e] = v[e];
+                __syncwarp();
+                const int n = col0 + sub_c;
+                if (n < p.N) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rl = i * 4 + sub_r;
+                        const int m = m_base + rl;
+                        if (m < p.M) {
+                            const float* sp = slab + rl * EPI_PITCH + sub_c;
+                            float4 r = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                            float* dst = obase + (long long)m * p.ldc + n;
+                            if (p.atomic) {
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(r.x), "f"(r.y),
+                                             "f"(r.z), "f"(r.w)
+                                             : "memory");
+                            } else {
+                                if (p.accumulate) {
+                                    float4 o = *reinterpret_cast<const float4*>(dst);
+                                    r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+                                }
+                                *reinterpret_cast<float4*>(dst) = r;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (OUT16 && (c & 1)) {
+            // two staged chunks: 32 rows x 64 columns of 16-bit values, 8 lanes x 16 bytes per row
+            const int cbase = col0 - 32;
+            if (have_k && cbase < p.N) {
+                __syncwarp();
+                const int n = cbase + sub_c * 2;
+                if (n < p.N) {
+                    __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(obase);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rl = i * 4 + sub_r;
+                        const int m = m_base + rl;
+                        if (m < p.M) {
+                            const uint32_t* sp = slab_u + rl * EPI_PITCH + sub_c;
+                            *reinterpret_cast<uint4*>(o16 + (long long)m * p.ldc + n) = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    };
+    uint32_t va[32], vb[32];
+    tmem_ld_32x32b_x32(tmem_acc, va);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; c += 2) {
+        tmem_ld_wait_regs(va);
+        tmem_ld_32x32b_x32(tmem_acc + (uint32_t)((c + 1) * 32), vb);
+        chunk(va, c);
+        tmem_ld_wait_regs(vb);
+        if (c + 2 < BN / 32) tmem_ld_32x32b_x32(tmem_acc + (uint32_t)((c + 2) * 32), va);
+        chunk(vb, c + 1);
+    }
+    if (do_stats) st_flush(st_b);
+}
+
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
@@ -229,7 +372,6 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ===================== epilogue (warps 2..5, both CTAs) =====================
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
         float* slab = epi + q * 32 * EPI_PITCH;
-        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
         int tile_iter = 0;
         for (int w = pair_id; w < num_work; w += num_pairs, ++tile_iter) {
             PairWork wk = decode_pair_work(p, w, total_iters);
@@ -238,103 +380,14 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_wait(&tfull_bar[as], aphase);
             tcgen05_fence_after();
             const int m_base = wk.m0 + (int)rank * BMH + q * 32;
-            float bias = 0.f;
-            if (p.bias != nullptr && m_base + lane < p.M && wk.split == 0) bias = p.bias[m_base + lane];
-            const bool have_k = wk.it_hi > wk.it_lo;
-            float* obase = p.out + (long long)wk.z * p.c_sz;
-            // GroupNorm statistics of the tile (fprop, no split-K): this lane's row, running sums of the sample the
-            // current columns belong to; flushed with two atomics whenever the sample changes and at the tile end
-            const bool do_stats = (MODE == MODE_FPROP) && p.rowstat != nullptr;
-            float st_s = 0.f, st_ss = 0.f;
-            int st_b = do_stats ? wk.n0 / p.st_Tp : 0;
-            auto st_flush = [&](int b) {
-                if (m_base + lane < p.M && b < p.st_B) {
-                    float* rs = p.rowstat + ((size_t)b * p.M + (m_base + lane)) * 2;
-                    atomicAdd(rs, st_s);
-                    atomicAdd(rs + 1, st_ss);
-                }
-                st_s = 0.f;
-                st_ss = 0.f;
-            };
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32);
-                tmem_ld_32x32b_x32(taddr, v);
-                tmem_ld_wait();
-                const int n = wk.n0 + c * 32 + sub_c;
-                if (have_k && wk.n0 + c * 32 < p.N) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) slab[lane * EPI_PITCH + e] = __uint_as_float(v[e]) + bias;
-                    if (do_stats) {
-                        const int col0 = wk.n0 + c * 32;
-                        int b = col0 / p.st_Tp, t = col0 - b * p.st_Tp;
-                        if (b != st_b) { st_flush(st_b); st_b = b; }
-                        if (p.st_Tp >= 32) {
-                            // at most one sample boundary inside the 32 columns: [0, nb) -> sample b, [nb, 32) -> b + 1
-                            const int nb = p.st_Tp - t;
-                            const int lim0 = min(min(nb, p.st_T - t), p.N - col0);
-                            const int lim1 = min(nb + p.st_T, p.N - col0);
-                            float s1 = 0.f, ss1 = 0.f;
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) {
-                                const float val = __uint_as_float(v[e]) + bias;
-                                if (e < lim0) { st_s += val; st_ss = fmaf(val, val, st_ss); }
-                                if (e >= nb && e < lim1) { s1 += val; ss1 = fmaf(val, val, ss1); }
-                            }
-                            if (nb < 32) {
-                                st_flush(st_b);
-                                st_b = b + 1;
-                                st_s = s1;
-                                st_ss = ss1;
-                            }
-                        } else {
-#pragma unroll 1
-                            for (int e = 0; e < 32; ++e) {
-                                const float val = slab[lane * EPI_PITCH + e];
-                                if (t < p.st_T && col0 + e < p.N) { st_s += val; st_ss = fmaf(val, val, st_ss); }
-                                if (++t == p.st_Tp) { st_flush(st_b); t = 0; st_b = st_b + 1; }
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (n < p.N) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int rl = i * 4 + sub_r;
-                            const int m = m_base + rl;
-                            if (m < p.M) {
-                                const float* sp = slab + rl * EPI_PITCH + sub_c;
-                                float4 r = make_float4(sp[0], sp[1], sp[2], sp[3]);
-                                if (p.out_bf16) {
-                                    uint2 pk = make_uint2(f2_to_op16x2(r.x, r.y), f2_to_op16x2(r.z, r.w));
-                                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(obase) + (long long)m * p.ldc + n) = pk;
-                                } else {
-                                    float* dst = obase + (long long)m * p.ldc + n;
-                                    if (p.atomic) {
-                                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(r.x), "f"(r.y),
-                                                     "f"(r.z), "f"(r.w)
-                                                     : "memory");
-                                    } else {
-                                        if (p.accumulate) {
-                                            float4 o = *reinterpret_cast<const float4*>(dst);
-                                            r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
-                                        }
-                                        *reinterpret_cast<float4*>(dst) = r;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
+            const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+            if (p.out_bf16) epilogue_tile<MODE, true>(p, wk, tmem_acc, slab, m_base, lane);
+            else epilogue_tile<MODE, false>(p, wk, tmem_acc, slab, m_base, lane);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {
                 if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_leader(&tempty_bar[as]);
             }
-            if (do_stats) st_flush(st_b);
         }
     }
 
