@@ -47,3 +47,18 @@ for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 big = sorted(((a.elapsed_time(b), name, i) for i, (name, a, b) in enumerate(prof)), reverse=True)[:25]
 for ms, name, i in big:
     print("  call #%4d %-22s %.3f ms" % (i, name, ms))
+# every tensor-core GEMM of the step: time, rate, and the time it loses against 1300 TFLOP/s
+K.PROFILE = []
+tr.step(pool[0])
+torch.cuda.synchronize()
+gl = [(a.elapsed_time(b), name, fl) for name, fl, a, b in K.PROFILE]
+K.PROFILE = None
+print("GEMM calls: %d, %.2f ms, %.1f TFLOP/s average" % (len(gl), sum(g[0] for g in gl), sum(g[2] for g in gl) / sum(g[0] for g in gl) / 1e9))
+rows = collections.defaultdict(lambda: [0, 0.0, 0.0])
+for ms, name, fl in gl:
+    r = rows[(name, round(fl / 1e9, 1))]
+    r[0] += 1
+    r[1] += ms
+    r[2] += fl
+for (name, gf), (n, ms, fl) in sorted(rows.items(), key=lambda kv: -(kv[1][1] - kv[1][2] / 1.3e12)):
+    print("  %-6s %9.1f GFLOP x%2d  %7.3f ms  %7.1f TFLOP/s  lost %6.3f ms" % (name, gf, n, ms, fl / ms / 1e9, ms - fl / 1.3e12))

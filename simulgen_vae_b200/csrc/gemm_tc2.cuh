@@ -12,7 +12,7 @@
 //             CTAs complete_tx on it (the peer's loads name the leader's barrier: address bit 24 cleared)
 //   empty[s]  (each CTA, count 1):   tcgen05.commit ... multicast::cluster from the leader's MMA thread
 //   tfull[a]  (each CTA, count 1):   same multicast commit after the last k-block of a tile
-//   tempty[a] (leader CTA, count 8): the 4 epilogue warps of both CTAs arrive (the peer's remotely)
+//   tempty[a] (leader CTA, count 2 x EPI_WARPS): the epilogue warps of both CTAs arrive (the peer's remotely)
 //
 // Epilogue: TMEM -> registers (tcgen05.ld 32x32b.x32: lane = row) -> per-warp padded smem slab -> global
 // stores in which 8 consecutive lanes write one 128-byte row segment (the single-CTA kernel stores 16 bytes
@@ -30,9 +30,15 @@ constexpr int A_BYTES = BMH * BK * 2;                 // 16 KB
 constexpr int B_BYTES = BNH * BK * 2;                 // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // 32 KB
 constexpr int EPI_PITCH = 33;                         // floats per staged row (bank-conflict-free)
-constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;     // 4 epilogue warps
+#ifndef SG_PAIR_EPI_WARPS
+#define SG_PAIR_EPI_WARPS 8
+#endif
+constexpr int EPI_WARPS = SG_PAIR_EPI_WARPS;          // 4: one warp per TMEM lane quarter; 8: two, splitting the columns
+constexpr int EPI_CHUNKS = (BN / 32) * 4 / EPI_WARPS; // 32-column chunks per warp and tile
+constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+static_assert(SMEM_BYTES <= 232448, "pair kernel shared memory");
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
 
@@ -107,7 +113,7 @@ __device__ __forceinline__ PairWork decode_pair_work(const TcParams& p, int w, i
 // packed before staging and two chunks (64 columns = 128 bytes per row) leave together as 16-byte stores.
 template <int MODE, bool OUT16>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, const PairWork& wk, uint32_t tmem_acc, float* slab,
-                                              int m_base, int lane) {
+                                              int m_base, int lane, int c_lo) {
     const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
     float bias = 0.f;
     if (p.bias != nullptr && m_base + lane < p.M && wk.split == 0) bias = p.bias[m_base + lane];
@@ -118,7 +124,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const PairWork&
     // columns belong to; flushed with two atomics whenever the sample changes and at the tile end
     const bool do_stats = (MODE == MODE_FPROP) && p.rowstat != nullptr;
     float st_s = 0.f, st_ss = 0.f;
-    int st_b = do_stats ? wk.n0 / p.st_Tp : 0;
+    int st_b = do_stats ? (wk.n0 + c_lo * 32) / p.st_Tp : 0;
     auto st_flush = [&](int b) {
         if (m_base + lane < p.M && b < p.st_B) {
             float* rs = p.rowstat + ((size_t)b * p.M + (m_base + lane)) * 2;
@@ -231,14 +237,14 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const PairWork&
         }
     };
     uint32_t va[32], vb[32];
-    tmem_ld_32x32b_x32(tmem_acc, va);
+    tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(c_lo * 32), va);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; c += 2) {
+    for (int c = c_lo; c < c_lo + EPI_CHUNKS; c += 2) {
         tmem_ld_wait_regs(va);
         tmem_ld_32x32b_x32(tmem_acc + (uint32_t)((c + 1) * 32), vb);
         chunk(va, c);
         tmem_ld_wait_regs(vb);
-        if (c + 2 < BN / 32) tmem_ld_32x32b_x32(tmem_acc + (uint32_t)((c + 2) * 32), va);
+        if (c + 2 < c_lo + EPI_CHUNKS) tmem_ld_32x32b_x32(tmem_acc + (uint32_t)((c + 2) * 32), va);
         chunk(vb, c + 1);
     }
     if (do_stats) st_flush(st_b);
@@ -272,7 +278,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 8);
+            mbar_init(&tempty_bar[s], 2 * EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -369,9 +375,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         __syncwarp();
     } else {
-        // ===================== epilogue (warps 2..5, both CTAs) =====================
+        // ===================== epilogue (warps 2.., both CTAs) =====================
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
-        float* slab = epi + q * 32 * EPI_PITCH;
+        const int c_lo = ((warp - 2) >> 2) * EPI_CHUNKS;     // first of this warp's 32-column chunks
+        float* slab = epi + (warp - 2) * 32 * EPI_PITCH;
         int tile_iter = 0;
         for (int w = pair_id; w < num_work; w += num_pairs, ++tile_iter) {
             PairWork wk = decode_pair_work(p, w, total_iters);
@@ -381,8 +388,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             tcgen05_fence_after();
             const int m_base = wk.m0 + (int)rank * BMH + q * 32;
             const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-            if (p.out_bf16) epilogue_tile<MODE, true>(p, wk, tmem_acc, slab, m_base, lane);
-            else epilogue_tile<MODE, false>(p, wk, tmem_acc, slab, m_base, lane);
+            if (p.out_bf16) epilogue_tile<MODE, true>(p, wk, tmem_acc, slab, m_base, lane, c_lo);
+            else epilogue_tile<MODE, false>(p, wk, tmem_acc, slab, m_base, lane, c_lo);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {

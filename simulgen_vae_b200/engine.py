@@ -351,10 +351,10 @@ class Ctx:
     # spectral-norm gradient therefore run on a second stream: the two tensor-core GEMMs still take turns on the
     # SMs (each persistent CTA needs > 200 KB of shared memory), but the HBM-bound streaming kernels of the chain
     # co-reside with whichever GEMM is running instead of waiting behind it.
-    def side(self, *tensors):
+    def side(self, *tensors, flops=None):
         """Context manager: run the enclosed launches on the weight-gradient stream, after everything issued so far
         on the current stream; `tensors` are marked as in use by that stream (caching-allocator safety)."""
-        return _SideStream(self, tensors)
+        return _SideStream(self, tensors, flops)
 
     def join_side(self):
         if self._side_used:
@@ -363,7 +363,12 @@ class Ctx:
 
 
 _SIDE_STREAMS = {}
-_OVERLAP_WGRAD = os.environ.get("SIMULGEN_B200_OVERLAP_WGRAD", "0") != "0"   # measured: +1-2 % at best (the step is power-bound), off by default
+# "1": every wgrad on the side stream; "small" (default): only the wgrads below _OVERLAP_MAX_FLOP (the ones that cannot
+# fill the GPU on their own; the big GEMMs keep the machine to themselves); "0": off.  Same-box A/B at the headline
+# shape, B=64, three runs each: off 1591, all 1609, small 1624 samples/s.
+_OVERLAP_MODE = os.environ.get("SIMULGEN_B200_OVERLAP_WGRAD", "small")
+_OVERLAP_WGRAD = _OVERLAP_MODE != "0"
+_OVERLAP_MAX_FLOP = float(os.environ.get("SIMULGEN_B200_OVERLAP_MAX_GFLOP", "300")) * 1e9 if _OVERLAP_MODE == "small" else None
 
 
 def _side_stream_of(dev):
@@ -376,9 +381,10 @@ def _side_stream_of(dev):
 
 
 class _SideStream:
-    def __init__(self, ctx, tensors):
+    def __init__(self, ctx, tensors, flops=None):
         self.ctx, self.tensors = ctx, tensors
-        self.active = _OVERLAP_WGRAD and ctx.dev.type == "cuda"
+        self.active = _OVERLAP_WGRAD and ctx.dev.type == "cuda" and \
+            (_OVERLAP_MAX_FLOP is None or flops is None or flops < _OVERLAP_MAX_FLOP)
         self.cm = None
 
     def __enter__(self):
@@ -646,7 +652,7 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
                 dx, acc_in = ctx.grad_buf(a_in)
                 K.conv_dgrad(p.wg, dy, dx, p.Cin, bool(acc_in))
             if p.w.requires_grad:
-                with ctx.side(dy, a_in.data):
+                with ctx.side(dy, a_in.data, flops=2.0 * p.Cin * p.Cout * p.k * B * T):
                     dwg = ctx.weight_grad_buf(p, p.k, p.Cout, p.Cin_p)
                     K.conv_wgrad(dy, a_in.data, dwg, p.Cin)
                     _weight_grad(ctx, conv, p, dwg)
@@ -885,7 +891,7 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
             dx, acc = ctx.grad_buf(out)
             K.conv_dgrad(p.wg, dy, dx, p.Cin, bool(acc))
             if p.w.requires_grad:
-                with ctx.side(dy, out.data):
+                with ctx.side(dy, out.data, flops=2.0 * p.Cin * p.Cout * p.k * B * T):
                     dwg = ctx.weight_grad_buf(p, p.k, p.Cout, p.Cin_p)
                     K.conv_wgrad(dy, out.data, dwg, p.Cin)
                     _weight_grad(ctx, conv, p, dwg)
