@@ -56,7 +56,7 @@ if rank == 0:
         # bf16 check is on the weight matrices only; fp32 mode checks every tensor
         if precision == "fp32" or k.endswith("weight_orig"):
             worst = max(worst, e)
-    for e, k in sorted(per, reverse=True)[:4]:
+    for e, k in sorted(per, reverse=True)[:int(os.environ.get("DP_CHECK_SHOW", "4"))]:
         print("   %.3e %s" % (e, k))
     tol = 1e-4 if precision == "fp32" else 5e-2
     print("dp_check[%s] world=%d worst rel-L2 weight difference DP vs single process: %.3e (%s)" %

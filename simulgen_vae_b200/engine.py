@@ -380,6 +380,18 @@ def _side_stream_of(dev):
     return st
 
 
+def order_after_side_stream(dev):
+    """Make the current stream wait for everything issued on the weight-gradient stream (no-op when the current stream
+    IS that stream - it waited for the compute stream when its context was entered - or when it was never used)."""
+    if dev.type != "cuda":
+        return
+    side = _SIDE_STREAMS.get((dev.type, dev.index))
+    if side is not None:
+        cur = torch.cuda.current_stream(dev)
+        if cur != side:
+            cur.wait_stream(side)
+
+
 class _SideStream:
     def __init__(self, ctx, tensors, flops=None):
         self.ctx, self.tensors = ctx, tensors

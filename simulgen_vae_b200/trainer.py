@@ -105,6 +105,9 @@ class Trainer:
 
     def _reduce(self, flat):
         dist = torch.distributed
+        # a bucket holds gradients written on the compute stream (heads, latent layers) and on the weight-gradient
+        # side stream (conv wgrads): NCCL orders itself after the CURRENT stream only, so join the other one first
+        engine.order_after_side_stream(flat.device)
         self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
 
     def _finish_reduce(self):
