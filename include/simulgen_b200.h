@@ -232,6 +232,22 @@ int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* items_host, int
                 float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                 double* gnorm_sq, void* stream);
 
+/* ---- preprocessing scan (modules/data_preprocess.py:65-165, SimulGen-VAE.py:279-283) --------------
+ * data: the field matrix [R = P*T][N] (nodes innermost), float64 (is_f64 = 1) or float32 - the dtype the reference's
+ * MinMaxScaler would compute in.
+ * sg_minmax_fit: out_min/out_max [N] <- nanmin / nanmax over the rows `rows[0..n_rows)` (device int64 indices; NULL =
+ *   rows 0..n_rows-1), i.e. MinMaxScaler.fit(FOM_data_aug[param_indices, time_indices, :]) (data_preprocess.py:108-113)
+ *   without materialising the sampled copy; merge = 1 folds the result into the existing out_min/out_max (chunked
+ *   datasets, MinMaxScaler.partial_fit semantics).  ws: scratch of ws_elems elements of the data dtype, >= 2 * N.
+ * sg_minmax_transform: X * scale + min with two roundings (scaler.transform: X *= scale_; X += min_,
+ *   data_preprocess.py:130-133) written to `out` ([R][N], same dtype, may alias data, may be NULL) and/or to `out_t`,
+ *   the float32 [P][N][T] layout training consumes (new_x_train.transpose((0,2,1)) -> np.float32,
+ *   SimulGen-VAE.py:282-283; T = time steps per parameter set, R % T == 0; NULL = skip). */
+int sg_minmax_fit(const void* data, int is_f64, const long long* rows, long long n_rows, long long N, void* ws,
+                  long long ws_elems, void* out_min, void* out_max, int merge, void* stream);
+int sg_minmax_transform(const void* data, int is_f64, long long R, long long N, const void* scale, const void* minv,
+                        void* out, float* out_t, long long T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,3 +145,32 @@ if want("sn_prepare"):
     plan = K.SnPlan(layers, dev, BF)
     n = sum(L["w"].numel() for L in layers)
     report("sn_prepare (3 big layers, %dM)" % (n // 1000000), timed(lambda: K.sn_prepare(plan, True)), n * 14)
+if want("minmax"):
+    # the preprocessing scan over B parameter sets of the headline field, float64 like the reference
+    import time
+    import numpy as np
+    R = B * T
+    xd = torch.rand(R, N, device=dev, dtype=torch.float64) * 40 - 20
+    mn, mx = torch.empty(N, dtype=torch.float64, device=dev), torch.empty(N, dtype=torch.float64, device=dev)
+    report("minmax_fit (f64, all rows)", timed(lambda: K.minmax_fit(xd, None, mn, mx)), R * N * 8)
+    rows = torch.sort(torch.randperm(R, device=dev)[:R // 10]).values
+    report("minmax_fit (f64, 10% rows)", timed(lambda: K.minmax_fit(xd, rows, mn, mx)), (R // 10) * N * 8)
+    K.minmax_fit(xd, None, mn, mx)
+    scale, minv = 1.4 / (mx - mn), -0.7 - mn * (1.4 / (mx - mn))
+    out_t = torch.empty(B, N, T, dtype=torch.float32, device=dev)
+    report("minmax_transform (f64 in place)", timed(lambda: K.minmax_transform(xd, scale, minv, out=xd)), 2 * R * N * 8)
+    report("minmax_transform (-> f32 [P,N,T])", timed(lambda: K.minmax_transform(xd, scale, minv, out=None, out_t=out_t, T=T)),
+           R * N * 12)
+    report("minmax_transform (both)", timed(lambda: K.minmax_transform(xd, scale, minv, out=xd, out_t=out_t, T=T)), R * N * 20)
+    # the reference's CPU path on a bounded sample (4 parameter sets): MinMaxScaler.fit + transform + transpose/cast
+    from sklearn.preprocessing import MinMaxScaler
+    xs = xd[:4 * T].cpu().numpy()
+    t0 = time.perf_counter()
+    sc = MinMaxScaler(feature_range=(-0.7, 0.7)).fit(xs)
+    t1 = time.perf_counter()
+    ys = sc.transform(xs)
+    x32 = np.float32(ys.reshape(4, T, N).transpose((0, 2, 1)))
+    t2 = time.perf_counter()
+    print("cpu (sklearn/numpy, %d cores, 4 parameter sets): fit %.1f GB/s, transform+transpose+cast %.1f GB/s" %
+          (os.cpu_count(), xs.nbytes / (t1 - t0) / 1e9, (xs.nbytes * 2.5) / (t2 - t1) / 1e9), flush=True)
+    del xd, out_t

@@ -109,9 +109,10 @@ class B200AugmentedLoader:
             out = torch.empty((B,) + tuple(self.data.shape[1:]), dtype=torch.float32, device=dev)
             op = None
             if self.emit_operand:
-                from .engine import tp_of
+                from .engine import get_precision, tp_of
                 N, T = self.data.shape[1], self.data.shape[2]
-                op = torch.empty(1, N, B, tp_of(T, "bf16"), dtype=torch.bfloat16, device=dev)
+                op16 = torch.float16 if get_precision() == "fp16" else torch.bfloat16
+                op = torch.empty(1, N, B, tp_of(T, "bf16"), dtype=op16, device=dev)
             K.assemble_batch(self.data, ids, table, inj, out, self.seed, self.draws, op)
             self.last_operand = op                        # Trainer.step(x, packed=loader.last_operand)
             self.draws += 1

@@ -384,13 +384,49 @@ def sn_prepare(plan, training):
 
 # ---- batch assembly + augmentation --------------------------------------------------------------
 def assemble_batch(data, ids, table, injected_noise, out, seed, draw, operand=None):
-    """data fp32 [P, N, T]; ids int32 [2, B]; table fp32 [4, B]; out fp32 [B, N, T]; operand: optional bf16
-    [1, N, B, Tp] (the packed input of the first encoder conv)."""
+    """data fp32 [P, N, T]; ids int32 [2, B]; table fp32 [4, B]; out fp32 [B, N, T]; operand: optional 16-bit
+    [1, N, B, Tp] (the packed input of the first encoder conv, bf16 or fp16 like the engine's precision mode)."""
     P, N, T = data.shape
     B = out.shape[0]
     assert ids.dtype == torch.int32 and tuple(ids.shape) == (2, B) and tuple(table.shape) == (4, B)
     Tp = operand.shape[3] if operand is not None else 0
     if operand is not None:
-        assert operand.dtype == torch.bfloat16 and tuple(operand.shape[:3]) == (1, N, B)
+        assert operand.dtype in OP16 and tuple(operand.shape[:3]) == (1, N, B)
+        _dt(operand)                     # selects the library build for this 16-bit format
     _call("sg_assemble_batch", _p(_f32(data, "data")), P, _p(ids), _p(_f32(table, "table")), _p(_f32(injected_noise, "noise")),
           _p(_f32(out, "out")), _p(operand), B, N, T, Tp, int(seed) & (2 ** 64 - 1), int(draw), _stream())
+
+
+# ---- preprocessing scan (SURVEY 8f N4) ------------------------------------------------------------------
+def _f64flag(t):
+    if t.dtype == torch.float64:
+        return 1
+    if t.dtype == torch.float32:
+        return 0
+    raise RuntimeError("simulgen_b200: the preprocessing scan works on float64 or float32 data, got %s" % t.dtype)
+
+
+def minmax_fit(data, rows, out_min, out_max, merge=False):
+    """data [R, N] float64/float32 (contiguous, nodes innermost); rows: int64 device tensor of row indices or None (all
+    rows); out_min / out_max [N] (data dtype) <- nanmin / nanmax over those rows (merged into their content if merge)."""
+    R, N = data.shape
+    assert data.is_contiguous() and out_min.dtype == data.dtype and out_max.dtype == data.dtype
+    assert out_min.numel() == N and out_max.numel() == N
+    if rows is not None:
+        assert rows.dtype == torch.int64 and rows.is_contiguous()
+    n_rows = R if rows is None else rows.numel()
+    ws = torch.empty(min(2 * N * 64, max(2 * N, 1 << 26)), dtype=data.dtype, device=data.device)
+    _call("sg_minmax_fit", _p(data), _f64flag(data), _p(rows), n_rows, N, _p(ws), ws.numel(), _p(out_min), _p(out_max),
+          int(merge), _stream())
+
+
+def minmax_transform(data, scale, minv, out=None, out_t=None, T=0):
+    """out [R, N] (may be `data` itself) <- data * scale + minv (two roundings); out_t fp32 [R // T, N, T] <- the same
+    values cast to float32 in the [P, N, T] training layout."""
+    R, N = data.shape
+    assert data.is_contiguous() and scale.dtype == data.dtype and minv.dtype == data.dtype
+    if out is not None:
+        assert out.dtype == data.dtype and out.is_contiguous() and out.shape == data.shape
+    if out_t is not None:
+        assert out_t.dtype == torch.float32 and out_t.is_contiguous() and T > 0 and tuple(out_t.shape) == (R // T, N, T)
+    _call("sg_minmax_transform", _p(data), _f64flag(data), R, N, _p(scale), _p(minv), _p(out), _p(out_t), int(T), _stream())

@@ -440,6 +440,31 @@ def assemble_batch(data, ids, table, injected_noise, out, seed, draw, operand=No
         write_planes(operand, s.permute(1, 0, 2), data.shape[2])
 
 
+def minmax_fit(data, rows, out_min, out_max, merge=False):
+    import numpy as np
+    x = data.cpu().numpy()
+    if rows is not None:
+        x = x[rows.cpu().numpy()]
+    with np.errstate(all="ignore"):
+        mn = np.fmin.reduce(x, axis=0, initial=np.inf) if x.shape[0] else np.full(x.shape[1], np.inf, x.dtype)
+        mx = np.fmax.reduce(x, axis=0, initial=-np.inf) if x.shape[0] else np.full(x.shape[1], -np.inf, x.dtype)
+    mn, mx = torch.from_numpy(mn.astype(x.dtype)).to(data.device), torch.from_numpy(mx.astype(x.dtype)).to(data.device)
+    if merge:
+        mn, mx = torch.fmin(out_min, mn), torch.fmax(out_max, mx)
+    out_min.copy_(mn)
+    out_max.copy_(mx)
+
+
+def minmax_transform(data, scale, minv, out=None, out_t=None, T=0):
+    val = data * scale          # two roundings, like X *= scale_; X += min_
+    val = val + minv
+    if out_t is not None:
+        R, N = data.shape
+        out_t.copy_(val.view(R // T, T, N).permute(0, 2, 1).to(torch.float32))
+    if out is not None:
+        out.copy_(val)
+
+
 class OptPlan:
     """Emulated counterpart of kernels.OptPlan: keeps the item list (tensors) instead of a device table."""
 
@@ -477,7 +502,7 @@ def sn_prepare(plan, training):
             sn_pack_weight(L["w"], L["sigma"], L["wg"], L["H"], L["Cin"], L["Cin_p"], L["k"], L["so"], L["si"], L["flip"])
 
 
-NAMES = ["OptPlan", "opt_step", "SnPlan", "sn_prepare", "assemble_batch", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
+NAMES = ["OptPlan", "opt_step", "SnPlan", "sn_prepare", "assemble_batch", "minmax_fit", "minmax_transform", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
          "conv_fprop", "conv_fprop_gn", "conv_dgrad", "conv_wgrad", "gn_stats", "gn_act_fwd", "gn_act_bwd", "recon_fwd", "recon_bwd",
          "head_fwd", "head_bwd", "latent_fwd", "latent_bwd", "reparam_main_fwd", "reparam_main_bwd", "kl2_reparam_fwd",
          "kl2_reparam_bwd", "philox_normal", "adamw_step"]
