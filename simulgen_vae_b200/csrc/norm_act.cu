@@ -333,12 +333,54 @@ gn_bwd_reduce_kernel(BwdArgs p, float* __restrict__ dgamma, float* __restrict__ 
     const int nchunk = (p.B + kChunkB - 1) / kChunkB;
     const int tasks = p.C * nchunk, wstride = gridDim.x * kWarpsPerBlock;
     const float2* mr2 = reinterpret_cast<const float2*>(p.mr);
+    const bool one_seg = (p.Tp >> 3) <= 32;
     for (int task = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < tasks; task += wstride) {
         const int c = task / nchunk, ch = task - c * nchunk;
         const int b_lo = ch * kChunkB, b_hi = min(p.B, b_lo + kChunkB);
         const int g = c / Cg;
         const float gm = __ldg(p.gamma + c), bt = __ldg(p.beta + c);
         float sumA = 0.f, sumB = 0.f;
+        if (one_seg) {
+            // rows of <= 256 elements: one segment per lane; the loads of row b + 1 are in flight while row b is
+            // being processed (the kernel is bound by load latency, not by bandwidth or issue slots)
+            const bool live = lane * 8 < p.T;
+            const long long row0 = (long long)c * p.B;
+            SegIn cur, nxt;
+            float2 st = __ldg(mr2 + b_lo * p.G + g), st_n = st;
+            if (live) bwd_load<RT, POST>(p, row0 + b_lo, lane, cur);
+#pragma unroll 1
+            for (int b = b_lo; b < b_hi; ++b) {
+                if (b + 1 < b_hi) {
+                    if (live) bwd_load<RT, POST>(p, row0 + b + 1, lane, nxt);
+                    st_n = __ldg(mr2 + (b + 1) * p.G + g);
+                }
+                float A = 0.f, Bx = 0.f;
+                if (live) {
+                    const float a = gm * st.y, sh = bt - st.x * a;
+                    F8 dyh, xhat, dpre;
+                    bwd_compute<ACT, POST>(p, cur, lane, a, sh, st.x, st.y, dyh, xhat, dpre);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        A += dyh.v[i];
+                        Bx = fmaf(dyh.v[i], xhat.v[i], Bx);
+                    }
+                }
+                const float sa = warp_sum(A), sb = warp_sum(Bx);
+                sumA += sa;
+                sumB += sb;
+                if (lane == 0) {
+                    atomicAdd(&S[(size_t)(b * p.G + g) * 2], (double)(gm * sa));
+                    atomicAdd(&S[(size_t)(b * p.G + g) * 2 + 1], (double)(gm * sb));
+                }
+                cur = nxt;
+                st = st_n;
+            }
+            if (lane == 0) {
+                atomicAdd(&dgamma[c], sumB);
+                atomicAdd(&dbeta[c], sumA);
+            }
+            continue;
+        }
         for (int b0 = b_lo; b0 < b_hi; b0 += R) {
             float a[R], sh[R], mean[R], rstd[R], A[R], Bx[R];
             bool ok[R];
@@ -413,6 +455,73 @@ gn_bwd_apply_kernel(BwdArgs p, const double* __restrict__ S, OT* __restrict__ dy
         const int g = has_gn ? c / Cg : 0;
         const float gm = has_gn ? __ldg(p.gamma + c) : 1.f, bt = has_gn ? __ldg(p.beta + c) : 0.f;
         float db = 0.f;
+        if (nseg_p <= 32) {
+            // rows of <= 256 elements: one segment per lane, the next row's loads in flight during the current row's math
+            const bool live = lane * 8 < p.T;
+            const long long row0 = (long long)c * p.B;
+            SegIn cur, nxt;
+            float2 st = make_float2(0.f, 1.f), st_n = st;
+            double s1 = 0.0, s2 = 0.0, s1_n = 0.0, s2_n = 0.0;
+            if (has_gn) {
+                st = __ldg(mr2 + b_lo * p.G + g);
+                s1 = S[(size_t)(b_lo * p.G + g) * 2];
+                s2 = S[(size_t)(b_lo * p.G + g) * 2 + 1];
+            }
+            if (live) bwd_load<RT, POST>(p, row0 + b_lo, lane, cur);
+#pragma unroll 1
+            for (int b = b_lo; b < b_hi; ++b) {
+                if (b + 1 < b_hi) {
+                    if (live) bwd_load<RT, POST>(p, row0 + b + 1, lane, nxt);
+                    if (has_gn) {
+                        st_n = __ldg(mr2 + (b + 1) * p.G + g);
+                        s1_n = S[(size_t)((b + 1) * p.G + g) * 2];
+                        s2_n = S[(size_t)((b + 1) * p.G + g) * 2 + 1];
+                    }
+                }
+                const long long row = row0 + b;
+                F8 o, dpre;
+                if (live) {
+                    const float rstd = st.y, a = has_gn ? gm * st.y : 1.f, sh = has_gn ? bt - st.x * a : 0.f;
+                    const float m1 = (float)s1 * inv_n, m2 = (float)s2 * inv_n;
+                    F8 dyh, xhat;
+                    bwd_compute<ACT, POST>(p, cur, lane, a, sh, st.x, rstd, dyh, xhat, dpre);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float v = dyh.v[i];
+                        if (has_gn) v = rstd * (gm * v - m1 - xhat.v[i] * m2);
+                        o.v[i] = v;
+                    }
+                    if (has_gn && lane * 8 + 8 > p.T) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (lane * 8 + i >= p.T) o.v[i] = 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) db += o.v[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { o.v[i] = 0.f; dpre.v[i] = 0.f; }
+                }
+                if (dres != nullptr && lane < nseg_p) {
+                    float* dr = dres + row * p.Tp + lane * 8;
+                    if (dres_accumulate) {
+                        F8 old = load8(dr);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dpre.v[i] += old.v[i];
+                    }
+                    store8(dr, dpre);
+                }
+                if (multi) store_planes_shfl_n(dy, row * p.Tp, planes, pstride, o, p.T, nseg_p, lane);
+                else if (lane < nseg_p) store8(dy + row * p.Tp + lane * 8, o);
+                cur = nxt;
+                st = st_n;
+                s1 = s1_n;
+                s2 = s2_n;
+            }
+            db = warp_sum(db);
+            if (lane == 0 && dbias != nullptr) atomicAdd(&dbias[c], db);
+            continue;
+        }
         for (int b0 = b_lo; b0 < b_hi; b0 += R) {
             float a[R], sh[R], mean[R], rstd[R], m1[R], m2[R];
             bool ok[R];
