@@ -12,13 +12,22 @@ import sys
 from .engine import fixed_eps, get_precision, set_precision, set_sample_offset, tp_of  # noqa: F401
 
 OVERLAY_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "overlay")
+OVERLAY_TRAIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "overlay_train")
 
 
-def install_overlay():
-    """Make `import modules.{VAE_network,encoder,decoder,common,losses}` resolve to the engine."""
-    if OVERLAY_DIR in sys.path:
-        sys.path.remove(OVERLAY_DIR)
+def install_overlay(train=None):
+    """Make `import modules.{VAE_network,encoder,decoder,common,losses}` resolve to the engine.  train=True also
+    shadows `modules.train` with the Trainer-based driver (simulgen_vae_b200.train_loop); by default the reference's own
+    train.py keeps running on top of the overlaid model modules (train=None keeps the current choice)."""
+    if train is None:
+        train = OVERLAY_TRAIN_DIR in sys.path
+    for d in (OVERLAY_DIR, OVERLAY_TRAIN_DIR):
+        if d in sys.path:
+            sys.path.remove(d)
     sys.path.insert(0, OVERLAY_DIR)
+    if train:
+        sys.path.insert(0, OVERLAY_TRAIN_DIR)
+        sys.modules.pop("modules.train", None)
     stale = [k for k, m in sys.modules.items()
              if (k == "modules" or k.startswith("modules.")) and OVERLAY_DIR not in (getattr(m, "__file__", None) or OVERLAY_DIR)]
     for k in stale:

@@ -310,3 +310,37 @@ def test_export_path_encoder_then_decoder_fix_mode(name):
     assert rel_l2(x_hat3, x_hat) < 1e-6      # (new eps draws scaled by 1e-8 and atomic summation order differ)
     for a, b in zip(kls, okls):
         assert rel_l2(a, b) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_engine_train_driver_on_gpu(precision, tmp_path, monkeypatch):
+    """the Trainer-based train() drop-in (simulgen_vae_b200.train_loop, `install_overlay(train=True)`) runs
+    the reference's epoch loop on the GPU - schedules, validation, checkpoints - and the loss goes down."""
+    import numpy as np
+    import simulgen_vae_b200 as sg
+    from simulgen_vae_b200 import engine, train_loop
+    monkeypatch.chdir(tmp_path)
+    sg.install_overlay()
+    cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[64, 32, 16], num_node=256, num_time=40)
+    g = torch.Generator().manual_seed(0)
+    t = torch.linspace(0, 1, cfg["num_time"])
+    data = 0.6 * torch.sin(6.28 * (t[None, None, :] * (1 + torch.rand(24, 1, 1, generator=g)) + torch.rand(1, cfg["num_node"], 1, generator=g)))
+    dev = torch.device("cuda:0")
+    train_dl = torch.utils.data.DataLoader(data[:16].to(dev), batch_size=8, shuffle=False)
+    val_dl = torch.utils.data.DataLoader(data[16:].to(dev), batch_size=8, shuffle=False)
+    sg.set_precision(precision)
+    try:
+        torch.manual_seed(5)
+        engine._rng_state().seed = None
+        loss, recon, kl, val = train_loop.train(8, 8, train_dl, val_dl, 2e-3, cfg["enc"], cfg["enc"][::-1], cfg["num_node"],
+                                                cfg["latent_dim"], cfg["hierarchical_dim"], cfg["num_time"], 1000000, "MSE", True, True)
+    finally:
+        sg.set_precision("bf16")
+    assert all(np.isfinite(c).all() and len(c) == 8 for c in (loss, recon, kl, val))
+    assert recon[-1] < 0.7 * recon[0], (recon[0], recon[-1])
+    assert val[0] > 0 and val[-1] > 0 and val[1] == val[0]            # validated at epoch 0 and the last one, carried between
+    sd = torch.load("checkpoints/SimulGen-VAE.pth", weights_only=False)
+    assert any(k.endswith("weight_orig") for k in sd) and all(torch.isfinite(v).all() for v in sd.values())
+    whole = torch.load("model_save/SimulGen-VAE", weights_only=False)
+    assert type(whole).__name__ == "VAE"
