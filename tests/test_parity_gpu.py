@@ -344,3 +344,36 @@ def test_engine_train_driver_on_gpu(precision, tmp_path, monkeypatch):
     assert any(k.endswith("weight_orig") for k in sd) and all(torch.isfinite(v).all() for v in sd.values())
     whole = torch.load("model_save/SimulGen-VAE", weights_only=False)
     assert type(whole).__name__ == "VAE"
+
+
+@pytest.mark.gpu
+def test_batched_export_is_batch_size_independent_on_gpu(tmp_path, monkeypatch):
+    """the batched latent-export sweep (simulgen_vae_b200.export) on the GPU, with the real Philox noise:
+    the same numbers whether the sweep runs one sample at a time (the reference's batch_size=1 loader) or regrouped into
+    batches, because the noise is keyed on (seed, draw, position in the sweep)."""
+    import numpy as np
+    import simulgen_vae_b200 as sg
+    from simulgen_vae_b200 import export
+    monkeypatch.chdir(tmp_path)
+    cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[64, 32, 16], num_node=256, num_time=40, batch=4, small=True, lossfun="MSE")
+    sg.set_precision("fp32")
+    try:
+        torch.manual_seed(2)
+        m = build_engine_vae(cfg, None).eval()
+        g = torch.Generator().manual_seed(4)
+        data = (torch.rand(11, cfg["num_node"], cfg["num_time"], generator=g) * 1.4 - 0.7).to(DEV)
+        outs = []
+        for bs in (1, 4, 11):
+            torch.manual_seed(9)
+            loader = torch.utils.data.DataLoader(data, batch_size=1, shuffle=False)
+            outs.append(export.evaluate_vae_reconstruction(m, loader, DEV, 11, cfg["enc"], cfg["hierarchical_dim"], cfg["latent_dim"],
+                                                           recon_iter=2, dataset_name="t", save_images=False, batch_size=bs,
+                                                           verbose=False))
+        for o in outs[1:]:
+            for a, b in zip(outs[0][:4], o[:4]):
+                assert a.shape == b.shape and np.allclose(a, b, rtol=2e-4, atol=2e-6), np.abs(a - b).max()
+        lat = outs[0][0]
+        assert np.abs(lat).max() > 0 and len(np.unique(lat.round(6), axis=0)) == 11          # every row filled, all distinct
+        assert (outs[0][2] > 0).all()
+    finally:
+        sg.set_precision("bf16")
