@@ -58,7 +58,7 @@ if rank == 0:
             worst = max(worst, e)
     for e, k in sorted(per, reverse=True)[:int(os.environ.get("DP_CHECK_SHOW", "4"))]:
         print("   %.3e %s" % (e, k))
-    tol = 1e-4 if precision == "fp32" else 5e-2
+    tol = 3e-4 if precision == "fp32" else 5e-2     # run-to-run atomics noise through 2 AdamW steps is ~1e-4
     print("dp_check[%s] world=%d worst rel-L2 weight difference DP vs single process: %.3e (%s)" %
           (precision, world, worst, "OK" if worst < tol else "FAIL"), flush=True)
     assert worst < tol

@@ -285,6 +285,7 @@ class Ctx:
         self.capture = capture
         self.sink = get_grad_sink() if record else None
         self._side_used = False
+        self._side_keep = []            # tensors read by the weight-gradient stream: kept alive until the next join
         self.prepared = {}              # id(module) -> _Prep from the batched preparation
         self.prep_record = []           # (module, kind) in execution order when preparing layer by layer
         self.prep_root = None
@@ -353,13 +354,17 @@ class Ctx:
     # co-reside with whichever GEMM is running instead of waiting behind it.
     def side(self, *tensors, flops=None):
         """Context manager: run the enclosed launches on the weight-gradient stream, after everything issued so far
-        on the current stream; `tensors` are marked as in use by that stream (caching-allocator safety)."""
+        on the current stream; `tensors` (its inputs) are kept alive until the compute stream has joined it again."""
         return _SideStream(self, tensors, flops)
 
     def join_side(self):
         if self._side_used:
             torch.cuda.current_stream(self.dev).wait_stream(_side_stream_of(self.dev))
             self._side_used = False
+            # the compute stream is now ordered after every side-stream reader: the operands may go back to the
+            # caching allocator (they were allocated on the compute stream, so plain stream order covers their reuse;
+            # no record_stream(), whose event-deferred frees make the allocator's behaviour timing dependent)
+            self._side_keep.clear()
 
 
 _SIDE_STREAMS = {}
@@ -403,9 +408,7 @@ class _SideStream:
         if self.active:
             side = _side_stream_of(self.ctx.dev)
             side.wait_stream(torch.cuda.current_stream(self.ctx.dev))
-            for t in self.tensors:
-                if t is not None:
-                    t.record_stream(side)
+            self.ctx._side_keep.extend(t for t in self.tensors if t is not None)
             self.cm = torch.cuda.stream(side)
             self.cm.__enter__()
             self.ctx._side_used = True
