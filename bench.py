@@ -374,7 +374,7 @@ def _main():
     }
     if e2e:
         line["e2e"] = e2e
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:           # the CPU baseline is timed on rank 0 of the 1-GPU run only
         try:
             sps, kind, cores, sec = cpu_reference_run(cfg, args.cpu_batch, 2, 1)
             line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": kind,
