@@ -105,7 +105,8 @@ def train(epochs, batch_size, train_dataloader, val_dataloader, LR, num_filter_e
         for image in train_dataloader:
             if not load_all or image.device != device:
                 image = image.to(device, non_blocking=True)
-            loss, recon, kl_sum, mse = trainer.step(image, beta=beta)
+            # data parallel: the noise stream is keyed on the GLOBAL sample index (rank-major within a step)
+            loss, recon, kl_sum, mse = trainer.step(image, beta=beta, sample_offset=rank * image.shape[0])
             acc += torch.stack([loss.double().reshape(()), recon.double().reshape(()) * alpha, kl_sum.double().reshape(()) * beta,
                                 mse.double().reshape(()) * alpha, trainer.gnorm_sq.sqrt().reshape(())])
             n_batches += 1

@@ -119,3 +119,45 @@ def test_data_parallel_world2_equals_single_process(tmp_path, fused):
     sd = m.state_dict()
     for k in sd:
         assert rel_l2(dp[k], sd[k]) < 5e-5, (k, rel_l2(dp[k], sd[k]))
+
+
+def _train_loop_worker(rank, world, port, workdir, data):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    if world > 1:
+        torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    os.makedirs(os.path.join(workdir, "w%d_r%d" % (world, rank)), exist_ok=True)
+    os.chdir(os.path.join(workdir, "w%d_r%d" % (world, rank)))
+    torch.randn_like = lambda t, *a, **k: torch.zeros_like(t)          # reparameterisation noise off: DP == single exactly
+    from simulgen_vae_b200 import train_loop
+    sg.install_overlay()
+    sg.set_precision("fp32")
+    cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[32, 16, 8], num_node=64, num_time=20)
+    B = 4
+    per = B // world
+    # every global batch of 4 is split rank-major: rank r takes samples [r*per, (r+1)*per) of it
+    idx = [b * B + rank * per + j for b in range(3) for j in range(per)]
+    train_dl = torch.utils.data.DataLoader(data[idx], batch_size=per, shuffle=False)
+    vidx = [12 + rank * per + j for j in range(per)]
+    val_dl = torch.utils.data.DataLoader(data[vidx], batch_size=per, shuffle=False)
+    torch.manual_seed(3)
+    with emu.install():
+        train_loop.train(4, B, train_dl, val_dl, 1e-3, cfg["enc"], cfg["enc"][::-1], cfg["num_node"], cfg["latent_dim"],
+                         cfg["hierarchical_dim"], cfg["num_time"], 1000000, "MSE", True, True, device="cpu")
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def test_train_driver_data_parallel_world2_equals_single_process(tmp_path):
+    """simulgen_vae_b200.train_loop.train under torch.distributed (gloo, 2 ranks, half of every batch each) ends with the
+    weights of the single-process run on the full batches; only rank 0 writes the checkpoints."""
+    g = torch.Generator().manual_seed(0)
+    data = torch.rand(16, 64, 20, generator=g) * 1.4 - 0.7
+    mp.spawn(_train_loop_worker, args=(2, _free_port(), str(tmp_path), data), nprocs=2, join=True)
+    mp.spawn(_train_loop_worker, args=(1, _free_port(), str(tmp_path), data), nprocs=1, join=True)
+    dp = torch.load(str(tmp_path / "w2_r0" / "checkpoints" / "SimulGen-VAE.pth"), weights_only=False)
+    single = torch.load(str(tmp_path / "w1_r0" / "checkpoints" / "SimulGen-VAE.pth"), weights_only=False)
+    assert not os.path.exists(str(tmp_path / "w2_r1" / "checkpoints" / "SimulGen-VAE.pth"))
+    assert list(dp.keys()) == list(single.keys())
+    for k in single:
+        assert rel_l2(dp[k], single[k]) < 1e-4, (k, rel_l2(dp[k], single[k]))
