@@ -1,8 +1,9 @@
-"""TEST INFRASTRUCTURE ONLY - loads the *unmodified* reference modules from /root/reference.
+"""TEST INFRASTRUCTURE ONLY - loads the *unmodified* reference modules from /root/reference, or from
+the staged byte-for-byte copy oracle/_ref (oracle/make_ref.sh; that is what travels to the GPU box).
 
-Only `oracle/make_golden.py`, tests that pin the oracle (skipped when the reference checkout is
-absent, e.g. on the GPU box) and `bench.py --impl reference` (when the checkout is present) may
-use this.  The product path (`simulgen_vae_b200`) never imports it.
+Only `oracle/make_golden*.py`, tests that pin the oracle or run the reference's own drivers on the
+engine's overlay, and `bench.py --impl reference` / `cpu_baseline` may use this.  The product path
+(`simulgen_vae_b200`) never imports it.
 
 The reference's hot-path files import four non-numerical packages that are missing from this
 image (`matplotlib`, `torchinfo`, `natsort`, `skimage`).  They are replaced by empty
@@ -16,7 +17,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SIMULGEN_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")      # written by oracle/make_ref.sh
+
+
+def _find_root():
+    """The reference checkout: $SIMULGEN_REFERENCE_ROOT, else /root/reference (build container), else the byte-for-byte
+    staged copy oracle/_ref (what the GPU box has; oracle/make_ref.sh)."""
+    env = os.environ.get("SIMULGEN_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _STAGED):
+        if os.path.isfile(os.path.join(cand, "modules", "VAE_network.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 _cache = None
 

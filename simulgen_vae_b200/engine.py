@@ -7,14 +7,18 @@ encoder and the decoder are each ONE torch.autograd.Function; inside, a small ta
 backward of every fused block, so no ATen kernel runs on the hot path and gradients are produced in
 a known order (which the data-parallel driver uses to overlap the NCCL all-reduce).
 
-Data layout inside the engine ("CR"): activations are [C, B, Tp] with Tp = roundup(T+2, 8) and the
-tail t >= T of every row zero - it is the convolution's zero padding, shared between neighbouring
-samples - so that every Conv1d is one implicit GEMM  D[Cout, B*Tp] = sum_taps Wg[tap] @ shift(act).
-GEMM operands are bf16 (tcgen05, fp32 accumulation) or fp32 (validation mode); conv outputs, norm
-statistics, the residual stream, latents, KL and losses stay fp32.
+Data layout inside the engine ("CR"): activations are [C, B, Tp], the tail t >= T of every row zero, so that
+every Conv1d is one implicit GEMM  D[Cout, B*Tp] = sum_taps Wg[tap] @ shift(act).
+  16-bit (tensor-core) modes: Tp = roundup(T, 8); the operand of a k-tap conv is stored as k pre-shifted planes
+      [planes, C, B, Tp] (zero-filled at the row ends = the conv padding), tap j selects a plane.
+  fp32 validation mode: Tp = roundup(T+2, 8); the SIMT GEMMs shift along the flattened (sample, time) axis and the
+      >= 2 zero columns between samples are the conv padding (tp_of() below).
+GEMM operands are bf16 / fp16 (tcgen05, fp32 accumulation) or fp32 (validation mode); norm statistics, the
+residual stream, latents, KL and losses stay fp32.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import threading
 import weakref
@@ -227,6 +231,30 @@ def set_materialize_xhat(flag: bool):
 
 def _materialize_xhat():
     return getattr(_sink, "xhat", True)
+
+
+def note_grad_mode():
+    """Called by the overlay modules right before Function.apply: inside Function.forward grad mode is always off and
+    needs_input_grad only says that the parameters COULD take a gradient, so under torch.no_grad() (validation,
+    export sweeps) the engine would otherwise record a backward tape that keeps every activation alive."""
+    _sink.grad_enabled = torch.is_grad_enabled()
+
+
+def _take_grad_mode():
+    g = getattr(_sink, "grad_enabled", True)
+    _sink.grad_enabled = True
+    return g
+
+
+def set_freeze_level(level: int):
+    """freeze_level of the next Decoder.forward of this thread (decoder.py:170,202-207); consumed by that call."""
+    _sink.freeze = int(level)
+
+
+def _take_freeze_level():
+    lvl = getattr(_sink, "freeze", -1)
+    _sink.freeze = -1
+    return lvl
 
 
 def set_packed_input(op):
@@ -748,6 +776,28 @@ def latent_seq(ctx: Ctx, seq, z: Ext, out_op_view=None, out_planes=1, name="") -
     return conv_block(ctx, conv, gn, a, K.ACT_GELU, out_op_view=out_op_view, out_planes=out_planes, name=name)
 
 
+def _freeze_latent(ctx: Ctx, dec, i, freeze_level, h, zs_f32, zs_next: Act):
+    """mode == "fix" and i < freeze_level (decoder.py:202-207): the first freeze_level + 1 such calls draw z and append it
+    to dec.zs; later calls reuse dec.zs[i + 1] (the reference's own indexing, kept as written).  zs_f32 = h + z as just
+    computed; inference only (no caller of the reference trains through it)."""
+    if ctx.tape is not None:
+        raise RuntimeError("simulgen_b200: freeze_level >= 0 is an inference feature (run it under torch.no_grad())")
+    B, T, C = ctx.B, ctx.T, zs_next.C
+    if len(dec.zs) < freeze_level + 1:
+        K.axpy(zs_f32, h, -1.0, True)                       # z = (h + z) - h, CR layout
+        z = torch.empty(B, C, T, dtype=torch.float32, device=ctx.dev)
+        K.unpack_f32(zs_f32, z, T)
+        dec.zs.append(z)
+        return
+    z = dec.zs[i + 1]                                       # IndexError / shape error exactly where the reference has them
+    if tuple(z.shape) != (B, C, T):
+        raise RuntimeError("The size of tensor a (%s) must match the size of tensor b (%s)" % (tuple(z.shape), (B, C, T)))
+    zc = ctx.f32(1, C, B, ctx.Tp)
+    K.pack_input(z.to(ctx.dev, torch.float32).contiguous(), zc, T)
+    K.axpy(zc[0], h, 1.0, True)                             # decoder_out + z (decoder.py:179)
+    K.gn_act_fwd(zc[0], None, None, None, None, 1.0, K.ACT_NONE, False, zs_next.data, None, T, 0)
+
+
 # ------------------------------------------------------------------------------------------------
 # encoder / decoder graphs
 # ------------------------------------------------------------------------------------------------
@@ -789,6 +839,7 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     B, T, Tp = ctx.B, ctx.T, ctx.Tp
     nb = len(dec.decoder_residual_blocks)
     kls = []
+    freeze_level = _take_freeze_level()
     prepare_all(ctx, dec)
     zs = latent_seq(ctx, dec.sequence_start[0], z, out_planes=_k(dec.decoder_blocks[0].module_list[0]._seq[0]),
                     name="decoder.start")
@@ -839,7 +890,11 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
                       name="decoder.zs%d" % i)
         kl_sum = ctx.f64(1)
         out_f32 = out.as_f32()
-        K.kl2_reparam_fwd(cz.f32, cxz.f32, eps, out_f32, std_scale, zs_next.data, None, kl_sum, T)
+        frozen = mode == "fix" and i < freeze_level
+        zs_f32 = ctx.f32(C, B, Tp) if frozen else None
+        K.kl2_reparam_fwd(cz.f32, cxz.f32, eps, out_f32, std_scale, zs_next.data, zs_f32, kl_sum, T)
+        if frozen:
+            _freeze_latent(ctx, dec, i, freeze_level, out_f32, zs_f32, zs_next)
         kl_t = ctx.f32(1)
         K.scale_f64_to_f32(kl_sum, kl_t, 0.5 / B)
         kl_ext = Ext(kl_t)
@@ -930,24 +985,35 @@ def _check_input(x, what):
         raise RuntimeError("simulgen_b200: %s must be a CUDA tensor - the engine has no CPU fallback" % what)
 
 
+def device_guard(dev):
+    """The C ABI takes a stream, not a device: every launch goes to the CURRENT device's stream.  The autograd
+    Functions (and Trainer.step) therefore make the tensors' device current for their duration, so a model living on
+    cuda:1 works from a process whose current device is cuda:0."""
+    if getattr(dev, "type", None) == "cuda":
+        return torch.cuda.device(dev)
+    return contextlib.nullcontext()
+
+
 class EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(fctx, enc, capture, x, *params):
         _check_input(x, "encoder input")
         fctx.set_materialize_grads(False)
-        x = x.contiguous().float()
-        record = any(fctx.needs_input_grad)
-        ctx = Ctx(x.shape[0], x.shape[2], x.device, record, capture)
-        last, xs = encoder_graph(ctx, enc, x)
+        with device_guard(x.device):
+            x = x.contiguous().float()
+            record = _take_grad_mode() and any(fctx.needs_input_grad)
+            ctx = Ctx(x.shape[0], x.shape[2], x.device, record, capture)
+            last, xs = encoder_graph(ctx, enc, x)
         fctx.ectx, fctx.exts, fctx.params = ctx, [last] + xs, params
         return (last.tensor,) + tuple(e.tensor for e in xs)
 
     @staticmethod
     def backward(fctx, *grads):
         ctx = fctx.ectx
-        for e, g in zip(fctx.exts, grads):
-            e.grad = _contig_f32(g)
-        ctx.run_backward()
+        with device_guard(ctx.dev):
+            for e, g in zip(fctx.exts, grads):
+                e.grad = _contig_f32(g)
+            ctx.run_backward()
         out = tuple(ctx.pgrads.get(id(p)) for p in fctx.params)
         fctx.ectx = None
         return (None, None, None) + out
@@ -964,7 +1030,8 @@ class ReparamMainFn(torch.autograd.Function):
         B, L2 = last.shape
         z = torch.empty(B, L2 // 2, dtype=torch.float32, device=last.device)
         kl = torch.empty(1, dtype=torch.float32, device=last.device)
-        K.reparam_main_fwd(last, eps, z, kl)
+        with device_guard(last.device):
+            K.reparam_main_fwd(last, eps, z, kl)
         fctx.save_for_backward(last, eps)
         return z, kl.view(())
 
@@ -972,7 +1039,8 @@ class ReparamMainFn(torch.autograd.Function):
     def backward(fctx, dz, dkl):
         last, eps = fctx.saved_tensors
         dlast = torch.empty_like(last)
-        K.reparam_main_bwd(last, eps, _contig_f32(dz), _contig_f32(dkl.reshape(1)) if dkl is not None else None, dlast)
+        with device_guard(last.device):
+            K.reparam_main_bwd(last, eps, _contig_f32(dz), _contig_f32(dkl.reshape(1)) if dkl is not None else None, dlast)
         return dlast, None
 
 
@@ -984,14 +1052,15 @@ class DecoderFn(torch.autograd.Function):
         params = rest[n_xs + 1:]
         _check_input(z, "decoder latent")
         fctx.set_materialize_grads(False)
-        z = z.contiguous().float()
-        record = any(fctx.needs_input_grad)
-        ctx = Ctx(z.shape[0], dec.num_time, z.device, record, capture)
-        z_ext = Ext(z)
-        xs_ext = [Ext(t.contiguous().float()) for t in xs_t]
-        if x is not None:
-            x = x.contiguous().float()
-        res = decoder_graph(ctx, dec, z_ext, xs_ext, x, lossfun, mode)
+        with device_guard(z.device):
+            z = z.contiguous().float()
+            record = _take_grad_mode() and any(fctx.needs_input_grad)
+            ctx = Ctx(z.shape[0], dec.num_time, z.device, record, capture)
+            z_ext = Ext(z)
+            xs_ext = [Ext(t.contiguous().float()) for t in xs_t]
+            if x is not None:
+                x = x.contiguous().float()
+            res = decoder_graph(ctx, dec, z_ext, xs_ext, x, lossfun, mode)
         fctx.ectx, fctx.res, fctx.params, fctx.z_ext, fctx.xs_ext = ctx, res, params, z_ext, xs_ext
         fctx.has_x = x is not None
         outs = [res["x_hat"]]
@@ -1004,16 +1073,17 @@ class DecoderFn(torch.autograd.Function):
     def backward(fctx, *grads):
         ctx, res = fctx.ectx, fctx.res
         grads = list(grads)
-        res["x_hat_ext"].grad = _contig_f32(grads.pop(0))
-        if fctx.has_x:
-            g = grads.pop(0)
-            res["recon"].grad = _contig_f32(g.reshape(1)) if g is not None else None
-            g = grads.pop(0)
-            res["mse"].grad = _contig_f32(g.reshape(1)) if g is not None else None
-        for k_ext in res["kls"]:
-            g = grads.pop(0)
-            k_ext.grad = _contig_f32(g.reshape(1)) if g is not None else None
-        ctx.run_backward()
+        with device_guard(ctx.dev):
+            res["x_hat_ext"].grad = _contig_f32(grads.pop(0))
+            if fctx.has_x:
+                g = grads.pop(0)
+                res["recon"].grad = _contig_f32(g.reshape(1)) if g is not None else None
+                g = grads.pop(0)
+                res["mse"].grad = _contig_f32(g.reshape(1)) if g is not None else None
+            for k_ext in res["kls"]:
+                g = grads.pop(0)
+                k_ext.grad = _contig_f32(g.reshape(1)) if g is not None else None
+            ctx.run_backward()
         pg = tuple(ctx.pgrads.get(id(p)) for p in fctx.params)
         gz = fctx.z_ext.grad
         gxs = tuple(e.grad for e in fctx.xs_ext)

@@ -55,14 +55,28 @@ def evaluate_vae_reconstruction(VAE, dataloader, device, num_param, num_filter_e
         save_dir = "checkpoints/%s" % dataset_name.replace(" ", "_").replace("(", "").replace(")", "").lower()
         os.makedirs(save_dir, exist_ok=True)
     n_levels = len(num_filter_enc) - 1
+    if verbose:
+        print("Evaluating %s..." % dataset_name)
+    # the sweep uses its own position-keyed noise stream; the training stream (seed, draw counter, sample offset) of
+    # this thread is put back afterwards so that training which continues after an evaluation does not replay draws
+    st = engine._rng_state()
+    saved_rng = (st.seed, st.counter, st.sample0)
+    try:
+        return _sweep(VAE, dataloader, device, num_param, n_levels, latent_dim, latent_dim_end, recon_iter, dataset_name,
+                      save_dir, batch_size, keep_reconstructed, verbose, reparameterize)
+    finally:
+        st.seed, st.counter, st.sample0 = saved_rng
+
+
+def _sweep(VAE, dataloader, device, num_param, n_levels, latent_dim, latent_dim_end, recon_iter, dataset_name, save_dir,
+           batch_size, keep_reconstructed, verbose, reparameterize):
+    from . import engine
     latent_vectors = np.zeros([num_param, latent_dim_end])
     hierarchical = np.zeros([num_param, n_levels, latent_dim])
     reconstruction_loss = np.zeros([num_param])
     reconstructed = None
     loss_total = 0.0
     row = 0
-    if verbose:
-        print("Evaluating %s..." % dataset_name)
     with torch.no_grad():
         for x in _regroup(dataloader, batch_size):
             x = x.to(device)
@@ -107,7 +121,6 @@ def evaluate_vae_reconstruction(VAE, dataloader, device, num_param, num_filter_e
             if save_dir is not None and row < 10 and keep_reconstructed:
                 _save_plots(save_dir, x, reconstructed, row, min(n, 10 - row), last_host)
             row += Bb
-    engine.set_sample_offset(0)
     if verbose:
         print("\nTotal %s MSE loss: %.3e\n--------------------------------\n" % (dataset_name, loss_total / max(row, 1)))
     if reconstructed is None:

@@ -80,6 +80,7 @@ class Decoder(nn.Module):
             # at the second level (decoder.py:179)
             raise RuntimeError("Decoder.forward needs xs with at least %d entries" % n_levels)
         xs = list(xs)
+        engine.note_grad_mode()
         outs = engine.DecoderFn.apply(self, capture, lossfun, mode, len(xs), z, *xs, x, *self.parameters())
         x_hat = outs[0]
         if x is not None:
@@ -88,8 +89,8 @@ class Decoder(nn.Module):
 
     def forward(self, z, xs=None, mode="random", freeze_level=-1):
         if freeze_level >= 0:
-            raise NotImplementedError("freeze_level >= 0 (decoder.py:202-207) is not used by any caller of the "
-                                      "reference and is not implemented by the B200 engine")
+            from simulgen_vae_b200 import engine
+            engine.set_freeze_level(freeze_level)            # decoder.py:202-207: cached / replayed latents in self.zs
         x_hat, _, _, kl_losses = self._run(z, xs, mode=mode)
         return x_hat, kl_losses
 

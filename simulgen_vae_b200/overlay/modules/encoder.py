@@ -52,6 +52,7 @@ class Encoder(nn.Module):
     def _run(self, x, capture=None):
         """(last [B, 2*z_dim], xs list) - `last` keeps mu|log_var fused for the reparam kernel."""
         from simulgen_vae_b200 import engine
+        engine.note_grad_mode()
         outs = engine.EncoderFn.apply(self, capture, x, *self.parameters())
         return outs[0], list(outs[1:])
 

@@ -49,7 +49,8 @@ def _gemm_layout_elems(mod):
 
 class Trainer:
     def __init__(self, model, lr=1e-3, alpha=1.0e6, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                 process_group=None, bucket_mb=64, fused=True, materialize_xhat=False, loss_scale=None):
+                 process_group=None, bucket_mb=64, fused=True, materialize_xhat=False, loss_scale=None,
+                 broadcast_init=True):
         self.model = model
         self.lr, self.alpha, self.betas, self.eps, self.wd = lr, alpha, betas, eps, weight_decay
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -65,6 +66,8 @@ class Trainer:
             self.world = torch.distributed.get_world_size(process_group)
         self.bucket_elems = bucket_mb * (1 << 20) // 4
         self.fused = fused
+        if self.world > 1 and broadcast_init:
+            self._broadcast_replica()
         # fp16 mode: gradients are stored as fp16 GEMM operands, so the loss is scaled by a power of two before backward
         # and the optimiser divides it out again (everything in between is linear).  None = automatic: numel/alpha
         # rounded to a power of two puts the reconstruction-loss gradient at O(1); bf16 / fp32 need none.
@@ -95,6 +98,17 @@ class Trainer:
                 self.sink.on_commit = self._on_commit
 
     # -- data parallel --------------------------------------------------------------------------
+    def _broadcast_replica(self):
+        """Data parallel needs IDENTICAL replicas: the reference's entry point builds the model on every rank without
+        a seed (SimulGen-VAE.py never calls manual_seed; train.py:65-72 draws the He weights and the spectral-norm
+        u / v vectors from the global RNG), so rank 0's parameters and buffers - weight_orig, bias, GroupNorm affine,
+        weight_u, weight_v - are broadcast once before the first step."""
+        dist = torch.distributed
+        src = dist.get_global_rank(self.pg, 0) if self.pg is not None else 0
+        with torch.no_grad():
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, src=src, group=self.pg)
+
     def _on_commit(self, committed):
         """Gradient arena filled up to `committed` elements: all-reduce complete buckets right away.  The
         collective is enqueued behind the wgrad GEMMs already issued on the compute stream and runs on
@@ -188,6 +202,7 @@ class Trainer:
                 S = 2.0 ** max(-24, min(24, round(math.log2(x.numel() / max(self.alpha, 1e-30)))))
         scale = 1.0 / (self.world * S)
         self.gnorm_sq.zero_()
+        self._works, self._launched = [], 0     # an exception that escaped a previous backward must not leak buckets
         if self.fused:
             self.sink.begin_step()
             engine.set_grad_sink(self.sink)

@@ -121,6 +121,47 @@ def test_data_parallel_world2_equals_single_process(tmp_path, fused):
         assert rel_l2(dp[k], sd[k]) < 5e-5, (k, rel_l2(dp[k], sd[k]))
 
 
+def _dp_unseeded_worker(rank, world, port, name, out_dir):
+    """Like the reference's entry point: every rank draws its OWN initial weights and spectral-norm vectors."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from simulgen_vae_b200.trainer import Trainer
+    g = load_golden(name)
+    half = g["x"].shape[0] // world
+    sg.set_precision("fp32")
+    torch.manual_seed(1000 + 17 * rank)                                # different replicas before the broadcast
+    with emu.install():
+        m = build_engine_vae(g["cfg"], None)
+        m.train(True)
+        before = {k: v.clone() for k, v in m.state_dict().items()}
+        tr = Trainer(m, lr=1e-3, alpha=g["alpha"], bucket_mb=0)
+        after_init = {k: v.clone() for k, v in m.state_dict().items()}
+        for i in range(2):
+            eps = [e[rank * half:(rank + 1) * half] for e in g["eps"]]
+            with sg.fixed_eps(eps):
+                tr.step(g["x"][rank * half:(rank + 1) * half], beta=g["beta"], sample_offset=rank * half)
+    torch.save(dict(before=before, init=after_init, final={k: v.clone() for k, v in m.state_dict().items()}),
+               os.path.join(out_dir, "rank%d.pt" % rank))
+    torch.distributed.destroy_process_group()
+
+
+def test_data_parallel_replicas_are_broadcast_from_rank0(tmp_path):
+    """ranks that build their model without a common seed must still train ONE model - Trainer
+    broadcasts rank 0's parameters and buffers (incl. weight_u / weight_v) before the first step."""
+    name = "toy3_small_mse"
+    mp.spawn(_dp_unseeded_worker, args=(2, _free_port(), name, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(str(tmp_path / "rank0.pt"))
+    r1 = torch.load(str(tmp_path / "rank1.pt"))
+    differ = [k for k in r0["before"] if not torch.equal(r0["before"][k], r1["before"][k])]
+    assert any(k.endswith("weight_orig") for k in differ) and any(k.endswith("weight_u") for k in differ)
+    for k in r0["init"]:
+        assert torch.equal(r0["init"][k], r0["before"][k]), k          # rank 0 is the source
+        assert torch.equal(r1["init"][k], r0["init"][k]), k
+        assert torch.equal(r1["final"][k], r0["final"][k]), k          # and the replicas stay identical
+    assert any(not torch.equal(r0["final"][k], r0["init"][k]) for k in r0["init"])
+
+
 def _train_loop_worker(rank, world, port, workdir, data):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     torch.set_num_threads(1)
