@@ -90,8 +90,12 @@ int sg_conv_fprop(const void* wg, const void* act, int act_planes, long long act
 int sg_conv_fprop_gn(const void* wg, const void* act, int act_planes, long long act_plane_stride, const float* bias,
                      void* out, int out_bf16, int Cin, int Cin_p, int Cout, int k, int B, int T, int Tp, int G,
                      float* stats, double* ws, float* rowstat, int dtype, void* stream);
-int sg_conv_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_plane_stride, float* dx, int Cin,
-                  int Cin_p, int Cout, int k, int R, int accumulate, int dtype, void* stream);
+/* dx [Cin][R]: fp32, or (dx_dtype = the 16-bit operand format; needs sg_conv_out16_ok(Cin)) 16-bit - the gradient of
+ * an activation whose only consumer was this conv; accumulate then adds to the 16-bit content. */
+int sg_conv_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_plane_stride, void* dx, int dx_dtype,
+                  int Cin, int Cin_p, int Cout, int k, int R, int accumulate, int dtype, void* stream);
+/* 1 when a GEMM with M output rows (fprop: Cout, dgrad: Cin) runs on the CTA-pair kernel and can store 16 bits */
+int sg_conv_out16_ok(int M);
 int sg_conv_wgrad(const void* dy, int dy_planes, long long dy_plane_stride, const void* act, int act_planes,
                   long long act_plane_stride, float* dwg, int Cin, int Cin_p, int Cout, int k, int R, int dtype,
                   void* stream);
@@ -101,18 +105,24 @@ int sg_conv_wgrad(const void* dy, int dy_planes, long long dy_plane_stride, cons
  * (nn.GroupNorm semantics; accumulated and finalised in fp64).  ws: >= 2*B*G doubles. */
 int sg_gn_stats(const float* y, double* ws, float* stats, int C, int B, int T, int Tp, int G, void* stream);
 /* pre = res + res_scale * act(gamma * (y - mean) * rstd + beta)   (stats == NULL: no norm, y used as is)
- * out = post_gelu ? gelu(pre) : pre ; written as operand (out_op, dtype, gap zeroed) and/or fp32. */
-int sg_gn_act_fwd(const float* y, const float* stats, const float* gamma, const float* beta,
+ * out = post_gelu ? gelu(pre) : pre ; written as operand (out_op, dtype, gap zeroed) and/or fp32.
+ * y [C][B][Tp] is fp32 or (y_dtype = the 16-bit operand format) the 16-bit pre-norm output that sg_conv_fprop_gn
+ * stored with out_bf16 != 0 - its statistics were taken from the fp32 accumulators. */
+int sg_gn_act_fwd(const void* y, int y_dtype, const float* stats, const float* gamma, const float* beta,
                   const void* res, int res_is_f32, float res_scale, int act, int post_gelu,
                   void* out_op, int planes, long long plane_stride, float* out_f32,
                   int C, int B, int T, int Tp, int G, int dtype, void* stream);
-/* Backward of the above.  dout fp32 [C][B][Tp].  Writes dy (dtype, gap zeroed) = grad wrt y,
+/* Backward of the above.  dout [C][B][Tp]: fp32, or (dout_dtype) the 16-bit format when the dgrad GEMM that produced it
+ * stored 16 bits (sg_conv_dgrad with a 16-bit dx).  Writes dy (dtype, gap zeroed) = grad wrt y,
  * dgamma/dbeta (may be NULL when stats == NULL), dbias[C] = sum_{b,t} dy, and dres (fp32,
  * (+)= per dres_accumulate bit 0) when res != NULL.  ws: >= 2*B*G doubles.  dres_accumulate bit 1: dgamma, dbeta,
- * dbias and ws were zeroed by the caller (they are accumulated into with atomics). */
-int sg_gn_act_bwd(const float* y, const float* stats, const float* gamma, const float* beta,
+ * dbias and ws were zeroed by the caller (they are accumulated into with atomics).
+ * GroupNorm layers (stats != NULL) run two passes and OVERWRITE dout with dz = dL/d(gamma*xhat+beta): pass 1 takes the
+ * reductions and evaluates the activation derivative once, pass 2 is dy = rstd*(gamma*dz - m1 - xhat*m2).
+ * 16-bit y / dout are accepted for GroupNorm layers only. */
+int sg_gn_act_bwd(const void* y, int y_dtype, const float* stats, const float* gamma, const float* beta,
                   const void* res, int res_is_f32, float res_scale, int act, int post_gelu,
-                  const float* dout, void* dy, int planes, long long plane_stride,
+                  void* dout, int dout_dtype, void* dy, int planes, long long plane_stride,
                   float* dgamma, float* dbeta, float* dbias, float* dres, int dres_accumulate, double* ws,
                   int C, int B, int T, int Tp, int G, int dtype, void* stream);
 
@@ -228,9 +238,20 @@ typedef struct {
     long long n;         /* elements of p */
     int Cout, Cin, Cin_p, k, flip, reserved;
 } sg_opt_item;
+/* Device-resident dynamic loss scaler of the fp16-operand mode (the reference has no mixed precision; semantics are
+ * torch.cuda.amp.GradScaler's).  The trainer multiplies the loss by `scale` ON THE DEVICE before backward; sg_opt_step
+ * divides the gradients by it, and when any gradient is non-finite it skips the whole update (parameters, moments and
+ * `step` untouched), multiplies `scale` by `backoff` and counts the event; `growth_interval` consecutive clean steps
+ * multiply it by `growth`.  `step` is the AdamW bias-correction counter (advanced only by applied steps).
+ * scaler == NULL: no scaling, bias corrections from the host's `step` argument.
+ * dots: n_dots doubles of scratch, n_dots >= (number of spectral-norm items) + 6. */
+typedef struct sg_scaler_state {
+    float scale, growth, backoff, min_scale, max_scale;
+    int growth_interval, good_steps, step, skipped, last_skipped;
+} sg_scaler_state;
 int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots, int n_dots,
                 float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                double* gnorm_sq, void* stream);
+                double* gnorm_sq, sg_scaler_state* scaler, void* stream);
 
 /* ---- preprocessing scan (modules/data_preprocess.py:65-165, SimulGen-VAE.py:279-283) --------------
  * data: the field matrix [R = P*T][N] (nodes innermost), float64 (is_f64 = 1) or float32 - the dtype the reference's

@@ -99,24 +99,35 @@ if want("recon"):
            y.numel() * ybytes + x.numel() * 4 + dy.numel() * 2 + rows.numel() * 4)
     del y, dy, rows, x
 if want("gn_act"):
-    for C, P, res in ((5120, 5, False), (5120, 1, False), (1024, 1, True)):
+    # (channels, operand planes, residual, 16-bit y, 16-bit incoming gradient): round-1 fp32 hand-offs and the
+    # round-2 16-bit ones (engine.store16) side by side.  Bytes = algorithmic minimum of the kernel as called.
+    for C, P, res, y16, d16 in ((5120, 5, False, False, False), (5120, 5, False, True, True), (5120, 1, False, False, False),
+                                (5120, 1, False, True, True), (1024, 1, True, False, False), (1024, 1, True, True, False)):
+        OPD = torch.float16
+        tag = "C=%d planes=%d res=%d y%d d%d" % (C, P, res, 16 if y16 else 32, 16 if d16 else 32)
         y = torch.randn(C, B, Tp, device=dev)
         y[..., T:] = 0
         gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
         stats = torch.empty(B, G, 2, device=dev)
-        report("gn_stats C=%d" % C, timed(lambda: K.gn_stats(y, stats, T, G)), y.numel() * 4)
-        out = torch.empty(P, C, B, Tp, device=dev, dtype=BF)
+        if not y16:
+            report("gn_stats C=%d" % C, timed(lambda: K.gn_stats(y, stats, T, G)), y.numel() * 4)
+        else:
+            K.gn_stats(y, stats, T, G)
+            y = y.to(OPD)
+        yb, db_ = (2 if y16 else 4), (2 if d16 else 4)
+        out = torch.empty(P, C, B, Tp, device=dev, dtype=OPD)
         of = torch.empty(C, B, Tp, device=dev) if res else None
         r = torch.randn(C, B, Tp, device=dev) if res else None
-        nb = y.numel() * 4 + out.numel() * 2 + (y.numel() * 8 if res else 0)
-        report("gn_act_fwd C=%d planes=%d res=%d" % (C, P, res),
+        nb = y.numel() * yb + out.numel() * 2 + (y.numel() * 8 if res else 0)
+        report("gn_act_fwd " + tag,
                timed(lambda: K.gn_act_fwd(y, stats, gamma, beta, r, 0.1 if res else 1.0, K.ACT_GELU, False, out, of, T, G)), nb)
-        dout = torch.randn(C, B, Tp, device=dev)
-        dyo = torch.empty(P, C, B, Tp, device=dev, dtype=BF)
+        dout = torch.randn(C, B, Tp, device=dev).to(OPD if d16 else torch.float32)
+        dyo = torch.empty(P, C, B, Tp, device=dev, dtype=OPD)
         dg, db, dbi = (torch.empty(C, device=dev) for _ in range(3))
         dres = torch.zeros(C, B, Tp, device=dev) if res else None
-        nb = y.numel() * 16 + dyo.numel() * 2 + (y.numel() * 12 if res else 0)
-        report("gn_act_bwd C=%d planes=%d res=%d" % (C, P, res),
+        # pass 1: y + dout read, dz written (+ dres read-modify-write); pass 2: y + dz read, dy planes written
+        nb = y.numel() * (2 * yb + 3 * db_) + dyo.numel() * 2 + (y.numel() * 8 if res else 0)
+        report("gn_act_bwd " + tag,
                timed(lambda: K.gn_act_bwd(y, stats, gamma, beta, r, 0.1 if res else 1.0, K.ACT_GELU, False, dout, dyo, dg, db, dbi,
                                           dres, 1, T, G)), nb)
         del y, out, dout, dyo, of, r, dres

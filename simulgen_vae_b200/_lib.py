@@ -30,11 +30,12 @@ SIGNATURES = {
     "sg_sn_weight_grad": [P, P, P, P, P, P, P, I, I, I, I, L, L, I, P],
     "sg_conv_fprop": [P, P, I, L, P, P, I, I, I, I, I, I, I, P],
     "sg_conv_fprop_gn": [P, P, I, L, P, P, I, I, I, I, I, I, I, I, I, P, P, P, I, P],
-    "sg_conv_dgrad": [P, P, I, L, P, I, I, I, I, I, I, I, P],
+    "sg_conv_dgrad": [P, P, I, L, P, I, I, I, I, I, I, I, I, P],
+    "sg_conv_out16_ok": [I],
     "sg_conv_wgrad": [P, I, L, P, I, L, P, I, I, I, I, I, I, P],
     "sg_gn_stats": [P, P, P, I, I, I, I, I, P],
-    "sg_gn_act_fwd": [P, P, P, P, P, I, F, I, I, P, I, L, P, I, I, I, I, I, I, P],
-    "sg_gn_act_bwd": [P, P, P, P, P, I, F, I, I, P, P, I, L, P, P, P, P, I, P, I, I, I, I, I, I, P],
+    "sg_gn_act_fwd": [P, I, P, P, P, P, I, F, I, I, P, I, L, P, I, I, I, I, I, I, P],
+    "sg_gn_act_bwd": [P, I, P, P, P, P, I, F, I, I, P, I, P, I, L, P, P, P, P, I, P, I, I, I, I, I, I, P],
     "sg_recon_fwd": [P, I, P, P, P, P, P, P, P, I, I, I, I, I, I, P],
     "sg_recon_bwd": [P, I, P, P, P, P, P, P, F, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "sg_scale_f64_to_f32": [P, P, D, I, P],
@@ -48,7 +49,7 @@ SIGNATURES = {
     "sg_kl2_reparam_bwd": [P, P, P, F, P, P, F, P, P, I, I, I, I, P],
     "sg_philox_normal": [P, I, L, U, U, L, P],
     "sg_adamw_step": [P, P, P, P, L, F, F, F, F, F, I, F, P, P],
-    "sg_opt_step": [P, P, I, P, I, F, F, F, F, F, I, F, P, P],
+    "sg_opt_step": [P, P, I, P, I, F, F, F, F, F, I, F, P, P, P],
     "sg_sn_prepare": [P, P, I, P, L, I, I, P],
     "sg_assemble_batch": [P, I, P, P, P, P, P, I, I, I, I, U, U, P],
     "sg_minmax_fit": [P, I, P, L, L, P, L, P, P, I, P],

@@ -371,7 +371,7 @@ int tc_fprop(const void* wg, const void* act, int act_planes, long long act_pstr
     TcParams p{};
     default_formats(p);
     const bool pair = use_pair(Cout);
-    SG_REQUIRE(!out_bf16 || (pair && !accumulate), "conv_fprop: bf16 output needs the CTA-pair kernel (Cout > 128) and no accumulation");
+    SG_REQUIRE(!out_bf16 || pair, "conv_fprop: 16-bit output needs the CTA-pair kernel (Cout > 128)");
     p.out = (float*)out; p.bias = bias; p.M = Cout; p.N = R; p.ldc = R; p.c_sz = 0;
     p.m_tiles = (int)cdiv(Cout, pair ? pair::PM : BM); p.n_tiles = (int)cdiv(R, BN); p.z_count = 1; p.group_m = 8;
     p.taps = k; p.kblocks = (int)cdiv(Cin, BK); p.pad = k / 2; p.accumulate = accumulate;
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(256) gn_rowstat_finalize_kernel(const float* _
     }
 }
 
-int tc_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_pstride, float* dx, int Cin, int Cin_p,
+int tc_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_pstride, void* dx, int out16, int Cin, int Cin_p,
              int Cout, int k, int R, int accumulate, cudaStream_t st) {
     CUtensorMap ma, mb;
     if (make_map_wg(&ma, wg, Cin_p, Cout, k)) return 1;
@@ -423,11 +423,14 @@ int tc_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_pstride
     TcParams p{};
     default_formats(p);
     const bool pair = use_pair(Cin);
-    p.out = dx; p.bias = nullptr; p.M = Cin; p.N = R; p.ldc = R; p.c_sz = 0;
+    SG_REQUIRE(!out16 || pair, "conv_dgrad: 16-bit output needs the CTA-pair kernel (Cin > 128)");
+    p.out = (float*)dx; p.bias = nullptr; p.M = Cin; p.N = R; p.ldc = R; p.c_sz = 0;
     p.m_tiles = (int)cdiv(Cin, pair ? pair::PM : BM); p.n_tiles = (int)cdiv(R, BN); p.z_count = 1; p.group_m = 8;
     p.taps = k; p.kblocks = (int)cdiv(Cout, BK); p.pad = k / 2; p.accumulate = accumulate;
     p.b_plane0 = dy_planes / 2 + k / 2; p.b_plane_step = -1; p.a_plane = 0;
     p.splits = pick_splits(p.m_tiles * p.n_tiles, p.taps * p.kblocks, pair ? num_sms() / 2 : num_sms());
+    if (out16) p.splits = 1;                 // 16-bit stores cannot be split-K partial sums
+    p.out_bf16 = out16;
     p.atomic = p.splits > 1;
     p.m_fastest = p.m_tiles <= p.n_tiles;
     if (p.atomic && !accumulate) cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)Cin * R, st);
@@ -508,15 +511,23 @@ int sg_conv_fprop_gn(const void* wg, const void* act, int act_planes, long long 
     return sg_gn_stats((const float*)out, ws, stats, Cout, B, T, Tp, G, stream);
 }
 
-int sg_conv_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_pstride, float* dx, int Cin, int Cin_p,
-                  int Cout, int k, int R, int accumulate, int dtype, void* stream) {
+int sg_conv_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_pstride, void* dx, int dx_dtype, int Cin,
+                  int Cin_p, int Cout, int k, int R, int accumulate, int dtype, void* stream) {
     SG_CHECK_OP16(dtype);
+    SG_CHECK_OP16(dx_dtype);
     SG_CONV_CHECK("conv_dgrad", dy_planes);
-    if (dtype == SG_F32)
-        return simt_dgrad((const float*)wg, (const float*)dy + (long long)(dy_planes / 2) * dy_pstride, dx, Cin, Cin_p,
+    if (dtype == SG_F32) {
+        SG_REQUIRE(dx_dtype == SG_F32, "conv_dgrad: the fp32 validation mode writes fp32 gradients");
+        return simt_dgrad((const float*)wg, (const float*)dy + (long long)(dy_planes / 2) * dy_pstride, (float*)dx, Cin, Cin_p,
                           Cout, k, R, accumulate, as_stream(stream));
-    return tc_dgrad(wg, dy, dy_planes, dy_pstride, dx, Cin, Cin_p, Cout, k, R, accumulate, as_stream(stream));
+    }
+    return tc_dgrad(wg, dy, dy_planes, dy_pstride, dx, is_op16(dx_dtype) ? 1 : 0, Cin, Cin_p, Cout, k, R, accumulate,
+                    as_stream(stream));
 }
+
+/* 1 when a GEMM with M output rows runs on the CTA-pair kernel, i.e. can store a 16-bit output (fprop: M = Cout,
+ * dgrad: M = Cin) */
+int sg_conv_out16_ok(int M) { return use_pair(M) ? 1 : 0; }
 
 int sg_conv_wgrad(const void* dy, int dy_planes, long long dy_pstride, const void* act, int act_planes,
                   long long act_pstride, float* dwg, int Cin, int Cin_p, int Cout, int k, int R, int dtype,

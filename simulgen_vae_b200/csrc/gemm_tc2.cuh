@@ -228,7 +228,20 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const PairWork&
                         const int m = m_base + rl;
                         if (m < p.M) {
                             const uint32_t* sp = slab_u + rl * EPI_PITCH + sub_c;
-                            *reinterpret_cast<uint4*>(o16 + (long long)m * p.ldc + n) = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                            uint4 nv = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                            uint4* dst = reinterpret_cast<uint4*>(o16 + (long long)m * p.ldc + n);
+                            if (p.accumulate) {
+                                // 16-bit destination that already holds a gradient contribution: add in fp32, round once more
+                                const uint4 ov = *dst;
+                                const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ov);
+                                uint32_t* nw = reinterpret_cast<uint32_t*>(&nv);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 a = op16x2_to_f2(nw[e]), b = op16x2_to_f2(ow[e]);
+                                    nw[e] = f2_to_op16x2(a.x + b.x, a.y + b.y);
+                                }
+                            }
+                            *dst = nv;
                         }
                     }
                 }

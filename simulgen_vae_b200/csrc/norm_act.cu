@@ -179,9 +179,9 @@ __device__ __forceinline__ void act_both_t(float x, float& val, float& dval) {
 // ---------------------------------------------------------------------------------------------
 // forward apply: pre = res + res_scale * act(a*y + sh); out = POST ? gelu(pre) : pre
 // ---------------------------------------------------------------------------------------------
-template <typename OT, typename RT, int ACT, bool POST>
+template <typename OT, typename RT, typename YT, int ACT, bool POST>
 __global__ void __launch_bounds__(kThreads)
-gn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
+gn_act_fwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                   const float* __restrict__ beta, const RT* __restrict__ res, float res_scale, OT* __restrict__ out_op,
                   int planes, long long pstride, float* __restrict__ out_f32, int C, int B, int T, int Tp, int G) {
     extern __shared__ float sg_rows[];
@@ -201,7 +201,7 @@ gn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mr, con
             a = gamma[c] * st.y;
             sh = beta[c] - st.x * a;
         }
-        const float* yrow = y + row * Tp;
+        const YT* yrow = y + row * Tp;
         auto compute = [&](int seg, F8& o) {
             if (seg * 8 < T) {
                 F8 yv = load8(yrow + seg * 8);
@@ -323,90 +323,113 @@ __device__ __forceinline__ void bwd_compute(const BwdArgs& p, const SegIn& in, i
 constexpr int kChunkB = 16;
 constexpr int kRowsInFlight = 2;
 
-// pass 1 (GroupNorm layers only): dgamma[c] += sum dyh*xhat, dbeta[c] += sum dyh, S[b][g] += gamma_c * (those)
-template <typename RT, int ACT, bool POST>
+// ---- GroupNorm layers: two passes with a 16-bit-friendly hand-off --------------------------------------------------
+// pass 1 reads y and the incoming gradient, evaluates the activation derivative ONCE and leaves
+//     dz = res_scale * dp * act'(gamma * xhat + beta),   dp = dout (* gelu'(pre) for the trailing GELU)
+// in place of dout (same dtype: fp32, or the 16-bit operand format when the producing dgrad GEMM stored 16 bits),
+// together with the reductions of the GroupNorm backward (S[b][g] += gamma_c * (sum dz, sum dz * xhat), dgamma, dbeta)
+// and the gradient of the residual input (dres (+)= dp).  pass 2 is then three FMAs per element,
+//     dy = rstd * (gamma * dz - m1 - xhat * m2) = c1 * dz + c2 * y + c3,
+// plus the shifted operand planes and dbias.  Round 1 read y (fp32) and dout (fp32) twice and evaluated the exact-erf
+// GELU derivative in both passes (profiles/r1_ncu_source_gn_bwd_summary.txt: 43 instructions per element, issue-bound).
+struct Pass1Args {
+    const void* y;
+    void* dout;               // in: dout, out: dz
+    const float* mr;
+    const float* gamma;
+    const float* beta;
+    const void* res;
+    float res_scale;
+    int C, B, T, Tp, G;
+};
+
+template <typename RT, typename YT, typename DT, int ACT, bool POST>
 __global__ void __launch_bounds__(kThreads)
-gn_bwd_reduce_kernel(BwdArgs p, float* __restrict__ dgamma, float* __restrict__ dbeta, double* __restrict__ S) {
+gn_bwd_pass1_kernel(Pass1Args p, float* __restrict__ dgamma, float* __restrict__ dbeta, double* __restrict__ S,
+                    float* __restrict__ dres, int dres_accumulate) {
     constexpr int R = kRowsInFlight;
     const int lane = threadIdx.x & 31;
     const int Cg = p.C / p.G;
     const int nchunk = (p.B + kChunkB - 1) / kChunkB;
     const int tasks = p.C * nchunk, wstride = gridDim.x * kWarpsPerBlock;
     const float2* mr2 = reinterpret_cast<const float2*>(p.mr);
-    const bool one_seg = (p.Tp >> 3) <= 32;
+    const YT* y = reinterpret_cast<const YT*>(p.y);
+    DT* dout = reinterpret_cast<DT*>(p.dout);
+    const RT* res = reinterpret_cast<const RT*>(p.res);
+    const bool has_res = res != nullptr;
+    const int nseg_p = p.Tp >> 3;
     for (int task = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < tasks; task += wstride) {
         const int c = task / nchunk, ch = task - c * nchunk;
         const int b_lo = ch * kChunkB, b_hi = min(p.B, b_lo + kChunkB);
         const int g = c / Cg;
         const float gm = __ldg(p.gamma + c), bt = __ldg(p.beta + c);
         float sumA = 0.f, sumB = 0.f;
-        if (one_seg) {
-            // rows of <= 256 elements: one segment per lane; the loads of row b + 1 are in flight while row b is
-            // being processed (the kernel is bound by load latency, not by bandwidth or issue slots)
-            const bool live = lane * 8 < p.T;
-            const long long row0 = (long long)c * p.B;
-            SegIn cur, nxt;
-            float2 st = __ldg(mr2 + b_lo * p.G + g), st_n = st;
-            if (live) bwd_load<RT, POST>(p, row0 + b_lo, lane, cur);
-#pragma unroll 1
-            for (int b = b_lo; b < b_hi; ++b) {
-                if (b + 1 < b_hi) {
-                    if (live) bwd_load<RT, POST>(p, row0 + b + 1, lane, nxt);
-                    st_n = __ldg(mr2 + (b + 1) * p.G + g);
-                }
-                float A = 0.f, Bx = 0.f;
-                if (live) {
-                    const float a = gm * st.y, sh = bt - st.x * a;
-                    F8 dyh, xhat, dpre;
-                    bwd_compute<ACT, POST>(p, cur, lane, a, sh, st.x, st.y, dyh, xhat, dpre);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        A += dyh.v[i];
-                        Bx = fmaf(dyh.v[i], xhat.v[i], Bx);
-                    }
-                }
-                const float sa = warp_sum(A), sb = warp_sum(Bx);
-                sumA += sa;
-                sumB += sb;
-                if (lane == 0) {
-                    atomicAdd(&S[(size_t)(b * p.G + g) * 2], (double)(gm * sa));
-                    atomicAdd(&S[(size_t)(b * p.G + g) * 2 + 1], (double)(gm * sb));
-                }
-                cur = nxt;
-                st = st_n;
-            }
-            if (lane == 0) {
-                atomicAdd(&dgamma[c], sumB);
-                atomicAdd(&dbeta[c], sumA);
-            }
-            continue;
-        }
         for (int b0 = b_lo; b0 < b_hi; b0 += R) {
-            float a[R], sh[R], mean[R], rstd[R], A[R], Bx[R];
+            float a[R], sh[R], nm[R], rstd[R], A[R], Bx[R];
             bool ok[R];
+            long long row[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 ok[r] = b0 + r < b_hi;
-                const float2 st = __ldg(mr2 + (ok[r] ? b0 + r : b0) * p.G + g);
-                mean[r] = st.x;
+                const int bb = ok[r] ? b0 + r : b0;
+                row[r] = ((long long)c * p.B + bb) * p.Tp;
+                const float2 st = __ldg(mr2 + bb * p.G + g);
                 rstd[r] = st.y;
                 a[r] = gm * st.y;
                 sh[r] = bt - st.x * a[r];
+                nm[r] = -st.x * st.y;                 // xhat = y * rstd + nm
                 A[r] = 0.f;
                 Bx[r] = 0.f;
             }
-            for (int seg = lane; seg * 8 < p.T; seg += 32) {
-                SegIn in[R];
+            for (int seg = lane; seg < nseg_p; seg += 32) {
+                const bool live = seg * 8 < p.T;
+                F8 yv[R], dv[R], rv[R];
+                if (live) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) bwd_load<RT, POST>(p, (long long)c * p.B + (ok[r] ? b0 + r : b0), seg, in[r]);
+                    for (int r = 0; r < R; ++r) {        // every load of every row first
+                        yv[r] = load8(y + row[r] + seg * 8);
+                        dv[r] = load8(dout + row[r] + seg * 8);
+                        if (POST && has_res) rv[r] = load8(res + row[r] + seg * 8);
+                    }
+                }
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    F8 dyh, xhat, dpre;
-                    bwd_compute<ACT, POST>(p, in[r], seg, a[r], sh[r], mean[r], rstd[r], dyh, xhat, dpre);
+                    F8 dz, dp;
+                    if (live) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        A[r] += dyh.v[i];
-                        Bx[r] = fmaf(dyh.v[i], xhat.v[i], Bx[r]);
+                        for (int i = 0; i < 8; ++i) {
+                            float val, dval;
+                            act_both_t<ACT>(fmaf(yv[r].v[i], a[r], sh[r]), val, dval);
+                            float d = dv[r].v[i];
+                            if (POST) d *= gelu_grad_f(fmaf(p.res_scale, val, has_res ? rv[r].v[i] : 0.f));
+                            dp.v[i] = d;
+                            dz.v[i] = p.res_scale * d * dval;
+                        }
+                        if (seg * 8 + 8 > p.T) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (seg * 8 + i >= p.T) { dz.v[i] = 0.f; dp.v[i] = 0.f; }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            A[r] += dz.v[i];
+                            Bx[r] = fmaf(dz.v[i], fmaf(yv[r].v[i], rstd[r], nm[r]), Bx[r]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { dz.v[i] = 0.f; dp.v[i] = 0.f; }
+                    }
+                    if (ok[r]) {
+                        store8(dout + row[r] + seg * 8, dz);
+                        if (dres != nullptr) {
+                            float* dr = dres + row[r] + seg * 8;
+                            if (dres_accumulate) {
+                                F8 old = load8(dr);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) dp.v[i] += old.v[i];
+                            }
+                            store8(dr, dp);
+                        }
                     }
                 }
             }
@@ -427,6 +450,113 @@ gn_bwd_reduce_kernel(BwdArgs p, float* __restrict__ dgamma, float* __restrict__ 
             atomicAdd(&dgamma[c], sumB);
             atomicAdd(&dbeta[c], sumA);
         }
+    }
+}
+
+template <typename OT, typename YT, typename DT>
+__global__ void __launch_bounds__(kThreads)
+gn_bwd_pass2_kernel(const YT* __restrict__ y, const DT* __restrict__ dz, const float* __restrict__ mr,
+                    const float* __restrict__ gamma, const double* __restrict__ S, OT* __restrict__ dy, int planes,
+                    long long pstride, float* __restrict__ dbias, int C, int B, int T, int Tp, int G, float inv_n) {
+    constexpr int R = kRowsInFlight;
+    extern __shared__ float sg_rows[];
+    const int lane = threadIdx.x & 31;
+    float* srow = sg_rows + (threadIdx.x >> 5) * (Tp + 8);
+    const bool multi = planes > 1;
+    const int nseg_p = Tp >> 3;
+    const bool shfl = nseg_p <= 32;
+    if (multi && !shfl) srow_clear_halo(srow, Tp, lane);
+    const int Cg = C / G;
+    const int nchunk = (B + kChunkB - 1) / kChunkB;
+    const int tasks = C * nchunk, wstride = gridDim.x * kWarpsPerBlock;
+    const float2* mr2 = reinterpret_cast<const float2*>(mr);
+    for (int task = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < tasks; task += wstride) {
+        const int c = task / nchunk, ch = task - c * nchunk;
+        const int b_lo = ch * kChunkB, b_hi = min(B, b_lo + kChunkB);
+        const int g = c / Cg;
+        const float gm = __ldg(gamma + c);
+        float db = 0.f;
+        for (int b0 = b_lo; b0 < b_hi; b0 += R) {
+            float c1[R], c2[R], c3[R];
+            bool ok[R];
+            long long row[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                ok[r] = b0 + r < b_hi;
+                const int bb = ok[r] ? b0 + r : b0;
+                row[r] = ((long long)c * B + bb) * Tp;
+                const float2 st = __ldg(mr2 + bb * G + g);
+                const float m1 = (float)S[(size_t)(bb * G + g) * 2] * inv_n;
+                const float m2 = (float)S[(size_t)(bb * G + g) * 2 + 1] * inv_n;
+                c1[r] = st.y * gm;
+                c2[r] = -st.y * st.y * m2;
+                c3[r] = st.y * (st.x * st.y * m2 - m1);
+            }
+            auto finish = [&](int r, int seg, const F8& yv, const F8& zv, F8& o) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o.v[i] = fmaf(c1[r], zv.v[i], fmaf(c2[r], yv.v[i], c3[r]));
+                if (seg * 8 + 8 > T) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (seg * 8 + i >= T) o.v[i] = 0.f;
+                }
+                if (ok[r]) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) db += o.v[i];
+                }
+            };
+            if (shfl || !multi) {
+                for (int seg = lane; seg < (shfl ? 32 : nseg_p); seg += 32) {
+                    const bool live = seg * 8 < T;
+                    F8 yv[R], zv[R];
+                    if (live) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            yv[r] = load8(y + row[r] + seg * 8);
+                            zv[r] = load8(dz + row[r] + seg * 8);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        F8 o;
+                        if (live) {
+                            finish(r, seg, yv[r], zv[r], o);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+                        }
+                        if (multi) {
+                            if (ok[r]) store_planes_shfl_n(dy, row[r], planes, pstride, o, T, nseg_p, lane);
+                        } else if (ok[r] && seg < nseg_p) {
+                            store8(dy + row[r] + seg * 8, o);
+                        }
+                    }
+                }
+            } else {
+                // long rows with shifted planes: staged through shared memory, one row at a time
+#pragma unroll 1
+                for (int r = 0; r < R; ++r) {
+                    if (!ok[r]) continue;
+                    for (int seg = lane; seg < nseg_p; seg += 32) {
+                        F8 o;
+                        if (seg * 8 < T) {
+                            F8 yv = load8(y + row[r] + seg * 8), zv = load8(dz + row[r] + seg * 8);
+                            finish(r, seg, yv, zv, o);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) srow[4 + seg * 8 + i] = o.v[i];
+                    }
+                    __syncwarp();
+                    store_row_planes(dy, row[r], planes, pstride, srow, T, Tp, lane);
+                    __syncwarp();
+                }
+            }
+        }
+        db = warp_sum(db);
+        if (lane == 0 && dbias != nullptr) atomicAdd(&dbias[c], db);
     }
 }
 
@@ -1088,20 +1218,20 @@ __global__ void recon_scalars_kernel(const float* g_loss, const float* g_mse, fl
 // ---------------------------------------------------------------------------------------------
 // host-side dispatch over the template parameters
 // ---------------------------------------------------------------------------------------------
-template <typename OT, typename RT, int ACT, bool POST>
-static void launch_fwd_t(const float* y, const float* mr, const float* gamma, const float* beta, const void* res,
+template <typename OT, typename RT, typename YT, int ACT, bool POST>
+static void launch_fwd_t(const void* y, const float* mr, const float* gamma, const float* beta, const void* res,
                          float res_scale, void* out_op, int planes, long long pstride, float* out_f32, int C, int B, int T,
                          int Tp, int G, cudaStream_t st) {
     size_t sm = (planes > 1 && out_op) ? sizeof(float) * kWarpsPerBlock * (Tp + 8) : 0;
-    gn_act_fwd_kernel<OT, RT, ACT, POST><<<persistent_grid((long long)C * B), kThreads, sm, st>>>(
-        y, mr, gamma, beta, (const RT*)res, res_scale, (OT*)out_op, planes, pstride, out_f32, C, B, T, Tp, G);
+    gn_act_fwd_kernel<OT, RT, YT, ACT, POST><<<persistent_grid((long long)C * B), kThreads, sm, st>>>(
+        (const YT*)y, mr, gamma, beta, (const RT*)res, res_scale, (OT*)out_op, planes, pstride, out_f32, C, B, T, Tp, G);
 }
 
-template <typename OT, typename RT>
-static int launch_fwd(int act, int post, const float* y, const float* mr, const float* gamma, const float* beta,
+template <typename OT, typename RT, typename YT>
+static int launch_fwd(int act, int post, const void* y, const float* mr, const float* gamma, const float* beta,
                       const void* res, float res_scale, void* out_op, int planes, long long pstride, float* out_f32, int C,
                       int B, int T, int Tp, int G, cudaStream_t st) {
-#define SG_F(ACT, POST) launch_fwd_t<OT, RT, ACT, POST>(y, mr, gamma, beta, res, res_scale, out_op, planes, pstride, out_f32, C, B, T, Tp, G, st)
+#define SG_F(ACT, POST) launch_fwd_t<OT, RT, YT, ACT, POST>(y, mr, gamma, beta, res, res_scale, out_op, planes, pstride, out_f32, C, B, T, Tp, G, st)
     if (act == SG_ACT_GELU) { if (post) SG_F(SG_ACT_GELU, true); else SG_F(SG_ACT_GELU, false); }
     else if (act == SG_ACT_TANH) { if (post) SG_F(SG_ACT_TANH, true); else SG_F(SG_ACT_TANH, false); }
     else { if (post) SG_F(SG_ACT_NONE, true); else SG_F(SG_ACT_NONE, false); }
@@ -1109,35 +1239,40 @@ static int launch_fwd(int act, int post, const float* y, const float* mr, const 
     return check_launch("gn_act_fwd");
 }
 
+// layers without GroupNorm (ConvTranspose1d + GELU, plain convs): one pass, fp32 y and dout
 template <typename OT, typename RT, int ACT, bool POST>
-static void launch_bwd_t(const BwdArgs& p, OT* dy, int planes, long long pstride, float* dgamma, float* dbeta, float* dbias,
-                         float* dres, int dres_accumulate, double* ws, cudaStream_t st) {
+static void launch_bwd_plain_t(const BwdArgs& p, OT* dy, int planes, long long pstride, float* dbias, float* dres,
+                               int dres_accumulate, double* ws, cudaStream_t st) {
     size_t sm = planes > 1 ? sizeof(float) * kWarpsPerBlock * (p.Tp + 8) : 0;
     int grid = persistent_grid((long long)p.C * cdiv(p.B, kChunkB));
-    if (p.mr != nullptr) gn_bwd_reduce_kernel<RT, ACT, POST><<<grid, kThreads, 0, st>>>(p, dgamma, dbeta, ws);
     gn_bwd_apply_kernel<OT, RT, ACT, POST><<<grid, kThreads, sm, st>>>(p, ws, dy, planes, pstride, dbias, dres, dres_accumulate);
 }
 
 template <typename OT, typename RT>
-static int launch_bwd(int act, int post, const BwdArgs& p, OT* dy, int planes, long long pstride, float* dgamma, float* dbeta,
-                      float* dbias, float* dres, int dres_accumulate, double* ws, cudaStream_t st) {
-    // dres_accumulate bit 1: the caller hands in dbias / dgamma / dbeta / ws already zeroed (one memset per step for
-    // the whole gradient arena instead of four tiny ones per layer)
-    const bool prezeroed = (dres_accumulate & 2) != 0;
-    dres_accumulate &= 1;
-    if (!prezeroed) {
-        if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * p.C, st);
-        if (p.mr != nullptr) {
-            cudaMemsetAsync(dgamma, 0, sizeof(float) * p.C, st);
-            cudaMemsetAsync(dbeta, 0, sizeof(float) * p.C, st);
-            cudaMemsetAsync(ws, 0, sizeof(double) * 2 * p.B * p.G, st);
-        }
-    }
-#define SG_B(ACT, POST) launch_bwd_t<OT, RT, ACT, POST>(p, dy, planes, pstride, dgamma, dbeta, dbias, dres, dres_accumulate, ws, st)
+static int launch_bwd_plain(int act, int post, const BwdArgs& p, OT* dy, int planes, long long pstride, float* dbias,
+                            float* dres, int dres_accumulate, double* ws, cudaStream_t st) {
+#define SG_B(ACT, POST) launch_bwd_plain_t<OT, RT, ACT, POST>(p, dy, planes, pstride, dbias, dres, dres_accumulate, ws, st)
     if (act == SG_ACT_GELU) { if (post) SG_B(SG_ACT_GELU, true); else SG_B(SG_ACT_GELU, false); }
     else if (act == SG_ACT_TANH) { if (post) SG_B(SG_ACT_TANH, true); else SG_B(SG_ACT_TANH, false); }
     else { if (post) SG_B(SG_ACT_NONE, true); else SG_B(SG_ACT_NONE, false); }
 #undef SG_B
+    return check_launch("gn_act_bwd");
+}
+
+// GroupNorm layers: pass 1 (dout -> dz in place, reductions, dres) + pass 2 (dy planes, dbias)
+template <typename OT, typename RT, typename YT, typename DT>
+static int launch_bwd_gn(int act, int post, const Pass1Args& p, OT* dy, int planes, long long pstride, float* dgamma,
+                         float* dbeta, float* dbias, float* dres, int dres_accumulate, double* ws, cudaStream_t st) {
+    const int grid = persistent_grid((long long)p.C * cdiv(p.B, kChunkB));
+#define SG_P1(ACT, POST) gn_bwd_pass1_kernel<RT, YT, DT, ACT, POST><<<grid, kThreads, 0, st>>>(p, dgamma, dbeta, ws, dres, dres_accumulate)
+    if (act == SG_ACT_GELU) { if (post) SG_P1(SG_ACT_GELU, true); else SG_P1(SG_ACT_GELU, false); }
+    else if (act == SG_ACT_TANH) { if (post) SG_P1(SG_ACT_TANH, true); else SG_P1(SG_ACT_TANH, false); }
+    else { if (post) SG_P1(SG_ACT_NONE, true); else SG_P1(SG_ACT_NONE, false); }
+#undef SG_P1
+    const size_t sm = (planes > 1 && (p.Tp >> 3) > 32) ? sizeof(float) * kWarpsPerBlock * (p.Tp + 8) : 0;
+    const float inv_n = (float)(1.0 / ((double)(p.C / p.G) * p.T));
+    gn_bwd_pass2_kernel<OT, YT, DT><<<grid, kThreads, sm, st>>>((const YT*)p.y, (const DT*)p.dout, p.mr, p.gamma, ws, dy, planes,
+                                                              pstride, dbias, p.C, p.B, p.T, p.Tp, p.G, inv_n);
     return check_launch("gn_act_bwd");
 }
 
@@ -1201,49 +1336,85 @@ int sg_gn_stats(const float* y, double* ws, float* mr, int C, int B, int T, int 
     return check_launch("gn_stats");
 }
 
-int sg_gn_act_fwd(const float* y, const float* mr, const float* gamma, const float* beta, const void* res,
+int sg_gn_act_fwd(const void* y, int y_dtype, const float* mr, const float* gamma, const float* beta, const void* res,
                   int res_is_f32, float res_scale, int act, int post_gelu, void* out_op, int planes,
                   long long plane_stride, float* out_f32, int C, int B, int T, int Tp, int G, int dtype, void* stream) {
     SG_CHECK_OP16(dtype);
+    SG_CHECK_OP16(y_dtype);
     SG_REQUIRE(Tp % 8 == 0, "gn_act_fwd: Tp %% 8 != 0");
     SG_REQUIRE(planes == 1 || planes == 3 || planes == 5, "gn_act_fwd: planes must be 1, 3 or 5");
     SG_REQUIRE(mr == nullptr || (G > 0 && C % G == 0), "gn_act_fwd: bad groups");
+    SG_REQUIRE(y_dtype == SG_F32 || is_op16(dtype), "gn_act_fwd: a 16-bit y needs a 16-bit operand mode");
     cudaStream_t st = as_stream(stream);
     if (G <= 0) G = 1;
+    typedef __nv_bfloat16 h16;
+    const bool y16 = is_op16(y_dtype), r16 = res != nullptr && !res_is_f32;
+#define SG_FW(OT, RT, YT) return launch_fwd<OT, RT, YT>(act, post_gelu, y, mr, gamma, beta, res, res_scale, out_op, planes, plane_stride, out_f32, C, B, T, Tp, G, st)
     if (is_op16(dtype)) {
-        if (res == nullptr || res_is_f32)
-            return launch_fwd<__nv_bfloat16, float>(act, post_gelu, y, mr, gamma, beta, res, res_scale, out_op, planes,
-                                                    plane_stride, out_f32, C, B, T, Tp, G, st);
-        return launch_fwd<__nv_bfloat16, __nv_bfloat16>(act, post_gelu, y, mr, gamma, beta, res, res_scale, out_op, planes,
-                                                        plane_stride, out_f32, C, B, T, Tp, G, st);
+        if (y16) { if (r16) SG_FW(h16, h16, h16); else SG_FW(h16, float, h16); }
+        else     { if (r16) SG_FW(h16, h16, float); else SG_FW(h16, float, float); }
     }
-    return launch_fwd<float, float>(act, post_gelu, y, mr, gamma, beta, res, res_scale, out_op, planes, plane_stride, out_f32,
-                                    C, B, T, Tp, G, st);
+    SG_REQUIRE(!r16, "gn_act_fwd: fp32 mode takes an fp32 residual");
+    SG_FW(float, float, float);
+#undef SG_FW
 }
 
-int sg_gn_act_bwd(const float* y, const float* mr, const float* gamma, const float* beta, const void* res,
-                  int res_is_f32, float res_scale, int act, int post_gelu, const float* dout, void* dy, int planes,
+int sg_gn_act_bwd(const void* y, int y_dtype, const float* mr, const float* gamma, const float* beta, const void* res,
+                  int res_is_f32, float res_scale, int act, int post_gelu, void* dout, int dout_dtype, void* dy, int planes,
                   long long plane_stride, float* dgamma, float* dbeta, float* dbias, float* dres, int dres_accumulate,
                   double* ws, int C, int B, int T, int Tp, int G, int dtype, void* stream) {
     SG_CHECK_OP16(dtype);
+    SG_CHECK_OP16(y_dtype);
+    SG_CHECK_OP16(dout_dtype);
     SG_REQUIRE(Tp % 8 == 0, "gn_act_bwd: Tp %% 8 != 0");
     SG_REQUIRE(planes == 1 || planes == 3 || planes == 5, "gn_act_bwd: planes must be 1, 3 or 5");
     SG_REQUIRE(mr == nullptr || (G > 0 && C % G == 0 && dgamma && dbeta && ws), "gn_act_bwd: bad GN arguments");
+    SG_REQUIRE((y_dtype == SG_F32 && dout_dtype == SG_F32) || (is_op16(dtype) && mr != nullptr),
+               "gn_act_bwd: 16-bit y / dout only for GroupNorm layers in a 16-bit operand mode");
     if (G <= 0) G = 1;
-    BwdArgs p{};
-    p.y = y; p.mr = mr; p.gamma = gamma; p.beta = beta; p.res = res; p.res_scale = res_scale; p.dout = dout;
-    p.C = C; p.B = B; p.T = T; p.Tp = Tp; p.G = G;
-    p.inv_n = mr ? 1.0 / ((double)(C / G) * T) : 0.0;
     cudaStream_t st = as_stream(stream);
-    if (is_op16(dtype)) {
-        if (res == nullptr || res_is_f32)
-            return launch_bwd<__nv_bfloat16, float>(act, post_gelu, p, (__nv_bfloat16*)dy, planes, plane_stride, dgamma, dbeta,
-                                                    dbias, dres, dres_accumulate, ws, st);
-        return launch_bwd<__nv_bfloat16, __nv_bfloat16>(act, post_gelu, p, (__nv_bfloat16*)dy, planes, plane_stride, dgamma,
-                                                        dbeta, dbias, dres, dres_accumulate, ws, st);
+    // dres_accumulate bit 1: the caller hands in dbias / dgamma / dbeta / ws already zeroed (one memset per step for
+    // the whole gradient arena instead of four tiny ones per layer)
+    const bool prezeroed = (dres_accumulate & 2) != 0;
+    dres_accumulate &= 1;
+    if (!prezeroed) {
+        if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * C, st);
+        if (mr != nullptr) {
+            cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st);
+            cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st);
+            cudaMemsetAsync(ws, 0, sizeof(double) * 2 * B * G, st);
+        }
     }
-    return launch_bwd<float, float>(act, post_gelu, p, (float*)dy, planes, plane_stride, dgamma, dbeta, dbias, dres,
-                                    dres_accumulate, ws, st);
+    typedef __nv_bfloat16 h16;
+    const bool r16 = res != nullptr && !res_is_f32;
+    if (mr != nullptr) {
+        Pass1Args p{};
+        p.y = y; p.dout = dout; p.mr = mr; p.gamma = gamma; p.beta = beta; p.res = res; p.res_scale = res_scale;
+        p.C = C; p.B = B; p.T = T; p.Tp = Tp; p.G = G;
+        const bool y16 = is_op16(y_dtype), d16 = is_op16(dout_dtype);
+#define SG_BG(OT, RT, YT, DT) return launch_bwd_gn<OT, RT, YT, DT>(act, post_gelu, p, (OT*)dy, planes, plane_stride, dgamma, dbeta, dbias, dres, dres_accumulate, ws, st)
+        if (is_op16(dtype)) {
+            if (r16) {
+                if (y16) { if (d16) SG_BG(h16, h16, h16, h16); else SG_BG(h16, h16, h16, float); }
+                else     { if (d16) SG_BG(h16, h16, float, h16); else SG_BG(h16, h16, float, float); }
+            } else {
+                if (y16) { if (d16) SG_BG(h16, float, h16, h16); else SG_BG(h16, float, h16, float); }
+                else     { if (d16) SG_BG(h16, float, float, h16); else SG_BG(h16, float, float, float); }
+            }
+        }
+        SG_REQUIRE(!r16, "gn_act_bwd: fp32 mode takes an fp32 residual");
+        SG_BG(float, float, float, float);
+#undef SG_BG
+    }
+    BwdArgs p{};
+    p.y = (const float*)y; p.mr = nullptr; p.gamma = gamma; p.beta = beta; p.res = res; p.res_scale = res_scale;
+    p.dout = (const float*)dout; p.C = C; p.B = B; p.T = T; p.Tp = Tp; p.G = G; p.inv_n = 0.0;
+    if (is_op16(dtype)) {
+        if (!r16)
+            return launch_bwd_plain<h16, float>(act, post_gelu, p, (h16*)dy, planes, plane_stride, dbias, dres, dres_accumulate, ws, st);
+        return launch_bwd_plain<h16, h16>(act, post_gelu, p, (h16*)dy, planes, plane_stride, dbias, dres, dres_accumulate, ws, st);
+    }
+    return launch_bwd_plain<float, float>(act, post_gelu, p, (float*)dy, planes, plane_stride, dbias, dres, dres_accumulate, ws, st);
 }
 
 int sg_recon_fwd(const void* y, int y_dtype, const float* mr, const float* gamma, const float* beta, const float* x,

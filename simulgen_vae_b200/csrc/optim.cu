@@ -60,14 +60,24 @@ __device__ __forceinline__ void decode(const sg_opt_item& it, int e, int& o, int
     gidx = ((long long)jj * it.Cout + o) * it.Cin_p + i;
 }
 
+// `bad` (may be NULL): incremented when a block sees a non-finite gradient.  For spectral-norm layers the block's share
+// of <G, W> is non-finite whenever one of its G elements is (inf * w = +-inf or NaN, NaN * w = NaN, and sums keep it);
+// plain vectors (biases, GroupNorm affine) are scanned with 0 * g, which is NaN exactly for non-finite g.
 __global__ void __launch_bounds__(kOptThreads)
-opt_dot_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ OptPrefix pf) {
+opt_dot_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ OptPrefix pf, double* __restrict__ bad) {
     __shared__ double sh[32];
     const int idx = find_item(pf, blockIdx.x);
     const sg_opt_item it = items[idx];
-    if (it.u == nullptr) return;
     const long long e0 = (long long)(blockIdx.x - pf.start[idx]) * kOptChunk;
     const long long e1 = min(it.n, e0 + kOptChunk);
+    if (it.u == nullptr) {
+        if (bad == nullptr) return;
+        float z = 0.f;
+        for (long long e = e0 + threadIdx.x; e < e1; e += kOptThreads) z = fmaf(0.f, it.g[e], z);
+        double t = block_sum((double)z, sh);
+        if (threadIdx.x == 0 && !isfinite(t)) atomicAdd(bad, 1.0);
+        return;
+    }
     float acc = 0.f;
     const bool direct = it.k == 1 && !it.flip && it.Cin_p == it.Cin;
     if (direct && (it.n & 3) == 0 && aligned16(it.g, it.p)) {
@@ -100,12 +110,50 @@ opt_dot_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ Op
         }
     }
     double t = block_sum((double)acc, sh);
-    if (threadIdx.x == 0) atomicAdd(it.dot, t);
+    if (threadIdx.x == 0) {
+        atomicAdd(it.dot, t);
+        if (bad != nullptr && !isfinite(t)) atomicAdd(bad, 1.0);
+    }
 }
 
 struct AdamArgs {
     float lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale;
+    int skip, pad;
 };
+
+// One thread between the two passes.  Without a scaler: bias corrections from the host's step counter.  With the
+// device-resident dynamic loss scaler (fp16 operands: include/simulgen_b200.h, sg_scaler_state): a step whose gradients
+// overflowed is SKIPPED (no parameter, moment or step-count change - torch.cuda.amp.GradScaler semantics) and the scale
+// backs off; `growth_interval` clean steps in a row grow it.  Nothing here needs the host: the Trainer multiplies the
+// loss by state->scale on the device and never reads it back.
+__global__ void opt_prologue_kernel(AdamArgs a, int host_step, sg_scaler_state* __restrict__ st, const double* __restrict__ bad,
+                                    AdamArgs* __restrict__ out, double* __restrict__ gnorm_sq) {
+    int step = host_step;
+    a.skip = 0;
+    if (st != nullptr) {
+        const float used = st->scale;
+        a.grad_scale = a.grad_scale / used;
+        if (bad != nullptr && bad[0] != 0.0) {
+            a.skip = 1;
+            st->scale = fmaxf(used * st->backoff, st->min_scale);
+            st->good_steps = 0;
+            st->skipped += 1;
+            st->last_skipped = 1;
+            if (gnorm_sq != nullptr) gnorm_sq[0] = (double)INFINITY;
+        } else {
+            st->step += 1;
+            st->last_skipped = 0;
+            if (++st->good_steps >= st->growth_interval) {
+                st->scale = fminf(used * st->growth, st->max_scale);
+                st->good_steps = 0;
+            }
+        }
+        step = st->step;
+    }
+    a.bc1 = (float)(1.0 - pow((double)a.b1, (double)step));
+    a.bc2_sqrt = sqrtf((float)(1.0 - pow((double)a.b2, (double)step)));
+    *out = a;
+}
 
 __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamArgs& a) {
     p = p * (1.f - a.lr * a.wd);
@@ -116,9 +164,11 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
 }
 
 __global__ void __launch_bounds__(kOptThreads)
-opt_step_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ OptPrefix pf, AdamArgs a,
+opt_step_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ OptPrefix pf, const AdamArgs* __restrict__ args,
                 double* __restrict__ gnorm_sq) {
     __shared__ double sh[32];
+    const AdamArgs a = *args;
+    if (a.skip) return;
     const int idx = find_item(pf, blockIdx.x);
     const sg_opt_item it = items[idx];
     const long long e0 = (long long)(blockIdx.x - pf.start[idx]) * kOptChunk;
@@ -224,8 +274,13 @@ using namespace sg;
 
 extern "C" int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots,
                            int n_dots, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                           float grad_scale, double* gnorm_sq, void* stream) {
+                           float grad_scale, double* gnorm_sq, sg_scaler_state* scaler, void* stream) {
     SG_REQUIRE(n_items > 0 && n_items <= kMaxItems, "opt_step: n_items=%d out of range (max %d)", n_items, kMaxItems);
+    // dots[0 .. n_dots - 3): one <G, W> per spectral-norm layer; then 1 double "non-finite gradient seen" and
+    // sizeof(AdamArgs) = 40 bytes (5 doubles) for the device copy of the step's scalars
+    SG_REQUIRE(dots != nullptr && n_dots >= 6, "opt_step: dots buffer needs >= 6 trailing scratch elements");
+    double* bad = dots + (n_dots - 6);
+    AdamArgs* dev_args = reinterpret_cast<AdamArgs*>(dots + (n_dots - 5));
     cudaStream_t st = as_stream(stream);
     OptPrefix pf;
     pf.n_items = n_items;
@@ -245,15 +300,12 @@ extern "C" int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* item
     }
     SG_REQUIRE(total < (1LL << 31), "opt_step: too many chunks");
     pf.start[n_items] = (int)total;
-    if (any_sn) {
-        SG_REQUIRE(dots != nullptr && n_dots > 0, "opt_step: dots buffer missing");
-        cudaMemsetAsync(dots, 0, sizeof(double) * n_dots, st);
-        opt_dot_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf);
-    }
-    AdamArgs a;
+    cudaMemsetAsync(dots, 0, sizeof(double) * n_dots, st);
+    if (any_sn || scaler != nullptr)
+        opt_dot_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, scaler != nullptr ? bad : nullptr);
+    AdamArgs a{};
     a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.wd = weight_decay; a.grad_scale = grad_scale;
-    a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
-    a.bc2_sqrt = sqrtf((float)(1.0 - pow((double)beta2, (double)step)));
-    opt_step_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, a, gnorm_sq);
+    opt_prologue_kernel<<<1, 1, 0, st>>>(a, step, scaler, scaler != nullptr ? bad : nullptr, dev_args, gnorm_sq);
+    opt_step_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, dev_args, gnorm_sq);
     return check_launch("opt_step");
 }

@@ -170,14 +170,28 @@ def conv_fprop_gn(wg, act, bias, out, Cin, stats, T, G):
 
 
 def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
-    """dy: operand [P, Cout, B, Tp]; dx fp32 [Cin, B, Tp]."""
+    """dy: operand [P, Cout, B, Tp]; dx [Cin, B, Tp] fp32, or the operand dtype when conv_out16_ok(Cin)."""
     k, Cout, Cin_p = wg.shape
     dp, dn, dstr = _planes(dy)
     R = dy.shape[2] * dy.shape[3]
     assert dy.shape[1] == Cout and dx.shape[0] == Cin and dx.numel() == Cin * R and wg.dtype == dy.dtype
+    assert dx.dtype == torch.float32 or dx.dtype == dy.dtype
+    dxd = _dt(dx)
     _timed("dgrad", 2.0 * Cin * Cout * k * R, lambda: _call(
-        "sg_conv_dgrad", _p(wg), dp, dn, dstr, _p(_f32(dx, "dx")), Cin, Cin_p, Cout, k, R, int(accumulate), _dt(dy),
+        "sg_conv_dgrad", _p(wg), dp, dn, dstr, _p(dx), dxd, Cin, Cin_p, Cout, k, R, int(accumulate), _dt(dy),
         _stream()))
+
+
+_OUT16_OK = {}
+
+
+def conv_out16_ok(M):
+    """True when a GEMM with M output rows (fprop: Cout, dgrad: Cin) runs on the CTA-pair kernel, which can store its
+    output in the 16-bit operand format."""
+    r = _OUT16_OK.get(M)
+    if r is None:
+        r = _OUT16_OK[M] = bool(_lib.load(False).sg_conv_out16_ok(int(M)))
+    return r
 
 
 def conv_wgrad(dy, act, dwg, Cin):
@@ -200,20 +214,24 @@ def gn_stats(y, stats, T, G):
 
 
 def gn_act_fwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, out_op, out_f32, T, G):
-    """out_op: operand [P, C, B, Tp] (all planes written) or None; res: [C, B, Tp] fp32 or operand dtype."""
+    """y: [C, B, Tp] fp32 or the 16-bit operand dtype (pre-norm conv output stored by conv_fprop_gn); out_op: operand
+    [P, C, B, Tp] (all planes written) or None; res: [C, B, Tp] fp32 or operand dtype."""
     C, B, Tp = y.shape
-    dt = _dt(out_op) if out_op is not None else SG_F32
+    yd = _dt(y)
+    dt = _dt(out_op) if out_op is not None else (yd if yd != SG_F32 else SG_F32)
     op, on, ostr = _planes(out_op)
     res_is_f32 = int(res is not None and res.dtype == torch.float32)
-    _call("sg_gn_act_fwd", _p(_f32(y, "y")), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(res), res_is_f32, float(res_scale),
+    _call("sg_gn_act_fwd", _p(y), yd, _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(res), res_is_f32, float(res_scale),
           int(act), int(post_gelu), op, on, ostr, _p(out_f32), C, B, T, Tp, int(G), dt, _stream())
 
 
 def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, dgamma, dbeta, dbias, dres,
                dres_accumulate, T, G, ws=None):
     """ws: optional ZEROED float64 workspace of >= 2*B*G elements; passing it also declares dgamma / dbeta / dbias as
-    already zeroed by the caller (the engine zeroes its whole gradient arena once per step)."""
+    already zeroed by the caller (the engine zeroes its whole gradient arena once per step).
+    y / dout: fp32 or (GroupNorm layers) the 16-bit operand dtype.  GroupNorm layers OVERWRITE dout (with dz)."""
     C, B, Tp = y.shape
+    yd, dd = _dt(y), _dt(dout)
     res_is_f32 = int(res is not None and res.dtype == torch.float32)
     flags = int(bool(dres_accumulate))
     if ws is None:
@@ -221,8 +239,8 @@ def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, 
     else:
         flags |= 2
     dp, dn, dstr = _planes(dy)
-    _call("sg_gn_act_bwd", _p(_f32(y, "y")), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(res), res_is_f32, float(res_scale),
-          int(act), int(post_gelu), _p(_f32(dout, "dout")), dp, dn, dstr, _p(dgamma), _p(dbeta), _p(dbias), _p(dres),
+    _call("sg_gn_act_bwd", _p(y), yd, _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(res), res_is_f32, float(res_scale),
+          int(act), int(post_gelu), _p(dout), dd, dp, dn, dstr, _p(dgamma), _p(dbeta), _p(dbias), _p(dres),
           flags, _p(ws), C, B, T, Tp, int(G), _dt(dy), _stream())
 
 
@@ -320,7 +338,8 @@ class OptPlan:
         import ctypes
         self.items = items
         n_sn = sum(1 for it in items if it.get("u") is not None)
-        self.dots = torch.zeros(max(n_sn, 1), dtype=torch.float64, device=device)
+        # one <G, W> per spectral-norm item + 6 doubles of scratch (non-finite flag, device copy of the step's scalars)
+        self.dots = torch.zeros(n_sn + 6, dtype=torch.float64, device=device)
         arr = (_lib.OptItem * len(items))()
         d = 0
         for a, it in zip(arr, items):
@@ -341,11 +360,35 @@ class OptPlan:
         self.n = len(items)
 
 
-def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq):
+SCALER_FIELDS = ("scale", "growth", "backoff", "min_scale", "max_scale",          # float32
+                 "growth_interval", "good_steps", "step", "skipped", "last_skipped")  # int32
+
+
+def make_scaler_state(device, scale, growth=2.0, backoff=0.5, growth_interval=200, min_scale=2.0 ** -24, max_scale=2.0 ** 24):
+    """Device copy of sg_scaler_state (include/simulgen_b200.h) as an int32[10] tensor whose first five words hold
+    float32 bits.  `state[:1].view(torch.float32)` is the live loss scale."""
+    import struct
+    words = list(struct.unpack("5i", struct.pack("5f", float(scale), float(growth), float(backoff), float(min_scale),
+                                                 float(max_scale)))) + [int(growth_interval), 0, 0, 0, 0]
+    return torch.tensor(words, dtype=torch.int32, device=device)
+
+
+def read_scaler_state(state):
+    """Host copy as a dict (synchronises; logging and tests only)."""
+    host = state.detach().cpu()
+    f = host[:5].view(torch.float32).tolist()
+    return dict(zip(SCALER_FIELDS, f + host[5:].tolist()))
+
+
+def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, scaler=None):
+    """scaler: optional make_scaler_state() tensor - the dynamic loss scale of the fp16-operand mode; `step` is then
+    ignored (the applied-step counter lives in the state) and grad_scale excludes the loss scale."""
     import ctypes
+    if scaler is not None:
+        assert scaler.dtype == torch.int32 and scaler.numel() == len(SCALER_FIELDS)
     _call("sg_opt_step", plan.table.data_ptr(), ctypes.addressof(plan._host), plan.n, plan.dots.data_ptr(),
           plan.dots.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
-          float(grad_scale), _p(gnorm_sq), _stream())
+          float(grad_scale), _p(gnorm_sq), _p(scaler), _stream())
 
 
 class SnPlan:

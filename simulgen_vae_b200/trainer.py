@@ -50,7 +50,7 @@ def _gemm_layout_elems(mod):
 class Trainer:
     def __init__(self, model, lr=1e-3, alpha=1.0e6, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
                  process_group=None, bucket_mb=64, fused=True, materialize_xhat=False, loss_scale=None,
-                 broadcast_init=True):
+                 broadcast_init=True, growth_interval=200):
         self.model = model
         self.lr, self.alpha, self.betas, self.eps, self.wd = lr, alpha, betas, eps, weight_decay
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -68,10 +68,16 @@ class Trainer:
         self.fused = fused
         if self.world > 1 and broadcast_init:
             self._broadcast_replica()
-        # fp16 mode: gradients are stored as fp16 GEMM operands, so the loss is scaled by a power of two before backward
-        # and the optimiser divides it out again (everything in between is linear).  None = automatic: numel/alpha
-        # rounded to a power of two puts the reconstruction-loss gradient at O(1); bf16 / fp32 need none.
+        # fp16 mode: gradients are stored as fp16 GEMM operands, so the loss is multiplied by a power of two before
+        # backward and the optimiser divides it out again (everything in between is linear).
+        #   loss_scale=None (default): DYNAMIC, device-resident (kernels.make_scaler_state / sg_scaler_state): starts at
+        #     numel/alpha rounded to a power of two (reconstruction-loss gradient at O(1)); a step whose gradients
+        #     overflowed is skipped inside sg_opt_step and the scale halves, `growth_interval` clean steps double it -
+        #     no host synchronisation.  Fused path only (the per-tensor path keeps the static initial value).
+        #   loss_scale=<float>: static.            bf16 / fp32 modes: no scaling.
         self.loss_scale = loss_scale
+        self.growth_interval = growth_interval
+        self.scaler = None                             # created at the first fp16 step (needs numel of a batch)
         self.materialize_xhat = materialize_xhat      # the step only needs the losses; x_hat stays in registers
         self._last = None
         self.sink = None
@@ -195,12 +201,18 @@ class Trainer:
         engine.set_packed_input(packed)
         b1, b2 = self.betas
         S = self.loss_scale
+        scaler = None
         if S is None:
             S = 1.0
             if engine.get_precision() == "fp16":
                 import math
                 S = 2.0 ** max(-24, min(24, round(math.log2(x.numel() / max(self.alpha, 1e-30)))))
-        scale = 1.0 / (self.world * S)
+                if self.fused:
+                    if self.scaler is None:
+                        self.scaler = K.make_scaler_state(self.dev, S, growth_interval=self.growth_interval)
+                    scaler = self.scaler
+                    S = scaler[:1].view(torch.float32)      # live device scalar: loss * S without a host read
+        scale = 1.0 / self.world if scaler is not None else 1.0 / (self.world * S)
         self.gnorm_sq.zero_()
         self._works, self._launched = [], 0     # an exception that escaped a previous backward must not leak buckets
         if self.fused:
@@ -213,7 +225,7 @@ class Trainer:
                 for k in kls[1:]:
                     kl_sum = kl_sum + k
                 loss = recon * self.alpha + kl_sum * beta
-                (loss * S if S != 1.0 else loss).backward()
+                (loss * S if (scaler is not None or S != 1.0) else loss).backward()
             finally:
                 engine.set_grad_sink(None)
                 engine.set_materialize_xhat(True)
@@ -221,7 +233,7 @@ class Trainer:
             if self.plan is None:
                 self._build_plan()
             self.step_count += 1
-            K.opt_step(self.plan, self.lr, b1, b2, self.eps, self.wd, self.step_count, scale, self.gnorm_sq)
+            K.opt_step(self.plan, self.lr, b1, b2, self.eps, self.wd, self.step_count, scale, self.gnorm_sq, scaler)
         else:
             for p in self.params:
                 p.grad = None
@@ -241,6 +253,10 @@ class Trainer:
                 K.adamw_step(p.data, g, m, v, self.lr, b1, b2, self.eps, self.wd, self.step_count, scale, self.gnorm_sq)
         self._last = (loss.detach(), recon.detach(), kl_sum.detach(), mse.detach())
         return self._last
+
+    def scaler_state(self):
+        """Dynamic loss scaler as a dict (scale, applied steps, skipped steps, ...), or None; synchronises."""
+        return K.read_scaler_state(self.scaler) if self.scaler is not None else None
 
     def scalars(self):
         """(loss, recon, kl_sum, mse, grad_norm) as Python floats - the only host synchronisation."""

@@ -137,9 +137,13 @@ def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
     w = wg[:, :, :Cin].float().flip(0).permute(2, 1, 0).contiguous()          # [ci][co][j'] = wg[k-1-j'][co][ci]
     y = F.conv1d(g, w, None, padding=k // 2).permute(1, 0, 2).reshape(dx.shape)
     if accumulate:
-        dx.add_(y)
+        dx.copy_((dx.float() + y).to(dx.dtype))            # 16-bit dx: add in fp32, round once more
     else:
         dx.copy_(y)
+
+
+def conv_out16_ok(M):
+    return M > 128
 
 
 def conv_wgrad(dy, act, dwg, Cin):
@@ -167,7 +171,7 @@ def gn_stats(y, stats, T, G):
 def _gn_forward(y, gamma, beta, res, res_scale, act, post_gelu, T, G, use_gn):
     """y [C,B,Tp] fp32 (differentiable); returns pre/out on the valid region [C,B,T]."""
     C, B, Tp = y.shape
-    yv = y[:, :, :T]
+    yv = y[:, :, :T].float()
     if use_gn:
         g = yv.reshape(G, C // G, B, T)
         mean = g.mean(dim=(1, 3), keepdim=True)
@@ -196,13 +200,13 @@ def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, 
                dres_accumulate, T, G, ws=None):
     use_gn = stats is not None
     with torch.enable_grad():
-        yl = y.detach().clone().requires_grad_(True)
+        yl = y.detach().float().clone().requires_grad_(True)
         gl = gamma.detach().clone().requires_grad_(True) if use_gn else None
         bl = beta.detach().clone().requires_grad_(True) if use_gn else None
         rl = res.detach().float().clone().requires_grad_(True) if res is not None else None
         o = _gn_forward(yl, gl, bl, rl, res_scale, act, post_gelu, T, G, use_gn)
         leaves = [t for t in (yl, gl, bl, rl) if t is not None]
-        grads = torch.autograd.grad(o, leaves, dout[:, :, :T], allow_unused=True)
+        grads = torch.autograd.grad(o, leaves, dout[:, :, :T].float(), allow_unused=True)
     gmap = dict(zip([id(t) for t in leaves], grads))
     gy = gmap[id(yl)]
     gy = gy.clone()
@@ -220,6 +224,8 @@ def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, 
         else:
             dres.zero_()
             dres[:, :, :T] = gr[:, :, :T]
+    if use_gn:
+        dout.fill_(float("nan"))       # the CUDA path overwrites dout (with dz): nothing may read it afterwards
 
 
 def _loss_terms(kind, d):
@@ -473,7 +479,27 @@ class OptPlan:
         self.n = len(items)
 
 
-def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq):
+def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, scaler=None):
+    if scaler is not None:
+        # sg_scaler_state semantics (csrc/optim.cu opt_prologue_kernel)
+        fl = scaler[:5].view(torch.float32)
+        used = float(fl[0])
+        grad_scale = grad_scale / used
+        bad = any(not bool(torch.isfinite(it["g"]).all()) for it in plan.items)
+        if bad:
+            fl[0] = max(used * float(fl[2]), float(fl[3]))
+            scaler[6] = 0
+            scaler[8] += 1
+            scaler[9] = 1
+            gnorm_sq.fill_(float("inf"))
+            return
+        scaler[7] += 1
+        scaler[9] = 0
+        scaler[6] += 1
+        if int(scaler[6]) >= int(scaler[5]):
+            fl[0] = min(used * float(fl[1]), float(fl[4]))
+            scaler[6] = 0
+        step = int(scaler[7])
     for it in plan.items:
         p = it["p"]
         if it.get("u") is not None:
@@ -502,7 +528,7 @@ def sn_prepare(plan, training):
             sn_pack_weight(L["w"], L["sigma"], L["wg"], L["H"], L["Cin"], L["Cin_p"], L["k"], L["so"], L["si"], L["flip"])
 
 
-NAMES = ["OptPlan", "opt_step", "SnPlan", "sn_prepare", "assemble_batch", "minmax_fit", "minmax_transform", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
+NAMES = ["conv_out16_ok", "OptPlan", "opt_step", "SnPlan", "sn_prepare", "assemble_batch", "minmax_fit", "minmax_transform", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
          "conv_fprop", "conv_fprop_gn", "conv_dgrad", "conv_wgrad", "gn_stats", "gn_act_fwd", "gn_act_bwd", "recon_fwd", "recon_bwd",
          "head_fwd", "head_bwd", "latent_fwd", "latent_bwd", "reparam_main_fwd", "reparam_main_bwd", "kl2_reparam_fwd",
          "kl2_reparam_bwd", "philox_normal", "adamw_step"]

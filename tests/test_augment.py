@@ -100,7 +100,7 @@ def test_trainer_step_with_packed_operand_equals_plain_step():
     from conftest import load_golden, rel_l2
     g = load_golden("toy3_small_mse")
     cfg = g["cfg"]
-    sg.set_precision("bf16")
+    sg.set_precision(sg.DEFAULT_PRECISION)
     data = torch.cat([g["x"], g["x"] * 0.8, g["x"] * 1.1]).numpy()
     res = []
     for packed in (False, True):

@@ -74,7 +74,7 @@ def test_standalone_block_wiring_cpu(cls_name, where, args, cin):
         with emu.install():
             _check(cls_name, where, args, cin, "cpu", 1e-5, 1e-4)
     finally:
-        sg.set_precision("bf16")
+        sg.set_precision(sg.DEFAULT_PRECISION)
 
 
 @pytest.mark.gpu
@@ -85,4 +85,4 @@ def test_standalone_block_gpu(cls_name, where, args, cin, precision, tol_out, to
     try:
         _check(cls_name, where, args, cin, "cuda", tol_out, tol_grad)
     finally:
-        sg.set_precision("bf16")
+        sg.set_precision(sg.DEFAULT_PRECISION)

@@ -73,7 +73,7 @@ def test_decoder_modes_and_freeze_level_cpu(monkeypatch):
         with emu.install():
             _run("cpu", monkeypatch)
     finally:
-        sg.set_precision("bf16")
+        sg.set_precision(sg.DEFAULT_PRECISION)
 
 
 @pytest.mark.gpu
@@ -82,4 +82,4 @@ def test_decoder_modes_and_freeze_level_gpu(monkeypatch):
     try:
         _run("cuda", monkeypatch)
     finally:
-        sg.set_precision("bf16")
+        sg.set_precision(sg.DEFAULT_PRECISION)

@@ -60,7 +60,7 @@ def test_reference_train_runs_on_the_overlay(tmp_path, monkeypatch):
         whole = torch.load("model_save/SimulGen-VAE", weights_only=False)
         assert type(whole).__module__ == "modules.VAE_network" and type(whole).__name__ == "VAE"
     finally:
-        sg.set_precision("bf16")
+        sg.set_precision(sg.DEFAULT_PRECISION)
         if ref_import.REFERENCE_ROOT in sys.path:
             sys.path.remove(ref_import.REFERENCE_ROOT)
         _purge_modules()
@@ -111,7 +111,7 @@ def test_engine_train_driver_matches_the_reference_driver(tmp_path, monkeypatch)
         ref_curves, ref_sd = run(False)
         eng_curves, eng_sd = run(True)
     finally:
-        sg.set_precision("bf16")
+        sg.set_precision(sg.DEFAULT_PRECISION)
     for name, a, b in zip(("loss", "recon", "kl", "val_loss"), ref_curves, eng_curves):
         assert a.shape == b.shape == (5,)
         assert np.allclose(a, b, rtol=2e-4, atol=1e-6), (name, a, b)

@@ -70,7 +70,7 @@ def test_batched_export_matches_reference_sweep(batch_size, tmp_path, monkeypatc
         assert txt.shape == (9,) and np.allclose(txt, rloss, rtol=1e-6)
         assert np.allclose(lat, ref[0], rtol=1e-4, atol=1e-6) and np.allclose(hier, ref[1], rtol=1e-4, atol=1e-6)
     finally:
-        sg.set_precision("bf16")
+        sg.set_precision(sg.DEFAULT_PRECISION)
         sg.install_overlay(train=False)
         if ref_import.REFERENCE_ROOT in sys.path:
             sys.path.remove(ref_import.REFERENCE_ROOT)

@@ -82,6 +82,32 @@ def test_tc_dgrad(shape):
     assert rel_l2(d1[:, :, :T], d2[:, :, :T]) < 1e-4, rel_l2(d1[:, :, :T], d2[:, :, :T])
 
 
+@pytest.mark.parametrize("shape", [s for s in SHAPES if s[0] > 128] + [(2560, 512, 1, 3, 200), (1280, 1280, 5, 1, 8)])
+@pytest.mark.parametrize("half", [False, True])
+def test_tc_dgrad_16bit_output(shape, half):
+    """dgrad with the gradient stored in the 16-bit operand format by the CTA-pair epilogue (activations whose only
+    consumer is this conv), plain and accumulating onto a 16-bit buffer, for bf16 and fp16 operands."""
+    Cin, Cout, k, B, T = shape
+    assert K.conv_out16_ok(Cin)
+    wg, act, dy, bias, Tp, Cin_p = make(*shape)
+    dt = torch.float16 if half else BF
+    if half:
+        wg, dy = wg.float().half(), dy.float().half()
+    ref = torch.empty(Cin, B, Tp, device=DEV)
+    emu.conv_dgrad(wg, dy, ref, Cin)
+    d1 = torch.full((Cin, B, Tp), 5.0, device=DEV, dtype=dt)
+    K.conv_dgrad(wg, dy, d1, Cin)
+    torch.cuda.synchronize()
+    tol = 6e-4 if half else 4e-3
+    assert rel_l2(d1[:, :, :T].float(), ref[:, :, :T]) < tol, rel_l2(d1[:, :, :T].float(), ref[:, :, :T])
+    d2 = d1.clone()
+    K.conv_dgrad(wg, dy, d1, Cin, accumulate=True)
+    emu.conv_dgrad(wg, dy, d2, Cin, accumulate=True)
+    torch.cuda.synchronize()
+    assert rel_l2(d1[:, :, :T].float(), d2[:, :, :T].float()) < tol, rel_l2(d1[:, :, :T].float(), d2[:, :, :T].float())
+    assert rel_l2(d1[:, :, :T].float(), 2 * ref[:, :, :T]) < tol * 1.5
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 def test_tc_wgrad(shape):
     Cin, Cout, k, B, T = shape

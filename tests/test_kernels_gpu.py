@@ -151,20 +151,27 @@ CASES = [
 
 
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32, torch.float16])
-@pytest.mark.parametrize("P,T", [(1, 21), (3, 21), (5, 21), (3, 300), (5, 200)])
-def test_gn_act_fwd_bwd(case, dtype, P, T):
+@pytest.mark.parametrize("dtype,y16,d16", [(torch.bfloat16, False, False), (torch.float32, False, False),
+                                           (torch.float16, False, False), (torch.float16, True, True),
+                                           (torch.float16, True, False), (torch.bfloat16, False, True)])
+@pytest.mark.parametrize("P,T", [(1, 21), (3, 21), (5, 21), (3, 300), (5, 200), (1, 200)])
+def test_gn_act_fwd_bwd(case, dtype, y16, d16, P, T):
     """T=21 / 200: rows of <= 256 elements (one segment per lane, shifted planes by warp shuffle);
-    T=300: longer rows (several segments per lane, planes staged through shared memory)."""
+    T=300: longer rows (several segments per lane, planes staged through shared memory).
+    y16 / d16: the pre-norm conv output / the incoming gradient stored in the 16-bit operand format (GroupNorm layers)."""
     use_gn, act, res_kind, res_scale, post = case
-    C, B, G = 48, 3, 8
+    if (y16 or d16) and not use_gn:
+        pytest.skip("16-bit y / dout exist for GroupNorm layers only")
+    C, B, G = 48, 19, 8                         # 19 samples: two (channel, 16-sample chunk) tasks, the second ragged
     Tp = tp_of(T)
     y = cr(C, B, T, seed=1) * 1.5 + 0.3
+    if y16:
+        y = y.to(dtype)
     gamma, beta = rnd(C, seed=2) * 0.5 + 1.0, rnd(C, seed=3) * 0.2
     stats = None
     if use_gn:
         stats = torch.empty(B, G, 2, device=DEV)
-        K.gn_stats(y, stats, T, G)
+        K.gn_stats(y.float(), stats, T, G)
     res = None
     if res_kind == "f32":
         res = cr(C, B, T, seed=4)
@@ -180,23 +187,28 @@ def test_gn_act_fwd_bwd(case, dtype, P, T):
     tol16 = {torch.float32: 2e-6, torch.bfloat16: 4e-3, torch.float16: 5e-4}[dtype]
     close(o1.float(), o2.float(), tol16, "fwd op")
     assert float(o1[:, :, :, T:].float().abs().max()) == 0.0
-    # backward
+    # backward (GroupNorm layers overwrite dout: each side gets its own copy)
     dout = cr(C, B, T, seed=5)
+    if d16:
+        dout = dout.to(dtype)
+    dout_k = dout.clone()
     dy1 = torch.full((P, C, B, Tp), 9.0, device=DEV, dtype=dtype)
     dy2 = torch.empty_like(dy1)
     dg1, db1, dbi1 = (torch.empty(C, device=DEV) for _ in range(3))
     dg2, db2, dbi2 = (torch.empty(C, device=DEV) for _ in range(3))
     dr1 = cr(C, B, T, seed=6) if res is not None else None
     dr2 = dr1.clone() if dr1 is not None else None
-    K.gn_act_bwd(y, stats, gamma if use_gn else None, beta if use_gn else None, res, res_scale, act, post, dout, dy1,
+    K.gn_act_bwd(y, stats, gamma if use_gn else None, beta if use_gn else None, res, res_scale, act, post, dout_k, dy1,
                  dg1 if use_gn else None, db1 if use_gn else None, dbi1, dr1, 1, T, GG)
     emu.gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post, dout, dy2, dg2, db2, dbi2, dr2, 1, T, G)
     tol = {torch.float32: 2e-5, torch.bfloat16: 5e-3, torch.float16: 6e-4}[dtype]
+    if d16:
+        tol *= 1.5                               # dz makes one more 16-bit round trip between the two passes
     close(dy1.float(), dy2.float(), tol, "dy")
     close(dbi1, dbi2, tol * 2, "dbias")
     if use_gn:
-        close(dg1, dg2, 2e-5, "dgamma")
-        close(db1, db2, 2e-5, "dbeta")
+        close(dg1, dg2, 3e-5, "dgamma")
+        close(db1, db2, 3e-5, "dbeta")
     if res is not None:
         close(dr1[:, :, :T], dr2[:, :, :T], 2e-5, "dres")
     assert float(dy1[:, :, :, T:].float().abs().max()) == 0.0
@@ -413,6 +425,52 @@ def test_opt_step_multi_tensor_matches_model():
         close(ia["m"], ib["m"], 2e-5, "m %s" % (sp,))
         close(ia["v"], ib["v"], 2e-5, "v %s" % (sp,))
     assert abs(float(ga) - float(gb)) / float(gb) < 1e-5
+
+
+@pytest.mark.parametrize("where", ["weight", "vector"])
+def test_opt_step_dynamic_loss_scaler_skips_overflowed_steps(where):
+    """sg_scaler_state: clean steps divide the loss scale out and count; a step with a non-finite gradient (in a
+    spectral-norm weight gradient or in a plain vector) leaves p / m / v / step untouched, halves the scale and reports
+    an infinite gradient norm; `growth_interval` clean steps double the scale.  Kernel against the torch model."""
+    def make():
+        p1, p2 = rnd(24, 20, 3, seed=1), rnd(4099, seed=2)
+        return [dict(p=p1, g=rnd(3, 24, 24, seed=3) * 64.0, m=torch.zeros_like(p1), v=torch.zeros_like(p1),
+                     u=torch.nn.functional.normalize(rnd(24, seed=4), dim=0),
+                     vv=torch.nn.functional.normalize(rnd(60, seed=5), dim=0), sigma=torch.tensor([1.7], device=DEV),
+                     Cout=24, Cin=20, Cin_p=24, k=3, flip=0),
+                dict(p=p2, g=rnd(4099, seed=6) * 64.0, m=torch.zeros_like(p2), v=torch.zeros_like(p2))]
+    a_items, b_items = make(), make()
+    pa, pb = K.OptPlan(a_items, DEV), emu.OptPlan(b_items, DEV)
+    sa = K.make_scaler_state(DEV, 64.0, growth_interval=2)
+    sb = K.make_scaler_state(DEV, 64.0, growth_interval=2)
+    ga, gb = (torch.zeros(1, device=DEV, dtype=torch.float64) for _ in range(2))
+    bad_item = 0 if where == "weight" else 1
+    for it in range(5):
+        if it == 1:                                          # overflow in this step's gradients
+            for items in (a_items, b_items):
+                items[bad_item]["g"].view(-1)[17] = float("inf") if where == "weight" else float("nan")
+        if it == 2:
+            for items in (a_items, b_items):
+                items[bad_item]["g"].view(-1)[17] = 1.0
+        before = [x["p"].clone() for x in a_items]
+        ga.zero_(); gb.zero_()
+        K.opt_step(pa, 1e-3, 0.9, 0.999, 1e-8, 0.01, 0, 1.0, ga, sa)
+        emu.opt_step(pb, 1e-3, 0.9, 0.999, 1e-8, 0.01, 0, 1.0, gb, sb)
+        st = K.read_scaler_state(sa)
+        assert st == K.read_scaler_state(sb), (it, st, K.read_scaler_state(sb))
+        if it == 1:
+            assert st["last_skipped"] == 1 and st["skipped"] == 1 and st["step"] == 1 and st["scale"] == 32.0
+            assert float(ga) == float("inf")
+            for x, b in zip(a_items, before):
+                assert torch.equal(x["p"], b)
+        else:
+            assert abs(float(ga) - float(gb)) / float(gb) < 1e-5
+    st = K.read_scaler_state(sa)
+    assert st["step"] == 4 and st["skipped"] == 1 and st["scale"] == 64.0     # 64 -> 32 (skipped step) -> 64 (two clean steps in a row)
+    for ia, ib in zip(a_items, b_items):
+        close(ia["p"], ib["p"], 2e-6, "p")
+        close(ia["m"], ib["m"], 2e-5, "m")
+        close(ia["v"], ib["v"], 2e-5, "v")
 
 
 @pytest.mark.parametrize("training", [True, False])

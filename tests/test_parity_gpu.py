@@ -33,7 +33,7 @@ def build_engine_vae(cfg, state_dict=None, seed=0):
 @pytest.fixture(autouse=True)
 def _restore_precision():
     yield
-    sg.set_precision("bf16")
+    sg.set_precision(sg.DEFAULT_PRECISION)
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -76,7 +76,7 @@ def test_bf16_mode_close_to_reference_golden(name):
     realistic-size bound is test_bf16_per_layer_parity_medium."""
     g = load_golden(name)
     cfg = g["cfg"]
-    sg.set_precision("bf16")
+    sg.set_precision(sg.DEFAULT_PRECISION)
     m = build_engine_vae(cfg, g["state_dict"])
     m.train(True)
     with sg.fixed_eps(g["eps"]):
@@ -340,7 +340,7 @@ def test_engine_train_driver_on_gpu(precision, tmp_path, monkeypatch):
         loss, recon, kl, val = train_loop.train(8, 8, train_dl, val_dl, 2e-3, cfg["enc"], cfg["enc"][::-1], cfg["num_node"],
                                                 cfg["latent_dim"], cfg["hierarchical_dim"], cfg["num_time"], 1000000, "MSE", True, True)
     finally:
-        sg.set_precision("bf16")
+        sg.set_precision(sg.DEFAULT_PRECISION)
     assert all(np.isfinite(c).all() and len(c) == 8 for c in (loss, recon, kl, val))
     assert recon[-1] < 0.7 * recon[0], (recon[0], recon[-1])
     assert val[0] > 0 and val[-1] > 0 and val[1] == val[0]            # validated at epoch 0 and the last one, carried between
@@ -380,4 +380,4 @@ def test_batched_export_is_batch_size_independent_on_gpu(tmp_path, monkeypatch):
         assert np.abs(lat).max() > 0 and len(np.unique(lat.round(6), axis=0)) == 11          # every row filled, all distinct
         assert (outs[0][2] > 0).all()
     finally:
-        sg.set_precision("bf16")
+        sg.set_precision(sg.DEFAULT_PRECISION)

@@ -54,13 +54,59 @@ def test_trainer_matches_torch_adamw(name, fused):
                 n_live = sum(1 for v in g["grads"].values() if v is not None)
                 assert tr.plan.n == n_live
     finally:
-        sg.set_precision("bf16")
+        sg.set_precision(sg.DEFAULT_PRECISION)
     for a, b in zip(losses, ref_losses):
         assert abs(a - b) / abs(b) < 1e-5
     rsd, sd = ref.state_dict(), m.state_dict()
     for k in rsd:
         assert rel_l2(sd[k], rsd[k]) < 2e-5, k
     assert tr.scalars()[4] > 0
+
+
+def test_fp16_dynamic_loss_scale_equals_static_and_skips_overflow():
+    """fp16 mode: the device-resident dynamic scaler (default) gives the weights of a static power-of-two scale while no
+    overflow occurs; a forced overflow (absurd scale) skips the step - weights, moments and the applied-step counter
+    unchanged - and halves the scale; training then continues."""
+    from simulgen_vae_b200.trainer import Trainer
+    g = load_golden("toy3_small_mse")
+    sg.set_precision("fp16")
+    try:
+        with emu.install():
+            def run(**kw):
+                m = build_engine_vae(g["cfg"], g["state_dict"])
+                m.train(True)
+                tr = Trainer(m, lr=1e-3, alpha=g["alpha"], **kw)
+                for i in range(3):
+                    with sg.fixed_eps(g["eps"]):
+                        tr.step(g["x"], beta=g["beta"])
+                return m, tr
+            m_dyn, tr_dyn = run()
+            st = tr_dyn.scaler_state()
+            assert st["step"] == 3 and st["skipped"] == 0 and st["good_steps"] == 3
+            m_static, tr_static = run(loss_scale=st["scale"])
+            assert tr_static.scaler is None
+            sd_a, sd_b = m_dyn.state_dict(), m_static.state_dict()
+            for k in sd_a:
+                assert torch.equal(sd_a[k], sd_b[k]), k
+            # overflow: fp16 gradients cannot hold a loss scaled by 2^60
+            before = {k: v.clone() for k, v in sd_a.items() if not k.endswith(("weight_u", "weight_v"))}
+            tr_dyn.scaler[:1].view(torch.float32).fill_(2.0 ** 60)
+            with sg.fixed_eps(g["eps"]):
+                tr_dyn.step(g["x"], beta=g["beta"])
+            st2 = tr_dyn.scaler_state()
+            assert st2["last_skipped"] == 1 and st2["skipped"] == 1 and st2["step"] == 3 and st2["scale"] == 2.0 ** 59
+            assert tr_dyn.scalars()[4] == float("inf")
+            after = m_dyn.state_dict()
+            for k, v in before.items():
+                assert torch.equal(after[k], v), k
+            tr_dyn.scaler[:1].view(torch.float32).fill_(st["scale"])
+            with sg.fixed_eps(g["eps"]):
+                tr_dyn.step(g["x"], beta=g["beta"])
+            st3 = tr_dyn.scaler_state()
+            assert st3["last_skipped"] == 0 and st3["step"] == 4
+            assert any(not torch.equal(m_dyn.state_dict()[k], v) for k, v in before.items())
+    finally:
+        sg.set_precision(sg.DEFAULT_PRECISION)
 
 
 def _free_port():
@@ -115,7 +161,7 @@ def test_data_parallel_world2_equals_single_process(tmp_path, fused):
                 with sg.fixed_eps(g["eps"]):
                     tr.step(g["x"], beta=g["beta"])
     finally:
-        sg.set_precision("bf16")
+        sg.set_precision(sg.DEFAULT_PRECISION)
     sd = m.state_dict()
     for k in sd:
         assert rel_l2(dp[k], sd[k]) < 5e-5, (k, rel_l2(dp[k], sd[k]))

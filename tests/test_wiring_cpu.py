@@ -38,7 +38,7 @@ def test_engine_wiring_matches_golden(name, precision):
             loss = rl * g["alpha"] + sum(kls) * g["beta"]
             loss.backward()
     finally:
-        sg.set_precision("bf16")
+        sg.set_precision(sg.DEFAULT_PRECISION)
     tol = {"fp32": 3e-5, "bf16": 3e-2, "fp16": 5e-3}[precision]
     assert rel_l2(x_hat, g["ref"]["x_hat"]) < tol
     assert rel_l2(rl, g["ref"]["recon"]) < tol
@@ -62,6 +62,56 @@ def test_engine_wiring_matches_golden(name, precision):
     for k, v in g["uv_after"].items():
         assert rel_l2(sd[k], v) < 1e-5, k
     print(name, precision, "worst grad rel-L2", worst)
+
+
+@pytest.mark.parametrize("precision,store16", [("fp16", "1"), ("bf16", "1"), ("fp16", "0")])
+def test_16bit_intermediates_wiring_against_oracle(precision, store16, monkeypatch):
+    """Host wiring of the 16-bit storage policy (engine.store16): 16-bit pre-norm conv outputs for layers wider than 128
+    channels and 16-bit activation gradients for the interior activations of a conv-GN-GELU sequence wider than 256
+    channels (here the 5x64 = 320-channel hidden layers of the decoder residual blocks), against the fp32 oracle."""
+    from simulgen_vae_b200 import engine
+    from oracle import vae_oracle as O
+    cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[64, 32], num_node=96, num_time=16, small=True, lossfun="MSE", batch=2)
+    monkeypatch.setattr(engine, "_STORE16", store16)
+    sg.set_precision(precision)
+    seen = {"y16": 0, "g16": 0}
+    try:
+        with emu.install():
+            from simulgen_vae_b200 import kernels as K
+            orig_bwd, orig_dgrad = K.gn_act_bwd, K.conv_dgrad
+
+            def bwd(y, stats, gamma, beta, res, rs, act, post, dout, *a, **k):
+                seen["y16"] += int(y.dtype != torch.float32)
+                seen["g16"] += int(dout.dtype != torch.float32)
+                return orig_bwd(y, stats, gamma, beta, res, rs, act, post, dout, *a, **k)
+
+            def dgrad(wg, dy, dx, Cin, accumulate=False):
+                assert dx.dtype == torch.float32 or (Cin > 256 and not accumulate)
+                return orig_dgrad(wg, dy, dx, Cin, accumulate)
+            K.gn_act_bwd, K.conv_dgrad = bwd, dgrad
+            torch.manual_seed(11)
+            m = build_engine_vae(cfg, None)
+            m.train(True)
+            sd = {k: v.clone() for k, v in m.state_dict().items()}
+            g = torch.Generator().manual_seed(12)
+            x = torch.rand(2, 96, 16, generator=g) * 1.4 - 0.7
+            eps = [torch.randn(s, generator=g) for s in O.eps_shapes(cfg, 2)]
+            with sg.fixed_eps(eps):
+                x_hat, rl, kls, mse = m(x)
+            (rl * 1e3 + sum(kls) * 1e-2).backward()
+    finally:
+        sg.set_precision(sg.DEFAULT_PRECISION)
+    if store16 == "1":
+        assert seen == {"y16": 2, "g16": 2}, seen       # the two 320-channel layers of the one DecoderResidualBlock
+    else:
+        assert seen == {"y16": 0, "g16": 0}
+    p = O.params_from_state_dict(sd)
+    ox, orl, okls, omse = O.vae_forward(p, x, eps, cfg["latent_dim"], cfg["lossfun"], training=True)
+    (orl * 1e3 + sum(okls) * 1e-2).backward()
+    tol = {"fp16": 1e-2, "bf16": 8e-2}[precision]
+    assert rel_l2(x_hat, ox) < tol
+    worst = max(rel_l2(q.grad, p[n].grad) for n, q in m.named_parameters() if q.grad is not None)
+    assert worst < tol, worst
 
 
 def test_state_dict_layout_matches_reference_default_preset():
