@@ -132,15 +132,17 @@ int sg_gn_act_bwd(const void* y, int y_dtype, const float* stats, const float* g
  * sum of the selected loss terms and sum of squared errors. */
 /* rowsums (optional, fp32 [N*B][4], 16-byte aligned; needs x): per-(n,b)-row partial sums of the GroupNorm
  * backward reductions, taken while y and x are in registers anyway; sg_recon_bwd then needs one pass. */
-int sg_recon_fwd(const void* y, int y_dtype, const float* stats, const float* gamma, const float* beta, const float* x,
-                 float* x_hat, double* loss_sums, float* rowsums, int N, int B, int T, int Tp, int G, int loss_kind,
-                 void* stream);
+/* x / x_dtype: the target, either fp32 [B][N][T] (SG_F32, the reference's layout) or the packed 16-bit operand of the
+ * first encoder conv [N][B][Tp] (x_dtype = the operand format; T % 8 == 0, 16-bit y): the values the encoder consumed. */
+int sg_recon_fwd(const void* y, int y_dtype, const float* stats, const float* gamma, const float* beta, const void* x,
+                 int x_dtype, float* x_hat, double* loss_sums, float* rowsums, int N, int B, int T, int Tp, int G,
+                 int loss_kind, void* stream);
 /* dx_hat = g_loss[0]*inv_numel*loss'(x_hat-x) + g_mse[0]*inv_numel*2(x_hat-x) + dxhat_ext (each optional),
  * then backward through tanh and GroupNorm -> dy (dtype, 1 plane), dgamma, dbeta, dbias.
  * rowsums: the buffer sg_recon_fwd filled (or NULL: two passes; also used when dxhat_ext != NULL).
  * ws: >= 2*B*G + 2 doubles. */
-int sg_recon_bwd(const void* y, int y_dtype, const float* stats, const float* gamma, const float* beta, const float* x,
-                 const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext,
+int sg_recon_bwd(const void* y, int y_dtype, const float* stats, const float* gamma, const float* beta, const void* x,
+                 int x_dtype, const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext,
                  const float* rowsums, void* dy, float* dgamma, float* dbeta, float* dbias, double* ws,
                  int N, int B, int T, int Tp, int G, int loss_kind, int dtype, void* stream);
 /* out[i] = (float)(in[i] * scale), n small. */

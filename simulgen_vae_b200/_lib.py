@@ -36,8 +36,8 @@ SIGNATURES = {
     "sg_gn_stats": [P, P, P, I, I, I, I, I, P],
     "sg_gn_act_fwd": [P, I, P, P, P, P, I, F, I, I, P, I, L, P, I, I, I, I, I, I, P],
     "sg_gn_act_bwd": [P, I, P, P, P, P, I, F, I, I, P, I, P, I, L, P, P, P, P, I, P, I, I, I, I, I, I, P],
-    "sg_recon_fwd": [P, I, P, P, P, P, P, P, P, I, I, I, I, I, I, P],
-    "sg_recon_bwd": [P, I, P, P, P, P, P, P, F, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
+    "sg_recon_fwd": [P, I, P, P, P, P, I, P, P, P, I, I, I, I, I, I, P],
+    "sg_recon_bwd": [P, I, P, P, P, P, I, P, P, F, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "sg_scale_f64_to_f32": [P, P, D, I, P],
     "sg_head_fwd": [P, P, P, P, P, I, I, I, I, I, P],
     "sg_head_bwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, P],

@@ -74,13 +74,20 @@ class B200AugmentedLoader:
     """Iterable with the DataLoader surface train.py uses (`for image in loader`, `len(loader)`): yields fp32
     [B, N, T] CUDA batches assembled by sg_assemble_batch from the GPU-resident dataset."""
 
-    def __init__(self, data, indices, batch_size, shuffle, augment, seed=0):
+    def __init__(self, data, indices, batch_size, shuffle, augment, seed=0, rank=0, world=1, group=None):
+        """batch_size is the PER-RANK batch (SimulGen-VAE.py:172 already divides Batch_size by the world size).  world > 1:
+        every global batch of batch_size * world samples is split rank-major - rank r assembles positions
+        [r * batch_size, (r + 1) * batch_size) of it - from ONE sampling order and ONE set of augmentation decisions
+        (rank 0 draws them once per epoch, exactly as a single process would, and broadcasts them), so data-parallel
+        training sees the batches of the single-process run at the global batch size.  The reference has no sampler at
+        all: each rank would draw its own shuffle of the whole dataset (augmentation.py:182-187,226-232)."""
         self.data = data                                  # [P, N, T] fp32 CUDA, contiguous
         self.indices = torch.as_tensor(indices, dtype=torch.int64)
         self.batch_size, self.shuffle, self.augment = batch_size, shuffle, augment
+        self.rank, self.world, self.group = int(rank), int(world), group
         self.dataset_len = data.shape[0]
         self._index_loader = DataLoader(Subset(_IndexDataset(self.dataset_len), self.indices.tolist()),
-                                        batch_size=batch_size, shuffle=shuffle, num_workers=0)
+                                        batch_size=batch_size * self.world, shuffle=shuffle, num_workers=0)
         self.seed, self.draws = seed, 0
         self.injected_noise = None                        # tests: callable(batch_position, shape) -> noise tensor
         self.last_decisions = None
@@ -88,18 +95,56 @@ class B200AugmentedLoader:
         self.last_operand = None
 
     def __len__(self):
-        return len(self._index_loader)
+        n = len(self._index_loader)
+        if self.world > 1 and len(self.indices) % (self.batch_size * self.world) % self.world:
+            n -= 1                                        # a ragged last global batch that cannot be split evenly is dropped
+        return n
+
+    def _decide(self, idx):
+        B = len(idx)
+        if self.augment:
+            return draw_decisions(idx, self.dataset_len)
+        return (np.zeros(B, np.float32), np.ones(B, np.float32), np.full(B, -1, np.int64), np.ones(B, np.float32),
+                np.zeros(B, np.float32))
+
+    def _global_batches(self):
+        """(indices, decisions) of this rank's share of every global batch of the epoch."""
+        if self.world == 1:
+            for idx in self._index_loader:
+                idx = idx.reshape(-1)
+                yield idx, self._decide(idx.tolist())
+            return
+        dist = torch.distributed
+        n, W = len(self.indices), self.world
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        on_dev = dist.get_backend(self.group) == "nccl"
+        plan = torch.zeros(6, n, dtype=torch.float64)
+        if self.rank == 0:
+            # the whole epoch at once, in the order a single process would draw it batch by batch
+            order = torch.cat([idx.reshape(-1) for idx in self._index_loader])
+            cols = [self._decide(order[i:i + self.batch_size * W].tolist()) for i in range(0, n, self.batch_size * W)]
+            dec = [np.concatenate([c[j] for c in cols]) for j in range(5)]
+            plan = torch.from_numpy(np.stack([order.numpy().astype(np.float64)] + [d.astype(np.float64) for d in dec]))
+        if on_dev:
+            plan = plan.to(self.data.device)
+        dist.broadcast(plan, src=src, group=self.group)
+        plan = plan.cpu()
+        Bg = self.batch_size * W
+        for g0 in range(0, n, Bg):
+            m = min(Bg, n - g0)
+            if m % W:
+                break                                     # ragged tail that cannot be split evenly
+            per = m // W
+            sl = slice(g0 + self.rank * per, g0 + (self.rank + 1) * per)
+            idx = plan[0, sl].to(torch.int64)
+            yield idx, (plan[1, sl].numpy().astype(np.float32), plan[2, sl].numpy().astype(np.float32),
+                        plan[3, sl].numpy().astype(np.int64), plan[4, sl].numpy().astype(np.float32),
+                        plan[5, sl].numpy().astype(np.float32))
 
     def __iter__(self):
         dev = self.data.device
-        for idx in self._index_loader:
-            idx = idx.reshape(-1)
+        for idx, (noise, scale, other, lam, om) in self._global_batches():
             B = idx.numel()
-            if self.augment:
-                noise, scale, other, lam, om = draw_decisions(idx.tolist(), self.dataset_len)
-            else:
-                noise, scale = np.zeros(B, np.float32), np.ones(B, np.float32)
-                other, lam, om = np.full(B, -1, np.int64), np.ones(B, np.float32), np.zeros(B, np.float32)
             self.last_decisions = dict(index=idx.clone(), noise=noise, scale=scale, other=other, lam=lam)
             table = torch.from_numpy(np.stack([noise, scale, lam, om]).astype(np.float32)).to(dev, non_blocking=True)
             ids = torch.stack([idx, torch.from_numpy(other)]).to(torch.int32).to(dev, non_blocking=True)
@@ -120,17 +165,36 @@ class B200AugmentedLoader:
 
 
 def create_augmented_dataloaders(x_data, batch_size, load_all=False, augmentation_config=None, val_split=0.2,
-                                 num_workers=None, device=None):
+                                 num_workers=None, device=None, process_group=None):
     """Same signature and split semantics as the reference (augmentation.py:151-241): an 80/20 split by
     torch.randperm, shuffled augmented training batches, ordered plain validation batches.  The dataset is moved
-    to the GPU once (the reference does the same for load_all=True, utils.py:41-43)."""
-    dev = torch.device(device) if device is not None else torch.device("cuda")
+    to the GPU once (the reference does the same for load_all=True, utils.py:41-43).
+
+    Under torch.distributed (SimulGen-VAE.py --use_ddp; `batch_size` is then already the per-rank share,
+    SimulGen-VAE.py:168-174) the split is rank 0's, broadcast to every rank, and both loaders hand rank r its
+    disjoint 1/W slice of every global batch (see B200AugmentedLoader)."""
+    dist = torch.distributed
+    ddp = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(process_group) if ddp else 0
+    world = dist.get_world_size(process_group) if ddp else 1
+    if device is None:
+        import os
+        device = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0")) if ddp else "cuda"
+    dev = torch.device(device)
     data = torch.as_tensor(x_data, dtype=torch.float32).to(dev).contiguous()
     n = data.shape[0]
     val_size = int(n * val_split)
     train_size = n - val_size
     perm = torch.randperm(n)
+    if world > 1:
+        src = dist.get_global_rank(process_group, 0) if process_group is not None else 0
+        on_dev = dist.get_backend(process_group) == "nccl"
+        perm = perm.to(dev) if on_dev else perm
+        dist.broadcast(perm, src=src, group=process_group)
+        perm = perm.cpu()
     train_idx, val_idx = perm[:train_size], perm[train_size:]
-    train = B200AugmentedLoader(data, train_idx, batch_size, shuffle=True, augment=True)
-    val = B200AugmentedLoader(data, val_idx, batch_size, shuffle=False, augment=False)
+    train = B200AugmentedLoader(data, train_idx, batch_size, shuffle=True, augment=True, rank=rank, world=world,
+                                group=process_group)
+    val = B200AugmentedLoader(data, val_idx, batch_size, shuffle=False, augment=False, rank=rank, world=world,
+                              group=process_group)
     return train, val

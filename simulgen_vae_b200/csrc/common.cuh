@@ -83,6 +83,42 @@ __device__ __forceinline__ F8 load8(const __nv_bfloat16* p) {
     }
     return r;
 }
+// Raw (unconverted) 8-element loads: kernels that keep several rows in flight hold the 16-bit rows as 4 registers each
+// until the row is actually processed (holding them converted would double the register footprint of the prefetch).
+struct Raw16 { uint4 q; };
+struct Raw32 { float4 a, b; };
+__device__ __forceinline__ Raw16 load_raw(const __nv_bfloat16* p) {
+    Raw16 r;
+    r.q = *reinterpret_cast<const uint4*>(p);
+    return r;
+}
+__device__ __forceinline__ Raw32 load_raw(const float* p) {
+    Raw32 r;
+    r.a = *reinterpret_cast<const float4*>(p);
+    r.b = *reinterpret_cast<const float4*>(p + 4);
+    return r;
+}
+__device__ __forceinline__ F8 cvt8(const Raw16& w) {
+    F8 r;
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(&w.q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = op16x2_to_f2(u[i]);
+        r.v[2 * i] = f.x;
+        r.v[2 * i + 1] = f.y;
+    }
+    return r;
+}
+__device__ __forceinline__ F8 cvt8(const Raw32& w) {
+    F8 r;
+    r.v[0] = w.a.x; r.v[1] = w.a.y; r.v[2] = w.a.z; r.v[3] = w.a.w;
+    r.v[4] = w.b.x; r.v[5] = w.b.y; r.v[6] = w.b.z; r.v[7] = w.b.w;
+    return r;
+}
+template <typename T> struct RawOf;
+template <> struct RawOf<float> { typedef Raw32 type; };
+template <> struct RawOf<__nv_bfloat16> { typedef Raw16 type; };
+
 __device__ __forceinline__ void store8(float* p, const F8& r) {
     *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);

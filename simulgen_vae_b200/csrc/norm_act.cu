@@ -179,37 +179,64 @@ __device__ __forceinline__ void act_both_t(float x, float& val, float& dval) {
 // ---------------------------------------------------------------------------------------------
 // forward apply: pre = res + res_scale * act(a*y + sh); out = POST ? gelu(pre) : pre
 // ---------------------------------------------------------------------------------------------
-template <typename OT, typename RT, typename YT, int ACT, bool POST>
-__global__ void __launch_bounds__(kThreads)
+// Work decomposition of the GroupNorm / activation kernels: a warp takes one (channel, chunk of <= kChunkB samples)
+// task and walks the chunk's rows - contiguous in memory - several at a time: every load of R rows is issued before the
+// first dependent instruction.  What bounds these kernels is bytes in flight per SM, not issue slots: with one 200-element
+// row per warp (400 B of 16-bit loads) and ~32 resident warps an SM has 13 KB outstanding against the ~40 KB that HBM
+// latency x bandwidth asks for (round 2, gpurun_out/r2_stream_gn_a.txt: the 16-bit y did not speed the one-row kernel up
+// at all).  R = 4 rows for 16-bit streams, 2 for fp32 ones (register budget).  Channel constants are loaded once per
+// task, there is no per-row index division, and per-channel sums cost one atomic per task.
+constexpr int kChunkB = 16;
+template <typename A, typename B2>
+struct RowsInFlight {
+    static constexpr int value = (sizeof(A) == 2 && sizeof(B2) == 2) ? 4 : 2;
+};
+
+template <typename OT, typename RT, typename YT, int ACT, bool POST, int PLANES>
+__global__ void __launch_bounds__(kThreads, 3)
 gn_act_fwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                   const float* __restrict__ beta, const RT* __restrict__ res, float res_scale, OT* __restrict__ out_op,
-                  int planes, long long pstride, float* __restrict__ out_f32, int C, int B, int T, int Tp, int G) {
+                  long long pstride, float* __restrict__ out_f32, int C, int B, int T, int Tp, int G) {
+    constexpr int R = RowsInFlight<YT, YT>::value;
+    constexpr int planes = PLANES;
     extern __shared__ float sg_rows[];
     const int lane = threadIdx.x & 31;
     float* srow = sg_rows + (threadIdx.x >> 5) * (Tp + 8);
-    const bool multi = planes > 1 && out_op != nullptr;
+    const bool multi = PLANES > 1 && out_op != nullptr;
     const int nseg_p = Tp >> 3;
     const bool shfl = multi && nseg_p <= 32;
     if (multi && !shfl) srow_clear_halo(srow, Tp, lane);
-    const int Cg = mr != nullptr ? C / G : 1;
-    const long long rows = (long long)C * B, wstride = (long long)gridDim.x * kWarpsPerBlock;
-    for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
-        int c = (int)(row / B), b = (int)(row % B);
-        float a = 1.f, sh = 0.f;
-        if (mr != nullptr) {
-            float2 st = *reinterpret_cast<const float2*>(mr + 2 * (b * G + c / Cg));
-            a = gamma[c] * st.y;
-            sh = beta[c] - st.x * a;
-        }
-        const YT* yrow = y + row * Tp;
-        auto compute = [&](int seg, F8& o) {
-            if (seg * 8 < T) {
-                F8 yv = load8(yrow + seg * 8);
-                F8 rv;
-                if (res != nullptr) rv = load8(res + row * Tp + seg * 8);
+    const bool has_gn = mr != nullptr;
+    const int Cg = has_gn ? C / G : 1;
+    const int nchunk = (B + kChunkB - 1) / kChunkB;
+    const int tasks = C * nchunk, wstride = gridDim.x * kWarpsPerBlock;
+    const float2* mr2 = reinterpret_cast<const float2*>(mr);
+    for (int task = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < tasks; task += wstride) {
+        const int c = task / nchunk, ch = task - c * nchunk;
+        const int b_lo = ch * kChunkB, b_hi = min(B, b_lo + kChunkB);
+        const int g = has_gn ? c / Cg : 0;
+        const float gm = has_gn ? __ldg(gamma + c) : 1.f, bt = has_gn ? __ldg(beta + c) : 0.f;
+        for (int b0 = b_lo; b0 < b_hi; b0 += R) {
+            float a[R], sh[R];
+            bool ok[R];
+            long long row[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                ok[r] = b0 + r < b_hi;
+                const int bb = ok[r] ? b0 + r : b0;
+                row[r] = ((long long)c * B + bb) * Tp;
+                a[r] = 1.f;
+                sh[r] = 0.f;
+                if (has_gn) {
+                    const float2 st = __ldg(mr2 + bb * G + g);
+                    a[r] = gm * st.y;
+                    sh[r] = bt - st.x * a[r];
+                }
+            }
+            auto finish = [&](int r, int seg, const F8& yv, const F8& rv, F8& o) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    float pre = res_scale * act_t<ACT>(fmaf(yv.v[i], a, sh));
+                    float pre = res_scale * act_t<ACT>(fmaf(yv.v[i], a[r], sh[r]));
                     if (res != nullptr) pre += rv.v[i];
                     if (POST) pre = gelu_f(pre);
                     o.v[i] = pre;
@@ -219,34 +246,63 @@ gn_act_fwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const 
                     for (int i = 0; i < 8; ++i)
                         if (seg * 8 + i >= T) o.v[i] = 0.f;
                 }
-            } else {
+            };
+            if (shfl || !multi) {
+                // rows of <= 256 elements with shifted planes (one segment per lane, planes from registers + shuffles),
+                // or single-plane / fp32-only rows of any length
+                for (int seg = lane; seg < (shfl ? 32 : nseg_p); seg += 32) {
+                    const bool live = seg * 8 < T;
+                    typename RawOf<YT>::type yw[R];
+                    typename RawOf<RT>::type rw[R];
+                    if (live) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
-            }
-        };
-        if (shfl) {
-            // rows of <= 256 elements: one segment per lane, shifted planes built from registers + shuffles
-            F8 o;
-            compute(lane, o);
-            if (out_f32 != nullptr && lane < nseg_p) store8(out_f32 + row * Tp + lane * 8, o);
-            store_planes_shfl_n(out_op, row * Tp, planes, pstride, o, T, nseg_p, lane);
-            continue;
-        }
-        for (int seg = lane; seg < nseg_p; seg += 32) {
-            F8 o;
-            compute(seg, o);
-            if (multi) {
+                        for (int r = 0; r < R; ++r) {        // every load of every row first, kept unconverted
+                            yw[r] = load_raw(y + row[r] + seg * 8);
+                            if (res != nullptr) rw[r] = load_raw(res + row[r] + seg * 8);
+                        }
+                    }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) srow[4 + seg * 8 + i] = o.v[i];
-            } else if (out_op != nullptr) {
-                store8(out_op + row * Tp + seg * 8, o);
+                    for (int r = 0; r < R; ++r) {
+                        F8 o;
+                        if (live) {
+                            F8 rv;
+                            if (res != nullptr) rv = cvt8(rw[r]);
+                            finish(r, seg, cvt8(yw[r]), rv, o);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+                        }
+                        if (ok[r]) {
+                            if (out_f32 != nullptr && seg < nseg_p) store8(out_f32 + row[r] + seg * 8, o);
+                            if (PLANES > 1 && shfl) store_planes_shfl<OT, PLANES>(out_op, row[r], pstride, o, T, nseg_p, lane);
+                            else if (out_op != nullptr && seg < nseg_p) store8(out_op + row[r] + seg * 8, o);
+                        }
+                    }
+                }
+            } else if (PLANES > 1) {
+                // long rows with shifted planes: staged through shared memory, one row at a time
+#pragma unroll 1
+                for (int r = 0; r < R; ++r) {
+                    if (!ok[r]) continue;
+                    for (int seg = lane; seg < nseg_p; seg += 32) {
+                        F8 o;
+                        if (seg * 8 < T) {
+                            F8 yv = load8(y + row[r] + seg * 8), rv;
+                            if (res != nullptr) rv = load8(res + row[r] + seg * 8);
+                            finish(r, seg, yv, rv, o);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) srow[4 + seg * 8 + i] = o.v[i];
+                        if (out_f32 != nullptr) store8(out_f32 + row[r] + seg * 8, o);
+                    }
+                    __syncwarp();
+                    store_row_planes(out_op, row[r], planes, pstride, srow, T, Tp, lane);
+                    __syncwarp();
+                }
             }
-            if (out_f32 != nullptr) store8(out_f32 + row * Tp + seg * 8, o);
-        }
-        if (multi) {
-            __syncwarp();
-            store_row_planes(out_op, row * Tp, planes, pstride, srow, T, Tp, lane);
-            __syncwarp();
         }
     }
 }
@@ -317,11 +373,7 @@ __device__ __forceinline__ void bwd_compute(const BwdArgs& p, const SegIn& in, i
     }
 }
 
-// Work decomposition of the backward kernels: a warp takes one (channel, chunk of <= kChunkB samples) task and walks
-// the chunk's rows - contiguous in memory - kRowsInFlight at a time.  Channel constants are loaded once per task,
-// there is no per-row index division, and the per-channel sums (dgamma, dbeta, dbias) cost one atomic per task.
-constexpr int kChunkB = 16;
-constexpr int kRowsInFlight = 2;
+constexpr int kRowsInFlight = 2;      // recon head and no-GroupNorm backward kernels (fp32 streams)
 
 // ---- GroupNorm layers: two passes with a 16-bit-friendly hand-off --------------------------------------------------
 // pass 1 reads y and the incoming gradient, evaluates the activation derivative ONCE and leaves
@@ -344,10 +396,10 @@ struct Pass1Args {
 };
 
 template <typename RT, typename YT, typename DT, int ACT, bool POST>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 gn_bwd_pass1_kernel(Pass1Args p, float* __restrict__ dgamma, float* __restrict__ dbeta, double* __restrict__ S,
                     float* __restrict__ dres, int dres_accumulate) {
-    constexpr int R = kRowsInFlight;
+    constexpr int R = RowsInFlight<YT, DT>::value;
     const int lane = threadIdx.x & 31;
     const int Cg = p.C / p.G;
     const int nchunk = (p.B + kChunkB - 1) / kChunkB;
@@ -383,25 +435,30 @@ gn_bwd_pass1_kernel(Pass1Args p, float* __restrict__ dgamma, float* __restrict__
             }
             for (int seg = lane; seg < nseg_p; seg += 32) {
                 const bool live = seg * 8 < p.T;
-                F8 yv[R], dv[R], rv[R];
+                typename RawOf<YT>::type yw[R];
+                typename RawOf<DT>::type dw[R];
+                typename RawOf<RT>::type rw[R];
                 if (live) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {        // every load of every row first
-                        yv[r] = load8(y + row[r] + seg * 8);
-                        dv[r] = load8(dout + row[r] + seg * 8);
-                        if (POST && has_res) rv[r] = load8(res + row[r] + seg * 8);
+                    for (int r = 0; r < R; ++r) {        // every load of every row first, kept unconverted
+                        yw[r] = load_raw(y + row[r] + seg * 8);
+                        dw[r] = load_raw(dout + row[r] + seg * 8);
+                        if (POST && has_res) rw[r] = load_raw(res + row[r] + seg * 8);
                     }
                 }
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     F8 dz, dp;
                     if (live) {
+                        const F8 yv = cvt8(yw[r]), dv = cvt8(dw[r]);
+                        F8 rv;
+                        if (POST && has_res) rv = cvt8(rw[r]);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             float val, dval;
-                            act_both_t<ACT>(fmaf(yv[r].v[i], a[r], sh[r]), val, dval);
-                            float d = dv[r].v[i];
-                            if (POST) d *= gelu_grad_f(fmaf(p.res_scale, val, has_res ? rv[r].v[i] : 0.f));
+                            act_both_t<ACT>(fmaf(yv.v[i], a[r], sh[r]), val, dval);
+                            float d = dv.v[i];
+                            if (POST) d *= gelu_grad_f(fmaf(p.res_scale, val, has_res ? rv.v[i] : 0.f));
                             dp.v[i] = d;
                             dz.v[i] = p.res_scale * d * dval;
                         }
@@ -413,7 +470,7 @@ gn_bwd_pass1_kernel(Pass1Args p, float* __restrict__ dgamma, float* __restrict__
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             A[r] += dz.v[i];
-                            Bx[r] = fmaf(dz.v[i], fmaf(yv[r].v[i], rstd[r], nm[r]), Bx[r]);
+                            Bx[r] = fmaf(dz.v[i], fmaf(yv.v[i], rstd[r], nm[r]), Bx[r]);
                         }
                     } else {
 #pragma unroll
@@ -453,16 +510,17 @@ gn_bwd_pass1_kernel(Pass1Args p, float* __restrict__ dgamma, float* __restrict__
     }
 }
 
-template <typename OT, typename YT, typename DT>
-__global__ void __launch_bounds__(kThreads)
+template <typename OT, typename YT, typename DT, int PLANES>
+__global__ void __launch_bounds__(kThreads, 3)
 gn_bwd_pass2_kernel(const YT* __restrict__ y, const DT* __restrict__ dz, const float* __restrict__ mr,
-                    const float* __restrict__ gamma, const double* __restrict__ S, OT* __restrict__ dy, int planes,
+                    const float* __restrict__ gamma, const double* __restrict__ S, OT* __restrict__ dy,
                     long long pstride, float* __restrict__ dbias, int C, int B, int T, int Tp, int G, float inv_n) {
-    constexpr int R = kRowsInFlight;
+    constexpr int R = RowsInFlight<YT, DT>::value;
+    constexpr int planes = PLANES;
     extern __shared__ float sg_rows[];
     const int lane = threadIdx.x & 31;
     float* srow = sg_rows + (threadIdx.x >> 5) * (Tp + 8);
-    const bool multi = planes > 1;
+    constexpr bool multi = PLANES > 1;
     const int nseg_p = Tp >> 3;
     const bool shfl = nseg_p <= 32;
     if (multi && !shfl) srow_clear_halo(srow, Tp, lane);
@@ -508,31 +566,32 @@ gn_bwd_pass2_kernel(const YT* __restrict__ y, const DT* __restrict__ dz, const f
             if (shfl || !multi) {
                 for (int seg = lane; seg < (shfl ? 32 : nseg_p); seg += 32) {
                     const bool live = seg * 8 < T;
-                    F8 yv[R], zv[R];
+                    typename RawOf<YT>::type yw[R];
+                    typename RawOf<DT>::type zw[R];
                     if (live) {
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            yv[r] = load8(y + row[r] + seg * 8);
-                            zv[r] = load8(dz + row[r] + seg * 8);
+                            yw[r] = load_raw(y + row[r] + seg * 8);
+                            zw[r] = load_raw(dz + row[r] + seg * 8);
                         }
                     }
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         F8 o;
                         if (live) {
-                            finish(r, seg, yv[r], zv[r], o);
+                            finish(r, seg, cvt8(yw[r]), cvt8(zw[r]), o);
                         } else {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
                         }
                         if (multi) {
-                            if (ok[r]) store_planes_shfl_n(dy, row[r], planes, pstride, o, T, nseg_p, lane);
+                            if (ok[r]) store_planes_shfl<OT, PLANES>(dy, row[r], pstride, o, T, nseg_p, lane);
                         } else if (ok[r] && seg < nseg_p) {
                             store8(dy + row[r] + seg * 8, o);
                         }
                     }
                 }
-            } else {
+            } else if (PLANES > 1) {
                 // long rows with shifted planes: staged through shared memory, one row at a time
 #pragma unroll 1
                 for (int r = 0; r < R; ++r) {
@@ -849,10 +908,26 @@ recon_fwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const f
 // A lane-per-row mapping (each lane walking its own row) was measured 2-5x slower: 32 different cache lines per
 // load instruction times ~48 resident warps overflow L1 before a line is consumed.
 
-template <typename YT, bool MSE, bool ROWSUMS, bool XHAT>
+// The target x is either the external fp32 tensor [B][N][T] (XT = float) or - XT = 16-bit - the packed operand of the
+// first encoder conv, [N][B][Tp] in the operand format: the same values the encoder consumes, in the layout of y, at half
+// the bytes (fp16 mode: |x| <= 0.7 carries an absolute rounding error <= 2.4e-4).
+template <typename XT>
+__device__ __forceinline__ const XT* x_row(const XT* x, int n, int bb, int B, int T, int Tp, size_t xstride) {
+    if (sizeof(XT) == 2) return x + ((size_t)n * B + bb) * Tp;
+    return x + (size_t)n * T + bb * xstride;
+}
+__device__ __forceinline__ F8 load8_x(const float* p) {
+    F8 r;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ F8 load8_x(const __nv_bfloat16* p) { return load8(p); }
+
+template <typename YT, typename XT, bool MSE, bool ROWSUMS, bool XHAT>
 __global__ void __launch_bounds__(kThreads, 4)
 recon_fwd_fast_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
-                      const float* __restrict__ beta, const float* __restrict__ x, float* __restrict__ x_hat,
+                      const float* __restrict__ beta, const XT* __restrict__ x, float* __restrict__ x_hat,
                       double* __restrict__ loss_sums, float4* __restrict__ rowsums, int N, int B, int T, int Tp, int G,
                       int loss_kind) {
     constexpr int R = kRowsInFlight;
@@ -868,7 +943,6 @@ recon_fwd_fast_kernel(const YT* __restrict__ y, const float* __restrict__ mr, co
         const float gam = __ldg(gamma + n), bet = __ldg(beta + n);
         const int g = n / Cg;
         const YT* ych = y + (size_t)n * B * Tp;
-        const float* xch = x + (size_t)n * T;
         float* hch = XHAT ? x_hat + (size_t)n * T : nullptr;
         float s0 = 0.f, s1 = 0.f;                            // fp32 partials of this channel, flushed to fp64 per channel
         for (int b0 = 0; b0 < B; b0 += R) {
@@ -887,18 +961,16 @@ recon_fwd_fast_kernel(const YT* __restrict__ y, const float* __restrict__ mr, co
 #pragma unroll
             for (int r = 0; r < R; ++r) { l0[r] = l1[r] = aL[r] = bL[r] = aM[r] = bM[r] = 0.f; }
             for (int seg = lane; seg < nseg; seg += 32) {
-                F8 yv[R];
-                float4 x0[R], x1[R];
+                F8 yv[R], xw[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {                // every load of every row first
                     const int bb = ok[r] ? b0 + r : b0;
                     yv[r] = load8(ych + (size_t)bb * Tp + seg * 8);
-                    x0[r] = __ldg(reinterpret_cast<const float4*>(xch + bb * xstride + seg * 8));
-                    x1[r] = __ldg(reinterpret_cast<const float4*>(xch + bb * xstride + seg * 8 + 4));
+                    xw[r] = load8_x(x_row(x, n, bb, B, T, Tp, xstride) + seg * 8);
                 }
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const float xv[8] = {x0[r].x, x0[r].y, x0[r].z, x0[r].w, x1[r].x, x1[r].y, x1[r].z, x1[r].w};
+                    const float* xv = xw[r].v;
                     float h[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -951,10 +1023,10 @@ recon_fwd_fast_kernel(const YT* __restrict__ y, const float* __restrict__ mr, co
     }
 }
 
-template <typename YT, typename OT, bool MSE>
+template <typename YT, typename XT, typename OT, bool MSE>
 __global__ void __launch_bounds__(kThreads, 4)
 recon_bwd_apply_fast_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
-                            const float* __restrict__ beta, const float* __restrict__ x, const float* __restrict__ scal,
+                            const float* __restrict__ beta, const XT* __restrict__ x, const float* __restrict__ scal,
                             const double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias, int N, int B,
                             int T, int Tp, int G, int loss_kind, float inv_n) {
     constexpr int R = kRowsInFlight;
@@ -971,7 +1043,6 @@ recon_bwd_apply_fast_kernel(const YT* __restrict__ y, const float* __restrict__ 
         const int g = n / Cg;
         const YT* ych = y + (size_t)n * B * Tp;
         OT* dch = dy + (size_t)n * B * Tp;
-        const float* xch = x + (size_t)n * T;
         float db = 0.f;
         for (int b0 = 0; b0 < B; b0 += R) {
             float a[R], sh[R], c1[R], c2[R], c3[R];
@@ -992,18 +1063,16 @@ recon_bwd_apply_fast_kernel(const YT* __restrict__ y, const float* __restrict__ 
             }
             for (int seg = lane; seg < nseg_p; seg += 32) {
                 if (seg < nseg) {
-                    F8 yv[R];
-                    float4 x0[R], x1[R];
+                    F8 yv[R], xw[R];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         const int bb = ok[r] ? b0 + r : b0;
                         yv[r] = load8(ych + (size_t)bb * Tp + seg * 8);
-                        x0[r] = __ldg(reinterpret_cast<const float4*>(xch + bb * xstride + seg * 8));
-                        x1[r] = __ldg(reinterpret_cast<const float4*>(xch + bb * xstride + seg * 8 + 4));
+                        xw[r] = load8_x(x_row(x, n, bb, B, T, Tp, xstride) + seg * 8);
                     }
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        const float xv[8] = {x0[r].x, x0[r].y, x0[r].z, x0[r].w, x1[r].x, x1[r].y, x1[r].z, x1[r].w};
+                        const float* xv = xw[r].v;
                         F8 o;
                         float acc = 0.f;
 #pragma unroll
@@ -1222,9 +1291,12 @@ template <typename OT, typename RT, typename YT, int ACT, bool POST>
 static void launch_fwd_t(const void* y, const float* mr, const float* gamma, const float* beta, const void* res,
                          float res_scale, void* out_op, int planes, long long pstride, float* out_f32, int C, int B, int T,
                          int Tp, int G, cudaStream_t st) {
-    size_t sm = (planes > 1 && out_op) ? sizeof(float) * kWarpsPerBlock * (Tp + 8) : 0;
-    gn_act_fwd_kernel<OT, RT, YT, ACT, POST><<<persistent_grid((long long)C * B), kThreads, sm, st>>>(
-        (const YT*)y, mr, gamma, beta, (const RT*)res, res_scale, (OT*)out_op, planes, pstride, out_f32, C, B, T, Tp, G);
+    size_t sm = (planes > 1 && out_op && (Tp >> 3) > 32) ? sizeof(float) * kWarpsPerBlock * (Tp + 8) : 0;
+    const int grid = persistent_grid((long long)C * cdiv(B, kChunkB));
+#define SG_FP(PL) gn_act_fwd_kernel<OT, RT, YT, ACT, POST, PL><<<grid, kThreads, sm, st>>>( \
+        (const YT*)y, mr, gamma, beta, (const RT*)res, res_scale, (OT*)out_op, pstride, out_f32, C, B, T, Tp, G)
+    if (out_op == nullptr || planes == 1) SG_FP(1); else if (planes == 3) SG_FP(3); else SG_FP(5);
+#undef SG_FP
 }
 
 template <typename OT, typename RT, typename YT>
@@ -1271,8 +1343,10 @@ static int launch_bwd_gn(int act, int post, const Pass1Args& p, OT* dy, int plan
 #undef SG_P1
     const size_t sm = (planes > 1 && (p.Tp >> 3) > 32) ? sizeof(float) * kWarpsPerBlock * (p.Tp + 8) : 0;
     const float inv_n = (float)(1.0 / ((double)(p.C / p.G) * p.T));
-    gn_bwd_pass2_kernel<OT, YT, DT><<<grid, kThreads, sm, st>>>((const YT*)p.y, (const DT*)p.dout, p.mr, p.gamma, ws, dy, planes,
-                                                              pstride, dbias, p.C, p.B, p.T, p.Tp, p.G, inv_n);
+#define SG_P2(PL) gn_bwd_pass2_kernel<OT, YT, DT, PL><<<grid, kThreads, sm, st>>>((const YT*)p.y, (const DT*)p.dout, p.mr, p.gamma, ws, \
+                                                                                dy, pstride, dbias, p.C, p.B, p.T, p.Tp, p.G, inv_n)
+    if (planes == 1) SG_P2(1); else if (planes == 3) SG_P2(3); else SG_P2(5);
+#undef SG_P2
     return check_launch("gn_act_bwd");
 }
 
@@ -1417,32 +1491,39 @@ int sg_gn_act_bwd(const void* y, int y_dtype, const float* mr, const float* gamm
     return launch_bwd_plain<float, float>(act, post_gelu, p, (float*)dy, planes, plane_stride, dbias, dres, dres_accumulate, ws, st);
 }
 
-int sg_recon_fwd(const void* y, int y_dtype, const float* mr, const float* gamma, const float* beta, const float* x,
-                 float* x_hat, double* loss_sums, float* rowsums, int N, int B, int T, int Tp, int G, int loss_kind,
-                 void* stream) {
+int sg_recon_fwd(const void* y, int y_dtype, const float* mr, const float* gamma, const float* beta, const void* xv,
+                 int x_dtype, float* x_hat, double* loss_sums, float* rowsums, int N, int B, int T, int Tp, int G,
+                 int loss_kind, void* stream) {
     SG_CHECK_OP16(y_dtype);
+    SG_CHECK_OP16(x_dtype);
     SG_REQUIRE(G > 0 && N % G == 0, "recon_fwd: N=%d not divisible by G=%d", N, G);
-    SG_REQUIRE(rowsums == nullptr || (x != nullptr && aligned16(rowsums)), "recon_fwd: rowsums needs x and 16-byte alignment");
+    SG_REQUIRE(rowsums == nullptr || (xv != nullptr && aligned16(rowsums)), "recon_fwd: rowsums needs x and 16-byte alignment");
+    const bool x16 = xv != nullptr && is_op16(x_dtype);
+    SG_REQUIRE(!x16 || ((T & 7) == 0 && is_op16(y_dtype) && (long long)N * B < (1LL << 31)),
+               "recon_fwd: a 16-bit packed target needs T %% 8 == 0 and a 16-bit y");
+    const float* x = x16 ? nullptr : (const float*)xv;
     cudaStream_t st = as_stream(stream);
-    if (x != nullptr) cudaMemsetAsync(loss_sums, 0, sizeof(double) * 2, st);
+    if (xv != nullptr) cudaMemsetAsync(loss_sums, 0, sizeof(double) * 2, st);
     bool vec = (T % 4 == 0) && aligned16(x) && aligned16(x_hat);
     int grid = persistent_grid((long long)N * B) * 2;
     const bool mse = loss_kind == SG_LOSS_MSE;
     const bool ybf = is_op16(y_dtype);
-    if (vec && x != nullptr && (T & 7) == 0 && (long long)N * B < (1LL << 31)) {
+    if (vec && xv != nullptr && (T & 7) == 0 && (long long)N * B < (1LL << 31)) {
         grid = persistent_grid(N);                           // one warp per channel
-#define SG_FAST(YT, MSE, RS, XH) \
-    recon_fwd_fast_kernel<YT, MSE, RS, XH><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, x, x_hat, loss_sums, \
-                                                                      (float4*)rowsums, N, B, T, Tp, G, loss_kind)
-#define SG_FAST2(YT, MSE) do { \
-        if (rowsums) { if (x_hat) SG_FAST(YT, MSE, true, true); else SG_FAST(YT, MSE, true, false); } \
-        else         { if (x_hat) SG_FAST(YT, MSE, false, true); else SG_FAST(YT, MSE, false, false); } } while (0)
-        if (ybf) { if (mse) SG_FAST2(__nv_bfloat16, true); else SG_FAST2(__nv_bfloat16, false); }
-        else     { if (mse) SG_FAST2(float, true); else SG_FAST2(float, false); }
+#define SG_FAST(YT, XT, MSE, RS, XH) \
+    recon_fwd_fast_kernel<YT, XT, MSE, RS, XH><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, (const XT*)xv, x_hat, loss_sums, \
+                                                                          (float4*)rowsums, N, B, T, Tp, G, loss_kind)
+#define SG_FAST2(YT, XT, MSE) do { \
+        if (rowsums) { if (x_hat) SG_FAST(YT, XT, MSE, true, true); else SG_FAST(YT, XT, MSE, true, false); } \
+        else         { if (x_hat) SG_FAST(YT, XT, MSE, false, true); else SG_FAST(YT, XT, MSE, false, false); } } while (0)
+        if (x16)      { if (mse) SG_FAST2(__nv_bfloat16, __nv_bfloat16, true); else SG_FAST2(__nv_bfloat16, __nv_bfloat16, false); }
+        else if (ybf) { if (mse) SG_FAST2(__nv_bfloat16, float, true); else SG_FAST2(__nv_bfloat16, float, false); }
+        else          { if (mse) SG_FAST2(float, float, true); else SG_FAST2(float, float, false); }
 #undef SG_FAST2
 #undef SG_FAST
         return check_launch("recon_fwd");
     }
+    SG_REQUIRE(!x16, "recon_fwd: the 16-bit packed target is only supported by the fast path");
 #define SG_RFWD(YT, VEC, MSE)                                                                                              \
     recon_fwd_kernel<YT, VEC, MSE><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, x, x_hat, loss_sums,          \
                                                               (float4*)rowsums, N, B, T, Tp, G, loss_kind)
@@ -1455,13 +1536,18 @@ int sg_recon_fwd(const void* y, int y_dtype, const float* mr, const float* gamma
     return check_launch("recon_fwd");
 }
 
-int sg_recon_bwd(const void* y, int y_dtype, const float* mr, const float* gamma, const float* beta, const float* x,
-                 const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext, const float* rowsums,
-                 void* dy, float* dgamma, float* dbeta, float* dbias, double* ws, int N, int B, int T, int Tp, int G,
-                 int loss_kind, int dtype, void* stream) {
+int sg_recon_bwd(const void* y, int y_dtype, const float* mr, const float* gamma, const float* beta, const void* xv,
+                 int x_dtype, const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext,
+                 const float* rowsums, void* dy, float* dgamma, float* dbeta, float* dbias, double* ws, int N, int B, int T,
+                 int Tp, int G, int loss_kind, int dtype, void* stream) {
     SG_CHECK_OP16(dtype);
+    SG_CHECK_OP16(x_dtype);
+    const bool x16 = xv != nullptr && is_op16(x_dtype);
+    SG_REQUIRE(!x16 || (rowsums != nullptr && dxhat_ext == nullptr && (T & 7) == 0 && is_op16(y_dtype) && is_op16(dtype)),
+               "recon_bwd: a 16-bit packed target needs the one-pass path (row sums, T %% 8 == 0, 16-bit y and dy)");
+    const float* x = x16 ? nullptr : (const float*)xv;
     SG_REQUIRE(G > 0 && N % G == 0 && Tp % 8 == 0, "recon_bwd: bad shape");
-    SG_REQUIRE(x != nullptr || (g_loss == nullptr && g_mse == nullptr), "recon_bwd: loss gradient without x");
+    SG_REQUIRE(xv != nullptr || (g_loss == nullptr && g_mse == nullptr), "recon_bwd: loss gradient without x");
     SG_REQUIRE(y_dtype == SG_F32 || y_dtype == dtype, "recon_bwd: a 16-bit y needs the same 16-bit mode");
     cudaStream_t st = as_stream(stream);
     double inv_n = 1.0 / ((double)(N / G) * T);
@@ -1474,7 +1560,7 @@ int sg_recon_bwd(const void* y, int y_dtype, const float* mr, const float* gamma
     int grid = persistent_grid((long long)N * B) * 2;
     const bool ybf = is_op16(y_dtype);
     typedef __nv_bfloat16 bf;
-    if (rowsums != nullptr && dxhat_ext == nullptr && x != nullptr) {
+    if (rowsums != nullptr && dxhat_ext == nullptr && xv != nullptr) {
         // one pass over y / x: the reductions of the GroupNorm backward were taken by the forward
         SG_REQUIRE((size_t)B * 2 * sizeof(float) <= 48 * 1024, "recon_bwd: batch too large for the combine kernel");
         dim3 gc((unsigned)cdiv(N / G, 64), G);
@@ -1484,18 +1570,21 @@ int sg_recon_bwd(const void* y, int y_dtype, const float* mr, const float* gamma
         const bool mse = loss_kind == SG_LOSS_MSE;
         if (vec && (T & 7) == 0 && (long long)N * B < (1LL << 31)) {
             grid = persistent_grid(N);                       // one warp per channel; dbias written, not accumulated
-#define SG_AF(YT, OT, MSE) \
-    recon_bwd_apply_fast_kernel<YT, OT, MSE><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, x, scal, S, (OT*)dy, dbias, \
-                                                                        N, B, T, Tp, G, loss_kind, (float)inv_n)
-            if (is_op16(dtype)) {
-                if (ybf) { if (mse) SG_AF(bf, bf, true); else SG_AF(bf, bf, false); }
-                else     { if (mse) SG_AF(float, bf, true); else SG_AF(float, bf, false); }
+#define SG_AF(YT, XT, OT, MSE) \
+    recon_bwd_apply_fast_kernel<YT, XT, OT, MSE><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, (const XT*)xv, scal, S, (OT*)dy, dbias, \
+                                                                            N, B, T, Tp, G, loss_kind, (float)inv_n)
+            if (x16) {
+                if (mse) SG_AF(bf, bf, bf, true); else SG_AF(bf, bf, bf, false);
+            } else if (is_op16(dtype)) {
+                if (ybf) { if (mse) SG_AF(bf, float, bf, true); else SG_AF(bf, float, bf, false); }
+                else     { if (mse) SG_AF(float, float, bf, true); else SG_AF(float, float, bf, false); }
             } else {
-                if (mse) SG_AF(float, float, true); else SG_AF(float, float, false);
+                if (mse) SG_AF(float, float, float, true); else SG_AF(float, float, float, false);
             }
 #undef SG_AF
             return check_launch("recon_bwd");
         }
+        SG_REQUIRE(!x16, "recon_bwd: the 16-bit packed target is only supported by the fast path");
 #define SG_APPLY(YT, OT, VEC, MSE)                                                                                         \
     recon_bwd_apply_kernel<YT, OT, VEC, MSE><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, x, scal, S, (OT*)dy,  \
                                                                          dbias, N, B, T, Tp, G, loss_kind, inv_n)

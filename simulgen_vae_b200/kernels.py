@@ -245,9 +245,12 @@ def gn_act_bwd(y, stats, gamma, beta, res, res_scale, act, post_gelu, dout, dy, 
 
 
 def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind, rowsums=None):
-    """rowsums: optional fp32 [N*B, 4] - partial sums of the GroupNorm backward taken by the forward."""
+    """rowsums: optional fp32 [N*B, 4] - partial sums of the GroupNorm backward taken by the forward.
+    x: fp32 [B, N, T], or the packed 16-bit operand plane [N, B, Tp] of the encoder input (same dtype as y)."""
     N, B, Tp = y.shape
-    _call("sg_recon_fwd", _p(y), _dt(y), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), _p(x_hat), _p(loss_sums),
+    xd = _dt(x) if x is not None else SG_F32
+    assert x is None or (tuple(x.shape) == (B, N, T) if xd == SG_F32 else tuple(x.shape) == (N, B, Tp))
+    _call("sg_recon_fwd", _p(y), _dt(y), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), xd, _p(x_hat), _p(loss_sums),
           _p(_f32(rowsums, "rowsums")), N, B, T, Tp, G, int(loss_kind), _stream())
 
 
@@ -257,7 +260,8 @@ def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy,
     ws = torch.empty(2 * B * G + 2, dtype=torch.float64, device=y.device)
     dp, dn, _ = _planes(dy)
     assert dn == 1
-    _call("sg_recon_bwd", _p(y), _dt(y), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), _p(g_loss), _p(g_mse), float(inv_numel),
+    xd = _dt(x) if x is not None else SG_F32
+    _call("sg_recon_bwd", _p(y), _dt(y), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), xd, _p(g_loss), _p(g_mse), float(inv_numel),
           _p(dxhat_ext), _p(_f32(rowsums, "rowsums")), dp, _p(dgamma), _p(dbeta), _p(dbias), _p(ws), N, B, T, Tp, G,
           int(loss_kind), _dt(dy),
           _stream())

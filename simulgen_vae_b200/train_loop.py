@@ -110,6 +110,9 @@ def train(epochs, batch_size, train_dataloader, val_dataloader, LR, num_filter_e
             acc += torch.stack([loss.double().reshape(()), recon.double().reshape(()) * alpha, kl_sum.double().reshape(()) * beta,
                                 mse.double().reshape(()) * alpha, trainer.gnorm_sq.sqrt().reshape(())])
             n_batches += 1
+        if ddp:                                                           # logged scalars are means over the GLOBAL batches
+            dist.all_reduce(acc)
+            acc /= dist.get_world_size()
         sums = acc.tolist()                                               # the epoch's only device -> host read
         if epoch % 20 == 0 or epoch == epochs - 1:
             model.eval()
@@ -124,6 +127,9 @@ def train(epochs, batch_size, train_dataloader, val_dataloader, LR, num_filter_e
                     r = recon.double().reshape(()) * alpha
                     vacc += torch.stack([r + kl_sum.double().reshape(()) * beta, r])
                     n_val += 1
+            if ddp:
+                dist.all_reduce(vacc)
+                vacc /= dist.get_world_size()
             v = vacc.tolist()
             loss_val_print[epoch] = v[0] / max(n_val, 1)
             recon_loss_val_print[epoch] = v[1] / max(n_val, 1)

@@ -248,3 +248,52 @@ def test_train_driver_data_parallel_world2_equals_single_process(tmp_path):
     assert list(dp.keys()) == list(single.keys())
     for k in single:
         assert rel_l2(dp[k], single[k]) < 1e-4, (k, rel_l2(dp[k], single[k]))
+
+
+def _loader_dp_worker(rank, world, port, workdir, data):
+    import random
+    import numpy as np
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    if world > 1:
+        torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    os.makedirs(os.path.join(workdir, "w%d_r%d" % (world, rank)), exist_ok=True)
+    os.chdir(os.path.join(workdir, "w%d_r%d" % (world, rank)))
+    torch.randn_like = lambda t, *a, **k: torch.zeros_like(t)          # reparameterisation noise off: DP == single exactly
+    # like the reference's entry point nobody seeds the ranks alike: rank 0 == the single process, rank 1 differs
+    random.seed(5 + 100 * rank); np.random.seed(6 + 100 * rank); torch.manual_seed(7 + 100 * rank)
+    sg.install_overlay(train=True)
+    sg.set_precision("fp32")
+    from modules.augmentation import create_augmented_dataloaders      # the overlay's drop-in
+    from modules.train import train
+    cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[32, 16, 8], num_node=64, num_time=20)
+    batch_size = 4 // world                                            # SimulGen-VAE.py:172: Batch_size //= world_size
+    with emu.install():
+        train_dl, val_dl = create_augmented_dataloaders(data.numpy(), batch_size, load_all=True, device="cpu")
+        for dl in (train_dl, val_dl):
+            dl.injected_noise = lambda levels, shape: torch.zeros((len(levels),) + tuple(shape))
+        assert len(train_dl) == 4 and len(val_dl) == 1
+        curves = train(4, batch_size, train_dl, val_dl, 1e-3, cfg["enc"], cfg["enc"][::-1], cfg["num_node"], cfg["latent_dim"],
+                       cfg["hierarchical_dim"], cfg["num_time"], 1000000, "MSE", True, True, device="cpu")
+    torch.save([torch.as_tensor(c) for c in curves], "curves.pt")
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def test_overlay_loader_shards_global_batches_across_ranks(tmp_path):
+    """`SimulGen-VAE.py --use_ddp` + install_overlay(train=True) without hand-sharding: the overlay's
+    create_augmented_dataloaders hands rank r its 1/W slice of every global batch (one split, one shuffle, one set of
+    augmentation decisions - rank 0's, broadcast), so 2 gloo ranks at per-rank batch 2 end with the weights and the loss
+    curves of the single process at batch 4."""
+    g = torch.Generator().manual_seed(0)
+    data = torch.rand(20, 64, 20, generator=g) * 1.4 - 0.7
+    mp.spawn(_loader_dp_worker, args=(2, _free_port(), str(tmp_path), data), nprocs=2, join=True)
+    mp.spawn(_loader_dp_worker, args=(1, _free_port(), str(tmp_path), data), nprocs=1, join=True)
+    dp = torch.load(str(tmp_path / "w2_r0" / "checkpoints" / "SimulGen-VAE.pth"), weights_only=False)
+    single = torch.load(str(tmp_path / "w1_r0" / "checkpoints" / "SimulGen-VAE.pth"), weights_only=False)
+    for k in single:
+        assert rel_l2(dp[k], single[k]) < 1e-4, (k, rel_l2(dp[k], single[k]))
+    c_dp = torch.load(str(tmp_path / "w2_r0" / "curves.pt"))
+    c_1 = torch.load(str(tmp_path / "w1_r0" / "curves.pt"))
+    for a, b in zip(c_dp, c_1):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-7), (a, b)
