@@ -9,7 +9,7 @@ reference's `modules/` is a namespace package (no __init__.py), so the remaining
 import os
 import sys
 
-from .engine import DEFAULT_PRECISION, fixed_eps, get_precision, set_precision, set_sample_offset, tp_of  # noqa: F401
+from .engine import DEFAULT_PRECISION, PackedBatch, fixed_eps, loss_target, set_loss_target, get_precision, set_precision, set_sample_offset, tp_of  # noqa: F401
 
 OVERLAY_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "overlay")
 OVERLAY_TRAIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "overlay_train")

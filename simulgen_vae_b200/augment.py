@@ -91,7 +91,8 @@ class B200AugmentedLoader:
         self.seed, self.draws = seed, 0
         self.injected_noise = None                        # tests: callable(batch_position, shape) -> noise tensor
         self.last_decisions = None
-        self.emit_operand = False                         # also produce the packed bf16 conv operand
+        self.emit_operand = False                         # also produce the packed 16-bit conv operand
+        self.yield_packed = False                         # yield engine.PackedBatch (operand only, no fp32 batch)
         self.last_operand = None
 
     def __len__(self):
@@ -151,17 +152,18 @@ class B200AugmentedLoader:
             inj = None
             if self.injected_noise is not None and (noise > 0).any():
                 inj = self.injected_noise(noise, tuple(self.data.shape[1:])).to(dev)
-            out = torch.empty((B,) + tuple(self.data.shape[1:]), dtype=torch.float32, device=dev)
+            from .engine import PackedBatch, get_precision, loss_target, tp_of
+            N, T = self.data.shape[1], self.data.shape[2]
+            packed_only = self.yield_packed and loss_target(T) == "operand"
+            out = None if packed_only else torch.empty((B, N, T), dtype=torch.float32, device=dev)
             op = None
-            if self.emit_operand:
-                from .engine import get_precision, tp_of
-                N, T = self.data.shape[1], self.data.shape[2]
+            if self.emit_operand or packed_only:
                 op16 = torch.float16 if get_precision() == "fp16" else torch.bfloat16
                 op = torch.empty(1, N, B, tp_of(T, "bf16"), dtype=op16, device=dev)
             K.assemble_batch(self.data, ids, table, inj, out, self.seed, self.draws, op)
             self.last_operand = op                        # Trainer.step(x, packed=loader.last_operand)
             self.draws += 1
-            yield out
+            yield PackedBatch(op, T) if packed_only else out
 
 
 def create_augmented_dataloaders(x_data, batch_size, load_all=False, augmentation_config=None, val_split=0.2,

@@ -35,7 +35,7 @@ assemble_batch_kernel(const float* __restrict__ data, const int* __restrict__ id
         const float* src = data + (size_t)idx * sample_elems + (size_t)n * T;
         const float* src2 = oth >= 0 ? data + (size_t)oth * sample_elems + (size_t)n * T : nullptr;
         const float* nz = (inj != nullptr) ? inj + (size_t)b * sample_elems + (size_t)n * T : nullptr;
-        float* dst = out + (size_t)b * sample_elems + (size_t)n * T;
+        float* dst = out != nullptr ? out + (size_t)b * sample_elems + (size_t)n * T : nullptr;
         for (int seg = lane; seg * 8 < Tp; seg += 32) {
             const int t0 = seg * 8;
             F8 v;
@@ -77,7 +77,9 @@ assemble_batch_kernel(const float* __restrict__ data, const int* __restrict__ id
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v.v[i] = __fadd_rn(__fmul_rn(lam, v.v[i]), __fmul_rn(om, w.v[i]));
                 }
-                if (VEC && t0 + 8 <= T) {
+                if (dst == nullptr) {
+                    // operand-only batch (engine.PackedBatch): the fp32 copy is never materialised
+                } else if (VEC && t0 + 8 <= T) {
                     *reinterpret_cast<float4*>(dst + t0) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
                     *reinterpret_cast<float4*>(dst + t0 + 4) = make_float4(v.v[4], v.v[5], v.v[6], v.v[7]);
                 } else {
@@ -105,6 +107,7 @@ extern "C" int sg_assemble_batch(const float* data, int P, const int* ids, const
                                  float* out, void* operand, int B, int N, int T, int Tp, unsigned long long seed,
                                  unsigned long long draw, void* stream) {
     SG_REQUIRE(B > 0 && N > 0 && T > 0 && P > 0, "assemble_batch: bad shape");
+    SG_REQUIRE(out != nullptr || operand != nullptr, "assemble_batch: neither an fp32 batch nor an operand to write");
     SG_REQUIRE(operand == nullptr || (Tp % 8 == 0 && Tp >= T), "assemble_batch: bad Tp=%d for T=%d", Tp, T);
     if (operand == nullptr) Tp = (T + 7) / 8 * 8;
     const bool vec = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;

@@ -296,16 +296,22 @@ static int num_sms() {
     return n;
 }
 
-static int pick_splits(int tiles, int iters, int sms) {
-    if (tiles >= sms || iters < 64) return 1;
+// Split-K factor.  Work items = tiles x splits are dealt round-robin to `sms` persistent CTAs (CTA pairs), so the time is
+// ceil(items / sms) waves of iters / splits k-blocks each.  Round 1 only split when tiles < sms; the 75-400-tile layers
+// then ran 2-5 waves at 54-90 % occupancy (profiles/r1_step_profile_b64.txt: the C -> 5C k1 weight gradients, 80 tiles
+// on 74 pairs, 450 TFLOP/s).  Now every shape takes the smallest factor whose last wave is >= 90 % full, as long as a
+// split keeps >= 16 k-blocks (the pipeline prologue / epilogue and the red.add traffic of the partial tiles grow with it).
+static int pick_splits(int tiles, int iters, int sms, bool only_underfilled = false) {
+    if (iters < 32 || (only_underfilled && tiles >= sms)) return 1;
     int best = 1;
     double best_eff = 0.0;
     for (int s = 1; s <= 16; ++s) {
-        if (iters / s < 32) break;
+        if (s > 1 && iters / s < 16) break;
         double waves = (double)tiles * s / sms;
         double eff = waves / ceil(waves);
+        if (s > 1) eff *= 1.0 - 0.01 * s;                  // a split is not free: prefer the smaller factor on ties
         if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
-        if (eff >= 0.93) break;
+        if (eff >= 0.90) break;
     }
     return best;
 }
@@ -376,7 +382,8 @@ int tc_fprop(const void* wg, const void* act, int act_planes, long long act_pstr
     p.m_tiles = (int)cdiv(Cout, pair ? pair::PM : BM); p.n_tiles = (int)cdiv(R, BN); p.z_count = 1; p.group_m = 8;
     p.taps = k; p.kblocks = (int)cdiv(Cin, BK); p.pad = k / 2; p.accumulate = accumulate;
     p.b_plane0 = act_planes / 2 - k / 2; p.b_plane_step = 1; p.a_plane = 0;
-    p.splits = pick_splits(p.m_tiles * p.n_tiles, p.taps * p.kblocks, pair ? num_sms() / 2 : num_sms());
+    // a conv that feeds a GroupNorm keeps its statistics in the epilogue: split only when the grid would be underfilled
+    p.splits = pick_splits(p.m_tiles * p.n_tiles, p.taps * p.kblocks, pair ? num_sms() / 2 : num_sms(), rowstat != nullptr);
     if (out_bf16) p.splits = 1;
     p.atomic = p.splits > 1;
     p.m_fastest = p.m_tiles <= p.n_tiles;

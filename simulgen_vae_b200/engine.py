@@ -278,6 +278,66 @@ def _take_freeze_level():
     return lvl
 
 
+class PackedBatch:
+    """A batch that exists only as the packed 16-bit operand of the first encoder conv, [1, N, B, Tp] in the engine's
+    operand format - what sg_assemble_batch (the resident-dataset loader) or sg_pack_input write.  VAE.forward,
+    Trainer.step and the engine's train() accept it in place of the fp32 [B, N, T] tensor: the encoder consumes the
+    operand as is and the reconstruction loss reads the same values (loss_target() == "operand"), so the fp32 batch is
+    never materialised.  fp16 operand mode with T % 8 == 0 only."""
+
+    def __init__(self, operand, T):
+        if operand.dim() != 4 or operand.shape[0] != 1 or operand.dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError("PackedBatch needs a 16-bit operand of shape [1, N, B, Tp]")
+        self.operand, self.T = operand, int(T)
+        self.shape = (operand.shape[2], operand.shape[1], int(T))
+        self.device = operand.device
+
+    def numel(self):
+        return self.shape[0] * self.shape[1] * self.shape[2]
+
+
+# Target of the reconstruction losses (VAE_network.py:110-111).  "input": the fp32 tensor x [B, N, T], as the reference.
+# "operand": the packed 16-bit operand of x that the first encoder conv consumes anyway ([N, B, Tp], the layout of the
+# recon conv's output): 2 instead of 4 bytes per element in both passes of the reconstruction head, coalesced like y, and
+# the fp32 batch need not exist at all (PackedBatch).  The target is then x rounded to fp16 (|x| <= 0.7: absolute error
+# <= 2.4e-4, a fixed perturbation of the data far below the model's reconstruction error).  Default: "operand" in fp16
+# mode when T % 8 == 0, "input" otherwise (bf16 has 3 bits less: the rounded target would cost gradient parity).
+_LOSS_TARGET = os.environ.get("SIMULGEN_B200_LOSS_TARGET", "auto")
+
+
+def set_loss_target(kind: str):
+    global _LOSS_TARGET
+    if kind not in ("auto", "input", "operand"):
+        raise ValueError("loss target must be 'auto', 'input' or 'operand'")
+    _LOSS_TARGET = kind
+
+
+def loss_target(T: int = 8) -> str:
+    if _PRECISION == "fp32" or T % 8:
+        return "input"
+    if _LOSS_TARGET == "auto":
+        return "operand" if _PRECISION == "fp16" else "input"
+    return _LOSS_TARGET
+
+
+def set_loss_operand(op):
+    """Hand the next decoder forward of this thread the packed operand of its target x (VAE.forward does)."""
+    _sink.loss_op = op
+
+
+def _take_loss_operand():
+    op = getattr(_sink, "loss_op", None)
+    _sink.loss_op = None
+    return op
+
+
+def take_last_packed():
+    """The packed operand the last encoder forward of this thread consumed (or wrote), once."""
+    op = getattr(_sink, "last_packed", None)
+    _sink.last_packed = None
+    return op
+
+
 def set_packed_input(op):
     """Hand the next encoder forward of this thread the already packed bf16 operand [1, N, B, Tp] of its input
     (written by sg_assemble_batch together with the batch): sg_pack_input is skipped once."""
@@ -832,11 +892,17 @@ def encoder_graph(ctx: Ctx, enc, x):
     B, N, T = x.shape
     prepare_all(ctx, enc)
     packed = _take_packed_input()
+    if isinstance(x, PackedBatch):
+        packed = x.operand
+        if tuple(packed.shape) != (1, N, B, ctx.Tp) or packed.dtype != ctx.op_dtype:
+            raise RuntimeError("simulgen_b200: PackedBatch operand %s / %s does not fit the %s mode (expected %s)"
+                               % (tuple(packed.shape), packed.dtype, _PRECISION, (1, N, B, ctx.Tp)))
     if packed is not None and tuple(packed.shape) == (1, N, B, ctx.Tp) and packed.dtype == ctx.op_dtype:
         a = Act(N, data=packed, needs_grad=False, name="x")
     else:
         a = Act(N, data=ctx.op(1, N, B, ctx.Tp), needs_grad=False, name="x")
         K.pack_input(x, a.data, T)
+    _sink.last_packed = a.data if ctx.op_dtype != torch.float32 else None
     L = len(enc.encoder_blocks)
     xs = []
     h = None
@@ -952,6 +1018,14 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     # backward head kernels) is stored as bf16; its GroupNorm statistics are taken from the fp32 accumulators
     y_16 = ctx.op_dtype != torch.float32 and N > 128
     y = torch.empty(N, B, Tp, dtype=ctx.op_dtype if y_16 else torch.float32, device=ctx.dev)
+    # loss target: the packed operand of x (same layout and dtype as y) or the fp32 tensor
+    x_op = _take_loss_operand()
+    use_op = x is not None and x_op is not None and y_16 and loss_target(T) == "operand" and \
+        tuple(x_op.shape) == (1, N, B, Tp) and x_op.dtype == ctx.op_dtype
+    if isinstance(x, PackedBatch):
+        if not use_op:
+            raise RuntimeError("simulgen_b200: a PackedBatch needs loss_target() == 'operand' (fp16 mode, T % 8 == 0)")
+    xt = x_op[0] if use_op else x
     stats = ctx.f32(B, G, 2)
     K.conv_fprop_gn(p.wg, out.data, conv.bias, y, p.Cin, stats, T, G)
     want_xhat = want_xhat and (_materialize_xhat() or x is None)
@@ -961,7 +1035,7 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     sums = ctx.f64(2)
     # training: the forward also takes the row sums of the GroupNorm backward (one backward pass instead of two)
     rowsums = ctx.f32(N * B, 4) if (ctx.tape is not None and x is not None) else None
-    K.recon_fwd(y, stats, gn.weight, gn.bias, x, x_hat, sums, T, G, loss_kind, rowsums)
+    K.recon_fwd(y, stats, gn.weight, gn.bias, xt, x_hat, sums, T, G, loss_kind, rowsums)
     inv_numel = 1.0 / float(B * N * T)
     if x is not None:
         both = ctx.f32(2)
@@ -978,8 +1052,13 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
                 return
             dy = ctx.op(1, N, B, Tp)
             dgamma, dbeta, dbias = ctx.vec_grad(gn.weight, N), ctx.vec_grad(gn.bias, N), ctx.vec_grad(conv.bias, N)
-            K.recon_bwd(y, stats, gn.weight, gn.bias, x, g_loss, g_mse, inv_numel, g_ext, dy, dgamma, dbeta, dbias,
-                        T, G, loss_kind, rowsums)
+            xb = xt
+            if use_op and g_ext is not None:                # a gradient wrt x_hat itself: the two-pass kernels read fp32 x
+                if isinstance(x, PackedBatch):
+                    raise RuntimeError("simulgen_b200: a gradient wrt x_hat needs the fp32 batch, not a PackedBatch")
+                xb = x
+            K.recon_bwd(y, stats, gn.weight, gn.bias, xb, g_loss, g_mse, inv_numel, g_ext, dy, dgamma, dbeta, dbias,
+                        T, G, loss_kind, rowsums if xb is xt else None)
             ctx.set_pgrad(gn.weight, dgamma)
             ctx.set_pgrad(gn.bias, dbeta)
             ctx.set_pgrad(conv.bias, dbias)
@@ -1006,6 +1085,8 @@ def _contig_f32(g):
 
 
 def _check_input(x, what):
+    if isinstance(x, PackedBatch):
+        x = x.operand
     if not x.is_cuda:
         raise RuntimeError("simulgen_b200: %s must be a CUDA tensor - the engine has no CPU fallback" % what)
 
@@ -1025,7 +1106,8 @@ class EncoderFn(torch.autograd.Function):
         _check_input(x, "encoder input")
         fctx.set_materialize_grads(False)
         with device_guard(x.device):
-            x = x.contiguous().float()
+            if not isinstance(x, PackedBatch):
+                x = x.contiguous().float()
             record = _take_grad_mode() and any(fctx.needs_input_grad)
             ctx = Ctx(x.shape[0], x.shape[2], x.device, record, capture)
             last, xs = encoder_graph(ctx, enc, x)
@@ -1083,7 +1165,7 @@ class DecoderFn(torch.autograd.Function):
             ctx = Ctx(z.shape[0], dec.num_time, z.device, record, capture)
             z_ext = Ext(z)
             xs_ext = [Ext(t.contiguous().float()) for t in xs_t]
-            if x is not None:
+            if x is not None and not isinstance(x, PackedBatch):
                 x = x.contiguous().float()
             res = decoder_graph(ctx, dec, z_ext, xs_ext, x, lossfun, mode)
         fctx.ectx, fctx.res, fctx.params, fctx.z_ext, fctx.xs_ext = ctx, res, params, z_ext, xs_ext

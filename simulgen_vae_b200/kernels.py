@@ -431,10 +431,12 @@ def sn_prepare(plan, training):
 
 # ---- batch assembly + augmentation --------------------------------------------------------------
 def assemble_batch(data, ids, table, injected_noise, out, seed, draw, operand=None):
-    """data fp32 [P, N, T]; ids int32 [2, B]; table fp32 [4, B]; out fp32 [B, N, T]; operand: optional 16-bit
-    [1, N, B, Tp] (the packed input of the first encoder conv, bf16 or fp16 like the engine's precision mode)."""
+    """data fp32 [P, N, T]; ids int32 [2, B]; table fp32 [4, B]; out fp32 [B, N, T] (None: operand only); operand:
+    optional 16-bit [1, N, B, Tp] (the packed input of the first encoder conv, bf16 or fp16 like the engine's precision
+    mode)."""
     P, N, T = data.shape
-    B = out.shape[0]
+    B = ids.shape[1]
+    assert out is None or tuple(out.shape) == (B, N, T)
     assert ids.dtype == torch.int32 and tuple(ids.shape) == (2, B) and tuple(table.shape) == (4, B)
     Tp = operand.shape[3] if operand is not None else 0
     if operand is not None:

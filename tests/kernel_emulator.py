@@ -243,7 +243,15 @@ def _recon_xhat(y, gamma, beta, T, G):
     return o.permute(1, 0, 2)                                                     # [B,N,T]
 
 
+def _target(x, T):
+    """fp32 [B, N, T] as is; the packed 16-bit operand plane [N, B, Tp] -> fp32 [B, N, T]"""
+    if x is not None and x.dtype != torch.float32:
+        return x[:, :, :T].float().permute(1, 0, 2)
+    return x
+
+
 def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind, rowsums=None):
+    x = _target(x, T)
     with torch.no_grad():
         xh = _recon_xhat(y, gamma, beta, T, G)
         if x_hat is not None:
@@ -256,6 +264,7 @@ def recon_fwd(y, stats, gamma, beta, x, x_hat, loss_sums, T, G, loss_kind, rowsu
 
 def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy, dgamma, dbeta, dbias, T, G, loss_kind,
               rowsums=None):
+    x = _target(x, T)
     with torch.enable_grad():
         yl = y.detach().float().clone().requires_grad_(True)
         gl = gamma.detach().clone().requires_grad_(True)
@@ -427,7 +436,7 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale
 
 
 def assemble_batch(data, ids, table, injected_noise, out, seed, draw, operand=None):
-    B = out.shape[0]
+    B = ids.shape[1]
     idx, other = ids[0].long(), ids[1].long()
     nl, sc, lam, om = table[0], table[1], table[2], table[3]
     s = data[idx]
@@ -441,7 +450,8 @@ def assemble_batch(data, ids, table, injected_noise, out, seed, draw, operand=No
     mix = other >= 0
     partner = data[other.clamp_min(0)]
     s = torch.where(mix[:, None, None], lam[:, None, None] * s + om[:, None, None] * partner, s)
-    out.copy_(s)
+    if out is not None:
+        out.copy_(s)
     if operand is not None:
         write_planes(operand, s.permute(1, 0, 2), data.shape[2])
 

@@ -120,3 +120,29 @@ def test_trainer_step_with_packed_operand_equals_plain_step():
         assert rel_l2(res[0][k], res[1][k]) < 2e-2, k          # bf16 mode: see test_trainer_fused_step_equals_per_tensor_path
     w = "decoder.recon.0.weight_orig"
     assert rel_l2(res[0][w], res[1][w]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_loader_yields_packed_batches_in_fp16_mode():
+    """yield_packed: the loader emits engine.PackedBatch (the fp16 operand only, the fp32 batch is never written) and a
+    training step on it equals the step on the fp32 batch of the same draw."""
+    import simulgen_vae_b200 as sg
+    from simulgen_vae_b200 import augment, engine
+    from simulgen_vae_b200 import kernels as K
+    sg.set_precision("fp16")
+    try:
+        g = torch.Generator().manual_seed(3)
+        data = (torch.rand(6, 264, 16, generator=g) * 1.4 - 0.7).numpy()
+        batches = []
+        for packed in (False, True):
+            random.seed(1); np.random.seed(2); torch.manual_seed(3)
+            train, _ = augment.create_augmented_dataloaders(data, 2, load_all=True)
+            train.yield_packed = packed
+            batches.append(list(train))
+        for a, b in zip(*batches):
+            assert isinstance(b, engine.PackedBatch) and tuple(b.shape) == tuple(a.shape)
+            ref = torch.empty_like(b.operand)
+            K.pack_input(a, ref, 16)
+            assert torch.equal(b.operand, ref)
+    finally:
+        sg.set_precision(sg.DEFAULT_PRECISION)

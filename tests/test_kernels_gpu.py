@@ -473,6 +473,49 @@ def test_opt_step_dynamic_loss_scaler_skips_overflowed_steps(where):
         close(ia["v"], ib["v"], 2e-5, "v")
 
 
+@pytest.mark.parametrize("loss", ["MSE", "MAE", "smoothL1", "Huber"])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("with_xhat", [False, True])
+def test_recon_head_with_packed_operand_target(loss, dtype, with_xhat):
+    """The reconstruction head reading its target from the packed 16-bit operand of x ([N, B, Tp], the layout of y;
+    engine.loss_target() == "operand") instead of the fp32 [B, N, T] tensor: forward sums, optional x_hat and the one-pass
+    backward against the torch model fed the same rounded target."""
+    N, B, G, T = 264, 5, 8, 200
+    Tp = engine.tp_of(T, "bf16")
+    kind = K.LOSS_KINDS[loss]
+    y = (rnd(N, B, Tp, seed=1) * 2.0).to(dtype)
+    gamma, beta = rnd(N, seed=2) * 0.5 + 1.0, rnd(N, seed=3) * 0.2
+    stats = torch.empty(B, G, 2, device=DEV)
+    K.gn_stats(y.float(), stats, T, G)
+    x = (rnd(B, N, T, seed=4) * 0.5).clamp(-0.7, 0.7)
+    op = torch.empty(1, N, B, Tp, device=DEV, dtype=dtype)
+    K.pack_input(x, op, T)
+    xh1 = torch.empty(B, N, T, device=DEV) if with_xhat else None
+    xh2 = torch.empty(B, N, T, device=DEV)
+    s1, s2 = (torch.empty(2, device=DEV, dtype=torch.float64) for _ in range(2))
+    rowsums = torch.full((N * B, 4), 9.0, device=DEV)
+    K.recon_fwd(y, stats, gamma, beta, op[0], xh1, s1, T, G, kind, rowsums)
+    emu.recon_fwd(y, stats, gamma, beta, op[0], xh2, s2, T, G, kind)
+    close(s1, s2, 1e-5, "loss sums")
+    if with_xhat:
+        close(xh1, xh2, 3e-6, "x_hat")
+    # against the fp32 target the loss moves by the rounding of x only
+    s3 = torch.empty(2, device=DEV, dtype=torch.float64)
+    emu.recon_fwd(y, stats, gamma, beta, x, xh2, s3, T, G, kind)
+    close(s1, s3, 2e-4 if dtype == torch.float16 else 2e-3, "loss sums vs fp32 target")
+    g_loss, g_mse = torch.tensor([1.0e6], device=DEV), torch.tensor([0.5], device=DEV)
+    inv = 1.0 / (B * N * T)
+    outs = []
+    for fn in (K.recon_bwd, emu.recon_bwd):
+        dy = torch.full((1, N, B, Tp), 9.0, device=DEV, dtype=dtype)
+        dg, db, dbi = (torch.empty(N, device=DEV) for _ in range(3))
+        fn(y, stats, gamma, beta, op[0], g_loss, g_mse, inv, None, dy, dg, db, dbi, T, G, kind, rowsums)
+        outs.append((dy.float(), dg, db, dbi))
+    tol16 = 6e-4 if dtype == torch.float16 else 5e-3
+    for a, b, nm in zip(outs[0], outs[1], ("dy", "dgamma", "dbeta", "dbias")):
+        close(a, b, tol16 if nm in ("dy", "dbias") else 5e-5, nm)
+
+
 @pytest.mark.parametrize("training", [True, False])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_sn_prepare_batched_matches_per_layer_model(training, dtype):

@@ -71,10 +71,11 @@ def test_16bit_intermediates_wiring_against_oracle(precision, store16, monkeypat
     channels (here the 5x64 = 320-channel hidden layers of the decoder residual blocks), against the fp32 oracle."""
     from simulgen_vae_b200 import engine
     from oracle import vae_oracle as O
-    cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[64, 32], num_node=96, num_time=16, small=True, lossfun="MSE", batch=2)
+    cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[64, 32], num_node=136, num_time=16, small=True, lossfun="MSE", batch=2)
     monkeypatch.setattr(engine, "_STORE16", store16)
     sg.set_precision(precision)
     seen = {"y16": 0, "g16": 0}
+    targets = []
     try:
         with emu.install():
             from simulgen_vae_b200 import kernels as K
@@ -89,18 +90,26 @@ def test_16bit_intermediates_wiring_against_oracle(precision, store16, monkeypat
                 assert dx.dtype == torch.float32 or (Cin > 256 and not accumulate)
                 return orig_dgrad(wg, dy, dx, Cin, accumulate)
             K.gn_act_bwd, K.conv_dgrad = bwd, dgrad
+            orig_rf = K.recon_fwd
+
+            def rf(y, stats, gamma, beta, x, *a, **k):
+                targets.append((x.dtype, tuple(x.shape)))
+                return orig_rf(y, stats, gamma, beta, x, *a, **k)
+            K.recon_fwd = rf
             torch.manual_seed(11)
             m = build_engine_vae(cfg, None)
             m.train(True)
             sd = {k: v.clone() for k, v in m.state_dict().items()}
             g = torch.Generator().manual_seed(12)
-            x = torch.rand(2, 96, 16, generator=g) * 1.4 - 0.7
+            x = torch.rand(2, 136, 16, generator=g) * 1.4 - 0.7
             eps = [torch.randn(s, generator=g) for s in O.eps_shapes(cfg, 2)]
             with sg.fixed_eps(eps):
                 x_hat, rl, kls, mse = m(x)
             (rl * 1e3 + sum(kls) * 1e-2).backward()
     finally:
         sg.set_precision(sg.DEFAULT_PRECISION)
+    # the loss target: fp16 mode reads the packed operand of x ([N, B, Tp], engine.loss_target), bf16 mode the fp32 tensor
+    assert targets == ([(torch.float16, (136, 2, 16))] if precision == "fp16" else [(torch.float32, (2, 136, 16))]), targets
     if store16 == "1":
         assert seen == {"y16": 2, "g16": 2}, seen       # the two 320-channel layers of the one DecoderResidualBlock
     else:
@@ -112,6 +121,53 @@ def test_16bit_intermediates_wiring_against_oracle(precision, store16, monkeypat
     assert rel_l2(x_hat, ox) < tol
     worst = max(rel_l2(q.grad, p[n].grad) for n, q in m.named_parameters() if q.grad is not None)
     assert worst < tol, worst
+
+
+def test_packed_batch_equals_fp32_batch_in_fp16_mode():
+    """engine.PackedBatch (the batch as the packed fp16 operand only - what the resident-dataset loader emits) gives the
+    step of the fp32 tensor bit for bit: the encoder consumes the same operand and the loss reads the same target."""
+    from simulgen_vae_b200 import engine
+    from simulgen_vae_b200 import kernels as K
+    from simulgen_vae_b200.trainer import Trainer
+    cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[32, 16], num_node=136, num_time=16, small=True, lossfun="MSE", batch=2)
+    sg.set_precision("fp16")
+    try:
+        with emu.install():
+            torch.manual_seed(3)
+            sd = None
+            outs = []
+            g = torch.Generator().manual_seed(5)
+            x = torch.rand(2, 136, 16, generator=g) * 1.4 - 0.7
+            eps = [torch.randn(s, generator=g) for s in __import__("oracle.vae_oracle", fromlist=["x"]).eps_shapes(cfg, 2)]
+            for packed in (False, True):
+                m = build_engine_vae(cfg, sd)
+                sd = sd or {k: v.clone() for k, v in m.state_dict().items()}
+                m.load_state_dict(sd)
+                m.train(True)
+                tr = Trainer(m, lr=1e-3, alpha=1e3)
+                inp = x
+                if packed:
+                    op = torch.empty(1, 136, 2, 16, dtype=torch.float16)
+                    K.pack_input(x, op, 16)
+                    inp = engine.PackedBatch(op, 16)
+                    assert inp.shape == (2, 136, 16)
+                with sg.fixed_eps(eps):
+                    out = tr.step(inp, beta=1e-2)
+                outs.append(([float(v) for v in out], {k: v.clone() for k, v in m.state_dict().items()}))
+        assert outs[0][0] == outs[1][0]
+        for k in outs[0][1]:
+            assert torch.equal(outs[0][1][k], outs[1][1][k]), k
+        # bf16 mode keeps the fp32 target: a PackedBatch is refused with a clear message
+        sg.set_precision("bf16")
+        with emu.install():
+            m = build_engine_vae(cfg, sd)
+            op = torch.empty(1, 136, 2, 16, dtype=torch.bfloat16)
+            K.pack_input(x, op, 16)
+            with pytest.raises(RuntimeError, match="PackedBatch"):
+                with sg.fixed_eps(eps):
+                    m(engine.PackedBatch(op, 16))
+    finally:
+        sg.set_precision(sg.DEFAULT_PRECISION)
 
 
 def test_state_dict_layout_matches_reference_default_preset():
