@@ -1,11 +1,18 @@
 #!/usr/bin/env python
-"""bench.py - VAE training throughput (samples/s) on the headline shape, 1..8 B200s.
+"""bench.py - VAE training throughput (samples/s) of the B200 engine, 1..8 B200s.
 
-  python bench.py --gpus N --steps K --warmup W            # the engine (this repo)
-  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path on the host cores
+  python bench.py --gpus N --steps K --warmup W            # the engine (this repo), BASELINE.json configs[1]
+  python bench.py --config {2,3,4,5} ...                    # the other BASELINE.json configs at their real size
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU path on the host cores
 
-One "step" = forward + backward + AdamW over one batch of synthetic [B, 95008, 200] fields
-(BASELINE.json configs[1]: preset 1, --size=small, bf16).  Prints ONE JSON line (rank 0).
+One "step" = forward + backward + AdamW over one batch of synthetic fields.  Prints ONE JSON line (rank 0).
+
+  value        steps with the inputs resident in HBM in the engine's input format (fp16 mode: engine.PackedBatch, the
+               packed operand of the batch that the resident-dataset loader emits; bf16 mode: fp32 [B, N, T])
+  e2e.value    HOST buffers: every step copies its batch from pinned host memory (H2D inside the timed region,
+               double-buffered on a copy stream) and reads the loss back - PCIe-bound at this shape
+  e2e.resident the reference's own mode (`load_all`, modules/utils.py:41-43): dataset resident in HBM, the host sends
+               sample indices + augmentation decisions per step, sg_assemble_batch gathers / augments / packs
 """
 import argparse
 import json
@@ -23,6 +30,16 @@ import torch  # noqa: E402
 
 HEADLINE = dict(latent_dim=32, hierarchical_dim=8, enc=[1024, 512, 256, 128], num_node=95008, num_time=200,
                 small=True, lossfun="MSE")
+# BASELINE.json configs[1..4].  `batch` = default per-GPU batch, `samples` = dataset size P.
+CONFIGS = {
+    2: dict(HEADLINE, name="preset1 --size=small, 484x200x95008 field", batch=64, samples=484),
+    3: dict(HEADLINE, small=False, name="preset1 --size=large, 484x200x95008 field", batch=64, samples=484),
+    4: dict(HEADLINE, num_node=1000000, num_time=1, name="static (Dim2=1) 4096x1x1,000,000-node field", batch=512, samples=4096),
+    # num_var is parsed and never read by the reference (modules/utils.py:311): the only meaning a [B, N, T] Conv1d model
+    # can give 4 variables is to fold them into the node axis, N = 4 x 95008 = 380032
+    5: dict(HEADLINE, num_node=380032, num_time=400, name="multi-variable num_var=4 (N = 4 x 95008 = 380032), 1024x400 field",
+            batch=16, samples=1024),
+}
 ALPHA, BETA, LR = 1.0e6, 1.0e-4, 1.0e-3
 METRIC = "VAE train samples/s @200x95008 fields"
 
@@ -78,19 +95,27 @@ def fwd_bwd_gflop_per_sample(cfg):
     return (fwd + bwd) / 1e9
 
 
-def synthetic_batches(n_batches, B, N, T, device, seed):
-    """SURVEY.md 8d generator, on the device, fp32 [B, N, T] in [-0.7, 0.7]."""
+def synthetic_fields(P, N, T, device, seed, chunk=16):
+    """SURVEY.md 8d generator, on the device, fp32 [P, N, T] in [-0.7, 0.7] (written chunk by chunk)."""
     g = torch.Generator(device=device).manual_seed(seed)
     a = torch.rand(N, generator=g, device=device) * 0.8 + 0.2
     phi = torch.rand(N, generator=g, device=device)
-    t = torch.arange(T, dtype=torch.float32, device=device) / T
-    out = []
-    for _ in range(n_batches):
-        f = torch.rand(B, generator=g, device=device) * 3.5 + 0.5
+    t = torch.arange(T, dtype=torch.float32, device=device) / max(T, 1)
+    out = torch.empty(P, N, T, dtype=torch.float32, device=device)
+    for p0 in range(0, P, chunk):
+        n = min(chunk, P - p0)
+        f = torch.rand(n, generator=g, device=device) * 3.5 + 0.5
         x = 0.7 * a[None, :, None] * torch.sin(6.283185307179586 * (f[:, None, None] * t[None, None, :] + phi[None, :, None]))
-        x += 0.02 * torch.randn(B, N, T, generator=g, device=device)
-        out.append(x.clamp_(-0.7, 0.7).contiguous())
+        x += 0.02 * torch.randn(n, N, T, generator=g, device=device)
+        out[p0:p0 + n] = x.clamp_(-0.7, 0.7)
+        del x
     return out
+
+
+def synthetic_batches(n_batches, B, N, T, device, seed):
+    """n_batches fp32 [B, N, T] batches of the generator above (helper of the scripts under scripts/)."""
+    xs = synthetic_fields(n_batches * B, N, T, device, seed).view(n_batches, B, N, T)
+    return [xs[i] for i in range(n_batches)]
 
 
 class ClockSampler:
@@ -123,19 +148,20 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], None, set()
+        sm, smax, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 smax = float(r[1])
+                power.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "power_w": statistics.median(power) if power else None, "samples": len(sm)}
 
 
 def build_engine_model(cfg, batch, device, seed=0):
@@ -154,8 +180,9 @@ def build_engine_model(cfg, batch, device, seed=0):
 # CPU arm: the reference's own implementation (or its oracle port) on the host cores
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_run(cfg, batch, steps, warmup):
-    """Returns (samples/s, kind, cores).  Uses the unmodified reference modules when /root/reference is
-    present (build container), else the oracle port (GPU box)."""
+    """Returns (samples/s, kind, cores, s/step).  Runs the UNMODIFIED reference modules (from /root/reference in the build
+    container, from the staged byte-for-byte copy oracle/_ref on the GPU box: oracle/make_ref.sh) - kind "reference";
+    only if neither exists the oracle port - kind "port"."""
     from oracle import ref_import, vae_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -207,133 +234,223 @@ def main():
         print(json.dumps(line), flush=True)
 
 
-def _main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("SIMULGEN_BENCH_BATCH", "64")), help="per-GPU batch")
-    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--nodes", type=int, default=HEADLINE["num_node"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=2)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"],
-                    help="16-bit operand format of the tensor-core path (fp16: same kernels, loss scaling, ~8x smaller rounding error)")
-    args = ap.parse_args()
-    cfg = dict(HEADLINE, num_node=args.nodes)
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    gflop = fwd_bwd_gflop_per_sample(cfg)
-    workload = "preset1 --size=small, %dx%d fields (N=%d nodes, T=%d), fwd+bwd+AdamW" % (
-        cfg["num_time"], cfg["num_node"], cfg["num_node"], cfg["num_time"])
-
-    if args.impl == "reference":
-        if rank != 0:
-            return None
-        sps, kind, cores, sec = cpu_reference_run(cfg, args.cpu_batch, max(1, min(args.steps, 3)), min(args.warmup, 1))
-        line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
-                "steps": max(1, min(args.steps, 3)), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "batch": args.cpu_batch, "device": "host CPU"},
-                "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": kind,
-                                 "sample": "%d steps of batch %d at the headline shape" % (max(1, min(args.steps, 3)), args.cpu_batch)},
-                "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        return line
-
-    assert torch.cuda.is_available(), "bench.py (engine arm) needs a CUDA device: there is no CPU fallback"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    pg = None
-    if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=dev)
-    import simulgen_vae_b200 as sg
-    from simulgen_vae_b200 import kernels as K
-    from simulgen_vae_b200.trainer import Trainer
-    sg.set_precision(args.precision)
-    B = args.batch
-    model = build_engine_model(cfg, B, dev, seed=0)          # same seed on every rank = identical replicas
-    trainer = Trainer(model, lr=LR, alpha=ALPHA, process_group=pg)
-    n_pool = 4
-    pool = synthetic_batches(n_pool, B, cfg["num_node"], cfg["num_time"], dev, seed=1234 + rank)
-
+def _timed_steps(step_fn, n, world, dev):
+    """n calls of step_fn(i) between barriers; device time (CUDA events), max over ranks."""
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(n):
+        step_fn(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t)
+    return ms
 
-    # ---- warm-up -----------------------------------------------------------------------------------
+
+def _main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[n-1]; 2 = headline")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("SIMULGEN_BENCH_BATCH", "0")), help="per-GPU batch (0: the config's default)")
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--nodes", type=int, default=0, help="override the node count (debugging)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--batch-sweep", default=os.environ.get("SIMULGEN_BENCH_SWEEP", "16,32"),
+                    help="extra per-GPU batch sizes timed after the main run (config 2, 1 GPU; '' = none)")
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp16"],
+                    help="16-bit operand format of the tensor-core path (default: the engine's default, fp16)")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.nodes:
+        cfg["num_node"] = args.nodes
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    gflop = fwd_bwd_gflop_per_sample(cfg)
+    N, T = cfg["num_node"], cfg["num_time"]
+    workload = "config %d: %s (N=%d nodes, T=%d), fwd+bwd+AdamW" % (args.config, cfg["name"], N, T)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return None
+        steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
+        sps, kind, cores, sec = cpu_reference_run(cfg, args.cpu_batch, steps, warm)
+        sample = "%d steps of batch %d at the shape of config %d (fwd+bwd+AdamW, fp32, all host threads)" % (steps, args.cpu_batch, args.config)
+        return {"impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "batch": args.cpu_batch, "device": "host CPU"},
+                "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
+                "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+
+    assert torch.cuda.is_available(), "bench.py (engine arm) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    import simulgen_vae_b200 as sg
+    from simulgen_vae_b200 import augment, engine, kernels as K
+    from simulgen_vae_b200.trainer import Trainer
+    precision = args.precision or sg.DEFAULT_PRECISION
+    sg.set_precision(precision)
+    B = args.batch or cfg["batch"]
+    # replicas: every rank draws its own weights (different seeds on purpose); Trainer broadcasts rank 0's
+    model = build_engine_model(cfg, B, dev, seed=rank)
+    trainer = Trainer(model, lr=LR, alpha=ALPHA)
+    packed_mode = engine.loss_target(T) == "operand"
+
+    def make_pool(batch, n_pool, seed):
+        xs = synthetic_fields(n_pool * batch, N, T, dev, seed).view(n_pool, batch, N, T)
+        if not packed_mode:
+            return [xs[i] for i in range(n_pool)], xs[0].numel() * 4
+        pool = []
+        for i in range(n_pool):
+            op = torch.empty(1, N, batch, sg.tp_of(T), dtype=torch.float16 if precision == "fp16" else torch.bfloat16, device=dev)
+            K.pack_input(xs[i].contiguous(), op, T)
+            pool.append(engine.PackedBatch(op, T))
+        return pool, pool[0].operand.numel() * 2
+
+    def run_value(batch, steps, warmup, tr):
+        n_pool = 4
+        pool, nbytes = make_pool(batch, n_pool, 1234 + rank)
+        for i in range(warmup):
+            tr.step(pool[i % n_pool], beta=BETA, sample_offset=rank * batch)
+        ms = _timed_steps(lambda i: tr.step(pool[i % n_pool], beta=BETA, sample_offset=rank * batch), steps, world, dev)
+        return ms, nbytes
+
+    # ---- timed region: inputs resident in HBM -----------------------------------------------------------------------
+    n_pool = 4
+    pool, pool_bytes = make_pool(B, n_pool, 1234 + rank)
     for i in range(args.warmup):
         trainer.step(pool[i % n_pool], beta=BETA, sample_offset=rank * B)
-    barrier()
-    # ---- timed region: inputs resident in HBM ----------------------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     K.PROFILE = []
     l0 = K.LAUNCHES
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        trainer.step(pool[i % n_pool], beta=BETA, sample_offset=rank * B)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms = _timed_steps(lambda i: trainer.step(pool[i % n_pool], beta=BETA, sample_offset=rank * B), args.steps, world, dev)
     clocks = sampler.stop() if rank == 0 else None
     launches = K.LAUNCHES - l0
     prof = K.PROFILE
     K.PROFILE = None
     gemm_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in prof)
-    gemm_flops = sum(f for _, f, _, _ in prof) * (cfg["num_time"] / sg.tp_of(cfg["num_time"], "bf16"))   # valid columns only
+    gemm_flops = sum(f for _, f, _, _ in prof) * (T / sg.tp_of(T, "bf16"))   # valid columns only
     scalars = trainer.scalars()
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = float(t)
+    scaler = trainer.scaler_state()
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- e2e: host buffers, H2D of every batch + D2H of the loss inside the timed region -------------------
+    # ---- e2e ------------------------------------------------------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        host = [p.cpu().pin_memory() for p in pool[:2]]
-        dbuf = [torch.empty_like(pool[0]) for _ in range(2)]
+        k_e2e = max(args.steps, 20)
+        # (1) HOST buffers: pinned host batches (fp16 staging in fp16 mode - the loader keeps its host-side copy of the
+        # dataset in the operand format, halving the PCIe bytes; fp32 otherwise), H2D of every batch inside the timed
+        # region on a copy stream, double-buffered against the previous step; the loss is read back every step.
+        src = synthetic_fields(2 * B, N, T, dev, 4321 + rank).view(2, B, N, T)
+        host_dtype = torch.float16 if (packed_mode and precision == "fp16") else (torch.bfloat16 if packed_mode else torch.float32)
+        host = [src[i].to(host_dtype).cpu().pin_memory() for i in range(2)]
+        del src
+        dbuf = [torch.empty(B, N, T, dtype=host_dtype, device=dev) for _ in range(2)]
+        ops = [torch.empty(1, N, B, sg.tp_of(T), dtype=host_dtype, device=dev) for _ in range(2)] if packed_mode else None
         copy_stream = torch.cuda.Stream()
         done = [torch.cuda.Event() for _ in range(2)]
         free = [torch.cuda.Event() for _ in range(2)]
-        k_e2e = max(2, min(args.steps, 4))
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        with torch.cuda.stream(copy_stream):
-            dbuf[0].copy_(host[0], non_blocking=True)
-            done[0].record(copy_stream)
         losses = []
-        for i in range(k_e2e):
-            cur, nxt = i % 2, (i + 1) % 2
-            if i + 1 < k_e2e:
-                with torch.cuda.stream(copy_stream):
-                    if i >= 1:
-                        copy_stream.wait_event(free[nxt])
-                    dbuf[nxt].copy_(host[nxt], non_blocking=True)     # overlaps the step below
-                    done[nxt].record(copy_stream)
-            torch.cuda.current_stream().wait_event(done[cur])
-            out = trainer.step(dbuf[cur], beta=BETA, sample_offset=rank * B)
-            free[cur].record()
-            losses.append(out[0].to("cpu", non_blocking=True))        # D2H of the step's loss
-        t1.record()
-        barrier()
-        ms_e2e = t0.elapsed_time(t1)
-        if world > 1:
-            t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            ms_e2e = float(t)
-        e2e = {"value": world * B * k_e2e / (ms_e2e / 1e3), "unit": "samples/s",
-               "h2d_bytes_per_step": pool[0].numel() * 4, "d2h_bytes_per_step": 4, "steps": k_e2e,
-               "note": "pinned host fp32 batches, H2D double-buffered on a copy stream, loss read back every step"}
+
+        def host_loop():
+            with torch.cuda.stream(copy_stream):
+                dbuf[0].copy_(host[0], non_blocking=True)
+                done[0].record(copy_stream)
+            for i in range(k_e2e):
+                cur, nxt = i % 2, (i + 1) % 2
+                if i + 1 < k_e2e:
+                    with torch.cuda.stream(copy_stream):
+                        if i >= 1:
+                            copy_stream.wait_event(free[nxt])
+                        dbuf[nxt].copy_(host[nxt], non_blocking=True)     # overlaps the step below
+                        done[nxt].record(copy_stream)
+                torch.cuda.current_stream().wait_event(done[cur])
+                if packed_mode:
+                    K.pack_input(dbuf[cur], ops[cur], T)                  # [B, N, T] -> operand layout, on the device
+                    out = trainer.step(engine.PackedBatch(ops[cur], T), beta=BETA, sample_offset=rank * B)
+                else:
+                    out = trainer.step(dbuf[cur], beta=BETA, sample_offset=rank * B)
+                free[cur].record()
+                losses.append(out[0].to("cpu", non_blocking=True))        # D2H of the step's loss
+        ms_host = _timed_steps(lambda i: host_loop() if i == 0 else None, 1, world, dev)
+        h2d = dbuf[0].numel() * dbuf[0].element_size()
+        del dbuf, ops, host
+        torch.cuda.empty_cache()
+        # (2) RESIDENT dataset (the reference's load_all mode): P samples fp32 in HBM, per step the host draws the
+        # sampling order + augmentation decisions and sends them (a few hundred bytes); sg_assemble_batch gathers,
+        # augments and emits the packed operand one batch ahead on its own stream (augment.B200AugmentedLoader).
+        resident = None
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        P = cfg["samples"]
+        need = P * N * T * 4
+        if need > 0.55 * free_b:
+            P = max(2 * B, int(0.55 * free_b / (N * T * 4)))
+        try:
+            data = synthetic_fields(P, N, T, dev, 99 + rank)
+            idx = torch.arange(P)
+            loader = augment.B200AugmentedLoader(data, idx, B, shuffle=True, augment=True, seed=7, rank=0, world=1)
+            loader.yield_packed = packed_mode
+            loader.prefetch = True
+            state = {"it": iter(loader), "n": 0, "h2d": 0}
+            losses_r = []
+
+            def resident_step(i):
+                try:
+                    batch = next(state["it"])
+                except StopIteration:
+                    state["it"] = iter(loader)
+                    batch = next(state["it"])
+                if batch.shape[0] != B:                                   # ragged last batch of an epoch: skip it
+                    return resident_step(i)
+                out = trainer.step(batch, beta=BETA, sample_offset=rank * B)
+                losses_r.append(out[0].to("cpu", non_blocking=True))
+                state["n"] += 1
+            for i in range(2):
+                resident_step(i)
+            state["n"] = 0
+            ms_res = _timed_steps(resident_step, k_e2e, world, dev)
+            resident = {"value": world * B * state["n"] / (ms_res / 1e3), "unit": "samples/s", "steps": state["n"],
+                        "dataset_samples_in_hbm": P, "h2d_bytes_per_step": B * (2 * 4 + 4 * 4), "d2h_bytes_per_step": 4,
+                        "vs_value": (world * B * state["n"] / (ms_res / 1e3)) / value}
+            del data, loader, state
+        except torch.cuda.OutOfMemoryError as e:  # pragma: no cover
+            resident = {"value": None, "error": "dataset does not fit next to the model: %s" % str(e)[:80]}
+        e2e = {"value": world * B * k_e2e / (ms_host / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4, "steps": k_e2e, "h2d_gb_per_s_per_gpu": h2d * k_e2e / (ms_host / 1e3) / 1e9,
+               "note": "host-buffer mode is bound by the host -> device link: pinned host batches (%s [B, N, T]), H2D "
+                       "double-buffered on a copy stream, re-layout on the device, loss read back every step" % str(host_dtype).replace("torch.", ""),
+               "resident": resident}
+
+    # ---- other per-GPU batch sizes (the reference's Batch_size is 16) ----------------------------------------------------
+    sweep = []
+    if world == 1 and args.config == 2 and args.batch_sweep and not args.nodes:
+        del pool
+        torch.cuda.empty_cache()
+        for bs in [int(v) for v in args.batch_sweep.split(",") if v.strip()]:
+            if bs == B:
+                continue
+            ms_b, _ = run_value(bs, max(10, args.steps), args.warmup, trainer)
+            v = bs * max(10, args.steps) / (ms_b / 1e3)
+            sweep.append({"per_gpu_batch": bs, "value": v, "ms_per_step": ms_b / max(10, args.steps)})
 
     if rank != 0:
         if world > 1:
@@ -346,37 +463,57 @@ def _main():
         pass
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md sustained ~1.4 PF)"
+    hbm_peak = peaks.get("hbm_gbs", 6500.0)
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     traffic = None          # DRAM bytes per GEMM launch from the committed ncu capture of this very command line
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_traffic_b64.json")))
-        if tr.get("per_gpu_batch") == B and cfg["num_node"] == HEADLINE["num_node"]:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_gemm_traffic_b64.json")))
+        if tr.get("per_gpu_batch") == B and args.config == 2 and tr.get("precision") == precision:
             traffic = tr["gemm_dram_bytes_per_launch"]
     except Exception:
         pass
+    for s_ in sweep:
+        s_["step_tensor_frac"] = s_["value"] * gflop * 1e9 / (peak * 1e12)
+    if args.config == 4:
+        # static fields: the step streams the 2.29 G parameters (spectral-norm preparation 14 B, forward + dgrad reads of the
+        # 16-bit copy 4 B, weight-gradient write 4 B, optimiser 36 B per element) and is bound by HBM, not by the tensor pipe
+        n_par = sum(p.numel() for p in model.parameters())
+        step_bytes = 58.0 * n_par + B * N * sg.tp_of(T) * (2 + 2 + 2 + 2 + 4)
+        gbs = step_bytes / (ms / args.steps / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "whole step (weight / optimiser streams dominate at T = 1)", "achieved": gbs,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                    "algorithmic_bytes_per_step": step_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
+                    "gemm_tflops": achieved, "gemm_share_of_step": gemm_ms / ms if ms > 0 else None}
+    else:
+        roofline = {"bound": "tensor", "kernel": "conv_gemm_tc2_kernel (tcgen05 cta_group::2 implicit-GEMM fprop/dgrad/wgrad)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "algorithmic_flop_per_launch": gemm_flops / max(len(prof), 1),
+                    "peak_source": peak_src, "launches_timed": len(prof),
+                    "share_of_step": gemm_ms / ms if ms > 0 else None}
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision,
         "data": "synthetic",
         "config": {"workload": workload, "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
-                   "l2_policy": "inputs larger than L2 (%.0f MB per batch, 4 batches cycled)" % (pool[0].numel() * 4 / 1e6),
+                   "l2_policy": "inputs larger than L2 (%.0f MB per batch, 4 batches cycled)" % (pool_bytes / 1e6),
                    "gflop_per_sample_fwd_bwd": gflop, "loss": scalars[0], "grad_norm": scalars[4],
-                   "notes": "x_hat is not written to HBM by the training step (train.py:142 discards it); the recon layer's "
-                            "pre-norm output is stored in the 16-bit operand format; gpu_launches counts C-ABI calls (each >= 1 kernel)"},
+                   "resident_input_format": "engine.PackedBatch: fp16 operand [N, B, T] written by the loader kernel" if packed_mode else "fp32 [B, N, T]",
+                   "loss_scaler": scaler,
+                   "batch_sweep": sweep,
+                   "notes": "operands of the tensor-core path are %s with fp32 accumulation (tcgen05 kind::f16); x_hat is not written to "
+                            "HBM by the training step (train.py:142 discards it); pre-norm conv outputs and interior activation "
+                            "gradients are stored in the 16-bit operand format in fp16 mode; the loss target is the packed operand of "
+                            "x in fp16 mode (DESIGN.md section 3); gpu_launches counts C-ABI calls (each >= 1 kernel)" % precision},
         "clocks": clocks,
         "gpu_launches": launches,
         "step_tensor_frac": value / world * gflop * 1e9 / (peak * 1e12),
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_tc_kernel (tcgen05 implicit-GEMM fprop/dgrad/wgrad)",
-                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                     "algorithmic_flop_per_launch": gemm_flops / max(len(prof), 1),
-                     "peak_source": peak_src, "launches_timed": len(prof),
-                     "share_of_step": gemm_ms / ms if ms > 0 else None},
+        "roofline": roofline,
     }
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:           # the CPU baseline is timed on rank 0 of the 1-GPU run only
         try:
-            sps, kind, cores, sec = cpu_reference_run(cfg, args.cpu_batch, 2, 1)
+            sps, kind, cores, sec = cpu_reference_run(cfg if args.config in (2, 3) else CONFIGS[2], args.cpu_batch, 2, 1)
             line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": kind,
                                     "sample": "2 steps of batch %d at the headline shape (fwd+bwd+AdamW, fp32)" % args.cpu_batch}
         except Exception as e:  # pragma: no cover

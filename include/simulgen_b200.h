@@ -46,9 +46,11 @@ int sg_version(void);
 int sg_device_supported(void);
 
 /* ---- layout ------------------------------------------------------------------------------- */
-/* x[B][N][T] fp32 -> out[N][B][Tp] (dtype), zero gap.  Replaces the implicit layout the reference
- * feeds nn.Conv1d with (encoder.py:34, SimulGen-VAE.py:281-283). */
-int sg_pack_input(const float* x, void* out, int B, int N, int T, int Tp, int dtype, void* stream);
+/* x[B][N][T] -> out[N][B][Tp] (dtype), zero gap.  Replaces the implicit layout the reference
+ * feeds nn.Conv1d with (encoder.py:34, SimulGen-VAE.py:281-283).  x is fp32 (x_dtype = SG_F32, the reference's
+ * format) or already in the 16-bit operand format (x_dtype == dtype, T % 8 == 0 = Tp: a staging buffer kept in 16 bits
+ * so that the host -> device copy moves half the bytes; pure re-layout). */
+int sg_pack_input(const void* x, int x_dtype, void* out, int B, int N, int T, int Tp, int dtype, void* stream);
 /* out[B][C][T] fp32 <- in[C][B][Tp] fp32 (used for x_hat-style exports and tests). */
 int sg_unpack_f32(const float* in, float* out, int B, int C, int T, int Tp, void* stream);
 /* dst[i] (+)= alpha * src[i] (fp32), n elements. */

@@ -12,11 +12,22 @@ from simulgen_vae_b200 import kernels as K  # noqa: E402
 from simulgen_vae_b200.trainer import Trainer  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+MODE = sys.argv[2] if len(sys.argv) > 2 else "packed"         # "packed": engine.PackedBatch inputs (bench.py's value loop); "fp32"
 cfg = bench.HEADLINE
 dev = torch.device("cuda")
 model = bench.build_engine_model(cfg, B, dev)
 tr = Trainer(model, lr=1e-3, alpha=1e6)
 pool = bench.synthetic_batches(2, B, cfg["num_node"], cfg["num_time"], dev, 1)
+import simulgen_vae_b200 as sg  # noqa: E402
+from simulgen_vae_b200 import engine  # noqa: E402
+if MODE == "packed" and engine.loss_target(cfg["num_time"]) == "operand":
+    packed = []
+    for x in pool:
+        op = torch.empty(1, cfg["num_node"], B, sg.tp_of(cfg["num_time"]), dtype=torch.float16, device=dev)
+        K.pack_input(x.contiguous(), op, cfg["num_time"])
+        packed.append(engine.PackedBatch(op, cfg["num_time"]))
+    pool = packed
+print("precision %s, inputs: %s, per-GPU batch %d" % (sg.get_precision(), type(pool[0]).__name__, B))
 for i in range(3):
     tr.step(pool[i % 2])
 torch.cuda.synchronize()

@@ -21,7 +21,7 @@ P, I, F, D, L, U = c_void_p, c_int, c_float, c_double, c_ll, c_ull
 
 # name -> argtypes, in the order of include/simulgen_b200.h
 SIGNATURES = {
-    "sg_pack_input": [P, P, I, I, I, I, I, P],
+    "sg_pack_input": [P, I, P, I, I, I, I, I, P],
     "sg_unpack_f32": [P, P, I, I, I, I, P],
     "sg_axpy_f32": [P, P, F, L, I, P],
     "sg_cast_f32": [P, P, L, I, P],

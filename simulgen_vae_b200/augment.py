@@ -93,7 +93,9 @@ class B200AugmentedLoader:
         self.last_decisions = None
         self.emit_operand = False                         # also produce the packed 16-bit conv operand
         self.yield_packed = False                         # yield engine.PackedBatch (operand only, no fp32 batch)
+        self.prefetch = False                             # assemble batch i + 1 on a side stream while batch i is consumed
         self.last_operand = None
+        self._stream = None
 
     def __len__(self):
         n = len(self._index_loader)
@@ -142,28 +144,69 @@ class B200AugmentedLoader:
                         plan[3, sl].numpy().astype(np.int64), plan[4, sl].numpy().astype(np.float32),
                         plan[5, sl].numpy().astype(np.float32))
 
+    def _assemble(self, idx, decisions):
+        """Launch sg_assemble_batch for one batch on the current stream; returns (what the loader yields, operand)."""
+        noise, scale, other, lam, om = decisions
+        dev = self.data.device
+        B = idx.numel()
+        self.last_decisions = dict(index=idx.clone(), noise=noise, scale=scale, other=other, lam=lam)
+        table = torch.from_numpy(np.stack([noise, scale, lam, om]).astype(np.float32)).to(dev, non_blocking=True)
+        ids = torch.stack([idx, torch.from_numpy(other)]).to(torch.int32).to(dev, non_blocking=True)
+        inj = None
+        if self.injected_noise is not None and (noise > 0).any():
+            inj = self.injected_noise(noise, tuple(self.data.shape[1:])).to(dev)
+        from .engine import PackedBatch, get_precision, loss_target, tp_of
+        N, T = self.data.shape[1], self.data.shape[2]
+        packed_only = self.yield_packed and loss_target(T) == "operand"
+        out = None if packed_only else torch.empty((B, N, T), dtype=torch.float32, device=dev)
+        op = None
+        if self.emit_operand or packed_only:
+            op16 = torch.float16 if get_precision() == "fp16" else torch.bfloat16
+            op = torch.empty(1, N, B, tp_of(T, "bf16"), dtype=op16, device=dev)
+        K.assemble_batch(self.data, ids, table, inj, out, self.seed, self.draws, op)
+        self.draws += 1
+        return (PackedBatch(op, T) if packed_only else out), op, (ids, table, inj)
+
     def __iter__(self):
         dev = self.data.device
-        for idx, (noise, scale, other, lam, om) in self._global_batches():
-            B = idx.numel()
-            self.last_decisions = dict(index=idx.clone(), noise=noise, scale=scale, other=other, lam=lam)
-            table = torch.from_numpy(np.stack([noise, scale, lam, om]).astype(np.float32)).to(dev, non_blocking=True)
-            ids = torch.stack([idx, torch.from_numpy(other)]).to(torch.int32).to(dev, non_blocking=True)
-            inj = None
-            if self.injected_noise is not None and (noise > 0).any():
-                inj = self.injected_noise(noise, tuple(self.data.shape[1:])).to(dev)
-            from .engine import PackedBatch, get_precision, loss_target, tp_of
-            N, T = self.data.shape[1], self.data.shape[2]
-            packed_only = self.yield_packed and loss_target(T) == "operand"
-            out = None if packed_only else torch.empty((B, N, T), dtype=torch.float32, device=dev)
-            op = None
-            if self.emit_operand or packed_only:
-                op16 = torch.float16 if get_precision() == "fp16" else torch.bfloat16
-                op = torch.empty(1, N, B, tp_of(T, "bf16"), dtype=op16, device=dev)
-            K.assemble_batch(self.data, ids, table, inj, out, self.seed, self.draws, op)
-            self.last_operand = op                        # Trainer.step(x, packed=loader.last_operand)
-            self.draws += 1
-            yield PackedBatch(op, T) if packed_only else out
+        if not (self.prefetch and dev.type == "cuda"):
+            for idx, decisions in self._global_batches():
+                batch, op, _ = self._assemble(idx, decisions)
+                self.last_operand = op                    # Trainer.step(x, packed=loader.last_operand)
+                yield batch
+            return
+        # One batch ahead: the gather / augmentation kernel of batch i + 1 is HBM-bound and runs on its own stream
+        # underneath the (tensor-core-bound) training step of batch i.  The dataset is read-only and every batch is a
+        # fresh allocation, so the side stream never waits for the consumer; the consumer waits for the batch's event.
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev)
+        side = self._stream
+
+        def launch(idx, decisions):
+            with torch.cuda.stream(side):
+                batch, op, keep = self._assemble(idx, decisions)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return batch, op, ev, keep
+
+        pending = None
+        for idx, decisions in self._global_batches():
+            nxt = launch(idx, decisions)
+            if pending is not None:
+                yield self._hand_over(pending)
+            pending = nxt
+        if pending is not None:
+            yield self._hand_over(pending)
+
+    def _hand_over(self, item):
+        batch, op, ev, keep = item
+        cur = torch.cuda.current_stream(self.data.device)
+        cur.wait_event(ev)
+        for t in (op, batch if isinstance(batch, torch.Tensor) else None) + tuple(keep):
+            if t is not None:
+                t.record_stream(cur)                      # allocated on the loader's stream, consumed on the caller's
+        self.last_operand = op
+        return batch
 
 
 def create_augmented_dataloaders(x_data, batch_size, load_all=False, augmentation_config=None, val_split=0.2,

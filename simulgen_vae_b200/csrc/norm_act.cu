@@ -74,6 +74,20 @@ __global__ void __launch_bounds__(kThreads) pack_input_kernel(const float* __res
     }
 }
 
+// the same re-layout for a batch that is already in the 16-bit operand format ([B][N][T], e.g. a host staging buffer
+// kept in fp16 so that the host -> device copy moves half the bytes); T % 8 == 0: whole 16-byte segments
+__global__ void __launch_bounds__(kThreads) pack_input16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                                int B, int N, int T) {
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)N * B, wstride = (long long)gridDim.x * kWarpsPerBlock;
+    for (long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += wstride) {
+        int n = (int)(row / B), b = (int)(row % B);
+        const uint4* src = reinterpret_cast<const uint4*>(x + ((long long)b * N + n) * T);
+        uint4* dst = reinterpret_cast<uint4*>(out + row * T);
+        for (int seg = lane; seg < T / 8; seg += 32) dst[seg] = __ldg(src + seg);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) unpack_f32_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                               int B, int C, int T, int Tp) {
     long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);  // row = c * B + b
@@ -197,7 +211,9 @@ __global__ void __launch_bounds__(kThreads, 3)
 gn_act_fwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                   const float* __restrict__ beta, const RT* __restrict__ res, float res_scale, OT* __restrict__ out_op,
                   long long pstride, float* __restrict__ out_f32, int C, int B, int T, int Tp, int G) {
-    constexpr int R = RowsInFlight<YT, YT>::value;
+    // multi-plane writers hold 12 neighbour values per row for the shifted copies: 2 rows in flight keep them in registers
+    // (measured, gpurun_out/r2_stream_gn_{a,c}.txt: 5 planes 0.185 ms with 1 row, 0.211 ms with 4 rows and spills)
+    constexpr int R = PLANES > 1 ? 2 : RowsInFlight<YT, YT>::value;
     constexpr int planes = PLANES;
     extern __shared__ float sg_rows[];
     const int lane = threadIdx.x & 31;
@@ -1356,13 +1372,21 @@ using namespace sg;
 
 extern "C" {
 
-int sg_pack_input(const float* x, void* out, int B, int N, int T, int Tp, int dtype, void* stream) {
+int sg_pack_input(const void* xv, int x_dtype, void* out, int B, int N, int T, int Tp, int dtype, void* stream) {
     SG_CHECK_OP16(dtype);
+    SG_CHECK_OP16(x_dtype);
     SG_REQUIRE(Tp % 8 == 0 && Tp >= T, "pack_input: bad Tp=%d for T=%d", Tp, T);
     long long rows = (long long)N * B;
     int grid = persistent_grid(rows) * 2;
-    bool vec = (T % 4 == 0) && aligned16(x);
     cudaStream_t st = as_stream(stream);
+    if (is_op16(x_dtype)) {
+        SG_REQUIRE(x_dtype == dtype && T % 8 == 0 && Tp == T && aligned16(xv) && aligned16(out),
+                   "pack_input: a 16-bit source needs the same operand format, T %% 8 == 0 and 16-byte alignment");
+        pack_input16_kernel<<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)xv, (__nv_bfloat16*)out, B, N, T);
+        return check_launch("pack_input");
+    }
+    const float* x = (const float*)xv;
+    bool vec = (T % 4 == 0) && aligned16(x);
 #define SG_PACK(OT, VEC) pack_input_kernel<OT, VEC><<<grid, kThreads, 0, st>>>(x, (OT*)out, B, N, T, Tp)
     if (is_op16(dtype)) { if (vec) SG_PACK(__nv_bfloat16, true); else SG_PACK(__nv_bfloat16, false); }
     else                  { if (vec) SG_PACK(float, true); else SG_PACK(float, false); }

@@ -102,11 +102,12 @@ def _f32(t, name):
 
 # ---- layout -------------------------------------------------------------------------------------
 def pack_input(x, out, T):
-    """out: operand [1, N, B, Tp]."""
+    """x [B, N, T] fp32 (or already the operand dtype: pure re-layout); out: operand [1, N, B, Tp]."""
     B, N, _ = x.shape
     Tp = out.shape[3]
-    assert out.shape[0] == 1
-    _call("sg_pack_input", _p(_f32(x, "x")), _p(out), B, N, T, Tp, _dt(out), _stream())
+    assert out.shape[0] == 1 and (x.dtype == torch.float32 or x.dtype == out.dtype)
+    od = _dt(out)
+    _call("sg_pack_input", _p(x), od if x.dtype != torch.float32 else SG_F32, _p(out), B, N, T, Tp, od, _stream())
 
 
 def unpack_f32(inp, out, T):

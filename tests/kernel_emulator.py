@@ -42,7 +42,7 @@ def center(t):
 
 # ---- layout -------------------------------------------------------------------------------------
 def pack_input(x, out, T):
-    write_planes(out, x.permute(1, 0, 2), T)
+    write_planes(out, x.float().permute(1, 0, 2), T)
 
 
 def unpack_f32(inp, out, T):
