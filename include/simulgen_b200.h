@@ -198,9 +198,11 @@ int sg_adamw_step(float* p, const float* g, float* m, float* v, long long n, flo
  *     lambda * scale * (data[idx] + noise_level * eps) + (1 - lambda) * data[partner]
  * (reference order: noise, scaling, mixup; every product and sum rounded separately like the ATen sequence).  eps: injected_noise [B][N][T] if given, else Philox normals keyed on
  * (seed, draw, dataset index, element).  operand (optional): bf16 [N][B][Tp] copy for the first encoder conv. */
+/* out may be NULL (operand-only batch).  blocks_per_sm: resident thread blocks per SM (0 = default 16; a loader that
+ * prefetches underneath the training step passes 2 so that the step's GEMM CTAs still fit on every SM). */
 int sg_assemble_batch(const float* data, int P, const int* ids, const float* table, const float* injected_noise,
                       float* out, void* operand, int B, int N, int T, int Tp, unsigned long long seed,
-                      unsigned long long draw, void* stream);
+                      unsigned long long draw, int blocks_per_sm, void* stream);
 
 /* ---- batched spectral-norm preparation: every layer of a sub-network in five launches ---------------
  * Same arithmetic as sg_sn_power_iter + sg_sn_pack_weight per layer (spectral_norm.py:62-114): the power

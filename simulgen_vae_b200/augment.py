@@ -163,7 +163,8 @@ class B200AugmentedLoader:
         if self.emit_operand or packed_only:
             op16 = torch.float16 if get_precision() == "fp16" else torch.bfloat16
             op = torch.empty(1, N, B, tp_of(T, "bf16"), dtype=op16, device=dev)
-        K.assemble_batch(self.data, ids, table, inj, out, self.seed, self.draws, op)
+        K.assemble_batch(self.data, ids, table, inj, out, self.seed, self.draws, op,
+                         blocks_per_sm=2 if (self.prefetch and dev.type == "cuda") else 0)
         self.draws += 1
         return (PackedBatch(op, T) if packed_only else out), op, (ids, table, inj)
 

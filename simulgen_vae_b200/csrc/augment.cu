@@ -105,14 +105,19 @@ using namespace sg;
 
 extern "C" int sg_assemble_batch(const float* data, int P, const int* ids, const float* table, const float* injected_noise,
                                  float* out, void* operand, int B, int N, int T, int Tp, unsigned long long seed,
-                                 unsigned long long draw, void* stream) {
+                                 unsigned long long draw, int blocks_per_sm, void* stream) {
     SG_REQUIRE(B > 0 && N > 0 && T > 0 && P > 0, "assemble_batch: bad shape");
     SG_REQUIRE(out != nullptr || operand != nullptr, "assemble_batch: neither an fp32 batch nor an operand to write");
     SG_REQUIRE(operand == nullptr || (Tp % 8 == 0 && Tp >= T), "assemble_batch: bad Tp=%d for T=%d", Tp, T);
     if (operand == nullptr) Tp = (T + 7) / 8 * 8;
     const bool vec = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    // blocks_per_sm (0 = 16): a prefetching loader runs this kernel on its own stream UNDERNEATH the training step; a
+    // small resident footprint (2 blocks = 512 threads per SM) leaves the thread slots and registers the persistent
+    // tensor-core GEMM CTAs need to start next to it - with the full grid the SMs fill up with these blocks first and
+    // the step waits for the whole gather (measured: resident e2e 0.906 of the device-resident rate, r2_bench_full_d.json)
+    if (blocks_per_sm <= 0 || blocks_per_sm > 16) blocks_per_sm = 16;
     long long blocks = cdiv((long long)B * N, kAugWarps);
-    int grid = (int)(blocks < 148LL * 16 ? blocks : 148LL * 16);
+    int grid = (int)(blocks < 148LL * blocks_per_sm ? blocks : 148LL * blocks_per_sm);
     cudaStream_t st = as_stream(stream);
     if (vec)
         assemble_batch_kernel<true><<<grid, kAugWarps * 32, 0, st>>>(data, ids, table, injected_noise, out, (__nv_bfloat16*)operand,

@@ -431,7 +431,7 @@ def sn_prepare(plan, training):
 
 
 # ---- batch assembly + augmentation --------------------------------------------------------------
-def assemble_batch(data, ids, table, injected_noise, out, seed, draw, operand=None):
+def assemble_batch(data, ids, table, injected_noise, out, seed, draw, operand=None, blocks_per_sm=0):
     """data fp32 [P, N, T]; ids int32 [2, B]; table fp32 [4, B]; out fp32 [B, N, T] (None: operand only); operand:
     optional 16-bit [1, N, B, Tp] (the packed input of the first encoder conv, bf16 or fp16 like the engine's precision
     mode)."""
@@ -444,7 +444,7 @@ def assemble_batch(data, ids, table, injected_noise, out, seed, draw, operand=No
         assert operand.dtype in OP16 and tuple(operand.shape[:3]) == (1, N, B)
         _dt(operand)                     # selects the library build for this 16-bit format
     _call("sg_assemble_batch", _p(_f32(data, "data")), P, _p(ids), _p(_f32(table, "table")), _p(_f32(injected_noise, "noise")),
-          _p(_f32(out, "out")), _p(operand), B, N, T, Tp, int(seed) & (2 ** 64 - 1), int(draw), _stream())
+          _p(_f32(out, "out")), _p(operand), B, N, T, Tp, int(seed) & (2 ** 64 - 1), int(draw), int(blocks_per_sm), _stream())
 
 
 # ---- preprocessing scan ------------------------------------------------------------------

@@ -435,7 +435,7 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale
     p.addcdiv_(m, denom, value=-lr / bc1)
 
 
-def assemble_batch(data, ids, table, injected_noise, out, seed, draw, operand=None):
+def assemble_batch(data, ids, table, injected_noise, out, seed, draw, operand=None, blocks_per_sm=0):
     B = ids.shape[1]
     idx, other = ids[0].long(), ids[1].long()
     nl, sc, lam, om = table[0], table[1], table[2], table[3]

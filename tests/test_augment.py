@@ -117,7 +117,10 @@ def test_trainer_step_with_packed_operand_equals_plain_step():
                 tr.step(x, beta=g["beta"], packed=train.last_operand)
         res.append({k: v.detach().clone() for k, v in m.state_dict().items()})
     for k in res[0]:
-        assert rel_l2(res[0][k], res[1][k]) < 2e-2, k          # bf16 mode: see test_trainer_fused_step_equals_per_tensor_path
+        # 16-bit modes: see test_trainer_fused_step_equals_per_tensor_path.  Vectors (biases, GroupNorm affine) start at 0 / 1
+        # and move by ~lr * sign(gradient) in the first Adam steps: the summation order of the atomics can flip an entry
+        tol = 0.3 if res[0][k].dim() == 1 else 2e-2
+        assert rel_l2(res[0][k], res[1][k]) < tol, k
     w = "decoder.recon.0.weight_orig"
     assert rel_l2(res[0][w], res[1][w]) < 1e-4
 

@@ -226,6 +226,31 @@ def test_baseline_config_shapes_parity(case, precision):
         assert worst_g < 6e-2, [r for r in greport if r[1] >= 6e-2]
 
 
+FULL_SIZE = {
+    # BASELINE.json configs[2], [3], [4] at their REAL node / time counts (batch reduced: parity does not depend on it)
+    "config3_large_95008": dict(latent_dim=32, hierarchical_dim=8, enc=[1024, 512, 256, 128], num_node=95008, num_time=200,
+                                small=False, batch=2, lossfun="MSE"),
+    "config4_static_1000000": dict(latent_dim=32, hierarchical_dim=8, enc=[1024, 512, 256, 128], num_node=1000000, num_time=1,
+                                   small=True, batch=8, lossfun="MSE"),
+    "config5_multivar_380032x400": dict(latent_dim=32, hierarchical_dim=8, enc=[1024, 512, 256, 128], num_node=380032,
+                                        num_time=400, small=True, batch=1, lossfun="MSE"),
+}
+
+
+@pytest.mark.parametrize("case", sorted(FULL_SIZE))
+def test_full_size_configs_parity_default_precision(case):
+    """the other BASELINE configs at real size (--size=large on 95008 nodes: 496 M parameters; static
+    T = 1 on 10^6 nodes: 2.29 G parameters; num_var = 4 folded into 380032 nodes with T = 400: rows longer than 256
+    elements) in the precision bench.py runs by default - north_star's 1e-2 for every activation and every gradient."""
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b < 120e9:
+        pytest.skip("needs a 180 GB device")
+    report, greport, worst_a, worst_g, med = _per_layer_report(FULL_SIZE[case], sg.DEFAULT_PRECISION, tag=case)
+    torch.cuda.empty_cache()
+    assert worst_a < 1e-2, [r for r in report if r[1] >= 1e-2]
+    assert worst_g < 1e-2, [r for r in greport if r[1] >= 1e-2]
+
+
 def test_elbo_curve_100_steps_within_1_percent():
     """train.py:139-168 step semantics for 100 steps on the toy fixture; bf16 engine vs the
     reference's recorded curve (same data, same eps stream, torch AdamW on both sides)."""
