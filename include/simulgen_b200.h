@@ -98,6 +98,9 @@ int sg_conv_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_pl
                   int Cin, int Cin_p, int Cout, int k, int R, int accumulate, int dtype, void* stream);
 /* 1 when a GEMM with M output rows (fprop: Cout, dgrad: Cin) runs on the CTA-pair kernel and can store 16 bits */
 int sg_conv_out16_ok(int M);
+/* Upper bound on the SMs the persistent GEMM grids of the following launches occupy (0 = all).  The data-parallel
+ * trainer lowers it while NCCL collectives overlap the backward pass so that their kernels find free SMs. */
+int sg_set_sm_limit(int sms);
 int sg_conv_wgrad(const void* dy, int dy_planes, long long dy_plane_stride, const void* act, int act_planes,
                   long long act_plane_stride, float* dwg, int Cin, int Cin_p, int Cout, int k, int R, int dtype,
                   void* stream);

@@ -32,6 +32,7 @@ SIGNATURES = {
     "sg_conv_fprop_gn": [P, P, I, L, P, P, I, I, I, I, I, I, I, I, I, P, P, P, I, P],
     "sg_conv_dgrad": [P, P, I, L, P, I, I, I, I, I, I, I, I, P],
     "sg_conv_out16_ok": [I],
+    "sg_set_sm_limit": [I],
     "sg_conv_wgrad": [P, I, L, P, I, L, P, I, I, I, I, I, I, P],
     "sg_gn_stats": [P, P, P, I, I, I, I, I, P],
     "sg_gn_act_fwd": [P, I, P, P, P, P, I, F, I, I, P, I, L, P, I, I, I, I, I, I, P],

@@ -96,6 +96,7 @@ class B200AugmentedLoader:
         self.prefetch = False                             # assemble batch i + 1 on a side stream while batch i is consumed
         self.last_operand = None
         self._stream = None
+        self._ring = {}
 
     def __len__(self):
         n = len(self._index_loader)
@@ -144,8 +145,9 @@ class B200AugmentedLoader:
                         plan[3, sl].numpy().astype(np.int64), plan[4, sl].numpy().astype(np.float32),
                         plan[5, sl].numpy().astype(np.float32))
 
-    def _assemble(self, idx, decisions):
-        """Launch sg_assemble_batch for one batch on the current stream; returns (what the loader yields, operand)."""
+    def _assemble(self, idx, decisions, slot=None):
+        """Launch sg_assemble_batch for one batch on the current stream; returns (what the loader yields, operand).
+        slot: ring slot whose preallocated output buffers are used (prefetch mode), else fresh allocations."""
         noise, scale, other, lam, om = decisions
         dev = self.data.device
         B = idx.numel()
@@ -158,13 +160,22 @@ class B200AugmentedLoader:
         from .engine import PackedBatch, get_precision, loss_target, tp_of
         N, T = self.data.shape[1], self.data.shape[2]
         packed_only = self.yield_packed and loss_target(T) == "operand"
-        out = None if packed_only else torch.empty((B, N, T), dtype=torch.float32, device=dev)
-        op = None
-        if self.emit_operand or packed_only:
-            op16 = torch.float16 if get_precision() == "fp16" else torch.bfloat16
-            op = torch.empty(1, N, B, tp_of(T, "bf16"), dtype=op16, device=dev)
+        op16 = torch.float16 if get_precision() == "fp16" else torch.bfloat16
+        want_op = self.emit_operand or packed_only
+        if slot is not None:
+            ring = self._ring.setdefault(slot, {})
+            key = (B, packed_only, want_op, op16)
+            if ring.get("key") != key:                    # (re)allocate this slot's buffers: first use or a ragged batch
+                ring.clear()
+                ring["key"] = key
+                ring["out"] = None if packed_only else torch.empty((B, N, T), dtype=torch.float32, device=dev)
+                ring["op"] = torch.empty(1, N, B, tp_of(T, "bf16"), dtype=op16, device=dev) if want_op else None
+            out, op = ring["out"], ring["op"]
+        else:
+            out = None if packed_only else torch.empty((B, N, T), dtype=torch.float32, device=dev)
+            op = torch.empty(1, N, B, tp_of(T, "bf16"), dtype=op16, device=dev) if want_op else None
         K.assemble_batch(self.data, ids, table, inj, out, self.seed, self.draws, op,
-                         blocks_per_sm=2 if (self.prefetch and dev.type == "cuda") else 0)
+                         blocks_per_sm=2 if slot is not None else 0)
         self.draws += 1
         return (PackedBatch(op, T) if packed_only else out), op, (ids, table, inj)
 
@@ -177,37 +188,47 @@ class B200AugmentedLoader:
                 yield batch
             return
         # One batch ahead: the gather / augmentation kernel of batch i + 1 is HBM-bound and runs on its own stream
-        # underneath the (tensor-core-bound) training step of batch i.  The dataset is read-only and every batch is a
-        # fresh allocation, so the side stream never waits for the consumer; the consumer waits for the batch's event.
+        # underneath the (tensor-core-bound) training step of batch i, with a small resident footprint (2 thread blocks
+        # per SM) so that the step's persistent GEMM CTAs still fit next to it.  Output buffers come from a ring of 3
+        # slots owned by the loader (no allocator traffic, no cudaMalloc in steady state): a yielded batch stays valid
+        # until the second-next batch is requested.  Slot reuse is ordered by events: the kernel that refills the slot of
+        # batch i - 2 waits for the marker the consumer's stream recorded when batch i - 1 was handed over, i.e. for
+        # everything that consumed batch i - 2.
         if self._stream is None:
             self._stream = torch.cuda.Stream(device=dev)
         side = self._stream
+        markers = {}
+        state = {"n": 0}
 
         def launch(idx, decisions):
+            i = state["n"]
+            state["n"] += 1
             with torch.cuda.stream(side):
-                batch, op, keep = self._assemble(idx, decisions)
+                if i - 2 in markers:
+                    side.wait_event(markers.pop(i - 2))
+                batch, op, keep = self._assemble(idx, decisions, slot=i % 3)
                 ev = torch.cuda.Event()
                 ev.record(side)
-            return batch, op, ev, keep
+            return i, batch, op, ev, keep
+
+        def hand_over(item):
+            i, batch, op, ev, keep = item
+            cur = torch.cuda.current_stream(dev)
+            m = torch.cuda.Event()
+            m.record(cur)                                 # everything issued so far (the consumers of batch i - 1) ...
+            markers[i] = m                                # ... must finish before slot (i - 1) % 3 is written for batch i + 2
+            cur.wait_event(ev)
+            self.last_operand = op
+            return batch
 
         pending = None
         for idx, decisions in self._global_batches():
             nxt = launch(idx, decisions)
             if pending is not None:
-                yield self._hand_over(pending)
+                yield hand_over(pending)
             pending = nxt
         if pending is not None:
-            yield self._hand_over(pending)
-
-    def _hand_over(self, item):
-        batch, op, ev, keep = item
-        cur = torch.cuda.current_stream(self.data.device)
-        cur.wait_event(ev)
-        for t in (op, batch if isinstance(batch, torch.Tensor) else None) + tuple(keep):
-            if t is not None:
-                t.record_stream(cur)                      # allocated on the loader's stream, consumed on the caller's
-        self.last_operand = op
-        return batch
+            yield hand_over(pending)
 
 
 def create_augmented_dataloaders(x_data, batch_size, load_all=False, augmentation_config=None, val_split=0.2,

@@ -41,7 +41,7 @@ assemble_batch_kernel(const float* __restrict__ data, const int* __restrict__ id
             F8 v;
             if (t0 < T) {
                 if (VEC && t0 + 8 <= T) {
-                    float4 a = __ldg(reinterpret_cast<const float4*>(src + t0)), c = __ldg(reinterpret_cast<const float4*>(src + t0 + 4));
+                    float4 a = __ldcs(reinterpret_cast<const float4*>(src + t0)), c = __ldcs(reinterpret_cast<const float4*>(src + t0 + 4));
                     v.v[0] = a.x; v.v[1] = a.y; v.v[2] = a.z; v.v[3] = a.w; v.v[4] = c.x; v.v[5] = c.y; v.v[6] = c.z; v.v[7] = c.w;
                 } else {
 #pragma unroll
@@ -68,7 +68,7 @@ assemble_batch_kernel(const float* __restrict__ data, const int* __restrict__ id
                 if (src2 != nullptr) {
                     F8 w;
                     if (VEC && t0 + 8 <= T) {
-                        float4 a = __ldg(reinterpret_cast<const float4*>(src2 + t0)), c = __ldg(reinterpret_cast<const float4*>(src2 + t0 + 4));
+                        float4 a = __ldcs(reinterpret_cast<const float4*>(src2 + t0)), c = __ldcs(reinterpret_cast<const float4*>(src2 + t0 + 4));
                         w.v[0] = a.x; w.v[1] = a.y; w.v[2] = a.z; w.v[3] = a.w; w.v[4] = c.x; w.v[5] = c.y; w.v[6] = c.z; w.v[7] = c.w;
                     } else {
 #pragma unroll

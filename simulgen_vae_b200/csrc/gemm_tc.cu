@@ -285,6 +285,12 @@ static int make_map_wg(CUtensorMap* m, const void* base, int Cin_p, int Cout, in
     return 0;
 }
 
+// SMs the persistent GEMM grids may occupy.  Data parallel: NCCL's kernels need SMs of their own while backward runs; a
+// persistent grid sized for all 148 SMs leaves its displaced CTAs waiting for the collective to finish, with their share
+// of the tiles (static round-robin) - the whole GEMM then ends when the collective does.  sg_set_sm_limit(148 - r) keeps
+// r SMs free for the collectives for as long as they are in flight (Trainer: backward only).  0 = no limit.
+static int g_sm_limit = 0;
+
 static int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -293,6 +299,7 @@ static int num_sms() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
+    if (g_sm_limit > 0 && g_sm_limit < n) return g_sm_limit & ~1;
     return n;
 }
 
@@ -530,6 +537,12 @@ int sg_conv_dgrad(const void* wg, const void* dy, int dy_planes, long long dy_ps
     }
     return tc_dgrad(wg, dy, dy_planes, dy_pstride, dx, is_op16(dx_dtype) ? 1 : 0, Cin, Cin_p, Cout, k, R, accumulate,
                     as_stream(stream));
+}
+
+int sg_set_sm_limit(int sms) {
+    SG_REQUIRE(sms >= 0, "set_sm_limit: negative SM count");
+    g_sm_limit = (sms > 0 && sms < 16) ? 16 : sms;
+    return 0;
 }
 
 /* 1 when a GEMM with M output rows runs on the CTA-pair kernel, i.e. can store a 16-bit output (fprop: M = Cout,

@@ -185,34 +185,40 @@ template <int OMAX>
 __global__ void __launch_bounds__(128)
 head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ sigma,
                 const float* __restrict__ dout, float* __restrict__ dwn, float* __restrict__ dh, int dh_accumulate,
-                int C, int B, int T, int Tp, int O) {
-    extern __shared__ float sdout[];  // [B][O]
-    for (int i = threadIdx.x; i < B * O; i += blockDim.x) sdout[i] = dout[i];
-    __syncthreads();
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int c = blockIdx.y;
-    if (t >= T) return;
-    float inv = 1.f / sigma[0];
+                int C, int B, int T, int Tp, int O, int Bc) {
+    extern __shared__ float sdout[];  // [Bc][O]: the upstream gradient, staged in chunks of Bc samples
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    const bool active = t < T;
+    const float inv = 1.f / sigma[0];
     float acc[OMAX], wv[OMAX];
 #pragma unroll
     for (int o = 0; o < OMAX; ++o) {
         acc[o] = 0.f;
-        wv[o] = o < O ? __ldg(w + (long long)o * C * T + (long long)c * T + t) * inv : 0.f;
+        wv[o] = (active && o < O) ? __ldg(w + (long long)o * C * T + (long long)c * T + t) * inv : 0.f;
     }
-    for (int b = 0; b < B; ++b) {
-        long long hi = ((long long)c * B + b) * Tp + t;
-        float hv = h[hi];
-        float d = 0.f;
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+        const int nb = min(Bc, B - b0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb * O; i += blockDim.x) sdout[i] = dout[(long long)b0 * O + i];
+        __syncthreads();
+        if (!active) continue;
+        for (int b = 0; b < nb; ++b) {
+            long long hi = ((long long)c * B + b0 + b) * Tp + t;
+            float hv = h[hi];
+            float d = 0.f;
 #pragma unroll
-        for (int o = 0; o < OMAX; ++o) {
-            if (o < O) {
-                float g = sdout[b * O + o];
-                acc[o] += g * hv;
-                d += wv[o] * g;
+            for (int o = 0; o < OMAX; ++o) {
+                if (o < O) {
+                    float g = sdout[b * O + o];
+                    acc[o] += g * hv;
+                    d += wv[o] * g;
+                }
             }
+            if (dh != nullptr) dh[hi] = dh_accumulate ? dh[hi] + d : d;
         }
-        if (dh != nullptr) dh[hi] = dh_accumulate ? dh[hi] + d : d;
     }
+    if (!active) return;
 #pragma unroll
     for (int o = 0; o < OMAX; ++o)
         if (o < O) dwn[(long long)o * C * T + (long long)c * T + t] = acc[o];
@@ -554,14 +560,15 @@ int sg_head_fwd(const float* h, const float* w_orig, const float* sigma, const f
 int sg_head_bwd(const float* h, const float* w_orig, const float* sigma, const float* dout, float* dwn, float* dbias,
                 float* dh, int dh_accumulate, int C, int B, int T, int Tp, int O, void* stream) {
     SG_REQUIRE(O <= 64, "head_bwd: O=%d > 64 unsupported", O);
-    SG_REQUIRE((size_t)B * O * sizeof(float) <= 48 * 1024, "head_bwd: B*O too large for shared memory");
     cudaStream_t st = as_stream(stream);
     dim3 grid((unsigned)cdiv(T, 128), C);
-    size_t sm = sizeof(float) * B * O;
+    // the upstream gradient [B][O] is staged in shared memory in chunks of Bc samples (large-batch static fields: B = 512)
+    const int Bc = (int)((size_t)B * O * sizeof(float) <= 32 * 1024 ? B : (32 * 1024) / (O * sizeof(float)));
+    size_t sm = sizeof(float) * Bc * O;
     if (O <= 8)
-        head_bwd_kernel<8><<<grid, 128, sm, st>>>(h, w_orig, sigma, dout, dwn, dh, dh_accumulate, C, B, T, Tp, O);
+        head_bwd_kernel<8><<<grid, 128, sm, st>>>(h, w_orig, sigma, dout, dwn, dh, dh_accumulate, C, B, T, Tp, O, Bc);
     else
-        head_bwd_kernel<64><<<grid, 128, sm, st>>>(h, w_orig, sigma, dout, dwn, dh, dh_accumulate, C, B, T, Tp, O);
+        head_bwd_kernel<64><<<grid, 128, sm, st>>>(h, w_orig, sigma, dout, dwn, dh, dh_accumulate, C, B, T, Tp, O, Bc);
     colsum_kernel<<<(O + 63) / 64, 64, 0, st>>>(dout, dbias, B, O);
     return check_launch("head_bwd");
 }

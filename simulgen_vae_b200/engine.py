@@ -219,17 +219,20 @@ class GradSink:
             raise RuntimeError("simulgen_b200: gradient size changed between steps")
         return self.vecs[off:off + n0]
 
-    def commit_weight(self, prep, dwg):
-        """Called once the wgrad GEMM writing `dwg` (a weight_buffer) has been enqueued."""
+    def commit_weight(self, prep, dwg, upto=None):
+        """Called once the wgrad GEMM writing `dwg` (a weight_buffer) has been enqueued.  upto: only the first `upto`
+        elements of the buffer are final so far (a weight gradient produced in row chunks, so that the all-reduce of the
+        first chunks overlaps the GEMMs of the later ones)."""
         key = id(prep.w)
         if key not in self.items:
             self.items[key] = dict(param=prep.w, g=dwg, u=prep.u, vv=prep.v, sigma=prep.sigma, Cout=prep.Cout,
                                    Cin=prep.Cin, Cin_p=prep.Cin_p, k=prep.k, flip=prep.flip)
             self.order.append(key)
         off, n = self.w_slots[key]
-        self.committed = max(self.committed, off + self._round(n))
+        done = off + (self._round(n) if upto is None or upto >= n else (upto // self.ALIGN * self.ALIGN))
+        self.committed = max(self.committed, done)
         if self.on_commit is not None:
-            self.on_commit(self.committed)
+            self.on_commit(self.committed, force=upto is not None)
 
 
 _sink = threading.local()
@@ -780,10 +783,35 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
             if p.w.requires_grad:
                 with ctx.side(dy, a_in.data, flops=2.0 * p.Cin * p.Cout * p.k * B * T):
                     dwg = ctx.weight_grad_buf(p, p.k, p.Cout, p.Cin_p)
-                    K.conv_wgrad(dy, a_in.data, dwg, p.Cin)
-                    _weight_grad(ctx, conv, p, dwg)
+                    _wgrad(ctx, conv, p, dy, a_in.data, dwg)
         ctx.tape.append(bwd)
     return out
+
+
+# Data parallel: a weight gradient of more than _CHUNK_WGRAD_ELEMS elements (encoder conv0: 97 M, the LAST gradient of the
+# step - nothing is left to hide its all-reduce behind) is produced in row chunks, each committed to the gradient sink as
+# soon as its GEMM is enqueued: the collective of chunk i runs underneath the GEMM of chunk i + 1.
+_CHUNK_WGRAD_ELEMS = int(float(os.environ.get("SIMULGEN_B200_CHUNK_WGRAD_MELEMS", "48")) * 1e6)
+_CHUNK_WGRAD_PARTS = int(os.environ.get("SIMULGEN_B200_CHUNK_WGRAD_PARTS", "4"))
+_CHUNK_WGRAD_ALIGN = int(os.environ.get("SIMULGEN_B200_CHUNK_WGRAD_ALIGN", "256"))      # rows per chunk: whole CTA-pair tiles
+
+
+def _wgrad(ctx: Ctx, conv, p: _Prep, dy, act, dwg):
+    sink = ctx.sink
+    chunked = (sink is not None and sink.on_commit is not None and p.sn and p.k == 1 and dy.shape[0] == 1 and
+               _CHUNK_WGRAD_PARTS > 1 and dwg.numel() >= _CHUNK_WGRAD_ELEMS and p.Cout >= 2 * _CHUNK_WGRAD_ALIGN)
+    if not chunked:
+        K.conv_wgrad(dy, act, dwg, p.Cin)
+        _weight_grad(ctx, conv, p, dwg)
+        return
+    if p.sn and getattr(conv, "_sg_sn_version", 0) != p.version:
+        raise RuntimeError("simulgen_b200: spectral-norm state of a layer advanced between forward and backward")
+    al = _CHUNK_WGRAD_ALIGN
+    rows = max(al, (p.Cout // _CHUNK_WGRAD_PARTS + al - 1) // al * al)
+    for m0 in range(0, p.Cout, rows):
+        m1 = min(p.Cout, m0 + rows)
+        K.conv_wgrad(dy[:, m0:m1], act, dwg[:, m0:m1], p.Cin)
+        sink.commit_weight(p, dwg, upto=m1 * p.Cin_p)
 
 
 def cgg_seq(ctx: Ctx, seq, a_in: Act, res: Act = None, res_scale=0.1, post_gelu=False, want_f32=False,

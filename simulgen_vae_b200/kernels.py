@@ -183,6 +183,16 @@ def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
         _stream()))
 
 
+def set_sm_limit(sms):
+    """SMs the persistent GEMM grids may use from now on (0 = all), in both library variants."""
+    for half in (False, True):
+        try:
+            _lib.call("sg_set_sm_limit", int(sms), half=half)
+        except RuntimeError:
+            if not half:
+                raise
+
+
 _OUT16_OK = {}
 
 

@@ -64,7 +64,13 @@ class Trainer:
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
-        self.bucket_elems = bucket_mb * (1 << 20) // 4
+        import os
+        bucket_mb = float(os.environ.get("SIMULGEN_B200_BUCKET_MB", bucket_mb))
+        self.bucket_elems = int(bucket_mb * (1 << 20)) // 4
+        # SMs kept free for NCCL's kernels while collectives overlap the backward pass (the persistent GEMM grids shrink
+        # by that many SMs; see sg_set_sm_limit) and whether the all-reduce overlaps backward at all (0: after backward)
+        self.reserve_sms = int(os.environ.get("SIMULGEN_B200_DP_RESERVE_SMS", "8"))
+        self.overlap = os.environ.get("SIMULGEN_B200_DP_OVERLAP", "1") != "0"
         self.fused = fused
         if self.world > 1 and broadcast_init:
             self._broadcast_replica()
@@ -115,11 +121,13 @@ class Trainer:
             for t in list(self.model.parameters()) + list(self.model.buffers()):
                 dist.broadcast(t.data, src=src, group=self.pg)
 
-    def _on_commit(self, committed):
+    def _on_commit(self, committed, force=False):
         """Gradient arena filled up to `committed` elements: all-reduce complete buckets right away.  The
         collective is enqueued behind the wgrad GEMMs already issued on the compute stream and runs on
-        NCCL's own stream while backward continues."""
-        if committed - self._launched >= self.bucket_elems:
+        NCCL's own stream while backward continues.  force: a chunk of a large gradient - reduce it now."""
+        if not self.overlap:
+            return
+        if committed - self._launched >= (1 if force else self.bucket_elems) and committed > self._launched:
             self._reduce(self.sink.weights[self._launched:committed])
             self._launched = committed
 
@@ -225,7 +233,14 @@ class Trainer:
                 for k in kls[1:]:
                     kl_sum = kl_sum + k
                 loss = recon * self.alpha + kl_sum * beta
-                (loss * S if (scaler is not None or S != 1.0) else loss).backward()
+                limit = self.world > 1 and self.overlap and self.reserve_sms > 0 and self.dev.type == "cuda"
+                if limit:
+                    K.set_sm_limit(torch.cuda.get_device_properties(self.dev).multi_processor_count - self.reserve_sms)
+                try:
+                    (loss * S if (scaler is not None or S != 1.0) else loss).backward()
+                finally:
+                    if limit:
+                        K.set_sm_limit(0)
             finally:
                 engine.set_grad_sink(None)
                 engine.set_materialize_xhat(True)

@@ -146,6 +146,10 @@ def conv_out16_ok(M):
     return M > 128
 
 
+def set_sm_limit(sms):
+    pass
+
+
 def conv_wgrad(dy, act, dwg, Cin):
     k, Cout, Cin_p = dwg.shape
     g = center(dy).float()                                                    # [Cout, B, Tp]
@@ -538,7 +542,7 @@ def sn_prepare(plan, training):
             sn_pack_weight(L["w"], L["sigma"], L["wg"], L["H"], L["Cin"], L["Cin_p"], L["k"], L["so"], L["si"], L["flip"])
 
 
-NAMES = ["conv_out16_ok", "OptPlan", "opt_step", "SnPlan", "sn_prepare", "assemble_batch", "minmax_fit", "minmax_transform", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
+NAMES = ["conv_out16_ok", "set_sm_limit", "OptPlan", "opt_step", "SnPlan", "sn_prepare", "assemble_batch", "minmax_fit", "minmax_transform", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
          "conv_fprop", "conv_fprop_gn", "conv_dgrad", "conv_wgrad", "gn_stats", "gn_act_fwd", "gn_act_bwd", "recon_fwd", "recon_bwd",
          "head_fwd", "head_bwd", "latent_fwd", "latent_bwd", "reparam_main_fwd", "reparam_main_bwd", "kl2_reparam_fwd",
          "kl2_reparam_bwd", "philox_normal", "adamw_step"]

@@ -261,8 +261,9 @@ def test_recon_fwd_bwd(loss, with_ext, one_pass, T, y_bf16):
 
 
 @pytest.mark.parametrize("O", [8, 64])
-def test_head_fwd_bwd(O):
-    C, B, T = 24, 3, 21
+@pytest.mark.parametrize("B,T", [(3, 21), (600, 1)])          # (600, 1): large-batch static fields, gradient staged in chunks
+def test_head_fwd_bwd(O, B, T):
+    C = 24
     Tp = tp_of(T)
     h = cr(C, B, T, seed=1)
     w = rnd(O, C * T, seed=2, scale=0.1)

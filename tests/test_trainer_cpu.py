@@ -119,6 +119,9 @@ def _free_port():
 
 def _dp_worker(rank, world, port, name, fused, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    # exercise the chunked weight-gradient commit (k = 1 layers produced in row chunks, each all-reduced on its own) on
+    # the toy model: every k = 1 layer with >= 16 output channels, 8-row chunks
+    os.environ.update(SIMULGEN_B200_CHUNK_WGRAD_MELEMS="0", SIMULGEN_B200_CHUNK_WGRAD_ALIGN="8")
     torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     from simulgen_vae_b200.trainer import Trainer
