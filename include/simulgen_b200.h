@@ -258,9 +258,33 @@ typedef struct sg_scaler_state {
     float scale, growth, backoff, min_scale, max_scale;
     int growth_interval, good_steps, step, skipped, last_skipped;
 } sg_scaler_state;
+/* Data parallel over NVLink peer memory (one process per GPU; no reference counterpart - the reference has no working
+ * multi-GPU path, modules/utils.py:209-238).  Every rank keeps its gradient arenas and ONE flat parameter buffer in
+ * symmetric memory, so that each rank holds device pointers to all of them:
+ *   wbase[r] / vbase[r]  weight-gradient arena / vector-gradient arena of rank r (same layout on every rank)
+ *   pbase[r]             flat parameter buffer of rank r (same layout on every rank)
+ * The optimiser is sharded (rank r owns a contiguous range of every tensor; `items` describe only that range):
+ *   sg_peer_reduce_dot   for the elements of its shard, rank `rank` LOADS the gradient from every rank's arena over
+ *                        NVLink, sums, stores the sum in its own arena and accumulates its share of <G, W> per layer
+ *                        (a fused reduce-scatter + dot: no separate collective, no SM time taken from the backward pass);
+ *   (host: one tiny all-reduce of `dots` - the only collective of the step)
+ *   sg_opt_step(peer, phase 2)  spectral-norm gradient + AdamW on the shard; the updated parameters are STORED to every
+ *                        rank's parameter buffer over NVLink (a fused all-gather).
+ * Optimiser HBM traffic and state per GPU shrink by the world size; the gradient is never all-reduced. */
+#define SG_MAX_PEERS 8
+typedef struct sg_peer {
+    int world, rank;
+    const char* wbase[SG_MAX_PEERS];
+    const char* vbase[SG_MAX_PEERS];
+    char* pbase[SG_MAX_PEERS];
+} sg_peer;
+int sg_peer_reduce_dot(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots, int n_dots,
+                       int want_bad_flag, const sg_peer* peer, void* stream);
+/* phase 0: everything (dot pass, scalars, update).  phase 2: the dot pass has been done (sg_peer_reduce_dot + the
+ * all-reduce of dots): scalars + update only.  peer (may be NULL): replicate the parameter stores to every rank. */
 int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots, int n_dots,
                 float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                double* gnorm_sq, sg_scaler_state* scaler, void* stream);
+                double* gnorm_sq, sg_scaler_state* scaler, const sg_peer* peer, int phase, void* stream);
 
 /* ---- preprocessing scan (modules/data_preprocess.py:65-165, SimulGen-VAE.py:279-283) --------------
  * data: the field matrix [R = P*T][N] (nodes innermost), float64 (is_f64 = 1) or float32 - the dtype the reference's

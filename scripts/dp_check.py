@@ -29,10 +29,8 @@ def run(model, batches, offset, pg_world):
     torch.manual_seed(11)                       # eps stream: Philox keyed on (seed, draw, global sample id)
     from simulgen_vae_b200 import engine
     engine._rng_state().seed = None             # restart the draw counter
-    tr = Trainer(model, lr=1e-3, alpha=1e6, bucket_mb=1)
-    if pg_world == 1:
-        tr.world = 1
-        tr.sink.on_commit = None
+    # the single-process repeat runs on rank 0 only: no collective may be issued there (broadcast_init included)
+    tr = Trainer(model, lr=1e-3, alpha=1e6, bucket_mb=1, broadcast_init=pg_world > 1, single_process=pg_world == 1)
     for x in batches:
         tr.step(x, beta=1e-4, sample_offset=offset)
     return tr

@@ -50,7 +50,8 @@ SIGNATURES = {
     "sg_kl2_reparam_bwd": [P, P, P, F, P, P, F, P, P, I, I, I, I, P],
     "sg_philox_normal": [P, I, L, U, U, L, P],
     "sg_adamw_step": [P, P, P, P, L, F, F, F, F, F, I, F, P, P],
-    "sg_opt_step": [P, P, I, P, I, F, F, F, F, F, I, F, P, P, P],
+    "sg_opt_step": [P, P, I, P, I, F, F, F, F, F, I, F, P, P, P, I, P],
+    "sg_peer_reduce_dot": [P, P, I, P, I, I, P, P],
     "sg_sn_prepare": [P, P, I, P, L, I, I, P],
     "sg_assemble_batch": [P, I, P, P, P, P, P, I, I, I, I, U, U, I, P],
     "sg_minmax_fit": [P, I, P, L, L, P, L, P, P, I, P],
@@ -70,6 +71,11 @@ class OptItem(ctypes.Structure):
     _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("u", c_void_p), ("vv", c_void_p),
                 ("sigma", c_void_p), ("dot", c_void_p), ("n", c_ll), ("Cout", c_int), ("Cin", c_int), ("Cin_p", c_int),
                 ("k", c_int), ("flip", c_int), ("reserved", c_int)]
+
+
+class Peer(ctypes.Structure):
+    """sg_peer of include/simulgen_b200.h"""
+    _fields_ = [("world", c_int), ("rank", c_int), ("wbase", c_void_p * 8), ("vbase", c_void_p * 8), ("pbase", c_void_p * 8)]
 
 
 def load(half=False):

@@ -116,6 +116,69 @@ opt_dot_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ Op
     }
 }
 
+// Peer memory (include/simulgen_b200.h, sg_peer): gradient of element `g` (a pointer into MY arena) on rank r
+__device__ __forceinline__ const float* peer_grad(const sg_peer& pc, const float* g, bool vec_arena, int r) {
+    const char* mine = vec_arena ? pc.vbase[pc.rank] : pc.wbase[pc.rank];
+    const char* theirs = vec_arena ? pc.vbase[r] : pc.wbase[r];
+    return reinterpret_cast<const float*>(theirs + (reinterpret_cast<const char*>(g) - mine));
+}
+__device__ __forceinline__ float* peer_param(const sg_peer& pc, float* p, int r) {
+    return reinterpret_cast<float*>(pc.pbase[r] + (reinterpret_cast<char*>(p) - pc.pbase[pc.rank]));
+}
+
+// Fused reduce-scatter + dot over NVLink peer memory.  `items` describe this rank's shard of every tensor; for each of its
+// elements the gradient is loaded from all `world` arenas (world - 1 of them remote: coalesced 16-byte P2P loads on the
+// k = 1 layers, tap-plane gathers otherwise), summed, written back into this rank's arena - no other rank reads or writes
+// those addresses: shards are disjoint in both layouts - and multiplied into the layer's <G, W>.
+__global__ void __launch_bounds__(kOptThreads)
+peer_reduce_dot_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ OptPrefix pf,
+                       const __grid_constant__ sg_peer pc, double* __restrict__ bad) {
+    __shared__ double sh[32];
+    const int idx = find_item(pf, blockIdx.x);
+    const sg_opt_item it = items[idx];
+    const long long e0 = (long long)(blockIdx.x - pf.start[idx]) * kOptChunk;
+    const long long e1 = min(it.n, e0 + kOptChunk);
+    const bool vec_arena = (it.reserved & 1) != 0;
+    const bool sn = it.u != nullptr;
+    const int W = pc.world;
+    float* gmine = const_cast<float*>(it.g);
+    float acc = 0.f, z = 0.f;
+    const bool direct = !sn || (it.k == 1 && !it.flip && it.Cin_p == it.Cin);
+    if (direct && (it.n & 3) == 0 && aligned16(it.g, it.p)) {
+        for (long long e = e0 + threadIdx.x * 4; e < e1; e += kOptThreads * 4) {
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < W; ++r) {
+                const float4 v = *reinterpret_cast<const float4*>(peer_grad(pc, it.g + e, vec_arena, r));
+                g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+            }
+            *reinterpret_cast<float4*>(gmine + e) = g;
+            if (sn) {
+                const float4 w = *reinterpret_cast<const float4*>(it.p + e);
+                acc += g.x * w.x + g.y * w.y + g.z * w.z + g.w * w.w;
+            } else {
+                z = fmaf(0.f, g.x + g.y + g.z + g.w, z);
+            }
+        }
+    } else {
+        for (long long e = e0 + threadIdx.x; e < e1; e += kOptThreads) {
+            long long gi = e;
+            if (sn) {
+                int o, q;
+                decode(it, (int)e, o, q, gi);
+            }
+            float g = 0.f;
+            for (int r = 0; r < W; ++r) g += *peer_grad(pc, it.g + gi, vec_arena, r);
+            gmine[gi] = g;
+            if (sn) acc += g * it.p[e]; else z = fmaf(0.f, g, z);
+        }
+    }
+    double t = block_sum((double)(sn ? acc : z), sh);
+    if (threadIdx.x == 0) {
+        if (sn) atomicAdd(it.dot, t);
+        if (bad != nullptr && !isfinite(t)) atomicAdd(bad, 1.0);
+    }
+}
+
 struct AdamArgs {
     float lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale;
     int skip, pad;
@@ -165,10 +228,22 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
 
 __global__ void __launch_bounds__(kOptThreads)
 opt_step_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ OptPrefix pf, const AdamArgs* __restrict__ args,
-                double* __restrict__ gnorm_sq) {
+                double* __restrict__ gnorm_sq, const __grid_constant__ sg_peer pc) {
     __shared__ double sh[32];
     const AdamArgs a = *args;
     if (a.skip) return;
+    // updated parameters go to this rank's buffer and, data parallel over peer memory, to every other rank's (fused
+    // all-gather: world - 1 remote stores per element over NVLink)
+    auto put4 = [&](float* dst, const float4& val) {
+        *reinterpret_cast<float4*>(dst) = val;
+        for (int r = 0; r < pc.world; ++r)
+            if (r != pc.rank) *reinterpret_cast<float4*>(peer_param(pc, dst, r)) = val;
+    };
+    auto put1 = [&](float* dst, float val) {
+        *dst = val;
+        for (int r = 0; r < pc.world; ++r)
+            if (r != pc.rank) *peer_param(pc, dst, r) = val;
+    };
     const int idx = find_item(pf, blockIdx.x);
     const sg_opt_item it = items[idx];
     const long long e0 = (long long)(blockIdx.x - pf.start[idx]) * kOptChunk;
@@ -209,7 +284,7 @@ opt_step_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ O
                 ss += gi * gi;
                 adam_update(p[i], m[i], v[i], gi, a);
             }
-            *reinterpret_cast<float4*>(it.p + e) = make_float4(p[0], p[1], p[2], p[3]);
+            put4(it.p + e, make_float4(p[0], p[1], p[2], p[3]));
             *reinterpret_cast<float4*>(it.m + e) = make_float4(m[0], m[1], m[2], m[3]);
             *reinterpret_cast<float4*>(it.v + e) = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -238,7 +313,7 @@ opt_step_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ O
                 ss += gi2 * gi2;
                 adam_update(p[t], m[t], v[t], gi2, a);
             }
-            *reinterpret_cast<float4*>(it.p + e) = make_float4(p[0], p[1], p[2], p[3]);
+            put4(it.p + e, make_float4(p[0], p[1], p[2], p[3]));
             *reinterpret_cast<float4*>(it.m + e) = make_float4(m[0], m[1], m[2], m[3]);
             *reinterpret_cast<float4*>(it.v + e) = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -257,7 +332,7 @@ opt_step_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ O
             ss += g * g;
             float p = it.p[e], m = it.m[e], v = it.v[e];
             adam_update(p, m, v, g, a);
-            it.p[e] = p;
+            put1(it.p + e, p);
             it.m[e] = m;
             it.v[e] = v;
         }
@@ -272,40 +347,83 @@ opt_step_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ O
 
 using namespace sg;
 
-extern "C" int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots,
-                           int n_dots, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                           float grad_scale, double* gnorm_sq, sg_scaler_state* scaler, void* stream) {
-    SG_REQUIRE(n_items > 0 && n_items <= kMaxItems, "opt_step: n_items=%d out of range (max %d)", n_items, kMaxItems);
-    // dots[0 .. n_dots - 3): one <G, W> per spectral-norm layer; then 1 double "non-finite gradient seen" and
-    // sizeof(AdamArgs) = 40 bytes (5 doubles) for the device copy of the step's scalars
-    SG_REQUIRE(dots != nullptr && n_dots >= 6, "opt_step: dots buffer needs >= 6 trailing scratch elements");
-    double* bad = dots + (n_dots - 6);
-    AdamArgs* dev_args = reinterpret_cast<AdamArgs*>(dots + (n_dots - 5));
-    cudaStream_t st = as_stream(stream);
-    OptPrefix pf;
+static int build_prefix(const sg_opt_item* items_host, int n_items, OptPrefix& pf, long long& total, bool& any_sn, const char* who) {
+    SG_REQUIRE(n_items > 0 && n_items <= kMaxItems, "%s: n_items=%d out of range (max %d)", who, n_items, kMaxItems);
     pf.n_items = n_items;
-    long long total = 0;
-    bool any_sn = false;
+    total = 0;
+    any_sn = false;
     for (int i = 0; i < n_items; ++i) {
         const sg_opt_item& it = items_host[i];
-        SG_REQUIRE(it.n > 0 && it.n < (1LL << 31), "opt_step: item %d has n=%lld", i, it.n);
+        SG_REQUIRE(it.n > 0 && it.n < (1LL << 31), "%s: item %d has n=%lld", who, i, it.n);
         if (it.u != nullptr) {
             any_sn = true;
-            SG_REQUIRE(it.dot != nullptr && it.sigma != nullptr && it.vv != nullptr && it.k >= 1 &&
-                           (long long)it.Cout * it.Cin * it.k == it.n && it.Cin_p >= it.Cin,
-                       "opt_step: item %d has inconsistent spectral-norm fields", i);
+            // n is the number of elements of THIS item: the whole tensor, or - sharded optimiser - whole rows of it
+            SG_REQUIRE(it.dot != nullptr && it.sigma != nullptr && it.vv != nullptr && it.k >= 1 && it.Cin_p >= it.Cin &&
+                           it.n <= (long long)it.Cout * it.Cin * it.k &&
+                           it.n % ((long long)(it.flip ? it.Cout : it.Cin) * it.k) == 0,
+                       "%s: item %d has inconsistent spectral-norm fields", who, i);
         }
         pf.start[i] = (int)total;
         total += cdiv(it.n, kOptChunk);
     }
-    SG_REQUIRE(total < (1LL << 31), "opt_step: too many chunks");
+    SG_REQUIRE(total < (1LL << 31), "%s: too many chunks", who);
     pf.start[n_items] = (int)total;
+    return 0;
+}
+
+static int check_peer(const sg_peer* peer, const char* who) {
+    SG_REQUIRE(peer->world >= 1 && peer->world <= SG_MAX_PEERS && peer->rank >= 0 && peer->rank < peer->world,
+               "%s: bad peer context (world %d, rank %d)", who, peer->world, peer->rank);
+    for (int r = 0; r < peer->world; ++r)
+        SG_REQUIRE(peer->wbase[r] != nullptr && peer->vbase[r] != nullptr && peer->pbase[r] != nullptr,
+                   "%s: missing base pointer of rank %d", who, r);
+    return 0;
+}
+
+extern "C" int sg_peer_reduce_dot(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots,
+                                  int n_dots, int want_bad_flag, const sg_peer* peer, void* stream) {
+    SG_REQUIRE(peer != nullptr && dots != nullptr && n_dots >= 6, "peer_reduce_dot: missing arguments");
+    if (check_peer(peer, "peer_reduce_dot")) return 1;
+    cudaStream_t st = as_stream(stream);
+    OptPrefix pf;
+    long long total;
+    bool any_sn;
+    if (build_prefix(items_host, n_items, pf, total, any_sn, "peer_reduce_dot")) return 1;
     cudaMemsetAsync(dots, 0, sizeof(double) * n_dots, st);
-    if (any_sn || scaler != nullptr)
-        opt_dot_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, scaler != nullptr ? bad : nullptr);
+    double* bad = dots + (n_dots - 6);
+    peer_reduce_dot_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, *peer, want_bad_flag ? bad : nullptr);
+    return check_launch("peer_reduce_dot");
+}
+
+extern "C" int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots,
+                           int n_dots, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                           float grad_scale, double* gnorm_sq, sg_scaler_state* scaler, const sg_peer* peer, int phase,
+                           void* stream) {
+    // dots[0 .. n_dots - 6): one <G, W> per spectral-norm layer; then 1 double "non-finite gradient seen" and
+    // sizeof(AdamArgs) = 40 bytes (5 doubles) for the device copy of the step's scalars
+    SG_REQUIRE(dots != nullptr && n_dots >= 6, "opt_step: dots buffer needs >= 6 trailing scratch elements");
+    SG_REQUIRE(phase == 0 || phase == 2, "opt_step: phase must be 0 or 2");
+    double* bad = dots + (n_dots - 6);
+    AdamArgs* dev_args = reinterpret_cast<AdamArgs*>(dots + (n_dots - 5));
+    cudaStream_t st = as_stream(stream);
+    OptPrefix pf;
+    long long total;
+    bool any_sn;
+    if (build_prefix(items_host, n_items, pf, total, any_sn, "opt_step")) return 1;
+    sg_peer pc{};
+    pc.world = 1;
+    if (peer != nullptr) {
+        if (check_peer(peer, "opt_step")) return 1;
+        pc = *peer;
+    }
+    if (phase == 0) {
+        cudaMemsetAsync(dots, 0, sizeof(double) * n_dots, st);
+        if (any_sn || scaler != nullptr)
+            opt_dot_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, scaler != nullptr ? bad : nullptr);
+    }
     AdamArgs a{};
     a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.wd = weight_decay; a.grad_scale = grad_scale;
     opt_prologue_kernel<<<1, 1, 0, st>>>(a, step, scaler, scaler != nullptr ? bad : nullptr, dev_args, gnorm_sq);
-    opt_step_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, dev_args, gnorm_sq);
+    opt_step_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, dev_args, gnorm_sq, pc);
     return check_launch("opt_step");
 }

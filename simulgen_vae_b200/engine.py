@@ -149,10 +149,16 @@ class GradSink:
 
     ALIGN = 64
 
-    def __init__(self, weight_elems, vec_elems, device):
+    def __init__(self, weight_elems, vec_elems, device, arenas=None):
+        """arenas: optional preallocated (weights, vecs) buffers - the data-parallel trainer hands in symmetric
+        (peer-mapped) memory so that the other ranks can read the gradients over NVLink."""
         self.dev = device
-        self.weights = torch.zeros(max(weight_elems, 1), dtype=torch.float32, device=device)
-        self.vecs = torch.zeros(max(vec_elems, 1), dtype=torch.float32, device=device)
+        if arenas is not None:
+            self.weights, self.vecs = arenas
+            assert self.weights.numel() >= max(weight_elems, 1) and self.vecs.numel() >= max(vec_elems, 1)
+        else:
+            self.weights = torch.zeros(max(weight_elems, 1), dtype=torch.float32, device=device)
+            self.vecs = torch.zeros(max(vec_elems, 1), dtype=torch.float32, device=device)
         self.scratch = torch.zeros(1 << 18, dtype=torch.float64, device=device)
         self.scratch_used = 0
         self.w_used = self.v_used = 0

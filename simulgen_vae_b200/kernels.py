@@ -358,21 +358,46 @@ class OptPlan:
         arr = (_lib.OptItem * len(items))()
         d = 0
         for a, it in zip(arr, items):
-            a.p, a.g, a.m, a.v = _p(it["p"]), _p(it["g"]), _p(it["m"]), _p(it["v"])
-            a.n = it["p"].numel()
+            # sharded optimiser (shard_item): p / g / u / vv are VIEWS that start at the shard, "n" is the shard length
+            a.p, a.g, a.m, a.v = it["p"].data_ptr(), it["g"].data_ptr(), _p(it["m"]), _p(it["v"])
+            a.n = int(it.get("n", it["p"].numel()))
+            a.reserved = int(bool(it.get("vec_arena", False)))
+            assert it["m"].numel() == a.n and it["v"].numel() == a.n
             if it.get("u") is not None:
-                a.u, a.vv, a.sigma = _p(it["u"]), _p(it["vv"]), _p(it["sigma"])
+                a.u, a.vv, a.sigma = it["u"].data_ptr(), it["vv"].data_ptr(), _p(it["sigma"])
                 a.dot = self.dots.data_ptr() + 8 * d
                 it["dot_index"] = d
                 d += 1
                 a.Cout, a.Cin, a.Cin_p, a.k, a.flip = it["Cout"], it["Cin"], it["Cin_p"], it["k"], int(it["flip"])
-                assert it["g"].numel() == it["k"] * it["Cout"] * it["Cin_p"]
+                assert "n" in it or it["g"].numel() == it["k"] * it["Cout"] * it["Cin_p"]
             else:
-                assert it["g"].numel() == a.n
+                assert "n" in it or it["g"].numel() == a.n
         self._host = arr                                  # keeps the host copy alive (read at every launch)
         raw = bytes(arr)
         self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
         self.n = len(items)
+        self.n_sn = n_sn
+
+
+def make_peer(rank, weight_ptrs, vec_ptrs, param_ptrs):
+    """sg_peer: device pointers to every rank's weight-gradient arena, vector-gradient arena and flat parameter buffer."""
+    world = len(weight_ptrs)
+    assert 1 <= world <= 8 and len(vec_ptrs) == world and len(param_ptrs) == world and 0 <= rank < world
+    pc = _lib.Peer()
+    pc.world, pc.rank = world, rank
+
+    def ptr(x):                 # a device pointer, or a tensor that starts at it (single-device tests of the kernels)
+        return x.data_ptr() if isinstance(x, torch.Tensor) else int(x)
+    for r in range(world):
+        pc.wbase[r], pc.vbase[r], pc.pbase[r] = ptr(weight_ptrs[r]), ptr(vec_ptrs[r]), ptr(param_ptrs[r])
+    return pc
+
+
+def peer_reduce_dot(plan, want_bad, peer):
+    """Fused reduce-scatter + <G, W> over peer memory for the shard `plan` describes (csrc/optim.cu)."""
+    import ctypes
+    _call("sg_peer_reduce_dot", plan.table.data_ptr(), ctypes.addressof(plan._host), plan.n, plan.dots.data_ptr(),
+          plan.dots.numel(), int(bool(want_bad)), ctypes.addressof(peer), _stream())
 
 
 SCALER_FIELDS = ("scale", "growth", "backoff", "min_scale", "max_scale",          # float32
@@ -395,15 +420,18 @@ def read_scaler_state(state):
     return dict(zip(SCALER_FIELDS, f + host[5:].tolist()))
 
 
-def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, scaler=None):
+def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, scaler=None, peer=None, phase=0):
     """scaler: optional make_scaler_state() tensor - the dynamic loss scale of the fp16-operand mode; `step` is then
-    ignored (the applied-step counter lives in the state) and grad_scale excludes the loss scale."""
+    ignored (the applied-step counter lives in the state) and grad_scale excludes the loss scale.
+    peer / phase: data parallel over peer memory - phase 2 runs after peer_reduce_dot + the all-reduce of plan.dots and
+    stores the updated parameters to every rank (make_peer)."""
     import ctypes
     if scaler is not None:
         assert scaler.dtype == torch.int32 and scaler.numel() == len(SCALER_FIELDS)
     _call("sg_opt_step", plan.table.data_ptr(), ctypes.addressof(plan._host), plan.n, plan.dots.data_ptr(),
           plan.dots.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
-          float(grad_scale), _p(gnorm_sq), _p(scaler), _stream())
+          float(grad_scale), _p(gnorm_sq), _p(scaler), ctypes.addressof(peer) if peer is not None else None, int(phase),
+          _stream())
 
 
 class SnPlan:

@@ -47,10 +47,65 @@ def _gemm_layout_elems(mod):
     return k * cout * ((cin + 7) // 8 * 8)
 
 
+def shard_item(it, rank, world):
+    """The part of one optimiser item (engine.GradSink.items: p, g[, u, vv, sigma, Cout, Cin, Cin_p, k, flip]) that rank
+    `rank` of `world` owns under the sharded optimiser, or None when its share is empty.  Spectral-norm weights are
+    split by whole rows of the native layout (Conv1d / Linear: output channels; ConvTranspose1d: input channels), which
+    are also contiguous row ranges of the k tap planes of the GEMM-layout gradient, so the shard is described by views
+    that simply START later - the kernels index them as if they were the whole tensor; everything else is split into
+    16-byte-aligned ranges.  Returns a dict with the views, "n" (elements of the shard) and "rows" = (lo, hi)."""
+    p, g = it["p"], it["g"]
+    if it.get("u") is not None:
+        Cout, Cin, Cin_p, k, flip = it["Cout"], it["Cin"], it["Cin_p"], it["k"], bool(it["flip"])
+        rows, rowlen = (Cin, Cout * k) if flip else (Cout, Cin * k)
+        lo, hi = rows * rank // world, rows * (rank + 1) // world
+        if hi <= lo:
+            return None
+        out = dict(it)
+        out.update(n=(hi - lo) * rowlen, rows=(lo, hi), full=it,
+                   p=p.reshape(-1)[lo * rowlen:], g=g.reshape(-1)[(lo if flip else lo * Cin_p):],
+                   u=it["u"] if flip else it["u"][lo:], vv=it["vv"][lo * k:] if flip else it["vv"])
+        return out
+    n = p.numel()
+    blocks = (n + 3) // 4
+    lo, hi = min(n, blocks * rank // world * 4), min(n, blocks * (rank + 1) // world * 4)
+    if hi <= lo:
+        return None
+    out = dict(it)
+    out.update(n=hi - lo, rows=(lo, hi), full=it, p=p.reshape(-1)[lo:], g=g.reshape(-1)[lo:])
+    return out
+
+
+class PeerMemory:
+    """Symmetric (peer-mapped) device buffers of a data-parallel group on one NVLink / NVSwitch box: every rank allocates
+    the same buffers and, after a rendezvous, holds device pointers to all of them (torch.distributed._symmetric_memory:
+    CUDA VMM allocations exported between the ranks' processes)."""
+
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem, self.group, self.device = symm_mem, group, device
+        self.handles = []
+        name = (group if group is not None else torch.distributed.group.WORLD).group_name
+        try:
+            symm_mem.enable_symm_mem_for_group(name)
+        except Exception:
+            pass
+        self.group_name = name
+
+    def empty(self, n, dtype=torch.float32):
+        """(tensor, [device pointer of rank r's copy for every r])"""
+        t = self.symm_mem.empty(int(n), dtype=dtype, device=self.device)
+        h = self.symm_mem.rendezvous(t, self.group_name)
+        self.handles.append(h)
+        ptrs = [int(x) for x in h.buffer_ptrs]
+        assert ptrs[h.rank] == t.data_ptr(), "symmetric memory: own pointer mismatch"
+        return t, ptrs
+
+
 class Trainer:
     def __init__(self, model, lr=1e-3, alpha=1.0e6, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
                  process_group=None, bucket_mb=64, fused=True, materialize_xhat=False, loss_scale=None,
-                 broadcast_init=True, growth_interval=200):
+                 broadcast_init=True, growth_interval=200, single_process=False, dp_mode=None):
         self.model = model
         self.lr, self.alpha, self.betas, self.eps, self.wd = lr, alpha, betas, eps, weight_decay
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -62,15 +117,23 @@ class Trainer:
         self.gnorm_sq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.pg = process_group
         self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        # single_process: ignore an initialised torch.distributed (a rank-local reference run next to a data-parallel one)
+        if not single_process and (process_group is not None or
+                                   (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
         import os
         bucket_mb = float(os.environ.get("SIMULGEN_B200_BUCKET_MB", bucket_mb))
         self.bucket_elems = int(bucket_mb * (1 << 20)) // 4
         # SMs kept free for NCCL's kernels while collectives overlap the backward pass (the persistent GEMM grids shrink
         # by that many SMs; see sg_set_sm_limit) and whether the all-reduce overlaps backward at all (0: after backward)
-        self.reserve_sms = int(os.environ.get("SIMULGEN_B200_DP_RESERVE_SMS", "8"))
+        self.reserve_sms = int(os.environ.get("SIMULGEN_B200_DP_RESERVE_SMS", "0"))
         self.overlap = os.environ.get("SIMULGEN_B200_DP_OVERLAP", "1") != "0"
+        # data-parallel exchange: "peer" (default on CUDA) = sharded optimiser over NVLink peer memory (PeerMemory,
+        # sg_peer_reduce_dot / sg_opt_step: no gradient all-reduce at all), "nccl" = bucketed ncclAllReduce of the gradient
+        # arena overlapped with backward + replicated optimiser (round 1); "peer" falls back to "nccl" when symmetric
+        # memory cannot be set up (and always on CPU / gloo)
+        self.dp_mode = os.environ.get("SIMULGEN_B200_DP", dp_mode or "peer")
+        self.peer = None
         self.fused = fused
         if self.world > 1 and broadcast_init:
             self._broadcast_replica()
@@ -90,6 +153,7 @@ class Trainer:
         self.plan = None
         self._works = []
         self._launched = 0
+        self._token = torch.zeros(1, dtype=torch.float32, device=dev)
         if fused:
             w_elems = v_elems = n_layers = 0
             wparams = set()
@@ -105,11 +169,56 @@ class Trainer:
             for p in self.params:
                 if id(p) not in wparams:
                     v_elems += engine.GradSink._round(p.numel())
-            self.sink = engine.GradSink(w_elems, v_elems, dev)
-            if self.world > 1:
+            arenas = None
+            if self.world > 1 and self.dp_mode == "peer" and dev.type == "cuda" and self.world <= 8:
+                arenas = self._setup_peer_memory(w_elems, v_elems)
+            self.sink = engine.GradSink(w_elems, v_elems, dev, arenas=arenas)
+            if self.world > 1 and self.peer is None:
+                self.dp_mode = "nccl"
                 self.sink.on_commit = self._on_commit
 
     # -- data parallel --------------------------------------------------------------------------
+    def _setup_peer_memory(self, w_elems, v_elems):
+        """Gradient arenas and ONE flat buffer for all parameters in symmetric memory; the parameters are re-homed into
+        the flat buffer (p.data becomes a view of it: same Parameter objects, same state dict).  Returns the two arenas,
+        or None (with a warning) when symmetric memory is unavailable - the NCCL path takes over."""
+        dist = torch.distributed
+        try:
+            pm = PeerMemory(self.pg, self.dev)
+            weights, wptrs = pm.empty(max(w_elems, 1))
+            vecs, vptrs = pm.empty(max(v_elems, 1))
+            allp = list(self.model.parameters())
+            offs, total = [], 0
+            for p in allp:
+                offs.append(total)
+                total += (p.numel() + 63) // 64 * 64
+            flat, pptrs = pm.empty(max(total, 1))
+            ok = torch.ones(1, device=self.dev)
+        except Exception as e:  # pragma: no cover - depends on the box
+            ok = torch.zeros(1, device=self.dev)
+            err = e
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.pg)
+        if float(ok) == 0:
+            import warnings
+            warnings.warn("simulgen_b200: symmetric peer memory unavailable (%s); data parallel falls back to NCCL all-reduce"
+                          % (locals().get("err", "another rank failed"),))
+            return None
+        weights.zero_()
+        vecs.zero_()
+        with torch.no_grad():
+            for p, off in zip(allp, offs):
+                view = flat[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+        rank = dist.get_rank(self.pg)
+        self.peer_mem = pm
+        self.peer = K.make_peer(rank, wptrs, vptrs, pptrs)
+        self.rank = rank
+        self._flat_params = flat
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=self.pg)
+        return weights, vecs
+
     def _broadcast_replica(self):
         """Data parallel needs IDENTICAL replicas: the reference's entry point builds the model on every rank without
         a seed (SimulGen-VAE.py never calls manual_seed; train.py:65-72 draws the He weights and the spectral-norm
@@ -182,6 +291,21 @@ class Trainer:
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
         return flat, ([] if len(bucket) == 1 else bucket), work
 
+    def _peer_step(self, b1, b2, scale, scaler):
+        """Sharded optimiser over peer memory.  Backward ran at full speed (no collective in flight); now
+          barrier -> every rank sums ITS shard of the gradient from all ranks' arenas (P2P loads) and takes its share of
+          the per-layer <G, W>  ->  all-reduce of those ~50 scalars (+ the overflow flag)  ->  AdamW on the shard, updated
+          parameters stored to all ranks (P2P stores)  ->  all-reduce of the gradient-norm partial = closing barrier."""
+        dist = torch.distributed
+        engine.order_after_side_stream(self.dev)
+        dist.all_reduce(self._token, group=self.pg)                       # every rank's arena is complete
+        K.peer_reduce_dot(self.plan, scaler is not None, self.peer)
+        if self.plan.n_sn or scaler is not None:
+            dist.all_reduce(self.plan.dots[:self.plan.n_sn + 1], group=self.pg)
+        K.opt_step(self.plan, self.lr, b1, b2, self.eps, self.wd, self.step_count, scale, self.gnorm_sq, scaler,
+                   peer=self.peer, phase=2)
+        dist.all_reduce(self.gnorm_sq, group=self.pg)                     # global norm; all parameter stores have landed
+
     # -- optimiser ---------------------------------------------------------------------------------
     def _state(self, p):
         if p not in self.m:
@@ -191,11 +315,22 @@ class Trainer:
 
     def _build_plan(self):
         items = []
+        vlo = self.sink.vecs.data_ptr()
+        vhi = vlo + self.sink.vecs.numel() * 4
         for key in self.sink.order:
             it = dict(self.sink.items[key])
             p = it.pop("param")
-            m, v = self._state(p)
-            it.update(p=p.data, m=m, v=v)
+            it.update(p=p.data, vec_arena=vlo <= it["g"].data_ptr() < vhi)
+            if self.peer is not None:
+                it = shard_item(it, self.rank, self.world)      # sharded optimiser: this rank's rows only
+                if it is None:
+                    continue
+                n = it["n"]
+                it.update(m=torch.zeros(n, dtype=torch.float32, device=self.dev),
+                          v=torch.zeros(n, dtype=torch.float32, device=self.dev))
+            else:
+                m, v = self._state(p)
+                it.update(m=m, v=v)
             items.append(it)
         self.sink.frozen = True
         self.plan = K.OptPlan(items, self.dev)
@@ -244,11 +379,18 @@ class Trainer:
             finally:
                 engine.set_grad_sink(None)
                 engine.set_materialize_xhat(True)
-            self._finish_reduce()
-            if self.plan is None:
+            if self.plan is None and self.peer is None:
+                self._finish_reduce()
                 self._build_plan()
+            elif self.plan is None:
+                self._build_plan()
+            elif self.peer is None:
+                self._finish_reduce()
             self.step_count += 1
-            K.opt_step(self.plan, self.lr, b1, b2, self.eps, self.wd, self.step_count, scale, self.gnorm_sq, scaler)
+            if self.peer is not None:
+                self._peer_step(b1, b2, scale, scaler)
+            else:
+                K.opt_step(self.plan, self.lr, b1, b2, self.eps, self.wd, self.step_count, scale, self.gnorm_sq, scaler)
         else:
             for p in self.params:
                 p.grad = None

@@ -491,15 +491,73 @@ class OptPlan:
     def __init__(self, items, device):
         self.items = items
         self.n = len(items)
+        self.n_sn = sum(1 for it in items if it.get("u") is not None)
+        self.dots = torch.zeros(self.n_sn + 6, dtype=torch.float64, device=device)
+        d = 0
+        for it in items:
+            if it.get("u") is not None:
+                it["dot_index"] = d
+                d += 1
 
 
-def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, scaler=None):
+# ---- sharded optimiser over peer memory (csrc/optim.cu: peer_reduce_dot_kernel, opt_step_kernel with sg_peer) -----------
+def make_peer(rank, weights, vecs, params):
+    """Emulated sg_peer: the tensors themselves (every rank's weight-gradient arena, vector arena, flat parameters)."""
+    return dict(rank=rank, world=len(weights), weights=list(weights), vecs=list(vecs), params=list(params))
+
+
+def _same_region(buffers, mine, t):
+    """the region tensor `t` occupies in buffers[mine], in every buffer"""
+    off = (t.data_ptr() - buffers[mine].data_ptr()) // t.element_size()
+    assert 0 <= off and off + t.numel() <= buffers[mine].numel()
+    return [b[off:off + t.numel()].view(t.shape) for b in buffers]
+
+
+def _w_gemm_layout(full):
+    """weight_orig in the GEMM layout [k][Cout][Cin_p] of its gradient"""
+    p, k, Cout, Cin, Cin_p = full["p"], full["k"], full["Cout"], full["Cin"], full["Cin_p"]
+    w = torch.zeros(k, Cout, Cin_p, dtype=p.dtype, device=p.device)
+    if full["flip"]:
+        w[:, :, :Cin] = p.reshape(Cin, Cout, k).flip(2).permute(2, 1, 0)
+    else:
+        w[:, :, :Cin] = p.reshape(Cout, Cin, k).permute(2, 0, 1)
+    return w
+
+
+def peer_reduce_dot(plan, want_bad, peer):
+    plan.dots.zero_()
+    me = peer["rank"]
+    for it in plan.items:
+        full, (lo, hi) = it["full"], it["rows"]
+        arenas = peer["vecs"] if it.get("vec_arena") else peer["weights"]
+        gs = _same_region(arenas, me, full["g"])
+        total = sum(g.double() for g in gs).to(torch.float32)
+        if full.get("u") is not None:
+            k, Cout, Cin_p = full["k"], full["Cout"], full["Cin_p"]
+            tot3, mine3 = total.view(k, Cout, Cin_p), gs[me].view(k, Cout, Cin_p)
+            sel = (slice(None), slice(None), slice(lo, hi)) if full["flip"] else (slice(None), slice(lo, hi), slice(None))
+            mine3[sel] = tot3[sel]
+            w3 = _w_gemm_layout(full)
+            dot = (tot3[sel].double() * w3[sel].double()).sum()
+            plan.dots[it["dot_index"]] += dot
+            bad = not bool(torch.isfinite(dot))
+        else:
+            gs[me].view(-1)[lo:hi] = total.view(-1)[lo:hi]
+            bad = not bool(torch.isfinite(total.view(-1)[lo:hi]).all())
+        if want_bad and bad:
+            plan.dots[plan.n_sn] += 1
+
+
+def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, scaler=None, peer=None, phase=0):
     if scaler is not None:
         # sg_scaler_state semantics (csrc/optim.cu opt_prologue_kernel)
         fl = scaler[:5].view(torch.float32)
         used = float(fl[0])
         grad_scale = grad_scale / used
-        bad = any(not bool(torch.isfinite(it["g"]).all()) for it in plan.items)
+        if phase == 2:
+            bad = float(plan.dots[plan.n_sn]) != 0.0
+        else:
+            bad = any(not bool(torch.isfinite(it["g"]).all()) for it in plan.items)
         if bad:
             fl[0] = max(used * float(fl[2]), float(fl[3]))
             scaler[6] = 0
@@ -514,6 +572,8 @@ def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_
             fl[0] = min(used * float(fl[1]), float(fl[4]))
             scaler[6] = 0
         step = int(scaler[7])
+    if peer is not None or any("full" in it for it in plan.items):
+        return _opt_step_sharded(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, peer)
     for it in plan.items:
         p = it["p"]
         if it.get("u") is not None:
@@ -524,6 +584,39 @@ def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_
         else:
             grad = it["g"].reshape(p.shape)
         adamw_step(p, grad, it["m"], it["v"], lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq)
+
+
+def _opt_step_sharded(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, peer):
+    """Shard items (trainer.shard_item): the gradient in this rank's arena already holds the sum over ranks on the shard's
+    rows (peer_reduce_dot) and plan.dots the all-reduced <G, W>; update the shard's rows and store them to every rank."""
+    me = peer["rank"] if peer is not None else 0
+    for it in plan.items:
+        full, (lo, hi) = it["full"], it["rows"]
+        p = full["p"]
+        if full.get("u") is not None:
+            k, Cout, Cin, Cin_p, flip = full["k"], full["Cout"], full["Cin"], full["Cin_p"], full["flip"]
+            G = full["g"].reshape(k, Cout, Cin_p)[:, :, :Cin]
+            if flip:
+                Gn = G.flip(0).permute(2, 1, 0)                   # [Cin, Cout, k]
+                uv = torch.outer(full["u"], full["vv"]).reshape(Cout, Cin, k).permute(1, 0, 2)
+            else:
+                Gn = G.permute(1, 2, 0)                          # [Cout, Cin, k]
+                uv = torch.outer(full["u"], full["vv"]).reshape(Cout, Cin, k)
+            sigma = full["sigma"]
+            dot = plan.dots[it["dot_index"]].float()
+            grad = ((Gn - dot / sigma * uv) / sigma).reshape(p.shape)[lo:hi].reshape(-1)
+            psh = p.reshape(p.shape[0], -1)[lo:hi].reshape(-1)
+        else:
+            grad = full["g"].reshape(-1)[lo:hi]
+            psh = p.reshape(-1)[lo:hi]
+        pnew = psh.clone()
+        adamw_step(pnew, grad.contiguous(), it["m"], it["v"], lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq)
+        targets = _same_region(peer["params"], me, p) if peer is not None else [p]
+        for t in targets:
+            if full.get("u") is not None:
+                t.reshape(t.shape[0], -1)[lo:hi] = pnew.view(hi - lo, -1)
+            else:
+                t.reshape(-1)[lo:hi] = pnew
 
 
 class SnPlan:
@@ -542,7 +635,7 @@ def sn_prepare(plan, training):
             sn_pack_weight(L["w"], L["sigma"], L["wg"], L["H"], L["Cin"], L["Cin_p"], L["k"], L["so"], L["si"], L["flip"])
 
 
-NAMES = ["conv_out16_ok", "set_sm_limit", "OptPlan", "opt_step", "SnPlan", "sn_prepare", "assemble_batch", "minmax_fit", "minmax_transform", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
+NAMES = ["conv_out16_ok", "set_sm_limit", "make_peer", "peer_reduce_dot", "OptPlan", "opt_step", "SnPlan", "sn_prepare", "assemble_batch", "minmax_fit", "minmax_transform", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
          "conv_fprop", "conv_fprop_gn", "conv_dgrad", "conv_wgrad", "gn_stats", "gn_act_fwd", "gn_act_bwd", "recon_fwd", "recon_bwd",
          "head_fwd", "head_bwd", "latent_fwd", "latent_bwd", "reparam_main_fwd", "reparam_main_bwd", "kl2_reparam_fwd",
          "kl2_reparam_bwd", "philox_normal", "adamw_step"]
