@@ -97,6 +97,14 @@ if want("recon"):
     inv = 1.0 / (B * N * T)
     report("recon_bwd (one pass)", timed(lambda: K.recon_bwd(y, stats, gamma, beta, x, gl, gm, inv, None, dy, dg, db, dbi, T, G, 0, rows)),
            y.numel() * ybytes + x.numel() * 4 + dy.numel() * 2 + rows.numel() * 4)
+    # round 2: the target read from the packed 16-bit operand of x ([N, B, Tp], the layout of y; engine.loss_target)
+    opx = torch.empty(1, N, B, Tp, device=dev, dtype=BF)
+    K.pack_input(x, opx, T)
+    report("recon_fwd (packed 16-bit target)", timed(lambda: K.recon_fwd(y, stats, gamma, beta, opx[0], None, sums, T, G, 0, rows)),
+           y.numel() * ybytes + opx.numel() * 2 + rows.numel() * 4)
+    report("recon_bwd (packed 16-bit target)", timed(lambda: K.recon_bwd(y, stats, gamma, beta, opx[0], gl, gm, inv, None, dy, dg, db, dbi, T, G, 0, rows)),
+           y.numel() * ybytes + opx.numel() * 2 + dy.numel() * 2 + rows.numel() * 4)
+    del opx
     del y, dy, rows, x
 if want("gn_act"):
     # (channels, operand planes, residual, 16-bit y, 16-bit incoming gradient): round-1 fp32 hand-offs and the

@@ -9,6 +9,7 @@ import re
 import sys
 
 src, out_txt, out_json, command, batch, steps = sys.argv[1:7]
+precision = sys.argv[7] if len(sys.argv) > 7 else "bf16"
 steps = int(steps)
 rows = list(csv.reader(l for l in open(src) if l.startswith('"')))
 ix = {h: i for i, h in enumerate(rows[0])}
@@ -46,7 +47,7 @@ ours = [a for k, a in agg.items() if k.startswith("sg::") or k.startswith("pair:
 n = sum(a[0] for a in gemm)
 byt = sum(a[2] + a[3] for a in gemm)
 ms = sum(a[1] for a in gemm)
-json.dump({"command": command, "per_gpu_batch": int(batch), "gemm_launches_per_step": n / steps,
+json.dump({"command": command, "per_gpu_batch": int(batch), "precision": precision, "gemm_launches_per_step": n / steps,
            "gemm_dram_bytes_per_step": byt / steps, "gemm_dram_bytes_per_launch": byt / max(n, 1),
            "gemm_ncu_ms_per_step": ms / steps,
            "gemm_share_of_engine_kernel_time": ms / max(sum(a[1] for a in ours), 1e-9),

@@ -85,12 +85,7 @@ class PeerMemory:
         import torch.distributed._symmetric_memory as symm_mem
         self.symm_mem, self.group, self.device = symm_mem, group, device
         self.handles = []
-        name = (group if group is not None else torch.distributed.group.WORLD).group_name
-        try:
-            symm_mem.enable_symm_mem_for_group(name)
-        except Exception:
-            pass
-        self.group_name = name
+        self.group_name = (group if group is not None else torch.distributed.group.WORLD).group_name
 
     def empty(self, n, dtype=torch.float32):
         """(tensor, [device pointer of rank r's copy for every r])"""
