@@ -445,12 +445,25 @@ def _main():
     if world == 1 and args.config == 2 and args.batch_sweep and not args.nodes:
         del pool
         torch.cuda.empty_cache()
+        n_sw = max(10, args.steps)
         for bs in [int(v) for v in args.batch_sweep.split(",") if v.strip()]:
             if bs == B:
                 continue
-            ms_b, _ = run_value(bs, max(10, args.steps), args.warmup, trainer)
-            v = bs * max(10, args.steps) / (ms_b / 1e3)
-            sweep.append({"per_gpu_batch": bs, "value": v, "ms_per_step": ms_b / max(10, args.steps)})
+            ms_b, _ = run_value(bs, n_sw, args.warmup, trainer)
+            ent = {"per_gpu_batch": bs, "value": bs * n_sw / (ms_b / 1e3), "ms_per_step": ms_b / n_sw}
+            # the same steps replayed as CUDA graphs (Trainer(cuda_graph=True)): at small batches the ~9 ms of host work
+            # per step (190 C-ABI calls from Python) is what bounds the eager rate, not the GPU
+            try:
+                trainer.cuda_graph = True
+                ms_g, _ = run_value(bs, n_sw, args.warmup + 4, trainer)
+                ent["cuda_graph"] = {"value": bs * n_sw / (ms_g / 1e3), "ms_per_step": ms_g / n_sw}
+            except Exception as e:  # pragma: no cover
+                ent["cuda_graph"] = {"value": None, "error": str(e)[:120]}
+            finally:
+                trainer.cuda_graph = False
+                trainer._graphs.clear()
+                torch.cuda.empty_cache()
+            sweep.append(ent)
 
     if rank != 0:
         if world > 1:
@@ -474,6 +487,8 @@ def _main():
         pass
     for s_ in sweep:
         s_["step_tensor_frac"] = s_["value"] * gflop * 1e9 / (peak * 1e12)
+        if s_.get("cuda_graph", {}).get("value"):
+            s_["cuda_graph"]["step_tensor_frac"] = s_["cuda_graph"]["value"] * gflop * 1e9 / (peak * 1e12)
     if args.config == 4:
         # static fields: the step streams the 2.29 G parameters (spectral-norm preparation 14 B, forward + dgrad reads of the
         # 16-bit copy 4 B, weight-gradient write 4 B, optimiser 36 B per element) and is bound by HBM, not by the tensor pipe

@@ -187,8 +187,11 @@ int sg_kl2_reparam_bwd(const float* cz, const float* cxz, const float* eps, floa
 
 /* ---- counter-based RNG (replaces torch.randn_like, decoder.py:221) ----------------------------
  * out[b][i] ~ N(0,1), keyed on (seed, stream_id, sample0 + b, i): identical for any batch split. */
-int sg_philox_normal(float* out, int B, long long per_sample, unsigned long long seed,
-                     unsigned long long stream_id, long long sample0, void* stream);
+int sg_philox_normal(float* out, int B, long long per_sample, unsigned long long seed, unsigned long long stream_id,
+                     long long sample0, const long long* counter, void* stream);
+/* counter (device, may be NULL) is added to stream_id on the device; sg_counter_add advances it.  A captured CUDA graph
+ * of the training step keeps its kernel arguments, so the draw index has to live in device memory. */
+int sg_counter_add(long long* counter, long long inc, void* stream);
 
 /* ---- optimiser (train.py:92,156-168: AdamW defaults + global grad L2 norm) ----------------------
  * One launch over a flat fp32 parameter arena.  gnorm_sq (double, (+)=) receives sum g^2. */

@@ -48,7 +48,8 @@ SIGNATURES = {
     "sg_reparam_main_bwd": [P, P, P, P, P, I, I, P],
     "sg_kl2_reparam_fwd": [P, P, P, P, F, P, I, L, P, P, I, I, I, I, I, P],
     "sg_kl2_reparam_bwd": [P, P, P, F, P, P, F, P, P, I, I, I, I, P],
-    "sg_philox_normal": [P, I, L, U, U, L, P],
+    "sg_philox_normal": [P, I, L, U, U, L, P, P],
+    "sg_counter_add": [P, L, P],
     "sg_adamw_step": [P, P, P, P, L, F, F, F, F, F, I, F, P, P],
     "sg_opt_step": [P, P, I, P, I, F, F, F, F, F, I, F, P, P, P, I, P],
     "sg_peer_reduce_dot": [P, P, I, P, I, I, P, P],

@@ -453,8 +453,11 @@ kl2_reparam_bwd_kernel(const float* __restrict__ cz, const float* __restrict__ c
 // =============================================================================================
 // Philox4x32-10 + Box-Muller
 // =============================================================================================
+// counter (may be NULL): device-resident draw counter added to stream_id - a CUDA-graph replay of the training step
+// then draws fresh noise every time although its kernel arguments are frozen (sg_counter_add advances it inside the graph)
 __global__ void philox_normal_kernel(float* __restrict__ out, int B, long long per_sample, uint64_t seed,
-                                     uint64_t stream_id, long long sample0) {
+                                     uint64_t stream_id, long long sample0, const long long* __restrict__ counter) {
+    if (counter != nullptr) stream_id += (uint64_t)counter[0];
     long long quads = (per_sample + 3) / 4;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= quads * B) return;
@@ -635,12 +638,19 @@ int sg_kl2_reparam_bwd(const float* cz, const float* cxz, const float* eps, floa
 }
 
 int sg_philox_normal(float* out, int B, long long per_sample, unsigned long long seed, unsigned long long stream_id,
-                     long long sample0, void* stream) {
+                     long long sample0, const long long* counter, void* stream) {
     long long quads = (per_sample + 3) / 4;
     long long total = quads * B;
     if (total <= 0) return 0;
-    philox_normal_kernel<<<(int)cdiv(total, 256), 256, 0, as_stream(stream)>>>(out, B, per_sample, seed, stream_id, sample0);
+    philox_normal_kernel<<<(int)cdiv(total, 256), 256, 0, as_stream(stream)>>>(out, B, per_sample, seed, stream_id, sample0, counter);
     return check_launch("philox_normal");
+}
+
+__global__ void counter_add_kernel(long long* c, long long inc) { c[0] += inc; }
+
+int sg_counter_add(long long* counter, long long inc, void* stream) {
+    counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(counter, inc);
+    return check_launch("counter_add");
 }
 
 int sg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

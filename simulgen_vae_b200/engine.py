@@ -132,6 +132,13 @@ def draw_eps(shape, device):
     if st.seed != seed:
         st.seed, st.counter = seed, 0
     out = torch.empty(shape, device=device, dtype=torch.float32)
+    dev_counter = getattr(st, "dev_counter", None)
+    if dev_counter is not None:
+        # CUDA-graph capture (Trainer): the draw index of the STEP lives in device memory (advanced inside the graph),
+        # the kernel argument only carries the index of the draw within the step
+        K.philox_normal(out, seed, st.graph_draw, st.sample0, dev_counter)
+        st.graph_draw += 1
+        return out
     K.philox_normal(out, seed, st.counter, st.sample0)
     st.counter += 1
     return out

@@ -73,7 +73,16 @@ def _planes(t):
     return t.data_ptr(), t.shape[0], (t.stride(0) if t.shape[0] > 1 else t[0].numel())
 
 
+try:
+    _raw_stream = torch._C._cuda_getCurrentRawStream      # ~0.3 us; torch.cuda.current_stream() builds a Stream object (~3 us)
+except AttributeError:  # pragma: no cover
+    _raw_stream = None
+
+
 def _stream():
+    """cudaStream_t of the current stream of the current device (every C-ABI call takes it)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -332,11 +341,18 @@ def kl2_reparam_bwd(cz, cxz, eps, std_scale, dzs, dkl, kl_scale, dcz, dcxz, T):
 
 
 # ---- RNG / optimiser ----------------------------------------------------------------------------
-def philox_normal(out, seed, stream_id, sample0):
+def philox_normal(out, seed, stream_id, sample0, counter=None):
+    """counter: optional int64 [1] device tensor added to stream_id on the device (CUDA-graph replays)."""
     B = out.shape[0]
     per = out.numel() // B
+    assert counter is None or (counter.dtype == torch.int64 and counter.numel() == 1)
     _call("sg_philox_normal", _p(_f32(out, "out")), B, per, int(seed) & (2 ** 64 - 1), int(stream_id), int(sample0),
-          _stream())
+          _p(counter), _stream())
+
+
+def counter_add(counter, inc):
+    assert counter.dtype == torch.int64 and counter.numel() == 1
+    _call("sg_counter_add", _p(counter), int(inc), _stream())
 
 
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq):
@@ -464,6 +480,9 @@ class SnPlan:
 
 def sn_prepare(plan, training):
     import ctypes
+    global _HALF
+    if plan.dtype != SG_F32:
+        _HALF = plan.dtype == SG_F16         # the plan's operand format selects the library build
     _call("sg_sn_prepare", plan.table.data_ptr(), ctypes.addressof(plan._host), plan.n, plan.ws.data_ptr(),
           plan.ws.numel(), int(training), plan.dtype, _stream())
 

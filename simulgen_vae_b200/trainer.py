@@ -100,7 +100,7 @@ class PeerMemory:
 class Trainer:
     def __init__(self, model, lr=1e-3, alpha=1.0e6, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
                  process_group=None, bucket_mb=64, fused=True, materialize_xhat=False, loss_scale=None,
-                 broadcast_init=True, growth_interval=200, single_process=False, dp_mode=None):
+                 broadcast_init=True, growth_interval=200, single_process=False, dp_mode=None, cuda_graph=None):
         self.model = model
         self.lr, self.alpha, self.betas, self.eps, self.wd = lr, alpha, betas, eps, weight_decay
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -149,6 +149,10 @@ class Trainer:
         self._works = []
         self._launched = 0
         self._token = torch.zeros(1, dtype=torch.float32, device=dev)
+        import os as _os
+        # replay the step as one CUDA graph once it has run eagerly (single GPU, fp16 mode): opt-in, SIMULGEN_B200_GRAPH=1
+        self.cuda_graph = bool(int(_os.environ.get("SIMULGEN_B200_GRAPH", "0"))) if cuda_graph is None else bool(cuda_graph)
+        self._graphs, self._graph_pool, self._dev_counter, self._dev_counter_host = {}, None, None, -1
         if fused:
             w_elems = v_elems = n_layers = 0
             wparams = set()
@@ -330,10 +334,71 @@ class Trainer:
         self.sink.frozen = True
         self.plan = K.OptPlan(items, self.dev)
 
+    # -- CUDA graph of the whole step -----------------------------------------------------------------
+    def _graph_ok(self, x):
+        return (self.cuda_graph and self.fused and self.world == 1 and self.plan is not None and self.dev.type == "cuda" and
+                engine.get_precision() == "fp16" and self.loss_scale is None and self.scaler is not None and
+                engine._rng_state().fixed is None and torch.randn_like is engine._ORIG_RANDN_LIKE)
+
+    def _graph_step(self, x, beta, sample_offset):
+        """One optimisation step as ONE cudaGraphLaunch.  The step issues ~190 C-ABI calls and ~400 allocations from
+        Python (~9 ms of host time): at the reference's batch size of 16 the GPU finishes its ~11 ms of work before the
+        host has issued it.  Everything that changes from step to step already lives in device memory - loss scale and
+        AdamW step count (sg_scaler_state), the Philox draw counter (sg_counter_add), the batch (a fixed input buffer:
+        the loader's ring slots are captured as they are, other tensors are copied into a static buffer) - so a
+        captured step can be replayed as is.  beta and the learning rate are kernel / operator arguments: a change
+        (once per epoch, train.py:144,237) captures a new graph."""
+        st = engine._rng_state()
+        packed = isinstance(x, engine.PackedBatch)
+        src = x.operand if packed else x
+        key = (src.data_ptr() if packed else "copy", tuple(src.shape), src.dtype, float(beta), float(self.lr), int(sample_offset))
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 16:
+                self._graphs.clear()                         # schedules walk through many (beta, lr) pairs: keep the cache small
+            static = src if packed else torch.empty_like(src)
+            if not packed:
+                static.copy_(src)
+            if self._dev_counter is None:
+                self._dev_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            inp = engine.PackedBatch(static, x.T) if packed else static
+            g = torch.cuda.CUDAGraph()
+            st.dev_counter, st.graph_draw = self._dev_counter, 0
+            try:
+                with torch.cuda.graph(g, pool=self._graph_pool):
+                    out = self._eager_step(inp, beta, sample_offset)
+                    draws = st.graph_draw
+                    K.counter_add(self._dev_counter, draws)
+            finally:
+                st.dev_counter = None
+            if self._graph_pool is None:
+                self._graph_pool = g.pool()
+            ent = self._graphs[key] = (g, static, out, draws, packed)
+            self.step_count -= 1                             # the capture pass did not execute anything
+        g, static, out, draws, packed = ent
+        if not packed:
+            static.copy_(src)
+        seed = torch.initial_seed()
+        if st.seed != seed:
+            st.seed, st.counter = seed, 0
+        if self._dev_counter_host != st.counter:             # eager steps (or a reseed) moved the draw counter meanwhile
+            self._dev_counter.fill_(st.counter)
+        g.replay()
+        st.counter += draws                                  # host mirror of the device counter (eager steps continue from it)
+        self._dev_counter_host = st.counter
+        self.step_count += 1
+        self._last = out
+        return out
+
     # -- one optimisation step -------------------------------------------------------------------
     def step(self, x, beta=1e-4, sample_offset=0, packed=None):
         """packed: optional bf16 operand of x written by the batch-assembly kernel (augment.B200AugmentedLoader with
         emit_operand=True): the encoder then skips its own input packing pass."""
+        if packed is None and self._graph_ok(x):
+            return self._graph_step(x, beta, sample_offset)
+        return self._eager_step(x, beta, sample_offset, packed)
+
+    def _eager_step(self, x, beta=1e-4, sample_offset=0, packed=None):
         model = self.model
         engine.set_sample_offset(sample_offset)
         engine.set_packed_input(packed)

@@ -421,7 +421,13 @@ def kl2_reparam_bwd(cz, cxz, eps, std_scale, dzs, dkl, kl_scale, dcz, dcxz, T):
 
 
 # ---- RNG / optimiser ----------------------------------------------------------------------------
-def philox_normal(out, seed, stream_id, sample0):
+def counter_add(counter, inc):
+    counter += inc
+
+
+def philox_normal(out, seed, stream_id, sample0, counter=None):
+    if counter is not None:
+        stream_id = int(stream_id) + int(counter)
     g = torch.Generator().manual_seed((int(seed) * 1000003 + int(stream_id) * 7919 + int(sample0)) % (2 ** 63))
     out.copy_(torch.randn(out.shape, generator=g))
 
@@ -635,7 +641,7 @@ def sn_prepare(plan, training):
             sn_pack_weight(L["w"], L["sigma"], L["wg"], L["H"], L["Cin"], L["Cin_p"], L["k"], L["so"], L["si"], L["flip"])
 
 
-NAMES = ["conv_out16_ok", "set_sm_limit", "make_peer", "peer_reduce_dot", "OptPlan", "opt_step", "SnPlan", "sn_prepare", "assemble_batch", "minmax_fit", "minmax_transform", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
+NAMES = ["counter_add", "conv_out16_ok", "set_sm_limit", "make_peer", "peer_reduce_dot", "OptPlan", "opt_step", "SnPlan", "sn_prepare", "assemble_batch", "minmax_fit", "minmax_transform", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
          "conv_fprop", "conv_fprop_gn", "conv_dgrad", "conv_wgrad", "gn_stats", "gn_act_fwd", "gn_act_bwd", "recon_fwd", "recon_bwd",
          "head_fwd", "head_bwd", "latent_fwd", "latent_bwd", "reparam_main_fwd", "reparam_main_bwd", "kl2_reparam_fwd",
          "kl2_reparam_bwd", "philox_normal", "adamw_step"]

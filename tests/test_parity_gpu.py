@@ -226,6 +226,51 @@ def test_baseline_config_shapes_parity(case, precision):
         assert worst_g < 6e-2, [r for r in greport if r[1] >= 6e-2]
 
 
+def test_cuda_graph_step_equals_eager_step():
+    """Trainer(cuda_graph=True): the whole optimisation step replayed as one CUDA graph (loss scale, AdamW step count and
+    Philox draw counter live in device memory) against the eager path on the same weights, batches and seed: same losses,
+    fresh noise on every replay, same weights after 6 steps."""
+    from simulgen_vae_b200 import engine
+    from simulgen_vae_b200 import kernels as K
+    from simulgen_vae_b200.trainer import Trainer
+    cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[128, 64, 32], num_node=520, num_time=40, small=True, batch=6, lossfun="MSE")
+    sg.set_precision("fp16")
+    try:
+        m0 = build_engine_vae(cfg, seed=4)
+        sd = {k: v.detach().clone() for k, v in m0.state_dict().items()}
+        xs = [O.synthetic_field(6, 520, 40, seed=20 + i).to(DEV) for i in range(3)]
+        results = []
+        for graph in (False, True):
+            m = build_engine_vae(cfg, seed=4)
+            m.load_state_dict(sd)
+            m.train(True)
+            torch.manual_seed(77)
+            engine._rng_state().seed = None
+            tr = Trainer(m, lr=1e-3, alpha=1e4, cuda_graph=graph)
+            losses, kls = [], []
+            for i in range(6):
+                x = xs[i % 3]
+                if i >= 3:                                   # second half: PackedBatch inputs (each operand buffer its own graph)
+                    op = torch.empty(1, 520, 6, 40, dtype=torch.float16, device=DEV)
+                    K.pack_input(x, op, 40)
+                    x = engine.PackedBatch(op, 40)
+                out = tr.step(x, beta=1e-2)
+                losses.append(float(out[0]))
+                kls.append(float(out[2]))
+            if graph:
+                assert len(tr._graphs) >= 2 and tr.scaler_state()["step"] == 6
+            results.append((losses, kls, {k: v.detach().clone() for k, v in m.state_dict().items()}))
+    finally:
+        sg.set_precision(sg.DEFAULT_PRECISION)
+    (l0, k0, w0), (l1, k1, w1) = results
+    for a, b in zip(l0, l1):
+        assert abs(a - b) / abs(a) < 2e-3, (l0, l1)
+    assert len(set(round(v, 3) for v in k1)) == len(k1)          # the KL terms move: every replay drew new noise
+    for k in w0:
+        if w0[k].dim() > 1:
+            assert rel_l2(w1[k], w0[k]) < 2e-2, (k, rel_l2(w1[k], w0[k]))
+
+
 FULL_SIZE = {
     # BASELINE.json configs[2], [3], [4] at their REAL node / time counts (batch reduced: parity does not depend on it)
     "config3_large_95008": dict(latent_dim=32, hierarchical_dim=8, enc=[1024, 512, 256, 128], num_node=95008, num_time=200,
