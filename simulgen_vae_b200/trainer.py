@@ -364,6 +364,10 @@ class Trainer:
             inp = engine.PackedBatch(static, x.T) if packed else static
             g = torch.cuda.CUDAGraph()
             st.dev_counter, st.graph_draw = self._dev_counter, 0
+            # inside a graph the weight-gradient side stream is not used (its fork / join would have to be captured from
+            # the autograd worker thread; the replay has no launch gaps for it to fill anyway)
+            overlap = engine._OVERLAP_WGRAD
+            engine._OVERLAP_WGRAD = False
             try:
                 with torch.cuda.graph(g, pool=self._graph_pool):
                     out = self._eager_step(inp, beta, sample_offset)
@@ -371,6 +375,7 @@ class Trainer:
                     K.counter_add(self._dev_counter, draws)
             finally:
                 st.dev_counter = None
+                engine._OVERLAP_WGRAD = overlap
             if self._graph_pool is None:
                 self._graph_pool = g.pool()
             ent = self._graphs[key] = (g, static, out, draws, packed)
