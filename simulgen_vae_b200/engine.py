@@ -1115,6 +1115,65 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
 
 
 # ------------------------------------------------------------------------------------------------
+# direct training step (no torch.autograd): what Trainer's fused path runs
+# ------------------------------------------------------------------------------------------------
+def train_step_direct(model, x, alpha, beta, scale=None):
+    """Forward + backward of `alpha * recon + beta * sum(kl)` (train.py:142-153) driven straight from the engine's own
+    tapes: encoder graph -> main-latent reparameterisation -> decoder graph + losses, then the three backward passes in
+    reverse, seeded with d loss / d recon = alpha and d loss / d kl_i = beta (times `scale`, the loss scale: a float or a
+    1-element device tensor).  The autograd Functions below do the same through torch.autograd for callers that own the
+    loop (the reference's train.py); here there is no autograd graph, no engine worker thread and no per-step Python
+    object churn - which also makes the whole step capturable as ONE CUDA graph (Trainer.cuda_graph).
+    Needs a gradient sink (set_grad_sink): parameter gradients go to its arenas.  Returns detached device scalars
+    (loss, recon, kl_sum, mse)."""
+    if get_grad_sink() is None:
+        raise RuntimeError("simulgen_b200: train_step_direct needs a gradient sink (Trainer installs one)")
+    enc, dec = model.encoder, model.decoder
+    _check_input(x, "input batch")
+    dev = x.device
+    with device_guard(dev), torch.no_grad():
+        if not isinstance(x, PackedBatch):
+            x = x.contiguous().float()
+        B, T = x.shape[0], x.shape[2]
+        ectx = Ctx(B, T, dev, True)
+        last, xs = encoder_graph(ectx, enc, x)
+        set_loss_operand(take_last_packed())
+        eps0 = draw_eps((B, model.latent_dim), dev)
+        z = torch.empty(B, last.tensor.shape[1] // 2, dtype=torch.float32, device=dev)
+        kl_main = torch.empty(1, dtype=torch.float32, device=dev)
+        K.reparam_main_fwd(last.tensor, eps0, z, kl_main)
+        dctx = Ctx(B, dec.num_time, dev, True)
+        z_ext = Ext(z)
+        n_levels = len(dec.decoder_residual_blocks) - 1
+        if len(xs) < n_levels:
+            raise RuntimeError("Decoder.forward needs xs with at least %d entries" % n_levels)
+        lossfun = model.lossfun if model.lossfun in model.loss_functions else "MSE"
+        res = decoder_graph(dctx, dec, z_ext, xs, x, lossfun, "random", want_xhat=False)
+        recon, mse = res["recon"].tensor, res["mse"].tensor
+        kl_sum = kl_main.clone()
+        for k_ext in res["kls"]:
+            kl_sum += k_ext.tensor
+        loss = recon * alpha + kl_sum * beta
+        # ---- backward ----
+        if isinstance(scale, torch.Tensor):                  # live device scalar (dynamic loss scaler): no host read
+            sc = scale.reshape(1).float()
+            g_recon, g_kl = sc * float(alpha), sc * float(beta)
+        else:
+            sc = 1.0 if scale is None else float(scale)
+            g_recon = torch.full((1,), sc * float(alpha), dtype=torch.float32, device=dev)
+            g_kl = torch.full((1,), sc * float(beta), dtype=torch.float32, device=dev)
+        res["recon"].grad = g_recon.contiguous()
+        for k_ext in res["kls"]:
+            k_ext.grad = g_kl.contiguous()
+        dctx.run_backward()
+        dlast = torch.empty_like(last.tensor)
+        K.reparam_main_bwd(last.tensor, eps0, z_ext.grad, g_kl.contiguous(), dlast)
+        last.grad = dlast
+        ectx.run_backward()
+    return loss.reshape(()), recon.reshape(()), kl_sum.reshape(()), mse.reshape(())
+
+
+# ------------------------------------------------------------------------------------------------
 # autograd boundary
 # ------------------------------------------------------------------------------------------------
 def _contig_f32(g):

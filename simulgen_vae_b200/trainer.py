@@ -153,6 +153,9 @@ class Trainer:
         # replay the step as one CUDA graph once it has run eagerly (single GPU, fp16 mode): opt-in, SIMULGEN_B200_GRAPH=1
         self.cuda_graph = bool(int(_os.environ.get("SIMULGEN_B200_GRAPH", "0"))) if cuda_graph is None else bool(cuda_graph)
         self._graphs, self._graph_pool, self._dev_counter, self._dev_counter_host = {}, None, None, -1
+        # fused path: drive the engine's tapes directly instead of going through torch.autograd (SIMULGEN_B200_DIRECT=0:
+        # the autograd Functions, as the reference's train.py uses them)
+        self.direct = _os.environ.get("SIMULGEN_B200_DIRECT", "1") != "0"
         if fused:
             w_elems = v_elems = n_layers = 0
             wparams = set()
@@ -336,7 +339,7 @@ class Trainer:
 
     # -- CUDA graph of the whole step -----------------------------------------------------------------
     def _graph_ok(self, x):
-        return (self.cuda_graph and self.fused and self.world == 1 and self.plan is not None and self.dev.type == "cuda" and
+        return (self.cuda_graph and self.fused and self.direct and not self.materialize_xhat and self.world == 1 and self.plan is not None and self.dev.type == "cuda" and
                 engine.get_precision() == "fp16" and self.loss_scale is None and self.scaler is not None and
                 engine._rng_state().fixed is None and torch.randn_like is engine._ORIG_RANDN_LIKE)
 
@@ -428,16 +431,21 @@ class Trainer:
             engine.set_grad_sink(self.sink)
             engine.set_materialize_xhat(self.materialize_xhat)
             try:
-                x_hat, recon, kls, mse = model(x)
-                kl_sum = kls[0]
-                for k in kls[1:]:
-                    kl_sum = kl_sum + k
-                loss = recon * self.alpha + kl_sum * beta
-                limit = self.world > 1 and self.overlap and self.reserve_sms > 0 and self.dev.type == "cuda"
+                limit = self.world > 1 and self.peer is None and self.overlap and self.reserve_sms > 0 and self.dev.type == "cuda"
                 if limit:
                     K.set_sm_limit(torch.cuda.get_device_properties(self.dev).multi_processor_count - self.reserve_sms)
                 try:
-                    (loss * S if (scaler is not None or S != 1.0) else loss).backward()
+                    if self.direct and not self.materialize_xhat:
+                        # the engine's own forward + backward, no torch.autograd in between (engine.train_step_direct)
+                        loss, recon, kl_sum, mse = engine.train_step_direct(
+                            model, x, self.alpha, beta, S if (scaler is not None or S != 1.0) else None)
+                    else:
+                        x_hat, recon, kls, mse = model(x)
+                        kl_sum = kls[0]
+                        for k in kls[1:]:
+                            kl_sum = kl_sum + k
+                        loss = recon * self.alpha + kl_sum * beta
+                        (loss * S if (scaler is not None or S != 1.0) else loss).backward()
                 finally:
                     if limit:
                         K.set_sm_limit(0)
