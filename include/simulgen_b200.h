@@ -282,9 +282,12 @@ typedef struct sg_peer {
     char* pbase[SG_MAX_PEERS];
 } sg_peer;
 int sg_peer_reduce_dot(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots, int n_dots,
-                       int want_bad_flag, const sg_peer* peer, void* stream);
+                       int want_bad_flag, int clear_dots, const sg_peer* peer, void* stream);
 /* phase 0: everything (dot pass, scalars, update).  phase 2: the dot pass has been done (sg_peer_reduce_dot + the
- * all-reduce of dots): scalars + update only.  peer (may be NULL): replicate the parameter stores to every rank. */
+ * all-reduce of dots): scalars + update only.  phase 3: update only, with the scalars a phase-2 call on the SAME dots
+ * buffer left there (the optimiser of one model split over two item tables - decoder / encoder - that share `dots`, so
+ * that the exchange of the decoder's share overlaps the encoder's backward and the next forward).
+ * peer (may be NULL): replicate the parameter stores to every rank. */
 int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots, int n_dots,
                 float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                 double* gnorm_sq, sg_scaler_state* scaler, const sg_peer* peer, int phase, void* stream);

@@ -22,7 +22,8 @@ sg.set_precision(precision)
 cfg = dict(bench.HEADLINE, num_node=2048, enc=[256, 128, 64, 32])
 Bl = 2
 B = Bl * world
-data = bench.synthetic_batches(2, B, cfg["num_node"], cfg["num_time"], dev, seed=7)      # same seed: same data on all ranks
+STEPS = int(os.environ.get("DP_CHECK_STEPS", "3"))       # >= 3: the pipelined exchange starts with the second step
+data = bench.synthetic_batches(STEPS, B, cfg["num_node"], cfg["num_time"], dev, seed=7)      # same seed: same data on all ranks
 
 
 def run(model, batches, offset, pg_world):
@@ -33,6 +34,7 @@ def run(model, batches, offset, pg_world):
     tr = Trainer(model, lr=1e-3, alpha=1e6, bucket_mb=1, broadcast_init=pg_world > 1, single_process=pg_world == 1)
     for x in batches:
         tr.step(x, beta=1e-4, sample_offset=offset)
+    tr.sync()
     return tr
 
 

@@ -381,7 +381,7 @@ static int check_peer(const sg_peer* peer, const char* who) {
 }
 
 extern "C" int sg_peer_reduce_dot(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots,
-                                  int n_dots, int want_bad_flag, const sg_peer* peer, void* stream) {
+                                  int n_dots, int want_bad_flag, int clear_dots, const sg_peer* peer, void* stream) {
     SG_REQUIRE(peer != nullptr && dots != nullptr && n_dots >= 6, "peer_reduce_dot: missing arguments");
     if (check_peer(peer, "peer_reduce_dot")) return 1;
     cudaStream_t st = as_stream(stream);
@@ -389,7 +389,7 @@ extern "C" int sg_peer_reduce_dot(const sg_opt_item* items_dev, const sg_opt_ite
     long long total;
     bool any_sn;
     if (build_prefix(items_host, n_items, pf, total, any_sn, "peer_reduce_dot")) return 1;
-    cudaMemsetAsync(dots, 0, sizeof(double) * n_dots, st);
+    if (clear_dots) cudaMemsetAsync(dots, 0, sizeof(double) * n_dots, st);
     double* bad = dots + (n_dots - 6);
     peer_reduce_dot_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, *peer, want_bad_flag ? bad : nullptr);
     return check_launch("peer_reduce_dot");
@@ -402,7 +402,7 @@ extern "C" int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* item
     // dots[0 .. n_dots - 6): one <G, W> per spectral-norm layer; then 1 double "non-finite gradient seen" and
     // sizeof(AdamArgs) = 40 bytes (5 doubles) for the device copy of the step's scalars
     SG_REQUIRE(dots != nullptr && n_dots >= 6, "opt_step: dots buffer needs >= 6 trailing scratch elements");
-    SG_REQUIRE(phase == 0 || phase == 2, "opt_step: phase must be 0 or 2");
+    SG_REQUIRE(phase == 0 || phase == 2 || phase == 3, "opt_step: phase must be 0, 2 or 3");
     double* bad = dots + (n_dots - 6);
     AdamArgs* dev_args = reinterpret_cast<AdamArgs*>(dots + (n_dots - 5));
     cudaStream_t st = as_stream(stream);
@@ -421,9 +421,11 @@ extern "C" int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* item
         if (any_sn || scaler != nullptr)
             opt_dot_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, scaler != nullptr ? bad : nullptr);
     }
-    AdamArgs a{};
-    a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.wd = weight_decay; a.grad_scale = grad_scale;
-    opt_prologue_kernel<<<1, 1, 0, st>>>(a, step, scaler, scaler != nullptr ? bad : nullptr, dev_args, gnorm_sq);
+    if (phase != 3) {
+        AdamArgs a{};
+        a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.wd = weight_decay; a.grad_scale = grad_scale;
+        opt_prologue_kernel<<<1, 1, 0, st>>>(a, step, scaler, scaler != nullptr ? bad : nullptr, dev_args, gnorm_sq);
+    }
     opt_step_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, dev_args, gnorm_sq, pc);
     return check_launch("opt_step");
 }

@@ -180,11 +180,16 @@ class GradSink:
     def _round(n):
         return (n + GradSink.ALIGN - 1) // GradSink.ALIGN * GradSink.ALIGN
 
-    def begin_step(self):
+    def begin_step(self, zero_vecs_from=0):
+        """zero_vecs_from: leave the first elements of the vector arena alone (the data-parallel trainer zeroes the
+        decoder's part later: the previous step's optimiser may still be reading it on another stream)."""
         self.committed = 0
         # the per-channel gradient vectors (bias, GroupNorm gain/shift) are accumulated with atomics: one memset of
         # the whole arena per step instead of three per layer; same for the fp64 scratch of the GroupNorm backward
-        self.vecs.zero_()
+        if zero_vecs_from > 0:
+            self.vecs[zero_vecs_from:].zero_()
+        else:
+            self.vecs.zero_()
         self.scratch.zero_()
         self.scratch_used = 0
 
@@ -1117,7 +1122,7 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
 # ------------------------------------------------------------------------------------------------
 # direct training step (no torch.autograd): what Trainer's fused path runs
 # ------------------------------------------------------------------------------------------------
-def train_step_direct(model, x, alpha, beta, scale=None):
+def train_step_direct(model, x, alpha, beta, scale=None, hooks=None):
     """Forward + backward of `alpha * recon + beta * sum(kl)` (train.py:142-153) driven straight from the engine's own
     tapes: encoder graph -> main-latent reparameterisation -> decoder graph + losses, then the three backward passes in
     reverse, seeded with d loss / d recon = alpha and d loss / d kl_i = beta (times `scale`, the loss scale: a float or a
@@ -1125,7 +1130,9 @@ def train_step_direct(model, x, alpha, beta, scale=None):
     loop (the reference's train.py); here there is no autograd graph, no engine worker thread and no per-step Python
     object churn - which also makes the whole step capturable as ONE CUDA graph (Trainer.cuda_graph).
     Needs a gradient sink (set_grad_sink): parameter gradients go to its arenas.  Returns detached device scalars
-    (loss, recon, kl_sum, mse)."""
+    (loss, recon, kl_sum, mse).
+    hooks (optional): object with before_decoder_forward() / after_decoder_backward(), called at those points of the step
+    - the data-parallel trainer starts the exchange of the decoder's gradients there (Trainer._peer_*)."""
     if get_grad_sink() is None:
         raise RuntimeError("simulgen_b200: train_step_direct needs a gradient sink (Trainer installs one)")
     enc, dec = model.encoder, model.decoder
@@ -1142,6 +1149,8 @@ def train_step_direct(model, x, alpha, beta, scale=None):
         z = torch.empty(B, last.tensor.shape[1] // 2, dtype=torch.float32, device=dev)
         kl_main = torch.empty(1, dtype=torch.float32, device=dev)
         K.reparam_main_fwd(last.tensor, eps0, z, kl_main)
+        if hooks is not None:
+            hooks.before_decoder_forward()
         dctx = Ctx(B, dec.num_time, dev, True)
         z_ext = Ext(z)
         n_levels = len(dec.decoder_residual_blocks) - 1
@@ -1166,6 +1175,8 @@ def train_step_direct(model, x, alpha, beta, scale=None):
         for k_ext in res["kls"]:
             k_ext.grad = g_kl.contiguous()
         dctx.run_backward()
+        if hooks is not None:
+            hooks.after_decoder_backward()
         dlast = torch.empty_like(last.tensor)
         K.reparam_main_bwd(last.tensor, eps0, z_ext.grad, g_kl.contiguous(), dlast)
         last.grad = dlast

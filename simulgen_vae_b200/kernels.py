@@ -365,14 +365,17 @@ class OptPlan:
     dict(p, g, m, v[, u, vv, sigma, Cout, Cin, Cin_p, k, flip]) whose tensors keep their addresses
     across steps (persistent gradient arena, optimiser state, spectral-norm buffers)."""
 
-    def __init__(self, items, device):
+    def __init__(self, items, device, dots=None, dot_base=0):
+        """dots / dot_base: share one scratch buffer between several plans (their <G, W> slots start at dot_base; the
+        trailing 6 elements - overflow flag, step scalars - are common)."""
         import ctypes
         self.items = items
         n_sn = sum(1 for it in items if it.get("u") is not None)
         # one <G, W> per spectral-norm item + 6 doubles of scratch (non-finite flag, device copy of the step's scalars)
-        self.dots = torch.zeros(n_sn + 6, dtype=torch.float64, device=device)
+        self.dots = torch.zeros(n_sn + 6, dtype=torch.float64, device=device) if dots is None else dots
+        assert self.dots.numel() >= dot_base + n_sn + 6
         arr = (_lib.OptItem * len(items))()
-        d = 0
+        d = dot_base
         for a, it in zip(arr, items):
             # sharded optimiser (shard_item): p / g / u / vv are VIEWS that start at the shard, "n" is the shard length
             a.p, a.g, a.m, a.v = it["p"].data_ptr(), it["g"].data_ptr(), _p(it["m"]), _p(it["v"])
@@ -409,11 +412,11 @@ def make_peer(rank, weight_ptrs, vec_ptrs, param_ptrs):
     return pc
 
 
-def peer_reduce_dot(plan, want_bad, peer):
+def peer_reduce_dot(plan, want_bad, peer, clear_dots=True):
     """Fused reduce-scatter + <G, W> over peer memory for the shard `plan` describes (csrc/optim.cu)."""
     import ctypes
     _call("sg_peer_reduce_dot", plan.table.data_ptr(), ctypes.addressof(plan._host), plan.n, plan.dots.data_ptr(),
-          plan.dots.numel(), int(bool(want_bad)), ctypes.addressof(peer), _stream())
+          plan.dots.numel(), int(bool(want_bad)), int(bool(clear_dots)), ctypes.addressof(peer), _stream())
 
 
 SCALER_FIELDS = ("scale", "growth", "backoff", "min_scale", "max_scale",          # float32

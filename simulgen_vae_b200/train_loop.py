@@ -115,6 +115,7 @@ def train(epochs, batch_size, train_dataloader, val_dataloader, LR, num_filter_e
             acc /= dist.get_world_size()
         sums = acc.tolist()                                               # the epoch's only device -> host read
         if epoch % 20 == 0 or epoch == epochs - 1:
+            trainer.sync()
             model.eval()
             vacc = torch.zeros(2, dtype=torch.float64, device=device)
             n_val = 0
@@ -151,6 +152,7 @@ def train(epochs, batch_size, train_dataloader, val_dataloader, LR, num_filter_e
                              epoch + 1, epochs, loss_print[epoch], loss_val_print[epoch], recon_print[epoch],
                              recon_loss_val_print[epoch], kl_print[epoch], beta, sums[4] / nb, dt,
                              (epochs - epoch) * dt / 3600, current_lr))
+    trainer.sync()
     if rank == 0:
         torch.save(model.state_dict(), "checkpoints/SimulGen-VAE.pth")
         torch.save(model, "model_save/SimulGen-VAE")

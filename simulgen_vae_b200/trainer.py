@@ -128,6 +128,7 @@ class Trainer:
         # arena overlapped with backward + replicated optimiser (round 1); "peer" falls back to "nccl" when symmetric
         # memory cannot be set up (and always on CPU / gloo)
         self.dp_mode = os.environ.get("SIMULGEN_B200_DP", dp_mode or "peer")
+        self.pipeline = os.environ.get("SIMULGEN_B200_DP_PIPELINE", "1") != "0"   # overlap the decoder's share of the exchange
         self.peer = None
         self.fused = fused
         if self.world > 1 and broadcast_init:
@@ -149,6 +150,11 @@ class Trainer:
         self._works = []
         self._launched = 0
         self._token = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._token2 = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.gnorm_dec = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.plan_dec, self._dots, self._v_split, self._pipelined_ok = None, None, 0, False
+        self._ev_dec_done, self._ev_reduced, self._step_scaler = None, None, None
+        self._peer_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         import os as _os
         # replay the step as one CUDA graph once it has run eagerly (single GPU, fp16 mode): opt-in, SIMULGEN_B200_GRAPH=1
         self.cuda_graph = bool(int(_os.environ.get("SIMULGEN_B200_GRAPH", "0"))) if cuda_graph is None else bool(cuda_graph)
@@ -293,20 +299,68 @@ class Trainer:
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
         return flat, ([] if len(bucket) == 1 else bucket), work
 
-    def _peer_step(self, b1, b2, scale, scaler):
-        """Sharded optimiser over peer memory.  Backward ran at full speed (no collective in flight); now
-          barrier -> every rank sums ITS shard of the gradient from all ranks' arenas (P2P loads) and takes its share of
-          the per-layer <G, W>  ->  all-reduce of those ~50 scalars (+ the overflow flag)  ->  AdamW on the shard, updated
-          parameters stored to all ranks (P2P stores)  ->  all-reduce of the gradient-norm partial = closing barrier."""
+    # Sharded optimiser over peer memory (sg_peer_reduce_dot / sg_opt_step with sg_peer).  Backward runs with no collective
+    # in flight.  The optimiser's items are split into the decoder's (complete after the decoder's backward) and the
+    # encoder's, over one shared scratch buffer, and the exchange is pipelined against the step itself:
+    #
+    #   main stream   ... decoder bwd | encoder bwd ............ | barrier, reduce(enc), all-reduce(dots), scalars, step(enc), barrier | next fwd: encoder ... | decoder
+    #   peer stream                   | barrier, reduce(dec) ...                                        | step(dec) + stores ........ barrier |  (waited for before the next decoder forward)
+    #
+    #   reduce(x): every rank LOADS its shard of x's gradients from all ranks' arenas (NVLink), sums, takes its share of <G, W>
+    #   step(x)  : spectral-norm gradient + AdamW on the shard, updated parameters STORED to all ranks (NVLink)
+    # so three quarters of the NVLink traffic (the decoder holds 75 % of the parameters) run underneath the encoder's backward
+    # and the next step's encoder forward.  "barrier" = an all-reduce of one scalar (stream-ordered, no host sync).
+    def before_decoder_forward(self):
+        self.sync()                                   # the decoder's parameters of the previous step have landed everywhere
+        if self._v_split > 0:
+            self.sink.vecs[:self._v_split].zero_()
+
+    def sync(self):
+        """Make the current stream wait for the part of the last optimiser step that runs on the peer stream (data
+        parallel, peer mode: the decoder's share).  Trainer.step does it itself where it matters; call it before reading
+        the model outside the trainer (validation forward, state_dict(), checkpoints)."""
+        if self._ev_dec_done is not None:
+            torch.cuda.current_stream(self.dev).wait_event(self._ev_dec_done)
+
+    def after_decoder_backward(self):
         dist = torch.distributed
         engine.order_after_side_stream(self.dev)
-        dist.all_reduce(self._token, group=self.pg)                       # every rank's arena is complete
-        K.peer_reduce_dot(self.plan, scaler is not None, self.peer)
-        if self.plan.n_sn or scaler is not None:
-            dist.all_reduce(self.plan.dots[:self.plan.n_sn + 1], group=self.pg)
+        cur = torch.cuda.current_stream(self.dev)
+        ps = self._peer_stream
+        ps.wait_stream(cur)
+        with torch.cuda.stream(ps):
+            dist.all_reduce(self._token2, group=self.pg)               # every rank's decoder gradients are complete
+            K.peer_reduce_dot(self.plan_dec, self._step_scaler is not None, self.peer, clear_dots=True)
+            self._ev_reduced = torch.cuda.Event()
+            self._ev_reduced.record(ps)
+
+    def _peer_exchange(self, b1, b2, scale, scaler, pipelined):
+        dist = torch.distributed
+        engine.order_after_side_stream(self.dev)
+        cur = torch.cuda.current_stream(self.dev)
+        ps = self._peer_stream
+        if pipelined:
+            cur.wait_event(self._ev_reduced)                            # reduce(dec) done: the shared dots are ours now
+        dist.all_reduce(self._token, group=self.pg)                     # every rank's (encoder) gradients are complete
+        if not pipelined and self.plan_dec is not None:
+            K.peer_reduce_dot(self.plan_dec, scaler is not None, self.peer, clear_dots=True)
+        K.peer_reduce_dot(self.plan, scaler is not None, self.peer, clear_dots=self.plan_dec is None)
+        n_red = self._dots.numel() - 5                                  # every <G, W> + the overflow flag
+        dist.all_reduce(self._dots[:n_red], group=self.pg)
         K.opt_step(self.plan, self.lr, b1, b2, self.eps, self.wd, self.step_count, scale, self.gnorm_sq, scaler,
                    peer=self.peer, phase=2)
-        dist.all_reduce(self.gnorm_sq, group=self.pg)                     # global norm; all parameter stores have landed
+        ps.wait_stream(cur)
+        with torch.cuda.stream(ps):
+            self.gnorm_dec.zero_()
+            if self.plan_dec is not None:
+                K.opt_step(self.plan_dec, self.lr, b1, b2, self.eps, self.wd, self.step_count, scale, self.gnorm_dec, scaler,
+                           peer=self.peer, phase=3)
+            dist.all_reduce(self.gnorm_dec, group=self.pg)              # closing barrier of the decoder's share
+            self._ev_dec_done = torch.cuda.Event()
+            self._ev_dec_done.record(ps)
+        dist.all_reduce(self.gnorm_sq, group=self.pg)                   # closing barrier of the encoder's share + norm
+        if not pipelined:
+            cur.wait_event(self._ev_dec_done)
 
     # -- optimiser ---------------------------------------------------------------------------------
     def _state(self, p):
@@ -322,7 +376,7 @@ class Trainer:
         for key in self.sink.order:
             it = dict(self.sink.items[key])
             p = it.pop("param")
-            it.update(p=p.data, vec_arena=vlo <= it["g"].data_ptr() < vhi)
+            it.update(p=p.data, vec_arena=vlo <= it["g"].data_ptr() < vhi, param_id=id(p))
             if self.peer is not None:
                 it = shard_item(it, self.rank, self.world)      # sharded optimiser: this rank's rows only
                 if it is None:
@@ -335,7 +389,26 @@ class Trainer:
                 it.update(m=m, v=v)
             items.append(it)
         self.sink.frozen = True
-        self.plan = K.OptPlan(items, self.dev)
+        if self.peer is None:
+            self.plan = K.OptPlan(items, self.dev)
+            return
+        # two item tables over one scratch buffer: the decoder's share (first in backward order) and the encoder's
+        dec_ids = set(id(p) for p in self.model.decoder.parameters()) if hasattr(self.model, "decoder") else set()
+        dec = [it for it in items if it["param_id"] in dec_ids]
+        enc = [it for it in items if it not in dec]
+        n_sn = sum(1 for it in items if it.get("u") is not None)
+        self._dots = torch.zeros(n_sn + 6, dtype=torch.float64, device=self.dev)
+        n_dec_sn = sum(1 for it in dec if it.get("u") is not None)
+        self.plan_dec = K.OptPlan(dec, self.dev, dots=self._dots, dot_base=0) if dec else None
+        self.plan = K.OptPlan(enc, self.dev, dots=self._dots, dot_base=n_dec_sn)
+        # the decoder's vectors must form a prefix of the vector arena (they are allocated in backward order)
+        sink = self.sink
+        dec_v = [sink.v_slots[k] for k in sink.v_slots if k in dec_ids]
+        enc_v = [sink.v_slots[k] for k in sink.v_slots if k not in dec_ids]
+        self._v_split = max((off + sink._round(n) for off, n in dec_v), default=0)
+        if enc_v and min(off for off, _ in enc_v) < self._v_split:
+            self._v_split = 0
+        self._pipelined_ok = self.plan_dec is not None and self._v_split > 0 and len(enc) > 0
 
     # -- CUDA graph of the whole step -----------------------------------------------------------------
     def _graph_ok(self, x):
@@ -426,8 +499,13 @@ class Trainer:
         scale = 1.0 / self.world if scaler is not None else 1.0 / (self.world * S)
         self.gnorm_sq.zero_()
         self._works, self._launched = [], 0     # an exception that escaped a previous backward must not leak buckets
+        pipelined = False
         if self.fused:
-            self.sink.begin_step()
+            will_pipeline = (self.peer is not None and self.plan is not None and self._pipelined_ok and self.pipeline and
+                             self.direct and not self.materialize_xhat)
+            self.sink.begin_step(zero_vecs_from=self._v_split if will_pipeline else 0)
+            if self.peer is not None and not will_pipeline:
+                self.sync()
             engine.set_grad_sink(self.sink)
             engine.set_materialize_xhat(self.materialize_xhat)
             try:
@@ -437,8 +515,11 @@ class Trainer:
                 try:
                     if self.direct and not self.materialize_xhat:
                         # the engine's own forward + backward, no torch.autograd in between (engine.train_step_direct)
+                        pipelined = self.peer is not None and self.plan is not None and self._pipelined_ok and self.pipeline
+                        self._step_scaler = scaler
                         loss, recon, kl_sum, mse = engine.train_step_direct(
-                            model, x, self.alpha, beta, S if (scaler is not None or S != 1.0) else None)
+                            model, x, self.alpha, beta, S if (scaler is not None or S != 1.0) else None,
+                            hooks=self if pipelined else None)
                     else:
                         x_hat, recon, kls, mse = model(x)
                         kl_sum = kls[0]
@@ -461,7 +542,7 @@ class Trainer:
                 self._finish_reduce()
             self.step_count += 1
             if self.peer is not None:
-                self._peer_step(b1, b2, scale, scaler)
+                self._peer_exchange(b1, b2, scale, scaler, pipelined)
             else:
                 K.opt_step(self.plan, self.lr, b1, b2, self.eps, self.wd, self.step_count, scale, self.gnorm_sq, scaler)
         else:
@@ -491,4 +572,8 @@ class Trainer:
     def scalars(self):
         """(loss, recon, kl_sum, mse, grad_norm) as Python floats - the only host synchronisation."""
         loss, recon, kl, mse = self._last
-        return float(loss), float(recon), float(kl), float(mse), float(self.gnorm_sq.sqrt())
+        gn = self.gnorm_sq
+        if self.peer is not None:                      # the decoder's share of the norm was accumulated on the peer stream
+            torch.cuda.current_stream(self.dev).wait_stream(self._peer_stream)
+            gn = gn + self.gnorm_dec
+        return float(loss), float(recon), float(kl), float(mse), float(gn.sqrt())

@@ -494,12 +494,12 @@ def minmax_transform(data, scale, minv, out=None, out_t=None, T=0):
 class OptPlan:
     """Emulated counterpart of kernels.OptPlan: keeps the item list (tensors) instead of a device table."""
 
-    def __init__(self, items, device):
+    def __init__(self, items, device, dots=None, dot_base=0):
         self.items = items
         self.n = len(items)
         self.n_sn = sum(1 for it in items if it.get("u") is not None)
-        self.dots = torch.zeros(self.n_sn + 6, dtype=torch.float64, device=device)
-        d = 0
+        self.dots = torch.zeros(self.n_sn + 6, dtype=torch.float64, device=device) if dots is None else dots
+        d = dot_base
         for it in items:
             if it.get("u") is not None:
                 it["dot_index"] = d
@@ -530,8 +530,9 @@ def _w_gemm_layout(full):
     return w
 
 
-def peer_reduce_dot(plan, want_bad, peer):
-    plan.dots.zero_()
+def peer_reduce_dot(plan, want_bad, peer, clear_dots=True):
+    if clear_dots:
+        plan.dots.zero_()
     me = peer["rank"]
     for it in plan.items:
         full, (lo, hi) = it["full"], it["rows"]
@@ -551,17 +552,26 @@ def peer_reduce_dot(plan, want_bad, peer):
             gs[me].view(-1)[lo:hi] = total.view(-1)[lo:hi]
             bad = not bool(torch.isfinite(total.view(-1)[lo:hi]).all())
         if want_bad and bad:
-            plan.dots[plan.n_sn] += 1
+            plan.dots[plan.dots.numel() - 6] += 1
+
+
+_STEP_ARGS = {}      # dots.data_ptr() -> (skip, step, grad_scale) left by the last phase-0/2 call (the device copy of AdamArgs)
 
 
 def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, scaler=None, peer=None, phase=0):
+    key = plan.dots.data_ptr()
+    if phase == 3:           # update only, scalars of the preceding phase-2 call on the same dots buffer
+        skip, step, grad_scale = _STEP_ARGS[key]
+        if skip:
+            return
+        return _opt_step_sharded(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, peer)
     if scaler is not None:
         # sg_scaler_state semantics (csrc/optim.cu opt_prologue_kernel)
         fl = scaler[:5].view(torch.float32)
         used = float(fl[0])
         grad_scale = grad_scale / used
         if phase == 2:
-            bad = float(plan.dots[plan.n_sn]) != 0.0
+            bad = float(plan.dots[plan.dots.numel() - 6]) != 0.0
         else:
             bad = any(not bool(torch.isfinite(it["g"]).all()) for it in plan.items)
         if bad:
@@ -570,6 +580,7 @@ def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_
             scaler[8] += 1
             scaler[9] = 1
             gnorm_sq.fill_(float("inf"))
+            _STEP_ARGS[key] = (True, step, grad_scale)
             return
         scaler[7] += 1
         scaler[9] = 0
@@ -578,6 +589,7 @@ def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_
             fl[0] = min(used * float(fl[1]), float(fl[4]))
             scaler[6] = 0
         step = int(scaler[7])
+    _STEP_ARGS[key] = (False, step, grad_scale)
     if peer is not None or any("full" in it for it in plan.items):
         return _opt_step_sharded(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, peer)
     for it in plan.items:

@@ -68,7 +68,7 @@ def _make_rank(dev, seed_g):
     return dict(flat=flat, weights=weights, vecs=vecs, items=items)
 
 
-def _run(K, dev, W, with_scaler):
+def _run(K, dev, W, with_scaler, split=False):
     ranks = [_make_rank(dev, 1000 * (r + 1)) for r in range(W)]
     # reference: the plain multi-tensor step (torch model) on the sum of all ranks' gradients
     ref = _make_rank(dev, 0)
@@ -88,12 +88,26 @@ def _run(K, dev, W, with_scaler):
                 s.update(m=torch.zeros(s["n"], device=dev), v=torch.zeros(s["n"], device=dev))
                 sh.append(s)
         rk["shards"] = sh
-        plans.append(K.OptPlan(sh, dev))
+        if split:
+            # two item tables over ONE scratch buffer, as the trainer splits decoder / encoder (Trainer._build_plan)
+            n_sn = sum(1 for it in sh if it.get("u") is not None)
+            dots = torch.zeros(n_sn + 6, dtype=torch.float64, device=dev)
+            first, second = sh[:len(sh) // 2], sh[len(sh) // 2:]
+            pa = K.OptPlan(first, dev, dots=dots, dot_base=0)
+            pb = K.OptPlan(second, dev, dots=dots, dot_base=sum(1 for it in first if it.get("u") is not None))
+            plans.append((pa, pb))
+        else:
+            plans.append(K.OptPlan(sh, dev))
         peers.append(K.make_peer(r, [q["weights"] for q in ranks], [q["vecs"] for q in ranks], [q["flat"] for q in ranks]))
         gn.append(torch.zeros(1, device=dev, dtype=torch.float64))
         scalers.append(RK.make_scaler_state(dev, 8.0) if with_scaler else None)
     for r in range(W):                                                   # (barrier) every rank reduces its shard
-        K.peer_reduce_dot(plans[r], with_scaler, peers[r])
+        if split:
+            K.peer_reduce_dot(plans[r][0], with_scaler, peers[r], clear_dots=True)
+            K.peer_reduce_dot(plans[r][1], with_scaler, peers[r], clear_dots=False)
+        else:
+            K.peer_reduce_dot(plans[r], with_scaler, peers[r])
+    dots_of = (lambda r: plans[r][0].dots) if split else (lambda r: plans[r].dots)
     # the step's only collective: all-reduce of the per-layer dots (+ overflow flag); shards see different subsets of
     # the spectral-norm layers only when a layer has fewer rows than ranks, so reduce by layer identity
     totals = {}
@@ -101,13 +115,17 @@ def _run(K, dev, W, with_scaler):
         for it in ranks[r]["shards"]:
             if it.get("u") is not None:
                 key = it["full"]["p"].data_ptr() - ranks[r]["flat"].data_ptr()
-                totals[key] = totals.get(key, 0.0) + float(plans[r].dots[it["dot_index"]])
+                totals[key] = totals.get(key, 0.0) + float(dots_of(r)[it["dot_index"]])
     for r in range(W):
         for it in ranks[r]["shards"]:
             if it.get("u") is not None:
-                plans[r].dots[it["dot_index"]] = totals[it["full"]["p"].data_ptr() - ranks[r]["flat"].data_ptr()]
+                dots_of(r)[it["dot_index"]] = totals[it["full"]["p"].data_ptr() - ranks[r]["flat"].data_ptr()]
     for r in range(W):
-        K.opt_step(plans[r], 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0 / W, gn[r], scalers[r], peer=peers[r], phase=2)
+        if split:      # scalars once (phase 2, second table), then the first table with the same scalars (phase 3)
+            K.opt_step(plans[r][1], 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0 / W, gn[r], scalers[r], peer=peers[r], phase=2)
+            K.opt_step(plans[r][0], 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0 / W, gn[r], scalers[r], peer=peers[r], phase=3)
+        else:
+            K.opt_step(plans[r], 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0 / W, gn[r], scalers[r], peer=peers[r], phase=2)
     if dev != "cpu":
         torch.cuda.synchronize()
     for r in range(W):
@@ -145,14 +163,14 @@ def test_shard_item_partitions_every_tensor():
 
 
 @pytest.mark.parametrize("W", [2, 3, 8])
-@pytest.mark.parametrize("with_scaler", [False, True])
-def test_peer_optimizer_virtual_ranks_cpu(W, with_scaler):
-    _run(emu, "cpu", W, with_scaler)
+@pytest.mark.parametrize("with_scaler,split", [(False, False), (True, False), (True, True)])
+def test_peer_optimizer_virtual_ranks_cpu(W, with_scaler, split):
+    _run(emu, "cpu", W, with_scaler, split)
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("W", [2, 3, 8])
-@pytest.mark.parametrize("with_scaler", [False, True])
-def test_peer_optimizer_virtual_ranks_gpu(W, with_scaler):
+@pytest.mark.parametrize("with_scaler,split", [(False, False), (True, False), (True, True), (False, True)])
+def test_peer_optimizer_virtual_ranks_gpu(W, with_scaler, split):
     from simulgen_vae_b200 import kernels as K
-    _run(K, "cuda", W, with_scaler)
+    _run(K, "cuda", W, with_scaler, split)
