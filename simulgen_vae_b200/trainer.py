@@ -395,7 +395,7 @@ class Trainer:
         # two item tables over one scratch buffer: the decoder's share (first in backward order) and the encoder's
         dec_ids = set(id(p) for p in self.model.decoder.parameters()) if hasattr(self.model, "decoder") else set()
         dec = [it for it in items if it["param_id"] in dec_ids]
-        enc = [it for it in items if it not in dec]
+        enc = [it for it in items if it["param_id"] not in dec_ids]
         n_sn = sum(1 for it in items if it.get("u") is not None)
         self._dots = torch.zeros(n_sn + 6, dtype=torch.float64, device=self.dev)
         n_dec_sn = sum(1 for it in dec if it.get("u") is not None)
