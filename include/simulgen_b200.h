@@ -282,7 +282,7 @@ typedef struct sg_peer {
     char* pbase[SG_MAX_PEERS];
 } sg_peer;
 int sg_peer_reduce_dot(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots, int n_dots,
-                       int want_bad_flag, int clear_dots, const sg_peer* peer, void* stream);
+                       int want_bad_flag, int clear_dots, int max_blocks, const sg_peer* peer, void* stream);
 /* phase 0: everything (dot pass, scalars, update).  phase 2: the dot pass has been done (sg_peer_reduce_dot + the
  * all-reduce of dots): scalars + update only.  phase 3: update only, with the scalars a phase-2 call on the SAME dots
  * buffer left there (the optimiser of one model split over two item tables - decoder / encoder - that share `dots`, so
@@ -290,7 +290,9 @@ int sg_peer_reduce_dot(const sg_opt_item* items_dev, const sg_opt_item* items_ho
  * peer (may be NULL): replicate the parameter stores to every rank. */
 int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots, int n_dots,
                 float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                double* gnorm_sq, sg_scaler_state* scaler, const sg_peer* peer, int phase, void* stream);
+                double* gnorm_sq, sg_scaler_state* scaler, const sg_peer* peer, int phase, int max_blocks, void* stream);
+/* max_blocks (sg_peer_reduce_dot, sg_opt_step): upper bound on the thread blocks of the launch (0 = one per 8192-element
+ * chunk); a launch that runs underneath the backward / forward pass on another stream passes 2 x SM count. */
 
 /* ---- preprocessing scan (modules/data_preprocess.py:65-165, SimulGen-VAE.py:279-283) --------------
  * data: the field matrix [R = P*T][N] (nodes innermost), float64 (is_f64 = 1) or float32 - the dtype the reference's

@@ -51,8 +51,8 @@ SIGNATURES = {
     "sg_philox_normal": [P, I, L, U, U, L, P, P],
     "sg_counter_add": [P, L, P],
     "sg_adamw_step": [P, P, P, P, L, F, F, F, F, F, I, F, P, P],
-    "sg_opt_step": [P, P, I, P, I, F, F, F, F, F, I, F, P, P, P, I, P],
-    "sg_peer_reduce_dot": [P, P, I, P, I, I, I, P, P],
+    "sg_opt_step": [P, P, I, P, I, F, F, F, F, F, I, F, P, P, P, I, I, P],
+    "sg_peer_reduce_dot": [P, P, I, P, I, I, I, I, P, P],
     "sg_sn_prepare": [P, P, I, P, L, I, I, P],
     "sg_assemble_batch": [P, I, P, P, P, P, P, I, I, I, I, U, U, I, P],
     "sg_minmax_fit": [P, I, P, L, L, P, L, P, P, I, P],

@@ -134,9 +134,12 @@ __global__ void __launch_bounds__(kOptThreads)
 peer_reduce_dot_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ OptPrefix pf,
                        const __grid_constant__ sg_peer pc, double* __restrict__ bad) {
     __shared__ double sh[32];
-    const int idx = find_item(pf, blockIdx.x);
+    // grid-stride over the 8192-element chunks: the grid may be much smaller than the chunk count (a launch that runs
+    // UNDERNEATH the backward pass keeps 2 blocks per SM so that the persistent GEMM CTAs still find room)
+    for (int chunk = blockIdx.x; chunk < pf.start[pf.n_items]; chunk += gridDim.x) {
+    const int idx = find_item(pf, chunk);
     const sg_opt_item it = items[idx];
-    const long long e0 = (long long)(blockIdx.x - pf.start[idx]) * kOptChunk;
+    const long long e0 = (long long)(chunk - pf.start[idx]) * kOptChunk;
     const long long e1 = min(it.n, e0 + kOptChunk);
     const bool vec_arena = (it.reserved & 1) != 0;
     const bool sn = it.u != nullptr;
@@ -176,6 +179,7 @@ peer_reduce_dot_kernel(const sg_opt_item* __restrict__ items, const __grid_const
     if (threadIdx.x == 0) {
         if (sn) atomicAdd(it.dot, t);
         if (bad != nullptr && !isfinite(t)) atomicAdd(bad, 1.0);
+    }
     }
 }
 
@@ -244,9 +248,10 @@ opt_step_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ O
         for (int r = 0; r < pc.world; ++r)
             if (r != pc.rank) *peer_param(pc, dst, r) = val;
     };
-    const int idx = find_item(pf, blockIdx.x);
+    for (int chunk = blockIdx.x; chunk < pf.start[pf.n_items]; chunk += gridDim.x) {      // grid-stride, see peer_reduce_dot_kernel
+    const int idx = find_item(pf, chunk);
     const sg_opt_item it = items[idx];
-    const long long e0 = (long long)(blockIdx.x - pf.start[idx]) * kOptChunk;
+    const long long e0 = (long long)(chunk - pf.start[idx]) * kOptChunk;
     const long long e1 = min(it.n, e0 + kOptChunk);
     const bool sn = it.u != nullptr;
     float inv_sigma = 1.f, coef = 0.f;
@@ -341,6 +346,7 @@ opt_step_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ O
         double t = block_sum((double)ss, sh);
         if (threadIdx.x == 0) atomicAdd(gnorm_sq, t);
     }
+    }
 }
 
 }  // namespace sg
@@ -381,7 +387,8 @@ static int check_peer(const sg_peer* peer, const char* who) {
 }
 
 extern "C" int sg_peer_reduce_dot(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots,
-                                  int n_dots, int want_bad_flag, int clear_dots, const sg_peer* peer, void* stream) {
+                                  int n_dots, int want_bad_flag, int clear_dots, int max_blocks, const sg_peer* peer,
+                                  void* stream) {
     SG_REQUIRE(peer != nullptr && dots != nullptr && n_dots >= 6, "peer_reduce_dot: missing arguments");
     if (check_peer(peer, "peer_reduce_dot")) return 1;
     cudaStream_t st = as_stream(stream);
@@ -391,14 +398,15 @@ extern "C" int sg_peer_reduce_dot(const sg_opt_item* items_dev, const sg_opt_ite
     if (build_prefix(items_host, n_items, pf, total, any_sn, "peer_reduce_dot")) return 1;
     if (clear_dots) cudaMemsetAsync(dots, 0, sizeof(double) * n_dots, st);
     double* bad = dots + (n_dots - 6);
-    peer_reduce_dot_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, *peer, want_bad_flag ? bad : nullptr);
+    const unsigned grid = (unsigned)((max_blocks > 0 && max_blocks < total) ? max_blocks : total);
+    peer_reduce_dot_kernel<<<grid, kOptThreads, 0, st>>>(items_dev, pf, *peer, want_bad_flag ? bad : nullptr);
     return check_launch("peer_reduce_dot");
 }
 
 extern "C" int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots,
                            int n_dots, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                            float grad_scale, double* gnorm_sq, sg_scaler_state* scaler, const sg_peer* peer, int phase,
-                           void* stream) {
+                           int max_blocks, void* stream) {
     // dots[0 .. n_dots - 6): one <G, W> per spectral-norm layer; then 1 double "non-finite gradient seen" and
     // sizeof(AdamArgs) = 40 bytes (5 doubles) for the device copy of the step's scalars
     SG_REQUIRE(dots != nullptr && n_dots >= 6, "opt_step: dots buffer needs >= 6 trailing scratch elements");
@@ -426,6 +434,7 @@ extern "C" int sg_opt_step(const sg_opt_item* items_dev, const sg_opt_item* item
         a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.wd = weight_decay; a.grad_scale = grad_scale;
         opt_prologue_kernel<<<1, 1, 0, st>>>(a, step, scaler, scaler != nullptr ? bad : nullptr, dev_args, gnorm_sq);
     }
-    opt_step_kernel<<<(unsigned)total, kOptThreads, 0, st>>>(items_dev, pf, dev_args, gnorm_sq, pc);
+    const unsigned grid = (unsigned)((max_blocks > 0 && max_blocks < total) ? max_blocks : total);
+    opt_step_kernel<<<grid, kOptThreads, 0, st>>>(items_dev, pf, dev_args, gnorm_sq, pc);
     return check_launch("opt_step");
 }

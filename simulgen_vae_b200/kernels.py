@@ -412,11 +412,11 @@ def make_peer(rank, weight_ptrs, vec_ptrs, param_ptrs):
     return pc
 
 
-def peer_reduce_dot(plan, want_bad, peer, clear_dots=True):
+def peer_reduce_dot(plan, want_bad, peer, clear_dots=True, max_blocks=0):
     """Fused reduce-scatter + <G, W> over peer memory for the shard `plan` describes (csrc/optim.cu)."""
     import ctypes
     _call("sg_peer_reduce_dot", plan.table.data_ptr(), ctypes.addressof(plan._host), plan.n, plan.dots.data_ptr(),
-          plan.dots.numel(), int(bool(want_bad)), int(bool(clear_dots)), ctypes.addressof(peer), _stream())
+          plan.dots.numel(), int(bool(want_bad)), int(bool(clear_dots)), int(max_blocks), ctypes.addressof(peer), _stream())
 
 
 SCALER_FIELDS = ("scale", "growth", "backoff", "min_scale", "max_scale",          # float32
@@ -439,7 +439,8 @@ def read_scaler_state(state):
     return dict(zip(SCALER_FIELDS, f + host[5:].tolist()))
 
 
-def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, scaler=None, peer=None, phase=0):
+def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, scaler=None, peer=None, phase=0,
+             max_blocks=0):
     """scaler: optional make_scaler_state() tensor - the dynamic loss scale of the fp16-operand mode; `step` is then
     ignored (the applied-step counter lives in the state) and grad_scale excludes the loss scale.
     peer / phase: data parallel over peer memory - phase 2 runs after peer_reduce_dot + the all-reduce of plan.dots and
@@ -450,7 +451,7 @@ def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_
     _call("sg_opt_step", plan.table.data_ptr(), ctypes.addressof(plan._host), plan.n, plan.dots.data_ptr(),
           plan.dots.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
           float(grad_scale), _p(gnorm_sq), _p(scaler), ctypes.addressof(peer) if peer is not None else None, int(phase),
-          _stream())
+          int(max_blocks), _stream())
 
 
 class SnPlan:

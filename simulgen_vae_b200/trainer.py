@@ -47,6 +47,11 @@ def _gemm_layout_elems(mod):
     return k * cout * ((cin + 7) // 8 * 8)
 
 
+def _os_env(name, default):
+    import os
+    return os.environ.get(name, default)
+
+
 def shard_item(it, rank, world):
     """The part of one optimiser item (engine.GradSink.items: p, g[, u, vv, sigma, Cout, Cin, Cin_p, k, flip]) that rank
     `rank` of `world` owns under the sharded optimiser, or None when its share is empty.  Spectral-norm weights are
@@ -155,6 +160,9 @@ class Trainer:
         self.plan_dec, self._dots, self._v_split, self._pipelined_ok = None, None, 0, False
         self._ev_dec_done, self._ev_reduced, self._step_scaler = None, None, None
         self._peer_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        # launches that run underneath the step on the peer stream keep a small resident footprint (blocks per SM x SMs)
+        self._bg_blocks = int(_os_env("SIMULGEN_B200_DP_BG_BLOCKS_PER_SM", "2")) * \
+            (torch.cuda.get_device_properties(dev).multi_processor_count if dev.type == "cuda" else 1)
         import os as _os
         # replay the step as one CUDA graph once it has run eagerly (single GPU, fp16 mode): opt-in, SIMULGEN_B200_GRAPH=1
         self.cuda_graph = bool(int(_os.environ.get("SIMULGEN_B200_GRAPH", "0"))) if cuda_graph is None else bool(cuda_graph)
@@ -330,7 +338,8 @@ class Trainer:
         ps.wait_stream(cur)
         with torch.cuda.stream(ps):
             dist.all_reduce(self._token2, group=self.pg)               # every rank's decoder gradients are complete
-            K.peer_reduce_dot(self.plan_dec, self._step_scaler is not None, self.peer, clear_dots=True)
+            K.peer_reduce_dot(self.plan_dec, self._step_scaler is not None, self.peer, clear_dots=True,
+                              max_blocks=self._bg_blocks)
             self._ev_reduced = torch.cuda.Event()
             self._ev_reduced.record(ps)
 
@@ -354,7 +363,7 @@ class Trainer:
             self.gnorm_dec.zero_()
             if self.plan_dec is not None:
                 K.opt_step(self.plan_dec, self.lr, b1, b2, self.eps, self.wd, self.step_count, scale, self.gnorm_dec, scaler,
-                           peer=self.peer, phase=3)
+                           peer=self.peer, phase=3, max_blocks=self._bg_blocks if pipelined else 0)
             dist.all_reduce(self.gnorm_dec, group=self.pg)              # closing barrier of the decoder's share
             self._ev_dec_done = torch.cuda.Event()
             self._ev_dec_done.record(ps)

@@ -530,7 +530,7 @@ def _w_gemm_layout(full):
     return w
 
 
-def peer_reduce_dot(plan, want_bad, peer, clear_dots=True):
+def peer_reduce_dot(plan, want_bad, peer, clear_dots=True, max_blocks=0):
     if clear_dots:
         plan.dots.zero_()
     me = peer["rank"]
@@ -558,7 +558,8 @@ def peer_reduce_dot(plan, want_bad, peer, clear_dots=True):
 _STEP_ARGS = {}      # dots.data_ptr() -> (skip, step, grad_scale) left by the last phase-0/2 call (the device copy of AdamArgs)
 
 
-def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, scaler=None, peer=None, phase=0):
+def opt_step(plan, lr, beta1, beta2, eps, weight_decay, step, grad_scale, gnorm_sq, scaler=None, peer=None, phase=0,
+             max_blocks=0):
     key = plan.dots.data_ptr()
     if phase == 3:           # update only, scalars of the preceding phase-2 call on the same dots buffer
         skip, step, grad_scale = _STEP_ARGS[key]

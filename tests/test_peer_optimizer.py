@@ -103,7 +103,7 @@ def _run(K, dev, W, with_scaler, split=False):
         scalers.append(RK.make_scaler_state(dev, 8.0) if with_scaler else None)
     for r in range(W):                                                   # (barrier) every rank reduces its shard
         if split:
-            K.peer_reduce_dot(plans[r][0], with_scaler, peers[r], clear_dots=True)
+            K.peer_reduce_dot(plans[r][0], with_scaler, peers[r], clear_dots=True, max_blocks=7)     # grid-stride path
             K.peer_reduce_dot(plans[r][1], with_scaler, peers[r], clear_dots=False)
         else:
             K.peer_reduce_dot(plans[r], with_scaler, peers[r])
@@ -123,7 +123,8 @@ def _run(K, dev, W, with_scaler, split=False):
     for r in range(W):
         if split:      # scalars once (phase 2, second table), then the first table with the same scalars (phase 3)
             K.opt_step(plans[r][1], 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0 / W, gn[r], scalers[r], peer=peers[r], phase=2)
-            K.opt_step(plans[r][0], 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0 / W, gn[r], scalers[r], peer=peers[r], phase=3)
+            K.opt_step(plans[r][0], 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0 / W, gn[r], scalers[r], peer=peers[r], phase=3,
+                       max_blocks=5)
         else:
             K.opt_step(plans[r], 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0 / W, gn[r], scalers[r], peer=peers[r], phase=2)
     if dev != "cpu":
