@@ -514,6 +514,10 @@ def _main():
                    "gflop_per_sample_fwd_bwd": gflop, "loss": scalars[0], "grad_norm": scalars[4],
                    "resident_input_format": "engine.PackedBatch: fp16 operand [N, B, T] written by the loader kernel" if packed_mode else "fp32 [B, N, T]",
                    "loss_scaler": scaler,
+                   "dp_exchange": (None if world == 1 else
+                                   ("peer memory: sharded optimiser, %s" % ("NVSwitch multicast (multimem.ld_reduce / multimem.st)"
+                                                                            if getattr(trainer, "multicast", False) else "P2P loads / stores")
+                                    if trainer.peer is not None else "nccl all-reduce overlapped with backward")),
                    "batch_sweep": sweep,
                    "notes": "operands of the tensor-core path are %s with fp32 accumulation (tcgen05 kind::f16); x_hat is not written to "
                             "HBM by the training step (train.py:142 discards it); pre-norm conv outputs and interior activation "

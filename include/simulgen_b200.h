@@ -280,6 +280,12 @@ typedef struct sg_peer {
     const char* wbase[SG_MAX_PEERS];
     const char* vbase[SG_MAX_PEERS];
     char* pbase[SG_MAX_PEERS];
+    /* NVSwitch multicast (NVLS) addresses of the same three buffers, or NULL: one multimem.ld_reduce returns the sum
+     * over ALL ranks' copies (reduced inside the switch: ingress 1/W of the P2P-load path), one multimem.st writes
+     * every rank's copy (egress 1/W of the P2P-store path). */
+    const char* wmc;
+    const char* vmc;
+    char* pmc;
 } sg_peer;
 int sg_peer_reduce_dot(const sg_opt_item* items_dev, const sg_opt_item* items_host, int n_items, double* dots, int n_dots,
                        int want_bad_flag, int clear_dots, int max_blocks, const sg_peer* peer, void* stream);

@@ -42,7 +42,7 @@ bench() {  # name [env...]
   echo "$line" > gpurun_out/r2_dp_${N}gpu_${name}_$TAG.json
   fmt "$name" "$line"
 }
-bench dp_peer_pipelined SIMULGEN_B200_DP=peer
-bench dp_peer_serial SIMULGEN_B200_DP=peer SIMULGEN_B200_DP_PIPELINE=0
+bench dp_peer_multicast SIMULGEN_B200_DP=peer
+bench dp_peer_p2p SIMULGEN_B200_DP=peer SIMULGEN_B200_DP_MULTICAST=0
 bench dp_nccl SIMULGEN_B200_DP=nccl
 cat $OUT

@@ -76,7 +76,8 @@ class OptItem(ctypes.Structure):
 
 class Peer(ctypes.Structure):
     """sg_peer of include/simulgen_b200.h"""
-    _fields_ = [("world", c_int), ("rank", c_int), ("wbase", c_void_p * 8), ("vbase", c_void_p * 8), ("pbase", c_void_p * 8)]
+    _fields_ = [("world", c_int), ("rank", c_int), ("wbase", c_void_p * 8), ("vbase", c_void_p * 8), ("pbase", c_void_p * 8),
+                ("wmc", c_void_p), ("vmc", c_void_p), ("pmc", c_void_p)]
 
 
 def load(half=False):

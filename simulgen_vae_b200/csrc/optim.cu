@@ -125,6 +125,34 @@ __device__ __forceinline__ const float* peer_grad(const sg_peer& pc, const float
 __device__ __forceinline__ float* peer_param(const sg_peer& pc, float* p, int r) {
     return reinterpret_cast<float*>(pc.pbase[r] + (reinterpret_cast<char*>(p) - pc.pbase[pc.rank]));
 }
+// NVSwitch multicast (NVLS) addresses of the element `g` / `p` of MY buffers
+__device__ __forceinline__ const float* mc_grad(const sg_peer& pc, const float* g, bool vec_arena) {
+    const char* mine = vec_arena ? pc.vbase[pc.rank] : pc.wbase[pc.rank];
+    return reinterpret_cast<const float*>((vec_arena ? pc.vmc : pc.wmc) + (reinterpret_cast<const char*>(g) - mine));
+}
+__device__ __forceinline__ float* mc_param(const sg_peer& pc, float* p) {
+    return reinterpret_cast<float*>(pc.pmc + (reinterpret_cast<char*>(p) - pc.pbase[pc.rank]));
+}
+// sum over every rank's copy, reduced inside the switch
+__device__ __forceinline__ float4 multimem_sum4(const float* mc) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+    return r;
+}
+__device__ __forceinline__ float multimem_sum1(const float* mc) {
+    float r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(r) : "l"(mc) : "memory");
+    return r;
+}
+// one store that lands in every rank's copy
+__device__ __forceinline__ void multimem_st4(float* mc, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_st1(float* mc, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(mc), "f"(v) : "memory");
+}
 
 // Fused reduce-scatter + dot over NVLink peer memory.  `items` describe this rank's shard of every tensor; for each of its
 // elements the gradient is loaded from all `world` arenas (world - 1 of them remote: coalesced 16-byte P2P loads on the
@@ -144,15 +172,20 @@ peer_reduce_dot_kernel(const sg_opt_item* __restrict__ items, const __grid_const
     const bool vec_arena = (it.reserved & 1) != 0;
     const bool sn = it.u != nullptr;
     const int W = pc.world;
+    const bool use_mc = (vec_arena ? pc.vmc : pc.wmc) != nullptr;
     float* gmine = const_cast<float*>(it.g);
     float acc = 0.f, z = 0.f;
     const bool direct = !sn || (it.k == 1 && !it.flip && it.Cin_p == it.Cin);
     if (direct && (it.n & 3) == 0 && aligned16(it.g, it.p)) {
         for (long long e = e0 + threadIdx.x * 4; e < e1; e += kOptThreads * 4) {
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = 0; r < W; ++r) {
-                const float4 v = *reinterpret_cast<const float4*>(peer_grad(pc, it.g + e, vec_arena, r));
-                g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+            if (use_mc) {
+                g = multimem_sum4(mc_grad(pc, it.g + e, vec_arena));
+            } else {
+                for (int r = 0; r < W; ++r) {
+                    const float4 v = *reinterpret_cast<const float4*>(peer_grad(pc, it.g + e, vec_arena, r));
+                    g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+                }
             }
             *reinterpret_cast<float4*>(gmine + e) = g;
             if (sn) {
@@ -170,7 +203,11 @@ peer_reduce_dot_kernel(const sg_opt_item* __restrict__ items, const __grid_const
                 decode(it, (int)e, o, q, gi);
             }
             float g = 0.f;
-            for (int r = 0; r < W; ++r) g += *peer_grad(pc, it.g + gi, vec_arena, r);
+            if (use_mc) {
+                g = multimem_sum1(mc_grad(pc, it.g + gi, vec_arena));
+            } else {
+                for (int r = 0; r < W; ++r) g += *peer_grad(pc, it.g + gi, vec_arena, r);
+            }
             gmine[gi] = g;
             if (sn) acc += g * it.p[e]; else z = fmaf(0.f, g, z);
         }
@@ -238,12 +275,15 @@ opt_step_kernel(const sg_opt_item* __restrict__ items, const __grid_constant__ O
     if (a.skip) return;
     // updated parameters go to this rank's buffer and, data parallel over peer memory, to every other rank's (fused
     // all-gather: world - 1 remote stores per element over NVLink)
+    const bool mc_st = pc.world > 1 && pc.pmc != nullptr;
     auto put4 = [&](float* dst, const float4& val) {
+        if (mc_st) { multimem_st4(mc_param(pc, dst), val); return; }        // lands in every rank's copy, mine included
         *reinterpret_cast<float4*>(dst) = val;
         for (int r = 0; r < pc.world; ++r)
             if (r != pc.rank) *reinterpret_cast<float4*>(peer_param(pc, dst, r)) = val;
     };
     auto put1 = [&](float* dst, float val) {
+        if (mc_st) { multimem_st1(mc_param(pc, dst), val); return; }
         *dst = val;
         for (int r = 0; r < pc.world; ++r)
             if (r != pc.rank) *peer_param(pc, dst, r) = val;

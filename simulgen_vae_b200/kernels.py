@@ -398,8 +398,9 @@ class OptPlan:
         self.n_sn = n_sn
 
 
-def make_peer(rank, weight_ptrs, vec_ptrs, param_ptrs):
-    """sg_peer: device pointers to every rank's weight-gradient arena, vector-gradient arena and flat parameter buffer."""
+def make_peer(rank, weight_ptrs, vec_ptrs, param_ptrs, multicast=None):
+    """sg_peer: device pointers to every rank's weight-gradient arena, vector-gradient arena and flat parameter buffer;
+    multicast: optional (weights, vecs, params) NVSwitch multicast addresses of the same buffers."""
     world = len(weight_ptrs)
     assert 1 <= world <= 8 and len(vec_ptrs) == world and len(param_ptrs) == world and 0 <= rank < world
     pc = _lib.Peer()
@@ -409,6 +410,8 @@ def make_peer(rank, weight_ptrs, vec_ptrs, param_ptrs):
         return x.data_ptr() if isinstance(x, torch.Tensor) else int(x)
     for r in range(world):
         pc.wbase[r], pc.vbase[r], pc.pbase[r] = ptr(weight_ptrs[r]), ptr(vec_ptrs[r]), ptr(param_ptrs[r])
+    if multicast is not None and all(multicast):
+        pc.wmc, pc.vmc, pc.pmc = int(multicast[0]), int(multicast[1]), int(multicast[2])
     return pc
 
 

@@ -93,13 +93,17 @@ class PeerMemory:
         self.group_name = (group if group is not None else torch.distributed.group.WORLD).group_name
 
     def empty(self, n, dtype=torch.float32):
-        """(tensor, [device pointer of rank r's copy for every r])"""
+        """(tensor, [device pointer of rank r's copy for every r], NVSwitch multicast address of the buffer or 0)"""
         t = self.symm_mem.empty(int(n), dtype=dtype, device=self.device)
         h = self.symm_mem.rendezvous(t, self.group_name)
         self.handles.append(h)
         ptrs = [int(x) for x in h.buffer_ptrs]
         assert ptrs[h.rank] == t.data_ptr(), "symmetric memory: own pointer mismatch"
-        return t, ptrs
+        try:
+            mc = int(h.multicast_ptr or 0)
+        except Exception:
+            mc = 0
+        return t, ptrs, mc
 
 
 class Trainer:
@@ -133,7 +137,10 @@ class Trainer:
         # arena overlapped with backward + replicated optimiser (round 1); "peer" falls back to "nccl" when symmetric
         # memory cannot be set up (and always on CPU / gloo)
         self.dp_mode = os.environ.get("SIMULGEN_B200_DP", dp_mode or "peer")
-        self.pipeline = os.environ.get("SIMULGEN_B200_DP_PIPELINE", "1") != "0"   # overlap the decoder's share of the exchange
+        # overlap the decoder's share of the exchange with the encoder's backward / the next forward.  Off by default:
+        # measured on 2 B200s it LOSES 0.2-0.9 ms (profiles/r2_dp_peer_pipeline_2gpu.txt) - the GPU is power-bound, a
+        # co-running exchange kernel slows the GEMMs by more than it hides
+        self.pipeline = os.environ.get("SIMULGEN_B200_DP_PIPELINE", "0") != "0"
         self.peer = None
         self.fused = fused
         if self.world > 1 and broadcast_init:
@@ -201,14 +208,14 @@ class Trainer:
         dist = torch.distributed
         try:
             pm = PeerMemory(self.pg, self.dev)
-            weights, wptrs = pm.empty(max(w_elems, 1))
-            vecs, vptrs = pm.empty(max(v_elems, 1))
+            weights, wptrs, wmc = pm.empty(max(w_elems, 1))
+            vecs, vptrs, vmc = pm.empty(max(v_elems, 1))
             allp = list(self.model.parameters())
             offs, total = [], 0
             for p in allp:
                 offs.append(total)
                 total += (p.numel() + 63) // 64 * 64
-            flat, pptrs = pm.empty(max(total, 1))
+            flat, pptrs, pmc = pm.empty(max(total, 1))
             ok = torch.ones(1, device=self.dev)
         except Exception as e:  # pragma: no cover - depends on the box
             ok = torch.zeros(1, device=self.dev)
@@ -228,7 +235,12 @@ class Trainer:
                 p.data = view
         rank = dist.get_rank(self.pg)
         self.peer_mem = pm
-        self.peer = K.make_peer(rank, wptrs, vptrs, pptrs)
+        import os
+        # NVSwitch multicast (NVLS): gradients are summed INSIDE the switch (multimem.ld_reduce) and parameters written
+        # to every rank with one store (multimem.st): NVLink traffic per GPU drops from (W-1)/W to 1/W of the buffers
+        use_mc = os.environ.get("SIMULGEN_B200_DP_MULTICAST", "1") != "0" and wmc and vmc and pmc
+        self.multicast = bool(use_mc)
+        self.peer = K.make_peer(rank, wptrs, vptrs, pptrs, (wmc, vmc, pmc) if use_mc else None)
         self.rank = rank
         self._flat_params = flat
         torch.cuda.synchronize(self.dev)

@@ -507,7 +507,7 @@ class OptPlan:
 
 
 # ---- sharded optimiser over peer memory (csrc/optim.cu: peer_reduce_dot_kernel, opt_step_kernel with sg_peer) -----------
-def make_peer(rank, weights, vecs, params):
+def make_peer(rank, weights, vecs, params, multicast=None):
     """Emulated sg_peer: the tensors themselves (every rank's weight-gradient arena, vector arena, flat parameters)."""
     return dict(rank=rank, world=len(weights), weights=list(weights), vecs=list(vecs), params=list(params))
 
