@@ -236,9 +236,11 @@ class Trainer:
         rank = dist.get_rank(self.pg)
         self.peer_mem = pm
         import os
-        # NVSwitch multicast (NVLS): gradients are summed INSIDE the switch (multimem.ld_reduce) and parameters written
-        # to every rank with one store (multimem.st): NVLink traffic per GPU drops from (W-1)/W to 1/W of the buffers
-        use_mc = os.environ.get("SIMULGEN_B200_DP_MULTICAST", "1") != "0" and wmc and vmc and pmc
+        # NVSwitch multicast (NVLS), opt-in: gradients summed INSIDE the switch (multimem.ld_reduce), parameters written to
+        # every rank with one store (multimem.st) - NVLink traffic per GPU drops from (W-1)/W to 1/W of the buffers.
+        # Correct (dp_check) but measured SLOWER than plain P2P loads / stores on this box at 2 and at 8 GPUs
+        # (41.9 vs 39.5 ms and 41.7 vs 40.7 ms per step, profiles/r2_dp_multicast_vs_p2p.txt), so it stays off.
+        use_mc = os.environ.get("SIMULGEN_B200_DP_MULTICAST", "0") != "0" and wmc and vmc and pmc
         self.multicast = bool(use_mc)
         self.peer = K.make_peer(rank, wptrs, vptrs, pptrs, (wmc, vmc, pmc) if use_mc else None)
         self.rank = rank
