@@ -341,11 +341,13 @@ def _main():
     if rank == 0:
         sampler.start()
     K.PROFILE = []
+    K.PROFILE_BYTES = 0
     l0 = K.LAUNCHES
     ms = _timed_steps(lambda i: trainer.step(pool[i % n_pool], beta=BETA, sample_offset=rank * B), args.steps, world, dev)
     clocks = sampler.stop() if rank == 0 else None
     launches = K.LAUNCHES - l0
     prof = K.PROFILE
+    gemm_alg_bytes = K.PROFILE_BYTES
     K.PROFILE = None
     gemm_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in prof)
     gemm_flops = sum(f for _, f, _, _ in prof) * (T / sg.tp_of(T, "bf16"))   # valid columns only
@@ -503,6 +505,10 @@ def _main():
         roofline = {"bound": "tensor", "kernel": "conv_gemm_tc2_kernel (tcgen05 cta_group::2 implicit-GEMM fprop/dgrad/wgrad)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                     "algorithmic_flop_per_launch": gemm_flops / max(len(prof), 1),
+                    "algorithmic_bytes_per_launch": gemm_alg_bytes / max(len(prof), 1),
+                    "traffic_source": "profiles/r2_gemm_traffic_b64.json: ncu dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch of "
+                                      "`python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --batch-sweep ''` (config 2, batch 64, fp16); "
+                                      "algorithmic_bytes_per_launch = every operand plane and the output moved once",
                     "peak_source": peak_src, "launches_timed": len(prof),
                     "share_of_step": gemm_ms / ms if ms > 0 else None}
     line = {

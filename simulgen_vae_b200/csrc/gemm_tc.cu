@@ -251,7 +251,10 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 3-D bf16 operand [planes][rows][cols] (cols contiguous), box 64 x 64 x 1, 128B swizzle, zero OOB fill
+// 3-D 16-bit operand [planes][rows][cols] (cols contiguous), box 64 x 64 x 1, 128B swizzle, zero OOB fill.
+// The tensor-map data type is BFLOAT16 in BOTH library builds (bf16 and, with -DSG_OP16_HALF, fp16 operands): TMA only
+// moves 2-byte elements here (no arithmetic, zero fill is all-zero bits in either format); the MMA's operand format is
+// set by the instruction descriptor (TcParams::a_fmt / b_fmt).
 static int make_map_op(CUtensorMap* m, const void* base, long long cols, long long rows, int planes,
                        long long plane_stride_elems) {
     EncodeTiledFn fn = get_encode_fn();

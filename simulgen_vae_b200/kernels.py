@@ -21,7 +21,11 @@ LAUNCHES = 0          # number of C-ABI calls (each launches >= 1 of our kernels
 PROFILE = None        # bench.py sets this to a list: (name, algorithmic_flops, start_event, end_event) per GEMM
 
 
-def _timed(name, flops, fn):
+PROFILE_BYTES = 0     # algorithmic operand + output bytes of the GEMMs timed into PROFILE (bench.py: roofline.traffic's yardstick)
+
+
+def _timed(name, flops, fn, nbytes=0):
+    global PROFILE_BYTES
     if PROFILE is None:
         fn()
         return
@@ -31,6 +35,12 @@ def _timed(name, flops, fn):
     fn()
     e1.record()
     PROFILE.append((name, flops, e0, e1))
+    PROFILE_BYTES += nbytes
+
+
+def _nb(*tensors):
+    """bytes of the given tensors (each read or written once: the algorithmic minimum of a GEMM)"""
+    return sum(t.numel() * t.element_size() for t in tensors if t is not None)
 
 
 _HALF = False         # library variant of the next call: set by _dt() whenever a 16-bit operand is seen
@@ -161,7 +171,7 @@ def conv_fprop(wg, act, bias, out, Cin, accumulate=False):
     assert act.shape[1] == Cin and out.shape[0] == Cout and out.numel() == Cout * R and wg.dtype == act.dtype
     _timed("fprop", 2.0 * Cin * Cout * k * R, lambda: _call(
         "sg_conv_fprop", _p(wg), ap, an, astr, _p(bias), _p(_f32(out, "out")), Cin, Cin_p, Cout, k, R, int(accumulate),
-        _dt(act), _stream()))
+        _dt(act), _stream()), _nb(wg, act[:k], out))
 
 
 def conv_fprop_gn(wg, act, bias, out, Cin, stats, T, G):
@@ -176,7 +186,7 @@ def conv_fprop_gn(wg, act, bias, out, Cin, stats, T, G):
     rowstat = torch.empty(2 * Cout * B, dtype=torch.float32, device=out.device) if act.dtype in OP16 else None
     _timed("fprop", 2.0 * Cin * Cout * k * B * Tp, lambda: _call(
         "sg_conv_fprop_gn", _p(wg), ap, an, astr, _p(bias), _p(out), out_bf16, Cin, Cin_p, Cout, k, B, T, Tp, int(G),
-        _p(_f32(stats, "stats")), _p(ws), _p(rowstat), _dt(act), _stream()))
+        _p(_f32(stats, "stats")), _p(ws), _p(rowstat), _dt(act), _stream()), _nb(wg, act[:k], out))
 
 
 def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
@@ -189,7 +199,7 @@ def conv_dgrad(wg, dy, dx, Cin, accumulate=False):
     dxd = _dt(dx)
     _timed("dgrad", 2.0 * Cin * Cout * k * R, lambda: _call(
         "sg_conv_dgrad", _p(wg), dp, dn, dstr, _p(dx), dxd, Cin, Cin_p, Cout, k, R, int(accumulate), _dt(dy),
-        _stream()))
+        _stream()), _nb(wg, dy[:k], dx))
 
 
 def set_sm_limit(sms):
@@ -222,7 +232,8 @@ def conv_wgrad(dy, act, dwg, Cin):
     R = dy.shape[2] * dy.shape[3]
     assert dy.shape[1] == Cout and act.shape[1] == Cin and dy.dtype == act.dtype
     _timed("wgrad", 2.0 * Cin * Cout * k * R, lambda: _call(
-        "sg_conv_wgrad", dp, dn, dstr, ap, an, astr, _p(_f32(dwg, "dwg")), Cin, Cin_p, Cout, k, R, _dt(act), _stream()))
+        "sg_conv_wgrad", dp, dn, dstr, ap, an, astr, _p(_f32(dwg, "dwg")), Cin, Cin_p, Cout, k, R, _dt(act), _stream()),
+        _nb(dy[:1], act[:k], dwg))
 
 
 # ---- GroupNorm + activation ---------------------------------------------------------------------
