@@ -13,7 +13,7 @@ from simulgen_vae_b200.trainer import Trainer  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 MODE = sys.argv[2] if len(sys.argv) > 2 else "packed"         # "packed": engine.PackedBatch inputs (bench.py's value loop); "fp32"
-cfg = bench.HEADLINE
+cfg = bench.CONFIGS[int(os.environ.get("PROFILE_CONFIG", "2"))]       # BASELINE.json configs[n-1]
 dev = torch.device("cuda")
 model = bench.build_engine_model(cfg, B, dev)
 tr = Trainer(model, lr=1e-3, alpha=1e6)

@@ -1,5 +1,5 @@
 """Training-step driver for the engine: the reference's step semantics (train.py:139-168) without
-its host synchronisations, plus data-parallel gradient all-reduce over NCCL.
+its host synchronisations, plus data parallelism (sharded optimiser over NVLink peer memory, or NCCL all-reduce).
 
   step(x):  VAE.forward -> alpha*recon + beta*sum(kl) -> backward
             -> (DP) bucketed all-reduce of the gradient arena, overlapped with the rest of backward
@@ -18,6 +18,8 @@ cross-check for the fused path in the tests and what the untouched reference tra
 with torch.optim.AdamW.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
@@ -45,11 +47,6 @@ def _gemm_layout_elems(mod):
     else:
         cout, cin, k = w.shape
     return k * cout * ((cin + 7) // 8 * 8)
-
-
-def _os_env(name, default):
-    import os
-    return os.environ.get(name, default)
 
 
 def shard_item(it, rank, world):
@@ -125,7 +122,6 @@ class Trainer:
         if not single_process and (process_group is not None or
                                    (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
-        import os
         bucket_mb = float(os.environ.get("SIMULGEN_B200_BUCKET_MB", bucket_mb))
         self.bucket_elems = int(bucket_mb * (1 << 20)) // 4
         # SMs kept free for NCCL's kernels while collectives overlap the backward pass (the persistent GEMM grids shrink
@@ -168,15 +164,14 @@ class Trainer:
         self._ev_dec_done, self._ev_reduced, self._step_scaler = None, None, None
         self._peer_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         # launches that run underneath the step on the peer stream keep a small resident footprint (blocks per SM x SMs)
-        self._bg_blocks = int(_os_env("SIMULGEN_B200_DP_BG_BLOCKS_PER_SM", "2")) * \
+        self._bg_blocks = int(os.environ.get("SIMULGEN_B200_DP_BG_BLOCKS_PER_SM", "2")) * \
             (torch.cuda.get_device_properties(dev).multi_processor_count if dev.type == "cuda" else 1)
-        import os as _os
         # replay the step as one CUDA graph once it has run eagerly (single GPU, fp16 mode): opt-in, SIMULGEN_B200_GRAPH=1
-        self.cuda_graph = bool(int(_os.environ.get("SIMULGEN_B200_GRAPH", "0"))) if cuda_graph is None else bool(cuda_graph)
+        self.cuda_graph = bool(int(os.environ.get("SIMULGEN_B200_GRAPH", "0"))) if cuda_graph is None else bool(cuda_graph)
         self._graphs, self._graph_pool, self._dev_counter, self._dev_counter_host = {}, None, None, -1
         # fused path: drive the engine's tapes directly instead of going through torch.autograd (SIMULGEN_B200_DIRECT=0:
         # the autograd Functions, as the reference's train.py uses them)
-        self.direct = _os.environ.get("SIMULGEN_B200_DIRECT", "1") != "0"
+        self.direct = os.environ.get("SIMULGEN_B200_DIRECT", "1") != "0"
         if fused:
             w_elems = v_elems = n_layers = 0
             wparams = set()
@@ -235,7 +230,6 @@ class Trainer:
                 p.data = view
         rank = dist.get_rank(self.pg)
         self.peer_mem = pm
-        import os
         # NVSwitch multicast (NVLS), opt-in: gradients summed INSIDE the switch (multimem.ld_reduce), parameters written to
         # every rank with one store (multimem.st) - NVLink traffic per GPU drops from (W-1)/W to 1/W of the buffers.
         # Correct (dp_check) but measured SLOWER than plain P2P loads / stores on this box at 2 and at 8 GPUs
