@@ -99,6 +99,72 @@ assemble_batch_kernel(const float* __restrict__ data, const int* __restrict__ id
     }
 }
 
+// Short rows (Tp == 8: static fields, T = 1 .. 8).  A warp per row would keep one lane of 32 busy over B * N rows.
+// Tiles of 32 channels x 32 samples instead: phase 1 walks the 32 * T contiguous floats each sample has in the tile
+// (lanes along (n, t): gather, augmentation and the fp32 store are coalesced) and leaves the values in shared memory,
+// phase 2 writes the operand rows (n, b) from there, lanes along b (16 contiguous bytes per lane).  The Philox keying
+// is the general kernel's: (seed, draw, dataset index, quad = n * Tp / 4 + t / 4), component t % 4.
+constexpr int kAugShortTile = 32;
+constexpr int kAugShortPitch = kAugShortTile * 8 + 1;
+
+__global__ void __launch_bounds__(kAugWarps * 32)
+assemble_batch_short_kernel(const float* __restrict__ data, const int* __restrict__ ids, const float* __restrict__ table,
+                            const float* __restrict__ inj, float* __restrict__ out, __nv_bfloat16* __restrict__ op, int B,
+                            int N, int T, uint64_t seed, uint64_t draw) {
+    __shared__ float xs[kAugShortTile][kAugShortPitch];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t sample_elems = (size_t)N * T;
+    const int tiles_b = (B + kAugShortTile - 1) / kAugShortTile;
+    const long long tiles = (long long)((N + kAugShortTile - 1) / kAugShortTile) * tiles_b;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int n0 = (int)(tile / tiles_b) * kAugShortTile, b0 = (int)(tile % tiles_b) * kAugShortTile;
+        const int run = min(kAugShortTile, N - n0) * T;
+        __syncthreads();
+        for (int bl = warp; bl < kAugShortTile && b0 + bl < B; bl += kAugWarps) {
+            const int b = b0 + bl;
+            const int idx = ids[b], oth = ids[B + b];
+            const float nl = table[b], sc = table[B + b], lam = table[2 * B + b], om = table[3 * B + b];
+            const size_t base = (size_t)n0 * T;
+            const float* src = data + (size_t)idx * sample_elems + base;
+            const float* src2 = oth >= 0 ? data + (size_t)oth * sample_elems + base : nullptr;
+            const float* nz = inj != nullptr ? inj + (size_t)b * sample_elems + base : nullptr;
+            float* dst = out != nullptr ? out + (size_t)b * sample_elems + base : nullptr;
+            for (int i = lane; i < run; i += 32) {
+                float v = __ldcs(src + i);
+                if (nl != 0.f) {
+                    float e;
+                    if (nz != nullptr) {
+                        e = __ldg(nz + i);
+                    } else {
+                        const int n = n0 + i / T, t = i % T;
+                        float q[4];
+                        philox_normal4(seed, draw, (uint64_t)idx, (uint64_t)n * 2 + (uint64_t)(t >> 2), q);
+                        e = (t & 2) ? ((t & 1) ? q[3] : q[2]) : ((t & 1) ? q[1] : q[0]);
+                    }
+                    v = __fadd_rn(v, __fmul_rn(e, nl));
+                }
+                v = __fmul_rn(v, sc);
+                if (src2 != nullptr) v = __fadd_rn(__fmul_rn(lam, v), __fmul_rn(om, __ldcs(src2 + i)));
+                if (dst != nullptr) dst[i] = v;
+                xs[bl][i] = v;
+            }
+        }
+        if (op == nullptr) continue;
+        __syncthreads();
+        const int b = b0 + lane;
+#pragma unroll
+        for (int j = 0; j < kAugShortTile / kAugWarps; ++j) {
+            const int nloc = warp + j * kAugWarps, n = n0 + nloc;
+            if (n < N && b < B) {
+                F8 r;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r.v[i] = i < T ? xs[lane][nloc * T + i] : 0.f;
+                store8(op + ((size_t)n * B + b) * 8, r);
+            }
+        }
+    }
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -119,6 +185,13 @@ extern "C" int sg_assemble_batch(const float* data, int P, const int* ids, const
     long long blocks = cdiv((long long)B * N, kAugWarps);
     int grid = (int)(blocks < 148LL * blocks_per_sm ? blocks : 148LL * blocks_per_sm);
     cudaStream_t st = as_stream(stream);
+    if (Tp == 8 && (reinterpret_cast<uintptr_t>(operand) & 15) == 0) {
+        const long long tiles = cdiv((long long)N, kAugShortTile) * cdiv((long long)B, kAugShortTile);
+        const long long cap = 148LL * (blocks_per_sm < 6 ? blocks_per_sm : 6);      // ~33 KB of shared memory per block
+        assemble_batch_short_kernel<<<(int)(tiles < cap ? tiles : cap), kAugWarps * 32, 0, st>>>(
+            data, ids, table, injected_noise, out, (__nv_bfloat16*)operand, B, N, T, seed, draw);
+        return check_launch("assemble_batch");
+    }
     if (vec)
         assemble_batch_kernel<true><<<grid, kAugWarps * 32, 0, st>>>(data, ids, table, injected_noise, out, (__nv_bfloat16*)operand,
                                                                      B, N, T, Tp, seed, draw);

@@ -29,6 +29,12 @@ static int persistent_grid(long long rows) {
     long long cap = 148LL * 8;
     return (int)(blocks < cap ? blocks : cap);
 }
+// short-row kernels (Tp == 8): 32 x 32 tiles, ~33 KB of shared memory per block -> 6 resident blocks per SM
+static int short_grid(int N, int B) {
+    long long tiles = cdiv((long long)N, 32) * cdiv((long long)B, 32);
+    long long cap = 148LL * 6;
+    return (int)(tiles < cap ? tiles : cap);
+}
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---------------------------------------------------------------------------------------------
@@ -1119,6 +1125,226 @@ recon_bwd_apply_fast_kernel(const YT* __restrict__ y, const float* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Short rows: Tp == 8 (T = 1 .. 8; the static configuration, Dim2 = 1, is T = 1 on 10^6 nodes x 512 samples).
+// A warp per row leaves 31 of 32 lanes idle there (measured: 207 + 204 + 67 ms of a 556 ms step in recon_fwd, recon_bwd
+// and pack_input at N = 10^6, B = 512).  Mapping of the short-row kernels: ONE THREAD PER ROW.  A block walks tiles of
+// 32 channels x 32 samples; warp w takes channels n0 + w, n0 + w + 8, ... and lane l the sample b0 + l, so the 32 rows a
+// warp touches per channel are 512 (16-bit) / 1024 (fp32) contiguous bytes of y / dy / the row sums.  The external fp32
+// tensors ([B][N][T]: x, x_hat) are contiguous along (n, t) instead: their tile goes through shared memory, read and
+// written in 32*T-float runs per sample.  No warp reductions per row (a row is one thread); dbias is one warp_sum per
+// (channel, 32 samples).
+// ---------------------------------------------------------------------------------------------
+constexpr int kShortTile = 32;
+constexpr int kShortPitch = kShortTile * 8 + 1;        // floats per sample in the staged tile (+1: conflict-free columns)
+constexpr int kShortRows = kShortTile / kWarpsPerBlock;  // channels per warp and tile
+
+// x[b0 .. b0+32)[n0 .. n0+32)[0 .. T) -> xs[sample][channel * T + t]
+__device__ __forceinline__ void short_stage_in(const float* __restrict__ x, float (*xs)[kShortPitch], int n0, int b0, int N,
+                                               int B, int T) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int run = min(kShortTile, N - n0) * T;
+    for (int bl = warp; bl < kShortTile && b0 + bl < B; bl += kWarpsPerBlock) {
+        const float* src = x + ((size_t)(b0 + bl) * N + n0) * T;
+        for (int i = lane; i < run; i += 32) xs[bl][i] = __ldg(src + i);
+    }
+}
+__device__ __forceinline__ void short_stage_out(float* __restrict__ x, float (*xs)[kShortPitch], int n0, int b0, int N,
+                                                int B, int T) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int run = min(kShortTile, N - n0) * T;
+    for (int bl = warp; bl < kShortTile && b0 + bl < B; bl += kWarpsPerBlock) {
+        float* dst = x + ((size_t)(b0 + bl) * N + n0) * T;
+        for (int i = lane; i < run; i += 32) dst[i] = xs[bl][i];
+    }
+}
+
+template <typename OT>
+__global__ void __launch_bounds__(kThreads)
+pack_input_short_kernel(const float* __restrict__ x, OT* __restrict__ out, int B, int N, int T) {
+    __shared__ float xs[kShortTile][kShortPitch];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_b = (B + kShortTile - 1) / kShortTile;
+    const long long tiles = (long long)((N + kShortTile - 1) / kShortTile) * tiles_b;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int n0 = (int)(tile / tiles_b) * kShortTile, b0 = (int)(tile % tiles_b) * kShortTile;
+        __syncthreads();
+        short_stage_in(x, xs, n0, b0, N, B, T);
+        __syncthreads();
+        const int b = b0 + lane;
+#pragma unroll
+        for (int j = 0; j < kShortRows; ++j) {
+            const int nl = warp + j * kWarpsPerBlock, n = n0 + nl;
+            if (n < N && b < B) {
+                F8 r;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r.v[i] = i < T ? xs[lane][nl * T + i] : 0.f;
+                store8(out + ((size_t)n * B + b) * 8, r);
+            }
+        }
+    }
+}
+
+// forward of the reconstruction head on short rows; x may be NULL (no loss: inference), XT = 16-bit: the packed operand
+template <typename YT, typename XT, bool MSE, bool ROWSUMS, bool XHAT>
+__global__ void __launch_bounds__(kThreads)
+recon_fwd_short_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const XT* __restrict__ x, float* __restrict__ x_hat,
+                       double* __restrict__ loss_sums, float4* __restrict__ rowsums, int N, int B, int T, int G,
+                       int loss_kind) {
+    constexpr bool kStageX = sizeof(XT) == 4;
+    __shared__ float xs[(kStageX || XHAT) ? kShortTile : 1][kShortPitch];
+    __shared__ double shm[2][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Cg = N / G;
+    const int tiles_b = (B + kShortTile - 1) / kShortTile;
+    const long long tiles = (long long)((N + kShortTile - 1) / kShortTile) * tiles_b;
+    const float2* mr2 = reinterpret_cast<const float2*>(mr);
+    const bool has_x = x != nullptr;
+    double d0 = 0.0, d1 = 0.0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int n0 = (int)(tile / tiles_b) * kShortTile, b0 = (int)(tile % tiles_b) * kShortTile;
+        if (kStageX || XHAT) __syncthreads();                 // the previous tile's readers / writers are done
+        if (kStageX && has_x) {
+            short_stage_in(reinterpret_cast<const float*>(x), xs, n0, b0, N, B, T);
+            __syncthreads();
+        }
+        const int b = b0 + lane;
+        F8 yv[kShortRows], xw[kShortRows];
+        bool ok[kShortRows];
+#pragma unroll
+        for (int j = 0; j < kShortRows; ++j) {                // every global load of the tile first
+            const int n = n0 + warp + j * kWarpsPerBlock;
+            ok[j] = n < N && b < B;
+            const size_t row = ok[j] ? (size_t)n * B + b : 0;
+            yv[j] = load8(y + row * 8);
+            if (!kStageX && has_x) xw[j] = load8(x + row * 8);
+        }
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kShortRows; ++j) {
+            const int nl = warp + j * kWarpsPerBlock, n = ok[j] ? n0 + nl : 0;
+            const float gam = __ldg(gamma + n), bet = __ldg(beta + n);
+            const float2 st = __ldg(mr2 + (ok[j] ? b : 0) * G + n / Cg);
+            const float a = gam * st.y, sh = bet - st.x * a, nm = -st.x * st.y;
+            float l0 = 0.f, l1 = 0.f, aL = 0.f, bL = 0.f, aM = 0.f, bM = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < T) {
+                    const float h = tanh_fast(fmaf(yv[j].v[i], a, sh));
+                    if (has_x) {
+                        const float xv = kStageX ? xs[lane][nl * T + i] : xw[j].v[i];
+                        const float d = h - xv;
+                        l1 = fmaf(d, d, l1);
+                        if (!MSE) l0 += loss_term(loss_kind, d);
+                        if (ROWSUMS) {
+                            const float om = fmaf(-h, h, 1.f);
+                            const float xn = fmaf(yv[j].v[i], st.y, nm);
+                            const float gm = d * om;
+                            aM += gm;
+                            bM = fmaf(gm, xn, bM);
+                            if (!MSE) {
+                                const float gl = loss_grad(loss_kind, d) * om;
+                                aL += gl;
+                                bL = fmaf(gl, xn, bL);
+                            }
+                        }
+                    }
+                    if (XHAT) xs[lane][nl * T + i] = h;       // this thread's own slot of the tile
+                }
+            }
+            if (ok[j]) {
+                if (ROWSUMS) {
+                    const float am = 2.f * aM, bm = 2.f * bM;
+                    rowsums[(size_t)n * B + b] = make_float4(MSE ? am : aL, MSE ? bm : bL, am, bm);
+                }
+                s0 += MSE ? l1 : l0;
+                s1 += l1;
+            }
+        }
+        d0 += (double)s0;
+        d1 += (double)s1;
+        if (XHAT) {
+            __syncthreads();
+            short_stage_out(x_hat, xs, n0, b0, N, B, T);
+        }
+    }
+    if (has_x) {
+        double t0 = block_sum(d0, shm[0]);
+        double t1 = block_sum(d1, shm[1]);
+        if (threadIdx.x == 0) {
+            atomicAdd(&loss_sums[0], t0);
+            atomicAdd(&loss_sums[1], t1);
+        }
+    }
+}
+
+// one-pass backward (step 2) on short rows: dy = c1 * g + c2 * y + c3 per element, zero padding, dbias accumulated
+template <typename YT, typename XT, typename OT, bool MSE>
+__global__ void __launch_bounds__(kThreads)
+recon_bwd_apply_short_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, const XT* __restrict__ x, const float* __restrict__ scal,
+                             const double* __restrict__ S, OT* __restrict__ dy, float* __restrict__ dbias, int N, int B,
+                             int T, int G, int loss_kind, float inv_n) {
+    constexpr bool kStageX = sizeof(XT) == 4;
+    __shared__ float xs[kStageX ? kShortTile : 1][kShortPitch];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Cg = N / G;
+    const int tiles_b = (B + kShortTile - 1) / kShortTile;
+    const long long tiles = (long long)((N + kShortTile - 1) / kShortTile) * tiles_b;
+    const float2* mr2 = reinterpret_cast<const float2*>(mr);
+    const float ga = scal[0], gm = scal[1];
+    const float g2 = 2.f * (ga + gm);
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int n0 = (int)(tile / tiles_b) * kShortTile, b0 = (int)(tile % tiles_b) * kShortTile;
+        if (kStageX) {
+            __syncthreads();
+            short_stage_in(reinterpret_cast<const float*>(x), xs, n0, b0, N, B, T);
+            __syncthreads();
+        }
+        const int b = b0 + lane;
+        F8 yv[kShortRows], xw[kShortRows];
+        bool ok[kShortRows];
+#pragma unroll
+        for (int j = 0; j < kShortRows; ++j) {
+            const int n = n0 + warp + j * kWarpsPerBlock;
+            ok[j] = n < N && b < B;
+            const size_t row = ok[j] ? (size_t)n * B + b : 0;
+            yv[j] = load8(y + row * 8);
+            if (!kStageX) xw[j] = load8(x + row * 8);
+        }
+#pragma unroll
+        for (int j = 0; j < kShortRows; ++j) {
+            const int nl = warp + j * kWarpsPerBlock, n = n0 + nl;          // warp-uniform
+            if (n >= N) break;
+            const int bb = ok[j] ? b : 0, g = n / Cg;
+            const float gam = __ldg(gamma + n), bet = __ldg(beta + n);
+            const float2 st = __ldg(mr2 + bb * G + g);
+            const float mean = st.x, rstd = st.y;
+            const float a = gam * rstd, sh = bet - mean * a;
+            const float m1 = (float)S[(size_t)(bb * G + g) * 2] * inv_n;
+            const float m2 = (float)S[(size_t)(bb * G + g) * 2 + 1] * inv_n;
+            const float c1 = rstd * gam, c2 = -rstd * rstd * m2, c3 = rstd * (mean * rstd * m2 - m1);
+            F8 o;
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                o.v[i] = 0.f;
+                if (i < T) {
+                    const float h = tanh_fast(fmaf(yv[j].v[i], a, sh));
+                    const float d = h - (kStageX ? xs[lane][nl * T + i] : xw[j].v[i]);
+                    const float gg = (MSE ? g2 * d : ga * loss_grad(loss_kind, d) + gm * 2.f * d) * fmaf(-h, h, 1.f);
+                    o.v[i] = fmaf(c1, gg, fmaf(c2, yv[j].v[i], c3));
+                    acc += o.v[i];
+                }
+            }
+            if (ok[j]) store8(dy + ((size_t)n * B + b) * 8, o);
+            acc = warp_sum(ok[j] ? acc : 0.f);
+            if (lane == 0) atomicAdd(dbias + n, acc);
+        }
+    }
+}
+
 // backward, step 1 of the one-pass path: fold the forward's row sums with the upstream scalars.
 // grid (ceil(Cg / 64), G), block 256: warp w handles channels c0 + w, c0 + w + 8, ... (< 64 per block)
 // dgamma[c] = sum_b Bx, dbeta[c] = sum_b A, S[b][g] += gamma_c * (A, Bx)  with (A, Bx) = ga*(.L) + gm*(.M)
@@ -1386,6 +1612,11 @@ int sg_pack_input(const void* xv, int x_dtype, void* out, int B, int N, int T, i
         return check_launch("pack_input");
     }
     const float* x = (const float*)xv;
+    if (Tp == 8 && aligned16(out)) {                         // short rows: one thread per row (static fields)
+        if (is_op16(dtype)) pack_input_short_kernel<__nv_bfloat16><<<short_grid(N, B), kThreads, 0, st>>>(x, (__nv_bfloat16*)out, B, N, T);
+        else                pack_input_short_kernel<float><<<short_grid(N, B), kThreads, 0, st>>>(x, (float*)out, B, N, T);
+        return check_launch("pack_input");
+    }
     bool vec = (T % 4 == 0) && aligned16(x);
 #define SG_PACK(OT, VEC) pack_input_kernel<OT, VEC><<<grid, kThreads, 0, st>>>(x, (OT*)out, B, N, T, Tp)
     if (is_op16(dtype)) { if (vec) SG_PACK(__nv_bfloat16, true); else SG_PACK(__nv_bfloat16, false); }
@@ -1532,6 +1763,21 @@ int sg_recon_fwd(const void* y, int y_dtype, const float* mr, const float* gamma
     int grid = persistent_grid((long long)N * B) * 2;
     const bool mse = loss_kind == SG_LOSS_MSE;
     const bool ybf = is_op16(y_dtype);
+    if (Tp == 8 && aligned16(y) && (!x16 || aligned16(xv))) {   // short rows: one thread per row (static fields)
+        grid = short_grid(N, B);
+#define SG_SH(YT, XT, MSE, RS, XH) \
+    recon_fwd_short_kernel<YT, XT, MSE, RS, XH><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, (const XT*)xv, x_hat, loss_sums, \
+                                                                           (float4*)rowsums, N, B, T, G, loss_kind)
+#define SG_SH2(YT, XT, MSE) do { \
+        if (rowsums) { if (x_hat) SG_SH(YT, XT, MSE, true, true); else SG_SH(YT, XT, MSE, true, false); } \
+        else         { if (x_hat) SG_SH(YT, XT, MSE, false, true); else SG_SH(YT, XT, MSE, false, false); } } while (0)
+        if (x16)      { if (mse) SG_SH2(__nv_bfloat16, __nv_bfloat16, true); else SG_SH2(__nv_bfloat16, __nv_bfloat16, false); }
+        else if (ybf) { if (mse) SG_SH2(__nv_bfloat16, float, true); else SG_SH2(__nv_bfloat16, float, false); }
+        else          { if (mse) SG_SH2(float, float, true); else SG_SH2(float, float, false); }
+#undef SG_SH2
+#undef SG_SH
+        return check_launch("recon_fwd");
+    }
     if (vec && xv != nullptr && (T & 7) == 0 && (long long)N * B < (1LL << 31)) {
         grid = persistent_grid(N);                           // one warp per channel
 #define SG_FAST(YT, XT, MSE, RS, XH) \
@@ -1592,6 +1838,22 @@ int sg_recon_bwd(const void* y, int y_dtype, const float* mr, const float* gamma
                                                                                dbeta, S, N, B, G);
         bool vec = (T % 4 == 0) && aligned16(x);
         const bool mse = loss_kind == SG_LOSS_MSE;
+        if (Tp == 8 && aligned16(y) && (!x16 || aligned16(xv)) && aligned16(dy)) {   // short rows: one thread per row
+            grid = short_grid(N, B);
+#define SG_AS(YT, XT, OT, MSE) \
+    recon_bwd_apply_short_kernel<YT, XT, OT, MSE><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, (const XT*)xv, scal, S, (OT*)dy, dbias, \
+                                                                             N, B, T, G, loss_kind, (float)inv_n)
+            if (x16) {
+                if (mse) SG_AS(bf, bf, bf, true); else SG_AS(bf, bf, bf, false);
+            } else if (is_op16(dtype)) {
+                if (ybf) { if (mse) SG_AS(bf, float, bf, true); else SG_AS(bf, float, bf, false); }
+                else     { if (mse) SG_AS(float, float, bf, true); else SG_AS(float, float, bf, false); }
+            } else {
+                if (mse) SG_AS(float, float, float, true); else SG_AS(float, float, float, false);
+            }
+#undef SG_AS
+            return check_launch("recon_bwd");
+        }
         if (vec && (T & 7) == 0 && (long long)N * B < (1LL << 31)) {
             grid = persistent_grid(N);                       // one warp per channel; dbias written, not accumulated
 #define SG_AF(YT, XT, OT, MSE) \

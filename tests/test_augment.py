@@ -90,6 +90,48 @@ def test_assemble_batch_philox_noise_and_operand():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("T", [1, 5, 8])
+@pytest.mark.parametrize("with_operand", [False, True])
+def test_assemble_batch_short_rows(T, with_operand):
+    """Static fields (T <= 8, rows padded to 8): the tile kernel (one thread per row instead of a warp) - bit-exact against
+    the torch model with injected noise, ragged 32 x 32 tiles on both axes; Philox noise keyed on the dataset index."""
+    from simulgen_vae_b200 import kernels as K
+    P, N, B = 9, 75, 70
+    dev = "cuda"
+    g = torch.Generator().manual_seed(3)
+    data = torch.randn(P, N, T, generator=g).to(dev)
+    idx = torch.randint(0, P, (B,), generator=g)
+    other = torch.where(torch.rand(B, generator=g) < 0.5, torch.randint(0, P, (B,), generator=g), torch.full((B,), -1))
+    ids = torch.stack([idx, other]).to(torch.int32).to(dev)
+    lam = torch.rand(B, generator=g)
+    table = torch.stack([torch.where(torch.rand(B, generator=g) < 0.5, torch.full((B,), 0.03), torch.zeros(B)),
+                         1.0 + 0.1 * torch.rand(B, generator=g), lam, 1.0 - lam]).float().to(dev)
+    noise = torch.randn(B, N, T, generator=g).to(dev)
+    outs = []
+    for fn in (K.assemble_batch, emu.assemble_batch):
+        out = torch.full((B, N, T), 7.0, device=dev)
+        op = torch.full((1, N, B, 8), 3.0, device=dev, dtype=torch.float16) if with_operand else None
+        fn(data, ids, table, noise, out, 5, 0, op)
+        outs.append((out, op))
+    assert torch.equal(outs[0][0], outs[1][0])
+    if with_operand:
+        assert torch.equal(outs[0][1], outs[1][1])
+        only = torch.full((1, N, B, 8), 3.0, device=dev, dtype=torch.float16)
+        K.assemble_batch(data, ids, table, noise, None, 5, 0, only)          # operand-only batch
+        assert torch.equal(only, outs[0][1])
+    zeros = torch.zeros(P, N, T, device=dev)
+    ids2 = torch.stack([torch.arange(B) % P, torch.full((B,), -1)]).to(torch.int32).to(dev)
+    table2 = torch.tensor([[0.05], [1.0], [1.0], [0.0]]).repeat(1, B).to(dev)
+    o1, o2 = torch.empty(B, N, T, device=dev), torch.empty(B, N, T, device=dev)
+    K.assemble_batch(zeros, ids2, table2, None, o1, 11, 0)
+    K.assemble_batch(zeros, ids2, table2, None, o2, 11, 1)
+    assert torch.equal(o1[0], o1[P]) and not torch.equal(o1[0], o1[1]) and not torch.equal(o1, o2)
+    uniq = o1[:P]                                          # P * N * T independent draws (>= 675): 5-sigma bounds
+    n = uniq.numel()
+    assert abs(float(uniq.std()) - 0.05) < 5 * 0.05 / (2 * n) ** 0.5 and abs(float(uniq.mean())) < 5 * 0.05 / n ** 0.5
+
+
+@pytest.mark.gpu
 def test_trainer_step_with_packed_operand_equals_plain_step():
     """The loader can emit the bf16 operand of the first conv together with the batch; feeding it to Trainer.step must
     give the same step as letting the encoder pack x itself."""

@@ -44,8 +44,8 @@ def close(a, b, tol, what=""):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-def test_pack_unpack(dtype):
-    B, N, T = 3, 37, 20
+@pytest.mark.parametrize("B,N,T", [(3, 37, 20), (70, 75, 1), (33, 64, 5), (3, 37, 8)])   # Tp == 8: short-row kernel (32 x 32 tiles)
+def test_pack_unpack(dtype, B, N, T):
     x = rnd(B, N, T)
     out = torch.full((1, N, B, tp_of(T)), 7.0, device=DEV, dtype=dtype)
     ref = torch.empty_like(out)
@@ -216,9 +216,10 @@ def test_gn_act_fwd_bwd(case, dtype, y16, d16, P, T):
 
 @pytest.mark.parametrize("loss", ["MSE", "MAE", "smoothL1", "Huber"])
 @pytest.mark.parametrize("with_ext,one_pass", [(False, False), (True, False), (False, True)])
-@pytest.mark.parametrize("T,y_bf16", [(21, False), (24, False), (24, True), (21, True)])   # 24: fast path (T % 8 == 0)
+@pytest.mark.parametrize("T,y_bf16", [(21, False), (24, False), (24, True), (21, True),    # 24: fast path (T % 8 == 0)
+                                      (1, False), (1, True), (5, True), (8, False)])         # Tp == 8: short-row kernels
 def test_recon_fwd_bwd(loss, with_ext, one_pass, T, y_bf16):
-    N, B, G = 40, 3, 8
+    N, B, G = (40, 3, 8) if T > 8 else (72, 70, 8)         # short rows: 32 x 32 tiles with ragged edges on both axes
     Tp = tp_of(T)
     kind = K.LOSS_KINDS[loss]
     y = cr(N, B, T, seed=1) * 2.0
@@ -477,11 +478,12 @@ def test_opt_step_dynamic_loss_scaler_skips_overflowed_steps(where):
 @pytest.mark.parametrize("loss", ["MSE", "MAE", "smoothL1", "Huber"])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("with_xhat", [False, True])
-def test_recon_head_with_packed_operand_target(loss, dtype, with_xhat):
+@pytest.mark.parametrize("T", [200, 8])                    # 8: short-row kernels
+def test_recon_head_with_packed_operand_target(loss, dtype, with_xhat, T):
     """The reconstruction head reading its target from the packed 16-bit operand of x ([N, B, Tp], the layout of y;
     engine.loss_target() == "operand") instead of the fp32 [B, N, T] tensor: forward sums, optional x_hat and the one-pass
     backward against the torch model fed the same rounded target."""
-    N, B, G, T = 264, 5, 8, 200
+    N, B, G = (264, 5, 8) if T > 8 else (72, 70, 8)
     Tp = engine.tp_of(T, "bf16")
     kind = K.LOSS_KINDS[loss]
     y = (rnd(N, B, Tp, seed=1) * 2.0).to(dtype)
