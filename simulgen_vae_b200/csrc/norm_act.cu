@@ -35,6 +35,13 @@ static int short_grid(int N, int B) {
     long long cap = 148LL * 6;
     return (int)(tiles < cap ? tiles : cap);
 }
+// short-row GroupNorm kernels: one warp per (<= 8 channels of a group, 32 samples) task
+static int short_task_grid(int C, int B, int G) {
+    const int Cg = C / G;
+    long long tasks = (long long)G * cdiv(Cg, 8) * cdiv(B, 32);
+    long long blocks = cdiv(tasks, kWarpsPerBlock), cap = 148LL * 8;
+    return (int)(blocks < cap ? blocks : cap);
+}
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---------------------------------------------------------------------------------------------
@@ -1204,21 +1211,22 @@ recon_fwd_short_kernel(const YT* __restrict__ y, const float* __restrict__ mr, c
     double d0 = 0.0, d1 = 0.0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int n0 = (int)(tile / tiles_b) * kShortTile, b0 = (int)(tile % tiles_b) * kShortTile;
+        const int b = b0 + lane;
+        typename RawOf<YT>::type yw[kShortRows];              // unconverted: nothing depends on the loads before the barrier
+        typename RawOf<XT>::type xr[kShortRows];
+        bool ok[kShortRows];
+#pragma unroll
+        for (int j = 0; j < kShortRows; ++j) {                // every global load of the tile first: the y rows are in
+            const int n = n0 + warp + j * kWarpsPerBlock;     // flight while the x tile is staged
+            ok[j] = n < N && b < B;
+            const size_t row = ok[j] ? (size_t)n * B + b : 0;
+            yw[j] = load_raw(y + row * 8);
+            if (!kStageX && has_x) xr[j] = load_raw(x + row * 8);
+        }
         if (kStageX || XHAT) __syncthreads();                 // the previous tile's readers / writers are done
         if (kStageX && has_x) {
             short_stage_in(reinterpret_cast<const float*>(x), xs, n0, b0, N, B, T);
             __syncthreads();
-        }
-        const int b = b0 + lane;
-        F8 yv[kShortRows], xw[kShortRows];
-        bool ok[kShortRows];
-#pragma unroll
-        for (int j = 0; j < kShortRows; ++j) {                // every global load of the tile first
-            const int n = n0 + warp + j * kWarpsPerBlock;
-            ok[j] = n < N && b < B;
-            const size_t row = ok[j] ? (size_t)n * B + b : 0;
-            yv[j] = load8(y + row * 8);
-            if (!kStageX && has_x) xw[j] = load8(x + row * 8);
         }
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -1228,18 +1236,21 @@ recon_fwd_short_kernel(const YT* __restrict__ y, const float* __restrict__ mr, c
             const float2 st = __ldg(mr2 + (ok[j] ? b : 0) * G + n / Cg);
             const float a = gam * st.y, sh = bet - st.x * a, nm = -st.x * st.y;
             float l0 = 0.f, l1 = 0.f, aL = 0.f, bL = 0.f, aM = 0.f, bM = 0.f;
+            const F8 yv = cvt8(yw[j]);
+            F8 xw;
+            if (!kStageX && has_x) xw = cvt8(xr[j]);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (i < T) {
-                    const float h = tanh_fast(fmaf(yv[j].v[i], a, sh));
+                    const float h = tanh_fast(fmaf(yv.v[i], a, sh));
                     if (has_x) {
-                        const float xv = kStageX ? xs[lane][nl * T + i] : xw[j].v[i];
+                        const float xv = kStageX ? xs[lane][nl * T + i] : xw.v[i];
                         const float d = h - xv;
                         l1 = fmaf(d, d, l1);
                         if (!MSE) l0 += loss_term(loss_kind, d);
                         if (ROWSUMS) {
                             const float om = fmaf(-h, h, 1.f);
-                            const float xn = fmaf(yv[j].v[i], st.y, nm);
+                            const float xn = fmaf(yv.v[i], st.y, nm);
                             const float gm = d * om;
                             aM += gm;
                             bM = fmaf(gm, xn, bM);
@@ -1297,21 +1308,22 @@ recon_bwd_apply_short_kernel(const YT* __restrict__ y, const float* __restrict__
     const float g2 = 2.f * (ga + gm);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int n0 = (int)(tile / tiles_b) * kShortTile, b0 = (int)(tile % tiles_b) * kShortTile;
+        const int b = b0 + lane;
+        typename RawOf<YT>::type yw[kShortRows];
+        typename RawOf<XT>::type xr[kShortRows];
+        bool ok[kShortRows];
+#pragma unroll
+        for (int j = 0; j < kShortRows; ++j) {                // in flight while the x tile is staged
+            const int n = n0 + warp + j * kWarpsPerBlock;
+            ok[j] = n < N && b < B;
+            const size_t row = ok[j] ? (size_t)n * B + b : 0;
+            yw[j] = load_raw(y + row * 8);
+            if (!kStageX) xr[j] = load_raw(x + row * 8);
+        }
         if (kStageX) {
             __syncthreads();
             short_stage_in(reinterpret_cast<const float*>(x), xs, n0, b0, N, B, T);
             __syncthreads();
-        }
-        const int b = b0 + lane;
-        F8 yv[kShortRows], xw[kShortRows];
-        bool ok[kShortRows];
-#pragma unroll
-        for (int j = 0; j < kShortRows; ++j) {
-            const int n = n0 + warp + j * kWarpsPerBlock;
-            ok[j] = n < N && b < B;
-            const size_t row = ok[j] ? (size_t)n * B + b : 0;
-            yv[j] = load8(y + row * 8);
-            if (!kStageX) xw[j] = load8(x + row * 8);
         }
 #pragma unroll
         for (int j = 0; j < kShortRows; ++j) {
@@ -1327,14 +1339,17 @@ recon_bwd_apply_short_kernel(const YT* __restrict__ y, const float* __restrict__
             const float c1 = rstd * gam, c2 = -rstd * rstd * m2, c3 = rstd * (mean * rstd * m2 - m1);
             F8 o;
             float acc = 0.f;
+            const F8 yv = cvt8(yw[j]);
+            F8 xw;
+            if (!kStageX) xw = cvt8(xr[j]);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 o.v[i] = 0.f;
                 if (i < T) {
-                    const float h = tanh_fast(fmaf(yv[j].v[i], a, sh));
-                    const float d = h - (kStageX ? xs[lane][nl * T + i] : xw[j].v[i]);
+                    const float h = tanh_fast(fmaf(yv.v[i], a, sh));
+                    const float d = h - (kStageX ? xs[lane][nl * T + i] : xw.v[i]);
                     const float gg = (MSE ? g2 * d : ga * loss_grad(loss_kind, d) + gm * 2.f * d) * fmaf(-h, h, 1.f);
-                    o.v[i] = fmaf(c1, gg, fmaf(c2, yv[j].v[i], c3));
+                    o.v[i] = fmaf(c1, gg, fmaf(c2, yv.v[i], c3));
                     acc += o.v[i];
                 }
             }
@@ -1527,6 +1542,218 @@ __global__ void recon_scalars_kernel(const float* g_loss, const float* g_mse, fl
 }
 
 // ---------------------------------------------------------------------------------------------
+// GroupNorm / activation kernels on short rows (Tp == 8, static fields): one thread per row, like the recon head above.
+// A warp takes a (slice of <= 8 channels of one group, 32 consecutive samples) task: lane = sample, so every access of a
+// channel is 32 contiguous rows, the per-channel sums are one warp_sum + one atomic per (channel, 32 samples) and the
+// per-(sample, group) sums of the backward stay in the lane's registers over the slice (2 double atomics per lane and
+// task instead of 2 per row).  The layers these run on are small (C <= 5120 channels), so dtype, activation and plane
+// count are RUN-TIME arguments (uniform branches): three kernels instead of another ~150 template instantiations.
+// ---------------------------------------------------------------------------------------------
+constexpr int kShortSlice = 8;
+
+__device__ __forceinline__ F8 load8_rt(const void* p, bool is16, size_t elem) {
+    return is16 ? load8(reinterpret_cast<const __nv_bfloat16*>(p) + elem) : load8(reinterpret_cast<const float*>(p) + elem);
+}
+__device__ __forceinline__ void store8_rt(void* p, bool is16, size_t elem, const F8& r) {
+    if (is16) store8(reinterpret_cast<__nv_bfloat16*>(p) + elem, r);
+    else store8(reinterpret_cast<float*>(p) + elem, r);
+}
+// o holds zeros for t >= T: plane pl is the row shifted by pl - PLANES / 2, zero outside [0, T)
+template <int PLANES>
+__device__ __forceinline__ void store_planes_short(void* base, bool is16, size_t row_off, long long pstride, const F8& o, int T) {
+#pragma unroll
+    for (int pl = 0; pl < PLANES; ++pl) {
+        F8 r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int j = i + pl - PLANES / 2;
+            r.v[i] = (j >= 0 && j < 8 && i < T) ? o.v[j] : 0.f;
+        }
+        store8_rt(base, is16, (size_t)pl * pstride + row_off, r);
+    }
+}
+__device__ __forceinline__ void store_planes_short_n(void* base, bool is16, size_t row_off, int planes, long long pstride,
+                                                     const F8& o, int T) {
+    if (planes == 5) store_planes_short<5>(base, is16, row_off, pstride, o, T);
+    else if (planes == 3) store_planes_short<3>(base, is16, row_off, pstride, o, T);
+    else store8_rt(base, is16, row_off, o);
+}
+
+struct ShortTask {
+    int c_lo, c_hi, g, b;
+    bool ok;
+};
+// task -> (channel slice inside one group, sample of this lane); Cg = channels per group (C without GroupNorm)
+__device__ __forceinline__ ShortTask short_task(int task, int nchunk, int slices, int Cg, int B, int lane) {
+    ShortTask t;
+    const int cs = task / nchunk, ch = task - cs * nchunk;
+    t.g = cs / slices;
+    t.c_lo = t.g * Cg + (cs - t.g * slices) * kShortSlice;
+    t.c_hi = min(t.c_lo + kShortSlice, (t.g + 1) * Cg);
+    t.b = ch * 32 + lane;
+    t.ok = t.b < B;
+    if (!t.ok) t.b = B - 1;
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads)
+gn_act_fwd_short_kernel(const void* __restrict__ y, int y16, const float* __restrict__ mr, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, const void* __restrict__ res, int r16, float res_scale, int act,
+                        int post, void* __restrict__ out_op, int o16, int planes, long long pstride,
+                        float* __restrict__ out_f32, int C, int B, int T, int G) {
+    const int lane = threadIdx.x & 31;
+    const bool has_gn = mr != nullptr;
+    const int Cg = has_gn ? C / G : C, groups = has_gn ? G : 1;
+    const int slices = (Cg + kShortSlice - 1) / kShortSlice, nchunk = (B + 31) / 32;
+    const int tasks = groups * slices * nchunk, wstride = gridDim.x * kWarpsPerBlock;
+    const float2* mr2 = reinterpret_cast<const float2*>(mr);
+    for (int task = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < tasks; task += wstride) {
+        const ShortTask t = short_task(task, nchunk, slices, Cg, B, lane);
+        float mean = 0.f, rstd = 1.f;
+        if (has_gn) {
+            const float2 st = __ldg(mr2 + t.b * G + t.g);
+            mean = st.x;
+            rstd = st.y;
+        }
+#pragma unroll 2
+        for (int c = t.c_lo; c < t.c_hi; ++c) {
+            const size_t row = ((size_t)c * B + t.b) * 8;
+            const F8 yv = load8_rt(y, y16, row);
+            F8 rv;
+            if (res != nullptr) rv = load8_rt(res, r16, row);
+            float a = 1.f, sh = 0.f;
+            if (has_gn) {
+                a = __ldg(gamma + c) * rstd;
+                sh = __ldg(beta + c) - mean * a;
+            }
+            F8 o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                o.v[i] = 0.f;
+                if (i < T) {
+                    float pre = res_scale * act_f(act, fmaf(yv.v[i], a, sh));
+                    if (res != nullptr) pre += rv.v[i];
+                    if (post) pre = gelu_f(pre);
+                    o.v[i] = pre;
+                }
+            }
+            if (t.ok) {
+                if (out_f32 != nullptr) store8(out_f32 + row, o);
+                if (out_op != nullptr) store_planes_short_n(out_op, o16, row, planes, pstride, o, T);
+            }
+        }
+    }
+}
+
+// pass 1 of the GroupNorm backward (see gn_bwd_pass1_kernel): dout -> dz in place, dres, dgamma / dbeta / S
+__global__ void __launch_bounds__(kThreads)
+gn_bwd_pass1_short_kernel(Pass1Args p, int y16, int d16, int r16, int act, int post, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, double* __restrict__ S, float* __restrict__ dres, int dres_accumulate) {
+    const int lane = threadIdx.x & 31;
+    const int Cg = p.C / p.G;
+    const int slices = (Cg + kShortSlice - 1) / kShortSlice, nchunk = (p.B + 31) / 32;
+    const int tasks = p.G * slices * nchunk, wstride = gridDim.x * kWarpsPerBlock;
+    const float2* mr2 = reinterpret_cast<const float2*>(p.mr);
+    const bool has_res = p.res != nullptr;
+    for (int task = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < tasks; task += wstride) {
+        const ShortTask t = short_task(task, nchunk, slices, Cg, p.B, lane);
+        const float2 st = __ldg(mr2 + t.b * p.G + t.g);
+        const float mean = st.x, rstd = st.y, nm = -st.x * st.y;
+        float SA = 0.f, SB = 0.f;                             // gamma-weighted sums of this lane's sample over the slice
+#pragma unroll 2
+        for (int c = t.c_lo; c < t.c_hi; ++c) {
+            const size_t row = ((size_t)c * p.B + t.b) * 8;
+            const F8 yv = load8_rt(p.y, y16, row), dv = load8_rt(p.dout, d16, row);
+            F8 rv;
+            if (post && has_res) rv = load8_rt(p.res, r16, row);
+            const float gm = __ldg(p.gamma + c);
+            const float a = gm * rstd, sh = __ldg(p.beta + c) - mean * a;
+            F8 dz, dp;
+            float A = 0.f, Bx = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                dz.v[i] = 0.f;
+                dp.v[i] = 0.f;
+                if (i < p.T) {
+                    float val, dval;
+                    act_both(act, fmaf(yv.v[i], a, sh), val, dval);
+                    float d = dv.v[i];
+                    if (post) d *= gelu_grad_f(fmaf(p.res_scale, val, has_res ? rv.v[i] : 0.f));
+                    dp.v[i] = d;
+                    dz.v[i] = p.res_scale * d * dval;
+                    A += dz.v[i];
+                    Bx = fmaf(dz.v[i], fmaf(yv.v[i], rstd, nm), Bx);
+                }
+            }
+            if (t.ok) {
+                store8_rt(p.dout, d16, row, dz);
+                if (dres != nullptr) {
+                    if (dres_accumulate) {
+                        const F8 old = load8(dres + row);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dp.v[i] += old.v[i];
+                    }
+                    store8(dres + row, dp);
+                }
+            } else {
+                A = 0.f;
+                Bx = 0.f;
+            }
+            SA = fmaf(gm, A, SA);
+            SB = fmaf(gm, Bx, SB);
+            const float sa = warp_sum(A), sb = warp_sum(Bx);
+            if (lane == 0) {
+                atomicAdd(&dgamma[c], sb);
+                atomicAdd(&dbeta[c], sa);
+            }
+        }
+        if (t.ok) {
+            atomicAdd(&S[(size_t)(t.b * p.G + t.g) * 2], (double)SA);
+            atomicAdd(&S[(size_t)(t.b * p.G + t.g) * 2 + 1], (double)SB);
+        }
+    }
+}
+
+// pass 2: dy = c1 * dz + c2 * y + c3 (zero padding), shifted operand planes, dbias
+__global__ void __launch_bounds__(kThreads)
+gn_bwd_pass2_short_kernel(const void* __restrict__ y, int y16, const void* __restrict__ dz, int d16,
+                          const float* __restrict__ mr, const float* __restrict__ gamma, const double* __restrict__ S,
+                          void* __restrict__ dy, int o16, int planes, long long pstride, float* __restrict__ dbias, int C,
+                          int B, int T, int G, float inv_n) {
+    const int lane = threadIdx.x & 31;
+    const int Cg = C / G;
+    const int slices = (Cg + kShortSlice - 1) / kShortSlice, nchunk = (B + 31) / 32;
+    const int tasks = G * slices * nchunk, wstride = gridDim.x * kWarpsPerBlock;
+    const float2* mr2 = reinterpret_cast<const float2*>(mr);
+    for (int task = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < tasks; task += wstride) {
+        const ShortTask t = short_task(task, nchunk, slices, Cg, B, lane);
+        const float2 st = __ldg(mr2 + t.b * G + t.g);
+        const float m1 = (float)S[(size_t)(t.b * G + t.g) * 2] * inv_n;
+        const float m2 = (float)S[(size_t)(t.b * G + t.g) * 2 + 1] * inv_n;
+        const float c2 = -st.y * st.y * m2, c3 = st.y * (st.x * st.y * m2 - m1);
+#pragma unroll 2
+        for (int c = t.c_lo; c < t.c_hi; ++c) {
+            const size_t row = ((size_t)c * B + t.b) * 8;
+            const F8 yv = load8_rt(y, y16, row), zv = load8_rt(dz, d16, row);
+            const float c1 = st.y * __ldg(gamma + c);
+            F8 o;
+            float db = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                o.v[i] = 0.f;
+                if (i < T) {
+                    o.v[i] = fmaf(c1, zv.v[i], fmaf(c2, yv.v[i], c3));
+                    db += o.v[i];
+                }
+            }
+            if (t.ok) store_planes_short_n(dy, o16, row, planes, pstride, o, T);
+            db = warp_sum(t.ok ? db : 0.f);
+            if (lane == 0 && dbias != nullptr) atomicAdd(&dbias[c], db);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-side dispatch over the template parameters
 // ---------------------------------------------------------------------------------------------
 template <typename OT, typename RT, typename YT, int ACT, bool POST>
@@ -1678,6 +1905,14 @@ int sg_gn_act_fwd(const void* y, int y_dtype, const float* mr, const float* gamm
     if (G <= 0) G = 1;
     typedef __nv_bfloat16 h16;
     const bool y16 = is_op16(y_dtype), r16 = res != nullptr && !res_is_f32;
+    SG_REQUIRE(!r16 || is_op16(dtype), "gn_act_fwd: fp32 mode takes an fp32 residual");
+    if (Tp == 8 && aligned16(y) && aligned16(res) && aligned16(out_op) && aligned16(out_f32) && (plane_stride & 7) == 0) {
+        const int g = mr != nullptr ? G : 1;                 // short rows: one thread per row (static fields)
+        gn_act_fwd_short_kernel<<<short_task_grid(C, B, g), kThreads, 0, st>>>(y, y16, mr, gamma, beta, res, r16, res_scale, act,
+                                                                              post_gelu, out_op, is_op16(dtype), planes,
+                                                                              plane_stride, out_f32, C, B, T, G);
+        return check_launch("gn_act_fwd");
+    }
 #define SG_FW(OT, RT, YT) return launch_fwd<OT, RT, YT>(act, post_gelu, y, mr, gamma, beta, res, res_scale, out_op, planes, plane_stride, out_f32, C, B, T, Tp, G, st)
     if (is_op16(dtype)) {
         if (y16) { if (r16) SG_FW(h16, h16, h16); else SG_FW(h16, float, h16); }
@@ -1721,6 +1956,17 @@ int sg_gn_act_bwd(const void* y, int y_dtype, const float* mr, const float* gamm
         p.y = y; p.dout = dout; p.mr = mr; p.gamma = gamma; p.beta = beta; p.res = res; p.res_scale = res_scale;
         p.C = C; p.B = B; p.T = T; p.Tp = Tp; p.G = G;
         const bool y16 = is_op16(y_dtype), d16 = is_op16(dout_dtype);
+        SG_REQUIRE(!r16 || is_op16(dtype), "gn_act_bwd: fp32 mode takes an fp32 residual");
+        if (Tp == 8 && aligned16(y) && aligned16(res) && aligned16(dout) && aligned16(dy) && aligned16(dres) &&
+            (plane_stride & 7) == 0) {                        // short rows: one thread per row (static fields)
+            const int grid = short_task_grid(C, B, G);
+            gn_bwd_pass1_short_kernel<<<grid, kThreads, 0, st>>>(p, y16, d16, r16, act, post_gelu, dgamma, dbeta, ws, dres,
+                                                                 dres_accumulate);
+            const float inv_n = (float)(1.0 / ((double)(C / G) * T));
+            gn_bwd_pass2_short_kernel<<<grid, kThreads, 0, st>>>(y, y16, dout, d16, mr, gamma, ws, dy, is_op16(dtype), planes,
+                                                                 plane_stride, dbias, C, B, T, G, inv_n);
+            return check_launch("gn_act_bwd");
+        }
 #define SG_BG(OT, RT, YT, DT) return launch_bwd_gn<OT, RT, YT, DT>(act, post_gelu, p, (OT*)dy, planes, plane_stride, dgamma, dbeta, dbias, dres, dres_accumulate, ws, st)
         if (is_op16(dtype)) {
             if (r16) {

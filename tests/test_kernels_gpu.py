@@ -154,15 +154,19 @@ CASES = [
 @pytest.mark.parametrize("dtype,y16,d16", [(torch.bfloat16, False, False), (torch.float32, False, False),
                                            (torch.float16, False, False), (torch.float16, True, True),
                                            (torch.float16, True, False), (torch.bfloat16, False, True)])
-@pytest.mark.parametrize("P,T", [(1, 21), (3, 21), (5, 21), (3, 300), (5, 200), (1, 200)])
+@pytest.mark.parametrize("P,T", [(1, 21), (3, 21), (5, 21), (3, 300), (5, 200), (1, 200),
+                                 (1, 1), (3, 1), (5, 1), (5, 5), (3, 8)])          # Tp == 8: short-row kernels
 def test_gn_act_fwd_bwd(case, dtype, y16, d16, P, T):
     """T=21 / 200: rows of <= 256 elements (one segment per lane, shifted planes by warp shuffle);
     T=300: longer rows (several segments per lane, planes staged through shared memory).
+    T<=8: short rows (static fields): one thread per row.
     y16 / d16: the pre-norm conv output / the incoming gradient stored in the 16-bit operand format (GroupNorm layers)."""
     use_gn, act, res_kind, res_scale, post = case
     if (y16 or d16) and not use_gn:
         pytest.skip("16-bit y / dout exist for GroupNorm layers only")
     C, B, G = 48, 19, 8                         # 19 samples: two (channel, 16-sample chunk) tasks, the second ragged
+    if T <= 8:
+        C, B = 80, 70                           # short rows: (8 + 2)-channel slices per group, 32-sample chunks, the last ragged
     Tp = tp_of(T)
     y = cr(C, B, T, seed=1) * 1.5 + 0.3
     if y16:
