@@ -187,7 +187,9 @@ extern "C" int sg_assemble_batch(const float* data, int P, const int* ids, const
     cudaStream_t st = as_stream(stream);
     if (Tp == 8 && (reinterpret_cast<uintptr_t>(operand) & 15) == 0) {
         const long long tiles = cdiv((long long)N, kAugShortTile) * cdiv((long long)B, kAugShortTile);
-        const long long cap = 148LL * (blocks_per_sm < 6 ? blocks_per_sm : 6);      // ~33 KB of shared memory per block
+        int nb = 0;                                           // the grid is persistent: launch exactly what is resident
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, assemble_batch_short_kernel, kAugWarps * 32, 0) != cudaSuccess || nb < 1) nb = 1;
+        const long long cap = 148LL * (blocks_per_sm < nb ? blocks_per_sm : nb);
         assemble_batch_short_kernel<<<(int)(tiles < cap ? tiles : cap), kAugWarps * 32, 0, st>>>(
             data, ids, table, injected_noise, out, (__nv_bfloat16*)operand, B, N, T, seed, draw);
         return check_launch("assemble_batch");

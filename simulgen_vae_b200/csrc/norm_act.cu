@@ -29,18 +29,38 @@ static int persistent_grid(long long rows) {
     long long cap = 148LL * 8;
     return (int)(blocks < cap ? blocks : cap);
 }
-// short-row kernels (Tp == 8): 32 x 32 tiles, ~33 KB of shared memory per block -> 6 resident blocks per SM
-static int short_grid(int N, int B) {
-    long long tiles = cdiv((long long)N, 32) * cdiv((long long)B, 32);
-    long long cap = 148LL * 6;
-    return (int)(tiles < cap ? tiles : cap);
+// Persistent short-row kernels (Tp == 8) split their tiles evenly over the grid, so the grid must be exactly what is
+// RESIDENT: with 888 blocks launched and 4-5 per SM resident (registers), the last 148-296 blocks ran alone after the
+// first wave and held a sixth to a third of the work (ncu, profiles/r2_ncu_config4_short_summary.txt: 39-43 % of the
+// warp slots active on average).  The occupancy query is per kernel instantiation.
+template <typename KernelT>
+static int resident_grid(KernelT kernel, long long work_blocks, int max_per_sm = 16) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kThreads, 0) != cudaSuccess || nb < 1) nb = 1;
+    if (nb > max_per_sm) nb = max_per_sm;
+    const long long cap = 148LL * nb;
+    return (int)(work_blocks < cap ? work_blocks : cap);
 }
+// warp-per-task persistent kernels (GroupNorm / activation): fixed 148 x 8 grid.  SIMULGEN_B200_GN_GRID=1 launches exactly
+// the resident grid for layers with many tasks per warp instead (no partial last wave) - measured on a B200 at the
+// headline shapes: no consistent gain (5-plane 16-bit backward 0.321 -> 0.347 ms, 1-plane fp32 backward 0.304 -> 0.288 ms,
+// step 38.0 / 38.3 vs 38.5 / 38.4 ms; profiles/r2_gn_grid_ab.txt), so it stays off.
+template <typename KernelT>
+static int task_grid(KernelT kernel, long long tasks, size_t smem) {
+    static const int mode = [] { const char* e = getenv("SIMULGEN_B200_GN_GRID"); return e ? atoi(e) : 0; }();
+    const int wide = persistent_grid(tasks);
+    if (mode == 0) return wide;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kThreads, smem) != cudaSuccess || nb < 1) return wide;
+    const long long resident = 148LL * nb;
+    if (resident < wide && tasks >= 4 * resident * kWarpsPerBlock) return (int)resident;
+    return wide;
+}
+static long long short_tiles(int N, int B) { return cdiv((long long)N, 32) * cdiv((long long)B, 32); }
 // short-row GroupNorm kernels: one warp per (<= 8 channels of a group, 32 samples) task
-static int short_task_grid(int C, int B, int G) {
+static long long short_task_blocks(int C, int B, int G) {
     const int Cg = C / G;
-    long long tasks = (long long)G * cdiv(Cg, 8) * cdiv(B, 32);
-    long long blocks = cdiv(tasks, kWarpsPerBlock), cap = 148LL * 8;
-    return (int)(blocks < cap ? blocks : cap);
+    return cdiv((long long)G * cdiv(Cg, 8) * cdiv(B, 32), kWarpsPerBlock);
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -1761,8 +1781,8 @@ static void launch_fwd_t(const void* y, const float* mr, const float* gamma, con
                          float res_scale, void* out_op, int planes, long long pstride, float* out_f32, int C, int B, int T,
                          int Tp, int G, cudaStream_t st) {
     size_t sm = (planes > 1 && out_op && (Tp >> 3) > 32) ? sizeof(float) * kWarpsPerBlock * (Tp + 8) : 0;
-    const int grid = persistent_grid((long long)C * cdiv(B, kChunkB));
-#define SG_FP(PL) gn_act_fwd_kernel<OT, RT, YT, ACT, POST, PL><<<grid, kThreads, sm, st>>>( \
+    const long long tasks = (long long)C * cdiv(B, kChunkB);
+#define SG_FP(PL) gn_act_fwd_kernel<OT, RT, YT, ACT, POST, PL><<<task_grid(gn_act_fwd_kernel<OT, RT, YT, ACT, POST, PL>, tasks, sm), kThreads, sm, st>>>( \
         (const YT*)y, mr, gamma, beta, (const RT*)res, res_scale, (OT*)out_op, pstride, out_f32, C, B, T, Tp, G)
     if (out_op == nullptr || planes == 1) SG_FP(1); else if (planes == 3) SG_FP(3); else SG_FP(5);
 #undef SG_FP
@@ -1804,15 +1824,15 @@ static int launch_bwd_plain(int act, int post, const BwdArgs& p, OT* dy, int pla
 template <typename OT, typename RT, typename YT, typename DT>
 static int launch_bwd_gn(int act, int post, const Pass1Args& p, OT* dy, int planes, long long pstride, float* dgamma,
                          float* dbeta, float* dbias, float* dres, int dres_accumulate, double* ws, cudaStream_t st) {
-    const int grid = persistent_grid((long long)p.C * cdiv(p.B, kChunkB));
-#define SG_P1(ACT, POST) gn_bwd_pass1_kernel<RT, YT, DT, ACT, POST><<<grid, kThreads, 0, st>>>(p, dgamma, dbeta, ws, dres, dres_accumulate)
+    const long long tasks = (long long)p.C * cdiv(p.B, kChunkB);
+#define SG_P1(ACT, POST) gn_bwd_pass1_kernel<RT, YT, DT, ACT, POST><<<task_grid(gn_bwd_pass1_kernel<RT, YT, DT, ACT, POST>, tasks, 0), kThreads, 0, st>>>(p, dgamma, dbeta, ws, dres, dres_accumulate)
     if (act == SG_ACT_GELU) { if (post) SG_P1(SG_ACT_GELU, true); else SG_P1(SG_ACT_GELU, false); }
     else if (act == SG_ACT_TANH) { if (post) SG_P1(SG_ACT_TANH, true); else SG_P1(SG_ACT_TANH, false); }
     else { if (post) SG_P1(SG_ACT_NONE, true); else SG_P1(SG_ACT_NONE, false); }
 #undef SG_P1
     const size_t sm = (planes > 1 && (p.Tp >> 3) > 32) ? sizeof(float) * kWarpsPerBlock * (p.Tp + 8) : 0;
     const float inv_n = (float)(1.0 / ((double)(p.C / p.G) * p.T));
-#define SG_P2(PL) gn_bwd_pass2_kernel<OT, YT, DT, PL><<<grid, kThreads, sm, st>>>((const YT*)p.y, (const DT*)p.dout, p.mr, p.gamma, ws, \
+#define SG_P2(PL) gn_bwd_pass2_kernel<OT, YT, DT, PL><<<task_grid(gn_bwd_pass2_kernel<OT, YT, DT, PL>, tasks, sm), kThreads, sm, st>>>((const YT*)p.y, (const DT*)p.dout, p.mr, p.gamma, ws, \
                                                                                 dy, pstride, dbias, p.C, p.B, p.T, p.Tp, p.G, inv_n)
     if (planes == 1) SG_P2(1); else if (planes == 3) SG_P2(3); else SG_P2(5);
 #undef SG_P2
@@ -1840,8 +1860,11 @@ int sg_pack_input(const void* xv, int x_dtype, void* out, int B, int N, int T, i
     }
     const float* x = (const float*)xv;
     if (Tp == 8 && aligned16(out)) {                         // short rows: one thread per row (static fields)
-        if (is_op16(dtype)) pack_input_short_kernel<__nv_bfloat16><<<short_grid(N, B), kThreads, 0, st>>>(x, (__nv_bfloat16*)out, B, N, T);
-        else                pack_input_short_kernel<float><<<short_grid(N, B), kThreads, 0, st>>>(x, (float*)out, B, N, T);
+        if (is_op16(dtype))
+            pack_input_short_kernel<__nv_bfloat16><<<resident_grid(pack_input_short_kernel<__nv_bfloat16>, short_tiles(N, B)), kThreads, 0, st>>>(
+                x, (__nv_bfloat16*)out, B, N, T);
+        else
+            pack_input_short_kernel<float><<<resident_grid(pack_input_short_kernel<float>, short_tiles(N, B)), kThreads, 0, st>>>(x, (float*)out, B, N, T);
         return check_launch("pack_input");
     }
     bool vec = (T % 4 == 0) && aligned16(x);
@@ -1908,7 +1931,7 @@ int sg_gn_act_fwd(const void* y, int y_dtype, const float* mr, const float* gamm
     SG_REQUIRE(!r16 || is_op16(dtype), "gn_act_fwd: fp32 mode takes an fp32 residual");
     if (Tp == 8 && aligned16(y) && aligned16(res) && aligned16(out_op) && aligned16(out_f32) && (plane_stride & 7) == 0) {
         const int g = mr != nullptr ? G : 1;                 // short rows: one thread per row (static fields)
-        gn_act_fwd_short_kernel<<<short_task_grid(C, B, g), kThreads, 0, st>>>(y, y16, mr, gamma, beta, res, r16, res_scale, act,
+        gn_act_fwd_short_kernel<<<resident_grid(gn_act_fwd_short_kernel, short_task_blocks(C, B, g)), kThreads, 0, st>>>(y, y16, mr, gamma, beta, res, r16, res_scale, act,
                                                                               post_gelu, out_op, is_op16(dtype), planes,
                                                                               plane_stride, out_f32, C, B, T, G);
         return check_launch("gn_act_fwd");
@@ -1959,11 +1982,11 @@ int sg_gn_act_bwd(const void* y, int y_dtype, const float* mr, const float* gamm
         SG_REQUIRE(!r16 || is_op16(dtype), "gn_act_bwd: fp32 mode takes an fp32 residual");
         if (Tp == 8 && aligned16(y) && aligned16(res) && aligned16(dout) && aligned16(dy) && aligned16(dres) &&
             (plane_stride & 7) == 0) {                        // short rows: one thread per row (static fields)
-            const int grid = short_task_grid(C, B, G);
-            gn_bwd_pass1_short_kernel<<<grid, kThreads, 0, st>>>(p, y16, d16, r16, act, post_gelu, dgamma, dbeta, ws, dres,
+            const long long blocks = short_task_blocks(C, B, G);
+            gn_bwd_pass1_short_kernel<<<resident_grid(gn_bwd_pass1_short_kernel, blocks), kThreads, 0, st>>>(p, y16, d16, r16, act, post_gelu, dgamma, dbeta, ws, dres,
                                                                  dres_accumulate);
             const float inv_n = (float)(1.0 / ((double)(C / G) * T));
-            gn_bwd_pass2_short_kernel<<<grid, kThreads, 0, st>>>(y, y16, dout, d16, mr, gamma, ws, dy, is_op16(dtype), planes,
+            gn_bwd_pass2_short_kernel<<<resident_grid(gn_bwd_pass2_short_kernel, blocks), kThreads, 0, st>>>(y, y16, dout, d16, mr, gamma, ws, dy, is_op16(dtype), planes,
                                                                  plane_stride, dbias, C, B, T, G, inv_n);
             return check_launch("gn_act_bwd");
         }
@@ -2010,9 +2033,8 @@ int sg_recon_fwd(const void* y, int y_dtype, const float* mr, const float* gamma
     const bool mse = loss_kind == SG_LOSS_MSE;
     const bool ybf = is_op16(y_dtype);
     if (Tp == 8 && aligned16(y) && (!x16 || aligned16(xv))) {   // short rows: one thread per row (static fields)
-        grid = short_grid(N, B);
 #define SG_SH(YT, XT, MSE, RS, XH) \
-    recon_fwd_short_kernel<YT, XT, MSE, RS, XH><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, (const XT*)xv, x_hat, loss_sums, \
+    recon_fwd_short_kernel<YT, XT, MSE, RS, XH><<<resident_grid(recon_fwd_short_kernel<YT, XT, MSE, RS, XH>, short_tiles(N, B)), kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, (const XT*)xv, x_hat, loss_sums, \
                                                                            (float4*)rowsums, N, B, T, G, loss_kind)
 #define SG_SH2(YT, XT, MSE) do { \
         if (rowsums) { if (x_hat) SG_SH(YT, XT, MSE, true, true); else SG_SH(YT, XT, MSE, true, false); } \
@@ -2085,9 +2107,8 @@ int sg_recon_bwd(const void* y, int y_dtype, const float* mr, const float* gamma
         bool vec = (T % 4 == 0) && aligned16(x);
         const bool mse = loss_kind == SG_LOSS_MSE;
         if (Tp == 8 && aligned16(y) && (!x16 || aligned16(xv)) && aligned16(dy)) {   // short rows: one thread per row
-            grid = short_grid(N, B);
 #define SG_AS(YT, XT, OT, MSE) \
-    recon_bwd_apply_short_kernel<YT, XT, OT, MSE><<<grid, kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, (const XT*)xv, scal, S, (OT*)dy, dbias, \
+    recon_bwd_apply_short_kernel<YT, XT, OT, MSE><<<resident_grid(recon_bwd_apply_short_kernel<YT, XT, OT, MSE>, short_tiles(N, B)), kThreads, 0, st>>>((const YT*)y, mr, gamma, beta, (const XT*)xv, scal, S, (OT*)dy, dbias, \
                                                                              N, B, T, G, loss_kind, (float)inv_n)
             if (x16) {
                 if (mse) SG_AS(bf, bf, bf, true); else SG_AS(bf, bf, bf, false);
