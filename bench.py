@@ -494,8 +494,12 @@ def _main():
     if args.config == 4:
         # static fields: the step streams the 2.29 G parameters (spectral-norm preparation 14 B, forward + dgrad reads of the
         # 16-bit copy 4 B, weight-gradient write 4 B, optimiser 36 B per element) and is bound by HBM, not by the tensor pipe
+        # plus the node-axis streams of the batch, counted on VALID elements only (no layout padding): x 4 B, its 16-bit
+        # operand written once and read by conv0 fprop / wgrad and by both head passes (5 x 2 B), the recon conv's output
+        # written once and read by the statistics, forward and backward passes (4 x 2 B), its gradient written once and read
+        # by dgrad and wgrad (3 x 2 B) = 28 B per (sample, node)
         n_par = sum(p.numel() for p in model.parameters())
-        step_bytes = 58.0 * n_par + B * N * sg.tp_of(T) * (2 + 2 + 2 + 2 + 4)
+        step_bytes = 58.0 * n_par + 28.0 * B * N * T
         gbs = step_bytes / (ms / args.steps / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": "whole step (weight / optimiser streams dominate at T = 1)", "achieved": gbs,
                     "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,

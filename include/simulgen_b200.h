@@ -84,6 +84,9 @@ int sg_sn_weight_grad(const float* dwg, const float* w_orig, const float* u, con
  * R % 8 == 0 and Cin_p % 8 == 0 are required (TMA global strides are multiples of 16 bytes).  */
 int sg_conv_fprop(const void* wg, const void* act, int act_planes, long long act_plane_stride, const float* bias,
                   float* out, int Cin, int Cin_p, int Cout, int k, int R, int accumulate, int dtype, void* stream);
+/* fprop with out [Cout][R] stored in the 16-bit operand format (no accumulate, no statistics; needs sg_conv_out16_ok(Cout)). */
+int sg_conv_fprop16(const void* wg, const void* act, int act_planes, long long act_plane_stride, const float* bias,
+                    void* out, int Cin, int Cin_p, int Cout, int k, int R, int dtype, void* stream);
 /* fprop of a conv that feeds a GroupNorm: also returns stats[B][G][2] = (mean, rstd) of the output (bias included).
  * With the CTA-pair tensor-core kernel the sums are taken in the GEMM epilogue from the fp32 accumulators
  * (rowstat: >= 2*Cout*B floats of scratch) and the separate statistics pass over the output disappears; otherwise
@@ -150,6 +153,26 @@ int sg_recon_bwd(const void* y, int y_dtype, const float* stats, const float* ga
                  int x_dtype, const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext,
                  const float* rowsums, void* dy, float* dgamma, float* dbeta, float* dbias, double* ws,
                  int N, int B, int T, int Tp, int G, int loss_kind, int dtype, void* stream);
+/* ---- static fields (Dim2 = 1, T = 1: SimulGen-VAE.py:279-283 with [P, N, 1] fields; csrc/static_ops.cu) -------------
+ * Compact [C][B] forms (B % 8 == 0) of the two N-channel layers, encoder conv0 (encoder.py:34) and the reconstruction
+ * head (decoder.py:117-121, VAE_network.py:110-111): to sg_conv_fprop / dgrad / wgrad a compact tensor is an activation
+ * with B / 8 samples of 8 valid columns, so the GEMMs do no work on padding.
+ * x fp32 [B][N] -> xc [N][B] (dtype) and, when xt != NULL, the fp32 transpose xt [N][B] (the loss target). */
+int sg_pack_static(const float* x, void* xc, float* xt, int B, int N, int dtype, void* stream);
+/* out[r] = in[r][0] of padded 16-bit rows [R][8];  out[r][0..8) = (in[r], 0 .. 0) fp32 (accumulate: out[r][0] += in[r]). */
+int sg_rows_compact16(const void* in, void* out, long long R, void* stream);
+int sg_rows_expand_f32(const float* in, float* out, long long R, int accumulate, void* stream);
+/* stats[b][g] = (mean, rstd) of GroupNorm(G, N) over y [N][B] (y_dtype); ws: 2 * B * G doubles. */
+int sg_static_stats(const void* y, int y_dtype, double* ws, float* stats, int N, int B, int G, void* stream);
+/* Tanh(GroupNorm(y)) against x [N][B] (x_dtype: fp32 or the operand format): loss_sums[2] as sg_recon_fwd, plus the
+ * reductions of the GroupNorm backward in ws (4 * N + 4 * B * G floats, followed by 2 * B * G + 2 floats of scratch for
+ * sg_static_recon_bwd, which must see the same ws).  y: 16-bit operand format, B <= 2048. */
+int sg_static_recon_fwd(const void* y, int y_dtype, const float* stats, const float* gamma, const float* beta, const void* x,
+                        int x_dtype, double* loss_sums, float* ws, int N, int B, int G, int loss_kind, void* stream);
+/* dy [N][B] (dtype, 16-bit), dgamma, dbeta, dbias [N] for upstream g_loss / g_mse (device scalars, either may be NULL). */
+int sg_static_recon_bwd(const void* y, int y_dtype, const float* stats, const float* gamma, const float* beta, const void* x,
+                        int x_dtype, const float* g_loss, const float* g_mse, float inv_numel, float* ws, void* dy,
+                        float* dgamma, float* dbeta, float* dbias, int N, int B, int G, int loss_kind, int dtype, void* stream);
 /* out[i] = (float)(in[i] * scale), n small. */
 int sg_scale_f64_to_f32(const double* in, float* out, double scale, int n, void* stream);
 

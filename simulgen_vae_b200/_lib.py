@@ -29,6 +29,7 @@ SIGNATURES = {
     "sg_sn_pack_weight": [P, P, P, I, I, I, I, L, L, I, I, P],
     "sg_sn_weight_grad": [P, P, P, P, P, P, P, I, I, I, I, L, L, I, P],
     "sg_conv_fprop": [P, P, I, L, P, P, I, I, I, I, I, I, I, P],
+    "sg_conv_fprop16": [P, P, I, L, P, P, I, I, I, I, I, I, P],
     "sg_conv_fprop_gn": [P, P, I, L, P, P, I, I, I, I, I, I, I, I, I, P, P, P, I, P],
     "sg_conv_dgrad": [P, P, I, L, P, I, I, I, I, I, I, I, I, P],
     "sg_conv_out16_ok": [I],
@@ -37,6 +38,12 @@ SIGNATURES = {
     "sg_gn_stats": [P, P, P, I, I, I, I, I, P],
     "sg_gn_act_fwd": [P, I, P, P, P, P, I, F, I, I, P, I, L, P, I, I, I, I, I, I, P],
     "sg_gn_act_bwd": [P, I, P, P, P, P, I, F, I, I, P, I, P, I, L, P, P, P, P, I, P, I, I, I, I, I, I, P],
+    "sg_pack_static": [P, P, P, I, I, I, P],
+    "sg_rows_compact16": [P, P, L, P],
+    "sg_rows_expand_f32": [P, P, L, I, P],
+    "sg_static_stats": [P, I, P, P, I, I, I, P],
+    "sg_static_recon_fwd": [P, I, P, P, P, P, I, P, P, I, I, I, I, P],
+    "sg_static_recon_bwd": [P, I, P, P, P, P, I, P, P, F, P, P, P, P, P, I, I, I, I, I, P],
     "sg_recon_fwd": [P, I, P, P, P, P, I, P, P, P, I, I, I, I, I, I, P],
     "sg_recon_bwd": [P, I, P, P, P, P, I, P, P, F, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "sg_scale_f64_to_f32": [P, P, D, I, P],

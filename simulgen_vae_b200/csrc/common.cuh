@@ -286,6 +286,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 // ---------------------------------------------------------------------------------------------
+// reconstruction losses (VAE_network.py:71-77): per-element term and derivative wrt d = x_hat - x
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float loss_term(int kind, float d) {
+    float ad = fabsf(d);
+    if (kind == SG_LOSS_MAE) return ad;
+    if (kind == SG_LOSS_SMOOTHL1 || kind == SG_LOSS_HUBER) return ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+    return d * d;
+}
+__device__ __forceinline__ float loss_grad(int kind, float d) {
+    float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    if (kind == SG_LOSS_MAE) return sgn;
+    if (kind == SG_LOSS_SMOOTHL1 || kind == SG_LOSS_HUBER) return fabsf(d) < 1.0f ? d : sgn;
+    return 2.f * d;
+}
+
+// ---------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------
 template <typename T>

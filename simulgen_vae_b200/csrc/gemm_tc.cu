@@ -501,6 +501,17 @@ int sg_conv_fprop(const void* wg, const void* act, int act_planes, long long act
                     as_stream(stream));
 }
 
+// fprop with the output in the 16-bit operand format and no statistics (the compact reconstruction conv of the static
+// configuration: its GroupNorm statistics are per column, csrc/static_ops.cu)
+int sg_conv_fprop16(const void* wg, const void* act, int act_planes, long long act_pstride, const float* bias, void* out,
+                    int Cin, int Cin_p, int Cout, int k, int R, int dtype, void* stream) {
+    SG_CHECK_OP16(dtype);
+    SG_CONV_CHECK("conv_fprop16", act_planes);
+    SG_REQUIRE(is_op16(dtype) && sg_conv_out16_ok(Cout), "conv_fprop16: needs a 16-bit operand mode and a CTA-pair sized layer (Cout=%d)", Cout);
+    return tc_fprop(wg, act, act_planes, act_pstride, bias, out, 1, Cin, Cin_p, Cout, k, R, 0, nullptr, 0, 0, nullptr,
+                    as_stream(stream));
+}
+
 int sg_conv_fprop_gn(const void* wg, const void* act, int act_planes, long long act_pstride, const float* bias, void* out,
                      int out_bf16, int Cin, int Cin_p, int Cout, int k, int B, int T, int Tp, int G, float* stats,
                      double* ws, float* rowstat, int dtype, void* stream) {

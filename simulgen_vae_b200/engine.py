@@ -341,6 +341,36 @@ def loss_target(T: int = 8) -> str:
     return _LOSS_TARGET
 
 
+# Static fields (Dim2 = 1, T = 1).  The CR layout pads every row to 8 elements, i.e. 1 valid column in 8 on the two
+# N-channel layers (encoder conv0, reconstruction conv + head) - the GEMMs would multiply 7 zero columns per sample and the
+# head kernels stream 8x the bytes.  For T = 1 a k = 1 conv is a plain matrix product over the batch, so those two layers
+# run on COMPACT tensors [C][B] instead (csrc/static_ops.cu): to the GEMM entry points a compact tensor is an activation
+# with B / 8 samples of 8 valid columns; small [C <= 1024][B] tensors are converted between the two forms on the way in
+# and out.  Needs B % 8 == 0, B <= 2048 and a 16-bit operand mode; SIMULGEN_B200_STATIC_COMPACT=0 keeps the padded path.
+_STATIC_COMPACT = os.environ.get("SIMULGEN_B200_STATIC_COMPACT", "1") != "0"
+
+
+def static_compact(B: int, T: int) -> bool:
+    return _STATIC_COMPACT and T == 1 and B % 8 == 0 and 8 <= B <= 2048 and _PRECISION != "fp32"
+
+
+class StaticTarget:
+    """What the compact encoder input leaves for the reconstruction loss: xc [N, B] in the operand format and / or
+    xt [N, B] fp32 (the transposed batch)."""
+    __slots__ = ("xc", "xt")
+
+    def __init__(self, xc, xt):
+        self.xc, self.xt = xc, xt
+
+    @staticmethod
+    def operand_policy() -> bool:
+        """loss_target() without its T % 8 condition: the 16-bit operand in fp16 mode, the fp32 values otherwise"""
+        return (_PRECISION == "fp16") if _LOSS_TARGET == "auto" else (_LOSS_TARGET == "operand")
+
+    def pick(self):
+        return self.xc if (self.xt is None or (self.operand_policy() and self.xc is not None)) else self.xt
+
+
 def set_loss_operand(op):
     """Hand the next decoder forward of this thread the packed operand of its target x (VAE.forward does)."""
     _sink.loss_op = op
@@ -378,11 +408,12 @@ class Act:
     """An activation in CR layout.  data: GEMM operand [planes, C, B, Tp] (bf16 / fp32; plane pl holds
     the rows shifted by pl - planes//2, see csrc/common.cuh) or None; f32: fp32 copy [C, B, Tp] or None;
     grad: fp32 gradient buffer [C, B, Tp] filled during backward."""
-    __slots__ = ("data", "f32", "grad", "C", "needs_grad", "name", "grad16")
+    __slots__ = ("data", "f32", "grad", "C", "needs_grad", "name", "grad16", "compact")
 
     def __init__(self, C, data=None, f32=None, needs_grad=True, name=""):
         self.C, self.data, self.f32, self.grad, self.needs_grad, self.name = C, data, f32, None, needs_grad, name
         self.grad16 = False     # True: the only gradient contributor is one dgrad GEMM that can store 16 bits
+        self.compact = False    # True: data is the compact static form [1, C, B / 8, 8] = [C][B] (static_compact())
 
     def center(self):
         return self.data[self.data.shape[0] // 2]
@@ -751,7 +782,18 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
     G = gn.num_groups if gn is not None else 0
     stats = None
     res_t = None
-    if gn is not None:
+    if a_in.compact:
+        # static fields, first encoder conv: the GEMM runs on the compact [N][B] operand (no padding columns), its small
+        # [Cout][B] result is expanded to the padded layout the rest of the network uses
+        assert p.k == 1 and gn is not None and not a_in.needs_grad
+        y16 = False
+        y = ctx.f32(p.Cout, B, Tp)
+        yc = ctx.f32(p.Cout, B // 8, 8)
+        K.conv_fprop(p.wg, a_in.data, conv.bias, yc, p.Cin)
+        K.rows_expand_f32(yc, y)
+        stats = ctx.f32(B, G, 2)
+        K.gn_stats(y, stats, T, G)
+    elif gn is not None:
         stats = ctx.f32(B, G, 2)
         K.conv_fprop_gn(p.wg, a_in.data, conv.bias, y, p.Cin, stats, T, G)   # statistics from the GEMM epilogue
     else:
@@ -799,9 +841,13 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
                 dx, acc_in = ctx.grad_buf(a_in)
                 K.conv_dgrad(p.wg, dy, dx, p.Cin, bool(acc_in))
             if p.w.requires_grad:
-                with ctx.side(dy, a_in.data, flops=2.0 * p.Cin * p.Cout * p.k * B * T):
+                dyw = dy
+                if a_in.compact:                           # [Cout][B] columns of dy against the compact input
+                    dyw = ctx.op(1, p.Cout, B // 8, 8)
+                    K.rows_compact16(dy[0], dyw[0])
+                with ctx.side(dyw, a_in.data, flops=2.0 * p.Cin * p.Cout * p.k * B * T):
                     dwg = ctx.weight_grad_buf(p, p.k, p.Cout, p.Cin_p)
-                    _wgrad(ctx, conv, p, dy, a_in.data, dwg)
+                    _wgrad(ctx, conv, p, dyw, a_in.data, dwg)
         ctx.tape.append(bwd)
     return out
 
@@ -943,12 +989,23 @@ def encoder_graph(ctx: Ctx, enc, x):
         if tuple(packed.shape) != (1, N, B, ctx.Tp) or packed.dtype != ctx.op_dtype:
             raise RuntimeError("simulgen_b200: PackedBatch operand %s / %s does not fit the %s mode (expected %s)"
                                % (tuple(packed.shape), packed.dtype, _PRECISION, (1, N, B, ctx.Tp)))
+    conv0 = enc.encoder_blocks[0].module_list[0]._seq[0]
     if packed is not None and tuple(packed.shape) == (1, N, B, ctx.Tp) and packed.dtype == ctx.op_dtype:
         a = Act(N, data=packed, needs_grad=False, name="x")
+        _sink.last_packed = a.data if ctx.op_dtype != torch.float32 else None
+    elif static_compact(B, T) and _k(conv0) == 1 and not isinstance(x, PackedBatch):
+        # static fields: the compact operand [N][B] (and the transposed fp32 batch when the loss reads fp32)
+        a = Act(N, data=ctx.op(1, N, B // 8, 8), needs_grad=False, name="x")
+        a.compact = True
+        tgt = StaticTarget(a.data.view(N, B), None)
+        if not StaticTarget.operand_policy():
+            tgt.xt = torch.empty(N, B, dtype=torch.float32, device=ctx.dev)
+        K.pack_static(x, a.data, tgt.xt)
+        _sink.last_packed = tgt
     else:
         a = Act(N, data=ctx.op(1, N, B, ctx.Tp), needs_grad=False, name="x")
         K.pack_input(x, a.data, T)
-    _sink.last_packed = a.data if ctx.op_dtype != torch.float32 else None
+        _sink.last_packed = a.data if ctx.op_dtype != torch.float32 else None
     L = len(enc.encoder_blocks)
     xs = []
     h = None
@@ -967,6 +1024,69 @@ def encoder_graph(ctx: Ctx, enc, x):
     last = head(ctx, enc.last_x_linear, h)
     finish_prepare(ctx)
     return last, [e for e in xs[:-1][::-1]]
+
+
+def _static_recon(ctx: Ctx, conv, gn, p, out: Act, x, handoff, lossfun: str, kls):
+    """Reconstruction head of the static configuration (T = 1) on compact tensors [C][B] (decoder.py:117-121 +
+    VAE_network.py:110-111, training only: x_hat is not materialised).  The recon conv reads the [Cin][B] columns of the
+    last decoder activation and writes y [N][B] in the operand format (1/8 of the padded bytes, no GEMM work on padding);
+    GroupNorm statistics, Tanh, both losses and the reductions of the GroupNorm backward are taken in two streaming passes
+    over y, the backward writes dy [N][B] in one more, and the dgrad / wgrad GEMMs run on the compact operands."""
+    B, T, dev = ctx.B, ctx.T, ctx.dev
+    N, G = p.Cout, gn.num_groups
+    B8 = B // 8
+    if isinstance(handoff, StaticTarget) and handoff.pick() is not None and tuple(handoff.pick().shape) == (N, B):
+        target = handoff.pick()
+    else:                                                   # decoder called on its own: transpose the target here
+        xt = torch.empty(N, B, dtype=torch.float32, device=dev)
+        xc = torch.empty(N, B, dtype=ctx.op_dtype, device=dev)
+        K.pack_static(x, xc, xt)
+        target = StaticTarget(xc, xt).pick()
+    hc = ctx.op(1, p.Cin, B8, 8)
+    K.rows_compact16(out.data[0], hc[0])
+    yc = torch.empty(N, B8, 8, dtype=ctx.op_dtype, device=dev)
+    K.conv_fprop16(p.wg, hc, conv.bias, yc, p.Cin)
+    y2 = yc.view(N, B)
+    stats = ctx.f32(B, G, 2)
+    K.static_stats(y2, stats, G)
+    loss_kind = K.LOSS_KINDS.get(lossfun, 0)
+    sums = ctx.f64(2)
+    ws = K.static_recon_ws(N, B, G, dev)
+    K.static_recon_fwd(y2, stats, gn.weight, gn.bias, target, sums, ws, G, loss_kind)
+    inv_numel = 1.0 / float(B * N * T)
+    both = ctx.f32(2)
+    K.scale_f64_to_f32(sums, both, inv_numel)
+    res = dict(x_hat=None, recon=Ext(both[0:1]), mse=Ext(both[1:2]), kls=kls)
+    xhat_ext = Ext(None)
+    res["x_hat_ext"] = xhat_ext
+
+    def recon_bwd(out=out):
+        g_loss, g_mse = res["recon"].grad, res["mse"].grad
+        if xhat_ext.grad is not None:
+            raise RuntimeError("simulgen_b200: a gradient wrt x_hat needs the padded reconstruction head "
+                               "(SIMULGEN_B200_STATIC_COMPACT=0 or materialize x_hat)")
+        if g_loss is None and g_mse is None:
+            return
+        dyc = ctx.op(1, N, B8, 8)
+        dgamma, dbeta, dbias = ctx.vec_grad(gn.weight, N), ctx.vec_grad(gn.bias, N), ctx.vec_grad(conv.bias, N)
+        K.static_recon_bwd(y2, stats, gn.weight, gn.bias, target, g_loss, g_mse, inv_numel, ws, dyc.view(N, B), dgamma, dbeta,
+                           dbias, G, loss_kind)
+        ctx.set_pgrad(gn.weight, dgamma)
+        ctx.set_pgrad(gn.bias, dbeta)
+        ctx.set_pgrad(conv.bias, dbias)
+        dx, acc = ctx.grad_buf(out)
+        if dx.dtype != torch.float32:
+            raise RuntimeError("simulgen_b200: static reconstruction head expects an fp32 gradient buffer")
+        dxc = ctx.f32(p.Cin, B8, 8)
+        K.conv_dgrad(p.wg, dyc, dxc, p.Cin, False)
+        K.rows_expand_f32(dxc, dx, bool(acc))
+        if p.w.requires_grad:
+            with ctx.side(dyc, hc, flops=2.0 * p.Cin * p.Cout * p.k * B * T):
+                dwg = ctx.weight_grad_buf(p, p.k, p.Cout, p.Cin_p)
+                K.conv_wgrad(dyc, hc, dwg, p.Cin)
+                _weight_grad(ctx, conv, p, dwg)
+    ctx.tape.append(recon_bwd)
+    return res
 
 
 def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xhat=True):
@@ -1063,9 +1183,14 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     # bf16 mode: the pre-norm output of the recon conv (the largest tensor of the step, read by the forward and the
     # backward head kernels) is stored as bf16; its GroupNorm statistics are taken from the fp32 accumulators
     y_16 = ctx.op_dtype != torch.float32 and N > 128
-    y = torch.empty(N, B, Tp, dtype=ctx.op_dtype if y_16 else torch.float32, device=ctx.dev)
     # loss target: the packed operand of x (same layout and dtype as y) or the fp32 tensor
     x_op = _take_loss_operand()
+    if static_compact(B, T) and p.k == 1 and x is not None and not isinstance(x, PackedBatch) and ctx.tape is not None \
+            and not (want_xhat and _materialize_xhat()) and K.conv_out16_ok(N) and out.data.shape[0] == 1:
+        return _static_recon(ctx, conv, gn, p, out, x, x_op, lossfun, kls)
+    if isinstance(x_op, StaticTarget):
+        x_op = None
+    y = torch.empty(N, B, Tp, dtype=ctx.op_dtype if y_16 else torch.float32, device=ctx.dev)
     use_op = x is not None and x_op is not None and y_16 and loss_target(T) == "operand" and \
         tuple(x_op.shape) == (1, N, B, Tp) and x_op.dtype == ctx.op_dtype
     if isinstance(x, PackedBatch):

@@ -174,6 +174,17 @@ def conv_fprop(wg, act, bias, out, Cin, accumulate=False):
         _dt(act), _stream()), _nb(wg, act[:k], out))
 
 
+def conv_fprop16(wg, act, bias, out, Cin):
+    """fprop with out [Cout, B, Tp] in the operand dtype (no statistics): conv_out16_ok(Cout) layers only."""
+    k, Cout, Cin_p = wg.shape
+    ap, an, astr = _planes(act)
+    R = act.shape[2] * act.shape[3]
+    assert act.shape[1] == Cin and out.shape[0] == Cout and out.numel() == Cout * R and wg.dtype == act.dtype == out.dtype
+    _timed("fprop", 2.0 * Cin * Cout * k * R, lambda: _call(
+        "sg_conv_fprop16", _p(wg), ap, an, astr, _p(bias), _p(out), Cin, Cin_p, Cout, k, R, _dt(act), _stream()),
+        _nb(wg, act[:k], out))
+
+
 def conv_fprop_gn(wg, act, bias, out, Cin, stats, T, G):
     """Conv + GroupNorm statistics: out [Cout, B, Tp] (fp32, or bf16 for the recon layer in bf16 mode),
     stats fp32 [B, G, 2] <- (mean, rstd).  The statistics come from the GEMM epilogue when the CTA-pair kernel runs."""
@@ -296,6 +307,53 @@ def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy,
           _p(dxhat_ext), _p(_f32(rowsums, "rowsums")), dp, _p(dgamma), _p(dbeta), _p(dbias), _p(ws), N, B, T, Tp, G,
           int(loss_kind), _dt(dy),
           _stream())
+
+
+# ---- static fields (T = 1): compact [C, B] forms of the two N-channel layers (csrc/static_ops.cu) ---------------
+def pack_static(x, xc, xt=None):
+    """x fp32 [B, N, 1] -> xc [N, B] in the operand format (+ xt fp32 [N, B], the loss target); B % 8 == 0."""
+    B, N = x.shape[0], x.shape[1]
+    assert x.dtype == torch.float32 and x.numel() == B * N and xc.numel() == B * N and (xt is None or xt.numel() == B * N)
+    _call("sg_pack_static", _p(x), _p(xc), _p(_f32(xt, "xt")), B, N, _dt(xc), _stream())
+
+
+def rows_compact16(padded, out):
+    """padded [..., 8] 16-bit rows -> out[...] = column 0."""
+    assert padded.dtype in OP16 and out.dtype == padded.dtype and padded.shape[-1] == 8 and padded.numel() == 8 * out.numel()
+    _dt(padded)
+    _call("sg_rows_compact16", _p(padded), _p(out), out.numel(), _stream())
+
+
+def rows_expand_f32(compact, padded, accumulate=False):
+    """compact fp32 [...] -> padded fp32 [..., 8]: column 0 (+)= compact, columns 1..7 = 0 (untouched when accumulating)."""
+    assert padded.shape[-1] == 8 and padded.numel() == 8 * compact.numel()
+    _call("sg_rows_expand_f32", _p(_f32(compact, "compact")), _p(_f32(padded, "padded")), compact.numel(), int(accumulate), _stream())
+
+
+def static_stats(y, stats, G):
+    """y [N, B] (16-bit or fp32) -> stats fp32 [B, G, 2] = (mean, rstd) of GroupNorm(G, N) per sample."""
+    N, B = y.shape
+    ws = torch.empty(2 * B * G, dtype=torch.float64, device=y.device)
+    _call("sg_static_stats", _p(y), _dt(y), _p(ws), _p(_f32(stats, "stats")), N, B, G, _stream())
+
+
+def static_recon_ws(N, B, G, device):
+    return torch.empty(4 * N + 4 * B * G + 2 * B * G + 8, dtype=torch.float32, device=device)
+
+
+def static_recon_fwd(y, stats, gamma, beta, x, loss_sums, ws, G, loss_kind):
+    """y, x [N, B] (y 16-bit; x fp32 or the operand format); ws = static_recon_ws(...), kept for static_recon_bwd."""
+    N, B = y.shape
+    assert tuple(x.shape) == (N, B) and ws.numel() >= 4 * N + 6 * B * G + 2
+    _call("sg_static_recon_fwd", _p(y), _dt(y), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), _dt(x), _p(loss_sums),
+          _p(_f32(ws, "ws")), N, B, G, int(loss_kind), _stream())
+
+
+def static_recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, ws, dy, dgamma, dbeta, dbias, G, loss_kind):
+    N, B = y.shape
+    assert tuple(dy.shape) == (N, B) and dy.dtype == y.dtype
+    _call("sg_static_recon_bwd", _p(y), _dt(y), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), _dt(x), _p(g_loss), _p(g_mse),
+          float(inv_numel), _p(_f32(ws, "ws")), _p(dy), _p(dgamma), _p(dbeta), _p(dbias), N, B, G, int(loss_kind), _dt(dy), _stream())
 
 
 # ---- linear heads -------------------------------------------------------------------------------

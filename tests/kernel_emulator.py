@@ -124,6 +124,12 @@ def conv_fprop(wg, act, bias, out, Cin, accumulate=False, T=None):
         out.copy_(y)
 
 
+def conv_fprop16(wg, act, bias, out, Cin):
+    tmp = torch.empty(out.shape, dtype=torch.float32, device=out.device)
+    conv_fprop(wg, act, bias, tmp, Cin)
+    out.copy_(tmp.to(out.dtype))
+
+
 def conv_fprop_gn(wg, act, bias, out, Cin, stats, T, G):
     tmp = torch.empty(out.shape, dtype=torch.float32, device=out.device)
     conv_fprop(wg, act, bias, tmp, Cin)
@@ -290,6 +296,46 @@ def recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, dxhat_ext, dy,
     dgamma.copy_(gg)
     dbeta.copy_(gb)
     dbias.copy_(gy.sum(dim=(1, 2)))
+
+
+# ---- static fields (T = 1): compact [C, B] forms (csrc/static_ops.cu) -----------------------------------------
+def pack_static(x, xc, xt=None):
+    B, N = x.shape[0], x.shape[1]
+    v = x.reshape(B, N).t()
+    xc.copy_(v.to(xc.dtype).reshape(xc.shape))
+    if xt is not None:
+        xt.copy_(v.reshape(xt.shape))
+
+
+def rows_compact16(padded, out):
+    out.copy_(padded[..., 0].reshape(out.shape))
+
+
+def rows_expand_f32(compact, padded, accumulate=False):
+    c = compact.reshape(padded.shape[:-1])
+    if accumulate:
+        padded[..., 0] += c
+    else:
+        padded.zero_()
+        padded[..., 0] = c
+
+
+def static_stats(y, stats, G):
+    gn_stats(y.float()[:, :, None], stats, 1, G)
+
+
+def static_recon_ws(N, B, G, device):
+    return torch.empty(4 * N + 6 * B * G + 8, dtype=torch.float32, device=device)
+
+
+def static_recon_fwd(y, stats, gamma, beta, x, loss_sums, ws, G, loss_kind):
+    recon_fwd(y.float()[:, :, None], stats, gamma, beta, x.float().t()[:, :, None].contiguous(), None, loss_sums, 1, G, loss_kind)
+
+
+def static_recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, ws, dy, dgamma, dbeta, dbias, G, loss_kind):
+    N, B = y.shape
+    recon_bwd(y.float()[:, :, None], stats, gamma, beta, x.float().t()[:, :, None].contiguous(), g_loss, g_mse, inv_numel, None,
+              dy.view(1, N, B, 1), dgamma, dbeta, dbias, 1, G, loss_kind)
 
 
 # ---- heads --------------------------------------------------------------------------------------
@@ -654,7 +700,7 @@ def sn_prepare(plan, training):
             sn_pack_weight(L["w"], L["sigma"], L["wg"], L["H"], L["Cin"], L["Cin_p"], L["k"], L["so"], L["si"], L["flip"])
 
 
-NAMES = ["counter_add", "conv_out16_ok", "set_sm_limit", "make_peer", "peer_reduce_dot", "OptPlan", "opt_step", "SnPlan", "sn_prepare", "assemble_batch", "minmax_fit", "minmax_transform", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
+NAMES = ["conv_fprop16", "pack_static", "rows_compact16", "rows_expand_f32", "static_stats", "static_recon_ws", "static_recon_fwd", "static_recon_bwd", "counter_add", "conv_out16_ok", "set_sm_limit", "make_peer", "peer_reduce_dot", "OptPlan", "opt_step", "SnPlan", "sn_prepare", "assemble_batch", "minmax_fit", "minmax_transform", "pack_input", "unpack_f32", "axpy", "scale_f64_to_f32", "sn_power_iter", "sn_pack_weight", "sn_weight_grad",
          "conv_fprop", "conv_fprop_gn", "conv_dgrad", "conv_wgrad", "gn_stats", "gn_act_fwd", "gn_act_bwd", "recon_fwd", "recon_bwd",
          "head_fwd", "head_bwd", "latent_fwd", "latent_bwd", "reparam_main_fwd", "reparam_main_bwd", "kl2_reparam_fwd",
          "kl2_reparam_bwd", "philox_normal", "adamw_step"]

@@ -558,3 +558,80 @@ def test_sn_prepare_batched_matches_per_layer_model(training, dtype):
             close(A["v"], Bm["v"], 1e-5, "v %s" % (sp,))
         if A["wg"] is not None:
             close(A["wg"].float(), Bm["wg"].float(), 1e-6 if dtype == torch.float32 else 4e-3, "wg %s" % (sp,))
+
+
+# ---- static fields (T = 1): compact [C][B] forms of the two N-channel layers (csrc/static_ops.cu) ------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("B,N", [(8, 37), (72, 100), (512, 1000)])
+@pytest.mark.parametrize("with_xt", [False, True])
+def test_pack_static(dtype, B, N, with_xt):
+    x = rnd(B, N, 1, seed=1)
+    outs = []
+    for fn in (K.pack_static, emu.pack_static):
+        xc = torch.full((1, N, B // 8, 8), 7.0, device=DEV, dtype=dtype)
+        xt = torch.full((N, B), 7.0, device=DEV) if with_xt else None
+        fn(x, xc, xt)
+        outs.append((xc, xt))
+    assert torch.equal(outs[0][0], outs[1][0])
+    if with_xt:
+        assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][1], x[:, :, 0].t())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_rows_compact_expand(dtype):
+    C, B = 48, 72
+    padded = rnd(C, B, 8, seed=2).to(dtype)
+    c1, c2 = (torch.full((C, B // 8, 8), 9.0, device=DEV, dtype=dtype) for _ in range(2))
+    K.rows_compact16(padded, c1)
+    emu.rows_compact16(padded, c2)
+    assert torch.equal(c1, c2) and torch.equal(c1.view(C, B), padded[:, :, 0])
+    comp = rnd(C, B // 8, 8, seed=3)
+    for acc in (False, True):
+        p1 = cr(C, B, 1, seed=4)
+        p2 = p1.clone()
+        K.rows_expand_f32(comp, p1, acc)
+        emu.rows_expand_f32(comp, p2, acc)
+        assert torch.equal(p1, p2)
+        assert float(p1[:, :, 1:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("B,N,G", [(8, 64, 8), (24, 1000, 8), (256, 1000, 8), (512, 4096, 8), (2048, 96, 4)])
+def test_static_stats(dtype, B, N, G):
+    y = (rnd(N, B, seed=1) * 1.5 + 0.3).to(dtype)
+    s1, s2 = torch.empty(B, G, 2, device=DEV), torch.empty(B, G, 2, device=DEV)
+    K.static_stats(y, s1, G)
+    emu.static_stats(y, s2, G)
+    close(s1, s2, 2e-6, "stats (mean, rstd)")
+
+
+@pytest.mark.parametrize("loss", ["MSE", "MAE", "smoothL1", "Huber"])
+@pytest.mark.parametrize("dtype,x16", [(torch.float16, True), (torch.float16, False), (torch.bfloat16, False)])
+@pytest.mark.parametrize("B,N", [(8, 64), (24, 1000), (256, 1000), (512, 4096)])
+def test_static_recon_fwd_bwd(loss, dtype, x16, B, N):
+    """The compact reconstruction head against the torch model of the padded one (T = 1): loss sums, dy, dgamma, dbeta,
+    dbias.  B = 24: 3 octets per channel (warps straddle channels: per-thread atomics); B = 256 / 512: whole warps."""
+    G = 8
+    kind = K.LOSS_KINDS[loss]
+    y = (rnd(N, B, seed=1) * 2.0).to(dtype)
+    gamma, beta = rnd(N, seed=2) * 0.5 + 1.0, rnd(N, seed=3) * 0.2
+    x = (rnd(N, B, seed=4) * 0.5).clamp(-0.7, 0.7)
+    if x16:
+        x = x.to(dtype)
+    stats = torch.empty(B, G, 2, device=DEV)
+    K.static_stats(y, stats, G)
+    g_loss, g_mse = torch.tensor([1.0e6], device=DEV), torch.tensor([0.5], device=DEV)
+    inv = 1.0 / (B * N)
+    outs = []
+    for mod in (K, emu):
+        sums = torch.empty(2, device=DEV, dtype=torch.float64)
+        ws = mod.static_recon_ws(N, B, G, DEV)
+        mod.static_recon_fwd(y, stats, gamma, beta, x, sums, ws, G, kind)
+        dy = torch.full((N, B), 9.0, device=DEV, dtype=dtype)
+        dg, db, dbi = (torch.full((N,), 9.0, device=DEV) for _ in range(3))
+        mod.static_recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv, ws, dy, dg, db, dbi, G, kind)
+        outs.append((sums, dy.float(), dg, db, dbi))
+    close(outs[0][0], outs[1][0], 1e-5, "loss sums")
+    tol16 = 6e-4 if dtype == torch.float16 else 5e-3          # dy is stored in the 16-bit operand format
+    for a, b, nm in zip(outs[0][1:], outs[1][1:], ("dy", "dgamma", "dbeta", "dbias")):
+        close(a, b, tol16 if nm in ("dy", "dbias") else 5e-5, nm)

@@ -271,6 +271,53 @@ def test_cuda_graph_step_equals_eager_step():
             assert rel_l2(w1[k], w0[k]) < 2e-2, (k, rel_l2(w1[k], w0[k]))
 
 
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_static_compact_path_parity(precision, monkeypatch):
+    """Static fields (T = 1, BASELINE.json configs[3]): the compact [C][B] path of the two N-channel layers
+    (engine.static_compact; what Trainer.step runs - x_hat is not materialised) against the fp32 oracle and against the
+    padded path on the same weights, input and eps."""
+    from simulgen_vae_b200 import engine
+    cfg = CONFIG_CASES["config4_static_T1"]
+    sg.set_precision(precision)
+    B = cfg["batch"]
+    x = O.synthetic_field(B, cfg["num_node"], cfg["num_time"], seed=3).to(DEV)
+    g = torch.Generator().manual_seed(1)
+    eps = [torch.randn(s, generator=g).to(DEV) for s in O.eps_shapes(cfg, B)]
+    runs = {}
+    sd = None
+    from simulgen_vae_b200 import kernels as K
+    for compact in (True, False):
+        monkeypatch.setattr(engine, "_STATIC_COMPACT", compact)
+        m = build_engine_vae(cfg, sd, seed=5)
+        if sd is None:
+            sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        m.train(True)
+        n0 = K.LAUNCHES
+        engine.set_materialize_xhat(False)
+        try:
+            with sg.fixed_eps(eps):
+                _, rl, kls, mse = m(x)
+            O.total_loss(rl, kls, 1e6, 1e-4).backward()
+        finally:
+            engine.set_materialize_xhat(True)
+        runs[compact] = (rl.detach(), mse.detach(), [k.detach() for k in kls],
+                         {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None})
+    p, acts, oxh, orl, okls, omse = _oracle_on_gpu(cfg, sd, x, eps)
+    rl, mse, kls, grads = runs[True]
+    tol = 1e-2 if precision == "fp16" else 5e-2
+    assert rel_l2(rl, orl) < tol and rel_l2(mse, omse) < tol
+    for a, b in zip(kls, okls):
+        assert rel_l2(a, b) < tol
+    worst = max((rel_l2(gv, p[n].grad), n) for n, gv in grads.items())
+    assert worst[0] < tol, worst
+    # compact vs padded: the same arithmetic up to summation order and one 16-bit rounding of y / dy
+    rl2, mse2, kls2, grads2 = runs[False]
+    assert set(grads) == set(grads2)
+    assert rel_l2(rl, rl2) < 2e-3 and rel_l2(mse, mse2) < 2e-3
+    worst2 = max((rel_l2(gv, grads2[n]), n) for n, gv in grads.items())
+    assert worst2[0] < (5e-3 if precision == "fp16" else 3e-2), worst2
+
+
 FULL_SIZE = {
     # BASELINE.json configs[2], [3], [4] at their REAL node / time counts (batch reduced: parity does not depend on it)
     "config3_large_95008": dict(latent_dim=32, hierarchical_dim=8, enc=[1024, 512, 256, 128], num_node=95008, num_time=200,

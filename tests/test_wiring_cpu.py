@@ -123,6 +123,60 @@ def test_16bit_intermediates_wiring_against_oracle(precision, store16, monkeypat
     assert worst < tol, worst
 
 
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("compact", [True, False])
+def test_static_fields_compact_wiring_against_oracle(precision, compact, monkeypatch):
+    """Static fields (T = 1): host wiring of the compact [C][B] path of the two N-channel layers (engine.static_compact:
+    pack_static -> compact conv0 GEMM -> expand; compact recon conv -> static head kernels -> compact dgrad / wgrad ->
+    expand) against the fp32 oracle, and that a batch which is not a multiple of 8 keeps the padded path."""
+    from simulgen_vae_b200 import engine
+    from oracle import vae_oracle as O
+    B = 8 if compact else 6
+    cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[64, 32], num_node=136, num_time=1, small=True, lossfun="Huber", batch=B)
+    sg.set_precision(precision)
+    calls = {"fwd": 0, "pack": 0, "targets": []}
+    try:
+        with emu.install():
+            from simulgen_vae_b200 import kernels as K
+            orig_f, orig_p = K.static_recon_fwd, K.pack_static
+
+            def sf(y, stats, gamma, beta, x, *a, **k):
+                calls["fwd"] += 1
+                calls["targets"].append((x.dtype, tuple(x.shape), tuple(y.shape)))
+                return orig_f(y, stats, gamma, beta, x, *a, **k)
+
+            def ps(*a, **k):
+                calls["pack"] += 1
+                return orig_p(*a, **k)
+            K.static_recon_fwd, K.pack_static = sf, ps
+            torch.manual_seed(11)
+            m = build_engine_vae(cfg, None)
+            m.train(True)
+            sd = {k: v.clone() for k, v in m.state_dict().items()}
+            g = torch.Generator().manual_seed(12)
+            x = torch.rand(B, 136, 1, generator=g) * 1.4 - 0.7
+            eps = [torch.randn(s, generator=g) for s in O.eps_shapes(cfg, B)]
+            engine.set_materialize_xhat(False)              # training: the compact head does not write x_hat
+            with sg.fixed_eps(eps):
+                x_hat, rl, kls, mse = m(x)
+            (rl * 1e3 + sum(kls) * 1e-2).backward()
+    finally:
+        engine.set_materialize_xhat(True)
+        sg.set_precision(sg.DEFAULT_PRECISION)
+    if compact:
+        tdt = torch.float16 if precision == "fp16" else torch.float32       # the loss-target policy of engine.loss_target
+        assert calls["fwd"] == 1 and calls["pack"] == 1 and calls["targets"] == [(tdt, (136, B), (136, B))], calls
+    else:
+        assert calls["fwd"] == 0 and calls["pack"] == 0, calls
+    p = O.params_from_state_dict(sd)
+    ox, orl, okls, omse = O.vae_forward(p, x, eps, cfg["latent_dim"], cfg["lossfun"], training=True)
+    (orl * 1e3 + sum(okls) * 1e-2).backward()
+    tol = {"fp16": 1e-2, "bf16": 8e-2}[precision]
+    assert rel_l2(rl, orl) < tol and rel_l2(mse, omse) < tol
+    worst = max(rel_l2(q.grad, p[n].grad) for n, q in m.named_parameters() if q.grad is not None)
+    assert worst < tol, worst
+
+
 def test_packed_batch_equals_fp32_batch_in_fp16_mode():
     """engine.PackedBatch (the batch as the packed fp16 operand only - what the resident-dataset loader emits) gives the
     step of the fp32 tensor bit for bit: the encoder consumes the same operand and the loss reads the same target."""
