@@ -271,13 +271,18 @@ def test_cuda_graph_step_equals_eager_step():
             assert rel_l2(w1[k], w0[k]) < 2e-2, (k, rel_l2(w1[k], w0[k]))
 
 
-@pytest.mark.parametrize("precision", ["fp16", "bf16"])
-def test_static_compact_path_parity(precision, monkeypatch):
+@pytest.mark.parametrize("precision,size", [("fp16", "small"), ("bf16", "small"), ("fp16", "full")])
+def test_static_compact_path_parity(precision, size, monkeypatch):
     """Static fields (T = 1, BASELINE.json configs[3]): the compact [C][B] path of the two N-channel layers
     (engine.static_compact; what Trainer.step runs - x_hat is not materialised) against the fp32 oracle and against the
     padded path on the same weights, input and eps."""
     from simulgen_vae_b200 import engine
     cfg = CONFIG_CASES["config4_static_T1"]
+    if size == "full":                                      # 10^6 nodes, 2.29 G parameters: the real configs[3] model
+        if torch.cuda.mem_get_info()[0] < 120e9:
+            pytest.skip("needs a 180 GB device")
+        cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[1024, 512, 256, 128], num_node=1000000, num_time=1, small=True,
+                   batch=8, lossfun="MSE")
     sg.set_precision(precision)
     B = cfg["batch"]
     x = O.synthetic_field(B, cfg["num_node"], cfg["num_time"], seed=3).to(DEV)
@@ -286,7 +291,7 @@ def test_static_compact_path_parity(precision, monkeypatch):
     runs = {}
     sd = None
     from simulgen_vae_b200 import kernels as K
-    for compact in (True, False):
+    for compact in ((True, False) if size == "small" else (True,)):
         monkeypatch.setattr(engine, "_STATIC_COMPACT", compact)
         m = build_engine_vae(cfg, sd, seed=5)
         if sd is None:
@@ -302,6 +307,8 @@ def test_static_compact_path_parity(precision, monkeypatch):
             engine.set_materialize_xhat(True)
         runs[compact] = (rl.detach(), mse.detach(), [k.detach() for k in kls],
                          {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None})
+        del m
+        torch.cuda.empty_cache()
     p, acts, oxh, orl, okls, omse = _oracle_on_gpu(cfg, sd, x, eps)
     rl, mse, kls, grads = runs[True]
     tol = 1e-2 if precision == "fp16" else 5e-2
@@ -310,6 +317,8 @@ def test_static_compact_path_parity(precision, monkeypatch):
         assert rel_l2(a, b) < tol
     worst = max((rel_l2(gv, p[n].grad), n) for n, gv in grads.items())
     assert worst[0] < tol, worst
+    if size != "small":
+        return
     # compact vs padded: the same arithmetic up to summation order and one 16-bit rounding of y / dy
     rl2, mse2, kls2, grads2 = runs[False]
     assert set(grads) == set(grads2)
