@@ -443,6 +443,7 @@ class Ctx:
         self.dev = device
         self.tape = [] if record else None
         self.op_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(_PRECISION, torch.float32)
+        _sink.centre_only = bool(_STATIC_CENTRE and T == 1 and self.op_dtype != torch.float32)    # see _k()
         self.pgrads = {}
         self.capture = capture
         self.sink = get_grad_sink() if record else None
@@ -766,8 +767,24 @@ def _weight_grad(ctx: Ctx, mod, p: _Prep, dwg):
 # ------------------------------------------------------------------------------------------------
 # fused blocks
 # ------------------------------------------------------------------------------------------------
+# Static fields (T = 1): with "same" padding a k-tap conv only ever sees its CENTRE tap (the other taps multiply the zero
+# padding), so in the 16-bit modes every conv runs as a k = 1 GEMM on the centre slice of its weight copy, activations and
+# gradients carry one operand plane instead of k, and the other taps of the weight gradient are exactly zero.
+# SIMULGEN_B200_STATIC_CENTRE=0 keeps the k-tap GEMMs.
+_STATIC_CENTRE = os.environ.get("SIMULGEN_B200_STATIC_CENTRE", "1") != "0"
+
+
+def _set_centre_only(ctx):
+    _sink.centre_only = bool(_STATIC_CENTRE and ctx.T == 1 and ctx.op_dtype != torch.float32)
+
+
+def _centre_only() -> bool:
+    return getattr(_sink, "centre_only", False)
+
+
 def _k(conv) -> int:
-    return int(conv.kernel_size[0])
+    """operand planes a consumer conv needs from its producer"""
+    return 1 if _centre_only() else int(conv.kernel_size[0])
 
 
 def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.0, post_gelu=False,
@@ -782,6 +799,11 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
     G = gn.num_groups if gn is not None else 0
     stats = None
     res_t = None
+    centre = _centre_only() and p.k > 1
+    wg = p.wg[p.k // 2:p.k // 2 + 1] if centre else p.wg                       # [1][Cout][Cin_p]: the centre tap
+    a_data = a_in.data
+    if centre and a_data.shape[0] > 1:
+        a_data = a_data[a_data.shape[0] // 2:a_data.shape[0] // 2 + 1]
     if a_in.compact:
         # static fields, first encoder conv: the GEMM runs on the compact [N][B] operand (no padding columns), its small
         # [Cout][B] result is expanded to the padded layout the rest of the network uses
@@ -795,9 +817,9 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
         K.gn_stats(y, stats, T, G)
     elif gn is not None:
         stats = ctx.f32(B, G, 2)
-        K.conv_fprop_gn(p.wg, a_in.data, conv.bias, y, p.Cin, stats, T, G)   # statistics from the GEMM epilogue
+        K.conv_fprop_gn(wg, a_data, conv.bias, y, p.Cin, stats, T, G)         # statistics from the GEMM epilogue
     else:
-        K.conv_fprop(p.wg, a_in.data, conv.bias, y, p.Cin)
+        K.conv_fprop(wg, a_data, conv.bias, y, p.Cin)
     if plain:
         out = Act(p.Cout, data=None, f32=y, name=name)
     else:
@@ -816,7 +838,7 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
             if g is None:
                 return
             out.grad = None
-            dy = ctx.op(p.k, p.Cout, B, Tp)          # k planes: dgrad reads dy shifted by the taps
+            dy = ctx.op(1 if centre else p.k, p.Cout, B, Tp)          # k planes: dgrad reads dy shifted by the taps
             dgamma = ctx.vec_grad(gn.weight, p.Cout) if gn is not None else None
             dbeta = ctx.vec_grad(gn.bias, p.Cout) if gn is not None else None
             dbias = ctx.vec_grad(conv.bias, p.Cout)
@@ -839,15 +861,20 @@ def conv_block(ctx: Ctx, conv, gn, a_in: Act, act, res: Act = None, res_scale=1.
             if a_in.needs_grad:
                 ctx.join_side()
                 dx, acc_in = ctx.grad_buf(a_in)
-                K.conv_dgrad(p.wg, dy, dx, p.Cin, bool(acc_in))
+                K.conv_dgrad(wg, dy, dx, p.Cin, bool(acc_in))
             if p.w.requires_grad:
                 dyw = dy
                 if a_in.compact:                           # [Cout][B] columns of dy against the compact input
                     dyw = ctx.op(1, p.Cout, B // 8, 8)
                     K.rows_compact16(dy[0], dyw[0])
-                with ctx.side(dyw, a_in.data, flops=2.0 * p.Cin * p.Cout * p.k * B * T):
+                with ctx.side(dyw, a_data, flops=2.0 * p.Cin * p.Cout * (1 if centre else p.k) * B * T):
                     dwg = ctx.weight_grad_buf(p, p.k, p.Cout, p.Cin_p)
-                    _wgrad(ctx, conv, p, dyw, a_in.data, dwg)
+                    if centre:                             # T = 1: only the centre tap has a gradient
+                        dwg.zero_()
+                        K.conv_wgrad(dyw, a_data, dwg[p.k // 2:p.k // 2 + 1], p.Cin)
+                        _weight_grad(ctx, conv, p, dwg)
+                    else:
+                        _wgrad(ctx, conv, p, dyw, a_data, dwg)
         ctx.tape.append(bwd)
     return out
 
@@ -982,6 +1009,7 @@ def encoder_graph(ctx: Ctx, enc, x):
     """encoder.py:146-167.  Returns (last Ext [B, 2*z_dim], [xs Ext ...] in the reference's reversed
     order without the deepest level)."""
     B, N, T = x.shape
+    _set_centre_only(ctx)
     prepare_all(ctx, enc)
     packed = _take_packed_input()
     if isinstance(x, PackedBatch):
@@ -1094,6 +1122,7 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     xs: list of Ext (xs[i] feeds level i); entries beyond the used levels are ignored, None entries skipped.
     Returns dict(x_hat, recon Ext|None, mse Ext|None, kls [Ext])."""
     B, T, Tp = ctx.B, ctx.T, ctx.Tp
+    _set_centre_only(ctx)
     nb = len(dec.decoder_residual_blocks)
     kls = []
     freeze_level = _take_freeze_level()
