@@ -279,6 +279,7 @@ def test_static_compact_path_parity(precision, size, monkeypatch):
     from simulgen_vae_b200 import engine
     cfg = CONFIG_CASES["config4_static_T1"]
     if size == "full":                                      # 10^6 nodes, 2.29 G parameters: the real configs[3] model
+        torch.cuda.empty_cache()
         if torch.cuda.mem_get_info()[0] < 120e9:
             pytest.skip("needs a 180 GB device")
         cfg = dict(latent_dim=32, hierarchical_dim=8, enc=[1024, 512, 256, 128], num_node=1000000, num_time=1, small=True,
