@@ -166,9 +166,11 @@ int sg_rows_expand_f32(const float* in, float* out, long long R, int accumulate,
 int sg_static_stats(const void* y, int y_dtype, double* ws, float* stats, int N, int B, int G, void* stream);
 /* Tanh(GroupNorm(y)) against x [N][B] (x_dtype: fp32 or the operand format): loss_sums[2] as sg_recon_fwd, plus the
  * reductions of the GroupNorm backward in ws (4 * N + 4 * B * G floats, followed by 2 * B * G + 2 floats of scratch for
- * sg_static_recon_bwd, which must see the same ws).  y: 16-bit operand format, B <= 2048. */
+ * sg_static_recon_bwd, which must see the same ws).  y: 16-bit operand format, B <= 2048.
+ * xhat_t (optional): x_hat transposed, fp32 [N][B] (x_hat[b][n][0] = xhat_t[n][b]). */
 int sg_static_recon_fwd(const void* y, int y_dtype, const float* stats, const float* gamma, const float* beta, const void* x,
-                        int x_dtype, double* loss_sums, float* ws, int N, int B, int G, int loss_kind, void* stream);
+                        int x_dtype, float* xhat_t, double* loss_sums, float* ws, int N, int B, int G, int loss_kind,
+                        void* stream);
 /* dy [N][B] (dtype, 16-bit), dgamma, dbeta, dbias [N] for upstream g_loss / g_mse (device scalars, either may be NULL). */
 int sg_static_recon_bwd(const void* y, int y_dtype, const float* stats, const float* gamma, const float* beta, const void* x,
                         int x_dtype, const float* g_loss, const float* g_mse, float inv_numel, float* ws, void* dy,

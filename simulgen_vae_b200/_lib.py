@@ -42,7 +42,7 @@ SIGNATURES = {
     "sg_rows_compact16": [P, P, L, P],
     "sg_rows_expand_f32": [P, P, L, I, P],
     "sg_static_stats": [P, I, P, P, I, I, I, P],
-    "sg_static_recon_fwd": [P, I, P, P, P, P, I, P, P, I, I, I, I, P],
+    "sg_static_recon_fwd": [P, I, P, P, P, P, I, P, P, P, I, I, I, I, P],
     "sg_static_recon_bwd": [P, I, P, P, P, P, I, P, P, F, P, P, P, P, P, I, I, I, I, I, P],
     "sg_recon_fwd": [P, I, P, P, P, P, I, P, P, P, I, I, I, I, I, I, P],
     "sg_recon_bwd": [P, I, P, P, P, P, I, P, P, F, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P],

@@ -11,7 +11,7 @@
 //   sg_rows_expand_f32        [R] -> padded [R][8] (zeros in columns 1..7), fp32, optionally accumulating onto column 0
 //   sg_static_stats           GroupNorm(G, N) statistics per (sample, group) of y [N][B]
 //   sg_static_recon_fwd       Tanh(GroupNorm(y)) vs x: loss sums + the reductions of the GroupNorm backward
-//                             (per channel and per (sample, group)): NO per-row side buffer, nothing else is written
+//                             (per channel and per (sample, group)): NO per-row side buffer; optionally x_hat, transposed
 //   sg_static_recon_bwd       dy [N][B] (operand format), dgamma, dbeta, dbias
 // Thread mapping of the head kernels: a thread owns one OCTET of samples (8 consecutive b: one 16-byte load of y) and walks
 // channels of ONE group, so the (mean, rstd) and the per-(sample, group) accumulators of its 8 samples stay in registers;
@@ -158,8 +158,9 @@ __global__ void static_finalize_kernel(const double* __restrict__ sums, float* _
 template <typename YT, typename XT, bool MSE>
 __global__ void __launch_bounds__(kStThreads)
 static_recon_fwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, const XT* __restrict__ x, double* __restrict__ loss_sums,
-                        float* __restrict__ chan4, float* __restrict__ s4, int N, int B, int G, int loss_kind) {
+                        const float* __restrict__ beta, const XT* __restrict__ x, float* __restrict__ xh,
+                        double* __restrict__ loss_sums, float* __restrict__ chan4, float* __restrict__ s4, int N, int B,
+                        int G, int loss_kind) {
     extern __shared__ float st_sh[];
     __shared__ double shm[2][32];
     constexpr int NS = MSE ? 2 : 4;
@@ -183,10 +184,12 @@ static_recon_fwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, 
             const F8 yv = load8(y + off), xv = load8(x + off);
             const float gam = __ldg(gamma + c), bet = __ldg(beta + c);
             float cs[4] = {0.f, 0.f, 0.f, 0.f};
+            F8 hv;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float a = gam * rstd[i];
                 const float h = tanh_fast(fmaf(yv.v[i], a, bet - mean[i] * a));
+                hv.v[i] = h;
                 const float d = h - xv.v[i];
                 l1 = fmaf(d, d, l1);
                 if (!MSE) l0 += loss_term(loss_kind, d);
@@ -206,6 +209,7 @@ static_recon_fwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, 
                 }
             }
             if (MSE) { cs[0] = cs[2]; cs[1] = cs[3]; }
+            if (xh != nullptr) store8(xh + off, hv);         // x_hat, transposed: [N][B]
 #pragma unroll
             for (int k = 0; k < 4; ++k) st_channel_add(chan4 + (size_t)c * 4 + k, cs[k], m);
         }
@@ -345,11 +349,13 @@ int sg_static_stats(const void* y, int y_dtype, double* ws, float* mr, int N, in
 
 // ws: 4 * N + 4 * B * G floats (chan4, s4), zeroed here; kept for sg_static_recon_bwd
 int sg_static_recon_fwd(const void* y, int y_dtype, const float* mr, const float* gamma, const float* beta, const void* x,
-                        int x_dtype, double* loss_sums, float* ws, int N, int B, int G, int loss_kind, void* stream) {
+                        int x_dtype, float* xhat_t, double* loss_sums, float* ws, int N, int B, int G, int loss_kind,
+                        void* stream) {
     SG_CHECK_OP16(y_dtype);
     SG_CHECK_OP16(x_dtype);
     SG_STATIC_SHAPE("static_recon_fwd");
-    SG_REQUIRE(is_op16(y_dtype) && st_aligned16(x) && st_aligned16(ws), "static_recon_fwd: y must be in the 16-bit operand format");
+    SG_REQUIRE(is_op16(y_dtype) && st_aligned16(x) && st_aligned16(ws) && st_aligned16(xhat_t),
+               "static_recon_fwd: y must be in the 16-bit operand format");
     cudaStream_t st = as_stream(stream);
     float* chan4 = ws;
     float* s4 = ws + (size_t)4 * N;
@@ -358,7 +364,7 @@ int sg_static_recon_fwd(const void* y, int y_dtype, const float* mr, const float
     const bool mse = loss_kind == SG_LOSS_MSE;
     const dim3 grid = st_grid(N, G);
 #define SG_SF(XT, MSE) static_recon_fwd_kernel<h16, XT, MSE><<<grid, kStThreads, sizeof(float) * kStThreads * 8 * (MSE ? 2 : 4), st>>>( \
-        (const h16*)y, mr, gamma, beta, (const XT*)x, loss_sums, chan4, s4, N, B, G, loss_kind)
+        (const h16*)y, mr, gamma, beta, (const XT*)x, xhat_t, loss_sums, chan4, s4, N, B, G, loss_kind)
     if (is_op16(x_dtype)) { if (mse) SG_SF(h16, true); else SG_SF(h16, false); }
     else                  { if (mse) SG_SF(float, true); else SG_SF(float, false); }
 #undef SG_SF

@@ -1054,9 +1054,10 @@ def encoder_graph(ctx: Ctx, enc, x):
     return last, [e for e in xs[:-1][::-1]]
 
 
-def _static_recon(ctx: Ctx, conv, gn, p, out: Act, x, handoff, lossfun: str, kls):
+def _static_recon(ctx: Ctx, conv, gn, p, out: Act, x, handoff, lossfun: str, kls, want_xhat=False):
     """Reconstruction head of the static configuration (T = 1) on compact tensors [C][B] (decoder.py:117-121 +
-    VAE_network.py:110-111, training only: x_hat is not materialised).  The recon conv reads the [Cin][B] columns of the
+    VAE_network.py:110-111; training - a gradient wrt x_hat itself is not supported here).  x_hat, when wanted, is written
+    transposed ([N][B], coalesced) and returned as a [B, N, 1] VIEW of that buffer.  The recon conv reads the [Cin][B] columns of the
     last decoder activation and writes y [N][B] in the operand format (1/8 of the padded bytes, no GEMM work on padding);
     GroupNorm statistics, Tanh, both losses and the reductions of the GroupNorm backward are taken in two streaming passes
     over y, the backward writes dy [N][B] in one more, and the dgrad / wgrad GEMMs run on the compact operands."""
@@ -1080,19 +1081,21 @@ def _static_recon(ctx: Ctx, conv, gn, p, out: Act, x, handoff, lossfun: str, kls
     loss_kind = K.LOSS_KINDS.get(lossfun, 0)
     sums = ctx.f64(2)
     ws = K.static_recon_ws(N, B, G, dev)
-    K.static_recon_fwd(y2, stats, gn.weight, gn.bias, target, sums, ws, G, loss_kind)
+    xhat_t = torch.empty(N, B, dtype=torch.float32, device=dev) if want_xhat else None
+    K.static_recon_fwd(y2, stats, gn.weight, gn.bias, target, sums, ws, G, loss_kind, xhat_t)
     inv_numel = 1.0 / float(B * N * T)
     both = ctx.f32(2)
     K.scale_f64_to_f32(sums, both, inv_numel)
-    res = dict(x_hat=None, recon=Ext(both[0:1]), mse=Ext(both[1:2]), kls=kls)
-    xhat_ext = Ext(None)
+    x_hat = xhat_t.t().unsqueeze(-1) if want_xhat else None
+    res = dict(x_hat=x_hat, recon=Ext(both[0:1]), mse=Ext(both[1:2]), kls=kls)
+    xhat_ext = Ext(x_hat)
     res["x_hat_ext"] = xhat_ext
 
     def recon_bwd(out=out):
         g_loss, g_mse = res["recon"].grad, res["mse"].grad
         if xhat_ext.grad is not None:
-            raise RuntimeError("simulgen_b200: a gradient wrt x_hat needs the padded reconstruction head "
-                               "(SIMULGEN_B200_STATIC_COMPACT=0 or materialize x_hat)")
+            raise RuntimeError("simulgen_b200: a gradient wrt x_hat itself needs the padded reconstruction head "
+                               "(set SIMULGEN_B200_STATIC_COMPACT=0)")
         if g_loss is None and g_mse is None:
             return
         dyc = ctx.op(1, N, B8, 8)
@@ -1215,8 +1218,8 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     # loss target: the packed operand of x (same layout and dtype as y) or the fp32 tensor
     x_op = _take_loss_operand()
     if static_compact(B, T) and p.k == 1 and x is not None and not isinstance(x, PackedBatch) and ctx.tape is not None \
-            and not (want_xhat and _materialize_xhat()) and K.conv_out16_ok(N) and out.data.shape[0] == 1:
-        return _static_recon(ctx, conv, gn, p, out, x, x_op, lossfun, kls)
+            and K.conv_out16_ok(N) and out.data.shape[0] == 1:
+        return _static_recon(ctx, conv, gn, p, out, x, x_op, lossfun, kls, want_xhat and _materialize_xhat())
     if isinstance(x_op, StaticTarget):
         x_op = None
     y = torch.empty(N, B, Tp, dtype=ctx.op_dtype if y_16 else torch.float32, device=ctx.dev)

@@ -341,12 +341,13 @@ def static_recon_ws(N, B, G, device):
     return torch.empty(4 * N + 4 * B * G + 2 * B * G + 8, dtype=torch.float32, device=device)
 
 
-def static_recon_fwd(y, stats, gamma, beta, x, loss_sums, ws, G, loss_kind):
-    """y, x [N, B] (y 16-bit; x fp32 or the operand format); ws = static_recon_ws(...), kept for static_recon_bwd."""
+def static_recon_fwd(y, stats, gamma, beta, x, loss_sums, ws, G, loss_kind, xhat_t=None):
+    """y, x [N, B] (y 16-bit; x fp32 or the operand format); ws = static_recon_ws(...), kept for static_recon_bwd;
+    xhat_t: optional fp32 [N, B] <- x_hat transposed."""
     N, B = y.shape
-    assert tuple(x.shape) == (N, B) and ws.numel() >= 4 * N + 6 * B * G + 2
-    _call("sg_static_recon_fwd", _p(y), _dt(y), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), _dt(x), _p(loss_sums),
-          _p(_f32(ws, "ws")), N, B, G, int(loss_kind), _stream())
+    assert tuple(x.shape) == (N, B) and ws.numel() >= 4 * N + 6 * B * G + 2 and (xhat_t is None or tuple(xhat_t.shape) == (N, B))
+    _call("sg_static_recon_fwd", _p(y), _dt(y), _p(_f32(stats, "stats")), _p(gamma), _p(beta), _p(x), _dt(x),
+          _p(_f32(xhat_t, "xhat_t")), _p(loss_sums), _p(_f32(ws, "ws")), N, B, G, int(loss_kind), _stream())
 
 
 def static_recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, ws, dy, dgamma, dbeta, dbias, G, loss_kind):

@@ -328,8 +328,12 @@ def static_recon_ws(N, B, G, device):
     return torch.empty(4 * N + 6 * B * G + 8, dtype=torch.float32, device=device)
 
 
-def static_recon_fwd(y, stats, gamma, beta, x, loss_sums, ws, G, loss_kind):
-    recon_fwd(y.float()[:, :, None], stats, gamma, beta, x.float().t()[:, :, None].contiguous(), None, loss_sums, 1, G, loss_kind)
+def static_recon_fwd(y, stats, gamma, beta, x, loss_sums, ws, G, loss_kind, xhat_t=None):
+    N, B = y.shape
+    xh = torch.empty(B, N, 1, dtype=torch.float32, device=y.device) if xhat_t is not None else None
+    recon_fwd(y.float()[:, :, None], stats, gamma, beta, x.float().t()[:, :, None].contiguous(), xh, loss_sums, 1, G, loss_kind)
+    if xhat_t is not None:
+        xhat_t.copy_(xh[:, :, 0].t())
 
 
 def static_recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv_numel, ws, dy, dgamma, dbeta, dbias, G, loss_kind):

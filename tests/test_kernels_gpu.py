@@ -626,12 +626,14 @@ def test_static_recon_fwd_bwd(loss, dtype, x16, B, N):
     for mod in (K, emu):
         sums = torch.empty(2, device=DEV, dtype=torch.float64)
         ws = mod.static_recon_ws(N, B, G, DEV)
-        mod.static_recon_fwd(y, stats, gamma, beta, x, sums, ws, G, kind)
+        xh = torch.full((N, B), 9.0, device=DEV)
+        mod.static_recon_fwd(y, stats, gamma, beta, x, sums, ws, G, kind, xh)
         dy = torch.full((N, B), 9.0, device=DEV, dtype=dtype)
         dg, db, dbi = (torch.full((N,), 9.0, device=DEV) for _ in range(3))
         mod.static_recon_bwd(y, stats, gamma, beta, x, g_loss, g_mse, inv, ws, dy, dg, db, dbi, G, kind)
-        outs.append((sums, dy.float(), dg, db, dbi))
+        outs.append((sums, dy.float(), dg, db, dbi, xh))
     close(outs[0][0], outs[1][0], 1e-5, "loss sums")
+    close(outs[0][5], outs[1][5], 3e-6, "x_hat (transposed)")
     tol16 = 6e-4 if dtype == torch.float16 else 5e-3          # dy is stored in the 16-bit operand format
-    for a, b, nm in zip(outs[0][1:], outs[1][1:], ("dy", "dgamma", "dbeta", "dbias")):
+    for a, b, nm in zip(outs[0][1:5], outs[1][1:5], ("dy", "dgamma", "dbeta", "dbias")):
         close(a, b, tol16 if nm in ("dy", "dbias") else 5e-5, nm)

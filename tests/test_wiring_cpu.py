@@ -156,12 +156,10 @@ def test_static_fields_compact_wiring_against_oracle(precision, compact, monkeyp
             g = torch.Generator().manual_seed(12)
             x = torch.rand(B, 136, 1, generator=g) * 1.4 - 0.7
             eps = [torch.randn(s, generator=g) for s in O.eps_shapes(cfg, B)]
-            engine.set_materialize_xhat(False)              # training: the compact head does not write x_hat
             with sg.fixed_eps(eps):
-                x_hat, rl, kls, mse = m(x)
+                x_hat, rl, kls, mse = m(x)                  # x_hat: a [B, N, 1] view of the head's transposed output
             (rl * 1e3 + sum(kls) * 1e-2).backward()
     finally:
-        engine.set_materialize_xhat(True)
         sg.set_precision(sg.DEFAULT_PRECISION)
     if compact:
         tdt = torch.float16 if precision == "fp16" else torch.float32       # the loss-target policy of engine.loss_target
@@ -173,6 +171,7 @@ def test_static_fields_compact_wiring_against_oracle(precision, compact, monkeyp
     (orl * 1e3 + sum(okls) * 1e-2).backward()
     tol = {"fp16": 1e-2, "bf16": 8e-2}[precision]
     assert rel_l2(rl, orl) < tol and rel_l2(mse, omse) < tol
+    assert tuple(x_hat.shape) == (B, 136, 1) and rel_l2(x_hat, ox) < tol
     worst = max(rel_l2(q.grad, p[n].grad) for n, q in m.named_parameters() if q.grad is not None)
     assert worst < tol, worst
 
