@@ -1056,7 +1056,7 @@ def encoder_graph(ctx: Ctx, enc, x):
 
 def _static_recon(ctx: Ctx, conv, gn, p, out: Act, x, handoff, lossfun: str, kls, want_xhat=False):
     """Reconstruction head of the static configuration (T = 1) on compact tensors [C][B] (decoder.py:117-121 +
-    VAE_network.py:110-111; training - a gradient wrt x_hat itself is not supported here).  x_hat, when wanted, is written
+    VAE_network.py:110-111; with or without a backward tape - a gradient wrt x_hat itself is not supported here).  x_hat, when wanted, is written
     transposed ([N][B], coalesced) and returned as a [B, N, 1] VIEW of that buffer.  The recon conv reads the [Cin][B] columns of the
     last decoder activation and writes y [N][B] in the operand format (1/8 of the padded bytes, no GEMM work on padding);
     GroupNorm statistics, Tanh, both losses and the reductions of the GroupNorm backward are taken in two streaming passes
@@ -1116,7 +1116,8 @@ def _static_recon(ctx: Ctx, conv, gn, p, out: Act, x, handoff, lossfun: str, kls
                 dwg = ctx.weight_grad_buf(p, p.k, p.Cout, p.Cin_p)
                 K.conv_wgrad(dyc, hc, dwg, p.Cin)
                 _weight_grad(ctx, conv, p, dwg)
-    ctx.tape.append(recon_bwd)
+    if ctx.tape is not None:
+        ctx.tape.append(recon_bwd)
     return res
 
 
@@ -1217,7 +1218,7 @@ def decoder_graph(ctx: Ctx, dec, z: Ext, xs, x, lossfun: str, mode: str, want_xh
     y_16 = ctx.op_dtype != torch.float32 and N > 128
     # loss target: the packed operand of x (same layout and dtype as y) or the fp32 tensor
     x_op = _take_loss_operand()
-    if static_compact(B, T) and p.k == 1 and x is not None and not isinstance(x, PackedBatch) and ctx.tape is not None \
+    if static_compact(B, T) and p.k == 1 and x is not None and not isinstance(x, PackedBatch) \
             and K.conv_out16_ok(N) and out.data.shape[0] == 1:
         return _static_recon(ctx, conv, gn, p, out, x, x_op, lossfun, kls, want_xhat and _materialize_xhat())
     if isinstance(x_op, StaticTarget):

@@ -24,13 +24,17 @@ def _purge_modules():
         del sys.modules[k]
 
 
-def _data():
+# static fields (Dim2 = 1): batch 8 so that the 16-bit modes take the compact [C][B] path of the two N-channel layers
+CFG_STATIC = dict(latent_dim=32, hierarchical_dim=8, enc=[32, 16, 8], num_node=200, num_time=1)
+
+
+def _data(cfg=CFG, samples=16):
     g = torch.Generator().manual_seed(0)
-    return torch.rand(16, CFG["num_node"], CFG["num_time"], generator=g) * 1.4 - 0.7
+    return torch.rand(samples, cfg["num_node"], cfg["num_time"], generator=g) * 1.4 - 0.7
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
-def test_unmodified_reference_train_runs_on_real_kernels(precision, tmp_path, monkeypatch):
+@pytest.mark.parametrize("precision,shape", [("fp32", "T20"), ("fp16", "T20"), ("fp16", "static")])
+def test_unmodified_reference_train_runs_on_real_kernels(precision, shape, tmp_path, monkeypatch):
     """reference train(): model.apply(initialize_weights_He / add_sn), AdamW over model.parameters(), loss.backward()
     through the engine's autograd Functions, the per-parameter grad-norm loop, validation under no_grad, torch.save of the
     state dict and of the whole module - on cuda:0.  In fp32 mode the loss curve must equal the engine's own train() driver
@@ -39,9 +43,22 @@ def test_unmodified_reference_train_runs_on_real_kernels(precision, tmp_path, mo
     monkeypatch.chdir(tmp_path)
     os.makedirs("checkpoints")
     os.makedirs("model_save")
-    data = _data().cuda()
-    args = (5, 4, None, None, 1e-3, CFG["enc"], CFG["enc"][::-1], CFG["num_node"], CFG["latent_dim"], CFG["hierarchical_dim"],
-            CFG["num_time"], 1000000, "MSE", True, True)
+    CFG = CFG_STATIC if shape == "static" else globals()["CFG"]
+    bs, n_train, n_all = (8, 16, 24) if shape == "static" else (4, 12, 16)
+    data = _data(CFG, n_all).cuda()
+    # alpha: the reference's train() has no loss scaling, so in fp16 mode alpha / numel must keep the gradients of the
+    # 16-bit operands in range; the static toy field has 1600 elements per batch -> alpha = 1e4
+    alpha = 10000 if shape == "static" else 1000000
+    args = (5, bs, None, None, 1e-3, CFG["enc"], CFG["enc"][::-1], CFG["num_node"], CFG["latent_dim"], CFG["hierarchical_dim"],
+            CFG["num_time"], alpha, "MSE", True, True)
+    seen = {"static_fwd": 0}
+    from simulgen_vae_b200 import kernels as K
+    orig_sf = K.static_recon_fwd
+
+    def counting_sf(*a, **k):
+        seen["static_fwd"] += 1
+        return orig_sf(*a, **k)
+    monkeypatch.setattr(K, "static_recon_fwd", counting_sf)
 
     def run(use_engine_driver):
         _purge_modules()
@@ -56,8 +73,8 @@ def test_unmodified_reference_train_runs_on_real_kernels(precision, tmp_path, mo
             torch.manual_seed(3)
             engine._rng_state().seed = None
             a = list(args)
-            a[2] = torch.utils.data.DataLoader(data[:12], batch_size=4, shuffle=False)
-            a[3] = torch.utils.data.DataLoader(data[12:], batch_size=4, shuffle=False)
+            a[2] = torch.utils.data.DataLoader(data[:n_train], batch_size=bs, shuffle=False)
+            a[3] = torch.utils.data.DataLoader(data[n_train:], batch_size=bs, shuffle=False)
             curves = train_mod.train(*a)
             sd = torch.load("checkpoints/SimulGen-VAE.pth", weights_only=False)
             whole = torch.load("model_save/SimulGen-VAE", weights_only=False)
@@ -73,12 +90,14 @@ def test_unmodified_reference_train_runs_on_real_kernels(precision, tmp_path, mo
     try:
         ref_curves, ref_sd = run(False)
         assert all(np.isfinite(c).all() for c in ref_curves)
-        ref_model = ref_import.build_reference_vae(dict(CFG, batch=4, small=True, lossfun="MSE"))
+        ref_model = ref_import.build_reference_vae(dict(CFG, batch=bs, small=True, lossfun="MSE"))
         assert list(ref_sd.keys()) == list(ref_model.state_dict().keys())
         ref_model.load_state_dict({k: v.cpu() for k, v in ref_sd.items()})       # engine checkpoint loads into the reference
         eng_curves, eng_sd = run(True)
     finally:
         sg.set_precision(sg.DEFAULT_PRECISION)
+    # static fields in a 16-bit mode: both drivers went through the compact head (train + validation forwards)
+    assert (seen["static_fwd"] > 0) == (shape == "static"), seen
     tol = 2e-4 if precision == "fp32" else 2e-2
     for name, a, b in zip(("loss", "recon", "kl", "val_loss"), ref_curves, eng_curves):
         assert a.shape == b.shape == (5,)

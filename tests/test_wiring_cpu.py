@@ -159,6 +159,16 @@ def test_static_fields_compact_wiring_against_oracle(precision, compact, monkeyp
             with sg.fixed_eps(eps):
                 x_hat, rl, kls, mse = m(x)                  # x_hat: a [B, N, 1] view of the head's transposed output
             (rl * 1e3 + sum(kls) * 1e-2).backward()
+            if compact:                                     # validation forward (no tape): compact head == padded head
+                m.eval()
+                with torch.no_grad(), sg.fixed_eps(eps):
+                    xe, rle, _, msee = m(x)
+                monkeypatch.setattr(engine, "_STATIC_COMPACT", False)
+                with torch.no_grad(), sg.fixed_eps(eps):
+                    xp, rlp, _, msep = m(x)
+                assert calls["fwd"] == 2 and calls["pack"] == 2
+                assert rel_l2(xe, xp) < 5e-3 and rel_l2(rle, rlp) < 5e-3 and rel_l2(msee, msep) < 5e-3
+                calls["fwd"], calls["pack"], calls["targets"] = 1, 1, calls["targets"][:1]
     finally:
         sg.set_precision(sg.DEFAULT_PRECISION)
     if compact:
