@@ -1021,7 +1021,7 @@ def encoder_graph(ctx: Ctx, enc, x):
     if packed is not None and tuple(packed.shape) == (1, N, B, ctx.Tp) and packed.dtype == ctx.op_dtype:
         a = Act(N, data=packed, needs_grad=False, name="x")
         _sink.last_packed = a.data if ctx.op_dtype != torch.float32 else None
-    elif static_compact(B, T) and _k(conv0) == 1 and not isinstance(x, PackedBatch):
+    elif static_compact(B, T) and int(conv0.kernel_size[0]) == 1 and not isinstance(x, PackedBatch):
         # static fields: the compact operand [N][B] (and the transposed fp32 batch when the loss reads fp32)
         a = Act(N, data=ctx.op(1, N, B // 8, 8), needs_grad=False, name="x")
         a.compact = True
