@@ -171,6 +171,10 @@ CONFIG_CASES = {
     # configs[3]: static fields, Dim2 = 1 (every k-tap conv degenerates to its centre tap), large batch
     "config4_static_T1": dict(latent_dim=32, hierarchical_dim=8, enc=[256, 128, 64, 32], num_node=4096, num_time=1,
                               small=True, batch=64, lossfun="MSE"),
+    # not a BASELINE config: few time steps (rows padded to 8 elements, k-tap convs with real neighbours): the
+    # one-thread-per-row kernels with shifted operand planes
+    "short_rows_T5": dict(latent_dim=32, hierarchical_dim=8, enc=[256, 128, 64, 32], num_node=1024, num_time=5,
+                          small=True, batch=40, lossfun="smoothL1"),
     # configs[4]: num_var = 4 folded into the node axis, T = 400 (rows longer than 256 elements), Huber loss
     "config5_multivar_T400": dict(latent_dim=32, hierarchical_dim=8, enc=[256, 128, 64, 32], num_node=4 * 512, num_time=400,
                                   small=True, batch=2, lossfun="Huber"),
