@@ -153,7 +153,8 @@ int sg_recon_bwd(const void* y, int y_dtype, const float* stats, const float* ga
                  int x_dtype, const float* g_loss, const float* g_mse, float inv_numel, const float* dxhat_ext,
                  const float* rowsums, void* dy, float* dgamma, float* dbeta, float* dbias, double* ws,
                  int N, int B, int T, int Tp, int G, int loss_kind, int dtype, void* stream);
-/* ---- static fields (Dim2 = 1, T = 1: SimulGen-VAE.py:279-283 with [P, N, 1] fields; csrc/static_ops.cu) -------------
+/* ---- static fields (preset Dim2 = 1 -> num_time = 1, modules/utils.py:306; SimulGen-VAE.py:279-283 with [P, N, 1] fields;
+ * csrc/static_ops.cu) -------------
  * Compact [C][B] forms (B % 8 == 0) of the two N-channel layers, encoder conv0 (encoder.py:34) and the reconstruction
  * head (decoder.py:117-121, VAE_network.py:110-111): to sg_conv_fprop / dgrad / wgrad a compact tensor is an activation
  * with B / 8 samples of 8 valid columns, so the GEMMs do no work on padding.

@@ -1,4 +1,5 @@
-// Static fields (Dim2 = 1, i.e. T = 1: SimulGen-VAE.py:279-283 feeds [P, N, 1] fields through the same Conv1d model) -
+// Static fields (preset Dim2 = 1 -> num_time = 1, modules/utils.py:306: SimulGen-VAE.py:279-283 feeds [P, N, 1] fields
+// through the same Conv1d model) -
 // compact forms of the two N-channel layers.
 //
 // The engine's CR layout pads every row to 8 elements, so at T = 1 the activations of the first encoder conv (N -> C,
