@@ -21,6 +21,9 @@ precision = sys.argv[1] if len(sys.argv) > 1 else "fp32"
 sg.set_precision(precision)
 cfg = dict(bench.HEADLINE, num_node=2048, enc=[256, 128, 64, 32])
 Bl = 2
+if os.environ.get("DP_CHECK_STATIC", "0") != "0":         # static fields (T = 1): per-rank batch 8 -> the compact [C][B] path
+    cfg["num_time"] = 1
+    Bl = 8
 B = Bl * world
 STEPS = int(os.environ.get("DP_CHECK_STEPS", "3"))       # >= 3: the pipelined exchange starts with the second step
 data = bench.synthetic_batches(STEPS, B, cfg["num_node"], cfg["num_time"], dev, seed=7)      # same seed: same data on all ranks
@@ -47,8 +50,15 @@ if rank == 0:
     run(m_1, data, 0, 1)
     worst, per = 0.0, []
     sd1, sd2 = m_1.state_dict(), m_dp.state_dict()
+    static = cfg["num_time"] == 1
     for k in sd1:
         a, b = sd1[k].double(), sd2[k].double()
+        if static and precision != "fp32" and k.endswith("weight_orig") and a.dim() == 3 and a.shape[2] > 1:
+            # T = 1: only the centre tap of a k-tap conv has a data gradient; the other taps receive the spectral-norm
+            # correction -<G, Wn> u v^T / sigma alone, whose scalar <G, Wn> is a heavily cancelling sum - with 16-bit
+            # gradients its sign is rounding noise, and AdamW turns either sign into a full +-lr step.  Any two summation
+            # orders (ranks, batch splits) disagree there; the taps that see data are compared.
+            a, b = a[:, :, a.shape[2] // 2], b[:, :, b.shape[2] // 2]
         e = float((a - b).norm() / (b.norm() + 1e-30))
         per.append((e, k))
         # bf16 mode: the summation order of the batch decides a few 1-ulp roundings of dy, and AdamW's m/sqrt(v)
