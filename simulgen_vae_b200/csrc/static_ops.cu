@@ -27,18 +27,34 @@ typedef __nv_bfloat16 h16;
 static bool st_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---- layout ------------------------------------------------------------------------------------------------------
+// tile: 64 nodes x 64 samples.  Reads walk a sample's 64 contiguous nodes (256 bytes per warp and row: 128-byte pieces ran
+// at 2.7 TB/s, profiles/r2_ncu_config4_static_summary.txt), writes walk a node's 64 contiguous samples.
 template <typename OT>
 __global__ void __launch_bounds__(kStThreads)
 pack_static_kernel(const float* __restrict__ x, OT* __restrict__ xc, float* __restrict__ xt, int B, int N) {
-    __shared__ float tile[64][33];
+    __shared__ float tile[64][65];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * 32, b0 = blockIdx.y * 64;
+    const int n0 = blockIdx.x * 64, b0 = blockIdx.y * 64;
+    const bool pairs = (N & 1) == 0;                         // 8-byte aligned pairs of nodes
     for (int i = warp; i < 64; i += kStThreads / 32) {
-        const int b = b0 + i, n = n0 + lane;
-        tile[i][lane] = (b < B && n < N) ? __ldcs(x + (size_t)b * N + n) : 0.f;
+        const int b = b0 + i, n = n0 + 2 * lane;
+        float v0 = 0.f, v1 = 0.f;
+        if (b < B) {
+            const float* src = x + (size_t)b * N + n;
+            if (pairs && n + 1 < N) {
+                const float2 v = __ldcs(reinterpret_cast<const float2*>(src));
+                v0 = v.x;
+                v1 = v.y;
+            } else {
+                if (n < N) v0 = __ldcs(src);
+                if (n + 1 < N) v1 = __ldcs(src + 1);
+            }
+        }
+        tile[i][2 * lane] = v0;
+        tile[i][2 * lane + 1] = v1;
     }
     __syncthreads();
-    for (int j = warp; j < 32; j += kStThreads / 32) {
+    for (int j = warp; j < 64; j += kStThreads / 32) {
         const int n = n0 + j, b = b0 + 2 * lane;             // B % 8 == 0: pairs never straddle the edge
         if (n < N && b < B) {
             const float v0 = tile[2 * lane][j], v1 = tile[2 * lane + 1][j];
@@ -314,7 +330,7 @@ extern "C" {
 int sg_pack_static(const float* x, void* xc, float* xt, int B, int N, int dtype, void* stream) {
     SG_CHECK_OP16(dtype);
     SG_REQUIRE(B > 0 && B % 8 == 0 && N > 0, "pack_static: the batch must be a multiple of 8 (B=%d)", B);
-    dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(B, 64));
+    dim3 grid((unsigned)cdiv(N, 64), (unsigned)cdiv(B, 64));
     cudaStream_t st = as_stream(stream);
     if (is_op16(dtype)) pack_static_kernel<h16><<<grid, kStThreads, 0, st>>>(x, (h16*)xc, xt, B, N);
     else pack_static_kernel<float><<<grid, kStThreads, 0, st>>>(x, (float*)xc, xt, B, N);
