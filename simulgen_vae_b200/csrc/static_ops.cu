@@ -173,7 +173,7 @@ __global__ void static_finalize_kernel(const double* __restrict__ sums, float* _
 // forward: loss sums, chan4[n] = sum_b (aL, bL, aM, bM), s4[b][g] = sum_{n in g} gamma_n (aL, bL, aM, bM) with
 //   aM = 2 d (1 - h^2), bM = aM * xhat  (the MSE gradient terms), aL / bL the same with loss'(d) (== the MSE ones for MSE)
 template <typename YT, typename XT, bool MSE>
-__global__ void __launch_bounds__(kStThreads)
+__global__ void __launch_bounds__(kStThreads)           // 80 registers, 3 blocks per SM; forcing 4 spills and is slower (0.86 vs 0.83 ms)
 static_recon_fwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                         const float* __restrict__ beta, const XT* __restrict__ x, float* __restrict__ xh,
                         double* __restrict__ loss_sums, float* __restrict__ chan4, float* __restrict__ s4, int N, int B,
@@ -271,7 +271,7 @@ __global__ void static_recon_combine_kernel(const float* __restrict__ g_loss, co
 }
 
 template <typename YT, typename XT, bool MSE>
-__global__ void __launch_bounds__(kStThreads)
+__global__ void __launch_bounds__(kStThreads, 4)
 static_recon_bwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gamma,
                         const float* __restrict__ beta, const XT* __restrict__ x, const float* __restrict__ scal,
                         const float* __restrict__ S2, h16* __restrict__ dy, float* __restrict__ dbias, int N, int B, int G,
@@ -313,9 +313,13 @@ static_recon_bwd_kernel(const YT* __restrict__ y, const float* __restrict__ mr, 
     }
 }
 
-static dim3 st_grid(int N, int G) {
+// blocks split the channels of a group evenly: launch what is resident (one wave), per kernel instantiation
+template <typename KernelT>
+static dim3 st_grid(KernelT kernel, size_t smem, int N, int G) {
     const int Cg = N / G;
-    int per_group = (148 * 6 + G - 1) / G;                   // ~6 blocks per SM over all groups
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kStThreads, smem) != cudaSuccess || nb < 1) nb = 2;
+    int per_group = 148 * nb / G;
     if (per_group > Cg) per_group = Cg;
     if (per_group < 1) per_group = 1;
     return dim3((unsigned)per_group, (unsigned)G);
@@ -358,8 +362,8 @@ int sg_static_stats(const void* y, int y_dtype, double* ws, float* mr, int N, in
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(ws, 0, sizeof(double) * 2 * B * G, st);
     const size_t sm = sizeof(float) * kStThreads * 16;
-    if (is_op16(y_dtype)) static_stats_kernel<h16><<<st_grid(N, G), kStThreads, sm, st>>>((const h16*)y, ws, N, B, G);
-    else static_stats_kernel<float><<<st_grid(N, G), kStThreads, sm, st>>>((const float*)y, ws, N, B, G);
+    if (is_op16(y_dtype)) static_stats_kernel<h16><<<st_grid(static_stats_kernel<h16>, sm, N, G), kStThreads, sm, st>>>((const h16*)y, ws, N, B, G);
+    else static_stats_kernel<float><<<st_grid(static_stats_kernel<float>, sm, N, G), kStThreads, sm, st>>>((const float*)y, ws, N, B, G);
     static_finalize_kernel<<<(unsigned)cdiv(B * G, 256), 256, 0, st>>>(ws, mr, B * G, 1.0 / (double)(N / G));
     return check_launch("static_stats");
 }
@@ -379,8 +383,8 @@ int sg_static_recon_fwd(const void* y, int y_dtype, const float* mr, const float
     cudaMemsetAsync(ws, 0, sizeof(float) * 4 * ((size_t)N + (size_t)B * G), st);
     cudaMemsetAsync(loss_sums, 0, sizeof(double) * 2, st);
     const bool mse = loss_kind == SG_LOSS_MSE;
-    const dim3 grid = st_grid(N, G);
-#define SG_SF(XT, MSE) static_recon_fwd_kernel<h16, XT, MSE><<<grid, kStThreads, sizeof(float) * kStThreads * 8 * (MSE ? 2 : 4), st>>>( \
+#define SG_SF(XT, MSE) static_recon_fwd_kernel<h16, XT, MSE><<<st_grid(static_recon_fwd_kernel<h16, XT, MSE>, sizeof(float) * kStThreads * 8 * (MSE ? 2 : 4), N, G), \
+                                                              kStThreads, sizeof(float) * kStThreads * 8 * (MSE ? 2 : 4), st>>>( \
         (const h16*)y, mr, gamma, beta, (const XT*)x, xhat_t, loss_sums, chan4, s4, N, B, G, loss_kind)
     if (is_op16(x_dtype)) { if (mse) SG_SF(h16, true); else SG_SF(h16, false); }
     else                  { if (mse) SG_SF(float, true); else SG_SF(float, false); }
@@ -409,8 +413,7 @@ int sg_static_recon_bwd(const void* y, int y_dtype, const float* mr, const float
     cudaMemsetAsync(dbias, 0, sizeof(float) * N, st);
     const bool mse = loss_kind == SG_LOSS_MSE;
     const float inv_n = (float)(1.0 / (double)(N / G));
-    const dim3 grid = st_grid(N, G);
-#define SG_SB(XT, MSE) static_recon_bwd_kernel<h16, XT, MSE><<<grid, kStThreads, 0, st>>>( \
+#define SG_SB(XT, MSE) static_recon_bwd_kernel<h16, XT, MSE><<<st_grid(static_recon_bwd_kernel<h16, XT, MSE>, 0, N, G), kStThreads, 0, st>>>( \
         (const h16*)y, mr, gamma, beta, (const XT*)x, scal, S2, (h16*)dy, dbias, N, B, G, loss_kind, inv_n)
     if (is_op16(x_dtype)) { if (mse) SG_SB(h16, true); else SG_SB(h16, false); }
     else                  { if (mse) SG_SB(float, true); else SG_SB(float, false); }
