@@ -114,11 +114,14 @@ assemble_batch_short_kernel(const float* __restrict__ data, const int* __restric
     __shared__ float xs[kAugShortTile][kAugShortPitch];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t sample_elems = (size_t)N * T;
+    // without an operand to write there is no transposition: the tile widens to 1024 channels (4 KB runs per sample at T = 1
+    // instead of 128-byte pieces) and shared memory is not used
+    const int tile_n = op != nullptr ? kAugShortTile : 1024;
     const int tiles_b = (B + kAugShortTile - 1) / kAugShortTile;
-    const long long tiles = (long long)((N + kAugShortTile - 1) / kAugShortTile) * tiles_b;
+    const long long tiles = (long long)((N + tile_n - 1) / tile_n) * tiles_b;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int n0 = (int)(tile / tiles_b) * kAugShortTile, b0 = (int)(tile % tiles_b) * kAugShortTile;
-        const int run = min(kAugShortTile, N - n0) * T;
+        const int n0 = (int)(tile / tiles_b) * tile_n, b0 = (int)(tile % tiles_b) * kAugShortTile;
+        const int run = min(tile_n, N - n0) * T;
         __syncthreads();
         for (int bl = warp; bl < kAugShortTile && b0 + bl < B; bl += kAugWarps) {
             const int b = b0 + bl;
@@ -146,7 +149,7 @@ assemble_batch_short_kernel(const float* __restrict__ data, const int* __restric
                 v = __fmul_rn(v, sc);
                 if (src2 != nullptr) v = __fadd_rn(__fmul_rn(lam, v), __fmul_rn(om, __ldcs(src2 + i)));
                 if (dst != nullptr) dst[i] = v;
-                xs[bl][i] = v;
+                if (op != nullptr) xs[bl][i] = v;
             }
         }
         if (op == nullptr) continue;
@@ -186,7 +189,7 @@ extern "C" int sg_assemble_batch(const float* data, int P, const int* ids, const
     int grid = (int)(blocks < 148LL * blocks_per_sm ? blocks : 148LL * blocks_per_sm);
     cudaStream_t st = as_stream(stream);
     if (Tp == 8 && (reinterpret_cast<uintptr_t>(operand) & 15) == 0) {
-        const long long tiles = cdiv((long long)N, kAugShortTile) * cdiv((long long)B, kAugShortTile);
+        const long long tiles = cdiv((long long)N, operand != nullptr ? kAugShortTile : 1024) * cdiv((long long)B, kAugShortTile);
         int nb = 0;                                           // the grid is persistent: launch exactly what is resident
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, assemble_batch_short_kernel, kAugWarps * 32, 0) != cudaSuccess || nb < 1) nb = 1;
         const long long cap = 148LL * (blocks_per_sm < nb ? blocks_per_sm : nb);
