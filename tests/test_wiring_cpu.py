@@ -186,6 +186,30 @@ def test_static_fields_compact_wiring_against_oracle(precision, compact, monkeyp
     assert worst < tol, worst
 
 
+def test_static_compact_gating_and_target_policy(monkeypatch):
+    """engine.static_compact: T = 1, batch a multiple of 8 and <= 2048, 16-bit modes only; StaticTarget.pick follows the
+    loss-target policy (fp16: the 16-bit operand, bf16 / 'input': the fp32 transpose)."""
+    from simulgen_vae_b200 import engine
+    try:
+        sg.set_precision("fp16")
+        assert engine.static_compact(8, 1) and engine.static_compact(512, 1) and engine.static_compact(2048, 1)
+        assert not engine.static_compact(6, 1) and not engine.static_compact(4096, 1) and not engine.static_compact(8, 2)
+        xc, xt = torch.zeros(4, 8, dtype=torch.float16), torch.zeros(4, 8)
+        assert engine.StaticTarget(xc, xt).pick() is xc and engine.StaticTarget(xc, None).pick() is xc
+        monkeypatch.setattr(engine, "_LOSS_TARGET", "input")
+        assert engine.StaticTarget(xc, xt).pick() is xt
+        monkeypatch.setattr(engine, "_LOSS_TARGET", "auto")
+        sg.set_precision("bf16")
+        assert engine.static_compact(8, 1) and engine.StaticTarget(xc, xt).pick() is xt
+        sg.set_precision("fp32")
+        assert not engine.static_compact(8, 1)
+        sg.set_precision("fp16")
+        monkeypatch.setattr(engine, "_STATIC_COMPACT", False)
+        assert not engine.static_compact(8, 1)
+    finally:
+        sg.set_precision(sg.DEFAULT_PRECISION)
+
+
 def test_packed_batch_equals_fp32_batch_in_fp16_mode():
     """engine.PackedBatch (the batch as the packed fp16 operand only - what the resident-dataset loader emits) gives the
     step of the fp32 tensor bit for bit: the encoder consumes the same operand and the loss reads the same target."""
