@@ -163,14 +163,14 @@ def test_shard_item_partitions_every_tensor():
             assert covered == n
 
 
-@pytest.mark.parametrize("W", [2, 3, 8])
+@pytest.mark.parametrize("W", [2, 3, 4, 8])
 @pytest.mark.parametrize("with_scaler,split", [(False, False), (True, False), (True, True)])
 def test_peer_optimizer_virtual_ranks_cpu(W, with_scaler, split):
     _run(emu, "cpu", W, with_scaler, split)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("W", [2, 3, 8])
+@pytest.mark.parametrize("W", [2, 3, 4, 8])
 @pytest.mark.parametrize("with_scaler,split", [(False, False), (True, False), (True, True), (False, True)])
 def test_peer_optimizer_virtual_ranks_gpu(W, with_scaler, split):
     from simulgen_vae_b200 import kernels as K
